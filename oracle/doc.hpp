@@ -850,7 +850,7 @@ struct Doc : ArenaCtx {
         frontiers.push_back(change.id_last());
         vv[change.id.peer] = change.ctr_end();
         store_insert(store, std::move(change), true, from_local ? 1000LL * 1000 : 0);
-        state_valid = false;
+        if (!from_local) state_valid = false;  // local ops keep `state` in sync themselves
     }
 
     // ---------------- import (encoding.rs:232-270, fast_snapshot.rs:270-288)
