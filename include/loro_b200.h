@@ -1,0 +1,129 @@
+/* loro_b200 -- C ABI of the B200-native batched CRDT merge engine.
+ *
+ * Drop-in boundary for ONE hot path of loro-dev/loro: batched `LoroDoc::import` of FastUpdates blobs
+ * into fresh documents -> (decode, causal scan, eg-walker merge) -> deep JSON state / import status.
+ * The reference has no C FFI for this path; every entry point cites the Rust interface it
+ * replaces (paths relative to /root/reference):
+ *
+ *   lb_import_batch          crates/loro/src/lib.rs:639  LoroDoc::import(&self, &[u8]) -> Result<ImportStatus>
+ *                            crates/loro/src/lib.rs:425  LoroDoc::import_batch (one fresh doc per blob here)
+ *                            crates/loro-internal/src/loro.rs:562-643 (header/checksum/mode checks first)
+ *   lb_doc_status            crates/loro-internal/src/encoding.rs:226-230 ImportStatus{success,pending}
+ *                            crates/loro-common/src/error.rs:8-105 (LoroError variants -> lb_doc_code)
+ *   lb_doc_json              crates/loro/src/lib.rs:866  LoroDoc::get_deep_value() (serde_json text, keys sorted)
+ *   lb_doc_vv                crates/loro/src/lib.rs:816  LoroDoc::oplog_vv()
+ *   lb_batch_counters        crates/loro-internal/src/loro.rs:1458 len_ops / len_changes (summed over the batch)
+ *
+ * Conventions (mirroring the reference): input buffers are borrowed for the duration of the call only;
+ * outputs are owned by the batch handle until lb_batch_free; a bad blob never aborts the batch -- it yields a
+ * per-document error code; checksum / mode are verified before anything else; missing dependencies are not
+ * errors (they are reported as `pending`).  Thread-safe for distinct handles.
+ *
+ * All compute runs in hand-written CUDA kernels (sm_100a).  There is no CPU fallback: without a CUDA device
+ * every entry point returns LB_ERR_NO_DEVICE.
+ */
+#ifndef LORO_B200_H
+#define LORO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum lb_status {
+    LB_OK = 0,
+    LB_ERR_INVALID_ARG = 1,
+    LB_ERR_NO_DEVICE = 2,
+    LB_ERR_CUDA = 3,
+    LB_ERR_OOM = 4,
+    LB_ERR_INTERNAL = 5
+} lb_status;
+
+/* per-document result code; the LoroError variant it corresponds to is given on the right */
+typedef enum lb_doc_code {
+    LB_DOC_OK = 0,
+    LB_DOC_ERR_DECODE = 1,          /* LoroError::DecodeError (short blob, bad magic, malformed block)  */
+    LB_DOC_ERR_CHECKSUM = 2,        /* LoroError::DecodeChecksumMismatchError                            */
+    LB_DOC_ERR_MODE = 3,            /* IncompatibleFutureEncodingError / ImportUnsupportedEncodingMode;  */
+                                    /* also FastSnapshot (mode 3): not on this path yet    */
+    LB_DOC_ERR_CORRUPT = 4,         /* LoroError::DecodeDataCorruptionError                               */
+    LB_DOC_ERR_UNSUPPORTED = 5,     /* well-formed, but uses ops the engine does not merge yet            */
+                                    /* (rich-text styles, movable list, counter, tree)                    */
+    LB_DOC_ERR_CAPACITY = 6         /* internal capacity bound exceeded (engine bug or adversarial input) */
+} lb_doc_code;
+
+typedef struct lb_blob {
+    const uint8_t* ptr; /* host pointer, borrowed */
+    size_t len;
+    uint64_t doc_id;    /* caller's label; one blob per document in this version */
+} lb_blob;
+
+typedef struct lb_options {
+    int device;          /* CUDA device ordinal */
+    uint32_t flags;      /* LB_FLAG_* */
+    uint32_t reserved[6];
+} lb_options;
+#define LB_FLAG_NO_JSON 1u      /* skip deep-value JSON materialisation */
+#define LB_FLAG_KEEP_DEVICE 2u  /* keep intermediate device tables for lb_debug_* (tests) */
+
+typedef struct lb_id_span {
+    uint64_t peer;
+    int32_t start; /* inclusive counter */
+    int32_t end;   /* exclusive counter */
+} lb_id_span;
+
+typedef struct lb_import_status {
+    lb_doc_code code;
+    size_t n_success;
+    const lb_id_span* success; /* ImportStatus.success (VersionRange) */
+    size_t n_pending;
+    const lb_id_span* pending; /* ImportStatus.pending */
+} lb_import_status;
+
+typedef struct lb_counters {
+    uint64_t docs, docs_ok;
+    uint64_t blob_bytes;
+    uint64_t blocks, changes, op_rows; /* decoded */
+    uint64_t atom_ops;                 /* merged ops (sum of change.atom_len of applied changes) */
+    uint64_t pending_changes;
+    uint64_t json_bytes;
+    uint64_t state_hash;               /* xor over docs of (xxh32(json) << 32 | len): order independent */
+} lb_counters;
+
+typedef struct lb_timings { /* device time per phase in milliseconds (CUDA events on the batch stream) */
+    float h2d, frame, decode, resolve, classify, integrate, materialise, d2h, total_device;
+    /* algorithmic bytes of the decode phase: blob bytes read + SoA bytes written */
+    uint64_t decode_bytes_read, decode_bytes_written;
+    uint32_t kernel_launches;
+} lb_timings;
+
+typedef struct lb_batch lb_batch;
+
+/* Import a batch of FastUpdates blobs, one fresh document per blob, from HOST memory. */
+lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out);
+
+/* Same, with the blobs already resident in device memory: `d_bytes` is one device buffer holding all blobs,
+ * blob i occupying [offsets[i], offsets[i+1]) (offsets: HOST array of n_docs+1 entries, each a multiple of
+ * 16).  Nothing is copied host->device except the offsets. */
+lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, size_t n_docs,
+                                 const lb_options* opt, lb_batch** out);
+
+size_t lb_doc_count(const lb_batch* b);
+lb_status lb_doc_status(const lb_batch* b, size_t doc, lb_import_status* out);
+lb_status lb_doc_json(const lb_batch* b, size_t doc, const char** utf8, size_t* len);
+lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n); /* start=0,end=vv[peer] */
+lb_status lb_batch_counters(const lb_batch* b, lb_counters* out);
+lb_status lb_batch_timings(const lb_batch* b, lb_timings* out);
+const char* lb_last_error(void); /* thread-local, human readable */
+void lb_batch_free(lb_batch* b);
+
+/* test hooks (need LB_FLAG_KEEP_DEVICE): copy one decoded SoA table to the host.
+ * name in {"op_cid","op_prop","op_vtype","op_len","op_counter","ch_counter","ch_len","ch_lamport",
+ *          "ch_ts","dep_peer","dep_counter","blk_doc","blk_nchanges"}; returns element count. */
+lb_status lb_debug_table(const lb_batch* b, const char* name, void* dst, size_t dst_bytes, size_t* n_elems,
+                         size_t* elem_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

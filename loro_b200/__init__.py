@@ -1,0 +1,15 @@
+"""loro_b200 -- B200-native batched CRDT merge engine (one hot path of loro-dev/loro).
+
+Host-side mirror of the reference's public API for that path (crates/loro/src/lib.rs):
+  LoroDoc::import / import_batch  ->  import_batch(blobs)            (one fresh document per blob)
+  ImportStatus                    ->  Batch.status(i)
+  LoroDoc::get_deep_value         ->  Batch.get_deep_value(i)
+  LoroDoc::oplog_vv               ->  Batch.oplog_vv(i)
+All compute runs in the CUDA library built from loro_b200/csrc (C ABI: include/loro_b200.h).  There is no
+CPU fallback: importing a batch without the built library or without a CUDA device raises.
+"""
+from .api import (Batch, DocError, EngineUnavailable, ImportStatus, import_batch, import_batch_device,
+                  library_path, load_library)
+
+__all__ = ["Batch", "DocError", "EngineUnavailable", "ImportStatus", "import_batch", "import_batch_device",
+           "library_path", "load_library"]

@@ -1,0 +1,204 @@
+"""ctypes binding of include/loro_b200.h (the same stub a cgo/N-API/Rust `extern "C"` shim would bind)."""
+import ctypes
+import json
+import os
+from collections import namedtuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DEFAULT_LIB = os.path.join(_HERE, "libloro_b200.so")
+
+LB_FLAG_NO_JSON = 1
+LB_FLAG_KEEP_DEVICE = 2
+
+DOC_CODES = {0: "Ok", 1: "DecodeError", 2: "DecodeChecksumMismatchError", 3: "IncompatibleFutureEncodingError",
+             4: "DecodeDataCorruptionError", 5: "Unsupported", 6: "CapacityExceeded"}
+
+ImportStatus = namedtuple("ImportStatus", "code success pending")
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA library is missing or no CUDA device is present (there is no CPU fallback)."""
+
+
+class DocError(RuntimeError):
+    def __init__(self, code):
+        super().__init__(DOC_CODES.get(code, str(code)))
+        self.code = code
+
+
+class _Blob(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_char_p), ("len", ctypes.c_size_t), ("doc_id", ctypes.c_uint64)]
+
+
+class _Options(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 6)]
+
+
+class _IdSpan(ctypes.Structure):
+    _fields_ = [("peer", ctypes.c_uint64), ("start", ctypes.c_int32), ("end", ctypes.c_int32)]
+
+
+class _Status(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int), ("n_success", ctypes.c_size_t), ("success", ctypes.POINTER(_IdSpan)),
+                ("n_pending", ctypes.c_size_t), ("pending", ctypes.POINTER(_IdSpan))]
+
+
+class _Counters(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("docs", "docs_ok", "blob_bytes", "blocks", "changes", "op_rows",
+                                                "atom_ops", "pending_changes", "json_bytes", "state_hash")]
+
+
+class _Timings(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("h2d", "frame", "decode", "resolve", "classify", "integrate",
+                                               "materialise", "d2h", "total_device")] + \
+               [("decode_bytes_read", ctypes.c_uint64), ("decode_bytes_written", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint32)]
+
+
+_libs = {}
+
+
+def library_path():
+    return _DEFAULT_LIB
+
+
+def load_library(path=None):
+    path = path or _DEFAULT_LIB
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise EngineUnavailable(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). loro_b200 has no CPU fallback.")
+    L = ctypes.CDLL(path)
+    vp = ctypes.c_void_p
+    L.lb_import_batch.argtypes = [ctypes.POINTER(_Blob), ctypes.c_size_t, ctypes.POINTER(_Options), ctypes.POINTER(vp)]
+    L.lb_import_batch_device.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t,
+                                         ctypes.POINTER(_Options), ctypes.POINTER(vp)]
+    L.lb_doc_count.restype = ctypes.c_size_t
+    L.lb_doc_count.argtypes = [vp]
+    L.lb_doc_status.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(_Status)]
+    L.lb_doc_json.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t)]
+    L.lb_doc_vv.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(_IdSpan)), ctypes.POINTER(ctypes.c_size_t)]
+    L.lb_batch_counters.argtypes = [vp, ctypes.POINTER(_Counters)]
+    L.lb_batch_timings.argtypes = [vp, ctypes.POINTER(_Timings)]
+    L.lb_last_error.restype = ctypes.c_char_p
+    L.lb_batch_free.argtypes = [vp]
+    L.lb_debug_table.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                                 ctypes.POINTER(ctypes.c_size_t)]
+    _libs[path] = L
+    return L
+
+
+def _check(L, rc, what):
+    if rc == 0:
+        return
+    msg = L.lb_last_error().decode(errors="replace")
+    if rc == 2:
+        raise EngineUnavailable(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed (lb_status={rc}): {msg}")
+
+
+class Batch:
+    """Result of one batched import; owns the engine-side outputs until closed."""
+
+    def __init__(self, L, handle, keep=None):
+        self._L = L
+        self._h = handle
+        self._keep = keep  # keeps input buffers alive for device-resident imports
+        self.n_docs = L.lb_doc_count(handle)
+
+    def close(self):
+        if self._h:
+            self._L.lb_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def status(self, i):
+        st = _Status()
+        _check(self._L, self._L.lb_doc_status(self._h, i, ctypes.byref(st)), "lb_doc_status")
+        suc = {st.success[k].peer: (st.success[k].start, st.success[k].end) for k in range(st.n_success)}
+        pen = {st.pending[k].peer: (st.pending[k].start, st.pending[k].end) for k in range(st.n_pending)}
+        return ImportStatus(st.code, suc, pen or None)
+
+    def json_bytes(self, i):
+        p = ctypes.c_char_p()
+        n = ctypes.c_size_t()
+        _check(self._L, self._L.lb_doc_json(self._h, i, ctypes.byref(p), ctypes.byref(n)), "lb_doc_json")
+        return ctypes.string_at(p, n.value)
+
+    def get_deep_value(self, i):
+        st = self.status(i)
+        if st.code != 0:
+            raise DocError(st.code)
+        return json.loads(self.json_bytes(i))
+
+    def oplog_vv(self, i):
+        spans = ctypes.POINTER(_IdSpan)()
+        n = ctypes.c_size_t()
+        _check(self._L, self._L.lb_doc_vv(self._h, i, ctypes.byref(spans), ctypes.byref(n)), "lb_doc_vv")
+        return {spans[k].peer: spans[k].end for k in range(n.value)}
+
+    def counters(self):
+        c = _Counters()
+        _check(self._L, self._L.lb_batch_counters(self._h, ctypes.byref(c)), "lb_batch_counters")
+        return {n: getattr(c, n) for n, _ in _Counters._fields_}
+
+    def timings(self):
+        t = _Timings()
+        _check(self._L, self._L.lb_batch_timings(self._h, ctypes.byref(t)), "lb_batch_timings")
+        return {n: getattr(t, n) for n, _ in _Timings._fields_}
+
+    def debug_table(self, name):
+        import numpy as np
+        n = ctypes.c_size_t()
+        es = ctypes.c_size_t()
+        _check(self._L, self._L.lb_debug_table(self._h, name.encode(), None, 0, ctypes.byref(n), ctypes.byref(es)),
+               "lb_debug_table")
+        dt = {1: np.uint8, 2: np.uint16, 4: np.int32, 8: np.int64}[es.value]
+        arr = np.empty(n.value, dtype=dt)
+        _check(self._L, self._L.lb_debug_table(self._h, name.encode(), arr.ctypes.data, arr.nbytes, ctypes.byref(n),
+                                               ctypes.byref(es)), "lb_debug_table")
+        return arr
+
+
+def import_batch(blobs, device=0, flags=0, lib_path=None):
+    """LoroDoc::import for a batch: one fresh document per blob (bytes-like), host buffers in."""
+    L = load_library(lib_path)
+    n = len(blobs)
+    arr = (_Blob * max(n, 1))()
+    keep = []
+    for i, b in enumerate(blobs):
+        b = bytes(b)
+        keep.append(b)
+        arr[i].ptr = b
+        arr[i].len = len(b)
+        arr[i].doc_id = i
+    opt = _Options(device=device, flags=flags)
+    h = ctypes.c_void_p()
+    _check(L, L.lb_import_batch(arr, n, ctypes.byref(opt), ctypes.byref(h)), "lb_import_batch")
+    return Batch(L, h.value)
+
+
+def import_batch_device(d_bytes_ptr, offsets, device=0, flags=0, lib_path=None, keep=None):
+    """Same with blobs already resident in HBM: `d_bytes_ptr` is a device pointer (int), `offsets` the n+1
+    blob boundaries (multiples of 16)."""
+    L = load_library(lib_path)
+    n = len(offsets) - 1
+    offs = (ctypes.c_uint64 * (n + 1))(*[int(x) for x in offsets])
+    opt = _Options(device=device, flags=flags)
+    h = ctypes.c_void_p()
+    _check(L, L.lb_import_batch_device(ctypes.c_void_p(d_bytes_ptr), offs, n, ctypes.byref(opt), ctypes.byref(h)),
+           "lb_import_batch_device")
+    return Batch(L, h.value, keep=keep)

@@ -1,0 +1,650 @@
+// loro_b200 -- host orchestration + C ABI (include/loro_b200.h).
+//
+// The host side only sizes tables, launches kernels and copies results; every byte of decode / merge /
+// materialisation work happens in the kernels of k_*.cuh.  There is no CPU fallback: with no CUDA device
+// the entry points fail with LB_ERR_NO_DEVICE.
+#include "../../include/loro_b200.h"
+
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+
+#include "lb_defs.h"
+#include "k_frame.cuh"
+#include "k_decode.cuh"
+#include "k_resolve.cuh"
+#include "k_classify.cuh"
+#include "k_seq.cuh"
+#include "k_state.cuh"
+
+static thread_local std::string g_last_error;
+const char* lb_last_error(void) { return g_last_error.c_str(); }
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            throw lb_status(LB_ERR_CUDA);                                                    \
+        }                                                                                    \
+    } while (0)
+
+// thread per doc helpers -------------------------------------------------------------------------
+__global__ void k_doc_sizes(const DocInfo* __restrict__ docs, u32 n_docs, u32* __restrict__ vvsize,
+                            u32* __restrict__ atoms, u32* __restrict__ mapslots, int which) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    bool ok = di.code == DOC_OK;
+    if (which == 0) vvsize[d] = ok ? di.n_changes * di.P : 0;
+    else {
+        atoms[d] = ok ? (u32)di.atom_total : 0;
+        mapslots[d] = ok ? di.C * di.K : 0;
+    }
+}
+// multi-field scan: CTA f scans field f (offsets in bytes inside the strided records)
+struct ScanJob { const u8* in; u8* out; size_t in_stride, out_stride; u64 n; };
+struct ScanJobs { ScanJob j[8]; };
+__global__ void k_excl_scan_multi(ScanJobs jobs) {
+    const ScanJob& jb = jobs.j[blockIdx.x];
+    const u8* in = jb.in; u8* out = jb.out; size_t in_stride = jb.in_stride, out_stride = jb.out_stride; u64 n = jb.n;
+    __shared__ u64 warp_tot[32];
+    __shared__ u64 carry_s;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n; base += blockDim.x) {
+        u64 i = base + threadIdx.x;
+        u64 v = i < n ? (u64) * (const u32*)(in + i * in_stride) : 0;
+        u64 s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t = __shfl_up_sync(LB_FULL, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane == 31) warp_tot[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            u64 t = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+            u64 ts = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 u = __shfl_up_sync(LB_FULL, ts, d);
+                if (lane >= d) ts += u;
+            }
+            warp_tot[lane] = ts - t;
+        }
+        __syncthreads();
+        u64 carry = carry_s;
+        if (i < n) *(u64*)(out + i * out_stride) = carry + warp_tot[w] + s - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[w] + s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *(u64*)(out + n * out_stride) = carry_s;
+}
+
+namespace {
+
+struct Dev {  // owns every device allocation of a batch
+    cudaStream_t stream = nullptr;
+    std::vector<void*> ptrs;
+    size_t bytes = 0;
+    template <class T>
+    T* alloc(size_t n, bool zero = false) {
+        void* p = nullptr;
+        size_t sz = (n ? n : 1) * sizeof(T);
+        sz = (sz + 255) & ~(size_t)255;
+        cudaError_t e = cudaMallocAsync(&p, sz, stream);
+        if (e != cudaSuccess) {
+            g_last_error = std::string("cudaMallocAsync(") + std::to_string(sz) + "): " + cudaGetErrorString(e);
+            throw lb_status(LB_ERR_OOM);
+        }
+        ptrs.push_back(p);
+        bytes += sz;
+        if (zero) CK(cudaMemsetAsync(p, 0, sz, stream));
+        return (T*)p;
+    }
+    void free_all() {
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
+        ptrs.clear();
+    }
+};
+
+struct Phase {
+    cudaEvent_t ev;
+};
+
+}  // namespace
+
+struct lb_batch {
+    Dev dev;
+    size_t n_docs = 0;
+    uint32_t flags = 0;
+    bool owns_bytes = false;
+    // device state
+    const u8* d_bytes = nullptr;
+    u64* d_offs = nullptr;
+    u32* d_lens = nullptr;
+    DocInfo* d_docs = nullptr;
+    BlockInfo* d_blocks = nullptr;
+    DocPeer* d_dpeer = nullptr;
+    u8* d_json = nullptr;
+    u64 n_blocks = 0, n_changes = 0, n_rows = 0, n_peers_tot = 0, json_total = 0;
+    Tables tb{};
+    // host results
+    std::vector<DocInfo> docs;
+    std::vector<DocPeer> dpeer;
+    std::vector<char> json;
+    bool json_fetched = false;
+    std::vector<std::vector<lb_id_span>> success, pending, vv;
+    std::vector<uint64_t> doc_ids;
+    lb_counters counters{};
+    lb_timings timings{};
+    cudaEvent_t ev[16];
+    int n_ev = 0;
+    bool ev_created = false;
+};
+
+namespace {
+
+const int TPB = 128;
+inline unsigned nblk(u64 n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+void mark(lb_batch* b) {
+    if (b->n_ev < 16) CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));
+}
+
+template <class T>
+T d2h_one(lb_batch* b, const T* src) {
+    T v;
+    CK(cudaMemcpyAsync(&v, src, sizeof(T), cudaMemcpyDeviceToHost, b->dev.stream));
+    CK(cudaStreamSynchronize(b->dev.stream));
+    return v;
+}
+
+void run_scans(lb_batch* b, std::vector<ScanJob> jobs) {
+    for (size_t i = 0; i < jobs.size(); i += 8) {
+        ScanJobs sj;
+        memset(&sj, 0, sizeof(sj));
+        unsigned n = 0;
+        for (; n < 8 && i + n < jobs.size(); n++) sj.j[n] = jobs[i + n];
+        LB_LAUNCH(k_excl_scan_multi, n, 1024, 0, b->dev.stream, sj);
+        b->timings.kernel_launches++;
+    }
+}
+#define FIELD_JOB(base, type, in_field, out_field, count)                                              \
+    ScanJob{(const u8*)(base) + offsetof(type, in_field), (u8*)(base) + offsetof(type, out_field), \
+            sizeof(type), sizeof(type), (u64)(count)}
+
+void pipeline(lb_batch* b) {
+    Dev& dv = b->dev;
+    cudaStream_t st = dv.stream;
+    u32 D = (u32)b->n_docs;
+    lb_timings& tm = b->timings;
+    if (D == 0) {
+        for (int i = 0; i < 7; i++) mark(b);
+        b->docs.resize(1);
+        return;
+    }
+    // ------------------------------------------------------------ phase 1: frame
+    b->d_docs = dv.alloc<DocInfo>(D + 1, true);
+    u32* d_nblocks = dv.alloc<u32>(D + 1, true);
+    u64* d_block0 = dv.alloc<u64>(D + 2, true);
+    LB_LAUNCH(k_frame_count, nblk(D), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, D, b->d_docs, d_nblocks);
+    run_scans(b, {ScanJob{(const u8*)d_nblocks, (u8*)d_block0, 4, 8, D}});
+    tm.kernel_launches += 1;
+    u64 B = d2h_one(b, d_block0 + D);
+    b->n_blocks = B;
+    b->d_blocks = dv.alloc<BlockInfo>(B + 1, true);
+    LB_LAUNCH(k_frame_fill, nblk(D), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, D, b->d_docs, d_block0, b->d_blocks);
+    tm.kernel_launches += 1;
+    mark(b);  // [1] frame done
+    // ------------------------------------------------------------ phase 2: decode
+    BlockInfo* blk = b->d_blocks;
+    if (B) {
+        LB_LAUNCH(k_block_count, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B);
+        tm.kernel_launches += 1;
+    }
+    run_scans(b, {FIELD_JOB(blk, BlockInfo, n_peers, peer0, B), FIELD_JOB(blk, BlockInfo, n_keys, key0, B),
+                  FIELD_JOB(blk, BlockInfo, n_cids, cid0, B), FIELD_JOB(blk, BlockInfo, n_changes, ch0, B),
+                  FIELD_JOB(blk, BlockInfo, n_deps, dep0, B), FIELD_JOB(blk, BlockInfo, n_ops, op0, B),
+                  FIELD_JOB(blk, BlockInfo, n_dels, del0, B)});
+    BlockInfo tot = d2h_one(b, blk + B);
+    u64 NP = tot.peer0, NK = tot.key0, NC = tot.cid0, NCH = tot.ch0, ND = tot.dep0, NR = tot.op0, NDEL = tot.del0;
+    if (NR >= 0xFFFFFFFFull || NCH >= 0xFFFFFFFFull) {
+        g_last_error = "batch too large: op rows / changes must fit 32 bits";
+        throw lb_status(LB_ERR_INVALID_ARG);
+    }
+    b->n_changes = NCH;
+    b->n_rows = NR;
+    b->n_peers_tot = NP;
+    Tables& t = b->tb;
+    t.peer_id = dv.alloc<u64>(NP);
+    t.key_off = dv.alloc<u64>(NK); t.key_len = dv.alloc<u32>(NK);
+    t.cid_root = dv.alloc<u8>(NC); t.cid_type = dv.alloc<u8>(NC); t.cid_peer_idx = dv.alloc<u32>(NC); t.cid_koc = dv.alloc<i32>(NC);
+    t.ch_block = dv.alloc<u32>(NCH); t.ch_counter = dv.alloc<i32>(NCH); t.ch_len = dv.alloc<u32>(NCH);
+    t.ch_lamport = dv.alloc<u32>(NCH); t.ch_ts = dv.alloc<i64>(NCH); t.ch_dep0 = dv.alloc<u64>(NCH);
+    t.ch_ndeps = dv.alloc<u32>(NCH); t.ch_dep_self = dv.alloc<u8>(NCH); t.ch_op0 = dv.alloc<u64>(NCH);
+    t.ch_nops = dv.alloc<u32>(NCH, true);
+    t.dep_peer_idx = dv.alloc<u32>(ND); t.dep_counter = dv.alloc<i32>(ND);
+    t.op_cid = dv.alloc<u32>(NR); t.op_prop = dv.alloc<i32>(NR); t.op_vtype = dv.alloc<u8>(NR); t.op_len = dv.alloc<u32>(NR);
+    t.op_counter = dv.alloc<i32>(NR); t.op_change = dv.alloc<u32>(NR); t.op_val_off = dv.alloc<u64>(NR);
+    t.op_val_len = dv.alloc<u32>(NR); t.op_del = dv.alloc<u32>(NR);
+    t.del_peer_idx = dv.alloc<u32>(NDEL); t.del_counter = dv.alloc<i32>(NDEL); t.del_len = dv.alloc<i32>(NDEL);
+    if (B) {
+        LB_LAUNCH(k_block_decode, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
+        tm.kernel_launches += 1;
+    }
+    mark(b);  // [2] decode done
+    // SURVEY 8d algorithmic bytes of decode: blob bytes read + SoA written
+    tm.decode_bytes_written = NR * 13 + NCH * (4 + 4 + 8 + 4) + ND * 12;
+    // ------------------------------------------------------------ phase 3: resolve
+    ResolveTables rt;
+    memset(&rt, 0, sizeof(rt));
+    rt.peer_id = t.peer_id; rt.key_off = t.key_off; rt.key_len = t.key_len;
+    rt.cid_root = t.cid_root; rt.cid_type = t.cid_type; rt.cid_peer_idx = t.cid_peer_idx; rt.cid_koc = t.cid_koc;
+    rt.ch_block = t.ch_block; rt.ch_counter = t.ch_counter; rt.ch_len = t.ch_len; rt.ch_lamport_wire = t.ch_lamport;
+    rt.ch_dep0 = t.ch_dep0; rt.ch_ndeps = t.ch_ndeps; rt.ch_dep_self = t.ch_dep_self;
+    rt.dep_peer_idx = t.dep_peer_idx; rt.dep_counter = t.dep_counter;
+    b->d_dpeer = dv.alloc<DocPeer>(NP, true);
+    rt.dpeer = b->d_dpeer; rt.peer_map = dv.alloc<u32>(NP);
+    DocContainer* dcont = dv.alloc<DocContainer>(NC + 1, true);
+    rt.dcont = dcont; rt.cid_map = dv.alloc<u32>(NC);
+    rt.dkey_off = dv.alloc<u64>(NK); rt.dkey_len = dv.alloc<u32>(NK); rt.key_map = dv.alloc<u32>(NK);
+    rt.blk_order = dv.alloc<u32>(B);
+    rt.ch_order = dv.alloc<u32>(NCH);
+    rt.ch_peer = dv.alloc<u16>(NCH);
+    rt.ch_applied = dv.alloc<u8>(NCH, true);
+    rt.ch_lamport = dv.alloc<u32>(NCH, true);
+    rt.ch_walk = dv.alloc<u32>(NCH);
+    LB_LAUNCH(k_doc_tables, nblk(D, 64), 64, 0, st, b->d_bytes, b->d_docs, D, blk, rt);
+    u32* d_tmp_a = dv.alloc<u32>(D + 1, true);
+    u32* d_tmp_b = dv.alloc<u32>(D + 1, true);
+    u32* d_tmp_c = dv.alloc<u32>(D + 1, true);
+    LB_LAUNCH(k_doc_sizes, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a, d_tmp_b, d_tmp_c, 0);
+    tm.kernel_launches += 2;
+    run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)b->d_docs + offsetof(DocInfo, vv0), 4, sizeof(DocInfo), D}});
+    u64 VV = d2h_one(b, &b->d_docs[D].vv0);
+    rt.ch_vv = dv.alloc<i32>(VV);
+    u32* d_cursor = dv.alloc<u32>(NP);
+    LB_LAUNCH(k_doc_causal, nblk(D, 64), 64, 0, st, b->d_docs, D, blk, rt, d_cursor);
+    LB_LAUNCH(k_doc_sizes, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a, d_tmp_b, d_tmp_c, 1);
+    tm.kernel_launches += 2;
+    run_scans(b, {ScanJob{(const u8*)d_tmp_b, (u8*)b->d_docs + offsetof(DocInfo, atom0), 4, sizeof(DocInfo), D},
+                  ScanJob{(const u8*)d_tmp_c, (u8*)b->d_docs + offsetof(DocInfo, mapslot0), 4, sizeof(DocInfo), D}});
+    DocInfo dtot = d2h_one(b, &b->d_docs[D]);
+    u64 NATOM = dtot.atom0, NSLOT = dtot.mapslot0;
+    mark(b);  // [3] resolve done
+    // ------------------------------------------------------------ phase 4: classify + map LWW
+    ClassifyTables ct;
+    memset(&ct, 0, sizeof(ct));
+    ct.blocks = blk; ct.ch_block = t.ch_block; ct.ch_applied = rt.ch_applied; ct.ch_lamport = rt.ch_lamport;
+    ct.ch_counter = t.ch_counter; ct.ch_peer = rt.ch_peer;
+    ct.op_cid = t.op_cid; ct.op_prop = t.op_prop; ct.op_vtype = t.op_vtype; ct.op_len = t.op_len;
+    ct.op_counter = t.op_counter; ct.op_change = t.op_change;
+    ct.cid_map = rt.cid_map; ct.key_map = rt.key_map; ct.dcont = dcont; ct.dpeer = b->d_dpeer;
+    ct.op_kind = dv.alloc<u8>(NR); ct.op_cidx = dv.alloc<u32>(NR); ct.op_lamport = dv.alloc<u32>(NR);
+    ct.atom_row = dv.alloc<u32>(NATOM);
+    ct.map_best = dv.alloc<unsigned long long>(NSLOT, true);
+    ct.map_row = dv.alloc<u32>(NSLOT);
+    if (NR) {
+        LB_LAUNCH(k_op_classify, nblk(NR, 256), 256, 0, st, b->d_docs, NR, ct);
+        LB_LAUNCH(k_map_winner, nblk(NR, 256), 256, 0, st, b->d_docs, NR, ct);
+        tm.kernel_launches += 2;
+    }
+    // capacities -> pools
+    u32* cap_leaf = dv.alloc<u32>(NC + 1, true);
+    u32* cap_node = dv.alloc<u32>(NC + 1, true);
+    u32* cap_out = dv.alloc<u32>(NC + 1, true);
+    u32* cap_cvv = dv.alloc<u32>(NC + 1, true);
+    u32* span_cap = dv.alloc<u32>(D + 1, true);
+    LB_LAUNCH(k_container_caps, nblk(D), TPB, 0, st, b->d_docs, D, dcont, cap_leaf, cap_node, cap_out, cap_cvv, span_cap);
+    tm.kernel_launches += 1;
+    run_scans(b, {ScanJob{(const u8*)cap_leaf, (u8*)dcont + offsetof(DocContainer, leaf0), 4, sizeof(DocContainer), NC},
+                  ScanJob{(const u8*)cap_node, (u8*)dcont + offsetof(DocContainer, node0), 4, sizeof(DocContainer), NC},
+                  ScanJob{(const u8*)cap_out, (u8*)dcont + offsetof(DocContainer, out0), 4, sizeof(DocContainer), NC},
+                  ScanJob{(const u8*)cap_cvv, (u8*)dcont + offsetof(DocContainer, cvv0), 4, sizeof(DocContainer), NC},
+                  ScanJob{(const u8*)span_cap, (u8*)b->d_docs + offsetof(DocInfo, span0), 4, sizeof(DocInfo), D}});
+    DocContainer ctot = d2h_one(b, dcont + NC);
+    DocInfo dtot2 = d2h_one(b, &b->d_docs[D]);
+    u64 NLEAF = ctot.leaf0, NNODE = ctot.node0, NOUT = ctot.out0, NCVV = ctot.cvv0, NSPAN = dtot2.span0;
+    mark(b);  // [4] classify done
+    // ------------------------------------------------------------ phase 5: sequence integration
+    SeqPools sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.leaf_sid = dv.alloc<u32>(NLEAF * 32); sp.leaf_len = dv.alloc<i32>(NLEAF * 32); sp.leaf_st = dv.alloc<u32>(NLEAF * 32);
+    sp.leaf_n = dv.alloc<u32>(NLEAF, true); sp.leaf_parent = dv.alloc<u32>(NLEAF); sp.leaf_next = dv.alloc<u32>(NLEAF);
+    sp.node_child = dv.alloc<u32>(NNODE * 32); sp.node_vis = dv.alloc<i32>(NNODE * 32);
+    sp.node_n = dv.alloc<u32>(NNODE, true); sp.node_parent = dv.alloc<u32>(NNODE);
+    sp.sp_peer = dv.alloc<u16>(NSPAN); sp.sp_ctr = dv.alloc<i32>(NSPAN); sp.sp_len = dv.alloc<i32>(NSPAN);
+    sp.sp_leaf = dv.alloc<u32>(NSPAN); sp.sp_ol_peer = dv.alloc<u16>(NSPAN); sp.sp_ol_ctr = dv.alloc<i32>(NSPAN);
+    sp.sp_or_peer = dv.alloc<u16>(NSPAN); sp.sp_or_ctr = dv.alloc<i32>(NSPAN);
+    sp.atom_sid = dv.alloc<u32>(NATOM);
+    sp.cvv = dv.alloc<i32>(NCVV, true);
+    sp.cont_epoch = dv.alloc<u32>(NC + 1);
+    sp.out_row = dv.alloc<u32>(NOUT); sp.out_off = dv.alloc<u32>(NOUT); sp.out_len = dv.alloc<u32>(NOUT);
+    SeqTables sq;
+    memset(&sq, 0, sizeof(sq));
+    sq.dpeer = b->d_dpeer; sq.dcont = dcont;
+    sq.ch_walk = rt.ch_walk; sq.ch_op0 = t.ch_op0; sq.ch_nops = t.ch_nops; sq.ch_peer = rt.ch_peer; sq.ch_vv = rt.ch_vv;
+    sq.ch_order = rt.ch_order; sq.ch_counter = t.ch_counter;
+    sq.op_kind = ct.op_kind; sq.op_cidx = ct.op_cidx; sq.op_prop = t.op_prop; sq.op_len = t.op_len;
+    sq.op_counter = t.op_counter; sq.op_del = t.op_del; sq.op_change = t.op_change;
+    sq.del_peer_idx = t.del_peer_idx; sq.del_counter = t.del_counter; sq.del_len = t.del_len;
+    sq.peer_map = rt.peer_map; sq.blocks = blk; sq.ch_block = t.ch_block; sq.atom_row = ct.atom_row;
+    LB_LAUNCH(k_seq_integrate, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, sp, sq);
+    tm.kernel_launches += 1;
+    mark(b);  // [5] integrate done
+    // ------------------------------------------------------------ phase 6: JSON
+    StateTables stt;
+    memset(&stt, 0, sizeof(stt));
+    stt.bytes = b->d_bytes; stt.dpeer = b->d_dpeer; stt.dcont = dcont;
+    stt.dkey_off = rt.dkey_off; stt.dkey_len = rt.dkey_len; stt.map_row = ct.map_row; stt.map_best = ct.map_best;
+    stt.op_kind = ct.op_kind; stt.op_vtype = t.op_vtype; stt.op_len = t.op_len; stt.op_counter = t.op_counter;
+    stt.op_change = t.op_change; stt.op_val_off = t.op_val_off; stt.op_val_len = t.op_val_len; stt.ch_peer = rt.ch_peer;
+    stt.out_row = sp.out_row; stt.out_off = sp.out_off; stt.out_len = sp.out_len;
+    unsigned long long* d_acc = dv.alloc<unsigned long long>(4, true);
+    if (!(b->flags & LB_FLAG_NO_JSON)) {
+        LB_LAUNCH(k_json, nblk(D, 64), 64, 0, st, b->d_docs, D, stt, (u8*)nullptr, 0);
+        LB_LAUNCH(k_json_padlen, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a);
+        tm.kernel_launches += 2;
+        run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)b->d_docs + offsetof(DocInfo, json_off), 4, sizeof(DocInfo), D}});
+        u64 JT = d2h_one(b, &b->d_docs[D].json_off);
+        b->json_total = JT;
+        b->d_json = dv.alloc<u8>(JT + 16, true);
+        LB_LAUNCH(k_json, nblk(D, 64), 64, 0, st, b->d_docs, D, stt, b->d_json, 1);
+        tm.kernel_launches += 1;
+    }
+    LB_LAUNCH(k_doc_hash, nblk(D), TPB, 0, st, b->d_docs, D, (const u8*)b->d_json, d_acc);
+    tm.kernel_launches += 1;
+    mark(b);  // [6] materialise done
+    // ------------------------------------------------------------ results to host
+    b->docs.resize(D + 1);
+    CK(cudaMemcpyAsync(b->docs.data(), b->d_docs, sizeof(DocInfo) * (D + 1), cudaMemcpyDeviceToHost, st));
+    b->dpeer.resize(NP);
+    if (NP) CK(cudaMemcpyAsync(b->dpeer.data(), b->d_dpeer, sizeof(DocPeer) * NP, cudaMemcpyDeviceToHost, st));
+    unsigned long long acc[4];
+    CK(cudaMemcpyAsync(acc, d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
+    mark(b);  // [7] d2h queued
+    CK(cudaStreamSynchronize(st));
+    lb_counters& c = b->counters;
+    c.docs = D;
+    c.docs_ok = acc[3];
+    c.blocks = B;
+    c.changes = NCH;
+    c.op_rows = NR;
+    c.atom_ops = acc[1];
+    c.pending_changes = acc[2];
+    c.state_hash = acc[0];
+    c.json_bytes = 0;
+    for (u32 d = 0; d < D; d++) c.json_bytes += b->docs[d].json_len;
+    (void)NDEL;
+}
+
+void build_status(lb_batch* b) {
+    size_t D = b->n_docs;
+    b->success.assign(D, {});
+    b->pending.assign(D, {});
+    b->vv.assign(D, {});
+    for (size_t d = 0; d < D; d++) {
+        DocInfo& di = b->docs[d];
+        if (di.code == DOC_OK && di.has_unsupported) di.code = DOC_ERR_UNSUPPORTED;
+        if (di.code != DOC_OK && di.code != DOC_ERR_UNSUPPORTED) continue;
+        for (u32 p = 0; p < di.P; p++) {
+            const DocPeer& dp = b->dpeer[di.peer0 + p];
+            if (dp.end_counter > 0) {
+                b->success[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
+                b->vv[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
+            }
+            if (dp.pend_hi > dp.pend_lo) b->pending[d].push_back(lb_id_span{dp.id, dp.pend_lo, dp.pend_hi});
+        }
+    }
+}
+
+void timings_from_events(lb_batch* b) {
+    auto el = [&](int a, int c) {
+        float ms = 0;
+        if (a < b->n_ev && c < b->n_ev) cudaEventElapsedTime(&ms, b->ev[a], b->ev[c]);
+        return ms;
+    };
+    lb_timings& t = b->timings;
+    t.h2d = el(0, 1);
+    t.frame = el(1, 2);
+    t.decode = el(2, 3);
+    t.resolve = el(3, 4);
+    t.classify = el(4, 5);
+    t.integrate = el(5, 6);
+    t.materialise = el(6, 7);
+    t.d2h = el(7, 8);
+    t.total_device = el(1, 7);
+}
+
+lb_status run_batch(lb_batch* b) {
+    try {
+        pipeline(b);
+        build_status(b);
+        timings_from_events(b);
+    } catch (lb_status s) {
+        return s;
+    }
+    return LB_OK;
+}
+
+lb_status check_device(const lb_options* opt) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        g_last_error = "no CUDA device: loro_b200 has no CPU fallback";
+        return LB_ERR_NO_DEVICE;
+    }
+    int dev = opt ? opt->device : 0;
+    if (dev < 0 || dev >= n) {
+        g_last_error = "bad device ordinal";
+        return LB_ERR_INVALID_ARG;
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        g_last_error = "cudaSetDevice failed";
+        return LB_ERR_CUDA;
+    }
+    return LB_OK;
+}
+
+void init_batch(lb_batch* b) {
+    CK(cudaStreamCreate(&b->dev.stream));
+    for (int i = 0; i < 16; i++) CK(cudaEventCreate(&b->ev[i]));
+    b->ev_created = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out) {
+    if (!out || (!blobs && n_blobs)) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    lb_status s = check_device(opt);
+    if (s != LB_OK) return s;
+    if (n_blobs >= 0x7FFFFFFFull) { g_last_error = "too many blobs"; return LB_ERR_INVALID_ARG; }
+    lb_batch* b = new lb_batch();
+    b->n_docs = n_blobs;
+    b->flags = opt ? opt->flags : 0;
+    u8* pinned = nullptr;
+    try {
+        init_batch(b);
+        std::vector<u64> offs(n_blobs + 1);
+        std::vector<u32> lens(n_blobs + 1, 0);
+        u64 total = 0;
+        for (size_t i = 0; i < n_blobs; i++) {
+            if (blobs[i].len > 0xFFFFFFF0ull || (!blobs[i].ptr && blobs[i].len)) {
+                g_last_error = "blob too large or null";
+                throw lb_status(LB_ERR_INVALID_ARG);
+            }
+            offs[i] = total;
+            lens[i] = (u32)blobs[i].len;
+            total += (blobs[i].len + 15) & ~(u64)15;
+            b->doc_ids.push_back(blobs[i].doc_id);
+            b->counters.blob_bytes += blobs[i].len;
+        }
+        offs[n_blobs] = total;
+        // stage through pinned memory so that the H2D copy is a single DMA
+        CK(cudaMallocHost((void**)&pinned, total ? total : 16));
+        for (size_t i = 0; i < n_blobs; i++) {
+            memcpy(pinned + offs[i], blobs[i].ptr, blobs[i].len);
+            size_t pad = (size_t)(((blobs[i].len + 15) & ~(u64)15) - blobs[i].len);
+            if (pad) memset(pinned + offs[i] + blobs[i].len, 0, pad);
+        }
+        CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
+        u8* d_bytes = b->dev.alloc<u8>(total + 64);
+        b->d_offs = b->dev.alloc<u64>(n_blobs + 1);
+        b->d_lens = b->dev.alloc<u32>(n_blobs + 1);
+        CK(cudaMemcpyAsync(d_bytes, pinned, total, cudaMemcpyHostToDevice, b->dev.stream));
+        CK(cudaMemcpyAsync(b->d_offs, offs.data(), sizeof(u64) * (n_blobs + 1), cudaMemcpyHostToDevice, b->dev.stream));
+        CK(cudaMemcpyAsync(b->d_lens, lens.data(), sizeof(u32) * (n_blobs + 1), cudaMemcpyHostToDevice, b->dev.stream));
+        b->d_bytes = d_bytes;
+        b->timings.decode_bytes_read = b->counters.blob_bytes;
+        mark(b);  // [1] h2d done (index 0 = start)
+        // event indices: 0 start,1 h2d,2 frame,3 decode,4 resolve,5 classify,6 integrate,7 materialise,8 d2h
+        s = run_batch(b);
+        CK(cudaStreamSynchronize(b->dev.stream));
+        cudaFreeHost(pinned);
+        pinned = nullptr;
+    } catch (lb_status e) {
+        s = e;
+    }
+    if (pinned) cudaFreeHost(pinned);
+    if (s != LB_OK) { lb_batch_free(b); return s; }
+    *out = b;
+    return LB_OK;
+}
+
+lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, size_t n_docs,
+                                 const lb_options* opt, lb_batch** out) {
+    if (!out || !offsets || (!d_bytes && n_docs)) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    lb_status s = check_device(opt);
+    if (s != LB_OK) return s;
+    lb_batch* b = new lb_batch();
+    b->n_docs = n_docs;
+    b->flags = opt ? opt->flags : 0;
+    try {
+        init_batch(b);
+        std::vector<u64> offs(n_docs + 1);
+        std::vector<u32> lens(n_docs + 1, 0);
+        for (size_t i = 0; i < n_docs; i++) {
+            if (offsets[i] & 15) { g_last_error = "blob offsets must be multiples of 16"; throw lb_status(LB_ERR_INVALID_ARG); }
+            if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFFFF0ull) {
+                g_last_error = "bad offsets";
+                throw lb_status(LB_ERR_INVALID_ARG);
+            }
+            offs[i] = offsets[i];
+            lens[i] = (u32)(offsets[i + 1] - offsets[i]);
+            b->doc_ids.push_back(i);
+            b->counters.blob_bytes += lens[i];
+        }
+        offs[n_docs] = offsets[n_docs];
+        CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
+        b->d_offs = b->dev.alloc<u64>(n_docs + 1);
+        b->d_lens = b->dev.alloc<u32>(n_docs + 1);
+        CK(cudaMemcpyAsync(b->d_offs, offs.data(), sizeof(u64) * (n_docs + 1), cudaMemcpyHostToDevice, b->dev.stream));
+        CK(cudaMemcpyAsync(b->d_lens, lens.data(), sizeof(u32) * (n_docs + 1), cudaMemcpyHostToDevice, b->dev.stream));
+        b->d_bytes = d_bytes;
+        b->timings.decode_bytes_read = b->counters.blob_bytes;
+        mark(b);  // [1]
+        s = run_batch(b);
+    } catch (lb_status e) {
+        s = e;
+    }
+    if (s != LB_OK) { lb_batch_free(b); return s; }
+    *out = b;
+    return LB_OK;
+}
+
+size_t lb_doc_count(const lb_batch* b) { return b ? b->n_docs : 0; }
+
+lb_status lb_doc_status(const lb_batch* b, size_t doc, lb_import_status* out) {
+    if (!b || !out || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
+    out->code = (lb_doc_code)b->docs[doc].code;
+    out->n_success = b->success[doc].size();
+    out->success = b->success[doc].data();
+    out->n_pending = b->pending[doc].size();
+    out->pending = b->pending[doc].data();
+    return LB_OK;
+}
+
+lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n) {
+    if (!b || !spans || !n || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
+    *spans = b->vv[doc].data();
+    *n = b->vv[doc].size();
+    return LB_OK;
+}
+
+lb_status lb_doc_json(const lb_batch* cb, size_t doc, const char** utf8, size_t* len) {
+    lb_batch* b = const_cast<lb_batch*>(cb);
+    if (!b || !utf8 || !len || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
+    if (b->flags & LB_FLAG_NO_JSON) { g_last_error = "batch was imported with LB_FLAG_NO_JSON"; return LB_ERR_INVALID_ARG; }
+    if (!b->json_fetched) {
+        b->json.resize(b->json_total + 1);
+        if (b->json_total) {
+            if (cudaMemcpy(b->json.data(), b->d_json, b->json_total, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                g_last_error = "json d2h failed";
+                return LB_ERR_CUDA;
+            }
+        }
+        b->json_fetched = true;
+    }
+    const DocInfo& di = b->docs[doc];
+    if (di.code != DOC_OK) { *utf8 = ""; *len = 0; return LB_OK; }
+    *utf8 = b->json.data() + di.json_off;
+    *len = di.json_len;
+    return LB_OK;
+}
+
+lb_status lb_batch_counters(const lb_batch* b, lb_counters* out) {
+    if (!b || !out) return LB_ERR_INVALID_ARG;
+    *out = b->counters;
+    return LB_OK;
+}
+lb_status lb_batch_timings(const lb_batch* b, lb_timings* out) {
+    if (!b || !out) return LB_ERR_INVALID_ARG;
+    *out = b->timings;
+    return LB_OK;
+}
+
+lb_status lb_debug_table(const lb_batch* b, const char* name, void* dst, size_t dst_bytes, size_t* n_elems,
+                         size_t* elem_size) {
+    if (!b || !name || !n_elems || !elem_size) return LB_ERR_INVALID_ARG;
+    if (!(b->flags & LB_FLAG_KEEP_DEVICE)) { g_last_error = "needs LB_FLAG_KEEP_DEVICE"; return LB_ERR_INVALID_ARG; }
+    std::string nm(name);
+    const void* src = nullptr;
+    size_t n = 0, es = 0;
+    const Tables& t = b->tb;
+#define TAB(str, ptr, cnt) if (nm == str) { src = ptr; n = cnt; es = sizeof(*ptr); }
+    TAB("op_cid", t.op_cid, b->n_rows) TAB("op_prop", t.op_prop, b->n_rows) TAB("op_vtype", t.op_vtype, b->n_rows)
+    TAB("op_len", t.op_len, b->n_rows) TAB("op_counter", t.op_counter, b->n_rows)
+    TAB("ch_counter", t.ch_counter, b->n_changes) TAB("ch_len", t.ch_len, b->n_changes)
+    TAB("ch_lamport", t.ch_lamport, b->n_changes) TAB("ch_ts", t.ch_ts, b->n_changes)
+#undef TAB
+    if (!src) { g_last_error = "unknown table"; return LB_ERR_INVALID_ARG; }
+    *n_elems = n;
+    *elem_size = es;
+    if (dst) {
+        if (dst_bytes < n * es) { g_last_error = "buffer too small"; return LB_ERR_INVALID_ARG; }
+        if (n && cudaMemcpy(dst, src, n * es, cudaMemcpyDeviceToHost) != cudaSuccess) return LB_ERR_CUDA;
+    }
+    return LB_OK;
+}
+
+void lb_batch_free(lb_batch* b) {
+    if (!b) return;
+    if (b->dev.stream) {
+        b->dev.free_all();
+        cudaStreamSynchronize(b->dev.stream);
+        if (b->ev_created)
+            for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
+        cudaStreamDestroy(b->dev.stream);
+    }
+    delete b;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// loro_b200 -- phase 4: per-op-row classification, atom->row index, map last-writer-wins.
+//
+// Replaces (reference, relative to crates/loro-internal/src):
+//   encoding/outdated_encode_reordered.rs:215-423 decode_op (value kind x container type -> op content)
+//   diff_calc.rs:423-551 MapDiffCalculator + delta/map_delta.rs:19-46 (LWW by (lamport, peer))
+// Fully data-parallel: one thread per op row; the LWW reduce is an atomicMax over a packed
+// (lamport, peer rank) key followed by a pass that elects the matching row.
+#pragma once
+#include "lb_defs.h"
+
+struct ClassifyTables {
+    const BlockInfo* blocks;
+    const u32* ch_block; const u8* ch_applied; const u32* ch_lamport; const i32* ch_counter; const u16* ch_peer;
+    const u32* op_cid; const i32* op_prop; const u8* op_vtype; const u32* op_len; const i32* op_counter;
+    const u32* op_change;
+    const u32* cid_map; const u32* key_map;
+    DocContainer* dcont; const DocPeer* dpeer;
+    // outputs
+    u8* op_kind; u32* op_cidx; u32* op_lamport;
+    u32* atom_row;          // per doc: atom -> op row (batch-wide row index, 32-bit)
+    unsigned long long* map_best;  // per (doc, container, key): max packed (lamport<<32 | rank<<16 | 1)
+    u32* map_row;           // winner row per slot
+};
+
+__device__ __forceinline__ u8 classify_op(u8 ctype, u8 vt) {
+    switch (ctype) {
+        case CT_TEXT:
+            if (vt == VK_STR) return OPK_SEQ_INS;
+            if (vt == VK_DELETE_SEQ) return OPK_SEQ_DEL;
+            return OPK_UNSUPPORTED;  // MarkStart / Null (style anchors): SURVEY 8f.2
+        case CT_LIST:
+            if (vt == VK_LORO_VALUE) return OPK_SEQ_INS;
+            if (vt == VK_DELETE_SEQ) return OPK_SEQ_DEL;
+            return OPK_UNSUPPORTED;
+        case CT_MAP:
+            if (vt == VK_LORO_VALUE) return OPK_MAP_SET;
+            if (vt == VK_DELETE_ONCE) return OPK_MAP_DEL;
+            return OPK_UNSUPPORTED;
+        default: return OPK_UNSUPPORTED;  // tree, movable list, counter, unknown
+    }
+}
+
+__global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTables t) {
+    u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    u32 ch = t.op_change[row];
+    const BlockInfo& bi = t.blocks[t.ch_block[ch]];
+    DocInfo& di = docs[bi.doc];
+    if (di.code != DOC_OK) { t.op_kind[row] = OPK_SKIP; return; }
+    u32 cidx = t.cid_map[bi.cid0 + t.op_cid[row]];
+    DocContainer& dc = t.dcont[di.cid0 + cidx];
+    u8 kind = classify_op(dc.type, t.op_vtype[row]);
+    if (!t.ch_applied[ch]) kind = OPK_SKIP;
+    u32 lam = t.ch_lamport[ch] + (u32)(t.op_counter[row] - t.ch_counter[ch]);
+    t.op_kind[row] = kind;
+    t.op_cidx[row] = cidx;
+    t.op_lamport[row] = lam;
+    if (kind == OPK_SKIP) return;
+    u32 len = t.op_len[row];
+    const DocPeer& dp = t.dpeer[di.peer0 + t.ch_peer[ch]];
+    // atom -> row index (used by the tracker to resolve ids; reference: id_to_cursor.rs)
+    u64 a0 = di.atom0 + dp.atom_base + (u32)t.op_counter[row];
+    for (u32 k = 0; k < len; k++) t.atom_row[a0 + k] = (u32)row;
+    switch (kind) {
+        case OPK_SEQ_INS:
+            atomicAdd(&dc.n_ins_rows, 1u);
+            atomicAdd(&dc.n_ins_atoms, len);
+            break;
+        case OPK_SEQ_DEL: atomicAdd(&dc.n_del_rows, 1u); break;
+        case OPK_MAP_SET: case OPK_MAP_DEL: {
+            atomicAdd(&dc.n_map_rows, 1u);
+            u32 key = t.key_map[bi.key0 + (u32)t.op_prop[row]];
+            unsigned long long pack = ((unsigned long long)lam << 32) | ((unsigned long long)dp.rank << 16) | 1ull;
+            atomicMax(&t.map_best[di.mapslot0 + (u64)cidx * di.K + key], pack);
+            break;
+        }
+        default:
+            atomicAdd(&dc.unsupported, 1u);
+            atomicAdd(&di.has_unsupported, 1u);
+    }
+}
+
+__global__ void k_map_winner(const DocInfo* __restrict__ docs, u64 n_rows, ClassifyTables t) {
+    u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    u8 kind = t.op_kind[row];
+    if (kind != OPK_MAP_SET && kind != OPK_MAP_DEL) return;
+    u32 ch = t.op_change[row];
+    const BlockInfo& bi = t.blocks[t.ch_block[ch]];
+    const DocInfo& di = docs[bi.doc];
+    const DocPeer& dp = t.dpeer[di.peer0 + t.ch_peer[ch]];
+    u32 key = t.key_map[bi.key0 + (u32)t.op_prop[row]];
+    u64 slot = di.mapslot0 + (u64)t.op_cidx[row] * di.K + key;
+    unsigned long long pack = ((unsigned long long)t.op_lamport[row] << 32) | ((unsigned long long)dp.rank << 16) | 1ull;
+    if (t.map_best[slot] == pack) t.map_row[slot] = (u32)row;
+}
+
+// thread per (doc-container entry): derive tracker pool capacities from the counted rows.
+__global__ void k_container_caps(DocInfo* __restrict__ docs, u32 n_docs, DocContainer* __restrict__ dcont,
+                                 u32* __restrict__ cap_leaf, u32* __restrict__ cap_node,
+                                 u32* __restrict__ cap_out, u32* __restrict__ cap_cvv,
+                                 u32* __restrict__ doc_span_cap) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    u32 spans_total = 0;
+    for (u32 c = 0; c < di.C_cap; c++) {
+        u64 g = di.cid0 + c;
+        u32 cl = 0, cn = 0, co = 0, cv = 0;
+        if (di.code == DOC_OK && c < di.C) {
+            DocContainer& dc = dcont[g];
+            if ((dc.type == CT_LIST || dc.type == CT_TEXT) && (dc.n_ins_rows + dc.n_del_rows) > 0) {
+                // every insert row creates one span and may split one; every delete row and every version
+                // switch boundary may split two
+                u64 spans = 3ull * dc.n_ins_rows + 2ull * dc.n_del_rows + 2ull * ((u64)di.n_applied + di.n_deps) + 8;
+                u64 by_atoms = (u64)dc.n_ins_atoms + 2;
+                if (by_atoms < spans) spans = by_atoms;
+                cl = (u32)(spans / 16 + 4);
+                cn = cl / 15 + 8;
+                co = (u32)spans;
+                cv = di.P;
+                spans_total += (u32)spans;
+            }
+        }
+        cap_leaf[g] = cl;
+        cap_node[g] = cn;
+        cap_out[g] = co;
+        cap_cvv[g] = cv;
+        if (di.code == DOC_OK && c < di.C) {
+            dcont[g].leaf_cap = cl;
+            dcont[g].node_cap = cn;
+            dcont[g].out_cap = co;
+        }
+    }
+    doc_span_cap[d] = spans_total;
+    docs[d].span_cap = spans_total;
+}

@@ -1,0 +1,411 @@
+// loro_b200 -- phase 2: change-block decode into batch-wide SoA tables.
+//
+// Replaces (reference, relative to crates/loro-internal/src):
+//   oplog/change_store/block_encode.rs:95-119 (EncodedBlock envelope), :527-659 (decode_block)
+//   oplog/change_store/block_meta_encode.rs:90-179 (decode_changes_header)
+//   encoding/arena.rs:94-101 (ContainerArena), block_encode.rs:290-300 (keys)
+//   encoding/value.rs:343-391, 603-700 (values stream), encoding/outdated_encode_reordered.rs:215-423
+//   third-party serde_columnar 0.3.14 column codecs (docs/encoding.md:1056-1398)
+// Round-1 shape: one thread per block, two passes (count -> host allocates -> fill).  Blocks are ~4 KB and a
+// batch holds 10^5..10^6 of them, so the parallelism is across blocks.
+#pragma once
+#include "lb_defs.h"
+
+// ---- skip one LoroValue (kind byte already consumed) ; iterative, bounded depth
+// reference: value.rs:620-700 read_value_content
+__device__ inline void skip_loro_value_content(Cur& c, u8 kind, u32* n_child_containers) {
+    // stack of remaining item counts; bit 31 marks a map level (items carry a key index)
+    u32 stack[24];
+    int sp = 0;
+    bool have = true;  // a value of `kind` must be consumed now
+    while (true) {
+        if (have) {
+            switch (kind) {
+                case 0: case 1: case 2: break;
+                case 3: (void)c.sleb(); break;
+                case 4: c.skip(8); break;
+                case 5: case 6: { u64 n = c.varint(); c.skip(n); break; }
+                case 7: case 8: {
+                    u64 n = c.varint();
+                    if (n > (1u << 28) || sp >= 24) { c.err = 1; return; }
+                    stack[sp++] = (u32)n | (kind == 8 ? 0x80000000u : 0);
+                    break;
+                }
+                case 9: (void)c.get(); if (n_child_containers) (*n_child_containers)++; break;
+                default: c.err = 1; return;
+            }
+            have = false;
+        }
+        if (c.err) return;
+        // pop finished levels
+        while (sp > 0 && (stack[sp - 1] & 0x7fffffffu) == 0) sp--;
+        if (sp == 0) return;
+        stack[sp - 1]--;
+        if (stack[sp - 1] & 0x80000000u) (void)c.varint();  // map key index
+        kind = c.get();
+        have = true;
+    }
+}
+
+// length in bytes of the value of op kind `vt` starting at c (advances c)
+__device__ inline void skip_value(Cur& c, u8 vt) {
+    switch (vt) {
+        case VK_NULL: case VK_TRUE: case VK_FALSE: case VK_DELETE_ONCE: case VK_DELETE_SEQ: break;
+        case VK_I64: case VK_DELTA_INT: (void)c.sleb(); break;
+        case VK_F64: c.skip(8); break;
+        case VK_STR: case VK_BINARY: { u64 n = c.varint(); c.skip(n); break; }
+        case VK_CONTAINER: (void)c.varint(); break;
+        case VK_LORO_VALUE: { u8 k = c.get(); skip_loro_value_content(c, k, nullptr); break; }
+        case VK_MARK_START: {
+            (void)c.get(); (void)c.varint(); (void)c.varint();
+            u8 k = c.get();
+            skip_loro_value_content(c, k, nullptr);
+            break;
+        }
+        case VK_TREE_MOVE: {
+            (void)c.varint();
+            u8 pn = c.get();
+            (void)c.varint();
+            if (!pn) (void)c.varint();
+            break;
+        }
+        case VK_RAW_TREE_MOVE: {
+            (void)c.varint(); (void)c.varint(); (void)c.varint();
+            u8 pn = c.get();
+            if (!pn) { (void)c.varint(); (void)c.varint(); }
+            break;
+        }
+        case VK_LIST_MOVE: (void)c.varint(); (void)c.varint(); (void)c.varint(); break;
+        case VK_LIST_SET: {
+            (void)c.varint(); (void)c.varint();
+            u8 k = c.get();
+            skip_loro_value_content(c, k, nullptr);
+            break;
+        }
+        default:
+            if (vt & 0x80) { u64 n = c.varint(); c.skip(n); }  // Future kinds: binary payload
+            else c.err = 1;
+    }
+}
+
+// columnar wrapper: varint(1) varint(ncols) then per column varint(len)+payload
+__device__ inline bool columnar_open(const u8* b, size_t n, int ncols, const u8** col, u32* col_len) {
+    Cur c(b, n);
+    if (c.varint() != 1) return false;
+    if (c.varint() != (u64)ncols) return false;
+    for (int i = 0; i < ncols; i++) {
+        u64 len = c.varint();
+        col[i] = c.p;
+        col_len[i] = (u32)len;
+        c.skip(len);
+    }
+    return !c.err && c.empty();
+}
+
+// ---------------------------------------------------------------- pass 1: envelope + counts
+__global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    BlockInfo bi = blocks[i];
+    const u8* b = bytes + bi.off;
+    Cur c(b, bi.len);
+    bi.counter_start = (u32)c.varint();
+    bi.counter_len = (u32)c.varint();
+    bi.lamport_start = (u32)c.varint();
+    bi.lamport_len = (u32)c.varint();
+    bi.n_changes = (u32)c.varint();
+    for (int s = 0; s < 8; s++) {
+        u64 len = c.varint();
+        bi.sec_off[s] = (u32)(c.p - b);
+        bi.sec_len[s] = (u32)len;
+        c.skip(len);
+    }
+    u32 err = 0;
+    if (c.err || !c.empty() || bi.n_changes == 0) err = LB_ERR(DOC_ERR_DECODE);
+    bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0;
+    bi.values_bytes = bi.sec_len[7];
+    if (!err) {
+        u32 N = bi.n_changes;
+        // header: peers, N-1 lens, BoolRle(N), AnyRle dep_len(N) -> n_deps
+        Cur h(b + bi.sec_off[0], bi.sec_len[0]);
+        u64 np = h.varint();
+        h.skip(8 * np);
+        for (u32 k = 0; k + 1 < N; k++) (void)h.varint();
+        u64 got = 0;
+        while (got < N && !h.err) got += h.varint();  // BoolRle run lengths
+        if (got != N) h.err = 1;
+        got = 0;
+        u64 ndeps = 0;
+        while (got < N && !h.err) {  // AnyRle<usize>
+            i64 sl = h.zigzag();
+            if (sl == 0) { h.err = 1; break; }
+            if (sl > 0) { u64 v = h.varint(); ndeps += v * (u64)sl; got += (u64)sl; }
+            else { for (i64 k = 0; k < -sl; k++) ndeps += h.varint(); got += (u64)(-sl); }
+        }
+        if (got != N || np == 0 || np > 0xFFF0) h.err = 1;
+        bi.n_peers = (u32)np;
+        bi.n_deps = (u32)ndeps;
+        // keys
+        Cur k(b + bi.sec_off[3], bi.sec_len[3]);
+        u32 nk = 0;
+        while (!k.empty() && !k.err) { u64 len = k.varint(); k.skip(len); nk++; }
+        bi.n_keys = nk;
+        // cids
+        Cur cc(b + bi.sec_off[2], bi.sec_len[2]);
+        bi.n_cids = (u32)cc.varint();
+        // ops: rows = sum |segment len| of the value_type column; dels = rows with kind DeleteSeq
+        const u8* col[4];
+        u32 col_len[4];
+        bool ok = columnar_open(b + bi.sec_off[5], bi.sec_len[5], 4, col, col_len);
+        u32 nops = 0, ndel = 0;
+        if (ok) {
+            Cur v(col[2], col_len[2]);
+            while (!v.empty() && !v.err) {
+                i64 sl = v.zigzag();
+                if (sl == 0) { v.err = 1; break; }
+                if (sl > 0) { u8 x = v.get(); nops += (u32)sl; if (x == VK_DELETE_SEQ) ndel += (u32)sl; }
+                else { for (i64 q = 0; q < -sl; q++) { u8 x = v.get(); if (x == VK_DELETE_SEQ) ndel++; } nops += (u32)(-sl); }
+            }
+            if (v.err) ok = false;
+        }
+        bi.n_ops = nops;
+        bi.n_dels = ndel;
+        if (h.err || k.err || cc.err || !ok || nops == 0) err = LB_ERR(DOC_ERR_DECODE);
+    }
+    bi.err = err;
+    if (err) { bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0; bi.n_changes = 0; }
+    blocks[i] = bi;
+}
+
+// ---------------------------------------------------------------- batch-wide SoA tables (device pointers)
+struct Tables {
+    // block-local peer tables
+    u64* peer_id;
+    // keys (block-local arena)
+    u64* key_off; u32* key_len;
+    // cids (block-local arena)
+    u8* cid_root; u8* cid_type; u32* cid_peer_idx; i32* cid_koc;  // key idx or counter
+    // changes
+    u32* ch_block; i32* ch_counter; u32* ch_len; u32* ch_lamport; i64* ch_ts;
+    u64* ch_dep0; u32* ch_ndeps; u8* ch_dep_self; u64* ch_op0; u32* ch_nops;
+    // deps (other peers)
+    u32* dep_peer_idx; i32* dep_counter;
+    // op rows
+    u32* op_cid; i32* op_prop; u8* op_vtype; u32* op_len; i32* op_counter; u32* op_change;
+    u64* op_val_off; u32* op_val_len; u32* op_del;  // op_del: index into del tables for DeleteSeq rows
+    // delete start ids
+    u32* del_peer_idx; i32* del_counter; i32* del_len;
+};
+
+// ---------------------------------------------------------------- pass 2: fill
+__global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks,
+                               Tables t) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    BlockInfo bi = blocks[i];
+    if (bi.err) return;
+    const u8* b = bytes + bi.off;
+    u32 N = bi.n_changes;
+    u32 err = 0;
+    // ---- header
+    Cur h(b + bi.sec_off[0], bi.sec_len[0]);
+    u64 np = h.varint();
+    for (u32 p = 0; p < bi.n_peers; p++) {
+        u64 id = 0;
+        for (int k = 0; k < 8; k++) id |= (u64)h.get() << (8 * k);
+        t.peer_id[bi.peer0 + p] = id;
+    }
+    (void)np;
+    // change lengths (N-1 explicit, last inferred)
+    {
+        i64 sum = 0;
+        i32 ctr = (i32)bi.counter_start;
+        for (u32 k = 0; k < N; k++) {
+            i64 len;
+            if (k + 1 < N) { len = (i64)h.varint(); sum += len; }
+            else len = (i64)bi.counter_len - sum;
+            if (len <= 0) err = LB_ERR(DOC_ERR_DECODE);
+            t.ch_block[bi.ch0 + k] = (u32)i;
+            t.ch_counter[bi.ch0 + k] = ctr;
+            t.ch_len[bi.ch0 + k] = (u32)len;
+            ctr += (i32)len;
+        }
+    }
+    // dep_on_self BoolRle (N)
+    {
+        u32 got = 0;
+        u8 state = 0;
+        while (got < N && !h.err) {
+            u64 run = h.varint();
+            if (got + run > N) { h.err = 1; break; }
+            for (u64 q = 0; q < run; q++) t.ch_dep_self[bi.ch0 + got + q] = state;
+            got += (u32)run;
+            state ^= 1;
+        }
+    }
+    // dep_len AnyRle<usize> (N)
+    {
+        u32 got = 0;
+        u64 dep = bi.dep0;
+        while (got < N && !h.err) {
+            i64 sl = h.zigzag();
+            if (sl == 0) { h.err = 1; break; }
+            u64 cnt = sl > 0 ? (u64)sl : (u64)(-sl);
+            if (got + cnt > N) { h.err = 1; break; }
+            u64 v = 0;
+            if (sl > 0) v = h.varint();
+            for (u64 q = 0; q < cnt; q++) {
+                if (sl < 0) v = h.varint();
+                t.ch_dep0[bi.ch0 + got + q] = dep;
+                t.ch_ndeps[bi.ch0 + got + q] = (u32)v;
+                dep += v;
+            }
+            got += (u32)cnt;
+        }
+        if (dep - bi.dep0 != bi.n_deps) h.err = 1;
+    }
+    // dep peer idx AnyRle<usize> (n_deps)
+    {
+        u32 got = 0;
+        while (got < bi.n_deps && !h.err) {
+            i64 sl = h.zigzag();
+            if (sl == 0) { h.err = 1; break; }
+            u64 cnt = sl > 0 ? (u64)sl : (u64)(-sl);
+            if (got + cnt > bi.n_deps) { h.err = 1; break; }
+            u64 v = 0;
+            if (sl > 0) v = h.varint();
+            for (u64 q = 0; q < cnt; q++) {
+                if (sl < 0) v = h.varint();
+                if (v >= bi.n_peers) err = LB_ERR(DOC_ERR_CORRUPT);
+                t.dep_peer_idx[bi.dep0 + got + q] = (u32)v;
+            }
+            got += (u32)cnt;
+        }
+    }
+    // dep counters DeltaOfDelta (n_deps)
+    {
+        DodCur d;
+        d.begin(&h);
+        if (bi.n_deps == 0 && d.has_first) h.err = 1;
+        for (u32 k = 0; k < bi.n_deps; k++) t.dep_counter[bi.dep0 + k] = (i32)d.next(k == 0);
+        d.finish();
+    }
+    // lamports DeltaOfDelta (N-1) ; last = lamport_start + lamport_len - last_len (block_meta_encode.rs:162)
+    {
+        DodCur d;
+        d.begin(&h);
+        for (u32 k = 0; k + 1 < N; k++) t.ch_lamport[bi.ch0 + k] = (u32)d.next(k == 0);
+        d.finish();
+        t.ch_lamport[bi.ch0 + N - 1] = bi.lamport_start + bi.lamport_len - t.ch_len[bi.ch0 + N - 1];
+    }
+    if (h.err || !h.empty()) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    // ---- change meta: timestamps DoD (N) ; commit-message lengths are not needed by the merge path
+    {
+        Cur m(b + bi.sec_off[1], bi.sec_len[1]);
+        DodCur d;
+        d.begin(&m);
+        for (u32 k = 0; k < N; k++) t.ch_ts[bi.ch0 + k] = d.next(k == 0);
+        d.finish();
+        if (m.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    }
+    // ---- keys
+    {
+        Cur k(b + bi.sec_off[3], bi.sec_len[3]);
+        for (u32 q = 0; q < bi.n_keys; q++) {
+            u64 len = k.varint();
+            t.key_off[bi.key0 + q] = bi.off + (u64)(k.p - b);
+            t.key_len[bi.key0 + q] = (u32)len;
+            k.skip(len);
+        }
+        if (k.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    }
+    // ---- cids (row-wise postcard, field count 4)
+    {
+        Cur c(b + bi.sec_off[2], bi.sec_len[2]);
+        (void)c.varint();
+        for (u32 q = 0; q < bi.n_cids; q++) {
+            if (c.varint() != 4) c.err = 1;
+            u8 is_root = c.get();
+            u8 type = c.get();
+            u64 pidx = c.varint();
+            i64 koc = c.zigzag();
+            if (is_root > 1) c.err = 1;
+            if (is_root) { if (koc < 0 || (u64)koc >= bi.n_keys) err = LB_ERR(DOC_ERR_CORRUPT); }
+            else if (pidx >= bi.n_peers) err = LB_ERR(DOC_ERR_CORRUPT);
+            t.cid_root[bi.cid0 + q] = is_root;
+            t.cid_type[bi.cid0 + q] = type;
+            t.cid_peer_idx[bi.cid0 + q] = (u32)pidx;
+            t.cid_koc[bi.cid0 + q] = (i32)koc;
+        }
+        if (c.err || !c.empty()) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    }
+    // ---- delete start ids (3 DeltaRle columns)
+    if (bi.sec_len[6]) {
+        const u8* col[3];
+        u32 cl[3];
+        if (!columnar_open(b + bi.sec_off[6], bi.sec_len[6], 3, col, cl)) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        else {
+            RleCur a(col[0], cl[0], 2), bb(col[1], cl[1], 2), cc(col[2], cl[2], 2);
+            i64 pa = 0, pb = 0, pc = 0;
+            for (u32 q = 0; q < bi.n_dels; q++) {
+                i64 x, y, z;
+                if (!a.next(&x) || !bb.next(&y) || !cc.next(&z)) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
+                pa += x; pb += y; pc += z;
+                if (pa < 0 || (u64)pa >= bi.n_peers || pc == 0) err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
+                t.del_peer_idx[bi.del0 + q] = (u32)pa;
+                t.del_counter[bi.del0 + q] = (i32)pb;
+                t.del_len[bi.del0 + q] = (i32)pc;
+            }
+            if (a.c.err || bb.c.err || cc.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        }
+    } else if (bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    // ---- ops: 4 columns + values walk
+    {
+        const u8* col[4];
+        u32 cl[4];
+        columnar_open(b + bi.sec_off[5], bi.sec_len[5], 4, col, cl);
+        RleCur c0(col[0], cl[0], 2), c1(col[1], cl[1], 2), c2(col[2], cl[2], 0), c3(col[3], cl[3], 1);
+        Cur v(b + bi.sec_off[7], bi.sec_len[7]);
+        i64 acc_c = 0, acc_p = 0;
+        i32 counter = (i32)bi.counter_start;
+        u32 change = 0;
+        u32 ch_first_row = 0;
+        u32 ndel = 0;
+        i32 next_boundary = (i32)bi.counter_start + (i32)t.ch_len[bi.ch0];
+        t.ch_op0[bi.ch0] = bi.op0;
+        for (u32 r = 0; r < bi.n_ops; r++) {
+            i64 dc, dp, vt, ln;
+            if (!c0.next(&dc) || !c1.next(&dp) || !c2.next(&vt) || !c3.next(&ln)) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
+            acc_c += dc;
+            acc_p += dp;
+            if (acc_c < 0 || (u64)acc_c >= bi.n_cids || ln <= 0 || change >= N) { err = err ? err : LB_ERR(DOC_ERR_CORRUPT); break; }
+            u64 row = bi.op0 + r;
+            t.op_cid[row] = (u32)acc_c;
+            t.op_prop[row] = (i32)acc_p;
+            t.op_vtype[row] = (u8)vt;
+            t.op_len[row] = (u32)ln;
+            t.op_counter[row] = counter;
+            t.op_change[row] = (u32)(bi.ch0 + change);
+            const u8* v0 = v.p;
+            // text/list payloads: point past the length prefix where that helps the consumers
+            skip_value(v, (u8)vt);
+            t.op_val_off[row] = bi.off + (u64)(v0 - b);
+            t.op_val_len[row] = (u32)(v.p - v0);
+            t.op_del[row] = (u8)vt == VK_DELETE_SEQ ? (u32)(bi.del0 + ndel++) : 0xFFFFFFFFu;
+            counter += (i32)ln;
+            if (counter >= next_boundary) {
+                t.ch_nops[bi.ch0 + change] = r + 1 - ch_first_row;
+                change++;
+                ch_first_row = r + 1;
+                if (change < N) {
+                    t.ch_op0[bi.ch0 + change] = bi.op0 + r + 1;
+                    next_boundary += (i32)t.ch_len[bi.ch0 + change];
+                }
+            }
+        }
+        if (v.err || !v.empty() || c0.c.err || c1.c.err || c2.c.err || c3.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels))
+            err = LB_ERR(DOC_ERR_CORRUPT);
+    }
+    if (err) blocks[i].err = err;
+}

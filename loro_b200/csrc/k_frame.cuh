@@ -1,0 +1,162 @@
+// loro_b200 -- phase 1: blob header check, xxHash32 checksum, FastUpdates framing.
+//
+// Replaces (reference, relative to crates/loro-internal/src):
+//   encoding.rs:299-330 parse_header_and_body, :278-295 check_checksum
+//   encoding/fast_snapshot.rs:270-288 decode_updates (the ULEB128 length-prefixed block walk)
+// One thread per blob: xxHash32 is a sequential recurrence per 16-byte stripe (4 independent
+// accumulators), so the parallelism is across blobs; loads are 32-bit and the stripe loop is unrolled
+// so that several independent loads are in flight per thread.
+#pragma once
+#include "lb_defs.h"
+
+__device__ __forceinline__ u32 ld32(const u8* p) {  // p is 4-byte aligned
+    return *(const u32*)p;
+}
+
+__device__ u32 xxh32_dev(const u8* d, size_t len, u32 seed) {
+    size_t off = 0;
+    u32 h;
+    if (len >= 16) {
+        u32 v1 = seed + XXP1 + XXP2, v2 = seed + XXP2, v3 = seed, v4 = seed - XXP1;
+        size_t limit = len - 16;
+        // 64-byte steps: 16 independent loads issued before the dependent multiply chains
+        while (off + 64 <= len) {
+            u32 w[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = ld32(d + off + 4 * i);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                v1 = rotl32(v1 + w[4 * s + 0] * XXP2, 13) * XXP1;
+                v2 = rotl32(v2 + w[4 * s + 1] * XXP2, 13) * XXP1;
+                v3 = rotl32(v3 + w[4 * s + 2] * XXP2, 13) * XXP1;
+                v4 = rotl32(v4 + w[4 * s + 3] * XXP2, 13) * XXP1;
+            }
+            off += 64;
+        }
+        while (off <= limit) {
+            v1 = rotl32(v1 + ld32(d + off) * XXP2, 13) * XXP1;
+            v2 = rotl32(v2 + ld32(d + off + 4) * XXP2, 13) * XXP1;
+            v3 = rotl32(v3 + ld32(d + off + 8) * XXP2, 13) * XXP1;
+            v4 = rotl32(v4 + ld32(d + off + 12) * XXP2, 13) * XXP1;
+            off += 16;
+        }
+        h = rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18);
+    } else {
+        h = seed + XXP5;
+    }
+    h += (u32)len;
+    while (off + 4 <= len) {
+        h = rotl32(h + ld32(d + off) * XXP3, 17) * XXP4;
+        off += 4;
+    }
+    while (off < len) {
+        h = rotl32(h + d[off] * XXP5, 11) * XXP1;
+        off++;
+    }
+    h ^= h >> 15;
+    h *= XXP2;
+    h ^= h >> 13;
+    h *= XXP3;
+    h ^= h >> 16;
+    return h;
+}
+
+// thread per blob: validate header + checksum, count blocks.
+__global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restrict__ offs,
+                              const u32* __restrict__ lens, u32 n_docs, DocInfo* __restrict__ docs,
+                              u32* __restrict__ doc_nblocks) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const u8* b = bytes + offs[d];   // blob starts are 16-byte aligned
+    size_t n = lens[d];
+    u32 code = DOC_OK;
+    u32 nb = 0;
+    if (n < 22) code = LB_ERR(DOC_ERR_DECODE);
+    else if (b[0] != 'l' || b[1] != 'o' || b[2] != 'r' || b[3] != 'o') code = LB_ERR(DOC_ERR_DECODE);
+    else {
+        u32 mode = ((u32)b[20] << 8) | b[21];
+        if (mode != 4) code = LB_ERR(DOC_ERR_MODE);
+        else {
+            u32 expect = (u32)b[16] | ((u32)b[17] << 8) | ((u32)b[18] << 16) | ((u32)b[19] << 24);
+            if (xxh32_dev(b + 20, n - 20, XX_SEED_LORO) != expect) code = LB_ERR(DOC_ERR_CHECKSUM);
+            else {
+                Cur c(b + 22, n - 22);
+                while (!c.empty()) {
+                    u64 len = c.varint();
+                    c.skip(len);
+                    if (c.err) break;
+                    nb++;
+                }
+                if (c.err) { code = LB_ERR(DOC_ERR_DECODE); nb = 0; }
+            }
+        }
+    }
+    docs[d].code = code;
+    doc_nblocks[d] = nb;
+}
+
+// thread per blob: emit block descriptors at the scanned positions.
+__global__ void k_frame_fill(const u8* __restrict__ bytes, const u64* __restrict__ offs,
+                             const u32* __restrict__ lens, u32 n_docs, DocInfo* __restrict__ docs,
+                             const u64* __restrict__ doc_block0, BlockInfo* __restrict__ blocks) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    u64 b0 = doc_block0[d];
+    docs[d].b0 = (u32)b0;
+    docs[d].b1 = (u32)doc_block0[d + 1];
+    if (docs[d].code != DOC_OK) return;
+    const u8* b = bytes + offs[d];
+    size_t n = lens[d];
+    Cur c(b + 22, n - 22);
+    u64 i = b0;
+    while (!c.empty()) {
+        u64 len = c.varint();
+        BlockInfo& bi = blocks[i++];
+        bi.doc = d;
+        bi.err = 0;
+        bi.off = offs[d] + (u64)(c.p - b);
+        bi.len = (u32)len;
+        c.skip(len);
+    }
+}
+
+// ------------------------------------------------------------------ generic strided exclusive scan
+// Single CTA (1024 threads) walking the array in tiles with a running carry.  Inputs are u32 fields at
+// in + i*in_stride (bytes), outputs u64 at out + i*out_stride; out[n] (one past) receives the total.
+__global__ void k_excl_scan(const u8* __restrict__ in, size_t in_stride, u8* __restrict__ out,
+                            size_t out_stride, u64 n) {
+    __shared__ u64 warp_tot[32];
+    __shared__ u64 carry_s;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (u64 base = 0; base < n; base += blockDim.x) {
+        u64 i = base + threadIdx.x;
+        u64 v = i < n ? (u64) * (const u32*)(in + i * in_stride) : 0;
+        u64 s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t = __shfl_up_sync(LB_FULL, s, d);
+            if (lane >= d) s += t;
+        }
+        if (lane == 31) warp_tot[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            u64 t = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+            u64 ts = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 u = __shfl_up_sync(LB_FULL, ts, d);
+                if (lane >= d) ts += u;
+            }
+            warp_tot[lane] = ts - t;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        u64 carry = carry_s;
+        if (i < n) *(u64*)(out + i * out_stride) = carry + warp_tot[w] + s - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[w] + s;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *(u64*)(out + n * out_stride) = carry_s;
+}

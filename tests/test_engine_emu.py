@@ -1,0 +1,79 @@
+"""Functional tests of the product's kernels compiled against the SIMT emulator (tests/emu): logic parity
+with the oracle in the GPU-less container.  The same checks run on the real CUDA build in test_engine_gpu.py.
+The emulated library is test infrastructure only -- loro_b200 never loads it by default."""
+import os
+import subprocess
+
+import pytest
+
+import oracle
+from oracle import OracleDoc
+from tests import workloads
+from tests.engine_checks import check_batch_against_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu", "libloro_b200_emu.so")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def build_emu():
+    subprocess.check_call([os.path.join(HERE, "emu", "build_emu.sh")])
+
+
+def test_small_mixed_doc():
+    a = OracleDoc(1)
+    t = a.get_text("text"); a.text_insert(t, 0, "Hello"); a.text_insert(t, 5, " World")
+    l = a.get_list("list"); a.list_insert(l, 0, 1, 2, 3); a.delete(l, 1, 1)
+    m = a.get_map("map"); a.map_set(m, "k", 5); a.map_set(m, "z", "str"); a.map_delete(m, "k")
+    b = check_batch_against_oracle([a.export_updates()], lib_path=EMU)
+    assert b.get_deep_value(0) == {"text": "Hello World", "list": [1, 3], "map": {"z": "str"}}
+    c = b.counters()
+    assert c["atom_ops"] == a.len_ops() and c["docs_ok"] == 1
+
+
+def test_fugue_known_answers():
+    """crates/loro-internal/tests/fugue.rs through the engine."""
+    a, b = OracleDoc(0), OracleDoc(1)
+    for ch in "olleH":
+        a.text_insert(a.get_text("text"), 0, ch)
+    for ch in "!dlroW ":
+        b.text_insert(b.get_text("text"), 0, ch)
+    workloads.merge(a, b)
+    a2, b2, c2 = OracleDoc(0), OracleDoc(1), OracleDoc(2)
+    c2.text_insert(c2.get_text("text"), 0, "2")
+    workloads.merge(a2, c2)
+    a2.text_insert(a2.get_text("text"), 0, "1")
+    b2.text_insert(b2.get_text("text"), 0, "b")
+    workloads.merge(a2, b2)
+    batch = check_batch_against_oracle([a.export_updates(), a2.export_updates()], lib_path=EMU)
+    assert batch.get_deep_value(0) == {"text": "Hello World!"}
+    assert batch.get_deep_value(1) == {"text": "b12"}
+
+
+def test_pending_and_bad_blobs():
+    a = OracleDoc(1)
+    a.text_insert(a.get_text("t"), 0, "abc")
+    a.commit()
+    vv1 = a.oplog_vv()
+    a.text_insert(a.get_text("t"), 3, "def")
+    full, tail = a.export_updates(), a.export_updates(vv1)
+    bad_sum = full[:30] + bytes([full[30] ^ 1]) + full[31:]
+    batch = check_batch_against_oracle([full, tail, bad_sum, b"lor0" + full[4:], full[:10], b""], lib_path=EMU)
+    assert batch.status(1).pending == {1: (3, 6)} and batch.status(1).success == {}
+    assert batch.get_deep_value(1) == {"t": ""}  # root registered at decode time, nothing applied
+    assert [batch.status(i).code for i in range(2, 6)] == [2, 1, 1, 1]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_multi_site_histories(seed):
+    blobs, jsons = [], []
+    for k in range(4):
+        blob, js, vv, _ = workloads.make_doc_history(seed * 100 + k, n_sites=2 + (seed + k) % 3, n_ops=120 + 40 * k)
+        blobs.append(blob)
+        jsons.append(js)
+    check_batch_against_oracle(blobs, lib_path=EMU, expect_json=jsons)
+
+
+def test_c1_two_peer_list_sync_small():
+    blob, js = workloads.c1_two_peer_list(seed=1, n_each=150)
+    check_batch_against_oracle([blob], lib_path=EMU, expect_json=[js])

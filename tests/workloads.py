@@ -1,0 +1,96 @@
+"""Seeded multi-site workloads built with the oracle (test infrastructure).
+
+Mirrors the reference's fuzz strategy (crates/fuzz/src/crdt_fuzzer.rs): N in-process sites apply random
+actions to Text/List/Map containers and sync through FastUpdates blobs.  Returns the full-history blob that
+`export(all_updates)` of a fully synced replica yields plus the oracle's expected results.
+"""
+import random
+
+import oracle
+from oracle import OracleDoc
+
+
+def merge(a, b):
+    return a.import_(b.export_updates(a.oplog_vv()))
+
+
+def random_edit(rnd, d, text, lst, mp, weights=(0.35, 0.15, 0.25, 0.10, 0.12, 0.03), unicode_=True):
+    r = rnd.random()
+    w = weights
+    alphabet = "abcdefg xyz\"\\\n" + ("é中😀" if unicode_ else "")
+    if r < w[0]:
+        n = d.seq_len(text)
+        d.text_insert(text, rnd.randint(0, n), "".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 5))))
+    elif r < w[0] + w[1]:
+        n = d.seq_len(text)
+        if n:
+            p = rnd.randrange(n)
+            d.delete(text, p, min(rnd.randint(1, 4), n - p))
+    elif r < w[0] + w[1] + w[2]:
+        n = d.seq_len(lst)
+        vals = []
+        for _ in range(rnd.randint(1, 3)):
+            k = rnd.random()
+            if k < 0.6:
+                vals.append(rnd.randint(-2**40, 2**40) if rnd.random() < 0.2 else rnd.randint(-100, 100))
+            elif k < 0.85:
+                vals.append("".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 8))))
+            elif k < 0.9:
+                vals.append(None)
+            elif k < 0.95:
+                vals.append(rnd.random() < 0.5)
+            else:
+                vals.append(float(rnd.randint(-1000, 1000)))
+        d.list_insert(lst, rnd.randint(0, n), *vals)
+    elif r < w[0] + w[1] + w[2] + w[3]:
+        n = d.seq_len(lst)
+        if n:
+            p = rnd.randrange(n)
+            d.delete(lst, p, min(rnd.randint(1, 4), n - p))
+    elif r < 1 - w[5]:
+        d.map_set(mp, "k%d" % rnd.randrange(16), rnd.randint(0, 999) if rnd.random() < 0.8 else "v%d" % rnd.randrange(9))
+    else:
+        d.map_delete(mp, "k%d" % rnd.randrange(16))
+
+
+def make_doc_history(seed, n_sites=3, n_ops=300, sync_prob=0.05, commit_prob=0.3, peers=None, unicode_=True):
+    """Returns (blob, expected_json_text, expected_vv, sites) for one document."""
+    rnd = random.Random(seed)
+    peers = peers or [rnd.getrandbits(64) | 1 for _ in range(n_sites)]
+    docs = [OracleDoc(p) for p in peers]
+    hs = [(d.get_text("text"), d.get_list("list"), d.get_map("map")) for d in docs]
+    for _ in range(n_ops):
+        i = rnd.randrange(n_sites)
+        random_edit(rnd, docs[i], *hs[i], unicode_=unicode_)
+        if rnd.random() < commit_prob:
+            docs[i].commit()
+        if n_sites > 1 and rnd.random() < sync_prob:
+            j = rnd.randrange(n_sites)
+            if j != i:
+                merge(docs[j], docs[i])
+    for _ in range(2):
+        for i in range(n_sites):
+            for j in range(n_sites):
+                if i != j:
+                    merge(docs[i], docs[j])
+    blob = docs[0].export_updates()
+    fresh = OracleDoc(1)
+    fresh.import_(blob)
+    return blob, fresh.json_text(), fresh.oplog_vv(), docs
+
+
+def c1_two_peer_list(seed=1, n_each=1000):
+    """BASELINE config C1: 2 peers x n_each List inserts of I64 at random positions, one change per 10 ops;
+    each side imports the other's updates.  Returns (blob_all, json_text)."""
+    rnd = random.Random(seed)
+    a, b = OracleDoc(1), OracleDoc(2)
+    la, lb = a.get_list("list"), b.get_list("list")
+    for k in range(n_each):
+        a.list_insert(la, rnd.randint(0, a.seq_len(la)), rnd.randint(-10**6, 10**6))
+        b.list_insert(lb, rnd.randint(0, b.seq_len(lb)), rnd.randint(-10**6, 10**6))
+        if k % 10 == 9:
+            a.commit(); b.commit()
+    merge(a, b)
+    merge(b, a)
+    assert a.json_text() == b.json_text()
+    return a.export_updates(), a.json_text()
