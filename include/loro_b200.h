@@ -103,10 +103,10 @@ typedef struct lb_batch lb_batch;
 lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out);
 
 /* Same, with the blobs already resident in device memory: `d_bytes` is one device buffer holding all blobs,
- * blob i occupying [offsets[i], offsets[i+1]) (offsets: HOST array of n_docs+1 entries, each a multiple of
- * 16).  Nothing is copied host->device except the offsets. */
-lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, size_t n_docs,
-                                 const lb_options* opt, lb_batch** out);
+ * blob i occupying [offsets[i], offsets[i] + lens[i]) (HOST arrays of n_docs entries; every offset a multiple
+ * of 16).  Nothing is copied host->device except these two small arrays. */
+lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, const uint32_t* lens,
+                                 size_t n_docs, const lb_options* opt, lb_batch** out);
 
 size_t lb_doc_count(const lb_batch* b);
 lb_status lb_doc_status(const lb_batch* b, size_t doc, lb_import_status* out);

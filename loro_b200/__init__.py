@@ -9,7 +9,7 @@ All compute runs in the CUDA library built from loro_b200/csrc (C ABI: include/l
 CPU fallback: importing a batch without the built library or without a CUDA device raises.
 """
 from .api import (Batch, DocError, EngineUnavailable, ImportStatus, import_batch, import_batch_device,
-                  library_path, load_library)
+                  library_path, load_library, pack_blobs)
 
 __all__ = ["Batch", "DocError", "EngineUnavailable", "ImportStatus", "import_batch", "import_batch_device",
-           "library_path", "load_library"]
+           "library_path", "load_library", "pack_blobs"]

@@ -73,8 +73,8 @@ def load_library(path=None):
     L = ctypes.CDLL(path)
     vp = ctypes.c_void_p
     L.lb_import_batch.argtypes = [ctypes.POINTER(_Blob), ctypes.c_size_t, ctypes.POINTER(_Options), ctypes.POINTER(vp)]
-    L.lb_import_batch_device.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_size_t,
-                                         ctypes.POINTER(_Options), ctypes.POINTER(vp)]
+    L.lb_import_batch_device.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32),
+                                         ctypes.c_size_t, ctypes.POINTER(_Options), ctypes.POINTER(vp)]
     L.lb_doc_count.restype = ctypes.c_size_t
     L.lb_doc_count.argtypes = [vp]
     L.lb_doc_status.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(_Status)]
@@ -191,14 +191,39 @@ def import_batch(blobs, device=0, flags=0, lib_path=None):
     return Batch(L, h.value)
 
 
-def import_batch_device(d_bytes_ptr, offsets, device=0, flags=0, lib_path=None, keep=None):
-    """Same with blobs already resident in HBM: `d_bytes_ptr` is a device pointer (int), `offsets` the n+1
-    blob boundaries (multiples of 16)."""
+def import_batch_device(d_bytes_ptr, offsets, lens, device=0, flags=0, lib_path=None, keep=None):
+    """Same with blobs already resident in HBM: `d_bytes_ptr` is a device pointer (int); blob i occupies
+    [offsets[i], offsets[i] + lens[i]) with every offset a multiple of 16."""
     L = load_library(lib_path)
-    n = len(offsets) - 1
-    offs = (ctypes.c_uint64 * (n + 1))(*[int(x) for x in offsets])
+    n = len(offsets)
+    assert len(lens) == n
+    if hasattr(offsets, "ctypes"):  # numpy fast path
+        import numpy as np
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        l_ = np.ascontiguousarray(lens, dtype=np.uint32)
+        offs = o.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+        ls = l_.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        keep = (keep, o, l_)
+    else:
+        offs = (ctypes.c_uint64 * max(n, 1))(*[int(x) for x in offsets])
+        ls = (ctypes.c_uint32 * max(n, 1))(*[int(x) for x in lens])
     opt = _Options(device=device, flags=flags)
     h = ctypes.c_void_p()
-    _check(L, L.lb_import_batch_device(ctypes.c_void_p(d_bytes_ptr), offs, n, ctypes.byref(opt), ctypes.byref(h)),
+    _check(L, L.lb_import_batch_device(ctypes.c_void_p(d_bytes_ptr), offs, ls, n, ctypes.byref(opt), ctypes.byref(h)),
            "lb_import_batch_device")
     return Batch(L, h.value, keep=keep)
+
+
+def pack_blobs(blobs):
+    """Concatenate blobs at 16-byte aligned starts -> (bytes, offsets, lens) for import_batch_device."""
+    import numpy as np
+    lens = np.fromiter((len(b) for b in blobs), dtype=np.uint32, count=len(blobs))
+    padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
+    offs = np.zeros(len(blobs), dtype=np.uint64)
+    if len(blobs):
+        offs[1:] = np.cumsum(padded)[:-1]
+    total = int(padded.sum())
+    buf = np.zeros(total + 64, dtype=np.uint8)
+    for b, o in zip(blobs, offs):
+        buf[int(o):int(o) + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    return buf, offs, lens

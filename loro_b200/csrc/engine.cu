@@ -518,9 +518,9 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
     return LB_OK;
 }
 
-lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, size_t n_docs,
-                                 const lb_options* opt, lb_batch** out) {
-    if (!out || !offsets || (!d_bytes && n_docs)) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
+lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, const uint32_t* blob_lens,
+                                 size_t n_docs, const lb_options* opt, lb_batch** out) {
+    if (!out || ((!offsets || !blob_lens || !d_bytes) && n_docs)) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
     *out = nullptr;
     lb_status s = check_device(opt);
     if (s != LB_OK) return s;
@@ -533,16 +533,12 @@ lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets
         std::vector<u32> lens(n_docs + 1, 0);
         for (size_t i = 0; i < n_docs; i++) {
             if (offsets[i] & 15) { g_last_error = "blob offsets must be multiples of 16"; throw lb_status(LB_ERR_INVALID_ARG); }
-            if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFFFF0ull) {
-                g_last_error = "bad offsets";
-                throw lb_status(LB_ERR_INVALID_ARG);
-            }
             offs[i] = offsets[i];
-            lens[i] = (u32)(offsets[i + 1] - offsets[i]);
+            lens[i] = blob_lens[i];
             b->doc_ids.push_back(i);
             b->counters.blob_bytes += lens[i];
         }
-        offs[n_docs] = offsets[n_docs];
+        offs[n_docs] = n_docs ? offsets[n_docs - 1] + lens[n_docs - 1] : 0;
         CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
         b->d_offs = b->dev.alloc<u64>(n_docs + 1);
         b->d_lens = b->dev.alloc<u32>(n_docs + 1);

@@ -77,3 +77,20 @@ def test_random_multi_site_histories(seed):
 def test_c1_two_peer_list_sync_small():
     blob, js = workloads.c1_two_peer_list(seed=1, n_each=150)
     check_batch_against_oracle([blob], lib_path=EMU, expect_json=[js])
+
+
+def test_device_entry_point_layout():
+    import loro_b200
+    blobs = [workloads.make_doc_history(9000 + k, n_sites=3, n_ops=80)[0] for k in range(5)]
+    host = loro_b200.import_batch(blobs, lib_path=EMU)
+    buf, offs, lens = loro_b200.pack_blobs(blobs)
+    dev = loro_b200.import_batch_device(buf.ctypes.data, offs, lens, lib_path=EMU, keep=buf)
+    for i in range(len(blobs)):
+        assert dev.status(i) == host.status(i)
+        assert dev.json_bytes(i) == host.json_bytes(i)
+    assert dev.counters()["state_hash"] == host.counters()["state_hash"]
+
+
+def test_longer_concurrent_branches():
+    blob, js, _, _ = workloads.make_doc_history(7001, n_sites=3, n_ops=900, sync_prob=0.006)
+    check_batch_against_oracle([blob], lib_path=EMU, expect_json=[js])

@@ -1,0 +1,115 @@
+"""Parity tests proper: the CUDA library on a real B200, through the C ABI, against the oracle.
+
+Every test is marked gpu (skipped in the GPU-less build container, where tests/test_engine_emu.py runs the
+same checks over the emulated build)."""
+import gzip
+import json
+import os
+
+import pytest
+
+import oracle
+from oracle import OracleDoc
+from tests import workloads
+from tests.engine_checks import check_batch_against_oracle
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_library_is_the_cuda_build():
+    import loro_b200
+    assert os.path.exists(loro_b200.library_path())
+    blob, js, _, _ = workloads.make_doc_history(5, n_sites=2, n_ops=60)
+    b = check_batch_against_oracle([blob], expect_json=[js])
+    assert b.timings()["kernel_launches"] > 10
+
+
+def test_small_mixed_and_fugue_known_answers():
+    a = OracleDoc(1)
+    t = a.get_text("text"); a.text_insert(t, 0, "Hello"); a.text_insert(t, 5, " World")
+    l = a.get_list("list"); a.list_insert(l, 0, 1, 2, 3); a.delete(l, 1, 1)
+    m = a.get_map("map"); a.map_set(m, "k", 5); a.map_set(m, "z", "str"); a.map_delete(m, "k")
+    x, y = OracleDoc(0), OracleDoc(1)
+    for ch in "olleH":
+        x.text_insert(x.get_text("text"), 0, ch)
+    for ch in "!dlroW ":
+        y.text_insert(y.get_text("text"), 0, ch)
+    workloads.merge(x, y)
+    a2, b2, c2 = OracleDoc(0), OracleDoc(1), OracleDoc(2)
+    c2.text_insert(c2.get_text("text"), 0, "2")
+    workloads.merge(a2, c2)
+    a2.text_insert(a2.get_text("text"), 0, "1")
+    b2.text_insert(b2.get_text("text"), 0, "b")
+    workloads.merge(a2, b2)
+    batch = check_batch_against_oracle([a.export_updates(), x.export_updates(), a2.export_updates()])
+    assert batch.get_deep_value(0) == {"text": "Hello World", "list": [1, 3], "map": {"z": "str"}}
+    assert batch.get_deep_value(1) == {"text": "Hello World!"}
+    assert batch.get_deep_value(2) == {"text": "b12"}
+
+
+def test_pending_bad_blobs_and_empty_batch():
+    import loro_b200
+    a = OracleDoc(1)
+    a.text_insert(a.get_text("t"), 0, "abc")
+    a.commit()
+    vv1 = a.oplog_vv()
+    a.text_insert(a.get_text("t"), 3, "def")
+    full, tail = a.export_updates(), a.export_updates(vv1)
+    bad_sum = full[:30] + bytes([full[30] ^ 1]) + full[31:]
+    batch = check_batch_against_oracle([full, tail, bad_sum, b"lor0" + full[4:], full[:10], b""])
+    assert batch.status(1).pending == {1: (3, 6)} and batch.status(1).success == {}
+    assert [batch.status(i).code for i in range(2, 6)] == [2, 1, 1, 1]
+    assert loro_b200.import_batch([]).n_docs == 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_multi_site_histories(seed):
+    blobs, jsons = [], []
+    for k in range(48):
+        blob, js, vv, _ = workloads.make_doc_history(seed * 1000 + k, n_sites=2 + (seed + k) % 4, n_ops=150 + 10 * (k % 20))
+        blobs.append(blob)
+        jsons.append(js)
+    check_batch_against_oracle(blobs, expect_json=jsons)
+
+
+def test_c1_two_peer_list_sync():
+    """BASELINE config C1: 2 peers x 1000 List inserts each, import/export plumbing bit-exact."""
+    blob, js = workloads.c1_two_peer_list(seed=1, n_each=1000)
+    check_batch_against_oracle([blob] * 3, expect_json=[js] * 3)
+
+
+def test_long_concurrent_branches():
+    blobs, jsons = [], []
+    for seed in range(6):
+        blob, js, _, _ = workloads.make_doc_history(7000 + seed, n_sites=3, n_ops=2500, sync_prob=0.004)
+        blobs.append(blob)
+        jsons.append(js)
+    check_batch_against_oracle(blobs, expect_json=jsons)
+
+
+def test_automerge_trace_end_content(golden_dir):
+    """BASELINE config C2 shape at small replication: the automerge-paper editing trace (259,778 patches,
+    crates/loro-internal/benches/text_r.rs) must materialise to its recorded endContent."""
+    import loro_b200
+    blob = gzip.open(os.path.join(golden_dir, "automerge_trace_blob.bin.gz"), "rb").read()
+    end = json.load(gzip.open(os.path.join(golden_dir, "automerge_trace.json.gz")))["endContent"]
+    batch = loro_b200.import_batch([blob] * 4)
+    for i in range(4):
+        assert batch.status(i).code == 0
+        assert batch.get_deep_value(i) == {"text": end}
+    assert batch.counters()["atom_ops"] == 4 * 259778
+
+
+def test_device_resident_entry_point_matches_host_path():
+    import torch
+    import loro_b200
+    blobs = [workloads.make_doc_history(9000 + k, n_sites=3, n_ops=200)[0] for k in range(16)]
+    host = loro_b200.import_batch(blobs)
+    buf, offs, lens = loro_b200.pack_blobs(blobs)
+    t = torch.from_numpy(buf).cuda()
+    dev = loro_b200.import_batch_device(t.data_ptr(), offs, lens, keep=t)
+    for i in range(len(blobs)):
+        assert dev.status(i) == host.status(i)
+        assert dev.json_bytes(i) == host.json_bytes(i)
+    assert dev.counters()["state_hash"] == host.counters()["state_hash"]
