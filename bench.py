@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""bench.py -- merged CRDT ops/sec of the batched import hot path (BASELINE.json metric).
+
+One "step" = one pass of the hot path (decode -> causal scan -> eg-walker merge -> deep JSON) over one batch
+of synthetic documents of config C3 (N docs x 10k mixed List/Map atom ops, 3 concurrent
+peers).  `value` is measured with the update blobs already resident in HBM (lb_import_batch_device); `e2e`
+is the same metric through the host-buffer C-ABI call (lb_import_batch: pinned staging + H2D inside the
+timed region, result JSON + status read back to the host).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--docs D] [--ops-per-doc 10000] [--distinct G]
+  python bench.py --impl reference ...     # the CPU arm: the oracle port of the reference path on host cores
+
+Under torchrun (N>1) every rank imports its own shard of documents (weak scaling: per-GPU work fixed) and
+the per-shard summary counters are exchanged with one NCCL all-gather per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "merged CRDT ops/sec (batched docs)"
+UNIT = "ops/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--docs", type=int, default=0, help="documents per GPU (0 = as many of the 100k as the host can generate in ~90 s)")
+    ap.add_argument("--ops-per-doc", type=int, default=10000)
+    ap.add_argument("--peers", type=int, default=3)
+    ap.add_argument("--distinct", type=int, default=0, help="distinct seeded docs generated per GPU; the batch cycles through them (0 = all distinct)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-docs", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def default_docs(args, world):
+    if args.docs:
+        return args.docs
+    cores = max(1, (os.cpu_count() or 1) // max(1, world))
+    # ~1.2 M generated atom ops/s/core; keep generation near 90 s
+    docs = int(cores * 1.2e6 * 90 / args.ops_per_doc)
+    return max(256, min(100000, docs))
+
+
+def make_workload(args, rank, world, n_docs):
+    from loro_b200.workload import C3Batch
+    distinct = args.distinct or n_docs
+    distinct = min(distinct, n_docs)
+    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    t0 = time.time()
+    gen = C3Batch(distinct, n_ops=args.ops_per_doc, n_peers=args.peers, first_doc=rank * n_docs, threads=threads)
+    return gen, distinct, time.time() - t0
+
+
+def cpu_baseline(args, gen, threads=None):
+    """The oracle port of the reference's CPU path on a bounded sample of the same workload."""
+    import oracle
+    import numpy as np
+    threads = threads or (os.cpu_count() or 1)
+    n = args.cpu_sample_docs or min(gen.n_docs, max(64, min(4096, threads * 48)))
+    # oracle.bench_import wants contiguous [off[i], off[i+1]) blobs: re-pack exact lengths
+    blobs = [gen.blob(i) for i in range(n)]
+    buf = b"".join(blobs)
+    o = [0]
+    for b in blobs:
+        o.append(o[-1] + len(b))
+    r = oracle.bench_import(np.frombuffer(buf, dtype=np.uint8), o, threads=threads, want_json=True)
+    return {"value": r["ops"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} docs of the same C3 workload ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON per doc, one doc per task"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    n = args.cpu_sample_docs or max(64, min(4096, threads * 48))
+    ns = argparse.Namespace(**vars(args))
+    ns.distinct = 0
+    gen, _, _ = make_workload(ns, 0, 1, n)
+    steps, warm = args.steps, args.warmup
+    vals = []
+    for s in range(warm + steps):
+        cb = cpu_baseline(args, gen, threads)
+        if s >= warm:
+            vals.append(cb)
+    total_ops_per_s = statistics.mean(v["value"] for v in vals)
+    ms = 1e3 * (gen.atom_ops / total_ops_per_s)
+    line = {"impl": "reference", "metric": METRIC, "value": total_ops_per_s, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"C3: {n} docs x {args.ops_per_doc} mixed List/Map atom ops, {args.peers} peers (bounded sample of the ours-arm workload)"},
+            "cpu_baseline": {"value": total_ops_per_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+            "e2e": {"value": total_ops_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import loro_b200
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n_docs = default_docs(args, world)
+    gen, distinct, gen_s = make_workload(args, rank, world, n_docs)
+    # lay the batch out in HBM: cycle through the distinct docs (each copy has its own bytes in HBM)
+    idx = np.arange(n_docs) % distinct
+    lens = gen.lens[idx].astype(np.uint32)
+    padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
+    offs = np.zeros(n_docs, dtype=np.uint64)
+    offs[1:] = np.cumsum(padded)[:-1]
+    total_bytes = int(padded.sum())
+    src = torch.from_numpy(np.ascontiguousarray(gen.bytes)).to(dev)
+    if distinct == n_docs:
+        d_bytes = src
+        offs = gen.offsets.astype(np.uint64).copy()
+    else:
+        d_bytes = torch.zeros(total_bytes + 64, dtype=torch.uint8, device=dev)
+        for i in range(n_docs):
+            o, n = int(gen.offsets[idx[i]]), int(lens[i])
+            d_bytes[int(offs[i]):int(offs[i]) + n] = src[o:o + n]
+        del src
+    counters_dev = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def step():
+        b = loro_b200.import_batch_device(d_bytes.data_ptr(), offs, lens, device=local, keep=d_bytes)
+        c = b.counters()
+        if world > 1:
+            counters_dev[:4] = torch.tensor([c["atom_ops"], c["docs_ok"], c["pending_changes"], c["state_hash"] & 0x7FFFFFFFFFFFFFFF], device=dev)
+            gathered = [torch.zeros_like(counters_dev) for _ in range(world)]
+            dist.all_gather(gathered, counters_dev)  # the one collective of the path: per-shard summary counters
+        tm = b.timings()
+        b.close()
+        return c, tm
+
+    for _ in range(args.warmup):
+        c, tm = step()
+    assert c["docs_ok"] == n_docs, c
+    atoms_per_step = c["atom_ops"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t_wall = time.time()
+    phase = {}
+    launches = 0
+    for _ in range(args.steps):
+        c, tm = step()
+        launches += tm["kernel_launches"]
+        for k in ("frame", "decode", "resolve", "classify", "integrate", "materialise", "total_device"):
+            phase[k] = phase.get(k, 0.0) + tm[k]
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_ms = (time.time() - t_wall) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    total_atoms = atoms_per_step * world
+    value = total_atoms * args.steps / (dev_ms * 1e-3)
+    ms_per_step = dev_ms / args.steps
+
+    # ---- e2e: host buffers in, JSON + status out, through the public C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        blobs = [gen.blob(int(idx[i])) for i in range(n_docs)]
+        h2d = int(lens.sum())
+        for _ in range(1):
+            b = loro_b200.import_batch(blobs, device=local)
+            b.json_bytes(0)
+            b.close()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        d2h = 0
+        for _ in range(args.steps):
+            b = loro_b200.import_batch(blobs, device=local)
+            b.json_bytes(0)  # pulls the whole JSON buffer of the batch to the host
+            cc = b.counters()
+            d2h = cc["json_bytes"] + n_docs * 256
+            b.close()
+        torch.cuda.synchronize()
+        e_ms = (time.time() - t0) * 1e3
+        te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_atoms * args.steps / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    n_steps = args.steps
+    rows = c["op_rows"]
+    integ_ms = phase["integrate"] / n_steps
+    dec_ms = phase["decode"] / n_steps
+    # list integration = 52 B per run (id, both origins, len read; rank written), runs = op rows
+    integ_bytes = rows * 52
+    dec_bytes = tm["decode_bytes_read"] + tm["decode_bytes_written"]
+    roof = {"bound": "hbm", "kernel": "k_seq_integrate", "achieved": integ_bytes / (integ_ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "share_of_step": integ_ms / (phase["total_device"] / n_steps)}
+    roof["frac"] = roof["achieved"] / peak
+    dec_roof = {"bound": "hbm", "kernel": "k_block_count+k_block_decode", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "traffic": None}
+    dec_roof["frac"] = dec_roof["achieved"] / peak
+    try:
+        import oracle
+        oracle.build()
+        cpu = cpu_baseline(args, gen)
+    except Exception as e:  # the bench must still print its line
+        cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"C3: {n_docs} docs/GPU x {args.ops_per_doc} mixed List/Map atom ops, {args.peers} concurrent peers, "
+                               f"one FastUpdates blob per doc (SURVEY.md 8d)",
+                   "docs_per_gpu": n_docs, "distinct_docs_per_gpu": distinct, "atom_ops_per_step_per_gpu": atoms_per_step,
+                   "op_rows_per_gpu": rows, "blob_bytes_per_gpu": int(lens.sum()), "l2": "inputs_larger_than_L2" if lens.sum() > 126e6 else "inputs fit L2",
+                   "generator_seconds": round(gen_s, 1), "host_cores": os.cpu_count()},
+        "phases_ms": {k: v / n_steps for k, v in phase.items()}, "wall_ms_per_step": wall_ms / n_steps,
+        "roofline": roof, "decode_roofline": dec_roof, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

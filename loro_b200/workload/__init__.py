@@ -1,0 +1,86 @@
+"""Seeded synthetic workloads (inputs for bench.py and the tests), in the reference's FastUpdates format.
+
+Host-side input tooling: nothing here runs inside the measured path, and nothing here uses oracle/."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libloro_workload.so")
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "gen.cpp")
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", _HERE])
+        L = ctypes.CDLL(_LIB)
+        L.lw_generate_c3.restype = ctypes.c_void_p
+        L.lw_generate_c3.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64] + [ctypes.c_int] * 7
+        L.lw_bytes.restype = ctypes.c_void_p
+        L.lw_bytes.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        L.lw_offsets.restype = ctypes.c_void_p
+        L.lw_offsets.argtypes = [ctypes.c_void_p]
+        L.lw_lens.restype = ctypes.c_void_p
+        L.lw_lens.argtypes = [ctypes.c_void_p]
+        L.lw_atoms.restype = ctypes.c_uint64
+        L.lw_atoms.argtypes = [ctypes.c_void_p]
+        L.lw_json.restype = ctypes.c_void_p
+        L.lw_json.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+        L.lw_free.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+class C3Batch:
+    """Config C3: per doc `n_peers` peers, `n_ops` mixed List/Map atom ops (60 % list insert of an
+    I64 or short Str, 15 % list delete of 1-4, 25 % map set on 16 keys with 10 % deletes); peers fork from a
+    common prefix of `prefix_ops`, edit concurrently in bursts and sync pairwise every ~`sync_every` ops;
+    seed = doc index.  One FastUpdates blob per doc = export(all_updates) of a fully synced replica."""
+
+    def __init__(self, n_docs, n_ops=10000, n_peers=3, prefix_ops=1000, sync_every=500, txn_ops=10,
+                 first_doc=0, seed_base=0, want_json=False, threads=None):
+        L = _load()
+        threads = threads or os.cpu_count() or 1
+        self._h = L.lw_generate_c3(seed_base, first_doc, n_docs, n_ops, n_peers, prefix_ops, sync_every, txn_ops,
+                                   1 if want_json else 0, threads)
+        total = ctypes.c_uint64()
+        p = L.lw_bytes(self._h, ctypes.byref(total))
+        self.n_docs = n_docs
+        self.bytes = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(total.value,))
+        self.offsets = np.ctypeslib.as_array(ctypes.cast(L.lw_offsets(self._h), ctypes.POINTER(ctypes.c_uint64)),
+                                             shape=(n_docs,)) if n_docs else np.zeros(0, np.uint64)
+        self.lens = np.ctypeslib.as_array(ctypes.cast(L.lw_lens(self._h), ctypes.POINTER(ctypes.c_uint32)),
+                                          shape=(n_docs,)) if n_docs else np.zeros(0, np.uint32)
+        self.atom_ops = L.lw_atoms(self._h)
+        self.want_json = want_json
+        self.config = dict(n_docs=n_docs, n_ops=n_ops, n_peers=n_peers, prefix_ops=prefix_ops,
+                           sync_every=sync_every, txn_ops=txn_ops, first_doc=first_doc, seed_base=seed_base)
+
+    def blob(self, i):
+        o, n = int(self.offsets[i]), int(self.lens[i])
+        return self.bytes[o:o + n].tobytes()
+
+    def blobs(self):
+        return [self.blob(i) for i in range(self.n_docs)]
+
+    def expected_json(self, i):
+        n = ctypes.c_uint64()
+        p = _load().lw_json(self._h, i, ctypes.byref(n))
+        return ctypes.string_at(p, n.value)
+
+    def close(self):
+        if self._h:
+            _load().lw_free(self._h)
+            self._h = None
+            self.bytes = self.offsets = self.lens = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
