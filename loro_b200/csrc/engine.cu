@@ -309,19 +309,20 @@ void pipeline(lb_batch* b) {
                   ScanJob{(const u8*)span_cap, (u8*)b->d_docs + offsetof(DocInfo, span0), 4, sizeof(DocInfo), D}});
     DocContainer ctot = d2h_one(b, dcont + NC);
     DocInfo dtot2 = d2h_one(b, &b->d_docs[D]);
-    u64 NLEAF = ctot.leaf0, NNODE = ctot.node0, NOUT = ctot.out0, NCVV = ctot.cvv0, NSPAN = dtot2.span0;
+    u64 NLEAF = ctot.leaf0, NNODE = ctot.node0, NOUT = ctot.out0, NCVV = ctot.cvv0;
+    (void)dtot2;
     mark(b);  // [4] classify done
     // ------------------------------------------------------------ phase 5: sequence integration
     SeqPools sp;
     memset(&sp, 0, sizeof(sp));
-    sp.leaf_sid = dv.alloc<u32>(NLEAF * 32); sp.leaf_len = dv.alloc<i32>(NLEAF * 32); sp.leaf_st = dv.alloc<u32>(NLEAF * 32);
+    sp.leaf_peer = dv.alloc<u16>(NLEAF * 32); sp.leaf_ctr = dv.alloc<i32>(NLEAF * 32);
+    sp.leaf_len = dv.alloc<i32>(NLEAF * 32); sp.leaf_st = dv.alloc<u16>(NLEAF * 32);
     sp.leaf_n = dv.alloc<u32>(NLEAF, true); sp.leaf_parent = dv.alloc<u32>(NLEAF); sp.leaf_next = dv.alloc<u32>(NLEAF);
     sp.node_child = dv.alloc<u32>(NNODE * 32); sp.node_vis = dv.alloc<i32>(NNODE * 32);
     sp.node_n = dv.alloc<u32>(NNODE, true); sp.node_parent = dv.alloc<u32>(NNODE);
-    sp.sp_peer = dv.alloc<u16>(NSPAN); sp.sp_ctr = dv.alloc<i32>(NSPAN); sp.sp_len = dv.alloc<i32>(NSPAN);
-    sp.sp_leaf = dv.alloc<u32>(NSPAN); sp.sp_ol_peer = dv.alloc<u16>(NSPAN); sp.sp_ol_ctr = dv.alloc<i32>(NSPAN);
-    sp.sp_or_peer = dv.alloc<u16>(NSPAN); sp.sp_or_ctr = dv.alloc<i32>(NSPAN);
-    sp.atom_sid = dv.alloc<u32>(NATOM);
+    sp.atom_leaf = dv.alloc<u32>(NATOM);
+    sp.a_ol_peer = dv.alloc<u16>(NATOM); sp.a_ol_ctr = dv.alloc<i32>(NATOM);
+    sp.a_or_peer = dv.alloc<u16>(NATOM); sp.a_or_ctr = dv.alloc<i32>(NATOM);
     sp.cvv = dv.alloc<i32>(NCVV, true);
     sp.cont_epoch = dv.alloc<u32>(NC + 1);
     sp.out_row = dv.alloc<u32>(NOUT); sp.out_off = dv.alloc<u32>(NOUT); sp.out_len = dv.alloc<u32>(NOUT);
@@ -329,12 +330,12 @@ void pipeline(lb_batch* b) {
     memset(&sq, 0, sizeof(sq));
     sq.dpeer = b->d_dpeer; sq.dcont = dcont;
     sq.ch_walk = rt.ch_walk; sq.ch_op0 = t.ch_op0; sq.ch_nops = t.ch_nops; sq.ch_peer = rt.ch_peer; sq.ch_vv = rt.ch_vv;
-    sq.ch_order = rt.ch_order; sq.ch_counter = t.ch_counter;
+    sq.ch_order = rt.ch_order; sq.ch_counter = t.ch_counter; sq.ch_ndeps = t.ch_ndeps; sq.ch_dep_self = t.ch_dep_self;
     sq.op_kind = ct.op_kind; sq.op_cidx = ct.op_cidx; sq.op_prop = t.op_prop; sq.op_len = t.op_len;
     sq.op_counter = t.op_counter; sq.op_del = t.op_del; sq.op_change = t.op_change;
     sq.del_peer_idx = t.del_peer_idx; sq.del_counter = t.del_counter; sq.del_len = t.del_len;
     sq.peer_map = rt.peer_map; sq.blocks = blk; sq.ch_block = t.ch_block; sq.atom_row = ct.atom_row;
-    LB_LAUNCH(k_seq_integrate, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, sp, sq);
+    LB_LAUNCH(k_seq_integrate, nblk(D, LB_SEQ_WARPS), 32 * LB_SEQ_WARPS, 0, st, b->d_docs, D, sp, sq);
     tm.kernel_launches += 1;
     mark(b);  // [5] integrate done
     // ------------------------------------------------------------ phase 6: JSON
@@ -447,6 +448,15 @@ lb_status check_device(const lb_options* opt) {
         g_last_error = "cudaSetDevice failed";
         return LB_ERR_CUDA;
     }
+#ifndef LB_SIMT_EMU
+    {   // keep freed table memory cached in the stream-ordered pool between batches
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+#endif
     return LB_OK;
 }
 

@@ -94,3 +94,28 @@ def test_device_entry_point_layout():
 def test_longer_concurrent_branches():
     blob, js, _, _ = workloads.make_doc_history(7001, n_sites=3, n_ops=900, sync_prob=0.006)
     check_batch_against_oracle([blob], lib_path=EMU, expect_json=[js])
+
+
+def test_automerge_trace_end_content(golden_dir):
+    """C2 shape on one document (259,778 patches): exercises multi-level trees and node spill past the
+    shared-memory cache."""
+    import gzip, json
+    import loro_b200
+    blob = gzip.open(os.path.join(golden_dir, "automerge_trace_blob.bin.gz"), "rb").read()
+    end = json.load(gzip.open(os.path.join(golden_dir, "automerge_trace.json.gz")))["endContent"]
+    b = loro_b200.import_batch([blob], lib_path=EMU)
+    assert b.status(0).code == 0 and b.get_deep_value(0) == {"text": end}
+    assert b.counters()["atom_ops"] == 259778
+
+
+def test_generator_three_way_agreement():
+    """The workload generator's origin-based Fugue replicas, the oracle's eg-walker replay and the engine's
+    kernels must agree on the final state of C3 documents (three independent formulations)."""
+    import loro_b200
+    from loro_b200.workload import C3Batch
+    gen = C3Batch(6, n_ops=1200, want_json=True, threads=4)
+    blobs = gen.blobs()
+    batch = check_batch_against_oracle(blobs, lib_path=EMU)
+    for i in range(gen.n_docs):
+        assert batch.json_bytes(i) == gen.expected_json(i)
+    assert batch.counters()["atom_ops"] == gen.atom_ops
