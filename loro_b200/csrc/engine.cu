@@ -9,6 +9,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 #include "lb_defs.h"
 #include "k_frame.cuh"
@@ -16,6 +17,7 @@
 #include "k_resolve.cuh"
 #include "k_classify.cuh"
 #include "k_seq.cuh"
+#include "k_seq_thread.cuh"
 #include "k_state.cuh"
 
 static thread_local std::string g_last_error;
@@ -300,7 +302,12 @@ void pipeline(lb_batch* b) {
     u32* cap_out = dv.alloc<u32>(NC + 1, true);
     u32* cap_cvv = dv.alloc<u32>(NC + 1, true);
     u32* span_cap = dv.alloc<u32>(D + 1, true);
-    LB_LAUNCH(k_container_caps, nblk(D), TPB, 0, st, b->d_docs, D, dcont, cap_leaf, cap_node, cap_out, cap_cvv, span_cap);
+    // mapping of the integration phase: one thread per document for large batches (every document advances
+    // concurrently), one warp per document for small ones.  LB_SEQ_MODE=warp|thread overrides (tests).
+    bool thread_mode = D >= 1024;
+    if (const char* m = getenv("LB_SEQ_MODE")) thread_mode = m[0] == 't';
+    u32 leaf_w = thread_mode ? LB_TF : 32;
+    LB_LAUNCH(k_container_caps, nblk(D), TPB, 0, st, b->d_docs, D, dcont, cap_leaf, cap_node, cap_out, cap_cvv, span_cap, leaf_w);
     tm.kernel_launches += 1;
     run_scans(b, {ScanJob{(const u8*)cap_leaf, (u8*)dcont + offsetof(DocContainer, leaf0), 4, sizeof(DocContainer), NC},
                   ScanJob{(const u8*)cap_node, (u8*)dcont + offsetof(DocContainer, node0), 4, sizeof(DocContainer), NC},
@@ -315,10 +322,10 @@ void pipeline(lb_batch* b) {
     // ------------------------------------------------------------ phase 5: sequence integration
     SeqPools sp;
     memset(&sp, 0, sizeof(sp));
-    sp.leaf_peer = dv.alloc<u16>(NLEAF * 32); sp.leaf_ctr = dv.alloc<i32>(NLEAF * 32);
-    sp.leaf_len = dv.alloc<i32>(NLEAF * 32); sp.leaf_st = dv.alloc<u16>(NLEAF * 32);
+    sp.leaf_peer = dv.alloc<u16>(NLEAF * leaf_w); sp.leaf_ctr = dv.alloc<i32>(NLEAF * leaf_w);
+    sp.leaf_len = dv.alloc<i32>(NLEAF * leaf_w); sp.leaf_st = dv.alloc<u16>(NLEAF * leaf_w);
     sp.leaf_n = dv.alloc<u32>(NLEAF, true); sp.leaf_parent = dv.alloc<u32>(NLEAF); sp.leaf_next = dv.alloc<u32>(NLEAF);
-    sp.node_child = dv.alloc<u32>(NNODE * 32); sp.node_vis = dv.alloc<i32>(NNODE * 32);
+    sp.node_child = dv.alloc<u32>(NNODE * leaf_w); sp.node_vis = dv.alloc<i32>(NNODE * leaf_w);
     sp.node_n = dv.alloc<u32>(NNODE, true); sp.node_parent = dv.alloc<u32>(NNODE);
     sp.atom_leaf = dv.alloc<u32>(NATOM);
     sp.a_ol_peer = dv.alloc<u16>(NATOM); sp.a_ol_ctr = dv.alloc<i32>(NATOM);
@@ -335,7 +342,8 @@ void pipeline(lb_batch* b) {
     sq.op_counter = t.op_counter; sq.op_del = t.op_del; sq.op_change = t.op_change;
     sq.del_peer_idx = t.del_peer_idx; sq.del_counter = t.del_counter; sq.del_len = t.del_len;
     sq.peer_map = rt.peer_map; sq.blocks = blk; sq.ch_block = t.ch_block; sq.atom_row = ct.atom_row;
-    LB_LAUNCH(k_seq_integrate, nblk(D, LB_SEQ_WARPS), 32 * LB_SEQ_WARPS, 0, st, b->d_docs, D, sp, sq);
+    if (thread_mode) LB_LAUNCH(k_seq_integrate_thread, nblk(D, 64), 64, 0, st, b->d_docs, D, sp, sq);
+    else LB_LAUNCH(k_seq_integrate, nblk(D, LB_SEQ_WARPS), 32 * LB_SEQ_WARPS, 0, st, b->d_docs, D, sp, sq);
     tm.kernel_launches += 1;
     mark(b);  // [5] integrate done
     // ------------------------------------------------------------ phase 6: JSON

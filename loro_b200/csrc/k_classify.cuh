@@ -99,7 +99,7 @@ __global__ void k_map_winner(const DocInfo* __restrict__ docs, u64 n_rows, Class
 __global__ void k_container_caps(DocInfo* __restrict__ docs, u32 n_docs, DocContainer* __restrict__ dcont,
                                  u32* __restrict__ cap_leaf, u32* __restrict__ cap_node,
                                  u32* __restrict__ cap_out, u32* __restrict__ cap_cvv,
-                                 u32* __restrict__ doc_span_cap) {
+                                 u32* __restrict__ doc_span_cap, u32 leaf_w) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     const DocInfo& di = docs[d];
@@ -115,8 +115,9 @@ __global__ void k_container_caps(DocInfo* __restrict__ docs, u32 n_docs, DocCont
                 u64 spans = 3ull * dc.n_ins_rows + 2ull * dc.n_del_rows + 2ull * ((u64)di.n_applied + di.n_deps) + 8;
                 u64 by_atoms = (u64)dc.n_ins_atoms + 2;
                 if (by_atoms < spans) spans = by_atoms;
-                cl = (u32)(spans / 16 + 4);
-                cn = cl / 15 + 8;
+                // leaves split at leaf_w slots into halves, nodes likewise: minimum fill leaf_w / 2
+                cl = (u32)(spans / (leaf_w / 2) + 4);
+                cn = cl / (leaf_w / 2 - 1) + 8;
                 co = (u32)spans;
                 cv = di.P;
                 spans_total += (u32)spans;
