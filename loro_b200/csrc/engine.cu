@@ -322,8 +322,11 @@ void pipeline(lb_batch* b) {
     // ------------------------------------------------------------ phase 5: sequence integration
     SeqPools sp;
     memset(&sp, 0, sizeof(sp));
-    sp.leaf_peer = dv.alloc<u16>(NLEAF * leaf_w); sp.leaf_ctr = dv.alloc<i32>(NLEAF * leaf_w);
-    sp.leaf_len = dv.alloc<i32>(NLEAF * leaf_w); sp.leaf_st = dv.alloc<u16>(NLEAF * leaf_w);
+    if (thread_mode) sp.tleaf = dv.alloc<uint4>(NLEAF * leaf_w);
+    else {
+        sp.leaf_peer = dv.alloc<u16>(NLEAF * leaf_w); sp.leaf_ctr = dv.alloc<i32>(NLEAF * leaf_w);
+        sp.leaf_len = dv.alloc<i32>(NLEAF * leaf_w); sp.leaf_st = dv.alloc<u16>(NLEAF * leaf_w);
+    }
     sp.leaf_n = dv.alloc<u32>(NLEAF, true); sp.leaf_parent = dv.alloc<u32>(NLEAF); sp.leaf_next = dv.alloc<u32>(NLEAF);
     sp.node_child = dv.alloc<u32>(NNODE * leaf_w); sp.node_vis = dv.alloc<i32>(NNODE * leaf_w);
     sp.node_n = dv.alloc<u32>(NNODE, true); sp.node_parent = dv.alloc<u32>(NNODE);

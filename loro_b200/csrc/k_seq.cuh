@@ -34,6 +34,7 @@
 struct SeqPools {
     // leaves
     u16* leaf_peer; i32* leaf_ctr; i32* leaf_len; u16* leaf_st; u32* leaf_n; u32* leaf_parent; u32* leaf_next;
+    uint4* tleaf;   // thread-per-document layout: one uint4 per slot (k_seq_thread.cuh)
     // internal nodes (global home; nodes < NS of the active container are cached in shared memory)
     u32* node_child; i32* node_vis; u32* node_n; u32* node_parent;
     // per-document atom-indexed arrays

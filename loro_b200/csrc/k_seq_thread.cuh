@@ -24,15 +24,51 @@ struct TSeq {
     __device__ __forceinline__ u64 atom_index(u32 peer, i32 ctr) const {
         return di->atom0 + t->dpeer[di->peer0 + peer].atom_base + (u32)ctr;
     }
+    // leaf slot = one uint4 {x: ctr, y: len, z: peer | st << 16, w: unused}; a leaf is 16 slots = 256 B
     __device__ __forceinline__ u64 ls(u32 leaf, int slot) const { return (leaf0 + leaf) * LB_TF + slot; }
     __device__ __forceinline__ u64 ns(u32 nd, int i) const { return (node0 + nd) * LB_TF + i; }
-    __device__ __forceinline__ i32 slot_vis(u64 si) const { return p.leaf_st[si] == 0 ? p.leaf_len[si] : 0; }
+    static __device__ __forceinline__ u32 s_peer(const uint4& v) { return v.z & 0xFFFFu; }
+    static __device__ __forceinline__ u32 s_st(const uint4& v) { return v.z >> 16; }
+    static __device__ __forceinline__ i32 s_ctr(const uint4& v) { return (i32)v.x; }
+    static __device__ __forceinline__ i32 s_len(const uint4& v) { return (i32)v.y; }
+    static __device__ __forceinline__ i32 s_vis(const uint4& v) { return (v.z >> 16) == 0 ? (i32)v.y : 0; }
+    static __device__ __forceinline__ uint4 mk_slot(u32 peer, i32 ctr, i32 len, u32 st) {
+        uint4 v; v.x = (u32)ctr; v.y = (u32)len; v.z = (peer & 0xFFFFu) | (st << 16); v.w = 0; return v;
+    }
+    // whole-leaf image in thread-local storage: all 16 loads are independent -> one memory round trip
+    __device__ __forceinline__ u32 leaf_load(u32 leaf, uint4* L) const {
+        const uint4* g = p.tleaf + (leaf0 + leaf) * LB_TF;
+#pragma unroll
+        for (int i = 0; i < LB_TF; i++) L[i] = g[i];
+        return p.leaf_n[leaf0 + leaf];
+    }
+    __device__ __forceinline__ void leaf_store(u32 leaf, const uint4* L, u32 n) {
+        uint4* g = p.tleaf + (leaf0 + leaf) * LB_TF;
+#pragma unroll
+        for (int i = 0; i < LB_TF; i++) if (i < (int)n) g[i] = L[i];
+        p.leaf_n[leaf0 + leaf] = n;
+    }
+    // node image: child[16] + vis[16] via vector loads
+    __device__ __forceinline__ u32 node_load_vis(u32 nd, i32* v) const {
+        const int4* g = (const int4*)(p.node_vis + (node0 + nd) * LB_TF);
+#pragma unroll
+        for (int i = 0; i < LB_TF / 4; i++) { int4 x = g[i]; v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w; }
+        return p.node_n[node0 + nd];
+    }
+    __device__ __forceinline__ void node_load_child(u32 nd, u32* c) const {
+        const uint4* g = (const uint4*)(p.node_child + (node0 + nd) * LB_TF);
+#pragma unroll
+        for (int i = 0; i < LB_TF / 4; i++) { uint4 x = g[i]; c[4 * i] = x.x; c[4 * i + 1] = x.y; c[4 * i + 2] = x.z; c[4 * i + 3] = x.w; }
+    }
 
     __device__ int nd_find(u32 nd, u32 child) const {
+        u32 c[LB_TF];
+        node_load_child(nd, c);
         u32 n = p.node_n[node0 + nd];
-        for (u32 i = 0; i < n; i++)
-            if (p.node_child[ns(nd, i)] == child) return (int)i;
-        return -1;
+        int idx = -1;
+#pragma unroll
+        for (int i = 0; i < LB_TF; i++) if (i < (int)n && c[i] == child && idx < 0) idx = i;
+        return idx;
     }
     __device__ void add_vis(u32 leaf, i32 delta) {
         if (delta == 0) return;
@@ -47,9 +83,11 @@ struct TSeq {
         }
     }
     __device__ i32 node_total(u32 nd) const {
-        u32 n = p.node_n[node0 + nd];
+        i32 v[LB_TF];
+        u32 n = node_load_vis(nd, v);
         i32 s = 0;
-        for (u32 i = 0; i < n; i++) s += p.node_vis[ns(nd, i)];
+#pragma unroll
+        for (int i = 0; i < LB_TF; i++) if (i < (int)n) s += v[i];
         return s;
     }
     __device__ void node_insert_no_split(u32 nd, int after, u32 child, i32 vis, bool kids_are_leaves) {
@@ -107,35 +145,37 @@ struct TSeq {
             kids_are_leaves = false;
         }
     }
+    static __device__ __forceinline__ int slot_in(const uint4* L, u32 n, u32 peer, i32 c) {
+        int r = -1;
+#pragma unroll
+        for (int s = 0; s < LB_TF; s++)
+            if (s < (int)n && r < 0 && s_peer(L[s]) == (peer & 0xFFFFu) && c >= s_ctr(L[s]) && c < s_ctr(L[s]) + s_len(L[s])) r = s;
+        return r;
+    }
     __device__ int slot_of(u32 leaf, u32 peer, i32 c) const {
-        u32 n = p.leaf_n[leaf0 + leaf];
-        for (u32 s = 0; s < n; s++) {
-            u64 si = ls(leaf, s);
-            if (p.leaf_peer[si] == (u16)peer) {
-                i32 sc = p.leaf_ctr[si];
-                if (c >= sc && c < sc + p.leaf_len[si]) return (int)s;
-            }
-        }
-        return -1;
+        uint4 L[LB_TF];
+        u32 n = leaf_load(leaf, L);
+        return slot_in(L, n, peer, c);
     }
     __device__ void leaf_split(u32 leaf) {
         if (n_leaves >= leaf_cap) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
         u32 nl = n_leaves++;
         const int H = LB_TF / 2;
+        uint4 L[LB_TF];
+        leaf_load(leaf, L);
         i32 moved = 0;
+        uint4* g = p.tleaf + (leaf0 + nl) * LB_TF;
+#pragma unroll
         for (int s = H; s < LB_TF; s++) {
-            u64 a = ls(leaf, s), b = ls(nl, s - H);
-            u16 pe = p.leaf_peer[a];
-            i32 ct = p.leaf_ctr[a], ln = p.leaf_len[a];
-            u16 st = p.leaf_st[a];
-            p.leaf_peer[b] = pe;
-            p.leaf_ctr[b] = ct;
-            p.leaf_len[b] = ln;
-            p.leaf_st[b] = st;
-            if (st == 0) moved += ln;
+            g[s - H] = L[s];
+            moved += s_vis(L[s]);
+        }
+        for (int s = H; s < LB_TF; s++) {
+            u32 pe = s_peer(L[s]);
             if (pe == PEER_UNKNOWN) unk_leaf = nl;
             else {
-                u64 a0 = atom_index(pe, ct);
+                u64 a0 = atom_index(pe, s_ctr(L[s]));
+                i32 ln = s_len(L[s]);
                 for (i32 i = 0; i < ln; i++) p.atom_leaf[a0 + i] = nl;
             }
         }
@@ -149,51 +189,54 @@ struct TSeq {
         p.node_vis[ns(parent, idx)] -= moved;
         node_insert(parent, idx, nl, moved, true);
     }
-    // open one slot at index `at` of `leaf` (splitting first if full); (leaf, at) updated to the opened slot
-    __device__ void leaf_open(u32& leaf, int& at) {
+    // insert slot value `nv` at index `at` of `leaf` (splitting first if full); returns the leaf that holds it
+    __device__ u32 leaf_insert(u32 leaf, int at, uint4 nv) {
         if (p.leaf_n[leaf0 + leaf] >= LB_TF) {
             leaf_split(leaf);
-            if (err) return;
+            if (err) return leaf;
             if (at > LB_TF / 2) { leaf = p.leaf_next[leaf0 + leaf]; at -= LB_TF / 2; }
         }
-        u32 n = p.leaf_n[leaf0 + leaf];
-        for (int s = (int)n - 1; s >= at; s--) {
-            u64 a = ls(leaf, s), b = ls(leaf, s + 1);
-            p.leaf_peer[b] = p.leaf_peer[a];
-            p.leaf_ctr[b] = p.leaf_ctr[a];
-            p.leaf_len[b] = p.leaf_len[a];
-            p.leaf_st[b] = p.leaf_st[a];
-        }
-        p.leaf_n[leaf0 + leaf] = n + 1;
+        uint4 L[LB_TF];
+        u32 n = leaf_load(leaf, L);
+#pragma unroll
+        for (int s = LB_TF - 1; s > 0; s--) if (s > at && s <= (int)n) L[s] = L[s - 1];
+#pragma unroll
+        for (int s = 0; s < LB_TF; s++) if (s == at) L[s] = nv;
+        leaf_store(leaf, L, n + 1);
+        return leaf;
     }
     // split the span containing atom (peer, c) right before that atom (no-op at a span start)
     __device__ void split_before(u32 peer, i32 c) {
         u32 leaf = p.atom_leaf[atom_index(peer, c)];
-        int slot = slot_of(leaf, peer, c);
+        uint4 L[LB_TF];
+        u32 n = leaf_load(leaf, L);
+        int slot = slot_in(L, n, peer, c);
         if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-        i32 ctr = p.leaf_ctr[ls(leaf, slot)];
+        uint4 sv = L[0];
+#pragma unroll
+        for (int s = 0; s < LB_TF; s++) if (s == slot) sv = L[s];
+        i32 ctr = s_ctr(sv);
         if (ctr == c) return;
-        if (p.leaf_n[leaf0 + leaf] >= LB_TF) {
+        if (n >= LB_TF) {
             leaf_split(leaf);
             if (err) return;
             leaf = p.atom_leaf[atom_index(peer, c)];
-            slot = slot_of(leaf, peer, c);
+            n = leaf_load(leaf, L);
+            slot = slot_in(L, n, peer, c);
             if (slot < 0) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
         }
-        u64 si = ls(leaf, slot);
-        i32 len = p.leaf_len[si];
-        u16 st = p.leaf_st[si];
+        i32 len = s_len(sv);
+        u32 st = s_st(sv);
         i32 k = c - ctr;
-        int at = slot + 1;
-        u32 lf = leaf;
-        leaf_open(lf, at);   // room is guaranteed: no split happens here
-        if (err) return;
-        p.leaf_len[si] = k;
-        u64 ni = ls(lf, at);
-        p.leaf_peer[ni] = (u16)peer;
-        p.leaf_ctr[ni] = c;
-        p.leaf_len[ni] = len - k;
-        p.leaf_st[ni] = st;
+        // shorten the left part in place, open the next slot for the right part
+#pragma unroll
+        for (int s = LB_TF - 1; s > 0; s--) if (s > slot + 1 && s <= (int)n) L[s] = L[s - 1];
+#pragma unroll
+        for (int s = 0; s < LB_TF; s++) {
+            if (s == slot) L[s] = mk_slot(peer, ctr, k, st);
+            if (s == slot + 1) L[s] = mk_slot(peer, c, len - k, st);
+        }
+        leaf_store(leaf, L, n + 1);
         u64 a_old = atom_index(peer, ctr), a_new = atom_index(peer, c);
         p.a_ol_peer[a_new] = (u16)peer;
         p.a_ol_ctr[a_new] = c - 1;
@@ -204,30 +247,37 @@ struct TSeq {
         i32 c = lo;
         while (c < hi && !err) {
             u64 ai = atom_index(peer, c);
-            if (p.atom_leaf[ai] == LEAF_NONE) { c++; continue; }
-            split_before(peer, c);
-            if (err) return;
             u32 leaf = p.atom_leaf[ai];
-            int slot = slot_of(leaf, peer, c);
+            if (leaf == LEAF_NONE) { c++; continue; }
+            uint4 L[LB_TF];
+            u32 n = leaf_load(leaf, L);
+            int slot = slot_in(L, n, peer, c);
             if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-            i32 s_len = p.leaf_len[ls(leaf, slot)];
-            if (c + s_len > hi) {
-                split_before(peer, hi);
+            uint4 sv = L[0];
+#pragma unroll
+            for (int s = 0; s < LB_TF; s++) if (s == slot) sv = L[s];
+            if (s_ctr(sv) != c || c + s_len(sv) > hi) {
+                // boundaries do not line up with the span: cut, then look again
+                if (s_ctr(sv) != c) split_before(peer, c);
+                if (!err && s_ctr(sv) + s_len(sv) > hi) split_before(peer, hi);
                 if (err) return;
-                s_len = hi - c;
                 leaf = p.atom_leaf[ai];
-                slot = slot_of(leaf, peer, c);
+                n = leaf_load(leaf, L);
+                slot = slot_in(L, n, peer, c);
+                if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+#pragma unroll
+                for (int s = 0; s < LB_TF; s++) if (s == slot) sv = L[s];
             }
-            u64 si = ls(leaf, slot);
-            u16 st = p.leaf_st[si];
-            u16 nst = st;
+            i32 s_len_ = s_len(sv);
+            u32 st = s_st(sv);
+            u32 nst = st;
             if (set_future == 1) nst |= ST_FUTURE;
-            if (set_future == 0) nst &= (u16)~ST_FUTURE;
-            nst = (u16)((nst & ST_FUTURE) | (((nst & 0x7FFF) + del_diff) & 0x7FFF));
-            p.leaf_st[si] = nst;
-            i32 before = st == 0 ? s_len : 0, after = nst == 0 ? s_len : 0;
+            if (set_future == 0) nst &= ~(u32)ST_FUTURE;
+            nst = (nst & ST_FUTURE) | (((nst & 0x7FFF) + del_diff) & 0x7FFF);
+            p.tleaf[ls(leaf, slot)] = mk_slot(peer, c, s_len_, nst);
+            i32 before = st == 0 ? s_len_ : 0, after = nst == 0 ? s_len_ : 0;
             add_vis(leaf, after - before);
-            c += s_len;
+            c += s_len_;
         }
     }
     __device__ void toggle_ops(u32 peer, i32 a, i32 b, int dir) {
@@ -284,7 +334,7 @@ struct TSeq {
         if (peer == PEER_UNKNOWN) {
             u32 n = p.leaf_n[leaf0 + unk_leaf];
             for (u32 s = 0; s < n; s++)
-                if (p.leaf_peer[ls(unk_leaf, s)] == PEER_UNKNOWN) return order_key(unk_leaf, (int)s);
+                if (s_peer(p.tleaf[ls(unk_leaf, s)]) == PEER_UNKNOWN) return order_key(unk_leaf, (int)s);
             return ~0ull;
         }
         u32 leaf = p.atom_leaf[atom_index(peer, c)];
@@ -294,7 +344,7 @@ struct TSeq {
         if (peer == PEER_UNKNOWN) { *op = PEER_NONE; *oc = -1; return; }
         u32 leaf = p.atom_leaf[atom_index(peer, c)];
         int slot = slot_of(leaf, peer, c);
-        if (p.leaf_ctr[ls(leaf, slot)] == c) { u64 a = atom_index(peer, c); *op = p.a_ol_peer[a]; *oc = p.a_ol_ctr[a]; }
+        if (s_ctr(p.tleaf[ls(leaf, slot)]) == c) { u64 a = atom_index(peer, c); *op = p.a_ol_peer[a]; *oc = p.a_ol_ctr[a]; }
         else { *op = (u16)peer; *oc = c - 1; }
     }
 
@@ -307,38 +357,48 @@ struct TSeq {
         i32 ol_ctr = -1;
         u32 cur_peer = PEER_NONE;
         i32 cur_ctr = 0, cur_len = 0;
+        uint4 L[LB_TF];
+        u32 ln_ = 0;
         if (pos > 0) {
             i32 rem = pos;
             u32 nd = root;
             for (u32 lvl = height; lvl >= 1; lvl--) {
-                u32 n = p.node_n[node0 + nd];
-                u32 i = 0;
-                for (; i < n; i++) {
-                    i32 v = p.node_vis[ns(nd, i)];
-                    if (rem <= v) break;
-                    rem -= v;
+                i32 v[LB_TF];
+                u32 n = node_load_vis(nd, v);
+                int idx = -1;
+#pragma unroll
+                for (int i = 0; i < LB_TF; i++) {
+                    if (i < (int)n && idx < 0) {
+                        if (rem <= v[i]) idx = i; else rem -= v[i];
+                    }
                 }
-                if (i >= n) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-                nd = p.node_child[ns(nd, i)];
+                if (idx < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+                nd = p.node_child[ns(nd, idx)];
             }
             leaf = nd;
-            u32 n = p.leaf_n[leaf0 + leaf];
-            u32 s = 0;
-            for (; s < n; s++) {
-                i32 v = slot_vis(ls(leaf, s));
-                if (v > 0 && rem <= v) break;
-                rem -= v;
+            ln_ = leaf_load(leaf, L);
+            int found = -1;
+#pragma unroll
+            for (int s = 0; s < LB_TF; s++) {
+                if (s < (int)ln_ && found < 0) {
+                    i32 v = s_vis(L[s]);
+                    if (v > 0 && rem <= v) found = s; else rem -= v;
+                }
             }
-            if (s >= n) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-            slot = (int)s;
+            if (found < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+            slot = found;
             off = rem;
-            u64 si = ls(leaf, slot);
-            cur_peer = p.leaf_peer[si];
-            cur_ctr = p.leaf_ctr[si];
-            cur_len = p.leaf_len[si];
+            uint4 sv = L[0];
+#pragma unroll
+            for (int s = 0; s < LB_TF; s++) if (s == slot) sv = L[s];
+            cur_peer = s_peer(sv);
+            cur_ctr = s_ctr(sv);
+            cur_len = s_len(sv);
             if (cur_peer == PEER_UNKNOWN) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
             ol_peer = (u16)cur_peer;
             ol_ctr = cur_ctr + off - 1;
+        } else {
+            ln_ = leaf_load(leaf, L);
         }
         // origin_right + in-between (future) spans
         u16 or_peer = PEER_NONE;
@@ -355,23 +415,28 @@ struct TSeq {
             u32 l2 = leaf;
             int from = scan_from;
             bool found = false;
-            while (l2 != LEAF_NONE && !found) {
-                u32 n = p.leaf_n[leaf0 + l2];
-                for (int s = from; s < (int)n; s++) {
-                    u64 si = ls(l2, s);
-                    if (!(p.leaf_st[si] & ST_FUTURE)) {
-                        or_peer = p.leaf_peer[si];
-                        or_ctr = p.leaf_ctr[si];
-                        pr_leaf = l2;
-                        pr_slot = s;
-                        pr_valid = true;
-                        found = true;
-                        break;
+            u32 n2 = ln_;
+            while (true) {
+#pragma unroll
+                for (int s = 0; s < LB_TF; s++) {
+                    if (s >= from && s < (int)n2 && !found) {
+                        if (!(s_st(L[s]) & ST_FUTURE)) {
+                            or_peer = (u16)s_peer(L[s]);
+                            or_ctr = s_ctr(L[s]);
+                            pr_leaf = l2;
+                            pr_slot = s;
+                            pr_valid = true;
+                            found = true;
+                        } else n_between++;
                     }
-                    n_between++;
                 }
-                if (!found) { l2 = p.leaf_next[leaf0 + l2]; from = 0; }
+                if (found) break;
+                l2 = p.leaf_next[leaf0 + l2];
+                if (l2 == LEAF_NONE) break;
+                from = 0;
+                n2 = leaf_load(l2, L);
             }
+            if (l2 != leaf) ln_ = leaf_load(leaf, L);   // restore the image of the cursor leaf
         }
         bool after_valid = false;
         u32 after_peer = 0;
@@ -397,9 +462,9 @@ struct TSeq {
             while (l2 != LEAF_NONE && seen < n_between && !stop) {
                 u32 n = p.leaf_n[leaf0 + l2];
                 for (int s = from; s < (int)n && seen < n_between && !stop; s++) {
-                    u64 si = ls(l2, s);
-                    u32 o_peer = p.leaf_peer[si];
-                    i32 o_ctr = p.leaf_ctr[si];
+                    uint4 ov = p.tleaf[ls(l2, s)];
+                    u32 o_peer = s_peer(ov);
+                    i32 o_ctr = s_ctr(ov);
                     seen++;
                     u64 o_key = order_key(l2, s);
                     if (!have_first) { first_key = o_key; have_first = true; }
@@ -469,13 +534,8 @@ struct TSeq {
             at = slot + 1;
         }
         if (at < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-        leaf_open(tgt_leaf, at);
+        tgt_leaf = leaf_insert(tgt_leaf, at, mk_slot(peer, ctr, len, 0));
         if (err) return;
-        u64 ni = ls(tgt_leaf, at);
-        p.leaf_peer[ni] = (u16)peer;
-        p.leaf_ctr[ni] = ctr;
-        p.leaf_len[ni] = len;
-        p.leaf_st[ni] = 0;
         u64 a0 = atom_index(peer, ctr);
         p.a_ol_peer[a0] = ol_peer;
         p.a_ol_ctr[a0] = ol_ctr;
@@ -507,11 +567,7 @@ struct TSeq {
             height = 1;
             first_leaf = 0;
             unk_leaf = 0;
-            u64 s0 = ls(0, 0);
-            p.leaf_peer[s0] = PEER_UNKNOWN;
-            p.leaf_ctr[s0] = 0;
-            p.leaf_len[s0] = UNKNOWN_LEN;
-            p.leaf_st[s0] = 0;
+            p.tleaf[ls(0, 0)] = mk_slot(PEER_UNKNOWN, 0, UNKNOWN_LEN, 0);
             p.leaf_n[leaf0] = 1;
             p.leaf_parent[leaf0] = 0;
             p.leaf_next[leaf0] = LEAF_NONE;
@@ -538,10 +594,10 @@ struct TSeq {
         for (u32 l2 = first_leaf; l2 != LEAF_NONE; l2 = p.leaf_next[leaf0 + l2]) {
             u32 n = p.leaf_n[leaf0 + l2];
             for (u32 s = 0; s < n; s++) {
-                u64 si = ls(l2, s);
-                u16 pe = p.leaf_peer[si];
-                if (p.leaf_st[si] != 0 || pe == PEER_UNKNOWN) continue;
-                i32 ct = p.leaf_ctr[si], ln = p.leaf_len[si];
+                uint4 sv = p.tleaf[ls(l2, s)];
+                u32 pe = s_peer(sv);
+                if (s_st(sv) != 0 || pe == PEER_UNKNOWN) continue;
+                i32 ct = s_ctr(sv), ln = s_len(sv);
                 if (n_out < dc.out_cap) {
                     u32 row = t->atom_row[atom_index(pe, ct)];
                     p.out_row[dc.out0 + n_out] = row;
@@ -578,6 +634,7 @@ __global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, S
     for (u32 c = 0; c < di.C; c++) pools.cont_epoch[di.cid0 + c] = 0xFFFFFFFFu;
     u32 P = di.P;
     u32 prev_peer = 0xFFFFFFFFu;
+    u32 cur_epoch = 0xFFFFFFFFu;   // epoch of the active container (kept in a register)
     for (u32 k = 0; k < di.n_applied && !s.err; k++) {
         u32 ch = tables.ch_walk[di.ch0 + k];
         u32 peer = tables.ch_peer[ch];
@@ -585,21 +642,29 @@ __global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, S
         u32 nr = tables.ch_nops[ch];
         bool chain = tables.ch_dep_self[ch] && tables.ch_ndeps[ch] == 0 && prev_peer == peer && k > 0;
         const i32* vv = nullptr;
+        // one-row-ahead software pipeline: the fields of row r+1 are requested before row r is processed
+        u8 n_kind = 0; u32 n_c = 0; i32 n_ctr = 0, n_len = 0, n_prop = 0; u32 n_del = 0;
+        if (nr) {
+            n_kind = tables.op_kind[r0]; n_c = tables.op_cidx[r0]; n_ctr = tables.op_counter[r0];
+            n_len = (i32)tables.op_len[r0]; n_prop = tables.op_prop[r0]; n_del = tables.op_del[r0];
+        }
         for (u32 r = 0; r < nr && !s.err; r++) {
-            u64 row = r0 + r;
-            u8 kind = tables.op_kind[row];
+            u8 kind = n_kind; u32 c = n_c; i32 ctr = n_ctr, len = n_len, prop = n_prop; u32 dl = n_del;
+            if (r + 1 < nr) {
+                u64 nx = r0 + r + 1;
+                n_kind = tables.op_kind[nx]; n_c = tables.op_cidx[nx]; n_ctr = tables.op_counter[nx];
+                n_len = (i32)tables.op_len[nx]; n_prop = tables.op_prop[nx]; n_del = tables.op_del[nx];
+            }
             if (kind != OPK_SEQ_INS && kind != OPK_SEQ_DEL) continue;
-            u32 c = tables.op_cidx[row];
-            i32 ctr = tables.op_counter[row];
-            i32 len = (i32)tables.op_len[row];
             if (c != s.cidx) {
+                if (s.cidx != 0xFFFFFFFFu) pools.cont_epoch[di.cid0 + s.cidx] = cur_epoch;
                 s.store_container();
                 s.load_container(c);
                 if (s.err) break;
+                cur_epoch = pools.cont_epoch[di.cid0 + c];
             }
-            u32 epoch = pools.cont_epoch[di.cid0 + c];
-            if (epoch != k) {
-                if (!(chain && epoch == k - 1)) {
+            if (cur_epoch != k) {
+                if (!(chain && cur_epoch == k - 1)) {
                     if (!vv) {
                         const DocPeer& dp = tables.dpeer[di.peer0 + peer];
                         i32 cc = tables.ch_counter[ch];
@@ -612,16 +677,17 @@ __global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, S
                     }
                     s.checkout(vv, peer, ctr);
                 }
-                pools.cont_epoch[di.cid0 + c] = k;
+                cur_epoch = k;
             }
-            if (kind == OPK_SEQ_INS) s.insert(peer, ctr, len, tables.op_prop[row]);
+            if (kind == OPK_SEQ_INS) s.insert(peer, ctr, len, prop);
             else {
-                u32 dl = tables.op_del[row];
                 const BlockInfo& bi = tables.blocks[tables.ch_block[ch]];
                 u32 tp = tables.peer_map[bi.peer0 + tables.del_peer_idx[dl]];
-                s.range_set(tp, tables.del_counter[dl], tables.del_counter[dl] + len, -1, +1);
+                i32 tc = tables.del_counter[dl];
+                s.range_set(tp, tc, tc + len, -1, +1);
             }
-            if (pools.cvv[s.cvv0 + peer] < ctr + len) pools.cvv[s.cvv0 + peer] = ctr + len;
+            // current_vv follows the tracker's own ops; in causal order this entry only grows
+            pools.cvv[s.cvv0 + peer] = ctr + len;
         }
         prev_peer = peer;
     }
