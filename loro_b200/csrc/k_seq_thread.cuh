@@ -635,61 +635,74 @@ __global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, S
     u32 P = di.P;
     u32 prev_peer = 0xFFFFFFFFu;
     u32 cur_epoch = 0xFFFFFFFFu;   // epoch of the active container (kept in a register)
-    for (u32 k = 0; k < di.n_applied && !s.err; k++) {
-        u32 ch = tables.ch_walk[di.ch0 + k];
-        u32 peer = tables.ch_peer[ch];
-        u64 r0 = tables.ch_op0[ch];
-        u32 nr = tables.ch_nops[ch];
-        bool chain = tables.ch_dep_self[ch] && tables.ch_ndeps[ch] == 0 && prev_peer == peer && k > 0;
-        const i32* vv = nullptr;
-        // one-row-ahead software pipeline: the fields of row r+1 are requested before row r is processed
-        u8 n_kind = 0; u32 n_c = 0; i32 n_ctr = 0, n_len = 0, n_prop = 0; u32 n_del = 0;
-        if (nr) {
-            n_kind = tables.op_kind[r0]; n_c = tables.op_cidx[r0]; n_ctr = tables.op_counter[r0];
-            n_len = (i32)tables.op_len[r0]; n_prop = tables.op_prop[r0]; n_del = tables.op_del[r0];
+    // Flat state machine: every loop iteration handles exactly one op row (or one change transition), so
+    // the lanes of a warp -- which walk different documents -- reconverge at every row instead of waiting
+    // for the longest change of the warp.
+    u32 k = 0, kcur = 0;           // next change to open / index of the open change
+    u32 ch = 0, peer = 0, nr = 0, r = 0;
+    u64 r0 = 0;
+    bool chain = false;
+    const i32* vv = nullptr;
+    u8 n_kind = 0; u32 n_c = 0; i32 n_ctr = 0, n_len = 0, n_prop = 0; u32 n_del = 0;
+    while (true) {
+        if (r >= nr) {
+            if (k >= di.n_applied || s.err) break;
+            if (k > 0) prev_peer = peer;
+            kcur = k;
+            ch = tables.ch_walk[di.ch0 + k];
+            peer = tables.ch_peer[ch];
+            r0 = tables.ch_op0[ch];
+            nr = tables.ch_nops[ch];
+            chain = tables.ch_dep_self[ch] && tables.ch_ndeps[ch] == 0 && prev_peer == peer && k > 0;
+            vv = nullptr;
+            r = 0;
+            k++;
+            if (nr) {
+                n_kind = tables.op_kind[r0]; n_c = tables.op_cidx[r0]; n_ctr = tables.op_counter[r0];
+                n_len = (i32)tables.op_len[r0]; n_prop = tables.op_prop[r0]; n_del = tables.op_del[r0];
+            }
+            continue;
         }
-        for (u32 r = 0; r < nr && !s.err; r++) {
-            u8 kind = n_kind; u32 c = n_c; i32 ctr = n_ctr, len = n_len, prop = n_prop; u32 dl = n_del;
-            if (r + 1 < nr) {
-                u64 nx = r0 + r + 1;
-                n_kind = tables.op_kind[nx]; n_c = tables.op_cidx[nx]; n_ctr = tables.op_counter[nx];
-                n_len = (i32)tables.op_len[nx]; n_prop = tables.op_prop[nx]; n_del = tables.op_del[nx];
-            }
-            if (kind != OPK_SEQ_INS && kind != OPK_SEQ_DEL) continue;
-            if (c != s.cidx) {
-                if (s.cidx != 0xFFFFFFFFu) pools.cont_epoch[di.cid0 + s.cidx] = cur_epoch;
-                s.store_container();
-                s.load_container(c);
-                if (s.err) break;
-                cur_epoch = pools.cont_epoch[di.cid0 + c];
-            }
-            if (cur_epoch != k) {
-                if (!(chain && cur_epoch == k - 1)) {
-                    if (!vv) {
-                        const DocPeer& dp = tables.dpeer[di.peer0 + peer];
-                        i32 cc = tables.ch_counter[ch];
-                        u32 lo = 0, hi = dp.ch_count;
-                        while (hi - lo > 1) {
-                            u32 mid = (lo + hi) >> 1;
-                            if (tables.ch_counter[tables.ch_order[di.ch0 + dp.ch_first + mid]] <= cc) lo = mid; else hi = mid;
-                        }
-                        vv = tables.ch_vv + di.vv0 + (u64)(dp.ch_first + lo) * P;
+        u8 kind = n_kind; u32 c = n_c; i32 ctr = n_ctr, len = n_len, prop = n_prop; u32 dl = n_del;
+        r++;
+        if (r < nr) {   // request the next row before working on this one
+            u64 nx = r0 + r;
+            n_kind = tables.op_kind[nx]; n_c = tables.op_cidx[nx]; n_ctr = tables.op_counter[nx];
+            n_len = (i32)tables.op_len[nx]; n_prop = tables.op_prop[nx]; n_del = tables.op_del[nx];
+        }
+        if (kind != OPK_SEQ_INS && kind != OPK_SEQ_DEL) continue;
+        if (c != s.cidx) {
+            if (s.cidx != 0xFFFFFFFFu) pools.cont_epoch[di.cid0 + s.cidx] = cur_epoch;
+            s.store_container();
+            s.load_container(c);
+            if (s.err) break;
+            cur_epoch = pools.cont_epoch[di.cid0 + c];
+        }
+        if (cur_epoch != kcur) {
+            if (!(chain && cur_epoch == kcur - 1)) {
+                if (!vv) {
+                    const DocPeer& dp = tables.dpeer[di.peer0 + peer];
+                    i32 cc = tables.ch_counter[ch];
+                    u32 lo = 0, hi = dp.ch_count;
+                    while (hi - lo > 1) {
+                        u32 mid = (lo + hi) >> 1;
+                        if (tables.ch_counter[tables.ch_order[di.ch0 + dp.ch_first + mid]] <= cc) lo = mid; else hi = mid;
                     }
-                    s.checkout(vv, peer, ctr);
+                    vv = tables.ch_vv + di.vv0 + (u64)(dp.ch_first + lo) * P;
                 }
-                cur_epoch = k;
+                s.checkout(vv, peer, ctr);
             }
-            if (kind == OPK_SEQ_INS) s.insert(peer, ctr, len, prop);
-            else {
-                const BlockInfo& bi = tables.blocks[tables.ch_block[ch]];
-                u32 tp = tables.peer_map[bi.peer0 + tables.del_peer_idx[dl]];
-                i32 tc = tables.del_counter[dl];
-                s.range_set(tp, tc, tc + len, -1, +1);
-            }
-            // current_vv follows the tracker's own ops; in causal order this entry only grows
-            pools.cvv[s.cvv0 + peer] = ctr + len;
+            cur_epoch = kcur;
         }
-        prev_peer = peer;
+        if (kind == OPK_SEQ_INS) s.insert(peer, ctr, len, prop);
+        else {
+            const BlockInfo& bi = tables.blocks[tables.ch_block[ch]];
+            u32 tp = tables.peer_map[bi.peer0 + tables.del_peer_idx[dl]];
+            i32 tc = tables.del_counter[dl];
+            s.range_set(tp, tc, tc + len, -1, +1);
+        }
+        // current_vv follows the tracker's own ops; in causal order this entry only grows
+        pools.cvv[s.cvv0 + peer] = ctr + len;
     }
     for (u32 c = 0; c < di.C && !s.err; c++) {
         const DocContainer& dc = tables.dcont[di.cid0 + c];
