@@ -63,7 +63,7 @@ def library_path():
 
 
 def load_library(path=None):
-    path = path or _DEFAULT_LIB
+    path = path or os.environ.get("LORO_B200_LIB") or _DEFAULT_LIB
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

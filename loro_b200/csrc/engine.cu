@@ -302,9 +302,10 @@ void pipeline(lb_batch* b) {
     u32* cap_out = dv.alloc<u32>(NC + 1, true);
     u32* cap_cvv = dv.alloc<u32>(NC + 1, true);
     u32* span_cap = dv.alloc<u32>(D + 1, true);
-    // mapping of the integration phase: one thread per document for large batches (every document advances
-    // concurrently), one warp per document for small ones.  LB_SEQ_MODE=warp|thread overrides (tests).
-    bool thread_mode = D >= 1024;
+    // mapping of the integration phase: one warp per document (k_seq.cuh).  The thread-per-document variant
+    // (k_seq_thread.cuh) is kept for experiments (LB_SEQ_MODE=thread): measured on B200 it loses to the warp
+    // kernel at every batch size because lanes of a warp sit in different long paths (checkout, leaf split).
+    bool thread_mode = false;
     if (const char* m = getenv("LB_SEQ_MODE")) thread_mode = m[0] == 't';
     u32 leaf_w = thread_mode ? LB_TF : 32;
     LB_LAUNCH(k_container_caps, nblk(D), TPB, 0, st, b->d_docs, D, dcont, cap_leaf, cap_node, cap_out, cap_cvv, span_cap, leaf_w);
@@ -324,8 +325,8 @@ void pipeline(lb_batch* b) {
     memset(&sp, 0, sizeof(sp));
     if (thread_mode) sp.tleaf = dv.alloc<uint4>(NLEAF * leaf_w);
     else {
-        sp.leaf_peer = dv.alloc<u16>(NLEAF * leaf_w); sp.leaf_ctr = dv.alloc<i32>(NLEAF * leaf_w);
-        sp.leaf_len = dv.alloc<i32>(NLEAF * leaf_w); sp.leaf_st = dv.alloc<u16>(NLEAF * leaf_w);
+        sp.leaf_ps = dv.alloc<u32>(NLEAF * leaf_w); sp.leaf_ctr = dv.alloc<i32>(NLEAF * leaf_w);
+        sp.leaf_len = dv.alloc<i32>(NLEAF * leaf_w);
     }
     sp.leaf_n = dv.alloc<u32>(NLEAF, true); sp.leaf_parent = dv.alloc<u32>(NLEAF); sp.leaf_next = dv.alloc<u32>(NLEAF);
     sp.node_child = dv.alloc<u32>(NNODE * leaf_w); sp.node_vis = dv.alloc<i32>(NNODE * leaf_w);

@@ -27,13 +27,14 @@
 #define LEAF_NONE 0xFFFFFFFFu
 #define ST_FUTURE 0x8000u
 #ifndef LB_SEQ_NS
-#define LB_SEQ_NS 24          // internal nodes cached in shared memory per warp
+#define LB_SEQ_NS 8           // internal nodes cached in shared memory per warp (more smem = less L1)
 #endif
 #define LB_SEQ_WARPS 4        // warps (documents) per CTA
 
 struct SeqPools {
     // leaves
-    u16* leaf_peer; i32* leaf_ctr; i32* leaf_len; u16* leaf_st; u32* leaf_n; u32* leaf_parent; u32* leaf_next;
+    u32* leaf_ps;    // warp layout: peer | state << 16 per slot
+    i32* leaf_ctr; i32* leaf_len; u32* leaf_n; u32* leaf_parent; u32* leaf_next;
     uint4* tleaf;   // thread-per-document layout: one uint4 per slot (k_seq_thread.cuh)
     // internal nodes (global home; nodes < NS of the active container are cached in shared memory)
     u32* node_child; i32* node_vis; u32* node_n; u32* node_parent;
@@ -61,13 +62,15 @@ struct SeqSmem {   // one per warp
     i32 vis[LB_SEQ_NS][32];
     u32 n[LB_SEQ_NS];
     u32 parent[LB_SEQ_NS];
+    u32 abase[32];   // atom_base of the document's first 32 peers
 };
 
 struct LeafImg { u32 n; u16 peer; i32 ctr; i32 len; u16 st; };   // lane i holds slot i of a leaf
 
 struct Seq {
-    SeqPools p;
+    const SeqPools& p;   // kernel parameters stay in the constant bank (__grid_constant__)
     const SeqTables* t;
+    __device__ Seq(const SeqPools& p_, const SeqTables* t_) : p(p_), t(t_) {}
     const DocInfo* di;
     SeqSmem* sm;
     int lane;
@@ -77,8 +80,10 @@ struct Seq {
     u64 leaf0, node0, cvv0;
     u32 leaf_cap, node_cap, n_leaves, n_nodes, root, height, first_leaf, unk_leaf;
 
+    u64 atom0;
     __device__ __forceinline__ u64 atom_index(u32 peer, i32 ctr) const {
-        return di->atom0 + t->dpeer[di->peer0 + peer].atom_base + (u32)ctr;
+        u32 base = peer < 32 ? sm->abase[peer] : t->dpeer[di->peer0 + peer].atom_base;
+        return atom0 + base + (u32)ctr;
     }
     // ---- node accessors (shared-memory cache for node ids < NS)
     __device__ __forceinline__ u32 nd_n(u32 nd) const { return nd < LB_SEQ_NS ? sm->n[nd] : p.node_n[node0 + nd]; }
@@ -100,17 +105,15 @@ struct Seq {
         unsigned m = __ballot_sync(LB_FULL, c == child);
         return __ffs(m) - 1;
     }
+    // Parent links carry the position inside the parent: link = (parent << 5) | index, NODE_NONE for the root.
     // ---- add `delta` visible atoms on the path leaf -> root
     __device__ void add_vis(u32 leaf, i32 delta) {
         if (delta == 0) return;
-        u32 child = leaf;
-        u32 nd = p.leaf_parent[leaf0 + leaf];
-        while (nd != NODE_NONE) {
-            int idx = nd_find(nd, child);
-            if (idx < 0) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
-            if (lane == idx) nd_add_vis(nd, idx, delta);
-            child = nd;
-            nd = nd_parent(nd);
+        u32 link = p.leaf_parent[leaf0 + leaf];
+        while (link != NODE_NONE) {
+            u32 nd = link >> 5;
+            if (lane == 0) nd_add_vis(nd, (int)(link & 31), delta);
+            link = nd_parent(nd);
         }
         __syncwarp();
     }
@@ -125,10 +128,11 @@ struct Seq {
         if (lane == at) { c = child; v = vis; }
         else if (lane > at) { c = c_up; v = v_up; }
         if (lane <= (int)n) nd_set(nd, lane, c, v);
-        if (lane == 0) {
-            nd_set_n(nd, n + 1);
-            if (kids_are_leaves) p.leaf_parent[leaf0 + child] = nd; else nd_set_parent(child, nd);
+        if (lane >= at && lane <= (int)n) {   // the new child and every child that moved one place up
+            u32 link = (nd << 5) | (u32)lane;
+            if (kids_are_leaves) p.leaf_parent[leaf0 + c] = link; else nd_set_parent(c, link);
         }
+        if (lane == 0) nd_set_n(nd, n + 1);
         __syncwarp();
     }
     __device__ i32 node_total(u32 nd) {
@@ -148,16 +152,17 @@ struct Seq {
             __syncwarp();
             if (lane >= 16) {
                 nd_set(nn, lane - 16, c, v);
-                if (kids_are_leaves) p.leaf_parent[leaf0 + c] = nn; else nd_set_parent(c, nn);
+                u32 link = (nn << 5) | (u32)(lane - 16);
+                if (kids_are_leaves) p.leaf_parent[leaf0 + c] = link; else nd_set_parent(c, link);
             }
             if (lane == 0) { nd_set_n(nd, 16); nd_set_n(nn, 16); }
             __syncwarp();
             if (after >= 16) node_insert_no_split(nn, after - 16, child, vis, kids_are_leaves);
             else node_insert_no_split(nd, after, child, vis, kids_are_leaves);
             i32 tot_old = node_total(nd), tot_new = node_total(nn);
-            u32 parent = nd_parent(nd);
+            u32 plink = nd_parent(nd);
             __syncwarp();   // every lane has read the parent link before it is rewritten
-            if (parent == NODE_NONE) {
+            if (plink == NODE_NONE) {
                 if (n_nodes >= node_cap) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
                 u32 nr = n_nodes++;
                 if (lane == 0) {
@@ -165,17 +170,17 @@ struct Seq {
                     nd_set(nr, 1, nn, tot_new);
                     nd_set_n(nr, 2);
                     nd_set_parent(nr, NODE_NONE);
-                    nd_set_parent(nd, nr);
-                    nd_set_parent(nn, nr);
+                    nd_set_parent(nd, (nr << 5) | 0u);
+                    nd_set_parent(nn, (nr << 5) | 1u);
                 }
                 __syncwarp();
                 root = nr;
                 height++;
                 return;
             }
-            int idx = nd_find(parent, nd);
-            if (idx < 0) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
-            if (lane == idx) nd_set(parent, idx, nd, tot_old);
+            u32 parent = plink >> 5;
+            int idx = (int)(plink & 31);
+            if (lane == 0) nd_set(parent, idx, nd, tot_old);
             __syncwarp();
             child = nn;
             vis = tot_new;
@@ -190,19 +195,19 @@ struct Seq {
         L.n = p.leaf_n[leaf0 + leaf];
         u64 b = (leaf0 + leaf) * 32 + lane;
         bool in = lane < (int)L.n;
-        L.peer = in ? p.leaf_peer[b] : (u16)PEER_NONE;
+        u32 ps = in ? p.leaf_ps[b] : ((u32)PEER_NONE | (1u << 16));
+        L.peer = (u16)ps;
+        L.st = (u16)(ps >> 16);
         L.ctr = in ? p.leaf_ctr[b] : 0;
         L.len = in ? p.leaf_len[b] : 0;
-        L.st = in ? p.leaf_st[b] : (u16)1;
         return L;
     }
     __device__ __forceinline__ void leaf_store(u32 leaf, const LeafImg& L, u32 new_n) {
         u64 b = (leaf0 + leaf) * 32 + lane;
         if (lane < (int)new_n) {
-            p.leaf_peer[b] = L.peer;
+            p.leaf_ps[b] = (u32)L.peer | ((u32)L.st << 16);
             p.leaf_ctr[b] = L.ctr;
             p.leaf_len[b] = L.len;
-            p.leaf_st[b] = L.st;
         }
         if (lane == 0) p.leaf_n[leaf0 + leaf] = new_n;
         __syncwarp();
@@ -221,10 +226,9 @@ struct Seq {
         i32 vis = L.st == 0 ? L.len : 0;
         if (lane >= 16) {
             u64 dst = (leaf0 + nl) * 32 + lane - 16;
-            p.leaf_peer[dst] = L.peer;
+            p.leaf_ps[dst] = (u32)L.peer | ((u32)L.st << 16);
             p.leaf_ctr[dst] = L.ctr;
             p.leaf_len[dst] = L.len;
-            p.leaf_st[dst] = L.st;
             if (L.peer != PEER_UNKNOWN) p.atom_leaf[atom_index(L.peer, L.ctr)] = nl;
         }
         // long spans: their remaining atoms cooperatively
@@ -248,10 +252,10 @@ struct Seq {
             p.leaf_next[leaf0 + leaf] = nl;
         }
         __syncwarp();
-        u32 parent = p.leaf_parent[leaf0 + leaf];
-        int idx = nd_find(parent, leaf);
-        if (idx < 0) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
-        if (lane == idx) nd_add_vis(parent, idx, -moved);
+        u32 plink = p.leaf_parent[leaf0 + leaf];
+        u32 parent = plink >> 5;
+        int idx = (int)(plink & 31);
+        if (lane == 0) nd_add_vis(parent, idx, -moved);
         __syncwarp();
         node_insert(parent, idx, nl, moved, true);
     }
@@ -320,22 +324,23 @@ struct Seq {
         i32 c = lo;
         while (c < hi && !err) {
             u64 ai = atom_index(peer, c);
-            if (p.atom_leaf[ai] == LEAF_NONE) { c++; continue; }
-            split_before(peer, c);
-            if (err) return;
-            // the span now starts at c; cut its tail if it extends beyond hi
             u32 leaf = p.atom_leaf[ai];
+            if (leaf == LEAF_NONE) { c++; continue; }
             LeafImg L = leaf_load(leaf);
             int slot = slot_of(L, peer, c);
             if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+            i32 s_ctr = __shfl_sync(LB_FULL, L.ctr, slot);
             i32 s_len = __shfl_sync(LB_FULL, L.len, slot);
-            if (c + s_len > hi) {
-                split_before(peer, hi);
+            if (s_ctr != c || c + s_len > hi) {
+                // boundaries do not line up with the span: cut it, then look again (rare)
+                if (s_ctr != c) split_before(peer, c);
+                if (!err && s_ctr + s_len > hi) split_before(peer, hi);
                 if (err) return;
-                s_len = hi - c;
                 leaf = p.atom_leaf[ai];
                 L = leaf_load(leaf);
                 slot = slot_of(L, peer, c);
+                if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+                s_len = __shfl_sync(LB_FULL, L.len, slot);
             }
             // status change of the whole span + visible-length propagation
             u16 st = __shfl_sync(LB_FULL, L.st, slot);
@@ -343,7 +348,7 @@ struct Seq {
             if (set_future == 1) nst |= ST_FUTURE;
             if (set_future == 0) nst &= (u16)~ST_FUTURE;
             nst = (u16)((nst & ST_FUTURE) | (((nst & 0x7FFF) + del_diff) & 0x7FFF));
-            if (lane == 0) p.leaf_st[(leaf0 + leaf) * 32 + slot] = nst;
+            if (lane == 0) p.leaf_ps[(leaf0 + leaf) * 32 + slot] = (peer & 0xFFFFu) | ((u32)nst << 16);
             __syncwarp();
             i32 before = st == 0 ? s_len : 0, after = nst == 0 ? s_len : 0;
             add_vis(leaf, after - before);
@@ -394,13 +399,11 @@ struct Seq {
     __device__ u64 order_key(u32 leaf, int slot) {
         u64 key = (u64)slot;
         int shift = 6;
-        u32 child = leaf;
-        u32 nd = p.leaf_parent[leaf0 + leaf];
-        while (nd != NODE_NONE) {
-            key |= (u64)nd_find(nd, child) << shift;
+        u32 link = p.leaf_parent[leaf0 + leaf];
+        while (link != NODE_NONE) {
+            key |= (u64)(link & 31) << shift;
             shift += 6;
-            child = nd;
-            nd = nd_parent(nd);
+            link = nd_parent(link >> 5);
         }
         return key;
     }
@@ -527,7 +530,7 @@ struct Seq {
                 u32 n = p.leaf_n[leaf0 + l2];
                 for (int s = from; s < (int)n && seen < n_between && !stop; s++) {
                     u64 si = (leaf0 + l2) * 32 + s;
-                    u32 o_peer = p.leaf_peer[si];
+                    u32 o_peer = p.leaf_ps[si] & 0xFFFFu;
                     i32 o_ctr = p.leaf_ctr[si];
                     seen++;
                     u64 o_key = order_key(l2, s);
@@ -678,12 +681,11 @@ struct Seq {
         first_leaf = 0;
         unk_leaf = 0;
         if (lane == 0) {
-            p.leaf_peer[leaf0 * 32] = PEER_UNKNOWN;
+            p.leaf_ps[leaf0 * 32] = PEER_UNKNOWN;
             p.leaf_ctr[leaf0 * 32] = 0;
             p.leaf_len[leaf0 * 32] = UNKNOWN_LEN;
-            p.leaf_st[leaf0 * 32] = 0;
             p.leaf_n[leaf0] = 1;
-            p.leaf_parent[leaf0] = 0;
+            p.leaf_parent[leaf0] = 0;   // (node 0 << 5) | index 0
             p.leaf_next[leaf0] = LEAF_NONE;
             nd_set(0, 0, 0, UNKNOWN_LEN);
             nd_set_n(0, 1);
@@ -726,8 +728,12 @@ struct Seq {
 };
 
 // one warp per document, LB_SEQ_WARPS documents per CTA
-__global__ void __launch_bounds__(32 * LB_SEQ_WARPS)
-k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, SeqPools pools, SeqTables tables) {
+#ifndef LB_SEQ_MINB
+#define LB_SEQ_MINB 8         // 8 CTAs x 4 warps = 32 resident documents per SM (64 registers/thread)
+#endif
+__global__ void __launch_bounds__(32 * LB_SEQ_WARPS, LB_SEQ_MINB)
+k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ SeqPools pools,
+                const __grid_constant__ SeqTables tables) {
     __shared__ SeqSmem smem[LB_SEQ_WARPS];
     u32 warp_in_cta = threadIdx.x >> 5;
     u32 warp_global = blockIdx.x * LB_SEQ_WARPS + warp_in_cta;
@@ -739,19 +745,21 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, SeqPools pools, SeqTable
     for (u32 c = 0; c < di.C; c++)
         if (tables.dcont[di.cid0 + c].leaf_cap) any = true;
     if (!any) return;
-    Seq s;
-    s.p = pools;
-    s.t = &tables;
+    Seq s(pools, &tables);
     s.di = &di;
     s.sm = &smem[warp_in_cta];
     s.lane = lane;
     s.err = 0;
     s.cidx = 0xFFFFFFFFu;
+    s.atom0 = di.atom0;
+    if (lane < (int)di.P) s.sm->abase[lane] = tables.dpeer[di.peer0 + lane].atom_base;
+    __syncwarp();
     for (u64 i = lane; i < di.atom_total; i += 32) pools.atom_leaf[di.atom0 + i] = LEAF_NONE;
     for (u32 c = lane; c < di.C; c += 32) pools.cont_epoch[di.cid0 + c] = 0xFFFFFFFFu;
     __syncwarp();
     u32 P = di.P;
     u32 prev_peer = 0xFFFFFFFFu;
+    u32 cur_epoch = 0xFFFFFFFFu;   // epoch of the active container (register; spilled on container switch)
     for (u32 k = 0; k < di.n_applied && !s.err; k++) {
         u32 ch = tables.ch_walk[di.ch0 + k];
         u32 peer = tables.ch_peer[ch];
@@ -769,13 +777,14 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, SeqPools pools, SeqTable
             i32 ctr = tables.op_counter[row];
             i32 len = (i32)tables.op_len[row];
             if (c != s.cidx) {
+                if (s.cidx != 0xFFFFFFFFu && lane == 0) pools.cont_epoch[di.cid0 + s.cidx] = cur_epoch;
                 s.store_container();
                 s.load_container(c);
                 if (s.err) break;
+                cur_epoch = pools.cont_epoch[di.cid0 + c];
             }
-            u32 epoch = pools.cont_epoch[di.cid0 + c];
-            if (epoch != k) {
-                if (!(chain && epoch == k - 1)) {
+            if (cur_epoch != k) {
+                if (!(chain && cur_epoch == k - 1)) {
                     if (!vv) {
                         const DocPeer& dp = tables.dpeer[di.peer0 + peer];
                         i32 cc = tables.ch_counter[ch];
@@ -788,9 +797,7 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, SeqPools pools, SeqTable
                     }
                     s.checkout(vv, peer, ctr);
                 }
-                __syncwarp();
-                if (lane == 0) pools.cont_epoch[di.cid0 + c] = k;
-                __syncwarp();
+                cur_epoch = k;
             }
             if (kind == OPK_SEQ_INS) s.insert(peer, ctr, len, tables.op_prop[row]);
             else {
@@ -799,9 +806,9 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, SeqPools pools, SeqTable
                 u32 tp = tables.peer_map[bi.peer0 + tables.del_peer_idx[dl]];
                 s.del(tp, tables.del_counter[dl], len);
             }
-            // current_vv of the tracker follows its own ops (tracker.rs:131-139, 228-231)
-            __syncwarp();
-            if (lane == 0 && pools.cvv[s.cvv0 + peer] < ctr + len) pools.cvv[s.cvv0 + peer] = ctr + len;
+            // current_vv of the tracker follows its own ops (tracker.rs:131-139, 228-231); in causal order this
+            // entry only grows, and insert()/del() end with a warp barrier
+            if (lane == 0) pools.cvv[s.cvv0 + peer] = ctr + len;
             __syncwarp();
         }
         prev_peer = peer;

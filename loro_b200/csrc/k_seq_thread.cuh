@@ -13,8 +13,9 @@
 #define LB_TF 16   // slots per leaf / children per node in the thread-per-document layout
 
 struct TSeq {
-    SeqPools p;
+    const SeqPools& p;   // kernel parameters stay in the constant bank (__grid_constant__)
     const SeqTables* t;
+    __device__ TSeq(const SeqPools& p_, const SeqTables* t_) : p(p_), t(t_) {}
     const DocInfo* di;
     u32 err;
     u32 cidx;
@@ -615,7 +616,8 @@ struct TSeq {
 };
 
 // one thread per document
-__global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, SeqPools pools, SeqTables tables) {
+__global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ SeqPools pools,
+                                       const __grid_constant__ SeqTables tables) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     DocInfo& di = docs[d];
@@ -624,9 +626,7 @@ __global__ void k_seq_integrate_thread(DocInfo* __restrict__ docs, u32 n_docs, S
     for (u32 c = 0; c < di.C; c++)
         if (tables.dcont[di.cid0 + c].leaf_cap) any = true;
     if (!any) return;
-    TSeq s;
-    s.p = pools;
-    s.t = &tables;
+    TSeq s(pools, &tables);
     s.di = &di;
     s.err = 0;
     s.cidx = 0xFFFFFFFFu;

@@ -99,6 +99,7 @@ inline uint64_t warp_exchange(unsigned mask, uint64_t v, int src_lane_valid_dumm
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
+#define __grid_constant__
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define threadIdx (simt::cur->tid)
