@@ -171,6 +171,7 @@ def main():
     import numpy as np
     import torch
     import loro_b200
+    from loro_b200.shard import gather_counters
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,15 +200,12 @@ def main():
             o, n = int(gen.offsets[idx[i]]), int(lens[i])
             d_bytes[int(offs[i]):int(offs[i]) + n] = src[o:o + n]
         del src
-    counters_dev = torch.zeros(8, dtype=torch.int64, device=dev)
 
     def step():
         b = loro_b200.import_batch_device(d_bytes.data_ptr(), offs, lens, device=local, keep=d_bytes)
         c = b.counters()
         if world > 1:
-            counters_dev[:4] = torch.tensor([c["atom_ops"], c["docs_ok"], c["pending_changes"], c["state_hash"] & 0x7FFFFFFFFFFFFFFF], device=dev)
-            gathered = [torch.zeros_like(counters_dev) for _ in range(world)]
-            dist.all_gather(gathered, counters_dev)  # the one collective of the path: per-shard summary counters
+            gather_counters(c, device=dev)  # the one collective of the path: per-shard summary counters (NCCL)
         tm = b.timings()
         b.close()
         return c, tm
