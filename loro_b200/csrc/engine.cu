@@ -19,6 +19,7 @@
 #include "k_seq.cuh"
 #include "k_seq_thread.cuh"
 #include "k_state.cuh"
+#include "host_stage.hpp"
 
 static thread_local std::string g_last_error;
 const char* lb_last_error(void) { return g_last_error.c_str(); }
@@ -138,7 +139,7 @@ struct lb_batch {
     // host results
     std::vector<DocInfo> docs;
     std::vector<DocPeer> dpeer;
-    std::vector<char> json;
+    char* json = nullptr;   // malloc'ed (never zero-filled): filled by lbstage::download
     bool json_fetched = false;
     std::vector<std::vector<lb_id_span>> success, pending, vv;
     std::vector<uint64_t> doc_ids;
@@ -491,7 +492,6 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
     lb_batch* b = new lb_batch();
     b->n_docs = n_blobs;
     b->flags = opt ? opt->flags : 0;
-    u8* pinned = nullptr;
     try {
         init_batch(b);
         std::vector<u64> offs(n_blobs + 1);
@@ -509,18 +509,17 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
             b->counters.blob_bytes += blobs[i].len;
         }
         offs[n_blobs] = total;
-        // stage through pinned memory so that the H2D copy is a single DMA
-        CK(cudaMallocHost((void**)&pinned, total ? total : 16));
-        for (size_t i = 0; i < n_blobs; i++) {
-            memcpy(pinned + offs[i], blobs[i].ptr, blobs[i].len);
-            size_t pad = (size_t)(((blobs[i].len + 15) & ~(u64)15) - blobs[i].len);
-            if (pad) memset(pinned + offs[i] + blobs[i].len, 0, pad);
-        }
+        // stage through the pinned ring: host gather of slot k overlaps the DMA of slot k-1 (host_stage.hpp)
+        std::vector<lbstage::BlobView> views(n_blobs);
+        for (size_t i = 0; i < n_blobs; i++) views[i] = lbstage::BlobView{blobs[i].ptr, blobs[i].len};
         CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
         u8* d_bytes = b->dev.alloc<u8>(total + 64);
         b->d_offs = b->dev.alloc<u64>(n_blobs + 1);
         b->d_lens = b->dev.alloc<u32>(n_blobs + 1);
-        CK(cudaMemcpyAsync(d_bytes, pinned, total, cudaMemcpyHostToDevice, b->dev.stream));
+        if (!lbstage::upload_blobs(views.data(), offs.data(), n_blobs, d_bytes, b->dev.stream)) {
+            g_last_error = "h2d staging failed";
+            throw lb_status(LB_ERR_CUDA);
+        }
         CK(cudaMemcpyAsync(b->d_offs, offs.data(), sizeof(u64) * (n_blobs + 1), cudaMemcpyHostToDevice, b->dev.stream));
         CK(cudaMemcpyAsync(b->d_lens, lens.data(), sizeof(u32) * (n_blobs + 1), cudaMemcpyHostToDevice, b->dev.stream));
         b->d_bytes = d_bytes;
@@ -529,12 +528,9 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
         // event indices: 0 start,1 h2d,2 frame,3 decode,4 resolve,5 classify,6 integrate,7 materialise,8 d2h
         s = run_batch(b);
         CK(cudaStreamSynchronize(b->dev.stream));
-        cudaFreeHost(pinned);
-        pinned = nullptr;
     } catch (lb_status e) {
         s = e;
     }
-    if (pinned) cudaFreeHost(pinned);
     if (s != LB_OK) { lb_batch_free(b); return s; }
     *out = b;
     return LB_OK;
@@ -602,18 +598,18 @@ lb_status lb_doc_json(const lb_batch* cb, size_t doc, const char** utf8, size_t*
     if (!b || !utf8 || !len || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
     if (b->flags & LB_FLAG_NO_JSON) { g_last_error = "batch was imported with LB_FLAG_NO_JSON"; return LB_ERR_INVALID_ARG; }
     if (!b->json_fetched) {
-        b->json.resize(b->json_total + 1);
-        if (b->json_total) {
-            if (cudaMemcpy(b->json.data(), b->d_json, b->json_total, cudaMemcpyDeviceToHost) != cudaSuccess) {
-                g_last_error = "json d2h failed";
-                return LB_ERR_CUDA;
-            }
+        b->json = (char*)malloc(b->json_total + 1);
+        if (!b->json) { g_last_error = "out of host memory"; return LB_ERR_OOM; }
+        if (b->json_total && !lbstage::download(b->d_json, (u8*)b->json, b->json_total, b->dev.stream)) {
+            g_last_error = "json d2h failed";
+            return LB_ERR_CUDA;
         }
+        b->json[b->json_total] = 0;
         b->json_fetched = true;
     }
     const DocInfo& di = b->docs[doc];
     if (di.code != DOC_OK) { *utf8 = ""; *len = 0; return LB_OK; }
-    *utf8 = b->json.data() + di.json_off;
+    *utf8 = b->json + di.json_off;
     *len = di.json_len;
     return LB_OK;
 }
@@ -662,6 +658,7 @@ void lb_batch_free(lb_batch* b) {
             for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
         cudaStreamDestroy(b->dev.stream);
     }
+    free(b->json);
     delete b;
 }
 

@@ -1,0 +1,143 @@
+// Host <-> device staging for the host-buffer entry points (lb_import_batch, lb_doc_json).
+//
+// The caller's blobs are ~100k separate pageable allocations; the JSON result is one large pageable buffer.
+// Both directions go through a small process-wide ring of pinned slots: worker threads gather/scatter one slot
+// while the copy engine moves the other, so the PCIe transfer overlaps the host memcpy and no batch-sized pinned
+// allocation (seconds for several GB) is ever made.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace lbstage {
+
+constexpr size_t SLOT_BYTES = 32u << 20;
+constexpr int N_SLOTS = 4;
+
+struct Ring {
+    uint8_t* slot[N_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[N_SLOTS];
+    bool ready = false;
+    std::mutex mu;
+    bool init() {
+        if (ready) return true;
+        for (int i = 0; i < N_SLOTS; i++) {
+            if (cudaMallocHost((void**)&slot[i], SLOT_BYTES) != cudaSuccess) return false;
+            if (cudaEventCreate(&ev[i]) != cudaSuccess) return false;
+        }
+        ready = true;
+        return true;
+    }
+};
+
+inline Ring& ring() {
+    static Ring r;
+    return r;
+}
+
+// LB_STAGE_SLOT (bytes, testing hook) shrinks the slot so that small inputs exercise the multi-slot, multi-thread paths.
+inline size_t slot_bytes() {
+    static size_t v = [] {
+        const char* e = getenv("LB_STAGE_SLOT");
+        size_t x = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+        return (x >= 64 && x <= SLOT_BYTES) ? x : SLOT_BYTES;
+    }();
+    return v;
+}
+
+inline unsigned n_workers() {
+    unsigned hc = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(8u, hc ? hc : 1u));
+}
+
+template <class F>
+inline void parallel_ranges(size_t lo, size_t hi, F&& f) {
+    unsigned T = n_workers();
+    size_t n = hi - lo;
+    if (n < std::min<size_t>(1u << 20, slot_bytes() / 2) || T == 1) { f(lo, hi); return; }
+    std::vector<std::thread> th;
+    size_t per = (n + T - 1) / T;
+    for (unsigned t = 0; t < T; t++) {
+        size_t a = lo + t * per, b = std::min(hi, a + per);
+        if (a >= b) break;
+        th.emplace_back([&f, a, b] { f(a, b); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// Copy bytes [lo,hi) of the virtual stream "blob i at offs[i], zero padded up to offs[i+1]" into dst (dst[0] = lo).
+struct BlobView { const uint8_t* ptr; size_t len; };
+inline void gather(const BlobView* blobs, const uint64_t* offs, size_t n_blobs, size_t lo, size_t hi, uint8_t* dst) {
+    size_t i = std::upper_bound(offs, offs + n_blobs + 1, (uint64_t)lo) - offs;
+    i = i ? i - 1 : 0;
+    size_t pos = lo;
+    while (pos < hi && i < n_blobs) {
+        size_t b0 = offs[i], bdata = b0 + blobs[i].len, b1 = offs[i + 1];
+        if (pos < bdata) {
+            size_t e = std::min(hi, bdata);
+            std::memcpy(dst + (pos - lo), blobs[i].ptr + (pos - b0), e - pos);
+            pos = e;
+        }
+        if (pos < hi && pos < b1) {
+            size_t e = std::min(hi, b1);
+            std::memset(dst + (pos - lo), 0, e - pos);
+            pos = e;
+        }
+        i++;
+    }
+    if (pos < hi) std::memset(dst + (pos - lo), 0, hi - pos);
+}
+
+// Host blobs -> one contiguous device buffer.  Returns false on a CUDA error.
+inline bool upload_blobs(const BlobView* blobs, const uint64_t* offs, size_t n_blobs, uint8_t* d_dst, cudaStream_t st) {
+    Ring& r = ring();
+    std::lock_guard<std::mutex> g(r.mu);
+    if (!r.init()) return false;
+    size_t total = offs[n_blobs];
+    const size_t SB = slot_bytes();
+    int k = 0;
+    for (size_t lo = 0; lo < total; lo += SB, k++) {
+        size_t hi = std::min(total, lo + SB);
+        int s = k % N_SLOTS;
+        if (k >= N_SLOTS && cudaEventSynchronize(r.ev[s]) != cudaSuccess) return false;
+        uint8_t* buf = r.slot[s];
+        parallel_ranges(lo, hi, [&](size_t a, size_t b) { gather(blobs, offs, n_blobs, a, b, buf + (a - lo)); });
+        if (cudaMemcpyAsync(d_dst + lo, buf, hi - lo, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+        if (cudaEventRecord(r.ev[s], st) != cudaSuccess) return false;
+    }
+    // the slots are reused by the next caller: drain before releasing the ring
+    return cudaStreamSynchronize(st) == cudaSuccess;
+}
+
+// Device buffer -> pageable host buffer.
+inline bool download(const uint8_t* d_src, uint8_t* dst, size_t total, cudaStream_t st) {
+    Ring& r = ring();
+    std::lock_guard<std::mutex> g(r.mu);
+    if (!r.init()) return false;
+    const size_t SB = slot_bytes();
+    size_t n_chunks = (total + SB - 1) / SB;
+    auto drain = [&](size_t c) -> bool {
+        int s = (int)(c % N_SLOTS);
+        if (cudaEventSynchronize(r.ev[s]) != cudaSuccess) return false;
+        size_t lo = c * SB, hi = std::min(total, lo + SB);
+        const uint8_t* buf = r.slot[s];
+        parallel_ranges(lo, hi, [&](size_t a, size_t b) { std::memcpy(dst + a, buf + (a - lo), b - a); });
+        return true;
+    };
+    for (size_t c = 0; c < n_chunks; c++) {
+        if (c >= (size_t)N_SLOTS && !drain(c - N_SLOTS)) return false;
+        int s = (int)(c % N_SLOTS);
+        size_t lo = c * SB, hi = std::min(total, lo + SB);
+        if (cudaMemcpyAsync(r.slot[s], d_src + lo, hi - lo, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+        if (cudaEventRecord(r.ev[s], st) != cudaSuccess) return false;
+    }
+    for (size_t c = n_chunks > (size_t)N_SLOTS ? n_chunks - N_SLOTS : 0; c < n_chunks; c++)
+        if (!drain(c)) return false;
+    return true;
+}
+
+}  // namespace lbstage

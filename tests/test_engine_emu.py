@@ -119,3 +119,25 @@ def test_generator_three_way_agreement():
     for i in range(gen.n_docs):
         assert batch.json_bytes(i) == gen.expected_json(i)
     assert batch.counters()["atom_ops"] == gen.atom_ops
+
+
+def test_host_staging_ring_small_slots():
+    """host_stage.hpp: multi-slot / multi-thread gather + scatter (LB_STAGE_SLOT shrinks the pinned slots) gives the
+    same bytes as the single-slot path."""
+    import hashlib, sys
+    blobs = [workloads.make_doc_history(900 + i, n_sites=2, n_ops=80)[0] for i in range(6)]
+    import loro_b200
+    b = loro_b200.import_batch(blobs, lib_path=EMU)
+    want = hashlib.sha256(b"\n".join(b.json_bytes(i) for i in range(len(blobs)))).hexdigest()
+    code = (
+        "import sys, hashlib, pickle; sys.path.insert(0, %r); import loro_b200\n"
+        "blobs = pickle.load(open(sys.argv[1], 'rb'))\n"
+        "b = loro_b200.import_batch(blobs, lib_path=%r)\n"
+        "print(hashlib.sha256(b'\\n'.join(b.json_bytes(i) for i in range(len(blobs)))).hexdigest())\n"
+    ) % (os.path.dirname(HERE), EMU)
+    import pickle, tempfile
+    with tempfile.NamedTemporaryFile(suffix=".pkl") as f:
+        pickle.dump(blobs, f); f.flush()
+        for slot in ("64", "4096"):
+            out = subprocess.check_output([sys.executable, "-c", code, f.name], env=dict(os.environ, LB_STAGE_SLOT=slot))
+            assert out.decode().strip() == want, slot
