@@ -102,7 +102,7 @@ class ClockSampler:
 def default_docs(args, world):
     if args.docs:
         return args.docs
-    cores = max(1, (os.cpu_count() or 1) // max(1, world))
+    cores = max(1, (host_cores() or 1) // max(1, world))
     # ~1.2 M generated atom ops/s/core; keep generation near 90 s
     docs = int(cores * 1.2e6 * 90 / args.ops_per_doc)
     return max(256, min(100000, docs))
@@ -112,7 +112,7 @@ def make_workload(args, rank, world, n_docs):
     from loro_b200.workload import C3Batch
     distinct = args.distinct or n_docs
     distinct = min(distinct, n_docs)
-    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    threads = max(1, (host_cores() or 1) // max(1, world))
     t0 = time.time()
     gen = C3Batch(distinct, n_ops=args.ops_per_doc, n_peers=args.peers, first_doc=rank * n_docs, threads=threads)
     return gen, distinct, time.time() - t0
@@ -122,7 +122,7 @@ def cpu_baseline(args, gen, threads=None):
     """The oracle port of the reference's CPU path on a bounded sample of the same workload."""
     import oracle
     import numpy as np
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or (host_cores() or 1)
     n = args.cpu_sample_docs or min(gen.n_docs, max(64, min(4096, threads * 48)))
     # oracle.bench_import wants contiguous [off[i], off[i+1]) blobs: re-pack exact lengths
     blobs = [gen.blob(i) for i in range(n)]
@@ -142,7 +142,7 @@ def run_reference(args):
         return
     import oracle
     oracle.build()
-    threads = os.cpu_count() or 1
+    threads = host_cores() or 1
     n = args.cpu_sample_docs or max(64, min(4096, threads * 48))
     ns = argparse.Namespace(**vars(args))
     ns.distinct = 0
@@ -162,6 +162,32 @@ def run_reference(args):
             "cpu_baseline": {"value": total_ops_per_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": total_ops_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def host_cores():
+    """Cores this process can really use: min(affinity, cgroup cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
+def ncu_traffic(kernel_key, rows):
+    """dram bytes per launch for `rows` op rows, scaled from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        best = None
+        for fn in sorted(os.listdir(os.path.join(here, "profiles"))):
+            if fn.endswith("_ncu_facts.json"):
+                best = os.path.join(here, "profiles", fn)
+        f = json.load(open(best))[kernel_key]
+        return {"bytes": f["dram_bytes_per_op_row"] * rows, "source": os.path.basename(best) + ": dram__bytes_read+write per op row x rows"}
+    except Exception:
+        return None
 
 
 def main():
@@ -286,18 +312,25 @@ def main():
     integ_bytes = rows * 52
     dec_bytes = tm["decode_bytes_read"] + tm["decode_bytes_written"]
     roof = {"bound": "hbm", "kernel": "k_seq_integrate", "achieved": integ_bytes / (integ_ms * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+            "unit": "GB/s", "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": integ_bytes,
             "share_of_step": integ_ms / (phase["total_device"] / n_steps)}
     roof["frac"] = roof["achieved"] / peak
+    tr = ncu_traffic("seq", rows)
+    if tr:
+        roof["traffic"] = tr["bytes"]
+        roof["traffic_source"] = tr["source"]
     dec_roof = {"bound": "hbm", "kernel": "k_block_count+k_block_decode", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9,
                 "peak": peak, "unit": "GB/s", "traffic": None}
     dec_roof["frac"] = dec_roof["achieved"] / peak
+    tr = ncu_traffic("decode", rows)
+    if tr:
+        dec_roof["traffic"] = tr["bytes"]
     try:
         import oracle
         oracle.build()
         cpu = cpu_baseline(args, gen)
     except Exception as e:  # the bench must still print its line
-        cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": f"failed: {e}"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,7 +339,7 @@ def main():
                                f"one FastUpdates blob per doc (SURVEY.md 8d)",
                    "docs_per_gpu": n_docs, "distinct_docs_per_gpu": distinct, "atom_ops_per_step_per_gpu": atoms_per_step,
                    "op_rows_per_gpu": rows, "blob_bytes_per_gpu": int(lens.sum()), "l2": "inputs_larger_than_L2" if lens.sum() > 126e6 else "inputs fit L2",
-                   "generator_seconds": round(gen_s, 1), "host_cores": os.cpu_count()},
+                   "generator_seconds": round(gen_s, 1), "host_cores": host_cores()},
         "phases_ms": {k: v / n_steps for k, v in phase.items()}, "wall_ms_per_step": wall_ms / n_steps,
         "roofline": roof, "decode_roofline": dec_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
