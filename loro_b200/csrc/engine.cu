@@ -17,7 +17,6 @@
 #include "k_resolve.cuh"
 #include "k_classify.cuh"
 #include "k_seq.cuh"
-#include "k_seq_thread.cuh"
 #include "k_state.cuh"
 #include "host_stage.hpp"
 
@@ -262,6 +261,7 @@ void pipeline(lb_batch* b) {
     rt.ch_applied = dv.alloc<u8>(NCH, true);
     rt.ch_lamport = dv.alloc<u32>(NCH, true);
     rt.ch_walk = dv.alloc<u32>(NCH);
+    rt.ch_pos = dv.alloc<u32>(NCH);
     LB_LAUNCH(k_doc_tables, nblk(D, 64), 64, 0, st, b->d_bytes, b->d_docs, D, blk, rt);
     u32* d_tmp_a = dv.alloc<u32>(D + 1, true);
     u32* d_tmp_b = dv.alloc<u32>(D + 1, true);
@@ -287,9 +287,12 @@ void pipeline(lb_batch* b) {
     ct.ch_counter = t.ch_counter; ct.ch_peer = rt.ch_peer;
     ct.op_cid = t.op_cid; ct.op_prop = t.op_prop; ct.op_vtype = t.op_vtype; ct.op_len = t.op_len;
     ct.op_counter = t.op_counter; ct.op_change = t.op_change;
+    ct.op_del = t.op_del; ct.del_peer_idx = t.del_peer_idx; ct.del_counter = t.del_counter; ct.del_len = t.del_len;
+    ct.peer_map = rt.peer_map;
     ct.cid_map = rt.cid_map; ct.key_map = rt.key_map; ct.dcont = dcont; ct.dpeer = b->d_dpeer;
     ct.op_kind = dv.alloc<u8>(NR); ct.op_cidx = dv.alloc<u32>(NR); ct.op_lamport = dv.alloc<u32>(NR);
     ct.atom_row = dv.alloc<u32>(NATOM);
+    ct.op_rec = dv.alloc<uint4>(NR); ct.op_aux = dv.alloc<u32>(NR);
     ct.map_best = dv.alloc<unsigned long long>(NSLOT, true);
     ct.map_row = dv.alloc<u32>(NSLOT);
     if (NR) {
@@ -303,12 +306,7 @@ void pipeline(lb_batch* b) {
     u32* cap_out = dv.alloc<u32>(NC + 1, true);
     u32* cap_cvv = dv.alloc<u32>(NC + 1, true);
     u32* span_cap = dv.alloc<u32>(D + 1, true);
-    // mapping of the integration phase: one warp per document (k_seq.cuh).  The thread-per-document variant
-    // (k_seq_thread.cuh) is kept for experiments (LB_SEQ_MODE=thread): measured on B200 it loses to the warp
-    // kernel at every batch size because lanes of a warp sit in different long paths (checkout, leaf split).
-    bool thread_mode = false;
-    if (const char* m = getenv("LB_SEQ_MODE")) thread_mode = m[0] == 't';
-    u32 leaf_w = thread_mode ? LB_TF : 32;
+    const u32 leaf_w = 32;   // slots per leaf = lanes per warp (k_seq.cuh)
     LB_LAUNCH(k_container_caps, nblk(D), TPB, 0, st, b->d_docs, D, dcont, cap_leaf, cap_node, cap_out, cap_cvv, span_cap, leaf_w);
     tm.kernel_launches += 1;
     run_scans(b, {ScanJob{(const u8*)cap_leaf, (u8*)dcont + offsetof(DocContainer, leaf0), 4, sizeof(DocContainer), NC},
@@ -324,17 +322,11 @@ void pipeline(lb_batch* b) {
     // ------------------------------------------------------------ phase 5: sequence integration
     SeqPools sp;
     memset(&sp, 0, sizeof(sp));
-    if (thread_mode) sp.tleaf = dv.alloc<uint4>(NLEAF * leaf_w);
-    else {
-        sp.leaf_ps = dv.alloc<u32>(NLEAF * leaf_w); sp.leaf_ctr = dv.alloc<i32>(NLEAF * leaf_w);
-        sp.leaf_len = dv.alloc<i32>(NLEAF * leaf_w);
-    }
-    sp.leaf_n = dv.alloc<u32>(NLEAF, true); sp.leaf_parent = dv.alloc<u32>(NLEAF); sp.leaf_next = dv.alloc<u32>(NLEAF);
-    sp.node_child = dv.alloc<u32>(NNODE * leaf_w); sp.node_vis = dv.alloc<i32>(NNODE * leaf_w);
-    sp.node_n = dv.alloc<u32>(NNODE, true); sp.node_parent = dv.alloc<u32>(NNODE);
+    sp.leaf = dv.alloc<uint4>(NLEAF * leaf_w);
+    sp.node = dv.alloc<uint2>(NNODE * leaf_w);
+    sp.node_parent = dv.alloc<u32>(NNODE);
     sp.atom_leaf = dv.alloc<u32>(NATOM);
-    sp.a_ol_peer = dv.alloc<u16>(NATOM); sp.a_ol_ctr = dv.alloc<i32>(NATOM);
-    sp.a_or_peer = dv.alloc<u16>(NATOM); sp.a_or_ctr = dv.alloc<i32>(NATOM);
+    sp.a_org = dv.alloc<uint4>(NATOM);
     sp.cvv = dv.alloc<i32>(NCVV, true);
     sp.cont_epoch = dv.alloc<u32>(NC + 1);
     sp.out_row = dv.alloc<u32>(NOUT); sp.out_off = dv.alloc<u32>(NOUT); sp.out_len = dv.alloc<u32>(NOUT);
@@ -343,12 +335,10 @@ void pipeline(lb_batch* b) {
     sq.dpeer = b->d_dpeer; sq.dcont = dcont;
     sq.ch_walk = rt.ch_walk; sq.ch_op0 = t.ch_op0; sq.ch_nops = t.ch_nops; sq.ch_peer = rt.ch_peer; sq.ch_vv = rt.ch_vv;
     sq.ch_order = rt.ch_order; sq.ch_counter = t.ch_counter; sq.ch_ndeps = t.ch_ndeps; sq.ch_dep_self = t.ch_dep_self;
-    sq.op_kind = ct.op_kind; sq.op_cidx = ct.op_cidx; sq.op_prop = t.op_prop; sq.op_len = t.op_len;
-    sq.op_counter = t.op_counter; sq.op_del = t.op_del; sq.op_change = t.op_change;
-    sq.del_peer_idx = t.del_peer_idx; sq.del_counter = t.del_counter; sq.del_len = t.del_len;
-    sq.peer_map = rt.peer_map; sq.blocks = blk; sq.ch_block = t.ch_block; sq.atom_row = ct.atom_row;
-    if (thread_mode) LB_LAUNCH(k_seq_integrate_thread, nblk(D, 64), 64, 0, st, b->d_docs, D, sp, sq);
-    else LB_LAUNCH(k_seq_integrate, nblk(D, LB_SEQ_WARPS), 32 * LB_SEQ_WARPS, 0, st, b->d_docs, D, sp, sq);
+    sq.ch_pos = rt.ch_pos;
+    sq.op_rec = ct.op_rec; sq.op_aux = ct.op_aux; sq.op_change = t.op_change; sq.op_counter = t.op_counter;
+    sq.atom_row = ct.atom_row;
+    LB_LAUNCH(k_seq_integrate, nblk(D, LB_SEQ_WARPS), 32 * LB_SEQ_WARPS, 0, st, b->d_docs, D, sp, sq);
     tm.kernel_launches += 1;
     mark(b);  // [5] integrate done
     // ------------------------------------------------------------ phase 6: JSON

@@ -13,10 +13,12 @@ struct ClassifyTables {
     const u32* ch_block; const u8* ch_applied; const u32* ch_lamport; const i32* ch_counter; const u16* ch_peer;
     const u32* op_cid; const i32* op_prop; const u8* op_vtype; const u32* op_len; const i32* op_counter;
     const u32* op_change;
+    const u32* op_del; const u32* del_peer_idx; const i32* del_counter; const i32* del_len; const u32* peer_map;
     const u32* cid_map; const u32* key_map;
     DocContainer* dcont; const DocPeer* dpeer;
     // outputs
     u8* op_kind; u32* op_cidx; u32* op_lamport;
+    uint4* op_rec; u32* op_aux;   // compact records for the tracker (layout: k_seq.cuh REC_*)
     u32* atom_row;          // per doc: atom -> op row (batch-wide row index, 32-bit)
     unsigned long long* map_best;  // per (doc, container, key): max packed (lamport<<32 | rank<<16 | 1)
     u32* map_row;           // winner row per slot
@@ -46,12 +48,39 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
     u32 ch = t.op_change[row];
     const BlockInfo& bi = t.blocks[t.ch_block[ch]];
     DocInfo& di = docs[bi.doc];
-    if (di.code != DOC_OK) { t.op_kind[row] = OPK_SKIP; return; }
+    if (di.code != DOC_OK) {
+        t.op_kind[row] = OPK_SKIP;
+        uint4 z; z.x = z.y = z.z = z.w = 0;
+        t.op_rec[row] = z;
+        return;
+    }
     u32 cidx = t.cid_map[bi.cid0 + t.op_cid[row]];
     DocContainer& dc = t.dcont[di.cid0 + cidx];
     u8 kind = classify_op(dc.type, t.op_vtype[row]);
     if (!t.ch_applied[ch]) kind = OPK_SKIP;
     u32 lam = t.ch_lamport[ch] + (u32)(t.op_counter[row] - t.ch_counter[ch]);
+    {   // tracker record: everything k_seq needs about this row in one 16-byte load
+        u32 w = (u32)t.op_prop[row], aux = 0, rev = 0;
+        if (kind == OPK_SEQ_DEL) {
+            u32 dl = t.op_del[row];
+            i32 dlen = t.del_len[dl];
+            u32 tp = t.peer_map[bi.peer0 + t.del_peer_idx[dl]];
+            i32 tc = t.del_counter[dl];
+            i32 n = (i32)t.op_len[row];
+            // the target atoms must exist: an applied delete causally follows the inserts it removes
+            if (tp >= di.P || tc < 0 || (i64)tc + n > (i64)t.dpeer[di.peer0 + tp].end_counter) kind = OPK_UNSUPPORTED;
+            w = (u32)tc;
+            aux = tp;
+            rev = dlen < 0 ? 1u : 0u;
+        }
+        uint4 rec;
+        rec.x = (u32)kind | (rev << 3) | (cidx << 4);
+        rec.y = (u32)t.op_counter[row];
+        rec.z = t.op_len[row];
+        rec.w = w;
+        t.op_rec[row] = rec;
+        t.op_aux[row] = aux;
+    }
     t.op_kind[row] = kind;
     t.op_cidx[row] = cidx;
     t.op_lamport[row] = lam;

@@ -32,6 +32,7 @@ struct ResolveTables {
     u32* ch_lamport;     // recomputed lamport
     u32* ch_walk;        // per doc: applied changes in replay order
     i32* ch_vv;          // per doc: n_changes * P
+    u32* ch_pos;         // per change: its position in the doc's ch_order (= row of ch_vv)
 };
 
 __device__ inline bool bytes_eq(const u8* a, const u8* b, u32 n) {
@@ -299,6 +300,7 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
         }
         t.ch_lamport[ch] = pick_lam;
         t.ch_applied[ch] = 1;
+        t.ch_pos[ch] = local;
         t.ch_walk[di.ch0 + walk_n++] = ch;
         dp.end_counter = ctr + (i32)t.ch_len[ch];
         di.atom_ops += t.ch_len[ch];

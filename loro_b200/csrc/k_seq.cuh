@@ -9,723 +9,821 @@
 //   diff_calc.rs:175-236,585-620 (per-change checkout then apply)
 //
 // Data structure: per container a B+tree.
-//   * leaves (HBM, SoA): up to 32 spans each as (peer, counter, len, state); one warp reads a whole leaf with
-//     four coalesced accesses and resolves "k-th visible atom" with a shuffle scan + ballot;
-//   * internal nodes: up to 32 (child, visible-length) pairs; the first NS nodes of the container being
-//     integrated live in SHARED memory (one private region per warp), the rest spill to HBM, so the descent
-//     and the visible-length updates of an op normally touch no global memory at all;
-//   * per document, dense atom-indexed arrays (HBM): atom -> leaf, atom -> op row, and the Fugue origins of
-//     every span start.  Spans never merge or disappear, they only split, and a split never moves atoms, so
-//     only a leaf split rewrites atom -> leaf entries.
+//   * leaves (HBM): 32 slots of one uint4 (peer | state << 16, counter, len, aux); lane i of the warp owns slot i,
+//     so a whole leaf -- spans, parent link (aux of slot 0) and next-leaf link (aux of slot 1) -- arrives with ONE
+//     128-bit load per lane, and "k-th visible atom" is a shuffle scan + ballot.  Unused slots hold a sentinel,
+//     so no count has to be read before the slots;
+//   * internal nodes: 32 (child, visible-length) pairs; the first NS nodes of the active container live in
+//     SHARED memory (one private region per warp), the rest spill to HBM;
+//   * per document, dense atom-indexed arrays (HBM): atom -> leaf and the Fugue origins of every span start
+//     (one uint4).  Spans never merge or disappear, they only split, and a split never moves atoms, so only a
+//     leaf split rewrites atom -> leaf entries.
+// The kernel is bound by the latency of dependent HBM loads (profiles/r1_ncu_seq.md), so everything that can
+// be looked up ahead is fetched lane-parallel: 32 change headers, 32 op records, the 32 target leaves of a
+// version switch are each one round trip, and the warp then consumes them with shuffles.
 // Deletes are applied by target id (for well-formed histories the reference's by-position deletion hits the
 // same atoms).  Every function is warp-synchronous: all 32 lanes call it with identical arguments; a
 // __syncwarp() separates reads by all lanes from a following write by one lane to the same location.
+// Rare paths (splits, the sibling scan) are separate __noinline__ functions working on per-warp state in
+// shared memory: the v2 kernel inlined them everywhere and stalled on instruction fetch (44k SASS lines).
 #pragma once
 #include "lb_defs.h"
 
 #define NODE_NONE 0xFFFFFFFFu
 #define LEAF_NONE 0xFFFFFFFFu
 #define ST_FUTURE 0x8000u
+#define SLOT_EMPTY ((u32)PEER_NONE | (1u << 16))   // no peer, never visible
 #ifndef LB_SEQ_NS
-#define LB_SEQ_NS 8           // internal nodes cached in shared memory per warp (more smem = less L1)
+#define LB_SEQ_NS 12          // internal nodes cached in shared memory per warp
 #endif
 #define LB_SEQ_WARPS 4        // warps (documents) per CTA
 
+// op record written by k_op_classify: x = kind | reversed << 3 | container << 4, y = counter, z = atoms,
+// w = insert position (SEQ_INS) or lowest target counter (SEQ_DEL); op_aux = target peer of a delete
+#define REC_KIND(x) ((x) & 7u)
+#define REC_REV(x) (((x) >> 3) & 1u)
+#define REC_CIDX(x) ((x) >> 4)
+
 struct SeqPools {
-    // leaves
-    u32* leaf_ps;    // warp layout: peer | state << 16 per slot
-    i32* leaf_ctr; i32* leaf_len; u32* leaf_n; u32* leaf_parent; u32* leaf_next;
-    uint4* tleaf;   // thread-per-document layout: one uint4 per slot (k_seq_thread.cuh)
-    // internal nodes (global home; nodes < NS of the active container are cached in shared memory)
-    u32* node_child; i32* node_vis; u32* node_n; u32* node_parent;
-    // per-document atom-indexed arrays
-    u32* atom_leaf;                                  // LEAF_NONE = not an inserted list/text atom (yet)
-    u16* a_ol_peer; i32* a_ol_ctr; u16* a_or_peer; i32* a_or_ctr;   // origins, valid at span starts
-    i32* cvv;
-    u32* cont_epoch;   // per container: last walk index that checked out / applied an op
+    uint4* leaf;         // [leaf][32]
+    uint2* node;         // [node][32] (child, visible atoms below)   (global home of the nodes)
+    u32* node_parent;    // (parent << 5) | index inside the parent, NODE_NONE for the root
+    u32* atom_leaf;      // LEAF_NONE = not an inserted list/text atom (yet)
+    uint4* a_org;        // origins, valid at span starts: x = ol_peer | or_peer << 16, y = ol_ctr, z = or_ctr
+    i32* cvv;            // per container: tracker current_vv (P entries)
+    u32* cont_epoch;     // per container: last walk index that checked out / applied an op
     u32* out_row; u32* out_off; u32* out_len;
 };
 
 struct SeqTables {
     const DocPeer* dpeer; DocContainer* dcont;
     const u32* ch_walk; const u64* ch_op0; const u32* ch_nops; const u16* ch_peer; const i32* ch_vv;
-    const u32* ch_order; const i32* ch_counter; const u32* ch_ndeps; const u8* ch_dep_self;
-    const u8* op_kind; const u32* op_cidx; const i32* op_prop; const u32* op_len; const i32* op_counter;
-    const u32* op_del; const u32* op_change;
-    const u32* del_peer_idx; const i32* del_counter; const i32* del_len;
-    const u32* peer_map; const BlockInfo* blocks; const u32* ch_block;
+    const u32* ch_order; const i32* ch_counter; const u32* ch_ndeps; const u8* ch_dep_self; const u32* ch_pos;
+    const uint4* op_rec; const u32* op_aux; const u32* op_change; const i32* op_counter;
     const u32* atom_row;
 };
 
 struct SeqSmem {   // one per warp
     u32 child[LB_SEQ_NS][32];
     i32 vis[LB_SEQ_NS][32];
-    u32 n[LB_SEQ_NS];
     u32 parent[LB_SEQ_NS];
-    u32 abase[32];   // atom_base of the document's first 32 peers
+    u32 abase[32];     // atom_base of the document's first 32 peers
+    i32 cvv[32];       // tracker version of the active container, first 32 peers
+    // active container
+    u32 root, height, first_leaf, n_leaves, n_nodes, unk_leaf, leaf_cap, node_cap;
+    u32 err;
+    u32 pad;
 };
 
-struct LeafImg { u32 n; u16 peer; i32 ctr; i32 len; u16 st; };   // lane i holds slot i of a leaf
-
-struct Seq {
-    const SeqPools& p;   // kernel parameters stay in the constant bank (__grid_constant__)
-    const SeqTables* t;
-    __device__ Seq(const SeqPools& p_, const SeqTables* t_) : p(p_), t(t_) {}
-    const DocInfo* di;
+// Everything a helper needs besides the pools; passed by value, lives in registers.
+struct Cx {
     SeqSmem* sm;
+    const DocPeer* dpeer;   // the document's peers
+    u64 leaf0, node0, atom0, cvv0;
+    u32 P;
     int lane;
-    u32 err;
-    // current container
-    u32 cidx;
-    u64 leaf0, node0, cvv0;
-    u32 leaf_cap, node_cap, n_leaves, n_nodes, root, height, first_leaf, unk_leaf;
+};
 
-    u64 atom0;
-    __device__ __forceinline__ u64 atom_index(u32 peer, i32 ctr) const {
-        u32 base = peer < 32 ? sm->abase[peer] : t->dpeer[di->peer0 + peer].atom_base;
-        return atom0 + base + (u32)ctr;
-    }
-    // ---- node accessors (shared-memory cache for node ids < NS)
-    __device__ __forceinline__ u32 nd_n(u32 nd) const { return nd < LB_SEQ_NS ? sm->n[nd] : p.node_n[node0 + nd]; }
-    __device__ __forceinline__ void nd_set_n(u32 nd, u32 v) { if (nd < LB_SEQ_NS) sm->n[nd] = v; else p.node_n[node0 + nd] = v; }
-    __device__ __forceinline__ u32 nd_parent(u32 nd) const { return nd < LB_SEQ_NS ? sm->parent[nd] : p.node_parent[node0 + nd]; }
-    __device__ __forceinline__ void nd_set_parent(u32 nd, u32 v) { if (nd < LB_SEQ_NS) sm->parent[nd] = v; else p.node_parent[node0 + nd] = v; }
-    __device__ __forceinline__ u32 nd_child(u32 nd, int i) const { return nd < LB_SEQ_NS ? sm->child[nd][i] : p.node_child[(node0 + nd) * 32 + i]; }
-    __device__ __forceinline__ i32 nd_vis(u32 nd, int i) const { return nd < LB_SEQ_NS ? sm->vis[nd][i] : p.node_vis[(node0 + nd) * 32 + i]; }
-    __device__ __forceinline__ void nd_set(u32 nd, int i, u32 c, i32 v) {
-        if (nd < LB_SEQ_NS) { sm->child[nd][i] = c; sm->vis[nd][i] = v; }
-        else { p.node_child[(node0 + nd) * 32 + i] = c; p.node_vis[(node0 + nd) * 32 + i] = v; }
-    }
-    __device__ __forceinline__ void nd_add_vis(u32 nd, int i, i32 d) {
-        if (nd < LB_SEQ_NS) sm->vis[nd][i] += d; else p.node_vis[(node0 + nd) * 32 + i] += d;
-    }
-    __device__ __forceinline__ int nd_find(u32 nd, u32 child) {   // index of `child` in node (warp-wide)
-        u32 n = nd_n(nd);
-        u32 c = lane < (int)n ? nd_child(nd, lane) : NODE_NONE;
-        unsigned m = __ballot_sync(LB_FULL, c == child);
-        return __ffs(m) - 1;
-    }
-    // Parent links carry the position inside the parent: link = (parent << 5) | index, NODE_NONE for the root.
-    // ---- add `delta` visible atoms on the path leaf -> root
-    __device__ void add_vis(u32 leaf, i32 delta) {
-        if (delta == 0) return;
-        u32 link = p.leaf_parent[leaf0 + leaf];
+__device__ __forceinline__ uint4 mk4(u32 x, u32 y, u32 z, u32 w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+__device__ __forceinline__ uint2 mk2(u32 x, u32 y) { uint2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ void seq_fail(const Cx& c, u32 code) {
+    if (c.lane == 0 && c.sm->err == 0) c.sm->err = code;
+    __syncwarp();
+}
+__device__ __forceinline__ u64 atom_index(const Cx& c, u32 peer, i32 ctr) {
+    u32 base = peer < 32 ? c.sm->abase[peer] : c.dpeer[peer].atom_base;
+    return c.atom0 + base + (u32)ctr;
+}
+__device__ __forceinline__ i32 cvv_get(const SeqPools& p, const Cx& c, u32 q) { return q < 32 ? c.sm->cvv[q] : p.cvv[c.cvv0 + q]; }
+__device__ __forceinline__ void cvv_set(const SeqPools& p, const Cx& c, u32 q, i32 v) { if (q < 32) c.sm->cvv[q] = v; else p.cvv[c.cvv0 + q] = v; }
+
+// ---- slots
+__device__ __forceinline__ u32 s_peer(const uint4& s) { return s.x & 0xFFFFu; }
+__device__ __forceinline__ u32 s_st(const uint4& s) { return s.x >> 16; }
+__device__ __forceinline__ i32 s_vis(const uint4& s) { return (s.x >> 16) == 0 ? (i32)s.z : 0; }
+__device__ __forceinline__ uint4 leaf_load(const SeqPools& p, const Cx& c, u32 leaf) { return p.leaf[(c.leaf0 + leaf) * 32 + c.lane]; }
+__device__ __forceinline__ void leaf_store(const SeqPools& p, const Cx& c, u32 leaf, const uint4& L) {
+    p.leaf[(c.leaf0 + leaf) * 32 + c.lane] = L;
+    __syncwarp();
+}
+__device__ __forceinline__ int leaf_count(const uint4& L) { return __popc(__ballot_sync(LB_FULL, s_peer(L) != PEER_NONE)); }
+// slot of the span containing atom (peer, ctr) inside a loaded leaf image, -1 when absent
+__device__ __forceinline__ int slot_of(const uint4& L, u32 peer, i32 ctr) {
+    unsigned m = __ballot_sync(LB_FULL, s_peer(L) == peer && ctr >= (i32)L.y && ctr < (i32)L.y + (i32)L.z);
+    return __ffs(m) - 1;
+}
+
+// ---- nodes (shared-memory cache for ids < NS)
+__device__ __forceinline__ uint2 nd_get(const SeqPools& p, const Cx& c, u32 nd, int i) {
+    return nd < LB_SEQ_NS ? mk2(c.sm->child[nd][i], (u32)c.sm->vis[nd][i]) : p.node[(c.node0 + nd) * 32 + i];
+}
+__device__ __forceinline__ void nd_set(const SeqPools& p, const Cx& c, u32 nd, int i, u32 child, i32 vis) {
+    if (nd < LB_SEQ_NS) { c.sm->child[nd][i] = child; c.sm->vis[nd][i] = vis; }
+    else p.node[(c.node0 + nd) * 32 + i] = mk2(child, (u32)vis);
+}
+__device__ __forceinline__ u32 nd_parent(const SeqPools& p, const Cx& c, u32 nd) {
+    return nd < LB_SEQ_NS ? c.sm->parent[nd] : p.node_parent[c.node0 + nd];
+}
+__device__ __forceinline__ void nd_set_parent(const SeqPools& p, const Cx& c, u32 nd, u32 v) {
+    if (nd < LB_SEQ_NS) c.sm->parent[nd] = v; else p.node_parent[c.node0 + nd] = v;
+}
+__device__ __forceinline__ void nd_add_vis(const SeqPools& p, const Cx& c, u32 nd, int i, i32 d) {
+    if (nd < LB_SEQ_NS) c.sm->vis[nd][i] += d;
+    else { uint2* q = &p.node[(c.node0 + nd) * 32 + i]; q->y = (u32)((i32)q->y + d); }
+}
+__device__ __forceinline__ void set_child_link(const SeqPools& p, const Cx& c, bool kids_are_leaves, u32 child, u32 link) {
+    if (kids_are_leaves) p.leaf[(c.leaf0 + child) * 32].w = link; else nd_set_parent(p, c, child, link);
+}
+// add `delta` visible atoms on the path (parent link of a leaf) -> root
+__device__ __forceinline__ void add_vis(const SeqPools& p, const Cx& c, u32 link, i32 delta) {
+    if (delta != 0 && c.lane == 0) {
         while (link != NODE_NONE) {
             u32 nd = link >> 5;
-            if (lane == 0) nd_add_vis(nd, (int)(link & 31), delta);
-            link = nd_parent(nd);
+            nd_add_vis(p, c, nd, (int)(link & 31), delta);
+            link = nd_parent(p, c, nd);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- insert (child, vis) into node `nd` right after index `after`; room must exist
+__device__ __forceinline__ void node_insert_no_split(const SeqPools& p, const Cx& c, u32 nd, int after, u32 child, i32 vis,
+                                                     bool kids_are_leaves) {
+    int lane = c.lane;
+    uint2 e = nd_get(p, c, nd, lane);
+    int n = __popc(__ballot_sync(LB_FULL, e.x != NODE_NONE));
+    u32 c_up = __shfl_up_sync(LB_FULL, e.x, 1);
+    u32 v_up = __shfl_up_sync(LB_FULL, e.y, 1);
+    int at = after + 1;
+    if (lane == at) { e.x = child; e.y = (u32)vis; }
+    else if (lane > at) { e.x = c_up; e.y = v_up; }
+    __syncwarp();
+    if (lane <= n) nd_set(p, c, nd, lane, e.x, (i32)e.y);
+    if (lane >= at && lane <= n) set_child_link(p, c, kids_are_leaves, e.x, (nd << 5) | (u32)lane);
+    __syncwarp();
+}
+__device__ __forceinline__ i32 node_total(const SeqPools& p, const Cx& c, u32 nd) {
+    return warp_sum((i32)nd_get(p, c, nd, c.lane).y);
+}
+// ---- insert with splits propagating upward
+__device__ __noinline__ void node_insert(const SeqPools& p, Cx c, u32 nd, int after, u32 child, i32 vis, bool kids_are_leaves) {
+    SeqSmem* sm = c.sm;
+    int lane = c.lane;
+    while (true) {
+        uint2 e = nd_get(p, c, nd, lane);
+        int n = __popc(__ballot_sync(LB_FULL, e.x != NODE_NONE));
+        if (n < 32) { node_insert_no_split(p, c, nd, after, child, vis, kids_are_leaves); return; }
+        if (sm->n_nodes >= sm->node_cap) { seq_fail(c, LB_ERR(DOC_ERR_CAPACITY)); return; }
+        __syncwarp();
+        u32 nn = sm->n_nodes;
+        __syncwarp();
+        if (lane == 0) sm->n_nodes = nn + 1;
+        // upper half moves to the new node
+        u32 uc = __shfl_down_sync(LB_FULL, e.x, 16);
+        u32 uv = __shfl_down_sync(LB_FULL, e.y, 16);
+        if (lane < 16) {
+            nd_set(p, c, nn, lane, uc, (i32)uv);
+            set_child_link(p, c, kids_are_leaves, uc, (nn << 5) | (u32)lane);
+        } else {
+            nd_set(p, c, nn, lane, NODE_NONE, 0);
+            nd_set(p, c, nd, lane, NODE_NONE, 0);
         }
         __syncwarp();
-    }
-    // ---- insert (child, vis) into node `nd` right after index `after`; room must exist
-    __device__ void node_insert_no_split(u32 nd, int after, u32 child, i32 vis, bool kids_are_leaves) {
-        u32 n = nd_n(nd);
-        u32 c = lane < (int)n ? nd_child(nd, lane) : 0;
-        i32 v = lane < (int)n ? nd_vis(nd, lane) : 0;
-        u32 c_up = __shfl_up_sync(LB_FULL, c, 1);
-        i32 v_up = __shfl_up_sync(LB_FULL, v, 1);
-        int at = after + 1;
-        if (lane == at) { c = child; v = vis; }
-        else if (lane > at) { c = c_up; v = v_up; }
-        if (lane <= (int)n) nd_set(nd, lane, c, v);
-        if (lane >= at && lane <= (int)n) {   // the new child and every child that moved one place up
-            u32 link = (nd << 5) | (u32)lane;
-            if (kids_are_leaves) p.leaf_parent[leaf0 + c] = link; else nd_set_parent(c, link);
-        }
-        if (lane == 0) nd_set_n(nd, n + 1);
-        __syncwarp();
-    }
-    __device__ i32 node_total(u32 nd) {
-        u32 n = nd_n(nd);
-        return warp_sum(lane < (int)n ? nd_vis(nd, lane) : 0);
-    }
-    // ---- insert with splits propagating upward
-    __device__ void node_insert(u32 nd, int after, u32 child, i32 vis, bool kids_are_leaves) {
-        while (true) {
-            u32 n = nd_n(nd);
-            if (n < 32) { node_insert_no_split(nd, after, child, vis, kids_are_leaves); return; }
-            if (n_nodes >= node_cap) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
+        if (after >= 16) node_insert_no_split(p, c, nn, after - 16, child, vis, kids_are_leaves);
+        else node_insert_no_split(p, c, nd, after, child, vis, kids_are_leaves);
+        i32 tot_old = node_total(p, c, nd), tot_new = node_total(p, c, nn);
+        u32 plink = nd_parent(p, c, nd);
+        __syncwarp();   // every lane has read the parent link before it is rewritten
+        if (plink == NODE_NONE) {
+            if (sm->n_nodes >= sm->node_cap) { seq_fail(c, LB_ERR(DOC_ERR_CAPACITY)); return; }
             __syncwarp();
-            u32 nn = n_nodes++;
-            u32 c = nd_child(nd, lane);
-            i32 v = nd_vis(nd, lane);
+            u32 nr = sm->n_nodes;
+            u32 h = sm->height;
             __syncwarp();
-            if (lane >= 16) {
-                nd_set(nn, lane - 16, c, v);
-                u32 link = (nn << 5) | (u32)(lane - 16);
-                if (kids_are_leaves) p.leaf_parent[leaf0 + c] = link; else nd_set_parent(c, link);
+            nd_set(p, c, nr, lane, lane == 0 ? nd : (lane == 1 ? nn : NODE_NONE), lane == 0 ? tot_old : (lane == 1 ? tot_new : 0));
+            if (lane == 0) {
+                nd_set_parent(p, c, nr, NODE_NONE);
+                nd_set_parent(p, c, nd, (nr << 5) | 0u);
+                nd_set_parent(p, c, nn, (nr << 5) | 1u);
+                sm->n_nodes = nr + 1;
+                sm->root = nr;
+                sm->height = h + 1;
             }
-            if (lane == 0) { nd_set_n(nd, 16); nd_set_n(nn, 16); }
             __syncwarp();
-            if (after >= 16) node_insert_no_split(nn, after - 16, child, vis, kids_are_leaves);
-            else node_insert_no_split(nd, after, child, vis, kids_are_leaves);
-            i32 tot_old = node_total(nd), tot_new = node_total(nn);
-            u32 plink = nd_parent(nd);
-            __syncwarp();   // every lane has read the parent link before it is rewritten
-            if (plink == NODE_NONE) {
-                if (n_nodes >= node_cap) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
-                u32 nr = n_nodes++;
-                if (lane == 0) {
-                    nd_set(nr, 0, nd, tot_old);
-                    nd_set(nr, 1, nn, tot_new);
-                    nd_set_n(nr, 2);
-                    nd_set_parent(nr, NODE_NONE);
-                    nd_set_parent(nd, (nr << 5) | 0u);
-                    nd_set_parent(nn, (nr << 5) | 1u);
-                }
-                __syncwarp();
-                root = nr;
-                height++;
-                return;
-            }
-            u32 parent = plink >> 5;
-            int idx = (int)(plink & 31);
-            if (lane == 0) nd_set(parent, idx, nd, tot_old);
-            __syncwarp();
-            child = nn;
-            vis = tot_new;
-            after = idx;
-            nd = parent;
-            kids_are_leaves = false;
+            return;
         }
-    }
-    // ---- leaf helpers
-    __device__ __forceinline__ LeafImg leaf_load(u32 leaf) {
-        LeafImg L;
-        L.n = p.leaf_n[leaf0 + leaf];
-        u64 b = (leaf0 + leaf) * 32 + lane;
-        bool in = lane < (int)L.n;
-        u32 ps = in ? p.leaf_ps[b] : ((u32)PEER_NONE | (1u << 16));
-        L.peer = (u16)ps;
-        L.st = (u16)(ps >> 16);
-        L.ctr = in ? p.leaf_ctr[b] : 0;
-        L.len = in ? p.leaf_len[b] : 0;
-        return L;
-    }
-    __device__ __forceinline__ void leaf_store(u32 leaf, const LeafImg& L, u32 new_n) {
-        u64 b = (leaf0 + leaf) * 32 + lane;
-        if (lane < (int)new_n) {
-            p.leaf_ps[b] = (u32)L.peer | ((u32)L.st << 16);
-            p.leaf_ctr[b] = L.ctr;
-            p.leaf_len[b] = L.len;
-        }
-        if (lane == 0) p.leaf_n[leaf0 + leaf] = new_n;
-        __syncwarp();
-    }
-    // slot of the span containing atom (peer, c) inside a loaded leaf image
-    __device__ __forceinline__ int slot_of(const LeafImg& L, u32 peer, i32 c) {
-        unsigned m = __ballot_sync(LB_FULL, lane < (int)L.n && L.peer == (u16)peer && c >= L.ctr && c < L.ctr + L.len);
-        return __ffs(m) - 1;
-    }
-    // ---- split a full leaf: upper 16 slots move to a new leaf (their atom -> leaf entries follow)
-    __device__ void leaf_split(u32 leaf) {
-        if (n_leaves >= leaf_cap) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
-        __syncwarp();
-        u32 nl = n_leaves++;
-        LeafImg L = leaf_load(leaf);
-        i32 vis = L.st == 0 ? L.len : 0;
-        if (lane >= 16) {
-            u64 dst = (leaf0 + nl) * 32 + lane - 16;
-            p.leaf_ps[dst] = (u32)L.peer | ((u32)L.st << 16);
-            p.leaf_ctr[dst] = L.ctr;
-            p.leaf_len[dst] = L.len;
-            if (L.peer != PEER_UNKNOWN) p.atom_leaf[atom_index(L.peer, L.ctr)] = nl;
-        }
-        // long spans: their remaining atoms cooperatively
-        unsigned longm = __ballot_sync(LB_FULL, lane >= 16 && L.len > 1 && L.peer != PEER_UNKNOWN);
-        while (longm) {
-            int s = __ffs(longm) - 1;
-            longm &= longm - 1;
-            u32 sp = __shfl_sync(LB_FULL, (u32)L.peer, s);
-            i32 sc = __shfl_sync(LB_FULL, L.ctr, s);
-            i32 sl = __shfl_sync(LB_FULL, L.len, s);
-            u64 a0 = atom_index(sp, sc);
-            for (i32 i = 1 + lane; i < sl; i += 32) p.atom_leaf[a0 + i] = nl;
-        }
-        unsigned unk = __ballot_sync(LB_FULL, lane >= 16 && L.peer == PEER_UNKNOWN);
-        if (unk) unk_leaf = nl;
-        i32 moved = warp_sum(lane >= 16 ? vis : 0);
-        if (lane == 0) {
-            p.leaf_n[leaf0 + leaf] = 16;
-            p.leaf_n[leaf0 + nl] = 16;
-            p.leaf_next[leaf0 + nl] = p.leaf_next[leaf0 + leaf];
-            p.leaf_next[leaf0 + leaf] = nl;
-        }
-        __syncwarp();
-        u32 plink = p.leaf_parent[leaf0 + leaf];
         u32 parent = plink >> 5;
         int idx = (int)(plink & 31);
-        if (lane == 0) nd_add_vis(parent, idx, -moved);
+        if (lane == 0) nd_set(p, c, parent, idx, nd, tot_old);
         __syncwarp();
-        node_insert(parent, idx, nl, moved, true);
+        child = nn;
+        vis = tot_new;
+        after = idx;
+        nd = parent;
+        kids_are_leaves = false;
     }
-    // ---- open one empty slot at index `at` (0..n) of `leaf`, splitting the leaf first when it is full.
-    // On return (leaf, at) name the opened slot, T is the shifted register image (slot `at` to be filled by
-    // the caller) and the leaf must be written back with leaf_store(leaf, T, T.n + 1).
-    __device__ void leaf_open(u32& leaf, int& at, LeafImg& T) {
-        if (T.n >= 32) {
-            leaf_split(leaf);
-            if (err) return;
-            if (at > 16) { leaf = p.leaf_next[leaf0 + leaf]; at -= 16; }
-            T = leaf_load(leaf);
-        }
-        u16 pe = __shfl_up_sync(LB_FULL, T.peer, 1);
-        i32 ct = __shfl_up_sync(LB_FULL, T.ctr, 1);
-        i32 ln = __shfl_up_sync(LB_FULL, T.len, 1);
-        u16 st = __shfl_up_sync(LB_FULL, T.st, 1);
-        if (lane > at) { T.peer = pe; T.ctr = ct; T.len = ln; T.st = st; }
+}
+
+// ---- split a full leaf: upper 16 slots move to a new leaf (their atom -> leaf entries follow)
+__device__ __noinline__ void leaf_split(const SeqPools& p, Cx c, u32 leaf) {
+    SeqSmem* sm = c.sm;
+    int lane = c.lane;
+    if (sm->n_leaves >= sm->leaf_cap) { seq_fail(c, LB_ERR(DOC_ERR_CAPACITY)); return; }
+    __syncwarp();
+    u32 nl = sm->n_leaves;
+    __syncwarp();
+    if (lane == 0) sm->n_leaves = nl + 1;
+    uint4 L = leaf_load(p, c, leaf);
+    u32 link = __shfl_sync(LB_FULL, L.w, 0);
+    u32 next = __shfl_sync(LB_FULL, L.w, 1);
+    uint4 U;
+    U.x = __shfl_down_sync(LB_FULL, L.x, 16);
+    U.y = __shfl_down_sync(LB_FULL, L.y, 16);
+    U.z = __shfl_down_sync(LB_FULL, L.z, 16);
+    U.w = lane == 1 ? next : 0;   // parent link (slot 0) is set by node_insert below
+    if (lane >= 16) { U.x = SLOT_EMPTY; U.y = 0; U.z = 0; }
+    __syncwarp();
+    p.leaf[(c.leaf0 + nl) * 32 + lane] = U;
+    uint4 O = L;
+    if (lane >= 16) { O.x = SLOT_EMPTY; O.y = 0; O.z = 0; }
+    if (lane == 1) O.w = nl;
+    p.leaf[(c.leaf0 + leaf) * 32 + lane] = O;
+    // atoms of the moved spans get their new home
+    u32 pe = s_peer(L);
+    bool moved_real = lane >= 16 && pe != PEER_NONE && pe != PEER_UNKNOWN;
+    if (moved_real) p.atom_leaf[atom_index(c, pe, (i32)L.y)] = nl;
+    unsigned longm = __ballot_sync(LB_FULL, moved_real && (i32)L.z > 1);
+    while (longm) {
+        int s = __ffs(longm) - 1;
+        longm &= longm - 1;
+        u32 sp = __shfl_sync(LB_FULL, pe, s);
+        i32 sc = (i32)__shfl_sync(LB_FULL, L.y, s);
+        i32 sl = (i32)__shfl_sync(LB_FULL, L.z, s);
+        u64 a0 = atom_index(c, sp, sc);
+        for (i32 i = 1 + lane; i < sl; i += 32) p.atom_leaf[a0 + i] = nl;
     }
-    // ---- split the span containing atom (peer, c) right before that atom (FugueSpan::_slice,
-    // fugue_span.rs:257-279); visible totals unchanged.  No-op when (peer, c) already starts a span.
-    __device__ void split_before(u32 peer, i32 c) {
-        u32 leaf = p.atom_leaf[atom_index(peer, c)];
-        LeafImg L = leaf_load(leaf);
-        int slot = slot_of(L, peer, c);
-        if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-        i32 ctr = __shfl_sync(LB_FULL, L.ctr, slot);
-        if (ctr == c) return;
-        if (L.n >= 32) {   // make room first; the span (still whole) may move to the new leaf
-            leaf_split(leaf);
-            if (err) return;
-            leaf = p.atom_leaf[atom_index(peer, c)];
-            L = leaf_load(leaf);
-            slot = slot_of(L, peer, c);
-            if (slot < 0 || L.n >= 32) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
+    unsigned unk = __ballot_sync(LB_FULL, lane >= 16 && pe == PEER_UNKNOWN);
+    if (unk && lane == 0) sm->unk_leaf = nl;
+    i32 moved = warp_sum(lane >= 16 ? s_vis(L) : 0);
+    u32 parent = link >> 5;
+    int idx = (int)(link & 31);
+    if (lane == 0) nd_add_vis(p, c, parent, idx, -moved);
+    __syncwarp();
+    node_insert(p, c, parent, idx, nl, moved, true);
+}
+
+// ---- split the span containing atom (peer, ctr) right before that atom (FugueSpan::_slice,
+// fugue_span.rs:257-279); visible totals unchanged.  No-op when (peer, ctr) already starts a span.
+__device__ __noinline__ void split_before(const SeqPools& p, Cx c, u32 peer, i32 ctr) {
+    int lane = c.lane;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        u32 leaf = p.atom_leaf[atom_index(c, peer, ctr)];
+        if (leaf == LEAF_NONE) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
+        uint4 L = leaf_load(p, c, leaf);
+        int slot = slot_of(L, peer, ctr);
+        if (slot < 0) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
+        i32 s_ctr = (i32)__shfl_sync(LB_FULL, L.y, slot);
+        if (s_ctr == ctr) return;
+        if (leaf_count(L) >= 32) {   // make room first; the span (still whole) may move to the new leaf
+            if (attempt) { seq_fail(c, LB_ERR(DOC_ERR_CAPACITY)); return; }
+            leaf_split(p, c, leaf);
+            if (c.sm->err) return;
+            continue;
         }
-        i32 len = __shfl_sync(LB_FULL, L.len, slot);
-        u16 st = __shfl_sync(LB_FULL, L.st, slot);
-        i32 k = c - ctr;
-        if (lane == slot) L.len = k;               // left part keeps its slot
-        u32 lf = leaf;
-        int at = slot + 1;
-        u16 pe = __shfl_up_sync(LB_FULL, L.peer, 1);
-        i32 ct = __shfl_up_sync(LB_FULL, L.ctr, 1);
-        i32 ln = __shfl_up_sync(LB_FULL, L.len, 1);
-        u16 s2 = __shfl_up_sync(LB_FULL, L.st, 1);
-        if (lane > at) { L.peer = pe; L.ctr = ct; L.len = ln; L.st = s2; }
-        if (lane == at) { L.peer = (u16)peer; L.ctr = c; L.len = len - k; L.st = st; }
-        leaf_store(lf, L, L.n + 1);
-        // origins of the new span start; the right part's atoms may need a new home leaf
-        u64 a_old = atom_index(peer, ctr), a_new = atom_index(peer, c);
-        u16 orp = p.a_or_peer[a_old];
-        i32 orc = p.a_or_ctr[a_old];
-        if (lane == 0) {
-            p.a_ol_peer[a_new] = (u16)peer;
-            p.a_ol_ctr[a_new] = c - 1;
-            p.a_or_peer[a_new] = orp;
-            p.a_or_ctr[a_new] = orc;
-        }
-        if (lf != leaf)
-            for (i32 i = lane; i < len - k; i += 32) p.atom_leaf[a_new + i] = lf;
+        i32 s_len = (i32)__shfl_sync(LB_FULL, L.z, slot);
+        u32 s_x = __shfl_sync(LB_FULL, L.x, slot);
+        i32 k = ctr - s_ctr;
+        u32 ux = __shfl_up_sync(LB_FULL, L.x, 1);
+        u32 uy = __shfl_up_sync(LB_FULL, L.y, 1);
+        u32 uz = __shfl_up_sync(LB_FULL, L.z, 1);
+        if (lane == slot) L.z = (u32)k;                       // left part keeps its slot
+        else if (lane == slot + 1) { L.x = s_x; L.y = (u32)ctr; L.z = (u32)(s_len - k); }
+        else if (lane > slot + 1) { L.x = ux; L.y = uy; L.z = uz; }
+        leaf_store(p, c, leaf, L);
+        // origins of the new span start: left origin is its predecessor, right origin is inherited
+        uint4 og = p.a_org[atom_index(c, peer, s_ctr)];
+        if (lane == 0) p.a_org[atom_index(c, peer, ctr)] = mk4(peer | (og.x & 0xFFFF0000u), (u32)(ctr - 1), og.z, 0);
         __syncwarp();
+        return;
     }
-    // ---- apply a status change to the inserted atoms [lo,hi) of `peer`
-    __device__ void range_set(u32 peer, i32 lo, i32 hi, int set_future, int del_diff) {
-        i32 c = lo;
-        while (c < hi && !err) {
-            u64 ai = atom_index(peer, c);
-            u32 leaf = p.atom_leaf[ai];
-            if (leaf == LEAF_NONE) { c++; continue; }
-            LeafImg L = leaf_load(leaf);
-            int slot = slot_of(L, peer, c);
-            if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-            i32 s_ctr = __shfl_sync(LB_FULL, L.ctr, slot);
-            i32 s_len = __shfl_sync(LB_FULL, L.len, slot);
-            if (s_ctr != c || c + s_len > hi) {
-                // boundaries do not line up with the span: cut it, then look again (rare)
-                if (s_ctr != c) split_before(peer, c);
-                if (!err && s_ctr + s_len > hi) split_before(peer, hi);
-                if (err) return;
-                leaf = p.atom_leaf[ai];
-                L = leaf_load(leaf);
-                slot = slot_of(L, peer, c);
-                if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-                s_len = __shfl_sync(LB_FULL, L.len, slot);
+}
+
+// ---- apply a status change to the inserted atoms [t0,t1) of `peer`: set_future 1/0/-1 (set, clear, keep),
+// del_diff added to the delete counter.  `hint` is a (possibly stale) atom -> leaf lookup of (peer, t0).
+__device__ __noinline__ void range_apply(const SeqPools& p, Cx c, u32 peer, i32 t0, i32 t1, int set_future, int del_diff, u32 hint) {
+    int lane = c.lane;
+    i32 cur = t0;
+    u32 leaf = hint;
+    int guard = 0;
+    while (cur < t1) {
+        if (leaf == LEAF_NONE) {
+            leaf = p.atom_leaf[atom_index(c, peer, cur)];
+            if (leaf == LEAF_NONE) { cur++; continue; }   // never integrated here (foreign container)
+        }
+        uint4 L = leaf_load(p, c, leaf);
+        int slot = slot_of(L, peer, cur);
+        if (slot < 0) {            // stale hint (a leaf split moved the span): look the atom up again
+            if (++guard > 2) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
+            leaf = LEAF_NONE;
+            continue;
+        }
+        i32 s_ctr = (i32)__shfl_sync(LB_FULL, L.y, slot);
+        i32 s_len = (i32)__shfl_sync(LB_FULL, L.z, slot);
+        if (s_ctr != cur || cur + s_len > t1) {
+            // boundaries do not line up with the span: cut it, then look again
+            if (s_ctr != cur) split_before(p, c, peer, cur);
+            if (!c.sm->err && s_ctr + s_len > t1) split_before(p, c, peer, t1);
+            if (c.sm->err) return;
+            leaf = LEAF_NONE;
+            guard = 0;
+            continue;
+        }
+        // every span of the chain cur, cur+len, ... that lives in this leaf and ends inside the range
+        bool mine = false;
+        while (true) {
+            unsigned m = __ballot_sync(LB_FULL, s_peer(L) == peer && (i32)L.y == cur && cur + (i32)L.z <= t1);
+            if (!m) break;
+            int s = __ffs(m) - 1;
+            if (lane == s) mine = true;
+            cur += (i32)__shfl_sync(LB_FULL, L.z, s);
+        }
+        i32 before = mine ? s_vis(L) : 0;
+        if (mine) {
+            u32 st = s_st(L);
+            if (set_future == 1) st |= ST_FUTURE;
+            if (set_future == 0) st &= ~ST_FUTURE;
+            st = (st & ST_FUTURE) | (((st & 0x7FFFu) + (u32)del_diff) & 0x7FFFu);
+            L.x = (L.x & 0xFFFFu) | (st << 16);
+            p.leaf[(c.leaf0 + leaf) * 32 + lane].x = L.x;
+        }
+        i32 delta = warp_sum((mine ? s_vis(L) : 0) - before);
+        add_vis(p, c, __shfl_sync(LB_FULL, L.w, 0), delta);
+        leaf = LEAF_NONE;
+        guard = 0;
+    }
+}
+
+// ---- retreat (dir=-1) / forward (dir=+1) the ops of peer `q` with counters [a,b) that touch container `cidx`.
+// The peer's changes covering [a,b) are enumerated 32 at a time, their op rows flattened over the lanes, so the
+// op records and the atom -> leaf lookups of 32 rows cost one round trip each.
+__device__ __noinline__ void toggle_ops(const SeqPools& p, const SeqTables& t, Cx c, u64 ch0, u32 cidx, u32 q, i32 a, i32 b, int dir) {
+    int lane = c.lane;
+    u32 row_a = t.atom_row[atom_index(c, q, a)], row_b = t.atom_row[atom_index(c, q, b - 1)];
+    u32 pos_a = t.ch_pos[t.op_change[row_a]], pos_b = t.ch_pos[t.op_change[row_b]];
+    for (u32 pb = pos_a; pb <= pos_b && !c.sm->err; pb += 32) {
+        u32 pos = pb + (u32)lane;
+        bool cv = pos <= pos_b;
+        u32 ch = cv ? t.ch_order[ch0 + pos] : 0;
+        u32 r0 = cv ? (u32)t.ch_op0[ch] : 0;
+        i32 nr = cv ? (i32)t.ch_nops[ch] : 0;
+        i32 incl = warp_incl_scan(nr, lane);
+        i32 total = __shfl_sync(LB_FULL, incl, 31);
+        i32 excl = incl - nr;
+        for (i32 g0 = 0; g0 < total && !c.sm->err; g0 += 32) {
+            i32 g = g0 + lane;
+            bool gv = g < total;
+            int j = 0;   // change of flat row g: number of lanes whose inclusive count is <= g
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                i32 v = __shfl_sync(LB_FULL, incl, (j + s - 1) & 31);
+                if (v <= g) j += s;
             }
-            // status change of the whole span + visible-length propagation
-            u16 st = __shfl_sync(LB_FULL, L.st, slot);
-            u16 nst = st;
-            if (set_future == 1) nst |= ST_FUTURE;
-            if (set_future == 0) nst &= (u16)~ST_FUTURE;
-            nst = (u16)((nst & ST_FUTURE) | (((nst & 0x7FFF) + del_diff) & 0x7FFF));
-            if (lane == 0) p.leaf_ps[(leaf0 + leaf) * 32 + slot] = (peer & 0xFFFFu) | ((u32)nst << 16);
-            __syncwarp();
-            i32 before = st == 0 ? s_len : 0, after = nst == 0 ? s_len : 0;
-            add_vis(leaf, after - before);
-            c += s_len;
+            j &= 31;
+            u32 row = __shfl_sync(LB_FULL, r0, j);
+            i32 row_excl = __shfl_sync(LB_FULL, excl, j);
+            row += (u32)(g - row_excl);
+            uint4 rec = mk4(0, 0, 0, 0);
+            u32 aux = 0;
+            if (gv) { rec = t.op_rec[row]; aux = t.op_aux[row]; }
+            u32 kind = REC_KIND(rec.x);
+            i32 rc = (i32)rec.y, rn = (i32)rec.z;
+            i32 c0 = rc > a ? rc : a, c1 = rc + rn < b ? rc + rn : b;
+            bool act = gv && (kind == OPK_SEQ_INS || kind == OPK_SEQ_DEL) && REC_CIDX(rec.x) == cidx && c0 < c1;
+            u32 tp = q;
+            i32 t0 = c0, t1 = c1;
+            int mode = dir < 0 ? 1 : 0;          // inserts: set / clear the future flag ; deletes: keep it, count
+            int dd = 0;
+            if (kind == OPK_SEQ_DEL) {
+                tp = aux;
+                i32 tc = (i32)rec.w;
+                if (!REC_REV(rec.x)) { t0 = tc + (c0 - rc); t1 = tc + (c1 - rc); }
+                else { t0 = tc + (rn - (c1 - rc)); t1 = tc + (rn - (c0 - rc)); }
+                mode = -1;
+                dd = dir;
+            }
+            u32 hint = act ? p.atom_leaf[atom_index(c, tp, t0)] : LEAF_NONE;
+            unsigned m = __ballot_sync(LB_FULL, act);
+            while (m && !c.sm->err) {
+                int s = __ffs(m) - 1;
+                m &= m - 1;
+                range_apply(p, c, __shfl_sync(LB_FULL, tp, s), __shfl_sync(LB_FULL, t0, s), __shfl_sync(LB_FULL, t1, s),
+                            __shfl_sync(LB_FULL, mode, s), __shfl_sync(LB_FULL, dd, s), __shfl_sync(LB_FULL, hint, s));
+            }
         }
     }
-    // ---- retreat (dir=-1) / forward (dir=+1) the ops of `peer` with counters [a,b) that touch this container
-    __device__ void toggle_ops(u32 peer, i32 a, i32 b, int dir) {
-        i32 c = a;
-        while (c < b && !err) {
-            u32 row = t->atom_row[atom_index(peer, c)];
-            i32 r_ctr = t->op_counter[row];
-            i32 r_end = r_ctr + (i32)t->op_len[row];
-            i32 hi = r_end < b ? r_end : b;
-            u8 kind = t->op_kind[row];
-            if (t->op_cidx[row] == cidx) {
-                if (kind == OPK_SEQ_INS) range_set(peer, c, hi, dir < 0 ? 1 : 0, 0);
-                else if (kind == OPK_SEQ_DEL) {
-                    u32 dl = t->op_del[row];
-                    i32 dlen = t->del_len[dl];
-                    i32 n = dlen < 0 ? -dlen : dlen;
-                    const BlockInfo& bi = t->blocks[t->ch_block[t->op_change[row]]];
-                    u32 tp = t->peer_map[bi.peer0 + t->del_peer_idx[dl]];
-                    i32 tc = t->del_counter[dl];
-                    i32 t0, t1;
-                    if (dlen > 0) { t0 = tc + (c - r_ctr); t1 = tc + (hi - r_ctr); }
-                    else { t0 = tc + (n - (hi - r_ctr)); t1 = tc + (n - (c - r_ctr)); }
-                    range_set(tp, t0, t1, -1, dir);
+}
+
+// ---- move the tracker of the active container to version vv (+ the author's own counter)
+__device__ __forceinline__ void checkout(const SeqPools& p, const SeqTables& t, const Cx& c, u64 ch0, u32 cidx, const i32* vv,
+                                         u32 own_peer, i32 own_ctr) {
+    int lane = c.lane;
+    for (u32 q0 = 0; q0 < c.P && !c.sm->err; q0 += 32) {
+        u32 q = q0 + (u32)lane;
+        i32 tgt = 0, cur = 0;
+        if (q < c.P) {
+            tgt = vv ? vv[q] : 0;
+            if (q == own_peer && own_ctr > tgt) tgt = own_ctr;
+            cur = cvv_get(p, c, q);
+        }
+        unsigned m = __ballot_sync(LB_FULL, cur != tgt);
+        while (m && !c.sm->err) {
+            int s = __ffs(m) - 1;
+            m &= m - 1;
+            i32 cu = __shfl_sync(LB_FULL, cur, s), tg = __shfl_sync(LB_FULL, tgt, s);
+            if (cu > tg) toggle_ops(p, t, c, ch0, cidx, q0 + (u32)s, tg, cu, -1);
+            else toggle_ops(p, t, c, ch0, cidx, q0 + (u32)s, cu, tg, +1);
+        }
+        __syncwarp();
+        if (q < c.P && cur != tgt) cvv_set(p, c, q, tgt);
+        __syncwarp();
+    }
+}
+
+// ---- position key of slot (leaf, slot) for cmp_pos (crdt_rope.rs:433-446)
+__device__ __forceinline__ u64 order_key(const SeqPools& p, const Cx& c, u32 leaf, int slot) {
+    u64 key = (u64)slot;
+    int shift = 6;
+    u32 link = p.leaf[(c.leaf0 + leaf) * 32].w;
+    while (link != NODE_NONE) {
+        key |= (u64)(link & 31) << shift;
+        shift += 6;
+        link = nd_parent(p, c, link >> 5);
+    }
+    return key;
+}
+__device__ __forceinline__ u64 order_key_of_atom(const SeqPools& p, const Cx& c, u32 peer, i32 ctr) {
+    u32 leaf;
+    uint4 L;
+    int slot;
+    if (peer == PEER_UNKNOWN) {
+        leaf = c.sm->unk_leaf;
+        L = leaf_load(p, c, leaf);
+        slot = __ffs(__ballot_sync(LB_FULL, s_peer(L) == PEER_UNKNOWN)) - 1;
+    } else {
+        leaf = p.atom_leaf[atom_index(c, peer, ctr)];
+        L = leaf_load(p, c, leaf);
+        slot = slot_of(L, peer, ctr);
+    }
+    return order_key(p, c, leaf, slot);
+}
+// origin_left of atom (peer, ctr): stored for span starts, implied inside a span
+__device__ __forceinline__ void atom_origin_left(const SeqPools& p, const Cx& c, u32 peer, i32 ctr, u32* op, i32* oc) {
+    if (peer == PEER_UNKNOWN) { *op = PEER_NONE; *oc = -1; return; }
+    u64 ai = atom_index(c, peer, ctr);
+    u32 leaf = p.atom_leaf[ai];
+    uint4 L = leaf_load(p, c, leaf);
+    int slot = slot_of(L, peer, ctr);
+    i32 s_ctr = (i32)__shfl_sync(LB_FULL, L.y, slot < 0 ? 0 : slot);
+    if (slot >= 0 && s_ctr == ctr) { uint4 og = p.a_org[ai]; *op = og.x & 0xFFFFu; *oc = (i32)og.y; }
+    else { *op = peer; *oc = ctr - 1; }
+}
+
+// ---- Fugue sibling scan among the concurrent (future) spans between the cursor and origin_right
+// (crdt_rope.rs:101-201).  Uniform serial code on the rare path.
+struct SibIn {
+    u32 leaf; int from; u32 n_between;
+    u32 ol_peer; i32 ol_ctr; u32 or_peer; i32 or_ctr;
+    bool pr_valid; u32 pr_leaf; int pr_slot;
+    u64 my_peer_id;
+};
+struct SibOut { bool after_valid; u32 after_peer; i32 after_ctr; };
+__device__ __noinline__ SibOut sibling_scan(const SeqPools& p, Cx c, SibIn in) {
+    SibOut out;
+    out.after_valid = false;
+    out.after_peer = 0;
+    out.after_ctr = 0;
+    u32 ol_peer = in.ol_peer, or_peer = in.or_peer;
+    i32 ol_ctr = in.ol_ctr, or_ctr = in.or_ctr;
+    // right parent of the new span: origin_right counts only if its origin_left equals ours
+    bool pr_valid = in.pr_valid;
+    u64 pr_key = 0;
+    if (pr_valid) {
+        u32 e_olp;
+        i32 e_olc;
+        if (or_peer == PEER_UNKNOWN) { e_olp = PEER_NONE; e_olc = -1; }
+        else { uint4 og = p.a_org[atom_index(c, or_peer, or_ctr)]; e_olp = og.x & 0xFFFFu; e_olc = (i32)og.y; }
+        pr_valid = e_olp == ol_peer && (ol_peer == PEER_NONE || e_olc == ol_ctr);
+        if (pr_valid) pr_key = order_key(p, c, in.pr_leaf, in.pr_slot);
+    }
+    bool scanning = false;
+    u64 first_key = 0;
+    bool have_first = false;
+    u32 l2 = in.leaf;
+    int from = in.from;
+    u32 seen = 0;
+    bool stop = false;
+    while (l2 != LEAF_NONE && seen < in.n_between && !stop) {
+        uint4 S = leaf_load(p, c, l2);
+        int n = leaf_count(S);
+        u32 next = __shfl_sync(LB_FULL, S.w, 1);
+        for (int s = from; s < n && seen < in.n_between && !stop; s++) {
+            u32 o_peer = __shfl_sync(LB_FULL, S.x, s) & 0xFFFFu;
+            i32 o_ctr = (i32)__shfl_sync(LB_FULL, S.y, s);
+            seen++;
+            u64 o_key = order_key(p, c, l2, s);
+            if (!have_first) { first_key = o_key; have_first = true; }
+            uint4 oo = p.a_org[atom_index(c, o_peer, o_ctr)];
+            u32 o_olp = oo.x & 0xFFFFu, o_orp = oo.x >> 16;
+            i32 o_olc = (i32)oo.y, o_orc = (i32)oo.z;
+            bool same_ol = o_olp == ol_peer && (ol_peer == PEER_NONE || o_olc == ol_ctr);
+            if (!same_ol) {
+                // "visited" is a prefix of the in-between spans: membership is a position test
+                bool in_visited = false;
+                if (o_olp != PEER_NONE && o_olp != PEER_UNKNOWN && p.atom_leaf[atom_index(c, o_olp, o_olc)] != LEAF_NONE) {
+                    u64 lk = order_key_of_atom(p, c, o_olp, o_olc);
+                    in_visited = lk >= first_key && lk < o_key;
+                }
+                if (!in_visited) { stop = true; break; }
+            }
+            if (same_ol) {
+                bool same_or = o_orp == or_peer && (or_peer == PEER_NONE || o_orc == or_ctr);
+                u64 o_peer_id = c.dpeer[o_peer].id;
+                if (same_or) {
+                    if (o_peer_id > in.my_peer_id) { stop = true; break; }
+                    scanning = false;
+                } else {
+                    bool o_pr = false;
+                    u64 o_pr_key = 0;
+                    if (o_orp != PEER_NONE) {
+                        u32 e_olp;
+                        i32 e_olc;
+                        atom_origin_left(p, c, o_orp, o_orc, &e_olp, &e_olc);
+                        if (e_olp == ol_peer && (ol_peer == PEER_NONE || e_olc == ol_ctr)) {
+                            o_pr = true;
+                            o_pr_key = order_key_of_atom(p, c, o_orp, o_orc);
+                        }
+                    }
+                    int cmp;
+                    if (o_pr && pr_valid) cmp = o_pr_key < pr_key ? -1 : (o_pr_key > pr_key ? 1 : 0);
+                    else if (o_pr) cmp = -1;
+                    else if (pr_valid) cmp = 1;
+                    else cmp = 0;
+                    if (cmp < 0) scanning = true;
+                    else if (cmp == 0 && o_peer_id > in.my_peer_id) { stop = true; break; }
+                    else scanning = false;
                 }
             }
-            c = hi;
+            if (!scanning) { out.after_valid = true; out.after_peer = o_peer; out.after_ctr = o_ctr; }
         }
+        l2 = next;
+        from = 0;
     }
-    __device__ void checkout(const i32* vv, u32 own_peer, i32 own_ctr) {
-        u32 P = di->P;
-        for (u32 q = 0; q < P && !err; q++) {
-            i32 tgt = vv ? vv[q] : 0;
-            if (q == own_peer && own_ctr > tgt) tgt = own_ctr;
-            i32 cur = p.cvv[cvv0 + q];
-            if (cur > tgt) toggle_ops(q, tgt, cur, -1);
-            else if (cur < tgt) toggle_ops(q, cur, tgt, +1);
-            __syncwarp();
-            if (cur != tgt && lane == 0) p.cvv[cvv0 + q] = tgt;
-        }
-        __syncwarp();
-    }
-    // ---- position key of slot (leaf, slot) for cmp_pos (crdt_rope.rs:433-446)
-    __device__ u64 order_key(u32 leaf, int slot) {
-        u64 key = (u64)slot;
-        int shift = 6;
-        u32 link = p.leaf_parent[leaf0 + leaf];
-        while (link != NODE_NONE) {
-            key |= (u64)(link & 31) << shift;
-            shift += 6;
-            link = nd_parent(link >> 5);
-        }
-        return key;
-    }
-    __device__ u64 order_key_of_atom(u32 peer, i32 c) {
-        if (peer == PEER_UNKNOWN) {
-            LeafImg L = leaf_load(unk_leaf);
-            unsigned m = __ballot_sync(LB_FULL, lane < (int)L.n && L.peer == PEER_UNKNOWN);
-            return order_key(unk_leaf, __ffs(m) - 1);
-        }
-        u32 leaf = p.atom_leaf[atom_index(peer, c)];
-        LeafImg L = leaf_load(leaf);
-        return order_key(leaf, slot_of(L, peer, c));
-    }
-    // origin_left of atom (peer, c): stored for span starts, implied inside a span
-    __device__ void atom_origin_left(u32 peer, i32 c, u16* op, i32* oc) {
-        if (peer == PEER_UNKNOWN) { *op = PEER_NONE; *oc = -1; return; }
-        u32 leaf = p.atom_leaf[atom_index(peer, c)];
-        LeafImg L = leaf_load(leaf);
-        int slot = slot_of(L, peer, c);
-        i32 s_ctr = __shfl_sync(LB_FULL, L.ctr, slot);
-        if (s_ctr == c) { u64 a = atom_index(peer, c); *op = p.a_ol_peer[a]; *oc = p.a_ol_ctr[a]; }
-        else { *op = (u16)peer; *oc = c - 1; }
-    }
+    return out;
+}
 
-    // ---- CrdtRope::insert (crdt_rope.rs:43-227)
-    __device__ void insert(u32 peer, i32 ctr, i32 len, i32 pos) {
+// ---- CrdtRope::insert (crdt_rope.rs:43-227)
+__device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 peer, i32 ctr, i32 len, i32 pos) {
+    SeqSmem* sm = c.sm;
+    int lane = c.lane;
+    for (int attempt = 0; attempt < 4; attempt++) {
         // 1. cursor: right after the pos-th visible atom (prefer-left)
-        u32 leaf = first_leaf;
-        int slot = 0;
-        i32 off = 0, rem = pos;
+        u32 leaf = sm->first_leaf;
+        i32 rem = pos;
         if (pos > 0) {
-            u32 nd = root;
-            for (u32 lvl = height; lvl >= 1; lvl--) {
-                u32 n = nd_n(nd);
-                i32 v = lane < (int)n ? nd_vis(nd, lane) : 0;
+            u32 nd = sm->root;
+            for (u32 lvl = sm->height; lvl >= 1; lvl--) {
+                uint2 e = nd_get(p, c, nd, lane);
+                i32 v = (i32)e.y;
                 i32 incl = warp_incl_scan(v, lane);
-                unsigned m = __ballot_sync(LB_FULL, lane < (int)n && incl >= rem);
+                unsigned m = __ballot_sync(LB_FULL, e.x != NODE_NONE && incl >= rem);
                 int idx = __ffs(m) - 1;
-                if (idx < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+                if (idx < 0) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
                 rem -= __shfl_sync(LB_FULL, incl - v, idx);
-                nd = nd_child(nd, idx);
+                nd = __shfl_sync(LB_FULL, e.x, idx);
             }
             leaf = nd;
         }
-        LeafImg L = leaf_load(leaf);
-        u16 ol_peer = PEER_NONE;
+        uint4 L = leaf_load(p, c, leaf);
+        int n = leaf_count(L);
+        int slot = 0;
+        i32 off = 0;
+        u32 ol_peer = PEER_NONE;
         i32 ol_ctr = -1;
-        u32 cur_peer = PEER_NONE;
+        u32 cur_x = 0;
         i32 cur_ctr = 0, cur_len = 0;
         if (pos > 0) {
-            i32 v = L.st == 0 ? L.len : 0;
+            i32 v = s_vis(L);
             i32 incl = warp_incl_scan(v, lane);
-            unsigned m = __ballot_sync(LB_FULL, lane < (int)L.n && incl >= rem);
+            unsigned m = __ballot_sync(LB_FULL, incl >= rem && v > 0);
             slot = __ffs(m) - 1;
-            if (slot < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
+            if (slot < 0) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
             off = rem - __shfl_sync(LB_FULL, incl - v, slot);
-            cur_peer = __shfl_sync(LB_FULL, (u32)L.peer, slot);
-            cur_ctr = __shfl_sync(LB_FULL, L.ctr, slot);
-            cur_len = __shfl_sync(LB_FULL, L.len, slot);
-            if (cur_peer == PEER_UNKNOWN) { err = LB_ERR(DOC_ERR_CORRUPT); return; }  // beyond the content
-            ol_peer = (u16)cur_peer;
+            cur_x = __shfl_sync(LB_FULL, L.x, slot);
+            cur_ctr = (i32)__shfl_sync(LB_FULL, L.y, slot);
+            cur_len = (i32)__shfl_sync(LB_FULL, L.z, slot);
+            if ((cur_x & 0xFFFFu) == PEER_UNKNOWN) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }  // beyond the content
+            ol_peer = cur_x & 0xFFFFu;
             ol_ctr = cur_ctr + off - 1;
         }
+        u32 cur_peer = cur_x & 0xFFFFu;
+        bool mid = pos > 0 && off < cur_len;      // the cursor sits inside a span: that span gets cut
         // 2. origin_right: first non-future span at/after the cursor; skipped spans are "in between"
-        u16 or_peer = PEER_NONE;
+        u32 or_peer = PEER_NONE;
         i32 or_ctr = -1;
-        bool pr_valid = false;        // is there a right parent?
+        bool pr_valid = false;
         u32 pr_leaf = 0;
         int pr_slot = 0;
         u32 n_between = 0;
-        int scan_from = (pos > 0 && off >= cur_len) ? slot + 1 : slot;
-        if (pos > 0 && off < cur_len) {
-            or_peer = (u16)cur_peer;
+        int scan_from = pos > 0 ? slot + 1 : 0;
+        if (mid) {
+            or_peer = cur_peer;
             or_ctr = cur_ctr + off;
         } else {
             u32 l2 = leaf;
             int from = scan_from;
-            LeafImg S = L;
+            uint4 S = L;
             while (true) {
-                bool cand = lane >= from && lane < (int)S.n;
-                unsigned nonfut = __ballot_sync(LB_FULL, cand && !(S.st & ST_FUTURE));
-                unsigned fut = __ballot_sync(LB_FULL, cand && (S.st & ST_FUTURE));
+                bool cand = lane >= from && s_peer(S) != PEER_NONE;
+                unsigned nonfut = __ballot_sync(LB_FULL, cand && !(S.x & (ST_FUTURE << 16)));
+                unsigned fut = __ballot_sync(LB_FULL, cand && (S.x & (ST_FUTURE << 16)));
                 if (nonfut) {
                     int f = __ffs(nonfut) - 1;
                     n_between += __popc(fut & ((1u << f) - 1));
-                    or_peer = (u16)__shfl_sync(LB_FULL, (u32)S.peer, f);
-                    or_ctr = __shfl_sync(LB_FULL, S.ctr, f);
+                    or_peer = __shfl_sync(LB_FULL, S.x, f) & 0xFFFFu;
+                    or_ctr = (i32)__shfl_sync(LB_FULL, S.y, f);
                     pr_leaf = l2;
                     pr_slot = f;
-                    pr_valid = true;   // provisional: confirmed below only when needed
+                    pr_valid = true;   // provisional: confirmed by the sibling scan only when needed
                     break;
                 }
                 n_between += __popc(fut);
-                l2 = p.leaf_next[leaf0 + l2];
+                l2 = __shfl_sync(LB_FULL, S.w, 1);
                 if (l2 == LEAF_NONE) break;
                 from = 0;
-                S = leaf_load(l2);
+                S = leaf_load(p, c, l2);
             }
         }
-        // 3. Fugue sibling scan among the concurrent (future) spans (rare path; uniform serial code)
-        bool after_valid = false;
-        u32 after_peer = 0;
-        i32 after_ctr = 0;   // insert right after the span starting at this atom
+        // 3. where to put it
+        u32 tgt_leaf = leaf;
+        int at = pos > 0 ? slot + 1 : 0;
         if (n_between) {
-            // right parent of the new span: origin_right counts only if its origin_left equals ours
-            u64 pr_key = 0;
-            if (pr_valid) {
-                u16 e_olp;
-                i32 e_olc;
-                if (or_peer == PEER_UNKNOWN) { e_olp = PEER_NONE; e_olc = -1; }
-                else { u64 a = atom_index(or_peer, or_ctr); e_olp = p.a_ol_peer[a]; e_olc = p.a_ol_ctr[a]; }
-                pr_valid = e_olp == ol_peer && (ol_peer == PEER_NONE || e_olc == ol_ctr);
-                if (pr_valid) pr_key = order_key(pr_leaf, pr_slot);
-            }
-            bool scanning = false;
-            u64 my_peer_id = t->dpeer[di->peer0 + peer].id;
-            u64 first_key = 0;
-            bool have_first = false;
-            u32 l2 = leaf;
-            int from = scan_from;
-            u32 seen = 0;
-            bool stop = false;
-            while (l2 != LEAF_NONE && seen < n_between && !stop) {
-                u32 n = p.leaf_n[leaf0 + l2];
-                for (int s = from; s < (int)n && seen < n_between && !stop; s++) {
-                    u64 si = (leaf0 + l2) * 32 + s;
-                    u32 o_peer = p.leaf_ps[si] & 0xFFFFu;
-                    i32 o_ctr = p.leaf_ctr[si];
-                    seen++;
-                    u64 o_key = order_key(l2, s);
-                    if (!have_first) { first_key = o_key; have_first = true; }
-                    u64 oa = atom_index(o_peer, o_ctr);
-                    u16 o_olp = p.a_ol_peer[oa];
-                    i32 o_olc = p.a_ol_ctr[oa];
-                    bool same_ol = o_olp == ol_peer && (ol_peer == PEER_NONE || o_olc == ol_ctr);
-                    if (!same_ol) {
-                        // "visited" is a prefix of the in-between spans: membership is a position test
-                        bool in_visited = false;
-                        if (o_olp != PEER_NONE && o_olp != PEER_UNKNOWN && p.atom_leaf[atom_index(o_olp, o_olc)] != LEAF_NONE) {
-                            u64 lk = order_key_of_atom(o_olp, o_olc);
-                            in_visited = lk >= first_key && lk < o_key;
-                        }
-                        if (!in_visited) { stop = true; break; }
-                    }
-                    if (same_ol) {
-                        u16 o_orp = p.a_or_peer[oa];
-                        i32 o_orc = p.a_or_ctr[oa];
-                        bool same_or = o_orp == or_peer && (or_peer == PEER_NONE || o_orc == or_ctr);
-                        u64 o_peer_id = t->dpeer[di->peer0 + o_peer].id;
-                        if (same_or) {
-                            if (o_peer_id > my_peer_id) { stop = true; break; }
-                            scanning = false;
-                        } else {
-                            bool o_pr = false;
-                            u64 o_pr_key = 0;
-                            if (o_orp != PEER_NONE) {
-                                u16 e_olp;
-                                i32 e_olc;
-                                atom_origin_left(o_orp, o_orc, &e_olp, &e_olc);
-                                if (e_olp == ol_peer && (ol_peer == PEER_NONE || e_olc == ol_ctr)) {
-                                    o_pr = true;
-                                    o_pr_key = order_key_of_atom(o_orp, o_orc);
-                                }
-                            }
-                            int cmp;
-                            if (o_pr && pr_valid) cmp = o_pr_key < pr_key ? -1 : (o_pr_key > pr_key ? 1 : 0);
-                            else if (o_pr) cmp = -1;
-                            else if (pr_valid) cmp = 1;
-                            else cmp = 0;
-                            if (cmp < 0) scanning = true;
-                            else if (cmp == 0 && o_peer_id > my_peer_id) { stop = true; break; }
-                            else scanning = false;
-                        }
-                    }
-                    if (!scanning) { after_valid = true; after_peer = o_peer; after_ctr = o_ctr; }
-                }
-                l2 = p.leaf_next[leaf0 + l2];
-                from = 0;
+            SibIn in;
+            in.leaf = leaf; in.from = scan_from; in.n_between = n_between;
+            in.ol_peer = ol_peer; in.ol_ctr = ol_ctr; in.or_peer = or_peer; in.or_ctr = or_ctr;
+            in.pr_valid = pr_valid; in.pr_leaf = pr_leaf; in.pr_slot = pr_slot;
+            in.my_peer_id = c.dpeer[peer].id;
+            SibOut so = sibling_scan(p, c, in);
+            if (so.after_valid) {
+                tgt_leaf = p.atom_leaf[atom_index(c, so.after_peer, so.after_ctr)];
+                if (tgt_leaf != leaf) { L = leaf_load(p, c, tgt_leaf); n = leaf_count(L); }
+                at = slot_of(L, so.after_peer, so.after_ctr) + 1;
+                if (at <= 0) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
+                mid = false;
             }
         }
-        // 4. physical insertion
-        u32 tgt_leaf;
-        int at;
-        LeafImg T;
-        if (after_valid) {
-            tgt_leaf = p.atom_leaf[atom_index(after_peer, after_ctr)];
-            T = leaf_load(tgt_leaf);
-            at = slot_of(T, after_peer, after_ctr) + 1;
-        } else if (pos == 0) {
-            tgt_leaf = first_leaf;
-            T = L;
-            at = 0;
-        } else if (off < cur_len) {
-            split_before(cur_peer, cur_ctr + off);
-            if (err) return;
-            tgt_leaf = p.atom_leaf[atom_index(cur_peer, cur_ctr + off)];   // right part: insert before it
-            T = leaf_load(tgt_leaf);
-            at = slot_of(T, cur_peer, cur_ctr + off);
-        } else {
-            tgt_leaf = leaf;
-            T = L;
-            at = slot + 1;
+        // 4. physical insertion into the loaded image: one new slot, two when the cursor span is cut
+        int need = mid ? 2 : 1;
+        if (n + need > 32) {
+            leaf_split(p, c, tgt_leaf);
+            if (sm->err) return;
+            continue;   // positions moved: locate the cursor again
         }
-        if (at < 0) { err = LB_ERR(DOC_ERR_CORRUPT); return; }
-        leaf_open(tgt_leaf, at, T);
-        if (err) return;
-        if (lane == at) { T.peer = (u16)peer; T.ctr = ctr; T.len = len; T.st = 0; }
-        leaf_store(tgt_leaf, T, T.n + 1);
-        u64 a0 = atom_index(peer, ctr);
-        if (lane == 0) {
-            p.a_ol_peer[a0] = ol_peer;
-            p.a_ol_ctr[a0] = ol_ctr;
-            p.a_or_peer[a0] = or_peer;
-            p.a_or_ctr[a0] = or_ctr;
+        uint4 og = mk4(0, 0, 0, 0);
+        if (mid) og = p.a_org[atom_index(c, cur_peer, cur_ctr)];   // right origin inherited by the cut-off tail
+        u32 link = __shfl_sync(LB_FULL, L.w, 0);
+        u32 ux = __shfl_up_sync(LB_FULL, L.x, need);
+        u32 uy = __shfl_up_sync(LB_FULL, L.y, need);
+        u32 uz = __shfl_up_sync(LB_FULL, L.z, need);
+        if (lane >= at + need) { L.x = ux; L.y = uy; L.z = uz; }
+        if (lane == at) { L.x = peer; L.y = (u32)ctr; L.z = (u32)len; }
+        if (mid) {
+            if (lane == at - 1) L.z = (u32)off;
+            if (lane == at + 1) { L.x = cur_x; L.y = (u32)(cur_ctr + off); L.z = (u32)(cur_len - off); }
         }
+        leaf_store(p, c, tgt_leaf, L);
+        u64 a0 = atom_index(c, peer, ctr);
+        if (lane == 0) p.a_org[a0] = mk4(ol_peer | (or_peer << 16), (u32)ol_ctr, (u32)or_ctr, 0);
+        if (mid && lane == 1)
+            p.a_org[atom_index(c, cur_peer, cur_ctr + off)] = mk4(cur_peer | (og.x & 0xFFFF0000u), (u32)(cur_ctr + off - 1), og.z, 0);
         for (i32 i = lane; i < len; i += 32) p.atom_leaf[a0 + i] = tgt_leaf;
-        __syncwarp();
-        add_vis(tgt_leaf, len);
+        add_vis(p, c, link, len);
+        return;
     }
+    seq_fail(c, LB_ERR(DOC_ERR_CAPACITY));
+}
 
-    // ---- delete by target id (crdt_rope.rs:236-315 ; tracker.rs:173-232)
-    __device__ void del(u32 tpeer, i32 tctr, i32 n) { range_set(tpeer, tctr, tctr + n, -1, +1); }
+// ---- container switching: internal nodes < NS and the tracker version live in shared memory while a
+// container is active
+__device__ __noinline__ void store_container(const SeqPools& p, const SeqTables& t, Cx c, u64 cid0, u32 cidx) {
+    if (cidx == 0xFFFFFFFFu) return;
+    SeqSmem* sm = c.sm;
+    int lane = c.lane;
+    __syncwarp();
+    u32 cached = sm->n_nodes < LB_SEQ_NS ? sm->n_nodes : LB_SEQ_NS;
+    for (u32 nd = 0; nd < cached; nd++) {
+        p.node[(c.node0 + nd) * 32 + lane] = mk2(sm->child[nd][lane], (u32)sm->vis[nd][lane]);
+        if (lane == 0) p.node_parent[c.node0 + nd] = sm->parent[nd];
+    }
+    if ((u32)lane < c.P) p.cvv[c.cvv0 + lane] = sm->cvv[lane];
+    if (lane == 0) {
+        DocContainer& dc = t.dcont[cid0 + cidx];
+        dc.n_leaves = sm->n_leaves;
+        dc.n_nodes = sm->n_nodes;
+        dc.root = sm->root;
+        dc.height = sm->height;
+        dc.first_leaf = sm->first_leaf;
+        dc.unk_sid = sm->unk_leaf;
+    }
+    __syncwarp();
+}
+// returns the container's Cx (pool bases); Tracker::new_with_unknown (tracker.rs:38-63) on first use: one
+// placeholder span of length u32::MAX/4
+__device__ __noinline__ Cx load_container(const SeqPools& p, const SeqTables& t, Cx c, u64 cid0, u32 cidx) {
+    SeqSmem* sm = c.sm;
+    int lane = c.lane;
+    const DocContainer& dc = t.dcont[cid0 + cidx];
+    c.leaf0 = dc.leaf0;
+    c.node0 = dc.node0;
+    c.cvv0 = dc.cvv0;
+    u32 n_leaves = dc.n_leaves, n_nodes = dc.n_nodes;
+    __syncwarp();
+    if (lane == 0) {
+        sm->leaf_cap = dc.leaf_cap;
+        sm->node_cap = dc.node_cap;
+        sm->n_leaves = n_leaves;
+        sm->n_nodes = n_nodes;
+        sm->root = dc.root;
+        sm->height = dc.height;
+        sm->first_leaf = dc.first_leaf;
+        sm->unk_leaf = dc.unk_sid;
+    }
+    if (n_leaves == 0) {
+        if (dc.leaf_cap < 1 || dc.node_cap < 1) { seq_fail(c, LB_ERR(DOC_ERR_CAPACITY)); return c; }
+        if (lane == 0) {
+            sm->n_leaves = 1;
+            sm->n_nodes = 1;
+            sm->root = 0;
+            sm->height = 1;
+            sm->first_leaf = 0;
+            sm->unk_leaf = 0;
+        }
+        // leaf 0: the placeholder span; parent link (node 0, index 0) in slot 0, no next leaf in slot 1
+        p.leaf[c.leaf0 * 32 + lane] = mk4(lane == 0 ? (u32)PEER_UNKNOWN : SLOT_EMPTY, 0, lane == 0 ? (u32)UNKNOWN_LEN : 0u,
+                                          lane == 1 ? LEAF_NONE : 0u);
+        nd_set(p, c, 0, lane, lane == 0 ? 0u : NODE_NONE, lane == 0 ? (i32)UNKNOWN_LEN : 0);
+        if (lane == 0) nd_set_parent(p, c, 0, NODE_NONE);
+        sm->cvv[lane] = 0;
+        for (u32 q = 32 + (u32)lane; q < c.P; q += 32) p.cvv[c.cvv0 + q] = 0;
+        __syncwarp();
+        return c;
+    }
+    u32 cached = n_nodes < LB_SEQ_NS ? n_nodes : LB_SEQ_NS;
+    for (u32 nd = 0; nd < cached; nd++) {
+        uint2 e = p.node[(c.node0 + nd) * 32 + lane];
+        sm->child[nd][lane] = e.x;
+        sm->vis[nd][lane] = (i32)e.y;
+        if (lane == 0) sm->parent[nd] = p.node_parent[c.node0 + nd];
+    }
+    sm->cvv[lane] = (u32)lane < c.P ? p.cvv[c.cvv0 + lane] : 0;
+    __syncwarp();
+    return c;
+}
 
-    // ---- container switching: internal nodes < NS live in shared memory while a container is active
-    __device__ void load_container(u32 c) {
-        DocContainer& dc = t->dcont[di->cid0 + c];
-        cidx = c;
-        leaf0 = dc.leaf0;
-        node0 = dc.node0;
-        leaf_cap = dc.leaf_cap;
-        node_cap = dc.node_cap;
-        n_leaves = dc.n_leaves;
-        n_nodes = dc.n_nodes;
-        root = dc.root;
-        height = dc.height;
-        first_leaf = dc.first_leaf;
-        cvv0 = dc.cvv0;
-        unk_leaf = dc.unk_sid;
-        if (n_leaves == 0) { init_container(); return; }
-        u32 cached = n_nodes < LB_SEQ_NS ? n_nodes : LB_SEQ_NS;
-        for (u32 nd = 0; nd < cached; nd++) {
-            sm->child[nd][lane] = p.node_child[(node0 + nd) * 32 + lane];
-            sm->vis[nd][lane] = p.node_vis[(node0 + nd) * 32 + lane];
-            if (lane == 0) { sm->n[nd] = p.node_n[node0 + nd]; sm->parent[nd] = p.node_parent[node0 + nd]; }
-        }
-        __syncwarp();
-    }
-    __device__ void store_container() {
-        if (cidx == 0xFFFFFFFFu) return;
-        __syncwarp();
-        u32 cached = n_nodes < LB_SEQ_NS ? n_nodes : LB_SEQ_NS;
-        for (u32 nd = 0; nd < cached; nd++) {
-            p.node_child[(node0 + nd) * 32 + lane] = sm->child[nd][lane];
-            p.node_vis[(node0 + nd) * 32 + lane] = sm->vis[nd][lane];
-            if (lane == 0) { p.node_n[node0 + nd] = sm->n[nd]; p.node_parent[node0 + nd] = sm->parent[nd]; }
-        }
-        if (lane == 0) {
-            DocContainer& dc = t->dcont[di->cid0 + cidx];
-            dc.n_leaves = n_leaves;
-            dc.n_nodes = n_nodes;
-            dc.root = root;
-            dc.height = height;
-            dc.first_leaf = first_leaf;
-            dc.unk_sid = unk_leaf;
-        }
-        __syncwarp();
-    }
-    // Tracker::new_with_unknown (tracker.rs:38-63): one placeholder span of length u32::MAX/4
-    __device__ void init_container() {
-        if (leaf_cap < 1 || node_cap < 1) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
-        n_leaves = 1;
-        n_nodes = 1;
-        root = 0;
-        height = 1;
-        first_leaf = 0;
-        unk_leaf = 0;
-        if (lane == 0) {
-            p.leaf_ps[leaf0 * 32] = PEER_UNKNOWN;
-            p.leaf_ctr[leaf0 * 32] = 0;
-            p.leaf_len[leaf0 * 32] = UNKNOWN_LEN;
-            p.leaf_n[leaf0] = 1;
-            p.leaf_parent[leaf0] = 0;   // (node 0 << 5) | index 0
-            p.leaf_next[leaf0] = LEAF_NONE;
-            nd_set(0, 0, 0, UNKNOWN_LEN);
-            nd_set_n(0, 1);
-            nd_set_parent(0, NODE_NONE);
-        }
-        for (u32 q = lane; q < di->P; q += 32) p.cvv[cvv0 + q] = 0;
-        __syncwarp();
-    }
-    // ---- emit the final visible runs of the current container (after checkout to the final version)
-    __device__ void emit_output() {
-        DocContainer& dc = t->dcont[di->cid0 + cidx];
-        u32 n_out = 0;
-        u32 total = 0;
-        u32 l2 = first_leaf;
-        while (l2 != LEAF_NONE) {
-            LeafImg L = leaf_load(l2);
-            bool live = lane < (int)L.n && L.st == 0 && L.peer != PEER_UNKNOWN;
-            unsigned m = __ballot_sync(LB_FULL, live);
-            if (live) {
-                u32 o = n_out + __popc(m & ((1u << lane) - 1));
-                if (o < dc.out_cap) {
-                    u32 row = t->atom_row[atom_index(L.peer, L.ctr)];
-                    p.out_row[dc.out0 + o] = row;
-                    p.out_off[dc.out0 + o] = (u32)(L.ctr - t->op_counter[row]);
-                    p.out_len[dc.out0 + o] = (u32)L.len;
-                }
+// ---- emit the final visible runs of the active container (after checkout to the final version)
+__device__ __noinline__ void emit_output(const SeqPools& p, const SeqTables& t, Cx c, u64 cid0, u32 cidx) {
+    int lane = c.lane;
+    DocContainer& dc = t.dcont[cid0 + cidx];
+    u32 n_out = 0;
+    u32 total = 0;
+    u32 l2 = c.sm->first_leaf;
+    u32 out_cap = dc.out_cap;
+    u64 out0 = dc.out0;
+    while (l2 != LEAF_NONE) {
+        uint4 L = leaf_load(p, c, l2);
+        u32 pe = s_peer(L);
+        bool live = pe != PEER_NONE && pe != PEER_UNKNOWN && s_st(L) == 0;
+        unsigned m = __ballot_sync(LB_FULL, live);
+        if (live) {
+            u32 o = n_out + __popc(m & ((1u << lane) - 1));
+            if (o < out_cap) {
+                u32 row = t.atom_row[atom_index(c, pe, (i32)L.y)];
+                p.out_row[out0 + o] = row;
+                p.out_off[out0 + o] = (u32)((i32)L.y - t.op_counter[row]);
+                p.out_len[out0 + o] = L.z;
             }
-            total += (u32)warp_sum(live ? L.len : 0);
-            n_out += __popc(m);
-            l2 = p.leaf_next[leaf0 + l2];
         }
-        if (n_out > dc.out_cap) err = LB_ERR(DOC_ERR_CAPACITY);
-        __syncwarp();
-        if (lane == 0) {
-            dc.n_out = n_out < dc.out_cap ? n_out : dc.out_cap;
-            dc.seq_len = total;
-        }
-        __syncwarp();
+        total += (u32)warp_sum(live ? (i32)L.z : 0);
+        n_out += __popc(m);
+        l2 = __shfl_sync(LB_FULL, L.w, 1);
     }
-};
+    if (n_out > out_cap) seq_fail(c, LB_ERR(DOC_ERR_CAPACITY));
+    __syncwarp();
+    if (lane == 0) {
+        dc.n_out = n_out < out_cap ? n_out : out_cap;
+        dc.seq_len = total;
+    }
+    __syncwarp();
+}
 
 // one warp per document, LB_SEQ_WARPS documents per CTA
 #ifndef LB_SEQ_MINB
@@ -741,97 +839,116 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
     if (warp_global >= n_docs) return;
     DocInfo& di = docs[warp_global];
     if (di.code != DOC_OK || di.n_applied == 0) return;
+    const u64 cid0 = di.cid0, ch0 = di.ch0, vv0 = di.vv0;
+    const u32 P = di.P, C = di.C, n_applied = di.n_applied;
     bool any = false;
-    for (u32 c = 0; c < di.C; c++)
-        if (tables.dcont[di.cid0 + c].leaf_cap) any = true;
+    for (u32 ci = 0; ci < C; ci++)
+        if (tables.dcont[cid0 + ci].leaf_cap) any = true;
     if (!any) return;
-    Seq s(pools, &tables);
-    s.di = &di;
-    s.sm = &smem[warp_in_cta];
-    s.lane = lane;
-    s.err = 0;
-    s.cidx = 0xFFFFFFFFu;
-    s.atom0 = di.atom0;
-    if (lane < (int)di.P) s.sm->abase[lane] = tables.dpeer[di.peer0 + lane].atom_base;
+    Cx c;
+    c.sm = &smem[warp_in_cta];
+    c.dpeer = tables.dpeer + di.peer0;
+    c.leaf0 = c.node0 = c.cvv0 = 0;
+    c.atom0 = di.atom0;
+    c.P = P;
+    c.lane = lane;
+    SeqSmem* sm = c.sm;
+    sm->abase[lane] = (u32)lane < P ? c.dpeer[lane].atom_base : 0;
+    if (lane == 0) sm->err = 0;
     __syncwarp();
-    for (u64 i = lane; i < di.atom_total; i += 32) pools.atom_leaf[di.atom0 + i] = LEAF_NONE;
-    for (u32 c = lane; c < di.C; c += 32) pools.cont_epoch[di.cid0 + c] = 0xFFFFFFFFu;
+    for (u64 i = lane; i < di.atom_total; i += 32) pools.atom_leaf[c.atom0 + i] = LEAF_NONE;
+    for (u32 ci = lane; ci < C; ci += 32) pools.cont_epoch[cid0 + ci] = 0xFFFFFFFFu;
     __syncwarp();
-    u32 P = di.P;
+    u32 cidx = 0xFFFFFFFFu;
     u32 prev_peer = 0xFFFFFFFFu;
     u32 cur_epoch = 0xFFFFFFFFu;   // epoch of the active container (register; spilled on container switch)
-    for (u32 k = 0; k < di.n_applied && !s.err; k++) {
-        u32 ch = tables.ch_walk[di.ch0 + k];
-        u32 peer = tables.ch_peer[ch];
-        u64 r0 = tables.ch_op0[ch];
-        u32 nr = tables.ch_nops[ch];
-        // fast path (no checkout): the change only depends on its predecessor, which was the previous change
-        // of the walk, and the container's tracker sat at that version when it was last touched
-        bool chain = tables.ch_dep_self[ch] && tables.ch_ndeps[ch] == 0 && prev_peer == peer && k > 0;
-        const i32* vv = nullptr;
-        for (u32 r = 0; r < nr && !s.err; r++) {
-            u64 row = r0 + r;
-            u8 kind = tables.op_kind[row];
-            if (kind != OPK_SEQ_INS && kind != OPK_SEQ_DEL) continue;
-            u32 c = tables.op_cidx[row];
-            i32 ctr = tables.op_counter[row];
-            i32 len = (i32)tables.op_len[row];
-            if (c != s.cidx) {
-                if (s.cidx != 0xFFFFFFFFu && lane == 0) pools.cont_epoch[di.cid0 + s.cidx] = cur_epoch;
-                s.store_container();
-                s.load_container(c);
-                if (s.err) break;
-                cur_epoch = pools.cont_epoch[di.cid0 + c];
-            }
-            if (cur_epoch != k) {
-                if (!(chain && cur_epoch == k - 1)) {
-                    if (!vv) {
-                        const DocPeer& dp = tables.dpeer[di.peer0 + peer];
-                        i32 cc = tables.ch_counter[ch];
-                        u32 lo = 0, hi = dp.ch_count;
-                        while (hi - lo > 1) {
-                            u32 mid = (lo + hi) >> 1;
-                            if (tables.ch_counter[tables.ch_order[di.ch0 + dp.ch_first + mid]] <= cc) lo = mid; else hi = mid;
-                        }
-                        vv = tables.ch_vv + di.vv0 + (u64)(dp.ch_first + lo) * P;
-                    }
-                    s.checkout(vv, peer, ctr);
-                }
-                cur_epoch = k;
-            }
-            if (kind == OPK_SEQ_INS) s.insert(peer, ctr, len, tables.op_prop[row]);
-            else {
-                u32 dl = tables.op_del[row];
-                const BlockInfo& bi = tables.blocks[tables.ch_block[ch]];
-                u32 tp = tables.peer_map[bi.peer0 + tables.del_peer_idx[dl]];
-                s.del(tp, tables.del_counter[dl], len);
-            }
-            // current_vv of the tracker follows its own ops (tracker.rs:131-139, 228-231); in causal order this
-            // entry only grows, and insert()/del() end with a warp barrier
-            if (lane == 0) pools.cvv[s.cvv0 + peer] = ctr + len;
-            __syncwarp();
+    for (u32 kb = 0; kb < n_applied && !sm->err; kb += 32) {
+        // ---- 32 change headers of the walk per round trip
+        u32 kk = kb + (u32)lane;
+        u32 h_ch = 0, h_peer = 0, h_r0 = 0, h_nr = 0, h_pos = 0;
+        bool h_simple = false;
+        if (kk < n_applied) {
+            h_ch = tables.ch_walk[ch0 + kk];
+            h_peer = tables.ch_peer[h_ch];
+            h_r0 = (u32)tables.ch_op0[h_ch];
+            h_nr = tables.ch_nops[h_ch];
+            h_pos = tables.ch_pos[h_ch];
+            h_simple = tables.ch_dep_self[h_ch] && tables.ch_ndeps[h_ch] == 0;
         }
-        prev_peer = peer;
+        u32 cnt = n_applied - kb < 32 ? n_applied - kb : 32;
+        for (u32 j = 0; j < cnt && !sm->err; j++) {
+            u32 k = kb + j;
+            u32 peer = __shfl_sync(LB_FULL, h_peer, j);
+            u32 r0 = __shfl_sync(LB_FULL, h_r0, j);
+            u32 nr = __shfl_sync(LB_FULL, h_nr, j);
+            u32 pos = __shfl_sync(LB_FULL, h_pos, j);
+            // fast path (no checkout): the change only depends on its predecessor, which was the previous change
+            // of the walk, and the container's tracker sat at that version when it was last touched
+            bool chain = __shfl_sync(LB_FULL, (int)h_simple, j) && prev_peer == peer && k > 0;
+            const i32* vv = tables.ch_vv + vv0 + (u64)pos * P;
+            for (u32 rb = 0; rb < nr && !sm->err; rb += 32) {
+                // ---- 32 op records per round trip
+                uint4 rec = mk4(0, 0, 0, 0);
+                u32 aux = 0;
+                if (rb + (u32)lane < nr) { rec = tables.op_rec[r0 + rb + lane]; aux = tables.op_aux[r0 + rb + lane]; }
+                u32 kind_l = REC_KIND(rec.x);
+                // deletes: (possibly stale) home leaf of the first target atom
+                u32 hint_l = kind_l == OPK_SEQ_DEL ? pools.atom_leaf[atom_index(c, aux, (i32)rec.w)] : LEAF_NONE;
+                unsigned m = __ballot_sync(LB_FULL, kind_l == OPK_SEQ_INS || kind_l == OPK_SEQ_DEL);
+                while (m && !sm->err) {
+                    int s = __ffs(m) - 1;
+                    m &= m - 1;
+                    u32 rx = __shfl_sync(LB_FULL, rec.x, s);
+                    i32 ctr = (i32)__shfl_sync(LB_FULL, rec.y, s);
+                    i32 len = (i32)__shfl_sync(LB_FULL, rec.z, s);
+                    i32 prop = (i32)__shfl_sync(LB_FULL, rec.w, s);
+                    u32 ci = REC_CIDX(rx);
+                    if (ci != cidx) {
+                        if (cidx != 0xFFFFFFFFu && lane == 0) pools.cont_epoch[cid0 + cidx] = cur_epoch;
+                        store_container(pools, tables, c, cid0, cidx);
+                        c = load_container(pools, tables, c, cid0, ci);
+                        cidx = ci;
+                        if (sm->err) break;
+                        cur_epoch = pools.cont_epoch[cid0 + ci];
+                    }
+                    if (cur_epoch != k) {
+                        if (!(chain && cur_epoch == k - 1)) checkout(pools, tables, c, ch0, cidx, vv, peer, ctr);
+                        cur_epoch = k;
+                    }
+                    if (REC_KIND(rx) == OPK_SEQ_INS) seq_insert(pools, c, peer, ctr, len, prop);
+                    else   // delete by target id (crdt_rope.rs:236-315 ; tracker.rs:173-232)
+                        range_apply(pools, c, __shfl_sync(LB_FULL, aux, s), prop, prop + len, -1, +1, __shfl_sync(LB_FULL, hint_l, s));
+                    // current_vv of the tracker follows its own ops (tracker.rs:131-139, 228-231); in causal order
+                    // this entry only grows
+                    __syncwarp();
+                    if (lane == 0) cvv_set(pools, c, peer, ctr + len);
+                    __syncwarp();
+                }
+            }
+            prev_peer = peer;
+        }
     }
     // final version = everything applied
-    for (u32 c = 0; c < di.C && !s.err; c++) {
-        const DocContainer& dc = tables.dcont[di.cid0 + c];
-        if (!dc.leaf_cap || (dc.n_leaves == 0 && c != s.cidx)) continue;
-        if (c != s.cidx) {
-            s.store_container();
-            s.load_container(c);
+    for (u32 ci = 0; ci < C && !sm->err; ci++) {
+        const DocContainer& dc = tables.dcont[cid0 + ci];
+        if (!dc.leaf_cap || (dc.n_leaves == 0 && ci != cidx)) continue;
+        if (ci != cidx) {
+            store_container(pools, tables, c, cid0, cidx);
+            c = load_container(pools, tables, c, cid0, ci);
+            cidx = ci;
         }
-        for (u32 q = 0; q < P && !s.err; q++) {
-            i32 tgt = tables.dpeer[di.peer0 + q].end_counter;
-            i32 cur = pools.cvv[s.cvv0 + q];
-            if (cur > tgt) s.toggle_ops(q, tgt, cur, -1);
-            else if (cur < tgt) s.toggle_ops(q, cur, tgt, +1);
+        for (u32 q = 0; q < P && !sm->err; q++) {
+            i32 tgt = c.dpeer[q].end_counter;
+            i32 cur = cvv_get(pools, c, q);
+            if (cur > tgt) toggle_ops(pools, tables, c, ch0, cidx, q, tgt, cur, -1);
+            else if (cur < tgt) toggle_ops(pools, tables, c, ch0, cidx, q, cur, tgt, +1);
             __syncwarp();
-            if (lane == 0) pools.cvv[s.cvv0 + q] = tgt;
+            if (lane == 0) cvv_set(pools, c, q, tgt);
             __syncwarp();
         }
-        if (!s.err) s.emit_output();
+        if (!sm->err) emit_output(pools, tables, c, cid0, cidx);
     }
-    s.store_container();
-    if (lane == 0 && s.err) di.code = s.err;
+    store_container(pools, tables, c, cid0, cidx);
+    __syncwarp();
+    if (lane == 0 && sm->err) di.code = sm->err;
 }

@@ -23,6 +23,7 @@ struct dim3 {
 };
 struct uint3_ { unsigned x, y, z; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
 
 namespace simt {
