@@ -363,6 +363,58 @@ __device__ __noinline__ void range_apply(const SeqPools& p, Cx c, u32 peer, i32 
     }
 }
 
+// ---- lane-local status change: every lane applies its OWN range [t0,t1) of `peer` with atomics (state word of
+// the slot, visible lengths on the path to the root), so 32 ranges proceed at once and their dependent loads
+// overlap.  Handles the spans that line up with the range; returns the first counter that needs the
+// warp-cooperative path (a span must be cut, or the atom is unknown here), t1 when done.  No structure
+// changes happen while lanes run this, so the hints taken at the start of the batch stay valid.
+__device__ __forceinline__ i32 toggle_lane(const SeqPools& p, const Cx& c, u32 peer, i32 t0, i32 t1, int set_future, int del_diff,
+                                           u32 hint) {
+    i32 cur = t0;
+    u32 leaf = hint;
+    while (cur < t1) {
+        if (leaf == LEAF_NONE) {
+            leaf = p.atom_leaf[atom_index(c, peer, cur)];
+            if (leaf == LEAF_NONE) return cur;
+        }
+        uint4* base = p.leaf + (c.leaf0 + leaf) * 32;
+        int found = -1;
+        uint4 sl = mk4(0, 0, 0, 0);
+        u32 link = NODE_NONE;
+#pragma unroll 1
+        for (int s0 = 0; s0 < 32 && found < 0; s0 += 4) {
+            uint4 v0 = base[s0], v1 = base[s0 + 1], v2 = base[s0 + 2], v3 = base[s0 + 3];
+            if (s0 == 0) link = v0.w;
+            if ((v0.x & 0xFFFFu) == peer && cur >= (i32)v0.y && cur < (i32)(v0.y + v0.z)) { found = s0; sl = v0; }
+            else if ((v1.x & 0xFFFFu) == peer && cur >= (i32)v1.y && cur < (i32)(v1.y + v1.z)) { found = s0 + 1; sl = v1; }
+            else if ((v2.x & 0xFFFFu) == peer && cur >= (i32)v2.y && cur < (i32)(v2.y + v2.z)) { found = s0 + 2; sl = v2; }
+            else if ((v3.x & 0xFFFFu) == peer && cur >= (i32)v3.y && cur < (i32)(v3.y + v3.z)) { found = s0 + 3; sl = v3; }
+            else if ((v3.x & 0xFFFFu) == PEER_NONE) break;   // slots are compact: nothing further
+        }
+        if (found < 0) return cur;
+        i32 len = (i32)sl.z;
+        if ((i32)sl.y != cur || cur + len > t1) return cur;
+        u32* word = &base[found].x;
+        u32 old, nw;
+        if (set_future == 1) { old = atomicOr(word, (u32)ST_FUTURE << 16); nw = old | ((u32)ST_FUTURE << 16); }
+        else if (set_future == 0) { old = atomicAnd(word, ~((u32)ST_FUTURE << 16)); nw = old & ~((u32)ST_FUTURE << 16); }
+        else { u32 d = (u32)del_diff << 16; old = atomicAdd(word, d); nw = old + d; }
+        i32 delta = ((nw >> 16) == 0 ? len : 0) - ((old >> 16) == 0 ? len : 0);
+        if (delta != 0) {
+            while (link != NODE_NONE) {
+                u32 nd = link >> 5;
+                int idx = (int)(link & 31);
+                if (nd < LB_SEQ_NS) atomicAdd(&c.sm->vis[nd][idx], delta);
+                else atomicAdd((i32*)&p.node[(c.node0 + nd) * 32 + idx].y, delta);
+                link = nd_parent(p, c, nd);
+            }
+        }
+        cur += len;
+        leaf = LEAF_NONE;
+    }
+    return cur;
+}
+
 // ---- retreat (dir=-1) / forward (dir=+1) the ops of peer `q` with counters [a,b) that touch container `cidx`.
 // The peer's changes covering [a,b) are enumerated 32 at a time, their op rows flattened over the lanes, so the
 // op records and the atom -> leaf lookups of 32 rows cost one round trip each.
@@ -412,12 +464,16 @@ __device__ __noinline__ void toggle_ops(const SeqPools& p, const SeqTables& t, C
                 dd = dir;
             }
             u32 hint = act ? p.atom_leaf[atom_index(c, tp, t0)] : LEAF_NONE;
-            unsigned m = __ballot_sync(LB_FULL, act);
+            // lane-parallel: each lane flips the spans of its own row; what needs a cut comes back for the warp
+            i32 done = t1;
+            if (act) done = toggle_lane(p, c, tp, t0, t1, mode, dd, hint);
+            __syncwarp();
+            unsigned m = __ballot_sync(LB_FULL, act && done < t1);
             while (m && !c.sm->err) {
                 int s = __ffs(m) - 1;
                 m &= m - 1;
-                range_apply(p, c, __shfl_sync(LB_FULL, tp, s), __shfl_sync(LB_FULL, t0, s), __shfl_sync(LB_FULL, t1, s),
-                            __shfl_sync(LB_FULL, mode, s), __shfl_sync(LB_FULL, dd, s), __shfl_sync(LB_FULL, hint, s));
+                range_apply(p, c, __shfl_sync(LB_FULL, tp, s), __shfl_sync(LB_FULL, done, s), __shfl_sync(LB_FULL, t1, s),
+                            __shfl_sync(LB_FULL, mode, s), __shfl_sync(LB_FULL, dd, s), LEAF_NONE);
             }
         }
     }
@@ -725,6 +781,9 @@ __device__ __noinline__ void store_container(const SeqPools& p, const SeqTables&
         if (lane == 0) p.node_parent[c.node0 + nd] = sm->parent[nd];
     }
     if ((u32)lane < c.P) p.cvv[c.cvv0 + lane] = sm->cvv[lane];
+#ifdef LB_SIMT_EMU
+    if (lane == 0 && getenv("LB_EMU_STATS")) fprintf(stderr, "container %u: leaves %u nodes %u height %u root %u\n", cidx, sm->n_leaves, sm->n_nodes, sm->height, sm->root);
+#endif
     if (lane == 0) {
         DocContainer& dc = t.dcont[cid0 + cidx];
         dc.n_leaves = sm->n_leaves;
