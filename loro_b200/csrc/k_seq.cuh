@@ -645,19 +645,24 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
         // 1. cursor: right after the pos-th visible atom (prefer-left)
         u32 leaf = sm->first_leaf;
         i32 rem = pos;
+        u32 my_link = NODE_NONE;   // lane l remembers the (node, index) the descent took at level l
+        bool have_path = false;
         if (pos > 0) {
             u32 nd = sm->root;
-            for (u32 lvl = sm->height; lvl >= 1; lvl--) {
+            u32 height = sm->height;
+            for (u32 lvl = height; lvl >= 1; lvl--) {
                 uint2 e = nd_get(p, c, nd, lane);
                 i32 v = (i32)e.y;
                 i32 incl = warp_incl_scan(v, lane);
                 unsigned m = __ballot_sync(LB_FULL, e.x != NODE_NONE && incl >= rem);
                 int idx = __ffs(m) - 1;
                 if (idx < 0) { seq_fail(c, LB_ERR(DOC_ERR_CORRUPT)); return; }
+                if ((u32)lane == lvl) my_link = (nd << 5) | (u32)idx;
                 rem -= __shfl_sync(LB_FULL, incl - v, idx);
                 nd = __shfl_sync(LB_FULL, e.x, idx);
             }
             leaf = nd;
+            have_path = height < 32;
         }
         uint4 L = leaf_load(p, c, leaf);
         int n = leaf_count(L);
@@ -761,8 +766,12 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
         if (lane == 0) p.a_org[a0] = mk4(ol_peer | (or_peer << 16), (u32)ol_ctr, (u32)or_ctr, 0);
         if (mid && lane == 1)
             p.a_org[atom_index(c, cur_peer, cur_ctr + off)] = mk4(cur_peer | (og.x & 0xFFFF0000u), (u32)(cur_ctr + off - 1), og.z, 0);
-        for (i32 i = lane; i < len; i += 32) p.atom_leaf[a0 + i] = tgt_leaf;
-        add_vis(p, c, link, len);
+        if (lane < len) p.atom_leaf[a0 + lane] = tgt_leaf;
+        for (i32 i = 32 + lane; i < len; i += 32) p.atom_leaf[a0 + i] = tgt_leaf;
+        if (have_path && tgt_leaf == leaf) {   // every level of the recorded path at once
+            if (my_link != NODE_NONE) nd_add_vis(p, c, my_link >> 5, (int)(my_link & 31), len);
+            __syncwarp();
+        } else add_vis(p, c, link, len);
         return;
     }
     seq_fail(c, LB_ERR(DOC_ERR_CAPACITY));
@@ -945,6 +954,7 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
             // of the walk, and the container's tracker sat at that version when it was last touched
             bool chain = __shfl_sync(LB_FULL, (int)h_simple, j) && prev_peer == peer && k > 0;
             const i32* vv = tables.ch_vv + vv0 + (u64)pos * P;
+            i32 cvv_dirty = -1;   // end counter of this change's last op in the active container, not yet in cvv
             for (u32 rb = 0; rb < nr && !sm->err; rb += 32) {
                 // ---- 32 op records per round trip
                 uint4 rec = mk4(0, 0, 0, 0);
@@ -964,6 +974,7 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
                     u32 ci = REC_CIDX(rx);
                     if (ci != cidx) {
                         if (cidx != 0xFFFFFFFFu && lane == 0) pools.cont_epoch[cid0 + cidx] = cur_epoch;
+                        if (cvv_dirty >= 0) { __syncwarp(); if (lane == 0) cvv_set(pools, c, peer, cvv_dirty); cvv_dirty = -1; }
                         store_container(pools, tables, c, cid0, cidx);
                         c = load_container(pools, tables, c, cid0, ci);
                         cidx = ci;
@@ -978,12 +989,11 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
                     else   // delete by target id (crdt_rope.rs:236-315 ; tracker.rs:173-232)
                         range_apply(pools, c, __shfl_sync(LB_FULL, aux, s), prop, prop + len, -1, +1, __shfl_sync(LB_FULL, hint_l, s));
                     // current_vv of the tracker follows its own ops (tracker.rs:131-139, 228-231); in causal order
-                    // this entry only grows
-                    __syncwarp();
-                    if (lane == 0) cvv_set(pools, c, peer, ctr + len);
-                    __syncwarp();
+                    // this entry only grows: written back when the container or the change ends
+                    cvv_dirty = ctr + len;
                 }
             }
+            if (cvv_dirty >= 0) { __syncwarp(); if (lane == 0) cvv_set(pools, c, peer, cvv_dirty); __syncwarp(); }
             prev_peer = peer;
         }
     }
