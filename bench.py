@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-docs", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-export", action="store_true", help="skip the re-export phase (import + state only)")
     return ap.parse_args()
 
 
@@ -130,9 +131,10 @@ def cpu_baseline(args, gen, threads=None):
     o = [0]
     for b in blobs:
         o.append(o[-1] + len(b))
-    r = oracle.bench_import(np.frombuffer(buf, dtype=np.uint8), o, threads=threads, want_json=True)
+    r = oracle.bench_import(np.frombuffer(buf, dtype=np.uint8), o, threads=threads, want_json=True,
+                            want_export=not args.no_export)
     return {"value": r["ops"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} docs of the same C3 workload ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON per doc, one doc per task"}
+            "sample": f"{n} docs of the same C3 workload ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON{"" if args.no_export else " + export(all_updates)"} per doc, one doc per task"}
 
 
 def run_reference(args):
@@ -227,8 +229,10 @@ def main():
             d_bytes[int(offs[i]):int(offs[i]) + n] = src[o:o + n]
         del src
 
+    xflags = 0 if args.no_export else loro_b200.api.LB_FLAG_EXPORT
+
     def step():
-        b = loro_b200.import_batch_device(d_bytes.data_ptr(), offs, lens, device=local, keep=d_bytes)
+        b = loro_b200.import_batch_device(d_bytes.data_ptr(), offs, lens, device=local, flags=xflags, keep=d_bytes)
         c = b.counters()
         if world > 1:
             gather_counters(c, device=dev)  # the one collective of the path: per-shard summary counters (NCCL)
@@ -254,7 +258,7 @@ def main():
     for _ in range(args.steps):
         c, tm = step()
         launches += tm["kernel_launches"]
-        for k in ("frame", "decode", "resolve", "classify", "integrate", "materialise", "total_device"):
+        for k in ("frame", "decode", "resolve", "classify", "integrate", "materialise", "reexport", "total_device"):
             phase[k] = phase.get(k, 0.0) + tm[k]
     ev1.record()
     torch.cuda.synchronize()
@@ -277,7 +281,7 @@ def main():
         blobs = [gen.blob(int(idx[i])) for i in range(n_docs)]
         h2d = int(lens.sum())
         for _ in range(1):
-            b = loro_b200.import_batch(blobs, device=local)
+            b = loro_b200.import_batch(blobs, device=local, flags=xflags)
             b.json_bytes(0)
             b.close()
         if world > 1:
@@ -286,10 +290,13 @@ def main():
         t0 = time.time()
         d2h = 0
         for _ in range(args.steps):
-            b = loro_b200.import_batch(blobs, device=local)
+            b = loro_b200.import_batch(blobs, device=local, flags=xflags)
             b.json_bytes(0)  # pulls the whole JSON buffer of the batch to the host
             cc = b.counters()
             d2h = cc["json_bytes"] + n_docs * 256
+            if xflags:
+                b.export_updates(0)  # pulls every document's re-exported blob to the host
+                d2h += b.timings()["export_bytes"]
             b.close()
         torch.cuda.synchronize()
         e_ms = (time.time() - t0) * 1e3
@@ -336,7 +343,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": f"C3: {n_docs} docs/GPU x {args.ops_per_doc} mixed List/Map atom ops, {args.peers} concurrent peers, "
-                               f"one FastUpdates blob per doc (SURVEY.md 8d)",
+                               f"one FastUpdates blob per doc (SURVEY.md 8d); import -> state JSON" + ("" if args.no_export else " -> re-export(all_updates)"),
                    "docs_per_gpu": n_docs, "distinct_docs_per_gpu": distinct, "atom_ops_per_step_per_gpu": atoms_per_step,
                    "op_rows_per_gpu": rows, "blob_bytes_per_gpu": int(lens.sum()), "l2": "inputs_larger_than_L2" if lens.sum() > 126e6 else "inputs fit L2",
                    "generator_seconds": round(gen_s, 1), "host_cores": host_cores()},

@@ -36,7 +36,8 @@ typedef enum lb_status {
     LB_ERR_NO_DEVICE = 2,
     LB_ERR_CUDA = 3,
     LB_ERR_OOM = 4,
-    LB_ERR_INTERNAL = 5
+    LB_ERR_INTERNAL = 5,
+    LB_ERR_UNSUPPORTED = 6   /* valid request the engine does not cover yet (see lb_last_error) */
 } lb_status;
 
 /* per-document result code; the LoroError variant it corresponds to is given on the right */
@@ -65,6 +66,7 @@ typedef struct lb_options {
 } lb_options;
 #define LB_FLAG_NO_JSON 1u      /* skip deep-value JSON materialisation */
 #define LB_FLAG_KEEP_DEVICE 2u  /* keep intermediate device tables for lb_debug_* (tests) */
+#define LB_FLAG_EXPORT 4u       /* also re-export every document (phase 7) for lb_doc_export_updates */
 
 typedef struct lb_id_span {
     uint64_t peer;
@@ -91,10 +93,11 @@ typedef struct lb_counters {
 } lb_counters;
 
 typedef struct lb_timings { /* device time per phase in milliseconds (CUDA events on the batch stream) */
-    float h2d, frame, decode, resolve, classify, integrate, materialise, d2h, total_device;
+    float h2d, frame, decode, resolve, classify, integrate, materialise, d2h, total_device, reexport;
     /* algorithmic bytes of the decode phase: blob bytes read + SoA bytes written */
     uint64_t decode_bytes_read, decode_bytes_written;
     uint32_t kernel_launches;
+    uint64_t export_bytes;             /* bytes written by the re-export phase */
 } lb_timings;
 
 typedef struct lb_batch lb_batch;
@@ -112,6 +115,12 @@ size_t lb_doc_count(const lb_batch* b);
 lb_status lb_doc_status(const lb_batch* b, size_t doc, lb_import_status* out);
 lb_status lb_doc_json(const lb_batch* b, size_t doc, const char** utf8, size_t* len);
 lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n); /* start=0,end=vv[peer] */
+/* LoroDoc::export(ExportMode::all_updates()) of document `doc` (crates/loro/src/lib.rs:1235, encoding.rs:350-416):
+ * the FastUpdates blob a fresh reference document would export after importing the same input.  Needs
+ * LB_FLAG_EXPORT at import time.  `from` (a version vector) must be NULL / 0 for now: only all_updates.
+ * LB_ERR_UNSUPPORTED: the document uses something the export phase does not cover yet (lb_last_error). */
+lb_status lb_doc_export_updates(const lb_batch* b, size_t doc, const lb_id_span* from, size_t n_from,
+                                const uint8_t** bytes, size_t* len);
 lb_status lb_batch_counters(const lb_batch* b, lb_counters* out);
 lb_status lb_batch_timings(const lb_batch* b, lb_timings* out);
 const char* lb_last_error(void); /* thread-local, human readable */

@@ -9,6 +9,7 @@ _DEFAULT_LIB = os.path.join(_HERE, "libloro_b200.so")
 
 LB_FLAG_NO_JSON = 1
 LB_FLAG_KEEP_DEVICE = 2
+LB_FLAG_EXPORT = 4
 
 DOC_CODES = {0: "Ok", 1: "DecodeError", 2: "DecodeChecksumMismatchError", 3: "IncompatibleFutureEncodingError",
              4: "DecodeDataCorruptionError", 5: "Unsupported", 6: "CapacityExceeded"}
@@ -50,9 +51,9 @@ class _Counters(ctypes.Structure):
 
 class _Timings(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("h2d", "frame", "decode", "resolve", "classify", "integrate",
-                                               "materialise", "d2h", "total_device")] + \
+                                               "materialise", "d2h", "total_device", "reexport")] + \
                [("decode_bytes_read", ctypes.c_uint64), ("decode_bytes_written", ctypes.c_uint64),
-                ("kernel_launches", ctypes.c_uint32)]
+                ("kernel_launches", ctypes.c_uint32), ("export_bytes", ctypes.c_uint64)]
 
 
 _libs = {}
@@ -79,6 +80,8 @@ def load_library(path=None):
     L.lb_doc_count.argtypes = [vp]
     L.lb_doc_status.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(_Status)]
     L.lb_doc_json.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t)]
+    L.lb_doc_export_updates.argtypes = [vp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
     L.lb_doc_vv.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(_IdSpan)), ctypes.POINTER(ctypes.c_size_t)]
     L.lb_batch_counters.argtypes = [vp, ctypes.POINTER(_Counters)]
     L.lb_batch_timings.argtypes = [vp, ctypes.POINTER(_Timings)]
@@ -90,13 +93,21 @@ def load_library(path=None):
     return L
 
 
+class EngineError(RuntimeError):
+    """A C-ABI call returned a non-zero lb_status; .status carries it (6 = LB_ERR_UNSUPPORTED)."""
+
+    def __init__(self, msg, status):
+        super().__init__(msg)
+        self.status = status
+
+
 def _check(L, rc, what):
     if rc == 0:
         return
     msg = L.lb_last_error().decode(errors="replace")
     if rc == 2:
         raise EngineUnavailable(f"{what}: {msg}")
-    raise RuntimeError(f"{what} failed (lb_status={rc}): {msg}")
+    raise EngineError(f"{what} failed (lb_status={rc}): {msg}", rc)
 
 
 class Batch:
@@ -131,6 +142,14 @@ class Batch:
         suc = {st.success[k].peer: (st.success[k].start, st.success[k].end) for k in range(st.n_success)}
         pen = {st.pending[k].peer: (st.pending[k].start, st.pending[k].end) for k in range(st.n_pending)}
         return ImportStatus(st.code, suc, pen or None)
+
+    def export_updates(self, i):
+        """LoroDoc::export(ExportMode::all_updates()) of document i (needs flags=LB_FLAG_EXPORT at import)."""
+        p = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        _check(self._L, self._L.lb_doc_export_updates(self._h, i, None, 0, ctypes.byref(p), ctypes.byref(n)),
+               "lb_doc_export_updates")
+        return ctypes.string_at(p.value, n.value)
 
     def json_bytes(self, i):
         p = ctypes.c_char_p()

@@ -18,6 +18,7 @@
 #include "k_classify.cuh"
 #include "k_seq.cuh"
 #include "k_state.cuh"
+#include "k_export.cuh"
 #include "host_stage.hpp"
 
 static thread_local std::string g_last_error;
@@ -87,6 +88,17 @@ __global__ void k_excl_scan_multi(ScanJobs jobs) {
     if (threadIdx.x == 0) *(u64*)(out + n * out_stride) = carry_s;
 }
 
+// thread per document: inputs of the export scans (output blocks, scratch words)
+__global__ void k_exp_sizes(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t, u32* __restrict__ n_blocks,
+                            u32* __restrict__ n_scratch) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    u32 nb = di.code == DOC_OK ? t.xdoc[d].n_mb : 0;
+    n_blocks[d] = nb;
+    n_scratch[d] = nb * 2 * (di.P + di.K + di.C);
+}
+
 namespace {
 
 struct Dev {  // owns every device allocation of a batch
@@ -107,6 +119,19 @@ struct Dev {  // owns every device allocation of a batch
         bytes += sz;
         if (zero) CK(cudaMemsetAsync(p, 0, sz, stream));
         return (T*)p;
+    }
+    // give a table back to the stream-ordered pool as soon as its last consumer has been enqueued
+    template <class T>
+    void release(T*& p) {
+        if (!p) return;
+        for (size_t i = 0; i < ptrs.size(); i++)
+            if (ptrs[i] == (void*)p) {
+                cudaFreeAsync((void*)p, stream);
+                ptrs[i] = ptrs.back();
+                ptrs.pop_back();
+                break;
+            }
+        p = nullptr;
     }
     void free_all() {
         for (void* p : ptrs) cudaFreeAsync(p, stream);
@@ -133,6 +158,12 @@ struct lb_batch {
     BlockInfo* d_blocks = nullptr;
     DocPeer* d_dpeer = nullptr;
     u8* d_json = nullptr;
+    u8* d_export = nullptr;      // phase 7 output: one FastUpdates blob per document
+    XDoc* d_xdoc = nullptr;
+    u64 export_total = 0;
+    std::vector<XDoc> xdocs;
+    uint8_t* exported = nullptr;  // malloc'ed host copy (lbstage::download)
+    bool export_fetched = false;
     u64 n_blocks = 0, n_changes = 0, n_rows = 0, n_peers_tot = 0, json_total = 0;
     Tables tb{};
     // host results
@@ -228,6 +259,7 @@ void pipeline(lb_batch* b) {
     t.cid_root = dv.alloc<u8>(NC); t.cid_type = dv.alloc<u8>(NC); t.cid_peer_idx = dv.alloc<u32>(NC); t.cid_koc = dv.alloc<i32>(NC);
     t.ch_block = dv.alloc<u32>(NCH); t.ch_counter = dv.alloc<i32>(NCH); t.ch_len = dv.alloc<u32>(NCH);
     t.ch_lamport = dv.alloc<u32>(NCH); t.ch_ts = dv.alloc<i64>(NCH); t.ch_dep0 = dv.alloc<u64>(NCH);
+    t.ch_msg_off = dv.alloc<u64>(NCH); t.ch_msg_len = dv.alloc<u32>(NCH, true);
     t.ch_ndeps = dv.alloc<u32>(NCH); t.ch_dep_self = dv.alloc<u8>(NCH); t.ch_op0 = dv.alloc<u64>(NCH);
     t.ch_nops = dv.alloc<u32>(NCH, true);
     t.dep_peer_idx = dv.alloc<u32>(ND); t.dep_counter = dv.alloc<i32>(ND);
@@ -340,6 +372,10 @@ void pipeline(lb_batch* b) {
     sq.atom_row = ct.atom_row;
     LB_LAUNCH(k_seq_integrate, nblk(D, LB_SEQ_WARPS), 32 * LB_SEQ_WARPS, 0, st, b->d_docs, D, sp, sq);
     tm.kernel_launches += 1;
+    if (!(b->flags & LB_FLAG_KEEP_DEVICE)) {   // the tracker pools are the largest tables of the batch: free them early
+        dv.release(sp.leaf); dv.release(sp.node); dv.release(sp.node_parent); dv.release(sp.atom_leaf); dv.release(sp.a_org);
+        dv.release(sp.cvv); dv.release(sp.cont_epoch); dv.release(ct.atom_row); dv.release(ct.op_rec);
+    }
     mark(b);  // [5] integrate done
     // ------------------------------------------------------------ phase 6: JSON
     StateTables stt;
@@ -364,6 +400,52 @@ void pipeline(lb_batch* b) {
     LB_LAUNCH(k_doc_hash, nblk(D), TPB, 0, st, b->d_docs, D, (const u8*)b->d_json, d_acc);
     tm.kernel_launches += 1;
     mark(b);  // [6] materialise done
+    // ------------------------------------------------------------ phase 7: re-export (all_updates per document)
+    if (b->flags & LB_FLAG_EXPORT) {
+        ExportTables xt;
+        memset(&xt, 0, sizeof(xt));
+        xt.bytes = b->d_bytes; xt.blocks = blk; xt.dpeer = b->d_dpeer; xt.dcont = dcont;
+        xt.dkey_off = rt.dkey_off; xt.dkey_len = rt.dkey_len; xt.key_map = rt.key_map; xt.peer_map = rt.peer_map;
+        xt.ch_order = rt.ch_order; xt.ch_applied = rt.ch_applied; xt.ch_block = t.ch_block; xt.ch_counter = t.ch_counter;
+        xt.ch_len = t.ch_len; xt.ch_lamport = rt.ch_lamport; xt.ch_ts = t.ch_ts; xt.ch_op0 = t.ch_op0; xt.ch_nops = t.ch_nops;
+        xt.ch_dep0 = t.ch_dep0; xt.ch_ndeps = t.ch_ndeps; xt.ch_dep_self = t.ch_dep_self;
+        xt.dep_peer_idx = t.dep_peer_idx; xt.dep_counter = t.dep_counter;
+        xt.ch_msg_off = t.ch_msg_off; xt.ch_msg_len = t.ch_msg_len;
+        xt.op_kind = ct.op_kind; xt.op_cidx = ct.op_cidx; xt.op_prop = t.op_prop; xt.op_len = t.op_len;
+        xt.op_counter = t.op_counter; xt.op_val_off = t.op_val_off; xt.op_val_len = t.op_val_len; xt.op_del = t.op_del;
+        xt.op_aux = ct.op_aux; xt.del_counter = t.del_counter; xt.del_len = t.del_len;
+        xt.r_astart = dv.alloc<u32>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.st_row = dv.alloc<u32>(NR);
+        xt.mo_xk = dv.alloc<u8>(NR); xt.mo_cidx = dv.alloc<u32>(NR); xt.mo_ctr = dv.alloc<i32>(NR); xt.mo_atoms = dv.alloc<u32>(NR);
+        xt.mo_prop = dv.alloc<i32>(NR); xt.mo_f0 = dv.alloc<u32>(NR); xt.mo_f1 = dv.alloc<u32>(NR); xt.mo_f2 = dv.alloc<i32>(NR);
+        xt.mo_st0 = dv.alloc<u32>(NR); xt.mo_nst = dv.alloc<u32>(NR);
+        xt.mc_src = dv.alloc<u32>(NCH); xt.mc_o0 = dv.alloc<u32>(NCH); xt.mc_no = dv.alloc<u32>(NCH); xt.mc_atoms = dv.alloc<u32>(NCH);
+        xt.mb_first = dv.alloc<u32>(NCH, true);
+        xt.xdoc = dv.alloc<XDoc>(D + 1, true);
+        b->d_xdoc = xt.xdoc;
+        LB_LAUNCH(k_exp_arena, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
+        LB_LAUNCH(k_exp_pack, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
+        LB_LAUNCH(k_exp_sizes, nblk(D), TPB, 0, st, b->d_docs, D, xt, d_tmp_a, d_tmp_b);
+        tm.kernel_launches += 3;
+        run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)xt.xdoc + offsetof(XDoc, ob0), 4, sizeof(XDoc), D},
+                      ScanJob{(const u8*)d_tmp_b, (u8*)xt.xdoc + offsetof(XDoc, scratch0), 4, sizeof(XDoc), D}});
+        XDoc xtot = d2h_one(b, xt.xdoc + D);
+        u64 NOB = xtot.ob0, NSCR = xtot.scratch0;
+        XBlock* xb = dv.alloc<XBlock>(NOB + 1);
+        u32* xscratch = dv.alloc<u32>(NSCR + 1);
+        LB_LAUNCH(k_exp_list, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb);
+        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, (u8*)nullptr, 0);
+        LB_LAUNCH(k_exp_layout, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb, d_tmp_a);
+        tm.kernel_launches += 3;
+        run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)xt.xdoc + offsetof(XDoc, exp_off), 4, sizeof(XDoc), D}});
+        u64 XT = d2h_one(b, &xt.xdoc[D].exp_off);
+        b->export_total = XT;
+        b->d_export = dv.alloc<u8>(XT + 16, true);
+        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, b->d_export, 1);
+        LB_LAUNCH(k_exp_finish, nblk(D), TPB, 0, st, b->d_docs, D, xt, b->d_export);
+        tm.kernel_launches += 2;
+        tm.export_bytes = XT;
+    }
+    mark(b);  // [7] export done
     // ------------------------------------------------------------ results to host
     b->docs.resize(D + 1);
     CK(cudaMemcpyAsync(b->docs.data(), b->d_docs, sizeof(DocInfo) * (D + 1), cudaMemcpyDeviceToHost, st));
@@ -371,7 +453,11 @@ void pipeline(lb_batch* b) {
     if (NP) CK(cudaMemcpyAsync(b->dpeer.data(), b->d_dpeer, sizeof(DocPeer) * NP, cudaMemcpyDeviceToHost, st));
     unsigned long long acc[4];
     CK(cudaMemcpyAsync(acc, d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
-    mark(b);  // [7] d2h queued
+    if (b->d_xdoc) {
+        b->xdocs.resize(D);
+        CK(cudaMemcpyAsync(b->xdocs.data(), b->d_xdoc, sizeof(XDoc) * D, cudaMemcpyDeviceToHost, st));
+    }
+    mark(b);  // [8] d2h queued
     CK(cudaStreamSynchronize(st));
     lb_counters& c = b->counters;
     c.docs = D;
@@ -421,8 +507,9 @@ void timings_from_events(lb_batch* b) {
     t.classify = el(4, 5);
     t.integrate = el(5, 6);
     t.materialise = el(6, 7);
-    t.d2h = el(7, 8);
-    t.total_device = el(1, 7);
+    t.reexport = el(7, 8);
+    t.d2h = el(8, 9);
+    t.total_device = el(1, 8);
 }
 
 lb_status run_batch(lb_batch* b) {
@@ -604,6 +691,29 @@ lb_status lb_doc_json(const lb_batch* cb, size_t doc, const char** utf8, size_t*
     return LB_OK;
 }
 
+lb_status lb_doc_export_updates(const lb_batch* cb, size_t doc, const lb_id_span* from, size_t n_from,
+                                const uint8_t** bytes, size_t* len) {
+    lb_batch* b = const_cast<lb_batch*>(cb);
+    if (!b || !bytes || !len || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
+    if (!(b->flags & LB_FLAG_EXPORT)) { g_last_error = "batch was imported without LB_FLAG_EXPORT"; return LB_ERR_INVALID_ARG; }
+    if (from || n_from) { g_last_error = "only all_updates (from = NULL) is exported"; return LB_ERR_UNSUPPORTED; }
+    if (b->docs[doc].code != DOC_OK) { g_last_error = "document failed to import"; return LB_ERR_INVALID_ARG; }
+    const XDoc& x = b->xdocs[doc];
+    if ((x.flags & 1) || x.exp_len == 0) { g_last_error = "document uses features the export phase does not cover"; return LB_ERR_UNSUPPORTED; }
+    if (!b->export_fetched) {
+        b->exported = (uint8_t*)malloc(b->export_total + 1);
+        if (!b->exported) { g_last_error = "out of host memory"; return LB_ERR_OOM; }
+        if (b->export_total && !lbstage::download(b->d_export, b->exported, b->export_total, b->dev.stream)) {
+            g_last_error = "export d2h failed";
+            return LB_ERR_CUDA;
+        }
+        b->export_fetched = true;
+    }
+    *bytes = b->exported + x.exp_off;
+    *len = x.exp_len;
+    return LB_OK;
+}
+
 lb_status lb_batch_counters(const lb_batch* b, lb_counters* out) {
     if (!b || !out) return LB_ERR_INVALID_ARG;
     *out = b->counters;
@@ -649,6 +759,7 @@ void lb_batch_free(lb_batch* b) {
         cudaStreamDestroy(b->dev.stream);
     }
     free(b->json);
+    free(b->exported);
     delete b;
 }
 

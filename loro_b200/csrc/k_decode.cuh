@@ -13,7 +13,7 @@
 
 // ---- skip one LoroValue (kind byte already consumed) ; iterative, bounded depth
 // reference: value.rs:620-700 read_value_content
-__device__ inline void skip_loro_value_content(Cur& c, u8 kind, u32* n_child_containers) {
+__device__ inline void skip_loro_value_content(Cur& c, u8 kind, u32* n_child_containers, u32* n_maps = nullptr) {
     // stack of remaining item counts; bit 31 marks a map level (items carry a key index)
     u32 stack[24];
     int sp = 0;
@@ -29,6 +29,7 @@ __device__ inline void skip_loro_value_content(Cur& c, u8 kind, u32* n_child_con
                     u64 n = c.varint();
                     if (n > (1u << 28) || sp >= 24) { c.err = 1; return; }
                     stack[sp++] = (u32)n | (kind == 8 ? 0x80000000u : 0);
+                    if (kind == 8 && n_maps) (*n_maps)++;
                     break;
                 }
                 case 9: (void)c.get(); if (n_child_containers) (*n_child_containers)++; break;
@@ -48,14 +49,14 @@ __device__ inline void skip_loro_value_content(Cur& c, u8 kind, u32* n_child_con
 }
 
 // length in bytes of the value of op kind `vt` starting at c (advances c)
-__device__ inline void skip_value(Cur& c, u8 vt) {
+__device__ inline void skip_value(Cur& c, u8 vt, u32* n_maps = nullptr) {
     switch (vt) {
         case VK_NULL: case VK_TRUE: case VK_FALSE: case VK_DELETE_ONCE: case VK_DELETE_SEQ: break;
         case VK_I64: case VK_DELTA_INT: (void)c.sleb(); break;
         case VK_F64: c.skip(8); break;
         case VK_STR: case VK_BINARY: { u64 n = c.varint(); c.skip(n); break; }
         case VK_CONTAINER: (void)c.varint(); break;
-        case VK_LORO_VALUE: { u8 k = c.get(); skip_loro_value_content(c, k, nullptr); break; }
+        case VK_LORO_VALUE: { u8 k = c.get(); skip_loro_value_content(c, k, nullptr, n_maps); break; }
         case VK_MARK_START: {
             (void)c.get(); (void)c.varint(); (void)c.varint();
             u8 k = c.get();
@@ -186,7 +187,7 @@ struct Tables {
     // cids (block-local arena)
     u8* cid_root; u8* cid_type; u32* cid_peer_idx; i32* cid_koc;  // key idx or counter
     // changes
-    u32* ch_block; i32* ch_counter; u32* ch_len; u32* ch_lamport; i64* ch_ts;
+    u32* ch_block; i32* ch_counter; u32* ch_len; u32* ch_lamport; i64* ch_ts; u64* ch_msg_off; u32* ch_msg_len;
     u64* ch_dep0; u32* ch_ndeps; u8* ch_dep_self; u64* ch_op0; u32* ch_nops;
     // deps (other peers)
     u32* dep_peer_idx; i32* dep_counter;
@@ -299,14 +300,34 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         t.ch_lamport[bi.ch0 + N - 1] = bi.lamport_start + bi.lamport_len - t.ch_len[bi.ch0 + N - 1];
     }
     if (h.err || !h.empty()) err = err ? err : LB_ERR(DOC_ERR_DECODE);
-    // ---- change meta: timestamps DoD (N) ; commit-message lengths are not needed by the merge path
+    // ---- change meta: timestamps DoD (N), commit-message lengths AnyRle<u32> (N), message bytes
     {
         Cur m(b + bi.sec_off[1], bi.sec_len[1]);
         DodCur d;
         d.begin(&m);
         for (u32 k = 0; k < N; k++) t.ch_ts[bi.ch0 + k] = d.next(k == 0);
         d.finish();
-        if (m.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        u32 got = 0;
+        while (got < N && !m.err) {
+            i64 sl = m.zigzag();
+            if (sl == 0) { m.err = 1; break; }
+            u64 cnt = sl > 0 ? (u64)sl : (u64)(-sl);
+            if (got + cnt > N) { m.err = 1; break; }
+            u64 v = 0;
+            if (sl > 0) v = m.varint();
+            for (u64 q = 0; q < cnt; q++) {
+                if (sl < 0) v = m.varint();
+                t.ch_msg_len[bi.ch0 + got + q] = (u32)v;
+            }
+            got += (u32)cnt;
+        }
+        u64 moff = bi.off + (u64)(m.p - b);
+        for (u32 k = 0; k < N && !m.err; k++) {
+            t.ch_msg_off[bi.ch0 + k] = moff;
+            moff += t.ch_msg_len[bi.ch0 + k];
+            m.skip(t.ch_msg_len[bi.ch0 + k]);
+        }
+        if (m.err || !m.empty()) err = err ? err : LB_ERR(DOC_ERR_DECODE);
     }
     // ---- keys
     {
@@ -371,6 +392,7 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         u32 change = 0;
         u32 ch_first_row = 0;
         u32 ndel = 0;
+        u32 n_maps = 0;
         i32 next_boundary = (i32)bi.counter_start + (i32)t.ch_len[bi.ch0];
         t.ch_op0[bi.ch0] = bi.op0;
         for (u32 r = 0; r < bi.n_ops; r++) {
@@ -388,7 +410,7 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             t.op_change[row] = (u32)(bi.ch0 + change);
             const u8* v0 = v.p;
             // text/list payloads: point past the length prefix where that helps the consumers
-            skip_value(v, (u8)vt);
+            skip_value(v, (u8)vt, &n_maps);
             t.op_val_off[row] = bi.off + (u64)(v0 - b);
             t.op_val_len[row] = (u32)(v.p - v0);
             t.op_del[row] = (u8)vt == VK_DELETE_SEQ ? (u32)(bi.del0 + ndel++) : 0xFFFFFFFFu;
@@ -406,6 +428,7 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         if (v.err || !v.empty() || c0.c.err || c1.c.err || c2.c.err || c3.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
         if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels))
             err = LB_ERR(DOC_ERR_CORRUPT);
+        blocks[i].n_value_maps = n_maps;
     }
     if (err) blocks[i].err = err;
 }

@@ -149,6 +149,7 @@ __global__ void k_doc_tables(const u8* __restrict__ bytes, DocInfo* __restrict__
                 dc.name_len = nlen;
                 dc.peer = peer;
                 dc.counter = is_root ? 0 : koc;
+                dc.key_or_peer = is_root ? t.key_map[bi.key0 + (u32)koc] : t.peer_map[bi.peer0 + t.cid_peer_idx[bi.cid0 + j]];
                 t.dcont[di.cid0 + C] = dc;
                 C++;
             }

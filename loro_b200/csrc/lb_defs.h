@@ -16,6 +16,8 @@ struct BlockInfo {
     u32 sec_len[8];     //   (offsets relative to `off`)
     u32 n_peers, n_keys, n_cids, n_ops, n_dels, n_deps;
     u32 values_bytes;
+    u32 n_value_maps;   // LoroValue::Map levels inside the values section (their keys are block-local indices)
+    u32 pad_;
     // exclusive-scan bases into the batch-wide tables (filled by the host after the count pass)
     u64 peer0, key0, cid0, ch0, dep0, op0, del0;
 };
@@ -77,7 +79,7 @@ struct DocContainer {
     u64 out0;   u32 out_cap;   u32 n_out;   // final visible runs (row, off, len)
     u32 seq_len;        // visible atoms
     u32 unk_sid;        // span id of the tracker's placeholder span
-    u32 pad2;
+    u32 key_or_peer;    // root: doc-level key index of the name ; normal: doc-level peer index of the creator
     u32 unsupported;
     u64 cvv0;           // tracker current_vv (P entries) base
 };

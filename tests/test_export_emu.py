@@ -1,0 +1,80 @@
+"""Phase 7 (re-export) on the emulated kernels: byte parity with the oracle's export of the same document."""
+import os
+import subprocess
+
+import pytest
+
+from oracle import OracleDoc
+from tests import workloads
+from tests.export_checks import check_export_against_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu", "libloro_b200_emu.so")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def build_emu():
+    subprocess.check_call([os.path.join(HERE, "emu", "build_emu.sh")])
+
+
+def test_export_small_mixed_doc():
+    a = OracleDoc(1)
+    t = a.get_text("text"); a.text_insert(t, 0, "Hello"); a.text_insert(t, 5, " World")
+    l = a.get_list("list"); a.list_insert(l, 0, 1, 2, 3); a.delete(l, 1, 1)
+    m = a.get_map("map"); a.map_set(m, "k", 5); a.map_set(m, "z", "str"); a.map_delete(m, "k")
+    check_export_against_oracle([a.export_updates()], lib_path=EMU)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_export_random_multi_site_histories(seed):
+    blobs = [workloads.make_doc_history(seed * 100 + i, n_sites=2 + i % 4, n_ops=200 + 40 * i, sync_prob=0.03 + 0.02 * (i % 3))[0]
+             for i in range(8)]
+    check_export_against_oracle(blobs, lib_path=EMU)
+
+
+def test_export_generator_documents():
+    from loro_b200.workload import C3Batch
+    gen = C3Batch(6, n_ops=2500, threads=4)
+    check_export_against_oracle(gen.blobs(), lib_path=EMU)
+
+
+def test_export_typing_runs_merge_across_changes():
+    """Consecutive inserts / deletes in separate commits: stored changes merge (same timestamp is not required for
+    ops inside one change; across changes can_merge_right needs ts_b <= ts_a) and op runs re-merge on export."""
+    a = OracleDoc(7)
+    t = a.get_text("t")
+    for i, ch in enumerate("the quick brown fox"):
+        a.text_insert(t, i, ch)
+        if i % 3 == 2:
+            a.commit()
+    l = a.get_list("l")
+    for i in range(40):
+        a.list_insert(l, i, i)
+    a.commit()
+    for i in range(10):
+        a.delete(l, 5, 1)          # forward deletes at one position merge into one span
+    for i in range(10):
+        a.delete(l, 20 - i, 1)     # backward deletes merge with a negative length
+    a.commit()
+    check_export_against_oracle([a.export_updates()], lib_path=EMU)
+
+
+def test_export_needs_flag_and_reports_unsupported():
+    import loro_b200
+    from loro_b200 import api
+    a = OracleDoc(3)
+    a.text_insert(a.get_text("t"), 0, "x" * 6000)   # one change above MAX_BLOCK_SIZE: split_change_then_insert
+    big = a.export_updates()
+    b = OracleDoc(4)
+    b.text_insert(b.get_text("t"), 0, "ok")
+    small = b.export_updates()
+    plain = loro_b200.import_batch([small], lib_path=EMU)
+    with pytest.raises(api.EngineError):
+        plain.export_updates(0)
+    batch = loro_b200.import_batch([big, small], flags=api.LB_FLAG_EXPORT, lib_path=EMU)
+    assert batch.get_deep_value(0) == {"t": "x" * 6000}
+    with pytest.raises(api.EngineError) as e:
+        batch.export_updates(0)
+    assert "does not cover" in str(e.value)
+    ref = OracleDoc(9); ref.import_(small)
+    assert batch.export_updates(1) == ref.export_updates()
