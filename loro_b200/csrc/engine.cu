@@ -88,17 +88,6 @@ __global__ void k_excl_scan_multi(ScanJobs jobs) {
     if (threadIdx.x == 0) *(u64*)(out + n * out_stride) = carry_s;
 }
 
-// thread per document: inputs of the export scans (output blocks, scratch words)
-__global__ void k_exp_sizes(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t, u32* __restrict__ n_blocks,
-                            u32* __restrict__ n_scratch) {
-    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_docs) return;
-    const DocInfo& di = docs[d];
-    u32 nb = di.code == DOC_OK ? t.xdoc[d].n_mb : 0;
-    n_blocks[d] = nb;
-    n_scratch[d] = nb * 2 * (di.P + di.K + di.C);
-}
-
 namespace {
 
 struct Dev {  // owns every device allocation of a batch
@@ -414,16 +403,23 @@ void pipeline(lb_batch* b) {
         xt.op_kind = ct.op_kind; xt.op_cidx = ct.op_cidx; xt.op_prop = t.op_prop; xt.op_len = t.op_len;
         xt.op_counter = t.op_counter; xt.op_val_off = t.op_val_off; xt.op_val_len = t.op_val_len; xt.op_del = t.op_del;
         xt.op_aux = ct.op_aux; xt.del_counter = t.del_counter; xt.del_len = t.del_len;
-        xt.r_astart = dv.alloc<u32>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.st_row = dv.alloc<u32>(NR);
-        xt.mo_xk = dv.alloc<u8>(NR); xt.mo_cidx = dv.alloc<u32>(NR); xt.mo_ctr = dv.alloc<i32>(NR); xt.mo_atoms = dv.alloc<u32>(NR);
-        xt.mo_prop = dv.alloc<i32>(NR); xt.mo_f0 = dv.alloc<u32>(NR); xt.mo_f1 = dv.alloc<u32>(NR); xt.mo_f2 = dv.alloc<i32>(NR);
-        xt.mo_st0 = dv.alloc<u32>(NR); xt.mo_nst = dv.alloc<u32>(NR);
-        xt.mc_src = dv.alloc<u32>(NCH); xt.mc_o0 = dv.alloc<u32>(NCH); xt.mc_no = dv.alloc<u32>(NCH); xt.mc_atoms = dv.alloc<u32>(NCH);
-        xt.mb_first = dv.alloc<u32>(NCH, true);
+        xt.r_astart = dv.alloc<u32>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.r_flag = dv.alloc<u8>(NR);
+        xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
         xt.xdoc = dv.alloc<XDoc>(D + 1, true);
         b->d_xdoc = xt.xdoc;
         LB_LAUNCH(k_exp_arena, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
-        LB_LAUNCH(k_exp_pack, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
+        if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
+        tm.kernel_launches += 2;
+        run_scans(b, {ScanJob{(const u8*)xt.ch_nseg, (u8*)xt.ch_seg0, 4, 8, NCH}});
+        u64 NSEG = d2h_one(b, xt.ch_seg0 + NCH);
+        xt.sg_src = dv.alloc<u32>(NSEG); xt.sg_r0 = dv.alloc<u32>(NSEG); xt.sg_from = dv.alloc<u32>(NSEG);
+        xt.sg_atoms = dv.alloc<u32>(NSEG); xt.sg_est = dv.alloc<u32>(NSEG); xt.sg_nmops = dv.alloc<u32>(NSEG);
+        xt.sg_ndel = dv.alloc<u32>(NSEG); xt.sg_nrows = dv.alloc<u32>(NSEG); xt.sg_last_head = dv.alloc<u32>(NSEG);
+        xt.fc_src = dv.alloc<u32>(NSEG); xt.fc_pos = dv.alloc<u32>(NSEG); xt.fc_r0 = dv.alloc<u32>(NSEG);
+        xt.fc_from = dv.alloc<u32>(NSEG); xt.fc_atoms = dv.alloc<u32>(NSEG); xt.fc_nrows = dv.alloc<u32>(NSEG);
+        xt.fc_ndel = dv.alloc<u32>(NSEG); xt.fc_block = dv.alloc<u8>(NSEG);
+        if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 1);
+        LB_LAUNCH(k_exp_store, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
         LB_LAUNCH(k_exp_sizes, nblk(D), TPB, 0, st, b->d_docs, D, xt, d_tmp_a, d_tmp_b);
         tm.kernel_launches += 3;
         run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)xt.xdoc + offsetof(XDoc, ob0), 4, sizeof(XDoc), D},

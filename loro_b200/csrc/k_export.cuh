@@ -9,43 +9,50 @@
 //   encoding/arena.rs:103-147 (ContainerArena), serde_columnar 0.3.14 column encoders (BoolRle, AnyRle,
 //   DeltaRle, DeltaOfDelta).
 //
-// What the imported document's change store looks like is re-derived from the decoded tables, per peer:
-//   A  ops of each decoded change go through the RleVec merge (block_encode.rs:651),
-//   B  changes enter the store in counter order (ChangeStore::insert_change, merge_interval 0 for imports),
-//   C  export re-inserts the stored changes into a fresh store (export_blocks_from) -- same rules, new sizes.
-// A thread per document runs A-C and leaves compact lists of merged ops / merged changes / output blocks;
-// a thread per output block then encodes it (two passes: sizes, bytes).
+// What the imported document's change store looks like is re-derived from the decoded tables:
+//   A  (thread per change) ops of each decoded change go through the RleVec merge (block_encode.rs:651); a change
+//      whose size estimate exceeds one block is cut into segments at op boundaries (split_change_then_insert);
+//   B  (thread per document, per peer in id order) the segments enter the store in counter order
+//      (ChangeStore::insert_change, merge_interval 0 for imports), and what comes out is pushed, as it completes,
+//   C  into the fresh store export builds (export_blocks_from): same rules, freshly computed sizes.
+// Only per-row flag bits (op start, segment start) and per-segment summaries are written; the merge decisions
+// look at the boundary ops only.  A thread per output block then gathers its ops into scratch columns and
+// encodes them (two passes: sizes, bytes).
 // Whether two neighbouring inserts merge depends on where their payloads landed in the importing document's
 // arenas (arena.rs:237-263): values are adjacent when nothing else was allocated in between (decode order),
 // strings additionally need the append-only buffer not to have been reallocated (capacity doubles from 32;
 // restated from append-only-bytes 0.1.12, same model as the oracle, unpinned by reference tests).
-// Not yet covered (lb_doc_export_updates answers LB_ERR_UNSUPPORTED for the document): changes whose size
-// estimate exceeds one block (split_change_then_insert), values containing nested maps (block-local key indices
-// inside the payload), documents with pending changes; Tree/MovableList/styles never reach this phase.
+// Not yet covered (lb_doc_export_updates answers LB_ERR_UNSUPPORTED for the document): a single insert larger
+// than a whole block (Op::slice inside split_change_then_insert), values containing nested maps (block-local key
+// indices inside the payload), documents with pending changes; Tree/MovableList/styles never reach this phase.
 #pragma once
 #include "lb_defs.h"
 
 enum { XK_NONE = 0, XK_LIST = 1, XK_TEXT = 2, XK_DEL = 3, XK_MAPSET = 4, XK_MAPDEL = 5 };
 #define LB_MAX_BLOCK_SIZE 4096   // change_store.rs:37
+#define XF_HEAD 1u               // row starts a (merged) op
+#define XF_SEG 2u                // row starts a segment of a split change
 
 struct XDoc {          // per document
-    u32 n_st, n_mo, n_mc, n_mb;   // store positions, merged ops, merged changes, output blocks
-    u32 flags;                    // bit0: export unsupported for this document
+    u32 n_fc, n_mb;    // final changes, output blocks
+    u32 flags;         // bit0: export unsupported for this document
     u32 pad;
-    u64 ob0;                      // first output block (batch-wide)
-    u64 scratch0;                 // first scratch word of this doc's blocks
-    u64 exp_off;                  // offset of the blob in the export buffer
+    u64 ob0;           // first output block (batch-wide)
+    u64 scratch0;      // first scratch word of this doc's blocks
+    u64 exp_off;       // offset of the blob in the export buffer
     u32 exp_len;
-    u32 n_blocks_pad;
+    u32 scratch_words;
 };
 struct XBlock {        // one output block
     u32 doc;
-    u32 mc0, mc1;      // merged-change range (absolute indices into mc_*)
+    u32 fc0, fc1;      // final-change range (absolute indices into fc_*)
     u32 len;           // encoded bytes (without the ULEB length prefix)
     u32 sec_len[8];
-    u32 col_len[8];    // ops columns 0-3, delete columns 4-6
-    u64 off;           // offset of the block bytes inside the export buffer
+    u32 col_len[8];    // ops columns 0-3, delete columns 4-6, [7] = register sizes
+    u64 off;           // offset of the block bytes inside the document's blob
     u64 scratch;       // scratch words of this block
+    u32 n_rows, n_dels;            // scratch capacities: rows, delete ops
+    u32 n_ops, n_del_ops, n_cids, pad;   // after the gather: merged ops, merged deletes, containers
 };
 
 struct ExportTables {
@@ -61,13 +68,14 @@ struct ExportTables {
     // per row
     u32* r_astart;     // arena position (values: atoms, strings: bytes) relative to the document
     u32* r_bytes;      // text rows: payload bytes
-    u32* st_row;       // store position -> row (per doc region [op0, op0 + n_st))
-    // merged ops (per doc region [op0, op0 + n_mo))
-    u8* mo_xk; u32* mo_cidx; i32* mo_ctr; u32* mo_atoms; i32* mo_prop; u32* mo_f0; u32* mo_f1; i32* mo_f2;
-    u32* mo_st0; u32* mo_nst;
-    // merged changes (per doc region [ch0, ch0 + n_mc)) and output blocks (first merged change, same region)
-    u32* mc_src; u32* mc_o0; u32* mc_no; u32* mc_atoms;
-    u32* mb_first;
+    u8* r_flag;        // XF_*
+    // per change
+    u32* ch_nseg;      // segments the change enters the store as (0 = not applied)
+    u64* ch_seg0;      // scan of ch_nseg
+    // per segment (index space: ch_seg0)
+    u32* sg_src; u32* sg_r0; u32* sg_from; u32* sg_atoms; u32* sg_est; u32* sg_nmops; u32* sg_ndel; u32* sg_nrows; u32* sg_last_head;
+    // final changes (same index space: a document never ends up with more changes than segments)
+    u32* fc_src; u32* fc_pos; u32* fc_r0; u32* fc_from; u32* fc_atoms; u32* fc_nrows; u32* fc_ndel; u8* fc_block;
     XDoc* xdoc;
 };
 
@@ -91,16 +99,6 @@ struct XOp {   // one (possibly merged) op: the fields the merge rules and the e
     // LIST/TEXT: f0 = arena start, f1 = arena end (TEXT: bytes; f1 - f0 = payload bytes)
     // DEL: f0 = target peer (doc-level), f1 = lowest target counter, f2 = signed length
 };
-__device__ __forceinline__ XOp xop_load(const ExportTables& t, u64 i) {
-    XOp o;
-    o.xk = t.mo_xk[i]; o.cidx = t.mo_cidx[i]; o.ctr = t.mo_ctr[i]; o.atoms = t.mo_atoms[i]; o.prop = t.mo_prop[i];
-    o.f0 = t.mo_f0[i]; o.f1 = t.mo_f1[i]; o.f2 = t.mo_f2[i]; o.st0 = t.mo_st0[i]; o.nst = t.mo_nst[i];
-    return o;
-}
-__device__ __forceinline__ void xop_store(const ExportTables& t, u64 i, const XOp& o) {
-    t.mo_xk[i] = o.xk; t.mo_cidx[i] = o.cidx; t.mo_ctr[i] = o.ctr; t.mo_atoms[i] = o.atoms; t.mo_prop[i] = o.prop;
-    t.mo_f0[i] = o.f0; t.mo_f1[i] = o.f1; t.mo_f2[i] = o.f2; t.mo_st0[i] = o.st0; t.mo_nst[i] = o.nst;
-}
 __device__ __forceinline__ u32 xop_estimate(const XOp& o) {   // list_op.rs:109-123, op/content.rs:70-77
     switch (o.xk) {
         case XK_LIST: return 4 * o.atoms;
@@ -167,6 +165,35 @@ __device__ inline void xop_merge(XOp& a, const XOp& b) {
     a.nst += b.nst;
 }
 
+// one decoded row as an op (map keys and delete targets at document level)
+__device__ inline XOp xop_from_row(const ExportTables& t, const DocInfo& di, u32 ch, u64 row) {
+    XOp o;
+    u8 kind = t.op_kind[row];
+    o.cidx = t.op_cidx[row];
+    o.ctr = t.op_counter[row];
+    o.atoms = t.op_len[row];
+    o.prop = t.op_prop[row];
+    o.f0 = o.f1 = 0; o.f2 = 0;
+    o.st0 = (u32)row; o.nst = 1;
+    switch (kind) {
+        case OPK_SEQ_INS:
+            if (t.dcont[di.cid0 + o.cidx].type == CT_TEXT) { o.xk = XK_TEXT; o.f0 = t.r_astart[row]; o.f1 = o.f0 + t.r_bytes[row]; }
+            else { o.xk = XK_LIST; o.f0 = t.r_astart[row]; o.f1 = o.f0 + o.atoms; }
+            break;
+        case OPK_SEQ_DEL: {
+            u32 dl = t.op_del[row];
+            o.xk = XK_DEL; o.f0 = t.op_aux[row]; o.f1 = (u32)t.del_counter[dl]; o.f2 = t.del_len[dl];
+            break;
+        }
+        case OPK_MAP_SET: case OPK_MAP_DEL:
+            o.xk = kind == OPK_MAP_SET ? XK_MAPSET : XK_MAPDEL;
+            o.prop = (i32)t.key_map[t.blocks[t.ch_block[ch]].key0 + (u32)o.prop];
+            break;
+        default: o.xk = XK_NONE;
+    }
+    return o;
+}
+
 // ---------------------------------------------------------------------------------------------- X1: arenas
 // thread per document: arena positions of every row in decode order (the importing document allocates while it
 // decodes: block_encode.rs:619-657)
@@ -175,13 +202,12 @@ __global__ void k_exp_arena(const DocInfo* __restrict__ docs, u32 n_docs, Export
     if (d >= n_docs) return;
     const DocInfo& di = docs[d];
     XDoc x;
-    x.n_st = x.n_mo = x.n_mc = x.n_mb = 0;
-    x.flags = 0; x.pad = 0; x.ob0 = 0; x.scratch0 = 0; x.exp_off = 0; x.exp_len = 0; x.n_blocks_pad = 0;
+    memset(&x, 0, sizeof(x));
     if (di.code == DOC_OK) {
         u32 vals = 0, strs = 0;
         for (u64 r = di.op0; r < di.op0 + di.n_ops; r++) {
             u8 k = t.op_kind[r];
-            if (k != OPK_SEQ_INS) continue;   // kind of a skipped (pending) row is OPK_SKIP: see k_exp_pack
+            if (k != OPK_SEQ_INS) continue;   // rows of pending changes are OPK_SKIP: such documents are not exported
             const DocContainer& dc = t.dcont[di.cid0 + t.op_cidx[r]];
             if (dc.type == CT_TEXT) {
                 Cur c(t.bytes + t.op_val_off[r], t.op_val_len[r]);
@@ -194,22 +220,104 @@ __global__ void k_exp_arena(const DocInfo* __restrict__ docs, u32 n_docs, Export
                 vals += t.op_len[r];
             }
         }
+        if ((di.has_unsupported & 0x7FFFFFFFu) || di.n_pending) x.flags |= 1;
+        for (u32 b = di.b0; b < di.b1; b++)
+            if (t.blocks[b].n_value_maps) x.flags |= 1;
     }
     t.xdoc[d] = x;
 }
 
-// ---------------------------------------------------------------------------------------------- X2: packing
-struct XChange {   // a (possibly merged) change during packing
-    u32 src;       // first source change: id, lamport, deps, timestamp, message
-    u32 o0, no;    // ops [o0, o0+no) in the mo arrays (absolute)
-    u32 atoms;
+// ---------------------------------------------------------------------------------------------- A: per change
+// thread per change.  pass 0: RleVec merge inside the change (XF_HEAD), split into segments (XF_SEG), segment count.
+// pass 1: one summary record per segment.
+__global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
+    u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_changes) return;
+    if (!t.ch_applied[ch]) { if (!pass) t.ch_nseg[ch] = 0; return; }
+    u32 doc = t.blocks[t.ch_block[ch]].doc;
+    const DocInfo& di = docs[doc];
+    u64 r0 = t.ch_op0[ch];
+    u32 nr = t.ch_nops[ch];
+    if (pass == 0) {
+        // intra-change merge + total estimate
+        XOp back;
+        back.xk = XK_NONE;
+        u32 est_ops = 0;
+        bool bad = false;
+        for (u32 r = 0; r < nr; r++) {
+            XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
+            if (o.xk == XK_NONE) bad = true;
+            if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[r0 + r] = 0; }
+            else { back = o; est_ops += xop_estimate(o); t.r_flag[r0 + r] = XF_HEAD; }
+        }
+        u32 ndeps = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
+        u32 est0 = 4 + (ndeps > 1 ? (ndeps - 1) * 4 : 0);
+        u32 nseg = 1;
+        t.r_flag[r0] |= XF_SEG;
+        if (est0 + est_ops > LB_MAX_BLOCK_SIZE) {
+            // split_change_then_insert (change_store.rs:913-1000): walk the merged ops
+            u64 est = est0;
+            bool has_ops = false;
+            u32 r = 0;
+            while (r < nr) {
+                XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
+                u32 r1 = r + 1;
+                while (r1 < nr && !(t.r_flag[r0 + r1] & XF_HEAD)) { xop_merge(o, xop_from_row(t, di, (u32)ch, r0 + r1)); r1++; }
+                u64 sz = xop_estimate(o);
+                if (sz >= (u64)LB_MAX_BLOCK_SIZE - est && has_ops) { t.r_flag[r0 + r] |= XF_SEG; nseg++; est = 4; has_ops = false; }
+                u64 room = (u64)LB_MAX_BLOCK_SIZE - est;
+                if (sz > room && (o.xk == XK_LIST || o.xk == XK_TEXT)) {
+                    u64 end = o.xk == XK_TEXT ? (room < o.atoms ? room : o.atoms) : (room / 4 < o.atoms ? room / 4 : o.atoms);
+                    if (end != 0) bad = true;   // the op itself would be sliced
+                }
+                est += sz;
+                if (est > LB_MAX_BLOCK_SIZE && has_ops) { t.r_flag[r0 + r] |= XF_SEG; nseg++; est = 4; }
+                has_ops = true;
+                r = r1;
+            }
+        }
+        t.ch_nseg[ch] = nseg;
+        if (bad) atomicOr(&t.xdoc[doc].flags, 1u);
+        return;
+    }
+    // pass 1: segment summaries
+    u64 sg = t.ch_seg0[ch];
+    u32 r = 0;
+    u32 from = 0;
+    while (r < nr) {
+        u32 r_start = r, est = 0, nm = 0, ndel = 0, atoms = 0, last_head = r;
+        do {
+            XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
+            last_head = r;
+            u32 r1 = r + 1;
+            while (r1 < nr && !(t.r_flag[r0 + r1] & XF_HEAD)) { xop_merge(o, xop_from_row(t, di, (u32)ch, r0 + r1)); r1++; }
+            est += xop_estimate(o);
+            nm++;
+            ndel += o.xk == XK_DEL;
+            atoms += o.atoms;
+            r = r1;
+        } while (r < nr && !(t.r_flag[r0 + r] & XF_SEG));
+        t.sg_src[sg] = (u32)ch; t.sg_r0[sg] = r_start; t.sg_from[sg] = from; t.sg_atoms[sg] = atoms; t.sg_est[sg] = est;
+        t.sg_nmops[sg] = nm; t.sg_ndel[sg] = ndel; t.sg_nrows[sg] = r - r_start; t.sg_last_head[sg] = last_head;
+        from += atoms;
+        sg++;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- B + C: the stores
+struct XEntry {        // a change on its way through a store: one segment, or a run of merged ones
+    u32 src, from;     // metadata of its first segment: source change + atom offset (deps, lamport, timestamp, message)
+    u32 pos, r0;       // where its rows start: position in ch_order (absolute) + row inside that change
+    u32 atoms, est_ops, nmops, ndel, nrows;
+    u32 lh_ch, lh_row; // last op: source change + row (inside that change) of its first row ...
+    XOp last;          // ... or, once the entry has been through a store, the accumulated op itself
+    bool last_valid;
 };
-struct XStore {    // the store of one peer while changes are inserted in counter order
-    bool have_block;
+struct XStore {
+    bool have_block, open_valid, open_starts_block;
     u32 blk_est;
-    u32 last_src;  // first source change of the block's last (merged) change
-    u32 w_op;      // next free merged-op slot (absolute)
-    u32 w_ch;      // next free merged-change slot (absolute)
+    XEntry open;       // the store's last change (still able to absorb the next one)
+    XOp back;          // last op of `open`, accumulated
 };
 __device__ __forceinline__ bool xmsg_same(const ExportTables& t, u32 a, u32 b) {
     u32 la = t.ch_msg_len[a], lb = t.ch_msg_len[b];
@@ -220,152 +328,150 @@ __device__ __forceinline__ bool xmsg_same(const ExportTables& t, u32 a, u32 b) {
         if (pa[i] != pb[i]) return false;
     return true;
 }
-// ChangeStore::insert_change + ChangesBlock::push_change (change_store.rs:711-764, 1244-1291) for the next change
-// of the peer.  Ops of X sit at [X.o0, X.o0 + X.no) at or after s.w_op; they are compacted down to s.w_op.
-// `mark_blocks`: record block starts (final pass only).  Returns false when the change would have to be split.
-__device__ inline bool xstore_insert(const ExportTables& t, XStore& s, XChange X, bool mark_blocks, bool split_when_exceeds) {
-    u32 ndeps = t.ch_ndeps[X.src] + (t.ch_dep_self[X.src] ? 1u : 0u);
-    u32 est = 4 + (ndeps > 1 ? (ndeps - 1) * 4 : 0);
-    for (u32 i = 0; i < X.no; i++) est += xop_estimate(xop_load(t, X.o0 + i));
-    bool ok = true;
-    if (est > LB_MAX_BLOCK_SIZE && split_when_exceeds) ok = false;   // split_change_then_insert: not restated yet
+__device__ __forceinline__ u32 xentry_ndeps(const ExportTables& t, const XEntry& e) {
+    return e.from ? 1u : t.ch_ndeps[e.src] + (t.ch_dep_self[e.src] ? 1u : 0u);
+}
+// cursor over the rows of an entry in store order (rows of consecutive applied changes of the peer)
+struct XRows {
+    const ExportTables& t; u32 pos; u32 r; u32 ch; u32 nr; u64 row0;
+    __device__ XRows(const ExportTables& t_, u32 pos_, u32 r_) : t(t_), pos(pos_), r(r_) { load(); }
+    __device__ void load() { ch = t.ch_order[pos]; nr = t.ch_nops[ch]; row0 = t.ch_op0[ch]; }
+    __device__ u64 row() const { return row0 + r; }
+    __device__ void next() {
+        r++;
+        while (r >= nr) { pos++; r = 0; ch = t.ch_order[pos]; if (!t.ch_applied[ch]) { nr = 0; continue; } nr = t.ch_nops[ch]; row0 = t.ch_op0[ch]; }
+    }
+};
+// accumulate the merged op that starts at the cursor (consumes its rows, at most `left` of them)
+__device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows& it, u32& left) {
+    XOp o = xop_from_row(t, di, it.ch, it.row());
+    left--;
+    if (left) it.next();
+    while (left && !(t.r_flag[it.row()] & XF_HEAD)) {
+        xop_merge(o, xop_from_row(t, di, it.ch, it.row()));
+        left--;
+        if (left) it.next();
+    }
+    return o;
+}
+// last op of an entry that came straight from stage A: from its head row to the end of its segment
+__device__ inline XOp xentry_last_op(const ExportTables& t, const DocInfo& di, const XEntry& E) {
+    if (E.last_valid) return E.last;
+    u64 row0 = t.ch_op0[E.lh_ch];
+    u32 nr = t.ch_nops[E.lh_ch];
+    XOp o = xop_from_row(t, di, E.lh_ch, row0 + E.lh_row);
+    u32 r = E.lh_row + 1;
+    while (r < nr && !(t.r_flag[row0 + r] & (XF_HEAD | XF_SEG))) { xop_merge(o, xop_from_row(t, di, E.lh_ch, row0 + r)); r++; }
+    return o;
+}
+// ChangeStore::insert_change + ChangesBlock::push_change (change_store.rs:711-764, 1244-1291): E is the next change
+// of the peer.  Returns true when the store's previous last change is complete (copied to `done`).
+__device__ inline bool xstore_push(const ExportTables& t, const DocInfo& di, XStore& s, const XEntry& E, XEntry& done,
+                                   bool& done_starts_block) {
+    u32 nd = xentry_ndeps(t, E);
+    u32 est = 4 + E.est_ops + (nd > 1 ? (nd - 1) * 4 : 0);
+    bool new_block = true;
     if (s.have_block) {
         bool is_full = est + s.blk_est > LB_MAX_BLOCK_SIZE;
-        bool can = t.ch_dep_self[X.src] && t.ch_ndeps[X.src] == 0 && t.ch_ts[X.src] <= t.ch_ts[s.last_src] &&
-                   xmsg_same(t, s.last_src, X.src);
+        bool dep_only_self = E.from ? true : (t.ch_dep_self[E.src] && t.ch_ndeps[E.src] == 0);
+        bool can = dep_only_self && t.ch_ts[E.src] <= t.ch_ts[s.open.src] && xmsg_same(t, s.open.src, E.src);
         bool single = false;
-        if (can && is_full && X.no == 1) single = xop_mergable(xop_load(t, s.w_op - 1), xop_load(t, X.o0));
+        if (can && is_full && E.nmops == 1) {
+            XRows it(t, E.pos, E.r0);
+            u32 left = E.nrows;
+            single = xop_mergable(s.back, xop_gather(t, di, it, left));
+        }
         if (can && (!is_full || single)) {
-            XOp back = xop_load(t, s.w_op - 1);
-            for (u32 i = 0; i < X.no; i++) {
-                XOp o = xop_load(t, X.o0 + i);
-                if (xop_mergable(back, o)) xop_merge(back, o);
-                else {
-                    xop_store(t, s.w_op - 1, back);
-                    s.blk_est += xop_estimate(o);
-                    back = o;
-                    s.w_op++;
-                }
+            // the ops of E are pushed onto the last change (RleVec::push): a prefix of them may merge into its last op
+            XRows it(t, E.pos, E.r0);
+            u32 left = E.nrows;
+            u32 merged = 0, merged_sz = 0, merged_del = 0;
+            while (left) {
+                u64 head_row = it.row();
+                XOp o = xop_gather(t, di, it, left);
+                if (!xop_mergable(s.back, o)) break;
+                merged_sz += xop_estimate(o);
+                merged_del += o.xk == XK_DEL;
+                xop_merge(s.back, o);
+                t.r_flag[head_row] &= (u8)~XF_HEAD;
+                merged++;
             }
-            xop_store(t, s.w_op - 1, back);
-            u32 lc = s.w_ch - 1;
-            t.mc_no[lc] = s.w_op - t.mc_o0[lc];
-            t.mc_atoms[lc] += X.atoms;
-            return ok;
+            s.blk_est += E.est_ops - merged_sz;          // only ops that did not merge count (change_store.rs:1271-1279)
+            s.open.atoms += E.atoms;
+            s.open.est_ops += E.est_ops - 8 * merged_del; // fresh estimate of the grown change (used by the next store)
+            s.open.nmops += E.nmops - merged;
+            s.open.ndel += E.ndel - merged_del;
+            s.open.nrows += E.nrows;
+            if (E.nmops > merged) s.back = xentry_last_op(t, di, E);
+            return false;
         }
-        if (!is_full) {
-            s.blk_est += est;
-            goto append;
-        }
+        if (!is_full) { s.blk_est += est; new_block = false; }
     }
-    // a new block starts with this change
-    s.have_block = true;
-    s.blk_est = est;
-    if (mark_blocks) t.mb_first[s.w_ch] = 1;
-append:
-    for (u32 i = 0; i < X.no; i++) {
-        if (s.w_op + i != X.o0 + i) xop_store(t, s.w_op + i, xop_load(t, X.o0 + i));
-    }
-    t.mc_src[s.w_ch] = X.src;
-    t.mc_o0[s.w_ch] = s.w_op;
-    t.mc_no[s.w_ch] = X.no;
-    t.mc_atoms[s.w_ch] = X.atoms;
-    s.w_op += X.no;
-    s.w_ch++;
-    s.last_src = X.src;
-    return ok;
+    bool closed = s.open_valid;
+    if (closed) { done = s.open; done.last = s.back; done.last_valid = true; done_starts_block = s.open_starts_block; }
+    if (new_block) { s.have_block = true; s.blk_est = est; }
+    s.open = E;
+    s.open_valid = true;
+    s.open_starts_block = new_block;
+    s.back = xentry_last_op(t, di, E);
+    return closed;
 }
 
 // thread per document
-__global__ void k_exp_pack(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t) {
+__global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     const DocInfo& di = docs[d];
     if (di.code != DOC_OK) return;
     XDoc x = t.xdoc[d];
-    u32 op_base = (u32)di.op0, ch_base = (u32)di.ch0;
-    u32 w_st = op_base, w_op = op_base, w_ch = ch_base;   // absolute write positions
-    bool unsupported = false;
+    if (x.flags & 1) { t.xdoc[d] = x; return; }
+    u64 w = t.ch_seg0[di.ch0];   // final changes of the document are written from its first segment slot on
+    u64 w0 = w;
+    u32 n_mb = 0;
+    auto emit = [&](const XEntry& e, bool starts_block) {
+        t.fc_src[w] = e.src; t.fc_pos[w] = e.pos; t.fc_r0[w] = e.r0; t.fc_from[w] = e.from; t.fc_atoms[w] = e.atoms;
+        t.fc_nrows[w] = e.nrows; t.fc_ndel[w] = e.ndel; t.fc_block[w] = starts_block ? 1 : 0;
+        n_mb += starts_block;
+        w++;
+    };
     for (u32 rank = 0; rank < di.P; rank++) {   // blocks are keyed by (peer id, counter): ascending peer id
         u32 p = 0;
         while (p < di.P && t.dpeer[di.peer0 + p].rank != rank) p++;
         if (p == di.P) break;
         const DocPeer& dp = t.dpeer[di.peer0 + p];
-        u32 a_op0 = w_op, a_ch0 = w_ch;
-        // ---- stage A: decoded changes, ops re-pushed through the RleVec merge
-        u32 a_op = a_op0, a_ch = a_ch0;
+        XStore s1, s2;   // import store, export store
+        s1.have_block = s1.open_valid = s1.open_starts_block = false; s1.blk_est = 0;
+        s2 = s1;
+        XEntry done;
+        bool done_blk = false;
         for (u32 k = 0; k < dp.ch_count; k++) {
-            u32 ch = t.ch_order[di.ch0 + dp.ch_first + k];
-            if (!t.ch_applied[ch]) continue;
-            u64 r0 = t.ch_op0[ch];
-            u32 nr = t.ch_nops[ch];
-            u32 first = a_op;
-            for (u32 r = 0; r < nr; r++) {
-                u64 row = r0 + r;
-                XOp o;
-                u8 kind = t.op_kind[row];
-                o.cidx = t.op_cidx[row];
-                o.ctr = t.op_counter[row];
-                o.atoms = t.op_len[row];
-                o.prop = t.op_prop[row];
-                o.f0 = o.f1 = 0; o.f2 = 0;
-                o.st0 = w_st; o.nst = 1;
-                t.st_row[w_st++] = (u32)row;
-                switch (kind) {
-                    case OPK_SEQ_INS:
-                        if (t.dcont[di.cid0 + o.cidx].type == CT_TEXT) { o.xk = XK_TEXT; o.f0 = t.r_astart[row]; o.f1 = o.f0 + t.r_bytes[row]; }
-                        else { o.xk = XK_LIST; o.f0 = t.r_astart[row]; o.f1 = o.f0 + o.atoms; }
-                        break;
-                    case OPK_SEQ_DEL: {
-                        u32 dl = t.op_del[row];
-                        o.xk = XK_DEL; o.f0 = t.op_aux[row]; o.f1 = (u32)t.del_counter[dl]; o.f2 = t.del_len[dl];
-                        break;
-                    }
-                    case OPK_MAP_SET: case OPK_MAP_DEL:
-                        o.xk = kind == OPK_MAP_SET ? XK_MAPSET : XK_MAPDEL;
-                        o.prop = (i32)t.key_map[t.blocks[t.ch_block[ch]].key0 + (u32)o.prop];
-                        break;
-                    default: o.xk = XK_NONE; unsupported = true;
+            u32 pos = (u32)di.ch0 + dp.ch_first + k;
+            u32 ch = t.ch_order[pos];
+            u32 nseg = t.ch_nseg[ch];
+            u64 sg = t.ch_seg0[ch];
+            for (u32 q = 0; q < nseg; q++, sg++) {
+                XEntry E;
+                E.src = ch; E.from = t.sg_from[sg]; E.pos = pos; E.r0 = t.sg_r0[sg]; E.atoms = t.sg_atoms[sg];
+                E.est_ops = t.sg_est[sg]; E.nmops = t.sg_nmops[sg]; E.ndel = t.sg_ndel[sg]; E.nrows = t.sg_nrows[sg];
+                E.lh_ch = ch; E.lh_row = t.sg_last_head[sg]; E.last_valid = false;
+                if (xstore_push(t, di, s1, E, done, done_blk)) {
+                    XEntry d2;
+                    bool d2_blk = false;
+                    if (xstore_push(t, di, s2, done, d2, d2_blk)) emit(d2, d2_blk);
                 }
-                if (a_op > first) {
-                    XOp back = xop_load(t, a_op - 1);
-                    if (xop_mergable(back, o)) { xop_merge(back, o); xop_store(t, a_op - 1, back); continue; }
-                }
-                xop_store(t, a_op++, o);
             }
-            t.mc_src[a_ch] = ch;
-            t.mc_o0[a_ch] = first;
-            t.mc_no[a_ch] = a_op - first;
-            t.mc_atoms[a_ch] = t.ch_len[ch];
-            a_ch++;
         }
-        // ---- stage B: import (insert_change, merge_interval 0, split_when_exceeds)
-        XStore s;
-        s.have_block = false; s.blk_est = 0; s.last_src = 0; s.w_op = a_op0; s.w_ch = a_ch0;
-        for (u32 k = a_ch0; k < a_ch; k++) {
-            XChange X;
-            X.src = t.mc_src[k]; X.o0 = t.mc_o0[k]; X.no = t.mc_no[k]; X.atoms = t.mc_atoms[k];
-            if (!xstore_insert(t, s, X, false, true)) unsupported = true;
+        if (s1.open_valid) {
+            XEntry d2;
+            bool d2_blk = false;
+            s1.open.last = s1.back;
+            s1.open.last_valid = true;
+            if (xstore_push(t, di, s2, s1.open, d2, d2_blk)) emit(d2, d2_blk);
         }
-        u32 b_op = s.w_op, b_ch = s.w_ch;
-        (void)b_op;
-        // ---- stage C: export (export_blocks_from -> fresh store, no splitting)
-        s.have_block = false; s.blk_est = 0; s.last_src = 0; s.w_op = a_op0; s.w_ch = a_ch0;
-        for (u32 k = a_ch0; k < b_ch; k++) t.mb_first[k] = 0;
-        for (u32 k = a_ch0; k < b_ch; k++) {
-            XChange X;
-            X.src = t.mc_src[k]; X.o0 = t.mc_o0[k]; X.no = t.mc_no[k]; X.atoms = t.mc_atoms[k];
-            xstore_insert(t, s, X, true, false);
-        }
-        for (u32 k = a_ch0; k < s.w_ch; k++) x.n_mb += t.mb_first[k];
-        w_op = s.w_op;
-        w_ch = s.w_ch;
+        if (s2.open_valid) emit(s2.open, s2.open_starts_block);
     }
-    x.n_st = w_st - op_base;
-    x.n_mo = w_op - op_base;
-    x.n_mc = w_ch - ch_base;
-    if (unsupported || (di.has_unsupported & 0x7FFFFFFFu) || di.n_pending) x.flags |= 1;
-    if (x.flags & 1) x.n_mb = 0;
+    x.n_fc = (u32)(w - w0);
+    x.n_mb = n_mb;
     t.xdoc[d] = x;
 }
 
@@ -376,23 +482,40 @@ __global__ void k_exp_list(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
     const DocInfo& di = docs[d];
     const XDoc& x = t.xdoc[d];
     if (di.code != DOC_OK || x.n_mb == 0) return;
-    u32 ch_base = (u32)di.ch0;
-    u64 ob = x.ob0;
-    u32 per = 2 * (di.P + di.K + di.C);
-    u32 open = 0xFFFFFFFFu;
-    u32 idx = 0;
-    for (u32 k = ch_base; k < ch_base + x.n_mc; k++) {
-        if (t.mb_first[k]) {
-            if (open != 0xFFFFFFFFu) { xb[ob + idx].mc1 = k; idx++; }
-            XBlock b;
-            b.doc = d; b.mc0 = k; b.mc1 = k; b.len = 0; b.off = 0;
-            for (int i = 0; i < 8; i++) { b.sec_len[i] = 0; b.col_len[i] = 0; }
-            b.scratch = x.scratch0 + (u64)idx * per;
-            xb[ob + idx] = b;
-            open = k;
+    u64 f0 = t.ch_seg0[di.ch0];
+    u32 regs = 2 * (di.P + di.K + di.C);
+    u64 scr = x.scratch0;
+    int idx = -1;
+    XBlock b;
+    memset(&b, 0, sizeof(b));
+    for (u64 k = f0; k < f0 + x.n_fc; k++) {
+        if (t.fc_block[k]) {
+            if (idx >= 0) { b.fc1 = (u32)k; xb[x.ob0 + idx] = b; scr += regs + 5 * b.n_rows + 3 * b.n_dels; }
+            idx++;
+            memset(&b, 0, sizeof(b));
+            b.doc = d; b.fc0 = (u32)k; b.scratch = scr;
         }
+        b.n_rows += t.fc_nrows[k];
+        b.n_dels += t.fc_ndel[k];
     }
-    if (open != 0xFFFFFFFFu) xb[ob + idx].mc1 = ch_base + x.n_mc;
+    if (idx >= 0) { b.fc1 = (u32)(f0 + x.n_fc); xb[x.ob0 + idx] = b; }
+}
+// thread per document: scratch words of its blocks (registers + op columns + delete columns)
+__global__ void k_exp_sizes(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t, u32* __restrict__ n_blocks,
+                            u32* __restrict__ n_scratch) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    const XDoc& x = t.xdoc[d];
+    u32 nb = di.code == DOC_OK ? x.n_mb : 0;
+    u64 words = 0;
+    if (nb) {
+        u64 f0 = t.ch_seg0[di.ch0];
+        words = (u64)nb * 2 * (di.P + di.K + di.C);
+        for (u64 k = f0; k < f0 + x.n_fc; k++) words += 5ull * t.fc_nrows[k] + 3ull * t.fc_ndel[k];
+    }
+    n_blocks[d] = nb;
+    n_scratch[d] = (u32)words;
 }
 
 // ---------------------------------------------------------------------------------------------- column encoders
@@ -498,7 +621,7 @@ __device__ inline void enc_dod(XSink& s, u32 n, F val) {
     if (bw.nbits) s.put((u8)((bw.cur & 0xFF) << (8 - bw.nbits)));
 }
 
-// ---------------------------------------------------------------------------------------------- X4/X6: encode
+// ---------------------------------------------------------------------------------------------- encode
 // First-use registers of one block (encoding/value_register.rs): order lists + inverse maps in scratch.
 struct XReg {
     u32* ord; u32* inv; u32 n;
@@ -511,15 +634,15 @@ struct XReg {
 };
 // cross-peer deps of the block's changes as one flat sequence (cursor: accesses are almost monotonic)
 struct XDeps {
-    const ExportTables& t; u32 mc0, N; u32 j; u32 base;
-    __device__ XDeps(const ExportTables& t_, u32 mc0_, u32 N_) : t(t_), mc0(mc0_), N(N_), j(0), base(0) {}
+    const ExportTables& t; u32 fc0, N; u32 j; u32 base;
+    __device__ XDeps(const ExportTables& t_, u32 fc0_, u32 N_) : t(t_), fc0(fc0_), N(N_), j(0), base(0) {}
+    __device__ u32 nd(u32 jj) const { return t.fc_from[fc0 + jj] ? 0u : t.ch_ndeps[t.fc_src[fc0 + jj]]; }
     __device__ u64 at(u32 i) {   // index of flat dep i in the dep tables
         if (i < base) { j = 0; base = 0; }
         while (j < N) {
-            u32 src = t.mc_src[mc0 + j];
-            u32 nd = t.ch_ndeps[src];
-            if (i < base + nd) return t.ch_dep0[src] + (i - base);
-            base += nd;
+            u32 n = nd(j);
+            if (i < base + n) return t.ch_dep0[t.fc_src[fc0 + j]] + (i - base);
+            base += n;
             j++;
         }
         return 0;
@@ -534,7 +657,7 @@ __device__ __forceinline__ u8 xk_value_type(u8 xk) {
     }
 }
 
-// thread per output block.  pass 0: registers + section sizes ; pass 1: bytes.
+// thread per output block.  pass 0: gather ops into scratch columns, registers, section sizes ; pass 1: bytes.
 __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
                              u32* __restrict__ scratch, u8* __restrict__ out, int pass) {
     u64 bi_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -547,35 +670,43 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     peers.ord = sc; peers.inv = sc + P;
     keys.ord = sc + 2 * P; keys.inv = keys.ord + K;
     cids.ord = keys.ord + 2 * K; cids.inv = cids.ord + C;
-    const u32 mc0 = B.mc0, N = B.mc1 - B.mc0;
-    const u32 o0 = t.mc_o0[mc0];
-    const u32 o1 = t.mc_o0[B.mc1 - 1] + t.mc_no[B.mc1 - 1];
-    const u32 n_ops = o1 - o0;
-    const u32 first_src = t.mc_src[mc0], last_src = t.mc_src[B.mc1 - 1];
+    u32* c_cidx = cids.ord + 2 * C;            // op columns, capacity n_rows each
+    u32* c_prop = c_cidx + B.n_rows;
+    u32* c_vt = c_prop + B.n_rows;
+    u32* c_atoms = c_vt + B.n_rows;
+    u32* c_bytes = c_atoms + B.n_rows;         // text: payload bytes ; other: first row of the op
+    u32* d_peer = c_bytes + B.n_rows;          // delete columns, capacity n_dels each
+    u32* d_ctr = d_peer + B.n_dels;
+    u32* d_len = d_ctr + B.n_dels;
+    const u32 fc0 = B.fc0, N = B.fc1 - B.fc0;
+    const u32 first_src = t.fc_src[fc0];
     u32 n_dep = 0;
-    for (u32 j = 0; j < N; j++) n_dep += t.ch_ndeps[t.mc_src[mc0 + j]];
-    u32 n_del = 0;
+    for (u32 j = 0; j < N; j++) n_dep += t.fc_from[fc0 + j] ? 0u : t.ch_ndeps[t.fc_src[fc0 + j]];
     if (pass == 0) {
         for (u32 i = 0; i < P; i++) peers.inv[i] = 0xFFFFFFFFu;
         for (u32 i = 0; i < K; i++) keys.inv[i] = 0xFFFFFFFFu;
         for (u32 i = 0; i < C; i++) cids.inv[i] = 0xFFFFFFFFu;
         peers.n = keys.n = cids.n = 0;
-    }
-    // peer of the block: the author of its changes
-    u32 block_peer;
-    {
-        const BlockInfo& sb = t.blocks[t.ch_block[first_src]];
-        block_peer = t.peer_map[sb.peer0];
-    }
-    if (pass == 0) {
-        peers.reg(block_peer);
-        // ops in order: containers, map keys, delete targets (block_encode.rs:180-236); values are made block-local
-        for (u32 i = o0; i < o1; i++) {
-            u8 xk = t.mo_xk[i];
-            t.mo_cidx[i] = cids.reg(t.mo_cidx[i]);
-            if (xk == XK_MAPSET || xk == XK_MAPDEL) t.mo_prop[i] = (i32)keys.reg((u32)t.mo_prop[i]);
-            else if (xk == XK_DEL) { t.mo_f0[i] = peers.reg(t.mo_f0[i]); n_del++; }
+        peers.reg(t.peer_map[t.blocks[t.ch_block[first_src]].peer0]);   // the author of the block's changes
+        // ops in order: containers, map keys, delete targets (block_encode.rs:180-236)
+        u32 n_ops = 0, n_del = 0;
+        for (u32 j = 0; j < N; j++) {
+            XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
+            u32 left = t.fc_nrows[fc0 + j];
+            while (left) {
+                u32 first_row = (u32)it.row();
+                XOp o = xop_gather(t, di, it, left);
+                c_cidx[n_ops] = cids.reg(o.cidx);
+                c_prop[n_ops] = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
+                c_vt[n_ops] = xk_value_type(o.xk);
+                c_atoms[n_ops] = o.atoms;
+                c_bytes[n_ops] = o.xk == XK_TEXT ? o.f1 - o.f0 : first_row;
+                if (o.xk == XK_DEL) { d_peer[n_del] = peers.reg(o.f0); d_ctr[n_del] = o.f1; d_len[n_del] = (u32)o.f2; n_del++; }
+                n_ops++;
+            }
         }
+        B.n_ops = n_ops;
+        B.n_del_ops = n_del;
         // ContainerArena::from_containers (arena.rs:103-147): roots register their name, normals their peer
         for (u32 i = 0; i < cids.n; i++) {
             const DocContainer& dc = t.dcont[di.cid0 + cids.ord[i]];
@@ -583,44 +714,46 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         }
         // encode_changes (block_meta_encode.rs:13-88): dependency peers
         for (u32 j = 0; j < N; j++) {
-            u32 src = t.mc_src[mc0 + j];
+            if (t.fc_from[fc0 + j]) continue;
+            u32 src = t.fc_src[fc0 + j];
             const BlockInfo& sb = t.blocks[t.ch_block[src]];
             for (u32 k = 0; k < t.ch_ndeps[src]; k++) peers.reg(t.peer_map[sb.peer0 + t.dep_peer_idx[t.ch_dep0[src] + k]]);
         }
-        B.col_len[7] = peers.n | (keys.n << 16);   // register sizes for pass 1 (cids.n lives in sec_len scratch below)
+        B.col_len[7] = peers.n | (keys.n << 16);
+        B.n_cids = cids.n;
     } else {
         peers.n = B.col_len[7] & 0xFFFFu;
         keys.n = B.col_len[7] >> 16;
-        for (u32 i = o0; i < o1; i++) n_del += t.mo_xk[i] == XK_DEL;
+        cids.n = B.n_cids;
     }
-    // number of containers: recount from the inverse map in pass 1
-    if (pass == 1) { u32 n = 0; for (u32 i = 0; i < C; i++) n += cids.inv[i] != 0xFFFFFFFFu; cids.n = n; }
+    const u32 n_ops = B.n_ops, n_del = B.n_del_ops;
 
     // ------------------------------------------------------------------ section writers (count or write)
+    auto dep_self = [&](u32 j) -> bool { return t.fc_from[fc0 + j] ? true : t.ch_dep_self[t.fc_src[fc0 + j]] != 0; };
     auto dep_local = [&](XDeps& dc, u32 i) -> i64 {
         u64 di_ = dc.at(i);
-        // source block of the owning change: dc.j is positioned on it after at()
-        const BlockInfo& sb = t.blocks[t.ch_block[t.mc_src[mc0 + dc.j]]];
+        const BlockInfo& sb = t.blocks[t.ch_block[t.fc_src[fc0 + dc.j]]];
         return (i64)peers.inv[t.peer_map[sb.peer0 + t.dep_peer_idx[di_]]];
     };
+    auto lamport = [&](u32 j) -> i64 { return (i64)t.ch_lamport[t.fc_src[fc0 + j]] + t.fc_from[fc0 + j]; };
     auto w_header = [&](XSink& s) {
         s.varint(peers.n);
         for (u32 i = 0; i < peers.n; i++) {
             u64 id = t.dpeer[di.peer0 + peers.ord[i]].id;
             for (int k = 0; k < 8; k++) s.put((u8)(id >> (8 * k)));
         }
-        for (u32 j = 0; j + 1 < N; j++) s.varint(t.mc_atoms[mc0 + j]);
-        enc_boolrle(s, N, [&](u32 j) { return t.ch_dep_self[t.mc_src[mc0 + j]] != 0; });
-        enc_anyrle(s, N, [&](u32 j) -> i64 { return (i64)t.ch_ndeps[t.mc_src[mc0 + j]]; }, WrVarint());
-        { XDeps dc(t, mc0, N); enc_anyrle(s, n_dep, [&](u32 i) -> i64 { return dep_local(dc, i); }, WrVarint()); }
-        { XDeps dc(t, mc0, N); enc_dod(s, n_dep, [&](u32 i) -> i64 { return (i64)t.dep_counter[dc.at(i)]; }); }
-        enc_dod(s, N - 1, [&](u32 j) -> i64 { return (i64)t.ch_lamport[t.mc_src[mc0 + j]]; });
+        for (u32 j = 0; j + 1 < N; j++) s.varint(t.fc_atoms[fc0 + j]);
+        enc_boolrle(s, N, dep_self);
+        { XDeps dc(t, fc0, N); enc_anyrle(s, N, [&](u32 j) -> i64 { return (i64)dc.nd(j); }, WrVarint()); }
+        { XDeps dc(t, fc0, N); enc_anyrle(s, n_dep, [&](u32 i) -> i64 { return dep_local(dc, i); }, WrVarint()); }
+        { XDeps dc(t, fc0, N); enc_dod(s, n_dep, [&](u32 i) -> i64 { return (i64)t.dep_counter[dc.at(i)]; }); }
+        enc_dod(s, N - 1, lamport);
     };
     auto w_meta = [&](XSink& s) {
-        enc_dod(s, N, [&](u32 j) -> i64 { return t.ch_ts[t.mc_src[mc0 + j]]; });
-        enc_anyrle(s, N, [&](u32 j) -> i64 { return (i64)t.ch_msg_len[t.mc_src[mc0 + j]]; }, WrVarint());
+        enc_dod(s, N, [&](u32 j) -> i64 { return t.ch_ts[t.fc_src[fc0 + j]]; });
+        enc_anyrle(s, N, [&](u32 j) -> i64 { return (i64)t.ch_msg_len[t.fc_src[fc0 + j]]; }, WrVarint());
         for (u32 j = 0; j < N; j++) {
-            u32 src = t.mc_src[mc0 + j];
+            u32 src = t.fc_src[fc0 + j];
             s.copy(t.bytes + t.ch_msg_off[src], t.ch_msg_len[src]);
         }
     };
@@ -644,57 +777,53 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     };
     auto w_opcol = [&](XSink& s, int col) {
         switch (col) {
-            case 0: enc_deltarle(s, n_ops, [&](u32 i) -> i64 { return (i64)t.mo_cidx[o0 + i]; }); break;
-            case 1: enc_deltarle(s, n_ops, [&](u32 i) -> i64 { return (i64)t.mo_prop[o0 + i]; }); break;
-            case 2: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)xk_value_type(t.mo_xk[o0 + i]); }, WrByte()); break;
-            default: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)t.mo_atoms[o0 + i]; }, WrVarint());
+            case 0: enc_deltarle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_cidx[i]; }); break;
+            case 1: enc_deltarle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_prop[i]; }); break;
+            case 2: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_vt[i]; }, WrByte()); break;
+            default: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_atoms[i]; }, WrVarint());
         }
     };
-    // delete rows as a flat sequence: cursor over the ops
-    u32 dcur_i = 0, dcur_op = o0;   // dcur_op = op index of delete number dcur_i (when valid)
-    bool dcur_valid = false;
-    auto del_op = [&](u32 i) -> u32 {
-        if (!dcur_valid || i < dcur_i) { dcur_i = 0; dcur_op = o0; while (t.mo_xk[dcur_op] != XK_DEL) dcur_op++; dcur_valid = true; }
-        while (dcur_i < i) { dcur_op++; while (t.mo_xk[dcur_op] != XK_DEL) dcur_op++; dcur_i++; }
-        return dcur_op;
-    };
     auto w_delcol = [&](XSink& s, int col) {
-        dcur_valid = false;
         switch (col) {
-            case 0: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)t.mo_f0[del_op(i)]; }); break;
-            case 1: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)t.mo_f1[del_op(i)]; }); break;
-            default: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)t.mo_f2[del_op(i)]; });
+            case 0: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)d_peer[i]; }); break;
+            case 1: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_ctr[i]; }); break;
+            default: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_len[i]; });
         }
     };
     auto w_values = [&](XSink& s) {
-        for (u32 i = o0; i < o1; i++) {
-            u8 xk = t.mo_xk[i];
-            u32 st0 = t.mo_st0[i], nst = t.mo_nst[i];
-            if (xk == XK_LIST) {
-                s.put(7);
-                s.varint(t.mo_atoms[i]);
-                for (u32 q = 0; q < nst; q++) {
-                    u32 row = t.st_row[st0 + q];
-                    Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
-                    (void)c.get();
-                    (void)c.varint();
-                    s.copy(c.p, c.left());
+        u32 op = 0;
+        for (u32 j = 0; j < N; j++) {
+            XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
+            u32 left = t.fc_nrows[fc0 + j];
+            bool fresh = true;
+            while (left) {
+                u64 row = it.row();
+                bool head = fresh || (t.r_flag[row] & XF_HEAD);
+                fresh = false;
+                u8 vt = 0;
+                if (head) {
+                    vt = (u8)c_vt[op];
+                    if (vt == VK_LORO_VALUE && t.op_kind[row] == OPK_SEQ_INS) { s.put(7); s.varint(c_atoms[op]); }
+                    else if (vt == VK_STR) s.varint(c_bytes[op]);
+                    op++;
                 }
-            } else if (xk == XK_TEXT) {
-                s.varint(t.mo_f1[i] - t.mo_f0[i]);
-                for (u32 q = 0; q < nst; q++) {
-                    u32 row = t.st_row[st0 + q];
+                u8 kind = t.op_kind[row];
+                if (kind == OPK_SEQ_INS) {
                     Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
-                    (void)c.varint();
+                    if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) (void)c.varint();
+                    else { (void)c.get(); (void)c.varint(); }
                     s.copy(c.p, c.left());
-                }
-            } else if (xk == XK_MAPSET) {
-                u32 row = t.st_row[st0];
-                s.copy(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                } else if (kind == OPK_MAP_SET) s.copy(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                left--;
+                if (left) it.next();
             }
         }
     };
-
+    u32 counter_len = 0;
+    for (u32 j = 0; j < N; j++) counter_len += t.fc_atoms[fc0 + j];
+    u32 counter0 = (u32)t.ch_counter[first_src] + t.fc_from[fc0];
+    u32 lam0 = (u32)lamport(0);
+    u32 lam_len = (u32)lamport(N - 1) + t.fc_atoms[B.fc1 - 1] - lam0;
     if (pass == 0) {
         XSink s;
         s.dst = nullptr;
@@ -712,11 +841,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             B.sec_len[6] = tot;
         } else B.sec_len[6] = 0;
         s.n = 0; w_values(s); B.sec_len[7] = (u32)s.n;
-        u32 counter_len = 0;
-        for (u32 j = 0; j < N; j++) counter_len += t.mc_atoms[mc0 + j];
-        u32 lam0 = t.ch_lamport[first_src];
-        u32 lam_len = t.ch_lamport[last_src] + t.mc_atoms[B.mc1 - 1] - lam0;
-        u32 len = varint_len((u32)t.ch_counter[first_src]) + varint_len(counter_len) + varint_len(lam0) + varint_len(lam_len) + varint_len(N);
+        u32 len = varint_len(counter0) + varint_len(counter_len) + varint_len(lam0) + varint_len(lam_len) + varint_len(N);
         for (int i = 0; i < 8; i++) len += varint_len(B.sec_len[i]) + B.sec_len[i];
         B.len = len;
         xb[bi_] = B;
@@ -728,11 +853,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     s.dst = out + base - varint_len(B.len);
     s.n = 0;
     s.varint(B.len);
-    u32 counter_len = 0;
-    for (u32 j = 0; j < N; j++) counter_len += t.mc_atoms[mc0 + j];
-    u32 lam0 = t.ch_lamport[first_src];
-    u32 lam_len = t.ch_lamport[last_src] + t.mc_atoms[B.mc1 - 1] - lam0;
-    s.varint((u32)t.ch_counter[first_src]);
+    s.varint(counter0);
     s.varint(counter_len);
     s.varint(lam0);
     s.varint(lam_len);

@@ -145,7 +145,7 @@ def test_export_generator_documents_and_scale_round_trip():
     from loro_b200 import api
     from loro_b200.workload import C3Batch
     from tests.export_checks import check_export_against_oracle
-    gen = C3Batch(512, n_ops=4000, threads=8)
+    gen = C3Batch(512, n_ops=10000, threads=8)   # full-size documents: the 1,000-op prefix change gets split
     blobs = gen.blobs()
     check_export_against_oracle(blobs[:12], reimport=False)
     first = loro_b200.import_batch(blobs, flags=api.LB_FLAG_EXPORT)
@@ -155,6 +155,12 @@ def test_export_generator_documents_and_scale_round_trip():
     assert again.counters()["atom_ops"] == first.counters()["atom_ops"] == gen.atom_ops
     for i in range(0, len(blobs), 37):
         assert again.export_updates(i) == outs[i]
+
+
+def test_export_automerge_trace(golden_dir):
+    from tests.export_checks import check_export_against_oracle
+    blob = gzip.open(os.path.join(golden_dir, "automerge_trace_blob.bin.gz"), "rb").read()
+    check_export_against_oracle([blob])
 
 
 def test_export_unsupported_is_reported_not_guessed():

@@ -38,6 +38,16 @@ def test_export_generator_documents():
     check_export_against_oracle(gen.blobs(), lib_path=EMU)
 
 
+def test_export_split_changes_and_trace(golden_dir):
+    """Changes above MAX_BLOCK_SIZE enter the store in segments (split_change_then_insert): the 1,000-op prefix
+    change of full-size C3 documents, and the merged typing runs of the automerge trace."""
+    import gzip
+    from loro_b200.workload import C3Batch
+    blobs = C3Batch(2, n_ops=10000, threads=2).blobs()
+    blobs.append(gzip.open(os.path.join(golden_dir, "automerge_trace_blob.bin.gz"), "rb").read())
+    check_export_against_oracle(blobs, lib_path=EMU, reimport=False)
+
+
 def test_export_typing_runs_merge_across_changes():
     """Consecutive inserts / deletes in separate commits: stored changes merge (same timestamp is not required for
     ops inside one change; across changes can_merge_right needs ts_b <= ts_a) and op runs re-merge on export."""
