@@ -376,14 +376,14 @@ void pipeline(lb_batch* b) {
     stt.out_row = sp.out_row; stt.out_off = sp.out_off; stt.out_len = sp.out_len;
     unsigned long long* d_acc = dv.alloc<unsigned long long>(4, true);
     if (!(b->flags & LB_FLAG_NO_JSON)) {
-        LB_LAUNCH(k_json, nblk(D, 64), 64, 0, st, b->d_docs, D, stt, (u8*)nullptr, 0);
+        LB_LAUNCH(k_json, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, stt, (u8*)nullptr, 0);
         LB_LAUNCH(k_json_padlen, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a);
         tm.kernel_launches += 2;
         run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)b->d_docs + offsetof(DocInfo, json_off), 4, sizeof(DocInfo), D}});
         u64 JT = d2h_one(b, &b->d_docs[D].json_off);
         b->json_total = JT;
         b->d_json = dv.alloc<u8>(JT + 16, true);
-        LB_LAUNCH(k_json, nblk(D, 64), 64, 0, st, b->d_docs, D, stt, b->d_json, 1);
+        LB_LAUNCH(k_json, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, stt, b->d_json, 1);
         tm.kernel_launches += 1;
     }
     LB_LAUNCH(k_doc_hash, nblk(D), TPB, 0, st, b->d_docs, D, (const u8*)b->d_json, d_acc);
@@ -407,9 +407,13 @@ void pipeline(lb_batch* b) {
         xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
         xt.xdoc = dv.alloc<XDoc>(D + 1, true);
         b->d_xdoc = xt.xdoc;
-        LB_LAUNCH(k_exp_arena, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
+        xt.ch_aval = dv.alloc<u32>(NCH + 1, true); xt.ch_astr = dv.alloc<u32>(NCH + 1, true);
+        xt.ch_aval0 = dv.alloc<u64>(NCH + 2, true); xt.ch_astr0 = dv.alloc<u64>(NCH + 2, true);
+        LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
+        if (NCH) LB_LAUNCH(k_exp_arena, nblk(NCH, 64), 64, 0, st, NCH, xt, b->d_docs);
+        run_scans(b, {ScanJob{(const u8*)xt.ch_aval, (u8*)xt.ch_aval0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_astr, (u8*)xt.ch_astr0, 4, 8, NCH}});
         if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
-        tm.kernel_launches += 2;
+        tm.kernel_launches += 3;
         run_scans(b, {ScanJob{(const u8*)xt.ch_nseg, (u8*)xt.ch_seg0, 4, 8, NCH}});
         u64 NSEG = d2h_one(b, xt.ch_seg0 + NCH);
         xt.sg_src = dv.alloc<u32>(NSEG); xt.sg_r0 = dv.alloc<u32>(NSEG); xt.sg_from = dv.alloc<u32>(NSEG);

@@ -71,6 +71,7 @@ struct ExportTables {
     u8* r_flag;        // XF_*
     // per change
     u32* ch_nseg;      // segments the change enters the store as (0 = not applied)
+    u32* ch_aval; u32* ch_astr; u64* ch_aval0; u64* ch_astr0;   // arena sums per change + their scans
     u64* ch_seg0;      // scan of ch_nseg
     // per segment (index space: ch_seg0)
     u32* sg_src; u32* sg_r0; u32* sg_from; u32* sg_atoms; u32* sg_est; u32* sg_nmops; u32* sg_ndel; u32* sg_nrows; u32* sg_last_head;
@@ -195,36 +196,44 @@ __device__ inline XOp xop_from_row(const ExportTables& t, const DocInfo& di, u32
 }
 
 // ---------------------------------------------------------------------------------------------- X1: arenas
-// thread per document: arena positions of every row in decode order (the importing document allocates while it
-// decodes: block_encode.rs:619-657)
-__global__ void k_exp_arena(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t) {
+// The importing document allocates arena space while it decodes (block_encode.rs:619-657): the position of a row's
+// payload is the sum over the rows decoded before it.  Changes are numbered in decode order, so: per-change sums
+// (thread per change), one scan over the changes, and k_exp_changes hands out the row positions.
+__global__ void k_exp_init(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     const DocInfo& di = docs[d];
     XDoc x;
     memset(&x, 0, sizeof(x));
     if (di.code == DOC_OK) {
-        u32 vals = 0, strs = 0;
-        for (u64 r = di.op0; r < di.op0 + di.n_ops; r++) {
-            u8 k = t.op_kind[r];
-            if (k != OPK_SEQ_INS) continue;   // rows of pending changes are OPK_SKIP: such documents are not exported
-            const DocContainer& dc = t.dcont[di.cid0 + t.op_cidx[r]];
-            if (dc.type == CT_TEXT) {
-                Cur c(t.bytes + t.op_val_off[r], t.op_val_len[r]);
-                u32 n = (u32)c.varint();
-                t.r_astart[r] = strs;
-                t.r_bytes[r] = n;
-                strs += n;
-            } else {
-                t.r_astart[r] = vals;
-                vals += t.op_len[r];
-            }
-        }
         if ((di.has_unsupported & 0x7FFFFFFFu) || di.n_pending) x.flags |= 1;
         for (u32 b = di.b0; b < di.b1; b++)
             if (t.blocks[b].n_value_maps) x.flags |= 1;
     }
     t.xdoc[d] = x;
+}
+__global__ void k_exp_arena(u64 n_changes, ExportTables t, const DocInfo* __restrict__ docs) {
+    u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_changes) return;
+    const BlockInfo& sb = t.blocks[t.ch_block[ch]];
+    const DocInfo& di = docs[sb.doc];
+    u32 vals = 0, strs = 0;
+    if (di.code == DOC_OK) {
+        u64 r0 = t.ch_op0[ch];
+        u32 nr = t.ch_nops[ch];
+        for (u32 r = 0; r < nr; r++) {
+            u64 row = r0 + r;
+            if (t.op_kind[row] != OPK_SEQ_INS) continue;   // rows of pending changes are OPK_SKIP: not exported
+            if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) {
+                Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                u32 n = (u32)c.varint();
+                t.r_bytes[row] = n;
+                strs += n;
+            } else vals += t.op_len[row];
+        }
+    }
+    t.ch_aval[ch] = vals;
+    t.ch_astr[ch] = strs;
 }
 
 // ---------------------------------------------------------------------------------------------- A: per change
@@ -239,6 +248,15 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
     u64 r0 = t.ch_op0[ch];
     u32 nr = t.ch_nops[ch];
     if (pass == 0) {
+        {   // arena positions of the rows (relative to the document)
+            u32 vals = (u32)(t.ch_aval0[ch] - t.ch_aval0[di.ch0]), strs = (u32)(t.ch_astr0[ch] - t.ch_astr0[di.ch0]);
+            for (u32 r = 0; r < nr; r++) {
+                u64 row = r0 + r;
+                if (t.op_kind[row] != OPK_SEQ_INS) continue;
+                if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) { t.r_astart[row] = strs; strs += t.r_bytes[row]; }
+                else { t.r_astart[row] = vals; vals += t.op_len[row]; }
+            }
+        }
         // intra-change merge + total estimate
         XOp back;
         back.xk = XK_NONE;
@@ -343,11 +361,22 @@ struct XRows {
     }
 };
 // accumulate the merged op that starts at the cursor (consumes its rows, at most `left` of them)
-__device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows& it, u32& left) {
+// bytes one row contributes to the values section of a (merged) op, without the op's own prefix
+__device__ __forceinline__ u32 row_value_bytes(const ExportTables& t, const XOp& o, u64 row) {
+    switch (o.xk) {
+        case XK_LIST: return t.op_val_len[row] - 1 - varint_len(t.op_len[row]);   // minus `07` + item count
+        case XK_TEXT: return t.r_bytes[row];
+        case XK_MAPSET: return t.op_val_len[row];
+        default: return 0;
+    }
+}
+__device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows& it, u32& left, u32* vbytes = nullptr) {
     XOp o = xop_from_row(t, di, it.ch, it.row());
+    if (vbytes) *vbytes += row_value_bytes(t, o, it.row());
     left--;
     if (left) it.next();
     while (left && !(t.r_flag[it.row()] & XF_HEAD)) {
+        if (vbytes) *vbytes += row_value_bytes(t, o, it.row());
         xop_merge(o, xop_from_row(t, di, it.ch, it.row()));
         left--;
         if (left) it.next();
@@ -689,13 +718,15 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         peers.n = keys.n = cids.n = 0;
         peers.reg(t.peer_map[t.blocks[t.ch_block[first_src]].peer0]);   // the author of the block's changes
         // ops in order: containers, map keys, delete targets (block_encode.rs:180-236)
-        u32 n_ops = 0, n_del = 0;
+        u32 n_ops = 0, n_del = 0, vbytes = 0;
         for (u32 j = 0; j < N; j++) {
             XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
             u32 left = t.fc_nrows[fc0 + j];
             while (left) {
                 u32 first_row = (u32)it.row();
-                XOp o = xop_gather(t, di, it, left);
+                XOp o = xop_gather(t, di, it, left, &vbytes);
+                if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
+                else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
                 c_cidx[n_ops] = cids.reg(o.cidx);
                 c_prop[n_ops] = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
                 c_vt[n_ops] = xk_value_type(o.xk);
@@ -707,6 +738,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         }
         B.n_ops = n_ops;
         B.n_del_ops = n_del;
+        B.sec_len[7] = vbytes;   // values section: sizes come with the gather, no second walk
         // ContainerArena::from_containers (arena.rs:103-147): roots register their name, normals their peer
         for (u32 i = 0; i < cids.n; i++) {
             const DocContainer& dc = t.dcont[di.cid0 + cids.ord[i]];
@@ -840,7 +872,6 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             for (int c = 0; c < 3; c++) { s.n = 0; w_delcol(s, c); B.col_len[4 + c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
             B.sec_len[6] = tot;
         } else B.sec_len[6] = 0;
-        s.n = 0; w_values(s); B.sec_len[7] = (u32)s.n;
         u32 len = varint_len(counter0) + varint_len(counter_len) + varint_len(lam0) + varint_len(lam_len) + varint_len(N);
         for (int i = 0; i < 8; i++) len += varint_len(B.sec_len[i]) + B.sec_len[i];
         B.len = len;

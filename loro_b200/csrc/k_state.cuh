@@ -25,7 +25,8 @@ struct Sink {
     u8* dst;   // nullptr = counting pass
     u64 n;
     u32 flags; // bit0: value the emitter cannot print exactly (non-integral f64, nested map value)
-    __device__ __forceinline__ void put(u8 c) { if (dst) dst[n] = c; n++; }
+    bool wr;   // this lane writes (one warp per document: lane 0 owns the sequential parts)
+    __device__ __forceinline__ void put(u8 c) { if (dst && wr) dst[n] = c; n++; }
     __device__ __forceinline__ void puts_(const char* s) { while (*s) put((u8)*s++); }
     __device__ void put_u64(u64 v) {
         char tmp[24];
@@ -76,7 +77,8 @@ struct Emitter {
     Frame st[MAX_FRAMES];
     int sp;
     u32 err;
-    __device__ Emitter(const StateTables& t_, const DocInfo& di_, Sink& o) : t(t_), di(di_), out(o), sp(0), err(0) {}
+    int lane;
+    __device__ Emitter(const StateTables& t_, const DocInfo& di_, Sink& o, int lane_) : t(t_), di(di_), out(o), sp(0), err(0), lane(lane_) {}
 
     __device__ int cmp_bytes(const u8* a, u32 al, const u8* b, u32 bl) {
         u32 n = al < bl ? al : bl;
@@ -150,47 +152,59 @@ struct Emitter {
             default: out.puts_("null"); return;
         }
     }
-    // print the LoroValue at *pp (kind byte + content), advancing *pp; may push a frame
-    __device__ void emit_value(const u8** pp, const u8* end, u32 id_peer, i32 id_ctr) {
+    // print a scalar LoroValue (kinds 0-6) at *pp into `o`; false (nothing consumed) for lists, maps, containers
+    __device__ bool emit_scalar(Sink& o, const u8** pp, const u8* end) {
         Cur c(*pp, (size_t)(end - *pp));
         u8 kind = c.get();
         switch (kind) {
-            case 0: out.puts_("null"); break;
-            case 1: out.puts_("true"); break;
-            case 2: out.puts_("false"); break;
-            case 3: out.put_i64(c.sleb()); break;
+            case 0: o.puts_("null"); break;
+            case 1: o.puts_("true"); break;
+            case 2: o.puts_("false"); break;
+            case 3: o.put_i64(c.sleb()); break;
             case 4: {
                 u64 bits = 0;
                 for (int i = 0; i < 8; i++) bits = (bits << 8) | c.get();
                 double d = __longlong_as_double((long long)bits);
                 // exact only for integral values below 2^53 (serde_json prints "x.0"); flag the rest
                 if (d == d && d > -9.0e15 && d < 9.0e15 && (double)(i64)d == d && !(d == 0 && (bits >> 63))) {
-                    out.put_i64((i64)d);
-                    out.puts_(".0");
+                    o.put_i64((i64)d);
+                    o.puts_(".0");
                 } else {
-                    out.flags |= 1;
-                    out.puts_("null");
+                    o.flags |= 1;
+                    o.puts_("null");
                 }
                 break;
             }
             case 5: {
                 u64 n = c.varint();
-                out.put('"');
-                out.put_escaped(c.p, n <= c.left() ? n : c.left());
-                out.put('"');
+                o.put('"');
+                o.put_escaped(c.p, n <= c.left() ? n : c.left());
+                o.put('"');
                 c.skip(n);
                 break;
             }
             case 6: {
                 u64 n = c.varint();
-                out.put('[');
+                o.put('[');
                 for (u64 i = 0; i < n && !c.err; i++) {
-                    if (i) out.put(',');
-                    out.put_u64(c.get());
+                    if (i) o.put(',');
+                    o.put_u64(c.get());
                 }
-                out.put(']');
+                o.put(']');
                 break;
             }
+            default: return false;
+        }
+        if (c.err) err = LB_ERR(DOC_ERR_CORRUPT);
+        *pp = c.p;
+        return true;
+    }
+    // print the LoroValue at *pp (kind byte + content), advancing *pp; may push a frame
+    __device__ void emit_value(const u8** pp, const u8* end, u32 id_peer, i32 id_ctr) {
+        if (emit_scalar(out, pp, end)) return;
+        Cur c(*pp, (size_t)(end - *pp));
+        u8 kind = c.get();
+        switch (kind) {
             case 7: case 8: {
                 u64 n = c.varint();
                 out.put(kind == 7 ? '[' : '{');
@@ -234,6 +248,57 @@ struct Emitter {
         }
         *end = c.end;
         return c.p;
+    }
+
+    // ---- one warp per document: the runs of a scalar-only list are split over the lanes (sizes, scan, write)
+    __device__ bool coop_list(u32 cidx) {
+        const DocContainer& dc = t.dcont[di.cid0 + cidx];
+        u32 n_out = dc.n_out;
+        if (n_out < 64) return false;
+        u32 chunk = (n_out + 31) / 32;
+        u32 lo = (u32)lane * chunk, hi = lo + chunk < n_out ? lo + chunk : n_out;
+        if (lo > n_out) lo = n_out;
+        Sink cnt;
+        cnt.dst = nullptr; cnt.n = 0; cnt.flags = 0; cnt.wr = false;
+        bool complex_ = false;
+        u32 elems = 0;
+        u32 err0 = err;   // a lane-local decode error must not leave the lanes in different states
+        for (u32 r = lo; r < hi && !complex_; r++) {
+            u32 row = t.out_row[dc.out0 + r];
+            u32 off = t.out_off[dc.out0 + r], len = t.out_len[dc.out0 + r];
+            const u8* end;
+            const u8* p = list_elem_ptr(row, off, &end);
+            for (u32 e = 0; e < len; e++) {
+                if (!emit_scalar(cnt, &p, end)) { complex_ = true; break; }
+                elems++;
+            }
+        }
+        if (__any_sync(LB_FULL, complex_ || err != err0)) { err = err0; return false; }
+        u32 mine = (u32)cnt.n + elems - (lane == 0 ? 1u : 0u);   // a comma before every element but the first
+        u32 incl = (u32)warp_incl_scan((int)mine, lane);
+        u32 total = __shfl_sync(LB_FULL, incl, 31);
+        u32 flags_all = cnt.flags;
+        for (int d = 16; d > 0; d >>= 1) flags_all |= __shfl_xor_sync(LB_FULL, flags_all, d);
+        out.flags |= flags_all;
+        if (out.dst) {
+            Sink w;
+            w.dst = out.dst; w.n = out.n + (incl - mine); w.flags = 0; w.wr = true;
+            bool first = lane == 0;
+            for (u32 r = lo; r < hi; r++) {
+                u32 row = t.out_row[dc.out0 + r];
+                u32 off = t.out_off[dc.out0 + r], len = t.out_len[dc.out0 + r];
+                const u8* end;
+                const u8* p = list_elem_ptr(row, off, &end);
+                for (u32 e = 0; e < len; e++) {
+                    if (!first) w.put(',');
+                    first = false;
+                    emit_scalar(w, &p, end);
+                }
+            }
+        }
+        __syncwarp();
+        out.n += total;
+        return true;
     }
 
     __device__ void run(void) {
@@ -285,6 +350,7 @@ struct Emitter {
                 }
                 case FK_LIST: {
                     const DocContainer& dc = t.dcont[di.cid0 + f.a];
+                    if (f.first && f.b == 0 && f.c == 0 && coop_list(f.a)) { out.put(']'); sp--; break; }
                     if (f.b >= dc.n_out) { out.put(']'); sp--; break; }
                     u32 row = t.out_row[dc.out0 + f.b];
                     u32 off = t.out_off[dc.out0 + f.b], len = t.out_len[dc.out0 + f.b];
@@ -377,17 +443,20 @@ struct Emitter {
 
 // pass = 0: count bytes into docs[d].json_len ; pass = 1: write at docs[d].json_off
 __global__ void k_json(DocInfo* __restrict__ docs, u32 n_docs, StateTables t, u8* __restrict__ json, int pass) {
-    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per document
+    int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
     DocInfo& di = docs[d];
-    if (di.code != DOC_OK) { if (!pass) di.json_len = 0; return; }
+    if (di.code != DOC_OK) { if (!pass && lane == 0) di.json_len = 0; return; }
     Sink s;
     s.dst = pass ? json + di.json_off : nullptr;
     s.n = 0;
     s.flags = 0;
-    Emitter e(t, di, s);
+    s.wr = lane == 0;
+    Emitter e(t, di, s, lane);
     e.run();
-    if (!pass) {
+    __syncwarp();
+    if (!pass && lane == 0) {
         di.json_len = (u32)s.n;
         if (e.err) di.code = e.err;
         else if (s.flags & 1) di.has_unsupported |= 0x80000000u;
