@@ -97,32 +97,66 @@ struct Emitter {
         if (sp >= MAX_FRAMES) { err = LB_ERR(DOC_ERR_CAPACITY); return; }
         st[sp++] = f;
     }
-    // text of a Text container: concatenation of the visible runs
+    // bytes [*b0,*b1) of the payload of visible run r of a Text container (runs address unicode scalar values)
+    __device__ const u8* text_run(const DocContainer& dc, u32 r, u64* b0, u64* b1) {
+        u32 row = t.out_row[dc.out0 + r];
+        u32 off = t.out_off[dc.out0 + r], len = t.out_len[dc.out0 + r];
+        Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+        u64 blen = c.varint();
+        const u8* s = c.p;
+        *b0 = off;
+        *b1 = off + len;
+        if (blen != t.op_len[row]) {  // non-ASCII: map unicode offsets to byte offsets
+            u64 i = 0, ch = 0;
+            *b0 = blen;
+            *b1 = blen;
+            bool got0 = false;
+            while (i <= blen) {
+                if (ch == off && !got0) { *b0 = i; got0 = true; }
+                if (ch == off + len) { *b1 = i; break; }
+                if (i == blen) break;
+                i++;
+                while (i < blen && (s[i] & 0xC0) == 0x80) i++;
+                ch++;
+            }
+        }
+        return s;
+    }
+    // text of a Text container: concatenation of the visible runs; with many runs the lanes split them
     __device__ void emit_text(u32 cidx) {
         const DocContainer& dc = t.dcont[di.cid0 + cidx];
         out.put('"');
-        for (u32 r = 0; r < dc.n_out; r++) {
-            u32 row = t.out_row[dc.out0 + r];
-            u32 off = t.out_off[dc.out0 + r], len = t.out_len[dc.out0 + r];
-            Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
-            u64 blen = c.varint();
-            const u8* s = c.p;
-            u64 b0 = off, b1 = off + len;
-            if (blen != t.op_len[row]) {  // non-ASCII: map unicode offsets to byte offsets
-                u64 i = 0, ch = 0;
-                b0 = blen;
-                b1 = blen;
-                bool got0 = false;
-                while (i <= blen) {
-                    if (ch == off && !got0) { b0 = i; got0 = true; }
-                    if (ch == off + len) { b1 = i; break; }
-                    if (i == blen) break;
-                    i++;
-                    while (i < blen && (s[i] & 0xC0) == 0x80) i++;
-                    ch++;
+        if (dc.n_out >= 64) {
+            u32 chunk = (dc.n_out + 31) / 32;
+            u32 lo = (u32)lane * chunk, hi = lo + chunk < dc.n_out ? lo + chunk : dc.n_out;
+            if (lo > dc.n_out) lo = dc.n_out;
+            Sink cnt;
+            cnt.dst = nullptr; cnt.n = 0; cnt.flags = 0; cnt.wr = false;
+            for (u32 r = lo; r < hi; r++) {
+                u64 b0, b1;
+                const u8* s = text_run(dc, r, &b0, &b1);
+                cnt.put_escaped(s + b0, b1 - b0);
+            }
+            u32 mine = (u32)cnt.n;
+            u32 incl = (u32)warp_incl_scan((int)mine, lane);
+            u32 total = __shfl_sync(LB_FULL, incl, 31);
+            if (out.dst) {
+                Sink w;
+                w.dst = out.dst; w.n = out.n + (incl - mine); w.flags = 0; w.wr = true;
+                for (u32 r = lo; r < hi; r++) {
+                    u64 b0, b1;
+                    const u8* s = text_run(dc, r, &b0, &b1);
+                    w.put_escaped(s + b0, b1 - b0);
                 }
             }
-            out.put_escaped(s + b0, b1 - b0);
+            __syncwarp();
+            out.n += total;
+        } else {
+            for (u32 r = 0; r < dc.n_out; r++) {
+                u64 b0, b1;
+                const u8* s = text_run(dc, r, &b0, &b1);
+                out.put_escaped(s + b0, b1 - b0);
+            }
         }
         out.put('"');
     }
