@@ -88,7 +88,16 @@ struct XSink {
     __device__ __forceinline__ void varint(u64 v) { while (v >= 0x80) { put((u8)(v | 0x80)); v >>= 7; } put((u8)v); }
     __device__ __forceinline__ void zigzag(i64 v) { varint(((u64)v << 1) ^ (u64)(v >> 63)); }
     __device__ __forceinline__ void copy(const u8* s, u64 len) {
-        if (dst) for (u64 i = 0; i < len; i++) dst[n + i] = s[i];
+        if (dst) {
+            u8* d = dst + n;
+            u64 i = 0;
+            while (i < len && ((uintptr_t)(d + i) & 3)) { d[i] = s[i]; i++; }
+            for (; i + 4 <= len; i += 4) {   // 4 independent byte loads, one aligned word store
+                u32 w = (u32)s[i] | ((u32)s[i + 1] << 8) | ((u32)s[i + 2] << 16) | ((u32)s[i + 3] << 24);
+                *(u32*)(d + i) = w;
+            }
+            for (; i < len; i++) d[i] = s[i];
+        }
         n += len;
     }
 };
@@ -719,6 +728,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         peers.reg(t.peer_map[t.blocks[t.ch_block[first_src]].peer0]);   // the author of the block's changes
         // ops in order: containers, map keys, delete targets (block_encode.rs:180-236)
         u32 n_ops = 0, n_del = 0, vbytes = 0;
+        u32 prev_cidx = 0, prev_prop = 0, prev_dp = 0, prev_dc = 0, prev_dl = 0;   // 32-bit wrap-around deltas
         for (u32 j = 0; j < N; j++) {
             XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
             u32 left = t.fc_nrows[fc0 + j];
@@ -727,12 +737,21 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                 XOp o = xop_gather(t, di, it, left, &vbytes);
                 if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
                 else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
-                c_cidx[n_ops] = cids.reg(o.cidx);
-                c_prop[n_ops] = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
-                c_vt[n_ops] = xk_value_type(o.xk);
+                // DeltaRle columns are stored as deltas right away (the encoders then read every value once)
+                u32 lc = cids.reg(o.cidx);
+                u32 lp = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
+                c_cidx[n_ops] = lc - prev_cidx; prev_cidx = lc;
+                c_prop[n_ops] = lp - prev_prop; prev_prop = lp;
+                c_vt[n_ops] = xk_value_type(o.xk) | ((u32)o.xk << 8);
                 c_atoms[n_ops] = o.atoms;
                 c_bytes[n_ops] = o.xk == XK_TEXT ? o.f1 - o.f0 : first_row;
-                if (o.xk == XK_DEL) { d_peer[n_del] = peers.reg(o.f0); d_ctr[n_del] = o.f1; d_len[n_del] = (u32)o.f2; n_del++; }
+                if (o.xk == XK_DEL) {
+                    u32 dp = peers.reg(o.f0);
+                    d_peer[n_del] = dp - prev_dp; prev_dp = dp;
+                    d_ctr[n_del] = o.f1 - prev_dc; prev_dc = o.f1;
+                    d_len[n_del] = (u32)o.f2 - prev_dl; prev_dl = (u32)o.f2;
+                    n_del++;
+                }
                 n_ops++;
             }
         }
@@ -807,45 +826,44 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             s.copy(t.bytes + t.dkey_off[di.key0 + k], t.dkey_len[di.key0 + k]);
         }
     };
+    // stored deltas are 32-bit differences of i32 / small u32 values: sign-extend to the true delta
     auto w_opcol = [&](XSink& s, int col) {
         switch (col) {
-            case 0: enc_deltarle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_cidx[i]; }); break;
-            case 1: enc_deltarle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_prop[i]; }); break;
-            case 2: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_vt[i]; }, WrByte()); break;
+            case 0: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_cidx[i]; }, WrZigzag()); break;
+            case 1: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_prop[i]; }, WrZigzag()); break;
+            case 2: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(c_vt[i] & 0xFFu); }, WrByte()); break;
             default: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_atoms[i]; }, WrVarint());
         }
     };
     auto w_delcol = [&](XSink& s, int col) {
         switch (col) {
-            case 0: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)d_peer[i]; }); break;
-            case 1: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_ctr[i]; }); break;
-            default: enc_deltarle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_len[i]; });
+            case 0: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_peer[i]; }, WrZigzag()); break;
+            case 1: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_ctr[i]; }, WrZigzag()); break;
+            default: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_len[i]; }, WrZigzag());
         }
     };
     auto w_values = [&](XSink& s) {
         u32 op = 0;
+        u32 xk = XK_NONE;
         for (u32 j = 0; j < N; j++) {
             XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
             u32 left = t.fc_nrows[fc0 + j];
             bool fresh = true;
             while (left) {
                 u64 row = it.row();
-                bool head = fresh || (t.r_flag[row] & XF_HEAD);
-                fresh = false;
-                u8 vt = 0;
-                if (head) {
-                    vt = (u8)c_vt[op];
-                    if (vt == VK_LORO_VALUE && t.op_kind[row] == OPK_SEQ_INS) { s.put(7); s.varint(c_atoms[op]); }
-                    else if (vt == VK_STR) s.varint(c_bytes[op]);
+                if (fresh || (t.r_flag[row] & XF_HEAD)) {
+                    xk = c_vt[op] >> 8;
+                    if (xk == XK_LIST) { s.put(7); s.varint(c_atoms[op]); }
+                    else if (xk == XK_TEXT) s.varint(c_bytes[op]);
                     op++;
                 }
-                u8 kind = t.op_kind[row];
-                if (kind == OPK_SEQ_INS) {
+                fresh = false;
+                if (xk == XK_LIST || xk == XK_TEXT) {
                     Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
-                    if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) (void)c.varint();
+                    if (xk == XK_TEXT) (void)c.varint();
                     else { (void)c.get(); (void)c.varint(); }
                     s.copy(c.p, c.left());
-                } else if (kind == OPK_MAP_SET) s.copy(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                } else if (xk == XK_MAPSET) s.copy(t.bytes + t.op_val_off[row], t.op_val_len[row]);
                 left--;
                 if (left) it.next();
             }
