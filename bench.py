@@ -79,13 +79,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def begin_region(self):
+        """nvidia-smi needs about a second before its first line: the sampler starts before the warm-up steps and
+        only what arrives after this call (= during the timed region) is reported."""
+        self.region0 = len(self.samples)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        region = self.samples[getattr(self, "region0", 0):]
+        note = None
+        if not region and self.samples:   # timed region shorter than one sampling period: closest samples instead
+            region = self.samples[-2:]
+            note = "no sample fell inside the timed region; last warm-up samples reported"
+        for s in region:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -96,8 +106,11 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def default_docs(args, world):
@@ -240,16 +253,18 @@ def main():
         b.close()
         return c, tm
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         c, tm = step()
     assert c["docs_ok"] == n_docs, c
     atoms_per_step = c["atom_ops"]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if rank == 0:
+        sampler.begin_region()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t_wall = time.time()
