@@ -6,6 +6,7 @@
 #include "../../include/loro_b200.h"
 
 #include <string>
+#include <thread>
 #include <vector>
 #include <cstring>
 #include <cstdio>
@@ -158,8 +159,14 @@ struct lb_batch {
     // host results
     std::vector<DocInfo> docs;
     std::vector<DocPeer> dpeer;
-    char* json = nullptr;   // malloc'ed (never zero-filled): filled by lbstage::download
+    char* json = nullptr;   // from lbstage::host_cache (never zero-filled): filled by lbstage::download
     bool json_fetched = false;
+    // host-buffer entry point: the JSON goes home on a second stream while the export phase still computes
+    bool eager_json = false, json_ok = true;
+    int device = 0;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t json_ev = nullptr;
+    std::thread json_thread;
     std::vector<std::vector<lb_id_span>> success, pending, vv;
     std::vector<uint64_t> doc_ids;
     lb_counters counters{};
@@ -389,6 +396,19 @@ void pipeline(lb_batch* b) {
     LB_LAUNCH(k_doc_hash, nblk(D), TPB, 0, st, b->d_docs, D, (const u8*)b->d_json, d_acc);
     tm.kernel_launches += 1;
     mark(b);  // [6] materialise done
+    if (b->eager_json && b->json_total && !(b->flags & LB_FLAG_NO_JSON)) {
+        CK(cudaStreamCreate(&b->stream2));
+        CK(cudaEventCreate(&b->json_ev));
+        CK(cudaEventRecord(b->json_ev, st));
+        b->json = (char*)lbstage::host_cache().take(b->json_total + 1);
+        if (!b->json) { g_last_error = "out of host memory"; throw lb_status(LB_ERR_OOM); }
+        b->json_thread = std::thread([b] {
+            bool ok = cudaSetDevice(b->device) == cudaSuccess && cudaStreamWaitEvent(b->stream2, b->json_ev, 0) == cudaSuccess &&
+                      lbstage::download(b->d_json, (u8*)b->json, b->json_total, b->stream2);
+            b->json[b->json_total] = 0;
+            b->json_ok = ok;
+        });
+    }
     // ------------------------------------------------------------ phase 7: re-export (all_updates per document)
     if (b->flags & LB_FLAG_EXPORT) {
         ExportTables xt;
@@ -569,6 +589,8 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
     lb_batch* b = new lb_batch();
     b->n_docs = n_blobs;
     b->flags = opt ? opt->flags : 0;
+    b->device = opt ? opt->device : 0;
+    b->eager_json = true;   // host buffers in, host results expected
     try {
         init_batch(b);
         std::vector<u64> offs(n_blobs + 1);
@@ -674,8 +696,13 @@ lb_status lb_doc_json(const lb_batch* cb, size_t doc, const char** utf8, size_t*
     lb_batch* b = const_cast<lb_batch*>(cb);
     if (!b || !utf8 || !len || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
     if (b->flags & LB_FLAG_NO_JSON) { g_last_error = "batch was imported with LB_FLAG_NO_JSON"; return LB_ERR_INVALID_ARG; }
+    if (b->json_thread.joinable()) {
+        b->json_thread.join();
+        if (!b->json_ok) { g_last_error = "json d2h failed"; return LB_ERR_CUDA; }
+        b->json_fetched = true;
+    }
     if (!b->json_fetched) {
-        b->json = (char*)malloc(b->json_total + 1);
+        b->json = (char*)lbstage::host_cache().take(b->json_total + 1);
         if (!b->json) { g_last_error = "out of host memory"; return LB_ERR_OOM; }
         if (b->json_total && !lbstage::download(b->d_json, (u8*)b->json, b->json_total, b->dev.stream)) {
             g_last_error = "json d2h failed";
@@ -701,7 +728,7 @@ lb_status lb_doc_export_updates(const lb_batch* cb, size_t doc, const lb_id_span
     const XDoc& x = b->xdocs[doc];
     if ((x.flags & 1) || x.exp_len == 0) { g_last_error = "document uses features the export phase does not cover"; return LB_ERR_UNSUPPORTED; }
     if (!b->export_fetched) {
-        b->exported = (uint8_t*)malloc(b->export_total + 1);
+        b->exported = (uint8_t*)lbstage::host_cache().take(b->export_total + 1);
         if (!b->exported) { g_last_error = "out of host memory"; return LB_ERR_OOM; }
         if (b->export_total && !lbstage::download(b->d_export, b->exported, b->export_total, b->dev.stream)) {
             g_last_error = "export d2h failed";
@@ -751,6 +778,9 @@ lb_status lb_debug_table(const lb_batch* b, const char* name, void* dst, size_t 
 
 void lb_batch_free(lb_batch* b) {
     if (!b) return;
+    if (b->json_thread.joinable()) b->json_thread.join();
+    if (b->json_ev) cudaEventDestroy(b->json_ev);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->dev.stream) {
         b->dev.free_all();
         cudaStreamSynchronize(b->dev.stream);
@@ -758,8 +788,8 @@ void lb_batch_free(lb_batch* b) {
             for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
         cudaStreamDestroy(b->dev.stream);
     }
-    free(b->json);
-    free(b->exported);
+    lbstage::host_cache().give(b->json);
+    lbstage::host_cache().give(b->exported);
     delete b;
 }
 

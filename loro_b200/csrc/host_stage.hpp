@@ -51,7 +51,53 @@ inline size_t slot_bytes() {
 
 inline unsigned n_workers() {
     unsigned hc = std::thread::hardware_concurrency();
-    return std::max(1u, std::min(8u, hc ? hc : 1u));
+    return std::max(1u, std::min(16u, hc ? hc : 1u));
+}
+
+// Result buffers (JSON, exported blobs) are GBs of pageable memory: a fresh malloc of that size is page-faulted
+// in on first touch every time.  Freed result buffers are kept (a few, size-matched) for the next batch.
+struct HostCache {
+    struct Hdr { size_t cap; size_t pad; };
+    std::mutex mu;
+    std::vector<void*> free_;
+    void* take(size_t n) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (size_t i = 0; i < free_.size(); i++) {
+                size_t cap = ((Hdr*)free_[i])->cap;
+                if (cap >= n && cap <= 2 * n + (1u << 20) && (best < 0 || cap < ((Hdr*)free_[best])->cap)) best = (int)i;
+            }
+            if (best >= 0) {
+                void* h = free_[best];
+                free_[best] = free_.back();
+                free_.pop_back();
+                return (char*)h + sizeof(Hdr);
+            }
+        }
+        Hdr* h = (Hdr*)malloc(n + sizeof(Hdr));
+        if (!h) return nullptr;
+        h->cap = n;
+        return (char*)h + sizeof(Hdr);
+    }
+    void give(void* p) {
+        if (!p) return;
+        Hdr* h = (Hdr*)((char*)p - sizeof(Hdr));
+        std::lock_guard<std::mutex> g(mu);
+        free_.push_back(h);
+        while (free_.size() > 4) {   // drop the smallest
+            size_t k = 0;
+            for (size_t i = 1; i < free_.size(); i++)
+                if (((Hdr*)free_[i])->cap < ((Hdr*)free_[k])->cap) k = i;
+            free(free_[k]);
+            free_[k] = free_.back();
+            free_.pop_back();
+        }
+    }
+};
+inline HostCache& host_cache() {
+    static HostCache c;
+    return c;
 }
 
 template <class F>
