@@ -49,16 +49,29 @@ enum { OPK_SKIP = 0, OPK_SEQ_INS = 1, OPK_SEQ_DEL = 2, OPK_MAP_SET = 3, OPK_MAP_
 #define UNKNOWN_LEN 0x3FFFFFFF  // u32::MAX / 4
 
 // ------------------------------------------------------------------ byte cursor (bounds checked)
+// Bytes are fetched eight at a time (one aligned 64-bit load per 8-byte window, validated by address so that code
+// moving `p` directly stays correct): the decoders are bound by the latency of their byte loads, not by bandwidth.
+// The batch byte buffer is padded, so the aligned window around any in-range byte is readable.
 struct Cur {
     const u8* p;
     const u8* end;
     u32 err;
-    __device__ __forceinline__ Cur(const u8* b, size_t n) : p(b), end(b + n), err(0) {}
+    u64 buf;
+    const u8* bp;   // address of the window held in buf (8-byte aligned), nullptr = none
+    __device__ __forceinline__ Cur(const u8* b, size_t n) : p(b), end(b + n), err(0), buf(0), bp(nullptr) {}
     __device__ __forceinline__ size_t left() const { return (size_t)(end - p); }
     __device__ __forceinline__ bool empty() const { return p >= end; }
     __device__ __forceinline__ u8 get() {
         if (p >= end) { err = 1; return 0; }
+#ifdef LB_CUR_UNBUFFERED
         return *p++;
+#else
+        const u8* a = (const u8*)((uintptr_t)p & ~(uintptr_t)7);
+        if (a != bp) { buf = *(const u64*)a; bp = a; }
+        u8 v = (u8)(buf >> (8 * (unsigned)((uintptr_t)p & 7)));
+        p++;
+        return v;
+#endif
     }
     __device__ __forceinline__ void skip(u64 n) {
         if (n > (u64)(end - p)) { err = 1; p = end; } else p += n;

@@ -96,6 +96,19 @@ def test_longer_concurrent_branches():
     check_batch_against_oracle([blob], lib_path=EMU, expect_json=[js])
 
 
+def test_more_than_32_peers():
+    """40 concurrent sites: peers beyond the 32 whose atom bases / tracker versions are cached in shared memory
+    take the global-memory paths of the integration kernel (C4 shape at test size)."""
+    from tests.export_checks import check_export_against_oracle
+    blobs, js = [], []
+    for i in range(3):
+        blob, j, _, _ = workloads.make_doc_history(4200 + i, n_sites=40, n_ops=900, sync_prob=0.04)
+        blobs.append(blob)
+        js.append(j)
+    check_batch_against_oracle(blobs, expect_json=js, lib_path=EMU)
+    check_export_against_oracle(blobs, lib_path=EMU)
+
+
 def test_automerge_trace_end_content(golden_dir):
     """C2 shape on one document (259,778 patches): exercises multi-level trees and node spill past the
     shared-memory cache."""

@@ -88,6 +88,18 @@ def test_long_concurrent_branches():
     check_batch_against_oracle(blobs, expect_json=jsons)
 
 
+def test_more_than_32_peers_c4_shape():
+    """Many concurrent sites on few documents (C4 shape at test size): peers >= 32 use the global-memory paths."""
+    from tests.export_checks import check_export_against_oracle
+    blobs, js = [], []
+    for i in range(6):
+        blob, j, _, _ = workloads.make_doc_history(4200 + i, n_sites=40 + 8 * (i % 3), n_ops=1500, sync_prob=0.04)
+        blobs.append(blob)
+        js.append(j)
+    check_batch_against_oracle(blobs, expect_json=js)
+    check_export_against_oracle(blobs)
+
+
 def test_automerge_trace_end_content(golden_dir):
     """BASELINE config C2 shape at small replication: the automerge-paper editing trace (259,778 patches,
     crates/loro-internal/benches/text_r.rs) must materialise to its recorded endContent."""
