@@ -56,7 +56,8 @@ typedef enum lb_doc_code {
 typedef struct lb_blob {
     const uint8_t* ptr; /* host pointer, borrowed */
     size_t len;
-    uint64_t doc_id;    /* caller's label; one blob per document in this version */
+    uint64_t doc_id;    /* blobs with the same doc_id are imported into ONE document (LoroDoc::import_batch,
+                           crates/loro/src/lib.rs:425); documents are numbered by first appearance */
 } lb_blob;
 
 typedef struct lb_options {

@@ -192,8 +192,10 @@ class Batch:
         return arr
 
 
-def import_batch(blobs, device=0, flags=0, lib_path=None):
-    """LoroDoc::import for a batch: one fresh document per blob (bytes-like), host buffers in."""
+def import_batch(blobs, device=0, flags=0, lib_path=None, doc_ids=None):
+    """LoroDoc::import for a batch: one fresh document per blob (bytes-like), host buffers in.
+    `doc_ids` (one int per blob) groups blobs into documents the way LoroDoc::import_batch takes several updates:
+    blobs with the same id form one document; documents are numbered in order of first appearance."""
     L = load_library(lib_path)
     n = len(blobs)
     arr = (_Blob * max(n, 1))()
@@ -203,7 +205,7 @@ def import_batch(blobs, device=0, flags=0, lib_path=None):
         keep.append(b)
         arr[i].ptr = b
         arr[i].len = len(b)
-        arr[i].doc_id = i
+        arr[i].doc_id = i if doc_ids is None else int(doc_ids[i])
     opt = _Options(device=device, flags=flags)
     h = ctypes.c_void_p()
     _check(L, L.lb_import_batch(arr, n, ctypes.byref(opt), ctypes.byref(h)), "lb_import_batch")

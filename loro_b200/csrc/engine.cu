@@ -7,6 +7,7 @@
 
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include <cstring>
 #include <cstdio>
@@ -144,6 +145,8 @@ struct lb_batch {
     const u8* d_bytes = nullptr;
     u64* d_offs = nullptr;
     u32* d_lens = nullptr;
+    size_t n_blobs = 0;                       // blobs in the byte buffer (>= n_docs: import_batch groups)
+    std::vector<u32> blob_doc, doc_blob0;     // blob -> document ; document -> first blob (n_docs + 1)
     DocInfo* d_docs = nullptr;
     BlockInfo* d_blocks = nullptr;
     DocPeer* d_dpeer = nullptr;
@@ -218,16 +221,23 @@ void pipeline(lb_batch* b) {
         return;
     }
     // ------------------------------------------------------------ phase 1: frame
+    u32 Q = (u32)b->n_blobs;
     b->d_docs = dv.alloc<DocInfo>(D + 1, true);
-    u32* d_nblocks = dv.alloc<u32>(D + 1, true);
-    u64* d_block0 = dv.alloc<u64>(D + 2, true);
-    LB_LAUNCH(k_frame_count, nblk(D), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, D, b->d_docs, d_nblocks);
-    run_scans(b, {ScanJob{(const u8*)d_nblocks, (u8*)d_block0, 4, 8, D}});
-    tm.kernel_launches += 1;
-    u64 B = d2h_one(b, d_block0 + D);
+    u32* d_blob_code = dv.alloc<u32>(Q + 1, true);
+    u32* d_blob_nblocks = dv.alloc<u32>(Q + 1, true);
+    u64* d_blob_block0 = dv.alloc<u64>(Q + 2, true);
+    u32* d_blob_doc = dv.alloc<u32>(Q + 1);
+    u32* d_doc_blob0 = dv.alloc<u32>(D + 2);
+    CK(cudaMemcpyAsync(d_blob_doc, b->blob_doc.data(), sizeof(u32) * Q, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_doc_blob0, b->doc_blob0.data(), sizeof(u32) * (D + 1), cudaMemcpyHostToDevice, st));
+    LB_LAUNCH(k_frame_count, nblk(Q), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_code, d_blob_nblocks);
+    run_scans(b, {ScanJob{(const u8*)d_blob_nblocks, (u8*)d_blob_block0, 4, 8, Q}});
+    LB_LAUNCH(k_frame_docs, nblk(D), TPB, 0, st, D, d_doc_blob0, d_blob_code, d_blob_block0, b->d_docs);
+    tm.kernel_launches += 2;
+    u64 B = d2h_one(b, d_blob_block0 + Q);
     b->n_blocks = B;
     b->d_blocks = dv.alloc<BlockInfo>(B + 1, true);
-    LB_LAUNCH(k_frame_fill, nblk(D), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, D, b->d_docs, d_block0, b->d_blocks);
+    LB_LAUNCH(k_frame_fill, nblk(Q), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_doc, d_blob_code, d_blob_block0, b->d_blocks);
     tm.kernel_launches += 1;
     mark(b);  // [1] frame done
     // ------------------------------------------------------------ phase 2: decode
@@ -593,24 +603,53 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
     b->eager_json = true;   // host buffers in, host results expected
     try {
         init_batch(b);
+        // blobs with the same doc_id form one document (LoroDoc::import_batch); documents are numbered in order of
+        // first appearance and their blobs laid out consecutively, in the order given
+        std::vector<u32> order(n_blobs);
+        {
+            std::unordered_map<u64, u32> doc_of;
+            std::vector<u32> doc_idx(n_blobs), count;
+            for (size_t i = 0; i < n_blobs; i++) {
+                auto it = doc_of.find(blobs[i].doc_id);
+                if (it == doc_of.end()) {
+                    it = doc_of.emplace(blobs[i].doc_id, (u32)count.size()).first;
+                    count.push_back(0);
+                    b->doc_ids.push_back(blobs[i].doc_id);
+                }
+                doc_idx[i] = it->second;
+                count[it->second]++;
+            }
+            size_t nd = count.size();
+            b->n_docs = nd;
+            b->doc_blob0.assign(nd + 1, 0);
+            for (size_t d = 0; d < nd; d++) b->doc_blob0[d + 1] = b->doc_blob0[d] + count[d];
+            std::vector<u32> cursor(b->doc_blob0.begin(), b->doc_blob0.end() - 1);
+            b->blob_doc.resize(n_blobs);
+            for (size_t i = 0; i < n_blobs; i++) {
+                u32 q = cursor[doc_idx[i]]++;
+                order[q] = (u32)i;
+                b->blob_doc[q] = doc_idx[i];
+            }
+        }
+        b->n_blobs = n_blobs;
         std::vector<u64> offs(n_blobs + 1);
         std::vector<u32> lens(n_blobs + 1, 0);
         u64 total = 0;
-        for (size_t i = 0; i < n_blobs; i++) {
-            if (blobs[i].len > 0xFFFFFFF0ull || (!blobs[i].ptr && blobs[i].len)) {
+        for (size_t q = 0; q < n_blobs; q++) {
+            const lb_blob& bl = blobs[order[q]];
+            if (bl.len > 0xFFFFFFF0ull || (!bl.ptr && bl.len)) {
                 g_last_error = "blob too large or null";
                 throw lb_status(LB_ERR_INVALID_ARG);
             }
-            offs[i] = total;
-            lens[i] = (u32)blobs[i].len;
-            total += (blobs[i].len + 15) & ~(u64)15;
-            b->doc_ids.push_back(blobs[i].doc_id);
-            b->counters.blob_bytes += blobs[i].len;
+            offs[q] = total;
+            lens[q] = (u32)bl.len;
+            total += (bl.len + 15) & ~(u64)15;
+            b->counters.blob_bytes += bl.len;
         }
         offs[n_blobs] = total;
         // stage through the pinned ring: host gather of slot k overlaps the DMA of slot k-1 (host_stage.hpp)
         std::vector<lbstage::BlobView> views(n_blobs);
-        for (size_t i = 0; i < n_blobs; i++) views[i] = lbstage::BlobView{blobs[i].ptr, blobs[i].len};
+        for (size_t q = 0; q < n_blobs; q++) views[q] = lbstage::BlobView{blobs[order[q]].ptr, blobs[order[q]].len};
         CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
         u8* d_bytes = b->dev.alloc<u8>(total + 64);
         b->d_offs = b->dev.alloc<u64>(n_blobs + 1);
@@ -653,9 +692,13 @@ lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets
             offs[i] = offsets[i];
             lens[i] = blob_lens[i];
             b->doc_ids.push_back(i);
+            b->blob_doc.push_back((u32)i);
+            b->doc_blob0.push_back((u32)i);
             b->counters.blob_bytes += lens[i];
         }
         offs[n_docs] = n_docs ? offsets[n_docs - 1] + lens[n_docs - 1] : 0;
+        b->doc_blob0.push_back((u32)n_docs);
+        b->n_blobs = n_docs;
         CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
         b->d_offs = b->dev.alloc<u64>(n_docs + 1);
         b->d_lens = b->dev.alloc<u32>(n_docs + 1);

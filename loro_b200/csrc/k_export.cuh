@@ -215,7 +215,7 @@ __global__ void k_exp_init(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
     XDoc x;
     memset(&x, 0, sizeof(x));
     if (di.code == DOC_OK) {
-        if ((di.has_unsupported & 0x7FFFFFFFu) || di.n_pending) x.flags |= 1;
+        if ((di.has_unsupported & 0x7FFFFFFFu) || di.n_pending || di.n_blobs > 1) x.flags |= 1;   // import_batch sorts its blobs: arena order differs
         for (u32 b = di.b0; b < di.b1; b++)
             if (t.blocks[b].n_value_maps) x.flags |= 1;
     }

@@ -63,12 +63,12 @@ __device__ u32 xxh32_dev(const u8* d, size_t len, u32 seed) {
 
 // thread per blob: validate header + checksum, count blocks.
 __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restrict__ offs,
-                              const u32* __restrict__ lens, u32 n_docs, DocInfo* __restrict__ docs,
-                              u32* __restrict__ doc_nblocks) {
-    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_docs) return;
-    const u8* b = bytes + offs[d];   // blob starts are 16-byte aligned
-    size_t n = lens[d];
+                              const u32* __restrict__ lens, u32 n_blobs, u32* __restrict__ blob_code,
+                              u32* __restrict__ blob_nblocks) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_blobs) return;
+    const u8* b = bytes + offs[q];   // blob starts are 16-byte aligned
+    size_t n = lens[q];
     u32 code = DOC_OK;
     u32 nb = 0;
     if (n < 22) code = LB_ERR(DOC_ERR_DECODE);
@@ -91,30 +91,44 @@ __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restric
             }
         }
     }
+    blob_code[q] = code;
+    blob_nblocks[q] = code == DOC_OK ? nb : 0;
+}
+
+// thread per document: a document is a run of consecutive blobs (LoroDoc::import_batch: loro.rs:1183-1290); the
+// first blob that fails decides the document's code (header, checksum and mode are checked before any state
+// change: loro.rs:584)
+__global__ void k_frame_docs(u32 n_docs, const u32* __restrict__ doc_blob0, const u32* __restrict__ blob_code,
+                             const u64* __restrict__ blob_block0, DocInfo* __restrict__ docs) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    u32 q0 = doc_blob0[d], q1 = doc_blob0[d + 1];
+    u32 code = DOC_OK;
+    for (u32 q = q0; q < q1 && code == DOC_OK; q++) code = blob_code[q];
     docs[d].code = code;
-    doc_nblocks[d] = nb;
+    docs[d].b0 = (u32)blob_block0[q0];
+    docs[d].b1 = (u32)blob_block0[q1];
+    docs[d].n_blobs = q1 - q0;
 }
 
 // thread per blob: emit block descriptors at the scanned positions.
 __global__ void k_frame_fill(const u8* __restrict__ bytes, const u64* __restrict__ offs,
-                             const u32* __restrict__ lens, u32 n_docs, DocInfo* __restrict__ docs,
-                             const u64* __restrict__ doc_block0, BlockInfo* __restrict__ blocks) {
-    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_docs) return;
-    u64 b0 = doc_block0[d];
-    docs[d].b0 = (u32)b0;
-    docs[d].b1 = (u32)doc_block0[d + 1];
-    if (docs[d].code != DOC_OK) return;
-    const u8* b = bytes + offs[d];
-    size_t n = lens[d];
+                             const u32* __restrict__ lens, u32 n_blobs, const u32* __restrict__ blob_doc,
+                             const u32* __restrict__ blob_code, const u64* __restrict__ blob_block0,
+                             BlockInfo* __restrict__ blocks) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_blobs) return;
+    if (blob_code[q] != DOC_OK) return;
+    const u8* b = bytes + offs[q];
+    size_t n = lens[q];
     Cur c(b + 22, n - 22);
-    u64 i = b0;
+    u64 i = blob_block0[q];
     while (!c.empty()) {
         u64 len = c.varint();
         BlockInfo& bi = blocks[i++];
-        bi.doc = d;
+        bi.doc = blob_doc[q];
         bi.err = 0;
-        bi.off = offs[d] + (u64)(c.p - b);
+        bi.off = offs[q] + (u64)(c.p - b);
         bi.len = (u32)len;
         c.skip(len);
     }

@@ -193,6 +193,19 @@ __global__ void k_doc_tables(const u8* __restrict__ bytes, DocInfo* __restrict__
         }
         t.dpeer[di.peer0 + p].ch_count += bi.n_changes;
     }
+    // blocks of one blob never overlap, blocks of several blobs (import_batch) may: keep every peer's list ordered
+    // by counter (stable, so a re-delivered change follows the first copy)
+    for (u32 p = 0; p < P; p++) {
+        const DocPeer& dp = t.dpeer[di.peer0 + p];
+        u32* lst = t.ch_order + di.ch0 + dp.ch_first;
+        for (u32 i = 1; i < dp.ch_count; i++) {
+            u32 c = lst[i];
+            i32 cc = t.ch_counter[c];
+            u32 j = i;
+            while (j > 0 && t.ch_counter[lst[j - 1]] > cc) { lst[j] = lst[j - 1]; j--; }
+            lst[j] = c;
+        }
+    }
     docs[d] = di;
 }
 
@@ -208,6 +221,9 @@ __device__ inline bool lamport_of(const DocInfo& di, const ResolveTables& t, u32
         if (t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + mid]] <= c) lo = mid;
         else hi = mid;
     }
+    // duplicates (the same change delivered twice inside an import_batch) sort next to each other: the first one
+    // is the one that was applied
+    while (lo > 0 && t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + lo - 1]] == t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + lo]]) lo--;
     u32 ch = t.ch_order[di.ch0 + dp.ch_first + lo];
     *out = t.ch_lamport[ch] + (u32)(c - t.ch_counter[ch]);
     *ch_out = ch;
@@ -286,16 +302,9 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
             i32 dc;
             if (k == t.ch_ndeps[ch]) { dpi = pick; dc = ctr - 1; }
             else { dpi = t.peer_map[bi.peer0 + t.dep_peer_idx[t.ch_dep0[ch] + k]]; dc = t.dep_counter[t.ch_dep0[ch] + k]; }
-            u32 l, dch;
+            u32 l = 0, dch = ch;
             lamport_of(di, t, dpi, dc, &l, &dch);
-            // row of dch inside the doc: position in its peer's list
-            const DocPeer& ddp = t.dpeer[di.peer0 + dpi];
-            u32 lo = 0, hi = ddp.ch_count;
-            while (hi - lo > 1) {
-                u32 mid = (lo + hi) >> 1;
-                if (t.ch_counter[t.ch_order[di.ch0 + ddp.ch_first + mid]] <= dc) lo = mid; else hi = mid;
-            }
-            const i32* dv = t.ch_vv + di.vv0 + (u64)(ddp.ch_first + lo) * P;
+            const i32* dv = t.ch_vv + di.vv0 + (u64)t.ch_pos[dch] * P;   // the dependency is applied: its row is known
             for (u32 q = 0; q < P; q++) if (dv[q] > v[q]) v[q] = dv[q];
             if (dc + 1 > v[dpi]) v[dpi] = dc + 1;
         }

@@ -44,7 +44,7 @@ struct DocInfo {
     u64 atom_ops;       // merged atoms
     u32 n_pending;      // pending changes
     u32 n_deps;         // cross-peer deps of all changes (capacity estimate)
-    u32 pad2;
+    u32 n_blobs;        // blobs imported into this document (import_batch)
     u32 has_unsupported;
     u64 json_off;
     u32 json_len;

@@ -154,3 +154,53 @@ def test_host_staging_ring_small_slots():
         for slot in ("64", "4096"):
             out = subprocess.check_output([sys.executable, "-c", code, f.name], env=dict(os.environ, LB_STAGE_SLOT=slot))
             assert out.decode().strip() == want, slot
+
+
+def _per_peer_blobs(seed, n_sites=3, n_ops=300):
+    """One history, exported as one blob per peer (each holds only that peer's changes, which depend on the
+    others'): the import_batch shape of SURVEY 8d's C3 variant."""
+    blob, js, vv, sites = workloads.make_doc_history(seed, n_sites=n_sites, n_ops=n_ops)
+    full = sites[0]
+    tot = full.oplog_vv()
+    parts = [full.export_updates({q: c for q, c in tot.items() if q != p}) for p in tot]
+    return blob, js, tot, parts
+
+
+def test_import_batch_groups_blobs_by_doc_id():
+    """LoroDoc::import_batch: several update blobs into one document, in any order, with a duplicate; changes whose
+    dependencies sit in a later blob resolve inside the batch (pending_changes.rs)."""
+    import random
+    import loro_b200
+    blobs, ids, want = [], [], []
+    for d in range(5):
+        whole, js, tot, parts = _per_peer_blobs(3100 + d, n_sites=2 + d % 3, n_ops=150 + 40 * d)
+        random.Random(d).shuffle(parts)
+        if d % 2:
+            parts.append(parts[0])          # the same update twice: a no-op (issue.rs:257-264)
+        for p in parts:
+            blobs.append(p)
+            ids.append(1000 + d)
+        want.append((js, tot))
+    # interleave documents: grouping is by id, not by position
+    order = list(range(len(blobs)))
+    random.Random(99).shuffle(order)
+    b = loro_b200.import_batch([blobs[i] for i in order], doc_ids=[ids[i] for i in order], lib_path=EMU)
+    assert b.n_docs == 5
+    first_seen = []
+    for i in order:
+        if ids[i] not in first_seen:
+            first_seen.append(ids[i])
+    for k, did in enumerate(first_seen):
+        js, tot = want[did - 1000]
+        st = b.status(k)
+        assert st.code == 0 and st.pending is None
+        assert b.json_bytes(k) == js
+        assert b.oplog_vv(k) == tot
+    # a missing part leaves the dependants pending, exactly as a lone import would
+    whole, js, tot, parts = _per_peer_blobs(3200, n_sites=3, n_ops=200)
+    b2 = loro_b200.import_batch(parts[:2], doc_ids=[7, 7], lib_path=EMU)
+    ref = OracleDoc(5)
+    for p in parts[:2]:
+        ref.import_(p)
+    assert b2.n_docs == 1 and b2.json_bytes(0) == ref.json_text()
+    assert b2.oplog_vv(0) == ref.oplog_vv()

@@ -100,6 +100,35 @@ def test_more_than_32_peers_c4_shape():
     check_export_against_oracle(blobs)
 
 
+def test_import_batch_groups_blobs_by_doc_id():
+    """Several update blobs per document (doc_id grouping = LoroDoc::import_batch), shuffled, with duplicates."""
+    import random
+    import loro_b200
+    from tests.test_engine_emu import _per_peer_blobs
+    blobs, ids, want = [], [], []
+    for d in range(24):
+        whole, js, tot, parts = _per_peer_blobs(3100 + d, n_sites=2 + d % 4, n_ops=150 + 40 * (d % 7))
+        random.Random(d).shuffle(parts)
+        if d % 2:
+            parts.append(parts[0])
+        blobs += parts
+        ids += [1000 + d] * len(parts)
+        want.append((js, tot))
+    order = list(range(len(blobs)))
+    random.Random(99).shuffle(order)
+    b = loro_b200.import_batch([blobs[i] for i in order], doc_ids=[ids[i] for i in order])
+    assert b.n_docs == 24
+    first_seen = []
+    for i in order:
+        if ids[i] not in first_seen:
+            first_seen.append(ids[i])
+    for k, did in enumerate(first_seen):
+        js, tot = want[did - 1000]
+        assert b.status(k).code == 0 and b.status(k).pending is None
+        assert b.json_bytes(k) == js
+        assert b.oplog_vv(k) == tot
+
+
 def test_automerge_trace_end_content(golden_dir):
     """BASELINE config C2 shape at small replication: the automerge-paper editing trace (259,778 patches,
     crates/loro-internal/benches/text_r.rs) must materialise to its recorded endContent."""
