@@ -275,9 +275,7 @@ void pipeline(lb_batch* b) {
     t.del_peer_idx = dv.alloc<u32>(NDEL); t.del_counter = dv.alloc<i32>(NDEL); t.del_len = dv.alloc<i32>(NDEL);
     if (B) {
         LB_LAUNCH(k_block_decode, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
-        LB_LAUNCH(k_block_columns, nblk(B * 8, 128), 128, 0, st, b->d_bytes, blk, B, t);
-        LB_LAUNCH(k_block_values, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
-        tm.kernel_launches += 3;
+        tm.kernel_launches += 1;
     }
     mark(b);  // [2] decode done
     // SURVEY 8d algorithmic bytes of decode: blob bytes read + SoA written

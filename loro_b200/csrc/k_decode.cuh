@@ -199,7 +199,7 @@ struct Tables {
 };
 
 // ---------------------------------------------------------------- pass 2: fill
-// pass 2a: header, change_meta, keys, cids (thread per block; small)
+// (no register cap: measured on B200, capping at 128 / 80 / 64 registers costs 1.2x / 2.1x / 2.5x in spills)
 __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks,
                                Tables t) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -361,116 +361,75 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         }
         if (c.err || !c.empty()) err = err ? err : LB_ERR(DOC_ERR_DECODE);
     }
-    if (err) blocks[i].err = err;
-}
-
-// ---------------------------------------------------------------- pass 2b: columns
-// thread per (block, column): the four `ops` columns and the three `delete_start_ids` columns are independent
-// run-length streams, so each gets its own thread (7x the parallelism of a thread per block, few registers).
-// column 0 container index (DeltaRle) 1 prop (DeltaRle) 2 value kind (AnyRle u8) 3 len (AnyRle varint)
-//        4 delete peer idx (DeltaRle) 5 delete counter (DeltaRle) 6 delete len (DeltaRle)
-__global__ void k_block_columns(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks, Tables t) {
-    u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u64 i = tid >> 3;
-    u32 col = (u32)(tid & 7);
-    if (i >= n_blocks || col == 7) return;
-    const BlockInfo& bi = blocks[i];
-    if (bi.err) return;
-    const u8* b = bytes + bi.off;
-    bool is_del = col >= 4;
-    u32 sec = is_del ? 6 : 5;
-    u32 n = is_del ? bi.n_dels : bi.n_ops;
-    if (is_del && bi.sec_len[6] == 0) {
-        if (n && col == 4) blocks[i].err = LB_ERR(DOC_ERR_DECODE);
-        return;
-    }
-    const u8* cols[4];
-    u32 cl[4];
-    if (!columnar_open(b + bi.sec_off[sec], bi.sec_len[sec], is_del ? 3 : 4, cols, cl)) {
-        if (col == 0 || col == 4) blocks[i].err = LB_ERR(DOC_ERR_DECODE);
-        return;
-    }
-    u32 k = is_del ? col - 4 : col;
-    int mode = (col == 2) ? 0 : (col == 3 ? 1 : 2);
-    bool delta = mode == 2;
-    RleCur c(cols[k], cl[k], mode);
-    i64 acc = 0;
-    u32 err = 0;
-    u64 base = is_del ? bi.del0 : bi.op0;
-    for (u32 r = 0; r < n; r++) {
-        i64 x;
-        if (!c.next(&x)) { err = LB_ERR(DOC_ERR_DECODE); break; }
-        if (delta) { acc += x; x = acc; }
-        switch (col) {
-            case 0:
-                if (x < 0 || (u64)x >= bi.n_cids) err = LB_ERR(DOC_ERR_CORRUPT);
-                t.op_cid[base + r] = (u32)x;
-                break;
-            case 1: t.op_prop[base + r] = (i32)x; break;
-            case 2: t.op_vtype[base + r] = (u8)x; break;
-            case 3:
-                if (x <= 0) err = LB_ERR(DOC_ERR_CORRUPT);
-                t.op_len[base + r] = (u32)x;
-                break;
-            case 4:
-                if (x < 0 || (u64)x >= bi.n_peers) err = LB_ERR(DOC_ERR_CORRUPT);
-                t.del_peer_idx[base + r] = (u32)x;
-                break;
-            case 5: t.del_counter[base + r] = (i32)x; break;
-            default:
-                if (x == 0) err = LB_ERR(DOC_ERR_CORRUPT);
-                t.del_len[base + r] = (i32)x;
+    // ---- delete start ids (3 DeltaRle columns)
+    if (bi.sec_len[6]) {
+        const u8* col[3];
+        u32 cl[3];
+        if (!columnar_open(b + bi.sec_off[6], bi.sec_len[6], 3, col, cl)) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        else {
+            RleCur a(col[0], cl[0], 2), bb(col[1], cl[1], 2), cc(col[2], cl[2], 2);
+            i64 pa = 0, pb = 0, pc = 0;
+            for (u32 q = 0; q < bi.n_dels; q++) {
+                i64 x, y, z;
+                if (!a.next(&x) || !bb.next(&y) || !cc.next(&z)) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
+                pa += x; pb += y; pc += z;
+                if (pa < 0 || (u64)pa >= bi.n_peers || pc == 0) err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
+                t.del_peer_idx[bi.del0 + q] = (u32)pa;
+                t.del_counter[bi.del0 + q] = (i32)pb;
+                t.del_len[bi.del0 + q] = (i32)pc;
+            }
+            if (a.c.err || bb.c.err || cc.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
         }
-    }
-    if (!err && (c.c.err || !c.c.empty() || c.run_left != 0)) err = LB_ERR(DOC_ERR_DECODE);
-    if (err) blocks[i].err = err;
-}
-
-// ---------------------------------------------------------------- pass 2c: values walk
-// thread per block: the values stream is one dependent chain (each value's start depends on the previous lengths);
-// counters, change boundaries and delete indices come with it.  Reads the kind / len columns written by 2b.
-__global__ void k_block_values(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks, Tables t) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    const BlockInfo& bi = blocks[i];
-    if (bi.err) return;
-    const u8* b = bytes + bi.off;
-    u32 N = bi.n_changes;
-    u32 err = 0;
-    Cur v(b + bi.sec_off[7], bi.sec_len[7]);
-    i32 counter = (i32)bi.counter_start;
-    u32 change = 0;
-    u32 ch_first_row = 0;
-    u32 ndel = 0;
-    u32 n_maps = 0;
-    i32 next_boundary = (i32)bi.counter_start + (i32)t.ch_len[bi.ch0];
-    t.ch_op0[bi.ch0] = bi.op0;
-    for (u32 r = 0; r < bi.n_ops; r++) {
-        u64 row = bi.op0 + r;
-        u8 vt = t.op_vtype[row];
-        u32 ln = t.op_len[row];
-        if (change >= N) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
-        t.op_counter[row] = counter;
-        t.op_change[row] = (u32)(bi.ch0 + change);
-        const u8* v0 = v.p;
-        skip_value(v, vt, &n_maps);
-        t.op_val_off[row] = bi.off + (u64)(v0 - b);
-        t.op_val_len[row] = (u32)(v.p - v0);
-        t.op_del[row] = vt == VK_DELETE_SEQ ? (u32)(bi.del0 + ndel++) : 0xFFFFFFFFu;
-        counter += (i32)ln;
-        if (counter >= next_boundary) {
-            t.ch_nops[bi.ch0 + change] = r + 1 - ch_first_row;
-            change++;
-            ch_first_row = r + 1;
-            if (change < N) {
-                t.ch_op0[bi.ch0 + change] = bi.op0 + r + 1;
-                next_boundary += (i32)t.ch_len[bi.ch0 + change];
+    } else if (bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    // ---- ops: 4 columns + values walk
+    {
+        const u8* col[4];
+        u32 cl[4];
+        columnar_open(b + bi.sec_off[5], bi.sec_len[5], 4, col, cl);
+        RleCur c0(col[0], cl[0], 2), c1(col[1], cl[1], 2), c2(col[2], cl[2], 0), c3(col[3], cl[3], 1);
+        Cur v(b + bi.sec_off[7], bi.sec_len[7]);
+        i64 acc_c = 0, acc_p = 0;
+        i32 counter = (i32)bi.counter_start;
+        u32 change = 0;
+        u32 ch_first_row = 0;
+        u32 ndel = 0;
+        u32 n_maps = 0;
+        i32 next_boundary = (i32)bi.counter_start + (i32)t.ch_len[bi.ch0];
+        t.ch_op0[bi.ch0] = bi.op0;
+        for (u32 r = 0; r < bi.n_ops; r++) {
+            i64 dc, dp, vt, ln;
+            if (!c0.next(&dc) || !c1.next(&dp) || !c2.next(&vt) || !c3.next(&ln)) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
+            acc_c += dc;
+            acc_p += dp;
+            if (acc_c < 0 || (u64)acc_c >= bi.n_cids || ln <= 0 || change >= N) { err = err ? err : LB_ERR(DOC_ERR_CORRUPT); break; }
+            u64 row = bi.op0 + r;
+            t.op_cid[row] = (u32)acc_c;
+            t.op_prop[row] = (i32)acc_p;
+            t.op_vtype[row] = (u8)vt;
+            t.op_len[row] = (u32)ln;
+            t.op_counter[row] = counter;
+            t.op_change[row] = (u32)(bi.ch0 + change);
+            const u8* v0 = v.p;
+            // text/list payloads: point past the length prefix where that helps the consumers
+            skip_value(v, (u8)vt, &n_maps);
+            t.op_val_off[row] = bi.off + (u64)(v0 - b);
+            t.op_val_len[row] = (u32)(v.p - v0);
+            t.op_del[row] = (u8)vt == VK_DELETE_SEQ ? (u32)(bi.del0 + ndel++) : 0xFFFFFFFFu;
+            counter += (i32)ln;
+            if (counter >= next_boundary) {
+                t.ch_nops[bi.ch0 + change] = r + 1 - ch_first_row;
+                change++;
+                ch_first_row = r + 1;
+                if (change < N) {
+                    t.ch_op0[bi.ch0 + change] = bi.op0 + r + 1;
+                    next_boundary += (i32)t.ch_len[bi.ch0 + change];
+                }
             }
         }
+        if (v.err || !v.empty() || c0.c.err || c1.c.err || c2.c.err || c3.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels))
+            err = LB_ERR(DOC_ERR_CORRUPT);
+        blocks[i].n_value_maps = n_maps;
     }
-    if (!err && (v.err || !v.empty())) err = LB_ERR(DOC_ERR_DECODE);
-    if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels))
-        err = LB_ERR(DOC_ERR_CORRUPT);
-    blocks[i].n_value_maps = n_maps;
     if (err) blocks[i].err = err;
 }
