@@ -434,28 +434,48 @@ void pipeline(lb_batch* b) {
         xt.op_counter = t.op_counter; xt.op_val_off = t.op_val_off; xt.op_val_len = t.op_val_len; xt.op_del = t.op_del;
         xt.op_aux = ct.op_aux; xt.del_counter = t.del_counter; xt.del_len = t.del_len;
         xt.r_astart = dv.alloc<u32>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.r_flag = dv.alloc<u8>(NR);
-        xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
+        xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_novf = dv.alloc<u32>(NCH + 1, true);
+        xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
+        xt.n_changes = NCH;
         xt.xdoc = dv.alloc<XDoc>(D + 1, true);
         b->d_xdoc = xt.xdoc;
         xt.ch_aval = dv.alloc<u32>(NCH + 1, true); xt.ch_astr = dv.alloc<u32>(NCH + 1, true);
         xt.ch_aval0 = dv.alloc<u64>(NCH + 2, true); xt.ch_astr0 = dv.alloc<u64>(NCH + 2, true);
+        // segment / final-change records: one slot per change + one per extra segment of a split change; the
+        // extras are counted by pass 0, so the arrays are sized with a bound first and checked after the scan
+        u64 SEGCAP = NCH + NCH / 4 + 1024;
+        if (getenv("LB_EXPORT_TIGHT_SEGCAP")) SEGCAP = NCH;   // testing hook: force the growth path
+        xt.sg_src = dv.alloc<u32>(SEGCAP); xt.sg_r0 = dv.alloc<u32>(SEGCAP); xt.sg_from = dv.alloc<u32>(SEGCAP);
+        xt.sg_atoms = dv.alloc<u32>(SEGCAP); xt.sg_est = dv.alloc<u32>(SEGCAP); xt.sg_nmops = dv.alloc<u32>(SEGCAP);
+        xt.sg_ndel = dv.alloc<u32>(SEGCAP); xt.sg_nrows = dv.alloc<u32>(SEGCAP); xt.sg_last_head = dv.alloc<u32>(SEGCAP);
+        xt.fc_src = dv.alloc<u32>(SEGCAP); xt.fc_pos = dv.alloc<u32>(SEGCAP); xt.fc_r0 = dv.alloc<u32>(SEGCAP);
+        xt.fc_from = dv.alloc<u32>(SEGCAP); xt.fc_atoms = dv.alloc<u32>(SEGCAP); xt.fc_nrows = dv.alloc<u32>(SEGCAP);
+        xt.fc_ndel = dv.alloc<u32>(SEGCAP); xt.fc_block = dv.alloc<u8>(SEGCAP);
         LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
         if (NCH) LB_LAUNCH(k_exp_arena, nblk(NCH, 64), 64, 0, st, NCH, xt, b->d_docs);
         run_scans(b, {ScanJob{(const u8*)xt.ch_aval, (u8*)xt.ch_aval0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_astr, (u8*)xt.ch_astr0, 4, 8, NCH}});
         if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
         tm.kernel_launches += 3;
-        run_scans(b, {ScanJob{(const u8*)xt.ch_nseg, (u8*)xt.ch_seg0, 4, 8, NCH}});
-        u64 NSEG = d2h_one(b, xt.ch_seg0 + NCH);
-        xt.sg_src = dv.alloc<u32>(NSEG); xt.sg_r0 = dv.alloc<u32>(NSEG); xt.sg_from = dv.alloc<u32>(NSEG);
-        xt.sg_atoms = dv.alloc<u32>(NSEG); xt.sg_est = dv.alloc<u32>(NSEG); xt.sg_nmops = dv.alloc<u32>(NSEG);
-        xt.sg_ndel = dv.alloc<u32>(NSEG); xt.sg_nrows = dv.alloc<u32>(NSEG); xt.sg_last_head = dv.alloc<u32>(NSEG);
-        xt.fc_src = dv.alloc<u32>(NSEG); xt.fc_pos = dv.alloc<u32>(NSEG); xt.fc_r0 = dv.alloc<u32>(NSEG);
-        xt.fc_from = dv.alloc<u32>(NSEG); xt.fc_atoms = dv.alloc<u32>(NSEG); xt.fc_nrows = dv.alloc<u32>(NSEG);
-        xt.fc_ndel = dv.alloc<u32>(NSEG); xt.fc_block = dv.alloc<u8>(NSEG);
-        if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 1);
+        run_scans(b, {ScanJob{(const u8*)xt.ch_novf, (u8*)xt.ch_seg0, 4, 8, NCH}});
+        u64 NOVF = d2h_one(b, xt.ch_seg0 + NCH);
+        if (NCH + NOVF > SEGCAP) {   // unusually many split changes: grow the tables, keep what pass 0 wrote
+            u64 cap = NCH + NOVF;
+            u32** sgs[9] = {&xt.sg_src, &xt.sg_r0, &xt.sg_from, &xt.sg_atoms, &xt.sg_est, &xt.sg_nmops, &xt.sg_ndel, &xt.sg_nrows, &xt.sg_last_head};
+            for (auto pp : sgs) {
+                u32* nw = dv.alloc<u32>(cap);
+                CK(cudaMemcpyAsync(nw, *pp, sizeof(u32) * NCH, cudaMemcpyDeviceToDevice, st));
+                dv.release(*pp);
+                *pp = nw;
+            }
+            u32** fcs[7] = {&xt.fc_src, &xt.fc_pos, &xt.fc_r0, &xt.fc_from, &xt.fc_atoms, &xt.fc_nrows, &xt.fc_ndel};
+            for (auto pp : fcs) { dv.release(*pp); *pp = dv.alloc<u32>(cap); }
+            dv.release(xt.fc_block);
+            xt.fc_block = dv.alloc<u8>(cap);
+        }
+        if (NOVF) { LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 1); tm.kernel_launches += 1; }
         LB_LAUNCH(k_exp_store, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
         LB_LAUNCH(k_exp_sizes, nblk(D), TPB, 0, st, b->d_docs, D, xt, d_tmp_a, d_tmp_b);
-        tm.kernel_launches += 3;
+        tm.kernel_launches += 2;
         run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)xt.xdoc + offsetof(XDoc, ob0), 4, sizeof(XDoc), D},
                       ScanJob{(const u8*)d_tmp_b, (u8*)xt.xdoc + offsetof(XDoc, scratch0), 4, sizeof(XDoc), D}});
         XDoc xtot = d2h_one(b, xt.xdoc + D);

@@ -71,9 +71,11 @@ struct ExportTables {
     u8* r_flag;        // XF_*
     // per change
     u32* ch_nseg;      // segments the change enters the store as (0 = not applied)
+    u32* ch_novf;      // nseg - 1 (scan input): only split changes need slots beyond their own
+    u64 n_changes;     // segment q of change ch lives at q == 0 ? ch : n_changes + ch_seg0[ch] + q - 1
     u32* ch_aval; u32* ch_astr; u64* ch_aval0; u64* ch_astr0;   // arena sums per change + their scans
-    u64* ch_seg0;      // scan of ch_nseg
-    // per segment (index space: ch_seg0)
+    u64* ch_seg0;      // scan of ch_novf
+    // per segment
     u32* sg_src; u32* sg_r0; u32* sg_from; u32* sg_atoms; u32* sg_est; u32* sg_nmops; u32* sg_ndel; u32* sg_nrows; u32* sg_last_head;
     // final changes (same index space: a document never ends up with more changes than segments)
     u32* fc_src; u32* fc_pos; u32* fc_r0; u32* fc_from; u32* fc_atoms; u32* fc_nrows; u32* fc_ndel; u8* fc_block;
@@ -269,13 +271,13 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
         // intra-change merge + total estimate
         XOp back;
         back.xk = XK_NONE;
-        u32 est_ops = 0;
+        u32 est_ops = 0, nm = 0, ndel = 0, last_head = 0;
         bool bad = false;
         for (u32 r = 0; r < nr; r++) {
             XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
             if (o.xk == XK_NONE) bad = true;
             if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[r0 + r] = 0; }
-            else { back = o; est_ops += xop_estimate(o); t.r_flag[r0 + r] = XF_HEAD; }
+            else { back = o; est_ops += xop_estimate(o); t.r_flag[r0 + r] = XF_HEAD; nm++; ndel += o.xk == XK_DEL; last_head = r; }
         }
         u32 ndeps = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
         u32 est0 = 4 + (ndeps > 1 ? (ndeps - 1) * 4 : 0);
@@ -304,11 +306,18 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
             }
         }
         t.ch_nseg[ch] = nseg;
+        t.ch_novf[ch] = nseg - 1;
+        if (nseg == 1) {   // the common case: the change is its own (only) segment, summarised right here
+            t.sg_src[ch] = (u32)ch; t.sg_r0[ch] = 0; t.sg_from[ch] = 0; t.sg_atoms[ch] = t.ch_len[ch]; t.sg_est[ch] = est_ops;
+            t.sg_nmops[ch] = nm; t.sg_ndel[ch] = ndel; t.sg_nrows[ch] = nr; t.sg_last_head[ch] = last_head;
+        }
         if (bad) atomicOr(&t.xdoc[doc].flags, 1u);
         return;
     }
-    // pass 1: segment summaries
-    u64 sg = t.ch_seg0[ch];
+    // pass 1 (split changes only): segment summaries
+    if (t.ch_nseg[ch] <= 1) return;
+    u64 sg_next = t.n_changes + t.ch_seg0[ch];
+    u64 sg = ch;
     u32 r = 0;
     u32 from = 0;
     while (r < nr) {
@@ -327,7 +336,7 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
         t.sg_src[sg] = (u32)ch; t.sg_r0[sg] = r_start; t.sg_from[sg] = from; t.sg_atoms[sg] = atoms; t.sg_est[sg] = est;
         t.sg_nmops[sg] = nm; t.sg_ndel[sg] = ndel; t.sg_nrows[sg] = r - r_start; t.sg_last_head[sg] = last_head;
         from += atoms;
-        sg++;
+        sg = sg_next++;
     }
 }
 
@@ -463,7 +472,7 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
     if (di.code != DOC_OK) return;
     XDoc x = t.xdoc[d];
     if (x.flags & 1) { t.xdoc[d] = x; return; }
-    u64 w = t.ch_seg0[di.ch0];   // final changes of the document are written from its first segment slot on
+    u64 w = di.ch0 + t.ch_seg0[di.ch0];   // as many slots as the document has segments
     u64 w0 = w;
     u32 n_mb = 0;
     auto emit = [&](const XEntry& e, bool starts_block) {
@@ -486,8 +495,8 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
             u32 pos = (u32)di.ch0 + dp.ch_first + k;
             u32 ch = t.ch_order[pos];
             u32 nseg = t.ch_nseg[ch];
-            u64 sg = t.ch_seg0[ch];
-            for (u32 q = 0; q < nseg; q++, sg++) {
+            for (u32 q = 0; q < nseg; q++) {
+                u64 sg = q == 0 ? (u64)ch : t.n_changes + t.ch_seg0[ch] + q - 1;
                 XEntry E;
                 E.src = ch; E.from = t.sg_from[sg]; E.pos = pos; E.r0 = t.sg_r0[sg]; E.atoms = t.sg_atoms[sg];
                 E.est_ops = t.sg_est[sg]; E.nmops = t.sg_nmops[sg]; E.ndel = t.sg_ndel[sg]; E.nrows = t.sg_nrows[sg];
@@ -520,7 +529,7 @@ __global__ void k_exp_list(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
     const DocInfo& di = docs[d];
     const XDoc& x = t.xdoc[d];
     if (di.code != DOC_OK || x.n_mb == 0) return;
-    u64 f0 = t.ch_seg0[di.ch0];
+    u64 f0 = di.ch0 + t.ch_seg0[di.ch0];
     u32 regs = 2 * (di.P + di.K + di.C);
     u64 scr = x.scratch0;
     int idx = -1;
@@ -548,7 +557,7 @@ __global__ void k_exp_sizes(const DocInfo* __restrict__ docs, u32 n_docs, Export
     u32 nb = di.code == DOC_OK ? x.n_mb : 0;
     u64 words = 0;
     if (nb) {
-        u64 f0 = t.ch_seg0[di.ch0];
+        u64 f0 = di.ch0 + t.ch_seg0[di.ch0];
         words = (u64)nb * 2 * (di.P + di.K + di.C);
         for (u64 k = f0; k < f0 + x.n_fc; k++) words += 5ull * t.fc_nrows[k] + 3ull * t.fc_ndel[k];
     }
