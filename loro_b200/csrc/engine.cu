@@ -483,14 +483,14 @@ void pipeline(lb_batch* b) {
         XBlock* xb = dv.alloc<XBlock>(NOB + 1);
         u32* xscratch = dv.alloc<u32>(NSCR + 1);
         LB_LAUNCH(k_exp_list, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb);
-        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB * 32, 32 * LB_EXP_WARPS), 32 * LB_EXP_WARPS, 0, st, b->d_docs, NOB, xt, xb, xscratch, (u8*)nullptr, 0);
+        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, (u8*)nullptr, 0);
         LB_LAUNCH(k_exp_layout, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb, d_tmp_a);
         tm.kernel_launches += 3;
         run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)xt.xdoc + offsetof(XDoc, exp_off), 4, sizeof(XDoc), D}});
         u64 XT = d2h_one(b, &xt.xdoc[D].exp_off);
         b->export_total = XT;
         b->d_export = dv.alloc<u8>(XT + 16, true);
-        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB * 32, 32 * LB_EXP_WARPS), 32 * LB_EXP_WARPS, 0, st, b->d_docs, NOB, xt, xb, xscratch, b->d_export, 1);
+        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, b->d_export, 1);
         LB_LAUNCH(k_exp_finish, nblk(D), TPB, 0, st, b->d_docs, D, xt, b->d_export);
         tm.kernel_launches += 2;
         tm.export_bytes = XT;

@@ -704,19 +704,11 @@ __device__ __forceinline__ u8 xk_value_type(u8 xk) {
     }
 }
 
-// WARP per output block.  pass 0: gather ops into scratch columns, registers, section sizes ; pass 1: bytes.
-// The row fields (pass 0) and the value payloads (pass 1) are what costs round trips to HBM: both are fetched /
-// copied by the 32 lanes together, 32 rows at a time; lane 0 runs the sequential parts (first-use registers, the
-// RleVec accumulation, the column encoders) on data staged in shared memory / L1-resident scratch columns.
-struct XStage { XOp o; u32 flag; u32 vb; u32 row; };
-#define LB_EXP_WARPS 4
+// thread per output block.  pass 0: gather ops into scratch columns, registers, section sizes ; pass 1: bytes.
 __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
                              u32* __restrict__ scratch, u8* __restrict__ out, int pass) {
-    __shared__ XStage stage_s[LB_EXP_WARPS][32];
-    u64 bi_ = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    u64 bi_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (bi_ >= n_blocks) return;
-    XStage* stage = stage_s[(threadIdx.x >> 5) % LB_EXP_WARPS];
     XBlock B = xb[bi_];
     const DocInfo& di = docs[B.doc];
     const u32 P = di.P, K = di.K, C = di.C;
@@ -738,99 +730,57 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     u32 n_dep = 0;
     for (u32 j = 0; j < N; j++) n_dep += t.fc_from[fc0 + j] ? 0u : t.ch_ndeps[t.fc_src[fc0 + j]];
     if (pass == 0) {
-        for (u32 i = lane; i < P; i += 32) peers.inv[i] = 0xFFFFFFFFu;
-        for (u32 i = lane; i < K; i += 32) keys.inv[i] = 0xFFFFFFFFu;
-        for (u32 i = lane; i < C; i += 32) cids.inv[i] = 0xFFFFFFFFu;
-        __syncwarp();
+        for (u32 i = 0; i < P; i++) peers.inv[i] = 0xFFFFFFFFu;
+        for (u32 i = 0; i < K; i++) keys.inv[i] = 0xFFFFFFFFu;
+        for (u32 i = 0; i < C; i++) cids.inv[i] = 0xFFFFFFFFu;
         peers.n = keys.n = cids.n = 0;
-        if (lane == 0) peers.reg(t.peer_map[t.blocks[t.ch_block[first_src]].peer0]);   // the author of the block's changes
+        peers.reg(t.peer_map[t.blocks[t.ch_block[first_src]].peer0]);   // the author of the block's changes
         // ops in order: containers, map keys, delete targets (block_encode.rs:180-236)
         u32 n_ops = 0, n_del = 0, vbytes = 0;
         u32 prev_cidx = 0, prev_prop = 0, prev_dp = 0, prev_dc = 0, prev_dl = 0;   // 32-bit wrap-around deltas
-        XOp cur;                 // the op being accumulated (lane 0)
-        cur.xk = XK_NONE;
-        u32 cur_first_row = 0;
-        bool have_cur = false;
-        auto flush = [&]() {     // lane 0: the accumulated op becomes one row of the columns
-            if (!have_cur) return;
-            const XOp& o = cur;
-            if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
-            else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
-            // DeltaRle columns are stored as deltas right away (the encoders then read every value once)
-            u32 lc = cids.reg(o.cidx);
-            u32 lp = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
-            c_cidx[n_ops] = lc - prev_cidx; prev_cidx = lc;
-            c_prop[n_ops] = lp - prev_prop; prev_prop = lp;
-            c_vt[n_ops] = xk_value_type(o.xk) | ((u32)o.xk << 8);
-            c_atoms[n_ops] = o.atoms;
-            c_bytes[n_ops] = o.xk == XK_TEXT ? o.f1 - o.f0 : cur_first_row;
-            if (o.xk == XK_DEL) {
-                u32 dp = peers.reg(o.f0);
-                d_peer[n_del] = dp - prev_dp; prev_dp = dp;
-                d_ctr[n_del] = o.f1 - prev_dc; prev_dc = o.f1;
-                d_len[n_del] = (u32)o.f2 - prev_dl; prev_dl = (u32)o.f2;
-                n_del++;
-            }
-            n_ops++;
-            have_cur = false;
-        };
         for (u32 j = 0; j < N; j++) {
-            u32 pos = t.fc_pos[fc0 + j], r = t.fc_r0[fc0 + j], left = t.fc_nrows[fc0 + j];
-            bool fresh = true;   // the first row of a stored change always starts an op
+            XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
+            u32 left = t.fc_nrows[fc0 + j];
             while (left) {
-                u32 ch = t.ch_order[pos];
-                u32 nr = t.ch_applied[ch] ? t.ch_nops[ch] : 0;
-                if (r >= nr) { pos++; r = 0; continue; }
-                u64 row0 = t.ch_op0[ch];
-                u32 take = nr - r < left ? nr - r : left;
-                for (u32 c0 = 0; c0 < take; c0 += 32) {
-                    u32 n = take - c0 < 32 ? take - c0 : 32;
-                    if ((u32)lane < n) {   // 32 rows per round trip
-                        u64 row = row0 + r + c0 + lane;
-                        XStage st;
-                        st.o = xop_from_row(t, di, ch, row);
-                        st.flag = t.r_flag[row];
-                        st.vb = row_value_bytes(t, st.o, row);
-                        st.row = (u32)row;
-                        stage[lane] = st;
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        for (u32 k = 0; k < n; k++) {
-                            const XStage& st = stage[k];
-                            if (fresh || (st.flag & XF_HEAD)) { flush(); cur = st.o; cur_first_row = st.row; have_cur = true; }
-                            else xop_merge(cur, st.o);
-                            vbytes += st.vb;
-                            fresh = false;
-                        }
-                    }
-                    __syncwarp();
+                u32 first_row = (u32)it.row();
+                XOp o = xop_gather(t, di, it, left, &vbytes);
+                if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
+                else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
+                // DeltaRle columns are stored as deltas right away (the encoders then read every value once)
+                u32 lc = cids.reg(o.cidx);
+                u32 lp = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
+                c_cidx[n_ops] = lc - prev_cidx; prev_cidx = lc;
+                c_prop[n_ops] = lp - prev_prop; prev_prop = lp;
+                c_vt[n_ops] = xk_value_type(o.xk) | ((u32)o.xk << 8);
+                c_atoms[n_ops] = o.atoms;
+                c_bytes[n_ops] = o.xk == XK_TEXT ? o.f1 - o.f0 : first_row;
+                if (o.xk == XK_DEL) {
+                    u32 dp = peers.reg(o.f0);
+                    d_peer[n_del] = dp - prev_dp; prev_dp = dp;
+                    d_ctr[n_del] = o.f1 - prev_dc; prev_dc = o.f1;
+                    d_len[n_del] = (u32)o.f2 - prev_dl; prev_dl = (u32)o.f2;
+                    n_del++;
                 }
-                left -= take;
-                r += take;
+                n_ops++;
             }
-            if (lane == 0) flush();
         }
-        if (lane == 0) {
-            B.n_ops = n_ops;
-            B.n_del_ops = n_del;
-            B.sec_len[7] = vbytes;   // values section: sizes come with the gather, no second walk
-            // ContainerArena::from_containers (arena.rs:103-147): roots register their name, normals their peer
-            for (u32 i = 0; i < cids.n; i++) {
-                const DocContainer& dc = t.dcont[di.cid0 + cids.ord[i]];
-                if (dc.is_root) keys.reg(dc.key_or_peer); else peers.reg(dc.key_or_peer);
-            }
-            // encode_changes (block_meta_encode.rs:13-88): dependency peers
-            for (u32 j = 0; j < N; j++) {
-                if (t.fc_from[fc0 + j]) continue;
-                u32 src = t.fc_src[fc0 + j];
-                const BlockInfo& sb = t.blocks[t.ch_block[src]];
-                for (u32 k = 0; k < t.ch_ndeps[src]; k++) peers.reg(t.peer_map[sb.peer0 + t.dep_peer_idx[t.ch_dep0[src] + k]]);
-            }
-            B.col_len[7] = peers.n | (keys.n << 16);
-            B.n_cids = cids.n;
+        B.n_ops = n_ops;
+        B.n_del_ops = n_del;
+        B.sec_len[7] = vbytes;   // values section: sizes come with the gather, no second walk
+        // ContainerArena::from_containers (arena.rs:103-147): roots register their name, normals their peer
+        for (u32 i = 0; i < cids.n; i++) {
+            const DocContainer& dc = t.dcont[di.cid0 + cids.ord[i]];
+            if (dc.is_root) keys.reg(dc.key_or_peer); else peers.reg(dc.key_or_peer);
         }
-        __syncwarp();
+        // encode_changes (block_meta_encode.rs:13-88): dependency peers
+        for (u32 j = 0; j < N; j++) {
+            if (t.fc_from[fc0 + j]) continue;
+            u32 src = t.fc_src[fc0 + j];
+            const BlockInfo& sb = t.blocks[t.ch_block[src]];
+            for (u32 k = 0; k < t.ch_ndeps[src]; k++) peers.reg(t.peer_map[sb.peer0 + t.dep_peer_idx[t.ch_dep0[src] + k]]);
+        }
+        B.col_len[7] = peers.n | (keys.n << 16);
+        B.n_cids = cids.n;
     } else {
         peers.n = B.col_len[7] & 0xFFFFu;
         keys.n = B.col_len[7] >> 16;
@@ -901,63 +851,30 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             default: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_len[i]; }, WrZigzag());
         }
     };
-    // values section, all lanes: 32 rows at a time, each lane places its row's payload (and, on the first row of an
-    // op, the op's prefix) at the offset a warp scan gives it
-    auto w_values_coop = [&](u8* dst) {
-        u32 op = 0;      // ops started so far
-        u64 at = 0;      // bytes written so far
+    auto w_values = [&](XSink& s) {
+        u32 op = 0;
+        u32 xk = XK_NONE;
         for (u32 j = 0; j < N; j++) {
-            u32 pos = t.fc_pos[fc0 + j], r = t.fc_r0[fc0 + j], left = t.fc_nrows[fc0 + j];
+            XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
+            u32 left = t.fc_nrows[fc0 + j];
             bool fresh = true;
             while (left) {
-                u32 ch = t.ch_order[pos];
-                u32 nr = t.ch_applied[ch] ? t.ch_nops[ch] : 0;
-                if (r >= nr) { pos++; r = 0; continue; }
-                u64 row0 = t.ch_op0[ch];
-                u32 take = nr - r < left ? nr - r : left;
-                for (u32 c0 = 0; c0 < take; c0 += 32) {
-                    u32 n = take - c0 < 32 ? take - c0 : 32;
-                    bool valid = (u32)lane < n;
-                    u64 row = row0 + r + c0 + (valid ? lane : 0);
-                    bool head = valid && ((fresh && lane == 0) || (t.r_flag[row] & XF_HEAD));
-                    unsigned hm = __ballot_sync(LB_FULL, head);
-                    u32 my_op = op + __popc(hm & ((2u << lane) - 1)) - 1;   // the op this row belongs to
-                    u32 xk = XK_NONE, pre = 0, pay = 0;
-                    const u8* src = nullptr;
-                    if (valid) {
-                        xk = c_vt[my_op] >> 8;
-                        if (xk == XK_LIST) {
-                            u32 skip = 1 + varint_len(t.op_len[row]);
-                            src = t.bytes + t.op_val_off[row] + skip;
-                            pay = t.op_val_len[row] - skip;
-                            if (head) pre = 1 + varint_len(c_atoms[my_op]);
-                        } else if (xk == XK_TEXT) {
-                            pay = t.r_bytes[row];
-                            src = t.bytes + t.op_val_off[row] + varint_len(pay);
-                            if (head) pre = varint_len(c_bytes[my_op]);
-                        } else if (xk == XK_MAPSET) {
-                            src = t.bytes + t.op_val_off[row];
-                            pay = t.op_val_len[row];
-                        }
-                    }
-                    u32 mine = pre + pay;
-                    u32 incl = (u32)warp_incl_scan((int)mine, lane);
-                    u32 total = __shfl_sync(LB_FULL, incl, 31);
-                    if (valid && mine) {
-                        XSink w;
-                        w.dst = dst; w.n = at + (incl - mine);
-                        if (pre) {
-                            if (xk == XK_LIST) { w.put(7); w.varint(c_atoms[my_op]); }
-                            else w.varint(c_bytes[my_op]);
-                        }
-                        w.copy(src, pay);
-                    }
-                    at += total;
-                    op += __popc(hm);
-                    fresh = false;
+                u64 row = it.row();
+                if (fresh || (t.r_flag[row] & XF_HEAD)) {
+                    xk = c_vt[op] >> 8;
+                    if (xk == XK_LIST) { s.put(7); s.varint(c_atoms[op]); }
+                    else if (xk == XK_TEXT) s.varint(c_bytes[op]);
+                    op++;
                 }
-                left -= take;
-                r += take;
+                fresh = false;
+                if (xk == XK_LIST || xk == XK_TEXT) {
+                    Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                    if (xk == XK_TEXT) (void)c.varint();
+                    else { (void)c.get(); (void)c.varint(); }
+                    s.copy(c.p, c.left());
+                } else if (xk == XK_MAPSET) s.copy(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                left--;
+                if (left) it.next();
             }
         }
     };
@@ -967,60 +884,52 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     u32 lam0 = (u32)lamport(0);
     u32 lam_len = (u32)lamport(N - 1) + t.fc_atoms[B.fc1 - 1] - lam0;
     if (pass == 0) {
-        if (lane == 0) {
-            XSink s;
-            s.dst = nullptr;
-            s.n = 0; w_header(s); B.sec_len[0] = (u32)s.n;
-            s.n = 0; w_meta(s); B.sec_len[1] = (u32)s.n;
-            s.n = 0; w_cids(s); B.sec_len[2] = (u32)s.n;
-            s.n = 0; w_keys(s); B.sec_len[3] = (u32)s.n;
-            B.sec_len[4] = 0;
-            u32 tot = 2;   // varint(1) varint(4)
-            for (int c = 0; c < 4; c++) { s.n = 0; w_opcol(s, c); B.col_len[c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
-            B.sec_len[5] = tot;
-            if (n_del) {
-                tot = 2;
-                for (int c = 0; c < 3; c++) { s.n = 0; w_delcol(s, c); B.col_len[4 + c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
-                B.sec_len[6] = tot;
-            } else B.sec_len[6] = 0;
-            u32 len = varint_len(counter0) + varint_len(counter_len) + varint_len(lam0) + varint_len(lam_len) + varint_len(N);
-            for (int i = 0; i < 8; i++) len += varint_len(B.sec_len[i]) + B.sec_len[i];
-            B.len = len;
-            xb[bi_] = B;
-        }
+        XSink s;
+        s.dst = nullptr;
+        s.n = 0; w_header(s); B.sec_len[0] = (u32)s.n;
+        s.n = 0; w_meta(s); B.sec_len[1] = (u32)s.n;
+        s.n = 0; w_cids(s); B.sec_len[2] = (u32)s.n;
+        s.n = 0; w_keys(s); B.sec_len[3] = (u32)s.n;
+        B.sec_len[4] = 0;
+        u32 tot = 2;   // varint(1) varint(4)
+        for (int c = 0; c < 4; c++) { s.n = 0; w_opcol(s, c); B.col_len[c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
+        B.sec_len[5] = tot;
+        if (n_del) {
+            tot = 2;
+            for (int c = 0; c < 3; c++) { s.n = 0; w_delcol(s, c); B.col_len[4 + c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
+            B.sec_len[6] = tot;
+        } else B.sec_len[6] = 0;
+        u32 len = varint_len(counter0) + varint_len(counter_len) + varint_len(lam0) + varint_len(lam_len) + varint_len(N);
+        for (int i = 0; i < 8; i++) len += varint_len(B.sec_len[i]) + B.sec_len[i];
+        B.len = len;
+        xb[bi_] = B;
         return;
     }
     // ---- pass 1: ULEB length prefix + block bytes at the document's slot
     u64 base = t.xdoc[B.doc].exp_off + B.off;
-    u64 values_at = 0;
-    if (lane == 0) {
-        XSink s;
-        s.dst = out + base - varint_len(B.len);
-        s.n = 0;
-        s.varint(B.len);
-        s.varint(counter0);
-        s.varint(counter_len);
-        s.varint(lam0);
-        s.varint(lam_len);
-        s.varint(N);
-        s.varint(B.sec_len[0]); w_header(s);
-        s.varint(B.sec_len[1]); w_meta(s);
-        s.varint(B.sec_len[2]); w_cids(s);
-        s.varint(B.sec_len[3]); w_keys(s);
-        s.varint(0);
-        s.varint(B.sec_len[5]);
-        s.varint(1); s.varint(4);
-        for (int c = 0; c < 4; c++) { s.varint(B.col_len[c]); w_opcol(s, c); }
-        s.varint(B.sec_len[6]);
-        if (n_del) {
-            s.varint(1); s.varint(3);
-            for (int c = 0; c < 3; c++) { s.varint(B.col_len[4 + c]); w_delcol(s, c); }
-        }
-        s.varint(B.sec_len[7]);
-        values_at = s.n;
+    XSink s;
+    s.dst = out + base - varint_len(B.len);
+    s.n = 0;
+    s.varint(B.len);
+    s.varint(counter0);
+    s.varint(counter_len);
+    s.varint(lam0);
+    s.varint(lam_len);
+    s.varint(N);
+    s.varint(B.sec_len[0]); w_header(s);
+    s.varint(B.sec_len[1]); w_meta(s);
+    s.varint(B.sec_len[2]); w_cids(s);
+    s.varint(B.sec_len[3]); w_keys(s);
+    s.varint(0);
+    s.varint(B.sec_len[5]);
+    s.varint(1); s.varint(4);
+    for (int c = 0; c < 4; c++) { s.varint(B.col_len[c]); w_opcol(s, c); }
+    s.varint(B.sec_len[6]);
+    if (n_del) {
+        s.varint(1); s.varint(3);
+        for (int c = 0; c < 3; c++) { s.varint(B.col_len[4 + c]); w_delcol(s, c); }
     }
-    values_at = __shfl_sync(LB_FULL, values_at, 0);
-    w_values_coop(out + base - varint_len(B.len) + values_at);
+    s.varint(B.sec_len[7]); w_values(s);
 }
 
 // thread per document: block offsets inside the blob, blob length (after encode pass 0)
