@@ -57,6 +57,10 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
     u32 cidx = t.cid_map[bi.cid0 + t.op_cid[row]];
     DocContainer& dc = t.dcont[di.cid0 + cidx];
     u8 kind = classify_op(dc.type, t.op_vtype[row]);
+    if ((kind == OPK_MAP_SET || kind == OPK_MAP_DEL) && (u32)t.op_prop[row] >= bi.n_keys) {
+        kind = OPK_SKIP;                       // a map op whose key index is outside the block's key arena
+        di.code = LB_ERR(DOC_ERR_CORRUPT);      // (any thread may write it: every writer stores the same code)
+    }
     if (!t.ch_applied[ch]) kind = OPK_SKIP;
     u32 lam = t.ch_lamport[ch] + (u32)(t.op_counter[row] - t.ch_counter[ch]);
     {   // tracker record: everything k_seq needs about this row in one 16-byte load

@@ -431,5 +431,11 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             err = LB_ERR(DOC_ERR_CORRUPT);
         blocks[i].n_value_maps = n_maps;
     }
-    if (err) blocks[i].err = err;
+    if (err) {
+        // row-parallel kernels find their document through op_change: every row of a failed block must point
+        // at one of the block's own changes, whatever the walk above managed to write
+        for (u32 r = 0; r < bi.n_ops; r++) t.op_change[bi.op0 + r] = (u32)bi.ch0;
+        for (u32 k = 0; k < N; k++) t.ch_block[bi.ch0 + k] = (u32)i;
+        blocks[i].err = err;
+    }
 }

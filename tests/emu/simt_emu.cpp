@@ -209,3 +209,42 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 }
 
 }  // namespace simt
+
+
+// ---------------------------------------------------------------- guarded allocations (LB_EMU_GUARD)
+#include <sys/mman.h>
+#include <unistd.h>
+#include <map>
+#include <mutex>
+namespace {
+std::mutex g_guard_mu;
+std::map<void*, std::pair<void*, size_t>> g_guard;   // user pointer -> (mapping, mapped bytes)
+}
+bool simt_guard_enabled() {
+    static int on = getenv("LB_EMU_GUARD") ? 1 : 0;
+    return on != 0;
+}
+cudaError_t simt_guard_malloc(void** p, size_t n) {
+    size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    size_t body = ((n ? n : 1) + 255) & ~(size_t)255;          // the engine rounds to 256 anyway
+    size_t pages = (body + page - 1) / page;
+    size_t total = (pages + 2) * page;
+    char* m = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) return 2;
+    mprotect(m, page, PROT_NONE);
+    mprotect(m + (pages + 1) * page, page, PROT_NONE);
+    char* user = m + (pages + 1) * page - body;                  // the end of the buffer touches the guard page
+    std::lock_guard<std::mutex> g(g_guard_mu);
+    g_guard[user] = {m, total};
+    *p = user;
+    return 0;
+}
+cudaError_t simt_guard_free(void* p) {
+    if (!p) return 0;
+    std::lock_guard<std::mutex> g(g_guard_mu);
+    auto it = g_guard.find(p);
+    if (it == g_guard.end()) { std::free(p); return 0; }
+    munmap(it->second.first, it->second.second);
+    g_guard.erase(it);
+    return 0;
+}

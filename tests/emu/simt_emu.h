@@ -256,8 +256,21 @@ typedef void* cudaStream_t;
 typedef struct simt_event_* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
-inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+// LB_EMU_GUARD=1: every "device" allocation ends right before an inaccessible page (and starts right after one),
+// so an out-of-bounds index faults at once instead of silently touching a neighbour (used by the fuzz test).
+cudaError_t simt_guard_malloc(void** p, size_t n);
+cudaError_t simt_guard_free(void* p);
+bool simt_guard_enabled();
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+    if (simt_guard_enabled()) return simt_guard_malloc(p, n);
+    *p = std::malloc(n ? n : 1);
+    return *p ? 0 : 2;
+}
+inline cudaError_t cudaFree(void* p) {
+    if (simt_guard_enabled()) return simt_guard_free(p);
+    std::free(p);
+    return 0;
+}
 inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
@@ -285,5 +298,6 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 
 // kernel launch: LB_LAUNCH(kernel, grid, block, smem_bytes, stream, args...)
 #define LB_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+    ((getenv("LB_EMU_KTRACE") ? fprintf(stderr, "simt_emu: launch %s\n", #kernel) : 0), \
+     simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); }))
 #define LB_DYN_SMEM(type, name) type* name = (type*)simt::cur->dyn_smem

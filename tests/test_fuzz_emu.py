@@ -1,0 +1,20 @@
+"""Malformed input must never make a kernel read or write outside its tables: mutation fuzzing of the emulated
+kernels with guard pages around every device allocation (tests/tools/fuzz_emu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu", "libloro_b200_emu.so")
+
+
+@pytest.mark.parametrize("seed", [21, 23])
+def test_mutated_blobs_stay_inside_their_tables(seed):
+    subprocess.check_call([os.path.join(HERE, "emu", "build_emu.sh")])
+    env = dict(os.environ, LB_EMU_GUARD="1", LB_EMU_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(HERE, "tools", "fuzz_emu.py"), EMU, str(seed), "150"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "fuzz done 150" in out.stdout

@@ -1,0 +1,51 @@
+"""Mutation fuzzer for the kernels (run by tests/test_fuzz_emu.py in a subprocess with LB_EMU_GUARD=1, where every
+"device" allocation of the emulated build sits between inaccessible pages): blobs of valid documents get a few
+bytes changed -- mostly the value bits of varints, so that the framing survives and the *values* (indices,
+counters, positions, lengths) go wild -- and the header checksum is recomputed so that they pass the frame
+phase.  The engine must answer with a per-document code or a state, never touch memory it does not own."""
+import random
+import struct
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import loro_b200                      # noqa: E402
+import oracle                         # noqa: E402
+from loro_b200 import api             # noqa: E402
+from tests import workloads           # noqa: E402
+
+
+def reseal(blob):
+    h = oracle.i64s(oracle.codec("xxh32", bytes(blob[20:]), 0x4F524F4C))[0] & 0xFFFFFFFF
+    return bytes(blob[:16]) + struct.pack("<I", h) + bytes(blob[20:])
+
+
+def main(lib, seed, n):
+    rnd = random.Random(seed)
+    base = [workloads.make_doc_history(100 + i, n_sites=3, n_ops=120)[0] for i in range(4)]
+    ok = 0
+    for _ in range(n):
+        b = bytearray(rnd.choice(base))
+        for _ in range(rnd.randint(1, 4)):
+            i = rnd.randrange(22, len(b))
+            mode = rnd.random()
+            if mode < 0.6:
+                b[i] = (b[i] & 0x80) | rnd.randrange(128)
+            elif mode < 0.85:
+                b[i] = rnd.randrange(256)
+            else:
+                b[i] ^= 1 << rnd.randrange(8)
+        r = loro_b200.import_batch([reseal(b)], flags=api.LB_FLAG_EXPORT, lib_path=lib)
+        if r.status(0).code == 0:
+            ok += 1
+            r.json_bytes(0)
+            try:
+                r.export_updates(0)
+            except api.EngineError:
+                pass
+        r.close()
+    print("fuzz done", n, "imported", ok)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
