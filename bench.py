@@ -114,18 +114,23 @@ class ClockSampler:
 
 
 def default_docs(args, world):
-    if args.docs:
-        return args.docs
+    """Documents per GPU: BASELINE's C3 figure (100 k) at every N, so that per-GPU work is fixed (weak scaling)."""
+    return args.docs or 100000
+
+
+def affordable_distinct(args, world, n_docs):
+    """How many DISTINCT documents this rank's share of the host cores can generate in about 90 s
+    (~1.2 M generated atom ops/s/core); the batch is filled by cycling through them (every copy has its own bytes
+    in HBM; `distinct_docs_per_gpu` in the config says how many there are)."""
+    if args.distinct:
+        return min(args.distinct, n_docs)
     cores = max(1, (host_cores() or 1) // max(1, world))
-    # ~1.2 M generated atom ops/s/core; keep generation near 90 s
-    docs = int(cores * 1.2e6 * 90 / args.ops_per_doc)
-    return max(256, min(100000, docs))
+    return max(64, min(n_docs, int(cores * 1.2e6 * 90 / args.ops_per_doc)))
 
 
 def make_workload(args, rank, world, n_docs):
     from loro_b200.workload import C3Batch
-    distinct = args.distinct or n_docs
-    distinct = min(distinct, n_docs)
+    distinct = affordable_distinct(args, world, n_docs)
     threads = max(1, (host_cores() or 1) // max(1, world))
     t0 = time.time()
     gen = C3Batch(distinct, n_ops=args.ops_per_doc, n_peers=args.peers, first_doc=rank * n_docs, threads=threads)
@@ -227,19 +232,18 @@ def main():
     # lay the batch out in HBM: cycle through the distinct docs (each copy has its own bytes in HBM)
     idx = np.arange(n_docs) % distinct
     lens = gen.lens[idx].astype(np.uint32)
-    padded = (lens.astype(np.uint64) + 15) & ~np.uint64(15)
-    offs = np.zeros(n_docs, dtype=np.uint64)
-    offs[1:] = np.cumsum(padded)[:-1]
-    total_bytes = int(padded.sum())
     src = torch.from_numpy(np.ascontiguousarray(gen.bytes)).to(dev)
+    g_offs = gen.offsets.astype(np.uint64)
     if distinct == n_docs:
         d_bytes = src
-        offs = gen.offsets.astype(np.uint64).copy()
+        offs = g_offs.copy()
     else:
-        d_bytes = torch.zeros(total_bytes + 64, dtype=torch.uint8, device=dev)
-        for i in range(n_docs):
-            o, n = int(gen.offsets[idx[i]]), int(lens[i])
-            d_bytes[int(offs[i]):int(offs[i]) + n] = src[o:o + n]
+        span = (int(src.numel()) + 15) & ~15            # one full copy of the generated buffer, 16-byte aligned
+        reps = (n_docs + distinct - 1) // distinct
+        d_bytes = torch.zeros(span * reps + 64, dtype=torch.uint8, device=dev)
+        for c in range(reps):
+            d_bytes[c * span:c * span + src.numel()] = src
+        offs = (g_offs[idx] + (np.arange(n_docs) // distinct).astype(np.uint64) * np.uint64(span)).astype(np.uint64)
         del src
 
     xflags = 0 if args.no_export else loro_b200.api.LB_FLAG_EXPORT
@@ -293,7 +297,8 @@ def main():
     # ---- e2e: host buffers in, JSON + status out, through the public C-ABI call
     e2e = None
     if not args.no_e2e:
-        blobs = [gen.blob(int(idx[i])) for i in range(n_docs)]
+        blob_of = [gen.blob(k) for k in range(distinct)]   # copies of a document share one host buffer
+        blobs = [blob_of[int(idx[i])] for i in range(n_docs)]
         h2d = int(lens.sum())
         for _ in range(1):
             b = loro_b200.import_batch(blobs, device=local, flags=xflags)
