@@ -844,11 +844,10 @@ void lb_batch_free(lb_batch* b) {
     if (b->json_thread.joinable()) b->json_thread.join();
     if (b->json_ev) cudaEventDestroy(b->json_ev);
     if (b->stream2) cudaStreamDestroy(b->stream2);
-    if (b->dev.stream) {
-        b->dev.free_all();
+    b->dev.free_all();
+    if (b->ev_created) {   // the stream exists whenever the events do (init_batch)
         cudaStreamSynchronize(b->dev.stream);
-        if (b->ev_created)
-            for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
+        for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
         cudaStreamDestroy(b->dev.stream);
     }
     lbstage::host_cache().give(b->json);

@@ -122,7 +122,7 @@ __global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restric
         c.skip(len);
     }
     u32 err = 0;
-    if (c.err || !c.empty() || bi.n_changes == 0) err = LB_ERR(DOC_ERR_DECODE);
+    if (c.err || !c.empty() || bi.n_changes == 0 || bi.n_changes > bi.len) err = LB_ERR(DOC_ERR_DECODE);   // a change costs >= 1 byte
     bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0;
     bi.values_bytes = bi.sec_len[7];
     if (!err) {
@@ -131,17 +131,22 @@ __global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restric
         Cur h(b + bi.sec_off[0], bi.sec_len[0]);
         u64 np = h.varint();
         h.skip(8 * np);
-        for (u32 k = 0; k + 1 < N; k++) (void)h.varint();
+        for (u32 k = 0; k + 1 < N && !h.err; k++) (void)h.varint();
         u64 got = 0;
-        while (got < N && !h.err) got += h.varint();  // BoolRle run lengths
+        while (got < N && !h.err) { u64 run = h.varint(); if (run > N) { h.err = 1; break; } got += run; }  // BoolRle run lengths
         if (got != N) h.err = 1;
         got = 0;
         u64 ndeps = 0;
         while (got < N && !h.err) {  // AnyRle<usize>
             i64 sl = h.zigzag();
             if (sl == 0) { h.err = 1; break; }
-            if (sl > 0) { u64 v = h.varint(); ndeps += v * (u64)sl; got += (u64)sl; }
-            else { for (i64 k = 0; k < -sl; k++) ndeps += h.varint(); got += (u64)(-sl); }
+            if (sl > 0) { u64 v = h.varint(); if (v > 0xFFFFFFFFull || (u64)sl > N) { h.err = 1; break; } ndeps += v * (u64)sl; got += (u64)sl; }
+            else {
+                if ((u64)(-sl) > N) { h.err = 1; break; }   // a literal run longer than the change count: corrupt
+                for (i64 k = 0; k < -sl && !h.err; k++) ndeps += h.varint();
+                got += (u64)(-sl);
+            }
+            if (ndeps > 0xFFFFFFFFull) { h.err = 1; break; }
         }
         if (got != N || np == 0 || np > 0xFFF0) h.err = 1;
         bi.n_peers = (u32)np;
@@ -158,20 +163,27 @@ __global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restric
         const u8* col[4];
         u32 col_len[4];
         bool ok = columnar_open(b + bi.sec_off[5], bi.sec_len[5], 4, col, col_len);
-        u32 nops = 0, ndel = 0;
+        u64 nops = 0, ndel = 0;
         if (ok) {
             Cur v(col[2], col_len[2]);
             while (!v.empty() && !v.err) {
                 i64 sl = v.zigzag();
-                if (sl == 0) { v.err = 1; break; }
-                if (sl > 0) { u8 x = v.get(); nops += (u32)sl; if (x == VK_DELETE_SEQ) ndel += (u32)sl; }
-                else { for (i64 q = 0; q < -sl; q++) { u8 x = v.get(); if (x == VK_DELETE_SEQ) ndel++; } nops += (u32)(-sl); }
+                if (sl == 0 || sl > (i64)0x7FFFFFFF || sl < -(i64)0x7FFFFFFF) { v.err = 1; break; }
+                if (sl > 0) { u8 x = v.get(); nops += (u64)sl; if (x == VK_DELETE_SEQ) ndel += (u64)sl; }
+                else { for (i64 q = 0; q < -sl && !v.err; q++) { u8 x = v.get(); if (x == VK_DELETE_SEQ) ndel++; } nops += (u64)(-sl); }
+                if (nops > 0x7FFFFFFFull) { v.err = 1; break; }
             }
             if (v.err) ok = false;
         }
-        bi.n_ops = nops;
-        bi.n_dels = ndel;
+        bi.n_ops = (u32)nops;
+        bi.n_dels = (u32)ndel;
         if (h.err || k.err || cc.err || !ok || nops == 0) err = LB_ERR(DOC_ERR_DECODE);
+        // run-length codes let a few bytes announce billions of rows: table sizes come from these counts, so a block
+        // whose counts are out of proportion to its bytes is rejected here (one bad blob must not sink the batch).
+        // Reference blocks stay below MAX_BLOCK_SIZE of estimated content, i.e. ~1.4 k rows.
+        u64 cap = 8ull * bi.len + 64;
+        if (nops > cap || ndeps > cap || N > cap || bi.n_cids > cap || bi.counter_len > (1u << 30) || nops > bi.counter_len)
+            err = LB_ERR(DOC_ERR_DECODE);
     }
     bi.err = err;
     if (err) { bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0; bi.n_changes = 0; }
