@@ -130,10 +130,6 @@ struct Dev {  // owns every device allocation of a batch
     }
 };
 
-struct Phase {
-    cudaEvent_t ev;
-};
-
 }  // namespace
 
 struct lb_batch {

@@ -133,44 +133,3 @@ __global__ void k_frame_fill(const u8* __restrict__ bytes, const u64* __restrict
         c.skip(len);
     }
 }
-
-// ------------------------------------------------------------------ generic strided exclusive scan
-// Single CTA (1024 threads) walking the array in tiles with a running carry.  Inputs are u32 fields at
-// in + i*in_stride (bytes), outputs u64 at out + i*out_stride; out[n] (one past) receives the total.
-__global__ void k_excl_scan(const u8* __restrict__ in, size_t in_stride, u8* __restrict__ out,
-                            size_t out_stride, u64 n) {
-    __shared__ u64 warp_tot[32];
-    __shared__ u64 carry_s;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (u64 base = 0; base < n; base += blockDim.x) {
-        u64 i = base + threadIdx.x;
-        u64 v = i < n ? (u64) * (const u32*)(in + i * in_stride) : 0;
-        u64 s = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u64 t = __shfl_up_sync(LB_FULL, s, d);
-            if (lane >= d) s += t;
-        }
-        if (lane == 31) warp_tot[w] = s;
-        __syncthreads();
-        if (w == 0) {
-            u64 t = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
-            u64 ts = t;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                u64 u = __shfl_up_sync(LB_FULL, ts, d);
-                if (lane >= d) ts += u;
-            }
-            warp_tot[lane] = ts - t;  // exclusive prefix of warp totals
-        }
-        __syncthreads();
-        u64 carry = carry_s;
-        if (i < n) *(u64*)(out + i * out_stride) = carry + warp_tot[w] + s - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry_s = carry + warp_tot[w] + s;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *(u64*)(out + n * out_stride) = carry_s;
-}

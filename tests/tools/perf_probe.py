@@ -3,7 +3,7 @@ to a large batch, run the device-resident entry point a few times, print per-pha
 import sys
 import time
 import os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 
