@@ -360,6 +360,7 @@ void pipeline(lb_batch* b) {
     sp.node = dv.alloc<uint2>(NNODE * leaf_w);
     sp.node_parent = dv.alloc<u32>(NNODE);
     sp.atom_leaf = dv.alloc<u32>(NATOM);
+    CK(cudaMemsetAsync(sp.atom_leaf, 0xFF, sizeof(u32) * NATOM, st));   // LEAF_NONE everywhere
     sp.a_org = dv.alloc<uint4>(NATOM);
     sp.cvv = dv.alloc<i32>(NCVV, true);
     sp.cont_epoch = dv.alloc<u32>(NC + 1);

@@ -102,8 +102,9 @@ __device__ __forceinline__ u32 s_peer(const uint4& s) { return s.x & 0xFFFFu; }
 __device__ __forceinline__ u32 s_st(const uint4& s) { return s.x >> 16; }
 __device__ __forceinline__ i32 s_vis(const uint4& s) { return (s.x >> 16) == 0 ? (i32)s.z : 0; }
 __device__ __forceinline__ uint4 leaf_load(const SeqPools& p, const Cx& c, u32 leaf) { return p.leaf[(c.leaf0 + leaf) * 32 + c.lane]; }
-__device__ __forceinline__ void leaf_store(const SeqPools& p, const Cx& c, u32 leaf, const uint4& L) {
-    p.leaf[(c.leaf0 + leaf) * 32 + c.lane] = L;
+// slots below `from` are unchanged by the caller: only the shifted tail goes back to HBM
+__device__ __forceinline__ void leaf_store(const SeqPools& p, const Cx& c, u32 leaf, const uint4& L, int from = 0) {
+    if (c.lane >= from) p.leaf[(c.leaf0 + leaf) * 32 + c.lane] = L;
     __syncwarp();
 }
 __device__ __forceinline__ int leaf_count(const uint4& L) { return __popc(__ballot_sync(LB_FULL, s_peer(L) != PEER_NONE)); }
@@ -299,7 +300,7 @@ __device__ __noinline__ void split_before(const SeqPools& p, Cx c, u32 peer, i32
         if (lane == slot) L.z = (u32)k;                       // left part keeps its slot
         else if (lane == slot + 1) { L.x = s_x; L.y = (u32)ctr; L.z = (u32)(s_len - k); }
         else if (lane > slot + 1) { L.x = ux; L.y = uy; L.z = uz; }
-        leaf_store(p, c, leaf, L);
+        leaf_store(p, c, leaf, L, slot);
         // origins of the new span start: left origin is its predecessor, right origin is inherited
         uint4 og = p.a_org[atom_index(c, peer, s_ctr)];
         if (lane == 0) p.a_org[atom_index(c, peer, ctr)] = mk4(peer | (og.x & 0xFFFF0000u), (u32)(ctr - 1), og.z, 0);
@@ -761,7 +762,7 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
             if (lane == at - 1) L.z = (u32)off;
             if (lane == at + 1) { L.x = cur_x; L.y = (u32)(cur_ctr + off); L.z = (u32)(cur_len - off); }
         }
-        leaf_store(p, c, tgt_leaf, L);
+        leaf_store(p, c, tgt_leaf, L, at > 0 ? at - 1 : 0);
         u64 a0 = atom_index(c, peer, ctr);
         if (lane == 0) p.a_org[a0] = mk4(ol_peer | (or_peer << 16), (u32)ol_ctr, (u32)or_ctr, 0);
         if (mid && lane == 1)
@@ -924,7 +925,6 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
     sm->abase[lane] = (u32)lane < P ? c.dpeer[lane].atom_base : 0;
     if (lane == 0) sm->err = 0;
     __syncwarp();
-    for (u64 i = lane; i < di.atom_total; i += 32) pools.atom_leaf[c.atom0 + i] = LEAF_NONE;
     for (u32 ci = lane; ci < C; ci += 32) pools.cont_epoch[cid0 + ci] = 0xFFFFFFFFu;
     __syncwarp();
     u32 cidx = 0xFFFFFFFFu;
