@@ -430,7 +430,7 @@ void pipeline(lb_batch* b) {
         xt.op_kind = ct.op_kind; xt.op_cidx = ct.op_cidx; xt.op_prop = t.op_prop; xt.op_len = t.op_len;
         xt.op_counter = t.op_counter; xt.op_val_off = t.op_val_off; xt.op_val_len = t.op_val_len; xt.op_del = t.op_del;
         xt.op_aux = ct.op_aux; xt.del_counter = t.del_counter; xt.del_len = t.del_len;
-        xt.r_astart = dv.alloc<u32>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.r_flag = dv.alloc<u8>(NR);
+        xt.x_rec = dv.alloc<uint4>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.r_flag = dv.alloc<u8>(NR);
         xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_novf = dv.alloc<u32>(NCH + 1, true);
         xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
         xt.n_changes = NCH;

@@ -66,7 +66,7 @@ struct ExportTables {
     const u64* op_val_off; const u32* op_val_len; const u32* op_del; const u32* op_aux;
     const i32* del_counter; const i32* del_len;
     // per row
-    u32* r_astart;     // arena position (values: atoms, strings: bytes) relative to the document
+    uint4* x_rec;      // resolved op record per row (xop_pack): kind | reversed | container, counter, prop, arena start / target counter
     u32* r_bytes;      // text rows: payload bytes
     u8* r_flag;        // XF_*
     // per change
@@ -177,8 +177,10 @@ __device__ inline void xop_merge(XOp& a, const XOp& b) {
     a.nst += b.nst;
 }
 
-// one decoded row as an op (map keys and delete targets at document level)
-__device__ inline XOp xop_from_row(const ExportTables& t, const DocInfo& di, u32 ch, u64 row) {
+// one decoded row as an op (map keys and delete targets at document level): the resolving form walks the decode
+// tables (container type, block key arena, delete table); k_exp_changes runs it once per row and leaves a 16-byte
+// record, which is what every later pass loads (three independent loads per row instead of a chain)
+__device__ inline XOp xop_resolve(const ExportTables& t, const DocInfo& di, u32 ch, u64 row, u32 astart) {
     XOp o;
     u8 kind = t.op_kind[row];
     o.cidx = t.op_cidx[row];
@@ -189,8 +191,8 @@ __device__ inline XOp xop_from_row(const ExportTables& t, const DocInfo& di, u32
     o.st0 = (u32)row; o.nst = 1;
     switch (kind) {
         case OPK_SEQ_INS:
-            if (t.dcont[di.cid0 + o.cidx].type == CT_TEXT) { o.xk = XK_TEXT; o.f0 = t.r_astart[row]; o.f1 = o.f0 + t.r_bytes[row]; }
-            else { o.xk = XK_LIST; o.f0 = t.r_astart[row]; o.f1 = o.f0 + o.atoms; }
+            if (t.dcont[di.cid0 + o.cidx].type == CT_TEXT) { o.xk = XK_TEXT; o.f0 = astart; o.f1 = o.f0 + t.r_bytes[row]; }
+            else { o.xk = XK_LIST; o.f0 = astart; o.f1 = o.f0 + o.atoms; }
             break;
         case OPK_SEQ_DEL: {
             u32 dl = t.op_del[row];
@@ -203,6 +205,29 @@ __device__ inline XOp xop_from_row(const ExportTables& t, const DocInfo& di, u32
             break;
         default: o.xk = XK_NONE;
     }
+    return o;
+}
+__device__ __forceinline__ uint4 xop_pack(const XOp& o) {
+    uint4 r;
+    r.x = (u32)o.xk | ((o.xk == XK_DEL && o.f2 < 0) ? 8u : 0u) | (o.cidx << 4);
+    r.y = (u32)o.ctr;
+    r.z = (u32)o.prop;
+    r.w = o.xk == XK_DEL ? o.f1 : o.f0;
+    return r;
+}
+__device__ __forceinline__ XOp xop_from_row(const ExportTables& t, const DocInfo&, u32, u64 row) {
+    uint4 r = t.x_rec[row];
+    XOp o;
+    o.xk = (u8)(r.x & 7u);
+    o.cidx = r.x >> 4;
+    o.ctr = (i32)r.y;
+    o.prop = (i32)r.z;
+    o.atoms = t.op_len[row];
+    o.f0 = r.w; o.f1 = 0; o.f2 = 0;
+    o.st0 = (u32)row; o.nst = 1;
+    if (o.xk == XK_LIST) o.f1 = o.f0 + o.atoms;
+    else if (o.xk == XK_TEXT) o.f1 = o.f0 + t.r_bytes[row];
+    else if (o.xk == XK_DEL) { o.f0 = t.op_aux[row]; o.f1 = r.w; o.f2 = (r.x & 8u) ? -(i32)o.atoms : (i32)o.atoms; }
     return o;
 }
 
@@ -259,25 +284,24 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
     u64 r0 = t.ch_op0[ch];
     u32 nr = t.ch_nops[ch];
     if (pass == 0) {
-        {   // arena positions of the rows (relative to the document)
-            u32 vals = (u32)(t.ch_aval0[ch] - t.ch_aval0[di.ch0]), strs = (u32)(t.ch_astr0[ch] - t.ch_astr0[di.ch0]);
-            for (u32 r = 0; r < nr; r++) {
-                u64 row = r0 + r;
-                if (t.op_kind[row] != OPK_SEQ_INS) continue;
-                if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) { t.r_astart[row] = strs; strs += t.r_bytes[row]; }
-                else { t.r_astart[row] = vals; vals += t.op_len[row]; }
-            }
-        }
-        // intra-change merge + total estimate
+        // arena positions of the rows (relative to the document) + RleVec merge inside the change + total estimate
+        u32 vals = (u32)(t.ch_aval0[ch] - t.ch_aval0[di.ch0]), strs = (u32)(t.ch_astr0[ch] - t.ch_astr0[di.ch0]);
         XOp back;
         back.xk = XK_NONE;
         u32 est_ops = 0, nm = 0, ndel = 0, last_head = 0;
         bool bad = false;
         for (u32 r = 0; r < nr; r++) {
-            XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
+            u64 row = r0 + r;
+            u32 astart = 0;
+            if (t.op_kind[row] == OPK_SEQ_INS) {
+                if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) { astart = strs; strs += t.r_bytes[row]; }
+                else { astart = vals; vals += t.op_len[row]; }
+            }
+            XOp o = xop_resolve(t, di, (u32)ch, row, astart);
+            t.x_rec[row] = xop_pack(o);
             if (o.xk == XK_NONE) bad = true;
-            if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[r0 + r] = 0; }
-            else { back = o; est_ops += xop_estimate(o); t.r_flag[r0 + r] = XF_HEAD; nm++; ndel += o.xk == XK_DEL; last_head = r; }
+            if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[row] = 0; }
+            else { back = o; est_ops += xop_estimate(o); t.r_flag[row] = XF_HEAD; nm++; ndel += o.xk == XK_DEL; last_head = r; }
         }
         u32 ndeps = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
         u32 est0 = 4 + (ndeps > 1 ? (ndeps - 1) * 4 : 0);
