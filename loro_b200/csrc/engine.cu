@@ -5,6 +5,7 @@
 // the entry points fail with LB_ERR_NO_DEVICE.
 #include "../../include/loro_b200.h"
 
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -427,7 +428,7 @@ void pipeline(lb_batch* b) {
         xt.ch_dep0 = t.ch_dep0; xt.ch_ndeps = t.ch_ndeps; xt.ch_dep_self = t.ch_dep_self;
         xt.dep_peer_idx = t.dep_peer_idx; xt.dep_counter = t.dep_counter;
         xt.ch_msg_off = t.ch_msg_off; xt.ch_msg_len = t.ch_msg_len;
-        xt.op_kind = ct.op_kind; xt.op_cidx = ct.op_cidx; xt.op_prop = t.op_prop; xt.op_len = t.op_len;
+        xt.op_kind = ct.op_kind; xt.op_vtype = t.op_vtype; xt.op_cidx = ct.op_cidx; xt.op_prop = t.op_prop; xt.op_len = t.op_len;
         xt.op_counter = t.op_counter; xt.op_val_off = t.op_val_off; xt.op_val_len = t.op_val_len; xt.op_del = t.op_del;
         xt.op_aux = ct.op_aux; xt.del_counter = t.del_counter; xt.del_len = t.del_len;
         xt.x_rec = dv.alloc<uint4>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.r_flag = dv.alloc<u8>(NR);
@@ -570,6 +571,33 @@ lb_status run_batch(lb_batch* b) {
     return LB_OK;
 }
 
+// host-side peek at a blob (only what import_batch's ordering needs: mode and the number of changes)
+u32 blob_mode(const uint8_t* p, size_t n) { return n >= 22 ? ((u32)p[20] << 8) | p[21] : 0xFFFFu; }
+u64 blob_change_count(const uint8_t* p, size_t n) {
+    if (n < 22) return 0;
+    size_t i = 22;
+    auto varint = [&](u64* v) {
+        *v = 0;
+        for (int s = 0; s < 70 && i < n; s += 7) {
+            uint8_t c = p[i++];
+            *v |= (u64)(c & 0x7f) << (s < 64 ? s : 63);
+            if (!(c & 0x80)) return true;
+        }
+        return false;
+    };
+    u64 total = 0;
+    while (i < n) {
+        u64 len, x;
+        if (!varint(&len) || len > n - i) break;
+        size_t end = i + (size_t)len;
+        bool ok = true;
+        for (int k = 0; k < 5 && ok; k++) ok = varint(&x) && i <= end;
+        if (ok) total += x;   // the fifth varint of the envelope is n_changes
+        i = end;
+    }
+    return total;
+}
+
 lb_status check_device(const lb_options* opt) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -646,6 +674,20 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
                 u32 q = cursor[doc_idx[i]]++;
                 order[q] = (u32)i;
                 b->blob_doc[q] = doc_idx[i];
+            }
+            // import_batch imports its blobs sorted by (mode, number of changes descending), stably
+            // (loro.rs:1194-1202): the order decides where payloads land in the document's arenas, which the
+            // re-export merge rules look at
+            for (size_t d = 0; d < nd; d++) {
+                u32 q0 = b->doc_blob0[d], q1 = b->doc_blob0[d + 1];
+                if (q1 - q0 < 2) continue;
+                std::vector<std::pair<std::pair<u32, i64>, u32>> keyed;
+                for (u32 q = q0; q < q1; q++) {
+                    const lb_blob& bl = blobs[order[q]];
+                    keyed.push_back({{blob_mode(bl.ptr, bl.len), -(i64)blob_change_count(bl.ptr, bl.len)}, order[q]});
+                }
+                std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+                for (u32 q = q0; q < q1; q++) order[q] = keyed[q - q0].second;
             }
         }
         b->n_blobs = n_blobs;

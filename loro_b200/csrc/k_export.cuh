@@ -24,7 +24,9 @@
 // restated from append-only-bytes 0.1.12, same model as the oracle, unpinned by reference tests).
 // Not yet covered (lb_doc_export_updates answers LB_ERR_UNSUPPORTED for the document): a single insert larger
 // than a whole block (Op::slice inside split_change_then_insert), values containing nested maps (block-local key
-// indices inside the payload), documents with pending changes; Tree/MovableList/styles never reach this phase.
+// indices inside the payload); Tree/MovableList/styles never reach this phase.  Pending changes stay out of the
+// export but their payloads still count for the arena positions; a document built from several blobs sees them
+// in import_batch's order (the host lays them out that way).
 #pragma once
 #include "lb_defs.h"
 
@@ -62,7 +64,7 @@ struct ExportTables {
     const u32* ch_lamport; const i64* ch_ts; const u64* ch_op0; const u32* ch_nops;
     const u64* ch_dep0; const u32* ch_ndeps; const u8* ch_dep_self; const u32* dep_peer_idx; const i32* dep_counter;
     const u64* ch_msg_off; const u32* ch_msg_len;
-    const u8* op_kind; const u32* op_cidx; const i32* op_prop; const u32* op_len; const i32* op_counter;
+    const u8* op_kind; const u8* op_vtype; const u32* op_cidx; const i32* op_prop; const u32* op_len; const i32* op_counter;
     const u64* op_val_off; const u32* op_val_len; const u32* op_del; const u32* op_aux;
     const i32* del_counter; const i32* del_len;
     // per row
@@ -242,7 +244,7 @@ __global__ void k_exp_init(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
     XDoc x;
     memset(&x, 0, sizeof(x));
     if (di.code == DOC_OK) {
-        if ((di.has_unsupported & 0x7FFFFFFFu) || di.n_pending || di.n_blobs > 1) x.flags |= 1;   // import_batch sorts its blobs: arena order differs
+        if (di.has_unsupported & 0x7FFFFFFFu) x.flags |= 1;
         for (u32 b = di.b0; b < di.b1; b++)
             if (t.blocks[b].n_value_maps) x.flags |= 1;
     }
@@ -259,8 +261,13 @@ __global__ void k_exp_arena(u64 n_changes, ExportTables t, const DocInfo* __rest
         u32 nr = t.ch_nops[ch];
         for (u32 r = 0; r < nr; r++) {
             u64 row = r0 + r;
-            if (t.op_kind[row] != OPK_SEQ_INS) continue;   // rows of pending changes are OPK_SKIP: not exported
-            if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) {
+            // every decoded op allocates, applied or still pending (decode precedes the pending check:
+            // encoding.rs:232-270), so the op class is taken from (container type, value kind), not from op_kind
+            u8 ctype = t.dcont[di.cid0 + t.op_cidx[row]].type;
+            u8 vt = t.op_vtype[row];
+            bool ins = (ctype == CT_TEXT && vt == VK_STR) || (ctype == CT_LIST && vt == VK_LORO_VALUE);
+            if (!ins) continue;
+            if (ctype == CT_TEXT) {
                 Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
                 u32 n = (u32)c.varint();
                 t.r_bytes[row] = n;

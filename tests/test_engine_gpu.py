@@ -204,6 +204,40 @@ def test_export_automerge_trace(golden_dir):
     check_export_against_oracle([blob])
 
 
+def test_export_with_pending_changes_and_after_import_batch():
+    import random
+    import loro_b200
+    from loro_b200 import api
+    from tests.test_engine_emu import _per_peer_blobs
+
+    def change_num(blob):
+        return sum(b["n_changes"] for b in oracle.decode_dump(blob)["blocks"])
+
+    singles, single_refs, groups, ids, group_refs = [], [], [], [], []
+    for k, seed in enumerate(range(3300, 3316)):
+        whole, js, tot, parts = _per_peer_blobs(seed, n_sites=2 + seed % 3, n_ops=200)
+        for p in parts:
+            ref = OracleDoc(5)
+            ref.import_(p)
+            singles.append(p)
+            single_refs.append(ref.export_updates())
+        random.Random(seed).shuffle(parts)
+        if seed % 2:
+            parts.append(parts[0])
+        ref = OracleDoc(5)
+        for p in sorted(parts, key=lambda p: -change_num(p)):
+            ref.import_(p)
+        groups += parts
+        ids += [k] * len(parts)
+        group_refs.append((ref.json_text(), ref.export_updates()))
+    b = loro_b200.import_batch(singles, flags=api.LB_FLAG_EXPORT)
+    for i in range(len(singles)):
+        assert b.export_updates(i) == single_refs[i], i
+    g = loro_b200.import_batch(groups, doc_ids=ids, flags=api.LB_FLAG_EXPORT)
+    for k, (js, ex) in enumerate(group_refs):
+        assert g.json_bytes(k) == js and g.export_updates(k) == ex, k
+
+
 def test_export_unsupported_is_reported_not_guessed():
     import loro_b200
     from loro_b200 import api

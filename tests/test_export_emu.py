@@ -88,3 +88,35 @@ def test_export_needs_flag_and_reports_unsupported():
     assert "does not cover" in str(e.value)
     ref = OracleDoc(9); ref.import_(small)
     assert batch.export_updates(1) == ref.export_updates()
+
+
+def test_export_with_pending_changes_and_after_import_batch():
+    """Pending changes stay out of the export but their payloads still moved the arenas; a document built from
+    several blobs is exported as the reference would after import_batch (blobs sorted by change count first)."""
+    import random
+    import loro_b200
+    import oracle
+    from loro_b200 import api
+    from tests.test_engine_emu import _per_peer_blobs
+
+    def change_num(blob):
+        return sum(b["n_changes"] for b in oracle.decode_dump(blob)["blocks"])
+
+    for seed in range(3300, 3306):
+        whole, js, tot, parts = _per_peer_blobs(seed, n_sites=3, n_ops=200)
+        # one per-peer blob alone: whatever depends on the other peers stays pending
+        b = loro_b200.import_batch(parts, flags=api.LB_FLAG_EXPORT, lib_path=EMU)
+        for i, p in enumerate(parts):
+            ref = OracleDoc(5)
+            ref.import_(p)
+            assert b.export_updates(i) == ref.export_updates(), (seed, i)
+        # all of them into one document, shuffled, sometimes with a duplicate
+        random.Random(seed).shuffle(parts)
+        if seed % 2:
+            parts.append(parts[0])
+        ref = OracleDoc(5)
+        for p in sorted(parts, key=lambda p: -change_num(p)):    # loro.rs:1198-1202 (stable)
+            ref.import_(p)
+        g = loro_b200.import_batch(parts, doc_ids=[1] * len(parts), flags=api.LB_FLAG_EXPORT, lib_path=EMU)
+        assert g.json_bytes(0) == ref.json_text()
+        assert g.export_updates(0) == ref.export_updates(), seed
