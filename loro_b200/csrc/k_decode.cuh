@@ -13,7 +13,32 @@
 
 // ---- skip one LoroValue (kind byte already consumed) ; iterative, bounded depth
 // reference: value.rs:620-700 read_value_content
+// scalar LoroValue kinds (everything but List / Map): skipped without the explicit stack
+__device__ __forceinline__ bool skip_loro_scalar(Cur& c, u8 kind, u32* n_child_containers) {
+    switch (kind) {
+        case 0: case 1: case 2: return true;
+        case 3: (void)c.sleb(); return true;
+        case 4: c.skip(8); return true;
+        case 5: case 6: { u64 n = c.varint(); c.skip(n); return true; }
+        case 9: (void)c.get(); if (n_child_containers) (*n_child_containers)++; return true;
+        default: return false;
+    }
+}
 __device__ inline void skip_loro_value_content(Cur& c, u8 kind, u32* n_child_containers, u32* n_maps = nullptr) {
+    // fast paths: a scalar, or a list of scalars (what a List insert carries) -- no stack, no local memory
+    if (skip_loro_scalar(c, kind, n_child_containers)) return;
+    if (kind == 7) {
+        Cur save = c;
+        u64 n = c.varint();
+        bool flat = n <= (1u << 28);
+        u32 kids = 0;
+        for (u64 i = 0; flat && i < n && !c.err; i++) {
+            u8 k = c.get();
+            if (!skip_loro_scalar(c, k, &kids)) flat = false;
+        }
+        if (flat) { if (n_child_containers) *n_child_containers += kids; return; }
+        c = save;          // nested content: start over on the general path
+    }
     // stack of remaining item counts; bit 31 marks a map level (items carry a key index)
     u32 stack[24];
     int sp = 0;
