@@ -435,6 +435,8 @@ void pipeline(lb_batch* b) {
         xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_novf = dv.alloc<u32>(NCH + 1, true);
         xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
         xt.n_changes = NCH;
+        xt.n_rows = NR;
+        xt.ch_syn = dv.alloc<u32>(NCH + 1, true); xt.ch_syn0 = dv.alloc<u64>(NCH + 2, true);
         xt.xdoc = dv.alloc<XDoc>(D + 1, true);
         b->d_xdoc = xt.xdoc;
         xt.ch_aval = dv.alloc<u32>(NCH + 1, true); xt.ch_astr = dv.alloc<u32>(NCH + 1, true);
@@ -454,8 +456,11 @@ void pipeline(lb_batch* b) {
         run_scans(b, {ScanJob{(const u8*)xt.ch_aval, (u8*)xt.ch_aval0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_astr, (u8*)xt.ch_astr0, 4, 8, NCH}});
         if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
         tm.kernel_launches += 3;
-        run_scans(b, {ScanJob{(const u8*)xt.ch_novf, (u8*)xt.ch_seg0, 4, 8, NCH}});
+        run_scans(b, {ScanJob{(const u8*)xt.ch_novf, (u8*)xt.ch_seg0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_syn, (u8*)xt.ch_syn0, 4, 8, NCH}});
         u64 NOVF = d2h_one(b, xt.ch_seg0 + NCH);
+        u64 NSYN = d2h_one(b, xt.ch_syn0 + NCH);
+        xt.s_rec = dv.alloc<uint4>(NSYN); xt.s_len = dv.alloc<u32>(NSYN); xt.s_bytes = dv.alloc<u32>(NSYN);
+        xt.s_flag = dv.alloc<u8>(NSYN); xt.s_voff = dv.alloc<u64>(NSYN); xt.s_vlen = dv.alloc<u32>(NSYN); xt.s_aux = dv.alloc<u32>(NSYN);
         if (NCH + NOVF > SEGCAP) {   // unusually many split changes: grow the tables, keep what pass 0 wrote
             u64 cap = NCH + NOVF;
             u32** sgs[9] = {&xt.sg_src, &xt.sg_r0, &xt.sg_from, &xt.sg_atoms, &xt.sg_est, &xt.sg_nmops, &xt.sg_ndel, &xt.sg_nrows, &xt.sg_last_head};

@@ -11,7 +11,8 @@
 //
 // What the imported document's change store looks like is re-derived from the decoded tables:
 //   A  (thread per change) ops of each decoded change go through the RleVec merge (block_encode.rs:651); a change
-//      whose size estimate exceeds one block is cut into segments at op boundaries (split_change_then_insert);
+//      whose size estimate exceeds one block is cut into segments (split_change_then_insert), List / Text inserts
+//      that do not fit a block are themselves cut (Op::slice) -- such a change is re-written as synthetic rows;
 //   B  (thread per document, per peer in id order) the segments enter the store in counter order
 //      (ChangeStore::insert_change, merge_interval 0 for imports), and what comes out is pushed, as it completes,
 //   C  into the fresh store export builds (export_blocks_from): same rules, freshly computed sizes.
@@ -22,9 +23,8 @@
 // arenas (arena.rs:237-263): values are adjacent when nothing else was allocated in between (decode order),
 // strings additionally need the append-only buffer not to have been reallocated (capacity doubles from 32;
 // restated from append-only-bytes 0.1.12, same model as the oracle, unpinned by reference tests).
-// Not yet covered (lb_doc_export_updates answers LB_ERR_UNSUPPORTED for the document): a single insert larger
-// than a whole block (Op::slice inside split_change_then_insert), values containing nested maps (block-local key
-// indices inside the payload); Tree/MovableList/styles never reach this phase.  Pending changes stay out of the
+// Not yet covered (lb_doc_export_updates answers LB_ERR_UNSUPPORTED for the document): values containing nested
+// maps (block-local key indices inside the payload); Tree/MovableList/styles never reach this phase.  Pending changes stay out of the
 // export but their payloads still count for the arena positions; a document built from several blobs sees them
 // in import_batch's order (the host lays them out that way).
 #pragma once
@@ -74,6 +74,10 @@ struct ExportTables {
     // per change
     u32* ch_nseg;      // segments the change enters the store as (0 = not applied)
     u32* ch_novf;      // nseg - 1 (scan input): only split changes need slots beyond their own
+    // changes whose split cuts an op (Op::slice, list_op.rs:603-658) get SYNTHETIC rows: one per source row or slice,
+    // addressed as row = n_rows + ch_syn0[ch] + i; every row accessor below understands both spaces
+    u32* ch_syn; u64* ch_syn0; u64 n_rows;
+    uint4* s_rec; u32* s_len; u32* s_bytes; u8* s_flag; u64* s_voff; u32* s_vlen; u32* s_aux;
     u64 n_changes;     // segment q of change ch lives at q == 0 ? ch : n_changes + ch_seg0[ch] + q - 1
     u32* ch_aval; u32* ch_astr; u64* ch_aval0; u64* ch_astr0;   // arena sums per change + their scans
     u64* ch_seg0;      // scan of ch_novf
@@ -110,6 +114,7 @@ __device__ __forceinline__ u32 varint_len(u64 v) { u32 k = 1; while (v >= 0x80) 
 // ---------------------------------------------------------------------------------------------- merge rules
 struct XOp {   // one (possibly merged) op: the fields the merge rules and the encoder need
     u8 xk; u32 cidx; i32 ctr; u32 atoms; i32 prop; u32 f0, f1; i32 f2; u32 st0, nst;
+    u32 g;   // TEXT: generation of the string arena buffer when the op's payload was allocated
     // LIST/TEXT: f0 = arena start, f1 = arena end (TEXT: bytes; f1 - f0 = payload bytes)
     // DEL: f0 = target peer (doc-level), f1 = lowest target counter, f2 = signed length
 };
@@ -138,7 +143,7 @@ __device__ inline bool xop_mergable(const XOp& a, const XOp& b) {   // op.rs:143
     if (a.ctr + (i32)a.atoms != b.ctr || a.cidx != b.cidx || a.xk != b.xk) return false;
     switch (a.xk) {
         case XK_LIST: return (i64)a.prop + a.atoms == b.prop && a.f1 == b.f0;
-        case XK_TEXT: return (i64)a.prop + a.atoms == b.prop && a.f1 == b.f0 && str_gen(a.f1) == str_gen(b.f1);
+        case XK_TEXT: return (i64)a.prop + a.atoms == b.prop && a.f1 == b.f0 && a.g == b.g;
         case XK_DEL: {
             if (a.f0 != b.f0) return false;    // ids of different peers never line up
             bool ab = d_bidi(a), bb = d_bidi(b);
@@ -189,11 +194,11 @@ __device__ inline XOp xop_resolve(const ExportTables& t, const DocInfo& di, u32 
     o.ctr = t.op_counter[row];
     o.atoms = t.op_len[row];
     o.prop = t.op_prop[row];
-    o.f0 = o.f1 = 0; o.f2 = 0;
+    o.f0 = o.f1 = 0; o.f2 = 0; o.g = 0;
     o.st0 = (u32)row; o.nst = 1;
     switch (kind) {
         case OPK_SEQ_INS:
-            if (t.dcont[di.cid0 + o.cidx].type == CT_TEXT) { o.xk = XK_TEXT; o.f0 = astart; o.f1 = o.f0 + t.r_bytes[row]; }
+            if (t.dcont[di.cid0 + o.cidx].type == CT_TEXT) { o.xk = XK_TEXT; o.f0 = astart; o.f1 = o.f0 + t.r_bytes[row]; o.g = str_gen(o.f1); }
             else { o.xk = XK_LIST; o.f0 = astart; o.f1 = o.f0 + o.atoms; }
             break;
         case OPK_SEQ_DEL: {
@@ -217,20 +222,54 @@ __device__ __forceinline__ uint4 xop_pack(const XOp& o) {
     r.w = o.xk == XK_DEL ? o.f1 : o.f0;
     return r;
 }
+// ---- row accessors: decoded rows [0, n_rows) and synthetic rows [n_rows, ...)
+__device__ __forceinline__ uint4 xr_rec(const ExportTables& t, u64 row) { return row < t.n_rows ? t.x_rec[row] : t.s_rec[row - t.n_rows]; }
+__device__ __forceinline__ u32 xr_len(const ExportTables& t, u64 row) { return row < t.n_rows ? t.op_len[row] : t.s_len[row - t.n_rows]; }
+__device__ __forceinline__ u32 xr_bytes(const ExportTables& t, u64 row) { return row < t.n_rows ? t.r_bytes[row] : t.s_bytes[row - t.n_rows]; }
+__device__ __forceinline__ u32 xr_aux(const ExportTables& t, u64 row) { return row < t.n_rows ? t.op_aux[row] : t.s_aux[row - t.n_rows]; }
+__device__ __forceinline__ u8* xr_flagp(const ExportTables& t, u64 row) { return row < t.n_rows ? &t.r_flag[row] : &t.s_flag[row - t.n_rows]; }
+__device__ __forceinline__ u8 xr_flag(const ExportTables& t, u64 row) { return *xr_flagp(t, row); }
+// the rows of a change as the export sees them
+__device__ __forceinline__ void change_rows(const ExportTables& t, u32 ch, u64* row0, u32* nr) {
+    u32 ns = t.ch_syn[ch];
+    if (ns) { *row0 = t.n_rows + t.ch_syn0[ch]; *nr = ns; }
+    else { *row0 = t.ch_op0[ch]; *nr = t.ch_nops[ch]; }
+}
+// payload bytes a row contributes to the values section (items of a list insert, text bytes, a whole map value)
+__device__ __forceinline__ void xr_payload(const ExportTables& t, u64 row, u32 xk, const u8** p, u32* n) {
+    if (row >= t.n_rows) { *p = t.bytes + t.s_voff[row - t.n_rows]; *n = t.s_vlen[row - t.n_rows]; return; }
+    const u8* v = t.bytes + t.op_val_off[row];
+    u32 vl = t.op_val_len[row];
+    if (xk == XK_LIST) { u32 skip = 1 + varint_len(t.op_len[row]); *p = v + skip; *n = vl - skip; }   // `07` + item count
+    else if (xk == XK_TEXT) { u32 nb = t.r_bytes[row]; *p = v + varint_len(nb); *n = nb; }
+    else if (xk == XK_MAPSET) { *p = v; *n = vl; }
+    else { *p = v; *n = 0; }
+}
 __device__ __forceinline__ XOp xop_from_row(const ExportTables& t, const DocInfo&, u32, u64 row) {
-    uint4 r = t.x_rec[row];
+    uint4 r = xr_rec(t, row);
     XOp o;
     o.xk = (u8)(r.x & 7u);
     o.cidx = r.x >> 4;
     o.ctr = (i32)r.y;
     o.prop = (i32)r.z;
-    o.atoms = t.op_len[row];
-    o.f0 = r.w; o.f1 = 0; o.f2 = 0;
+    o.atoms = xr_len(t, row);
+    o.f0 = r.w; o.f1 = 0; o.f2 = 0; o.g = 0;
     o.st0 = (u32)row; o.nst = 1;
     if (o.xk == XK_LIST) o.f1 = o.f0 + o.atoms;
-    else if (o.xk == XK_TEXT) o.f1 = o.f0 + t.r_bytes[row];
-    else if (o.xk == XK_DEL) { o.f0 = t.op_aux[row]; o.f1 = r.w; o.f2 = (r.x & 8u) ? -(i32)o.atoms : (i32)o.atoms; }
+    else if (o.xk == XK_TEXT) { o.f1 = o.f0 + xr_bytes(t, row); o.g = row < t.n_rows ? str_gen(o.f1) : xr_aux(t, row); }
+    else if (o.xk == XK_DEL) { o.f0 = xr_aux(t, row); o.f1 = r.w; o.f2 = (r.x & 8u) ? -(i32)o.atoms : (i32)o.atoms; }
     return o;
+}
+// byte offset of unicode scalar value k inside a UTF-8 payload of nb bytes holding n scalar values
+__device__ inline u32 text_byte_index(const u8* p, u32 nb, u32 n, u32 k) {
+    if (nb == n || k == 0) return k < nb ? k : nb;   // ASCII
+    u32 i = 0, ch = 0;
+    while (i < nb && ch < k) {
+        i++;
+        while (i < nb && (p[i] & 0xC0) == 0x80) i++;
+        ch++;
+    }
+    return i;
 }
 
 // ---------------------------------------------------------------------------------------------- X1: arenas
@@ -280,16 +319,128 @@ __global__ void k_exp_arena(u64 n_changes, ExportTables t, const DocInfo* __rest
 }
 
 // ---------------------------------------------------------------------------------------------- A: per change
-// thread per change.  pass 0: RleVec merge inside the change (XF_HEAD), split into segments (XF_SEG), segment count.
-// pass 1: one summary record per segment.
+// split_change_then_insert (change_store.rs:913-1000) for one change whose estimate exceeds a block: walks the
+// merged ops, cuts List / Text inserts that do not fit (Op::slice) and reports every piece -- atoms [a,b) of source
+// row `row`, whether it starts an op and whether it starts a segment -- to `emit`.
+struct XSplit { u32 nseg, nsyn; bool sliced; };
+template <class Emit>
+__device__ inline XSplit split_change(const ExportTables& t, const DocInfo& di, u32 ch, u64 r0, u32 nr, u32 est0, Emit emit) {
+    XSplit out;
+    out.nseg = 0; out.nsyn = 0; out.sliced = false;
+    u64 est = est0;
+    bool has_ops = false, seg_next = true;
+    u32 r = 0;
+    while (r < nr) {
+        // the merged op: rows [r, r1)
+        XOp o = xop_from_row(t, di, ch, r0 + r);
+        u32 r1 = r + 1;
+        while (r1 < nr && !(t.r_flag[r0 + r1] & XF_HEAD)) { xop_merge(o, xop_from_row(t, di, ch, r0 + r1)); r1++; }
+        const bool ins = o.xk == XK_LIST || o.xk == XK_TEXT;
+        const u32 total_bytes = o.xk == XK_TEXT ? o.f1 - o.f0 : 0;
+        u32 done = 0, done_bytes = 0;          // atoms / text bytes of this op already handed out
+        u32 cr = r, coff = 0;                  // source row and atom offset where the rest of the op starts
+        // hand out the next `count` atoms as one op
+        auto piece = [&](u32 count) {
+            bool head = true;
+            while (count) {
+                u32 ra = t.op_len[r0 + cr];
+                u32 take = ra - coff < count ? ra - coff : count;
+                u32 pb = 0;
+                if (o.xk == XK_TEXT) {
+                    const u8* pp; u32 pn;
+                    xr_payload(t, r0 + cr, XK_TEXT, &pp, &pn);
+                    pb = text_byte_index(pp, pn, ra, coff + take) - text_byte_index(pp, pn, ra, coff);
+                }
+                emit(r0 + cr, coff, coff + take, head, head && seg_next);
+                if (head && seg_next) { out.nseg++; seg_next = false; }
+                out.nsyn++;
+                head = false;
+                done += take;
+                done_bytes += pb;
+                count -= take;
+                coff += take;
+                if (coff == ra) { cr++; coff = 0; }
+            }
+            has_ops = true;
+        };
+        auto flush = [&]() { if (has_ops) { seg_next = true; est = 4; has_ops = false; } };
+        auto rest_size = [&]() -> u64 { return o.xk == XK_TEXT ? total_bytes - done_bytes : (o.xk == XK_LIST ? 4ull * (o.atoms - done) : xop_estimate(o)); };
+        if (rest_size() >= (u64)LB_MAX_BLOCK_SIZE - est) flush();
+        bool consumed = false;
+        while (true) {
+            u64 room = (u64)LB_MAX_BLOCK_SIZE - est;
+            if (rest_size() <= room || !ins) break;
+            u32 rem = o.atoms - done;
+            u64 end = o.xk == XK_TEXT ? (room < rem ? room : rem) : (room / 4 < rem ? room / 4 : rem);
+            if (end == 0) break;
+            out.sliced = true;
+            piece((u32)end);
+            flush();
+            if (done >= o.atoms) { consumed = true; break; }
+        }
+        if (!consumed) {
+            if (!ins) {
+                // ops that are never cut are copied row by row (a merged delete span keeps its rows)
+                est += rest_size();
+                if (est > LB_MAX_BLOCK_SIZE && has_ops) flush();
+                for (u32 q = r; q < r1; q++) {
+                    bool head = q == r;
+                    emit(r0 + q, 0, t.op_len[r0 + q], head, head && seg_next);
+                    if (head && seg_next) { out.nseg++; seg_next = false; }
+                    out.nsyn++;
+                }
+                has_ops = true;
+            } else {
+                est += rest_size();
+                if (est > LB_MAX_BLOCK_SIZE && has_ops) flush();
+                piece(o.atoms - done);
+            }
+        }
+        r = r1;
+    }
+    return out;
+}
+
+// one summary record per segment of a change whose rows (decoded or synthetic) carry XF_HEAD / XF_SEG
+__device__ inline void segment_summaries(const ExportTables& t, const DocInfo& di, u32 ch) {
+    u64 row0;
+    u32 nr;
+    change_rows(t, ch, &row0, &nr);
+    u64 sg_next = t.n_changes + t.ch_seg0[ch];
+    u64 sg = ch;
+    u32 r = 0, from = 0;
+    while (r < nr) {
+        u32 r_start = r, est = 0, nm = 0, ndel = 0, atoms = 0, last_head = r;
+        do {
+            XOp o = xop_from_row(t, di, ch, row0 + r);
+            last_head = r;
+            u32 r1 = r + 1;
+            while (r1 < nr && !(xr_flag(t, row0 + r1) & (XF_HEAD | XF_SEG))) { xop_merge(o, xop_from_row(t, di, ch, row0 + r1)); r1++; }
+            est += xop_estimate(o);
+            nm++;
+            ndel += o.xk == XK_DEL;
+            atoms += o.atoms;
+            r = r1;
+        } while (r < nr && !(xr_flag(t, row0 + r) & XF_SEG));
+        t.sg_src[sg] = ch; t.sg_r0[sg] = r_start; t.sg_from[sg] = from; t.sg_atoms[sg] = atoms; t.sg_est[sg] = est;
+        t.sg_nmops[sg] = nm; t.sg_ndel[sg] = ndel; t.sg_nrows[sg] = r - r_start; t.sg_last_head[sg] = last_head;
+        from += atoms;
+        sg = sg_next++;
+    }
+}
+
+// thread per change.  pass 0: per-row records, RleVec merge inside the change (XF_HEAD), segment count (XF_SEG marks
+// when no op has to be cut, a synthetic-row count otherwise).  pass 1 (split changes only): synthetic rows, summaries.
 __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
     u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_changes) return;
-    if (!t.ch_applied[ch]) { if (!pass) t.ch_nseg[ch] = 0; return; }
+    if (!t.ch_applied[ch]) { if (!pass) { t.ch_nseg[ch] = 0; t.ch_syn[ch] = 0; } return; }
     u32 doc = t.blocks[t.ch_block[ch]].doc;
     const DocInfo& di = docs[doc];
     u64 r0 = t.ch_op0[ch];
     u32 nr = t.ch_nops[ch];
+    u32 ndeps = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
+    u32 est0 = 4 + (ndeps > 1 ? (ndeps - 1) * 4 : 0);
     if (pass == 0) {
         // arena positions of the rows (relative to the document) + RleVec merge inside the change + total estimate
         u32 vals = (u32)(t.ch_aval0[ch] - t.ch_aval0[di.ch0]), strs = (u32)(t.ch_astr0[ch] - t.ch_astr0[di.ch0]);
@@ -310,34 +461,18 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
             if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[row] = 0; }
             else { back = o; est_ops += xop_estimate(o); t.r_flag[row] = XF_HEAD; nm++; ndel += o.xk == XK_DEL; last_head = r; }
         }
-        u32 ndeps = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
-        u32 est0 = 4 + (ndeps > 1 ? (ndeps - 1) * 4 : 0);
-        u32 nseg = 1;
-        t.r_flag[r0] |= XF_SEG;
+        u32 nseg = 1, nsyn = 0;
+        t.ch_syn[ch] = 0;   // (xop_from_row below must see the decoded rows)
         if (est0 + est_ops > LB_MAX_BLOCK_SIZE) {
-            // split_change_then_insert (change_store.rs:913-1000): walk the merged ops
-            u64 est = est0;
-            bool has_ops = false;
-            u32 r = 0;
-            while (r < nr) {
-                XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
-                u32 r1 = r + 1;
-                while (r1 < nr && !(t.r_flag[r0 + r1] & XF_HEAD)) { xop_merge(o, xop_from_row(t, di, (u32)ch, r0 + r1)); r1++; }
-                u64 sz = xop_estimate(o);
-                if (sz >= (u64)LB_MAX_BLOCK_SIZE - est && has_ops) { t.r_flag[r0 + r] |= XF_SEG; nseg++; est = 4; has_ops = false; }
-                u64 room = (u64)LB_MAX_BLOCK_SIZE - est;
-                if (sz > room && (o.xk == XK_LIST || o.xk == XK_TEXT)) {
-                    u64 end = o.xk == XK_TEXT ? (room < o.atoms ? room : o.atoms) : (room / 4 < o.atoms ? room / 4 : o.atoms);
-                    if (end != 0) bad = true;   // the op itself would be sliced
-                }
-                est += sz;
-                if (est > LB_MAX_BLOCK_SIZE && has_ops) { t.r_flag[r0 + r] |= XF_SEG; nseg++; est = 4; }
-                has_ops = true;
-                r = r1;
-            }
-        }
+            XSplit sp = split_change(t, di, (u32)ch, r0, nr, est0, [&](u64 row, u32 a, u32, bool, bool seg) {
+                if (seg && a == 0) t.r_flag[row] |= XF_SEG;   // valid when nothing gets cut (else the synthetic rows carry it)
+            });
+            nseg = sp.nseg;
+            if (sp.sliced && nseg > 1) nsyn = sp.nsyn;   // (a lone "slice" that is the whole op changes nothing)
+        } else t.r_flag[r0] |= XF_SEG;
         t.ch_nseg[ch] = nseg;
         t.ch_novf[ch] = nseg - 1;
+        t.ch_syn[ch] = nsyn;
         if (nseg == 1) {   // the common case: the change is its own (only) segment, summarised right here
             t.sg_src[ch] = (u32)ch; t.sg_r0[ch] = 0; t.sg_from[ch] = 0; t.sg_atoms[ch] = t.ch_len[ch]; t.sg_est[ch] = est_ops;
             t.sg_nmops[ch] = nm; t.sg_ndel[ch] = ndel; t.sg_nrows[ch] = nr; t.sg_last_head[ch] = last_head;
@@ -345,30 +480,46 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
         if (bad) atomicOr(&t.xdoc[doc].flags, 1u);
         return;
     }
-    // pass 1 (split changes only): segment summaries
+    // pass 1 (split changes only)
     if (t.ch_nseg[ch] <= 1) return;
-    u64 sg_next = t.n_changes + t.ch_seg0[ch];
-    u64 sg = ch;
-    u32 r = 0;
-    u32 from = 0;
-    while (r < nr) {
-        u32 r_start = r, est = 0, nm = 0, ndel = 0, atoms = 0, last_head = r;
-        do {
-            XOp o = xop_from_row(t, di, (u32)ch, r0 + r);
-            last_head = r;
-            u32 r1 = r + 1;
-            while (r1 < nr && !(t.r_flag[r0 + r1] & XF_HEAD)) { xop_merge(o, xop_from_row(t, di, (u32)ch, r0 + r1)); r1++; }
-            est += xop_estimate(o);
-            nm++;
-            ndel += o.xk == XK_DEL;
-            atoms += o.atoms;
-            r = r1;
-        } while (r < nr && !(t.r_flag[r0 + r] & XF_SEG));
-        t.sg_src[sg] = (u32)ch; t.sg_r0[sg] = r_start; t.sg_from[sg] = from; t.sg_atoms[sg] = atoms; t.sg_est[sg] = est;
-        t.sg_nmops[sg] = nm; t.sg_ndel[sg] = ndel; t.sg_nrows[sg] = r - r_start; t.sg_last_head[sg] = last_head;
-        from += atoms;
-        sg = sg_next++;
+    u32 nsyn = t.ch_syn[ch];
+    if (nsyn) {
+        // materialise the synthetic rows: a copy of every untouched row, one row per slice of a cut insert
+        u64 s0 = t.ch_syn0[ch];
+        u32 w = 0;
+        t.ch_syn[ch] = 0;   // the walk reads the decoded rows
+        split_change(t, di, (u32)ch, r0, nr, est0, [&](u64 row, u32 a, u32 b, bool head, bool seg) {
+            u64 i = s0 + w++;
+            uint4 rec = t.x_rec[row];
+            u32 xk = rec.x & 7u;
+            u32 ra = t.op_len[row];
+            const u8* pp; u32 pn;
+            xr_payload(t, row, xk, &pp, &pn);
+            u32 b0 = 0, b1 = pn;
+            if (xk == XK_TEXT) { b0 = text_byte_index(pp, pn, ra, a); b1 = text_byte_index(pp, pn, ra, b); }
+            else if (xk == XK_LIST && (a != 0 || b != ra)) {   // byte span of items [a,b)
+                Cur c(pp, pn);
+                for (u32 k = 0; k < a && !c.err; k++) { u8 kk = c.get(); skip_loro_value_content(c, kk, nullptr); }
+                b0 = (u32)(c.p - pp);
+                for (u32 k = a; k < b && !c.err; k++) { u8 kk = c.get(); skip_loro_value_content(c, kk, nullptr); }
+                b1 = (u32)(c.p - pp);
+            }
+            if (xk == XK_LIST || xk == XK_TEXT) {
+                rec.y += a;                                   // counter
+                rec.z += a;                                   // position
+                rec.w += xk == XK_TEXT ? b0 : a;              // arena start
+            }
+            t.s_rec[i] = rec;
+            t.s_len[i] = b - a;
+            t.s_bytes[i] = xk == XK_TEXT ? b1 - b0 : 0;
+            t.s_voff[i] = (u64)(pp - t.bytes) + b0;
+            t.s_vlen[i] = b1 - b0;
+            t.s_aux[i] = xk == XK_TEXT ? str_gen(t.x_rec[row].w + t.r_bytes[row]) : t.op_aux[row];
+            t.s_flag[i] = (head ? XF_HEAD : 0) | (seg ? XF_SEG : 0);
+        });
+        t.ch_syn[ch] = nsyn;
     }
+    segment_summaries(t, di, (u32)ch);
 }
 
 // ---------------------------------------------------------------------------------------------- B + C: the stores
@@ -402,29 +553,27 @@ __device__ __forceinline__ u32 xentry_ndeps(const ExportTables& t, const XEntry&
 struct XRows {
     const ExportTables& t; u32 pos; u32 r; u32 ch; u32 nr; u64 row0;
     __device__ XRows(const ExportTables& t_, u32 pos_, u32 r_) : t(t_), pos(pos_), r(r_) { load(); }
-    __device__ void load() { ch = t.ch_order[pos]; nr = t.ch_nops[ch]; row0 = t.ch_op0[ch]; }
+    __device__ void load() { ch = t.ch_order[pos]; change_rows(t, ch, &row0, &nr); }
     __device__ u64 row() const { return row0 + r; }
     __device__ void next() {
         r++;
-        while (r >= nr) { pos++; r = 0; ch = t.ch_order[pos]; if (!t.ch_applied[ch]) { nr = 0; continue; } nr = t.ch_nops[ch]; row0 = t.ch_op0[ch]; }
+        while (r >= nr) { pos++; r = 0; ch = t.ch_order[pos]; if (!t.ch_applied[ch]) { nr = 0; continue; } change_rows(t, ch, &row0, &nr); }
     }
 };
 // accumulate the merged op that starts at the cursor (consumes its rows, at most `left` of them)
 // bytes one row contributes to the values section of a (merged) op, without the op's own prefix
 __device__ __forceinline__ u32 row_value_bytes(const ExportTables& t, const XOp& o, u64 row) {
-    switch (o.xk) {
-        case XK_LIST: return t.op_val_len[row] - 1 - varint_len(t.op_len[row]);   // minus `07` + item count
-        case XK_TEXT: return t.r_bytes[row];
-        case XK_MAPSET: return t.op_val_len[row];
-        default: return 0;
-    }
+    const u8* p;
+    u32 n;
+    xr_payload(t, row, o.xk, &p, &n);
+    return n;
 }
 __device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows& it, u32& left, u32* vbytes = nullptr) {
     XOp o = xop_from_row(t, di, it.ch, it.row());
     if (vbytes) *vbytes += row_value_bytes(t, o, it.row());
     left--;
     if (left) it.next();
-    while (left && !(t.r_flag[it.row()] & XF_HEAD)) {
+    while (left && !(xr_flag(t, it.row()) & XF_HEAD)) {
         if (vbytes) *vbytes += row_value_bytes(t, o, it.row());
         xop_merge(o, xop_from_row(t, di, it.ch, it.row()));
         left--;
@@ -435,11 +584,12 @@ __device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows
 // last op of an entry that came straight from stage A: from its head row to the end of its segment
 __device__ inline XOp xentry_last_op(const ExportTables& t, const DocInfo& di, const XEntry& E) {
     if (E.last_valid) return E.last;
-    u64 row0 = t.ch_op0[E.lh_ch];
-    u32 nr = t.ch_nops[E.lh_ch];
+    u64 row0;
+    u32 nr;
+    change_rows(t, E.lh_ch, &row0, &nr);
     XOp o = xop_from_row(t, di, E.lh_ch, row0 + E.lh_row);
     u32 r = E.lh_row + 1;
-    while (r < nr && !(t.r_flag[row0 + r] & (XF_HEAD | XF_SEG))) { xop_merge(o, xop_from_row(t, di, E.lh_ch, row0 + r)); r++; }
+    while (r < nr && !(xr_flag(t, row0 + r) & (XF_HEAD | XF_SEG))) { xop_merge(o, xop_from_row(t, di, E.lh_ch, row0 + r)); r++; }
     return o;
 }
 // ChangeStore::insert_change + ChangesBlock::push_change (change_store.rs:711-764, 1244-1291): E is the next change
@@ -471,7 +621,7 @@ __device__ inline bool xstore_push(const ExportTables& t, const DocInfo& di, XSt
                 merged_sz += xop_estimate(o);
                 merged_del += o.xk == XK_DEL;
                 xop_merge(s.back, o);
-                t.r_flag[head_row] &= (u8)~XF_HEAD;
+                *xr_flagp(t, head_row) &= (u8)~XF_HEAD;
                 merged++;
             }
             s.blk_est += E.est_ops - merged_sz;          // only ops that did not merge count (change_store.rs:1271-1279)
@@ -891,19 +1041,19 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             bool fresh = true;
             while (left) {
                 u64 row = it.row();
-                if (fresh || (t.r_flag[row] & XF_HEAD)) {
+                if (fresh || (xr_flag(t, row) & XF_HEAD)) {
                     xk = c_vt[op] >> 8;
                     if (xk == XK_LIST) { s.put(7); s.varint(c_atoms[op]); }
                     else if (xk == XK_TEXT) s.varint(c_bytes[op]);
                     op++;
                 }
                 fresh = false;
-                if (xk == XK_LIST || xk == XK_TEXT) {
-                    Cur c(t.bytes + t.op_val_off[row], t.op_val_len[row]);
-                    if (xk == XK_TEXT) (void)c.varint();
-                    else { (void)c.get(); (void)c.varint(); }
-                    s.copy(c.p, c.left());
-                } else if (xk == XK_MAPSET) s.copy(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+                if (xk == XK_LIST || xk == XK_TEXT || xk == XK_MAPSET) {
+                    const u8* pp;
+                    u32 pn;
+                    xr_payload(t, row, xk, &pp, &pn);
+                    s.copy(pp, pn);
+                }
                 left--;
                 if (left) it.next();
             }

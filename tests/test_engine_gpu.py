@@ -238,13 +238,7 @@ def test_export_with_pending_changes_and_after_import_batch():
         assert g.json_bytes(k) == js and g.export_updates(k) == ex, k
 
 
-def test_export_unsupported_is_reported_not_guessed():
-    import loro_b200
-    from loro_b200 import api
-    a = OracleDoc(3)
-    a.text_insert(a.get_text("t"), 0, "x" * 6000)
-    batch = loro_b200.import_batch([a.export_updates()], flags=api.LB_FLAG_EXPORT)
-    assert batch.get_deep_value(0) == {"t": "x" * 6000}
-    with pytest.raises(api.EngineError) as e:
-        batch.export_updates(0)
-    assert e.value.status == 6
+def test_export_inserts_larger_than_a_block():
+    from tests.export_checks import check_export_against_oracle
+    from tests.test_export_emu import big_insert_documents
+    check_export_against_oracle(big_insert_documents())

@@ -69,25 +69,46 @@ def test_export_typing_runs_merge_across_changes():
     check_export_against_oracle([a.export_updates()], lib_path=EMU)
 
 
-def test_export_needs_flag_and_reports_unsupported():
+def test_export_needs_flag():
     import loro_b200
     from loro_b200 import api
-    a = OracleDoc(3)
-    a.text_insert(a.get_text("t"), 0, "x" * 6000)   # one change above MAX_BLOCK_SIZE: split_change_then_insert
-    big = a.export_updates()
     b = OracleDoc(4)
     b.text_insert(b.get_text("t"), 0, "ok")
-    small = b.export_updates()
-    plain = loro_b200.import_batch([small], lib_path=EMU)
+    plain = loro_b200.import_batch([b.export_updates()], lib_path=EMU)
     with pytest.raises(api.EngineError):
         plain.export_updates(0)
-    batch = loro_b200.import_batch([big, small], flags=api.LB_FLAG_EXPORT, lib_path=EMU)
-    assert batch.get_deep_value(0) == {"t": "x" * 6000}
-    with pytest.raises(api.EngineError) as e:
-        batch.export_updates(0)
-    assert "does not cover" in str(e.value)
-    ref = OracleDoc(9); ref.import_(small)
-    assert batch.export_updates(1) == ref.export_updates()
+
+
+def big_insert_documents():
+    """Changes with inserts larger than a block: split_change_then_insert cuts the op itself (Op::slice); the pieces
+    re-merge in the store when they are alone and stay apart when other ops follow."""
+    import random
+    docs = []
+    a = OracleDoc(3); a.text_insert(a.get_text("t"), 0, "x" * 6000); docs.append(a)
+    a = OracleDoc(3); a.text_insert(a.get_text("t"), 0, "h\u00e9llo w\u00f6rld \U0001F600 " * 900); docs.append(a)
+    a = OracleDoc(3); a.list_insert(a.get_list("l"), 0, *list(range(3000))); docs.append(a)
+    a = OracleDoc(3); t = a.get_text("t"); a.text_insert(t, 0, "abc"); a.text_insert(t, 1, "y" * 9000)
+    a.text_insert(t, 5, "zz"); a.map_set(a.get_map("m"), "k", 1); docs.append(a)
+    a = OracleDoc(3); l = a.get_list("l"); a.list_insert(l, 0, *["s%d" % i for i in range(1500)])
+    a.list_insert(l, 3, *[7] * 1200); docs.append(a)
+    a = OracleDoc(3); t = a.get_text("t"); a.text_insert(t, 0, "p" * 4090); a.text_insert(t, 4090, "r" * 10); a.commit()
+    a.text_insert(t, 0, "s" * 8200); docs.append(a)
+    for seed in (1, 2):
+        a = OracleDoc(3); t = a.get_text("t")
+        rnd = random.Random(seed)
+        for _ in range(24):
+            n = rnd.choice([1, 3, 50, 700, 4093, 4096, 5000, 12000])
+            a.text_insert(t, rnd.randrange(0, a.seq_len(t) + 1), "".join(rnd.choice("ab \u00e9\U0001F600") for _ in range(n)))
+            if rnd.random() < 0.3:
+                a.commit()
+            if rnd.random() < 0.3 and a.seq_len(t) > 10:
+                a.delete(t, rnd.randrange(0, a.seq_len(t) - 5), rnd.randrange(1, 5))
+        docs.append(a)
+    return [d.export_updates() for d in docs]
+
+
+def test_export_inserts_larger_than_a_block():
+    check_export_against_oracle(big_insert_documents(), lib_path=EMU)
 
 
 def test_export_with_pending_changes_and_after_import_batch():
