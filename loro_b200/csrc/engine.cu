@@ -459,6 +459,7 @@ void pipeline(lb_batch* b) {
         run_scans(b, {ScanJob{(const u8*)xt.ch_novf, (u8*)xt.ch_seg0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_syn, (u8*)xt.ch_syn0, 4, 8, NCH}});
         u64 NOVF = d2h_one(b, xt.ch_seg0 + NCH);
         u64 NSYN = d2h_one(b, xt.ch_syn0 + NCH);
+        xt.has_syn = NSYN ? 1 : 0;
         xt.s_rec = dv.alloc<uint4>(NSYN); xt.s_len = dv.alloc<u32>(NSYN); xt.s_bytes = dv.alloc<u32>(NSYN);
         xt.s_flag = dv.alloc<u8>(NSYN); xt.s_voff = dv.alloc<u64>(NSYN); xt.s_vlen = dv.alloc<u32>(NSYN); xt.s_aux = dv.alloc<u32>(NSYN);
         if (NCH + NOVF > SEGCAP) {   // unusually many split changes: grow the tables, keep what pass 0 wrote

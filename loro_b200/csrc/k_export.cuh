@@ -77,6 +77,7 @@ struct ExportTables {
     // changes whose split cuts an op (Op::slice, list_op.rs:603-658) get SYNTHETIC rows: one per source row or slice,
     // addressed as row = n_rows + ch_syn0[ch] + i; every row accessor below understands both spaces
     u32* ch_syn; u64* ch_syn0; u64 n_rows;
+    u32 has_syn;       // any synthetic row in the batch (uniform: the common batch never leaves the decoded rows)
     uint4* s_rec; u32* s_len; u32* s_bytes; u8* s_flag; u64* s_voff; u32* s_vlen; u32* s_aux;
     u64 n_changes;     // segment q of change ch lives at q == 0 ? ch : n_changes + ch_seg0[ch] + q - 1
     u32* ch_aval; u32* ch_astr; u64* ch_aval0; u64* ch_astr0;   // arena sums per change + their scans
@@ -223,21 +224,21 @@ __device__ __forceinline__ uint4 xop_pack(const XOp& o) {
     return r;
 }
 // ---- row accessors: decoded rows [0, n_rows) and synthetic rows [n_rows, ...)
-__device__ __forceinline__ uint4 xr_rec(const ExportTables& t, u64 row) { return row < t.n_rows ? t.x_rec[row] : t.s_rec[row - t.n_rows]; }
-__device__ __forceinline__ u32 xr_len(const ExportTables& t, u64 row) { return row < t.n_rows ? t.op_len[row] : t.s_len[row - t.n_rows]; }
-__device__ __forceinline__ u32 xr_bytes(const ExportTables& t, u64 row) { return row < t.n_rows ? t.r_bytes[row] : t.s_bytes[row - t.n_rows]; }
-__device__ __forceinline__ u32 xr_aux(const ExportTables& t, u64 row) { return row < t.n_rows ? t.op_aux[row] : t.s_aux[row - t.n_rows]; }
-__device__ __forceinline__ u8* xr_flagp(const ExportTables& t, u64 row) { return row < t.n_rows ? &t.r_flag[row] : &t.s_flag[row - t.n_rows]; }
+__device__ __forceinline__ uint4 xr_rec(const ExportTables& t, u64 row) { return (!t.has_syn || row < t.n_rows) ? t.x_rec[row] : t.s_rec[row - t.n_rows]; }
+__device__ __forceinline__ u32 xr_len(const ExportTables& t, u64 row) { return (!t.has_syn || row < t.n_rows) ? t.op_len[row] : t.s_len[row - t.n_rows]; }
+__device__ __forceinline__ u32 xr_bytes(const ExportTables& t, u64 row) { return (!t.has_syn || row < t.n_rows) ? t.r_bytes[row] : t.s_bytes[row - t.n_rows]; }
+__device__ __forceinline__ u32 xr_aux(const ExportTables& t, u64 row) { return (!t.has_syn || row < t.n_rows) ? t.op_aux[row] : t.s_aux[row - t.n_rows]; }
+__device__ __forceinline__ u8* xr_flagp(const ExportTables& t, u64 row) { return (!t.has_syn || row < t.n_rows) ? &t.r_flag[row] : &t.s_flag[row - t.n_rows]; }
 __device__ __forceinline__ u8 xr_flag(const ExportTables& t, u64 row) { return *xr_flagp(t, row); }
 // the rows of a change as the export sees them
 __device__ __forceinline__ void change_rows(const ExportTables& t, u32 ch, u64* row0, u32* nr) {
-    u32 ns = t.ch_syn[ch];
+    u32 ns = t.has_syn ? t.ch_syn[ch] : 0;
     if (ns) { *row0 = t.n_rows + t.ch_syn0[ch]; *nr = ns; }
     else { *row0 = t.ch_op0[ch]; *nr = t.ch_nops[ch]; }
 }
 // payload bytes a row contributes to the values section (items of a list insert, text bytes, a whole map value)
 __device__ __forceinline__ void xr_payload(const ExportTables& t, u64 row, u32 xk, const u8** p, u32* n) {
-    if (row >= t.n_rows) { *p = t.bytes + t.s_voff[row - t.n_rows]; *n = t.s_vlen[row - t.n_rows]; return; }
+    if (t.has_syn && row >= t.n_rows) { *p = t.bytes + t.s_voff[row - t.n_rows]; *n = t.s_vlen[row - t.n_rows]; return; }
     const u8* v = t.bytes + t.op_val_off[row];
     u32 vl = t.op_val_len[row];
     if (xk == XK_LIST) { u32 skip = 1 + varint_len(t.op_len[row]); *p = v + skip; *n = vl - skip; }   // `07` + item count
@@ -256,7 +257,7 @@ __device__ __forceinline__ XOp xop_from_row(const ExportTables& t, const DocInfo
     o.f0 = r.w; o.f1 = 0; o.f2 = 0; o.g = 0;
     o.st0 = (u32)row; o.nst = 1;
     if (o.xk == XK_LIST) o.f1 = o.f0 + o.atoms;
-    else if (o.xk == XK_TEXT) { o.f1 = o.f0 + xr_bytes(t, row); o.g = row < t.n_rows ? str_gen(o.f1) : xr_aux(t, row); }
+    else if (o.xk == XK_TEXT) { o.f1 = o.f0 + xr_bytes(t, row); o.g = (!t.has_syn || row < t.n_rows) ? str_gen(o.f1) : xr_aux(t, row); }
     else if (o.xk == XK_DEL) { o.f0 = xr_aux(t, row); o.f1 = r.w; o.f2 = (r.x & 8u) ? -(i32)o.atoms : (i32)o.atoms; }
     return o;
 }
