@@ -454,9 +454,8 @@ void pipeline(lb_batch* b) {
         LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
         if (NCH) LB_LAUNCH(k_exp_arena, nblk(NCH, 64), 64, 0, st, NCH, xt, b->d_docs);
         run_scans(b, {ScanJob{(const u8*)xt.ch_aval, (u8*)xt.ch_aval0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_astr, (u8*)xt.ch_astr0, 4, 8, NCH}});
-        if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt);
-        if (NCH) LB_LAUNCH(k_exp_split, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 2);
-        tm.kernel_launches += 4;
+        if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
+        tm.kernel_launches += 3;
         run_scans(b, {ScanJob{(const u8*)xt.ch_novf, (u8*)xt.ch_seg0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_syn, (u8*)xt.ch_syn0, 4, 8, NCH}});
         u64 NOVF = d2h_one(b, xt.ch_seg0 + NCH);
         u64 NSYN = d2h_one(b, xt.ch_syn0 + NCH);
@@ -477,7 +476,7 @@ void pipeline(lb_batch* b) {
             dv.release(xt.fc_block);
             xt.fc_block = dv.alloc<u8>(cap);
         }
-        if (NOVF) { LB_LAUNCH(k_exp_split, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 1); tm.kernel_launches += 1; }
+        if (NOVF) { LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 1); tm.kernel_launches += 1; }
         LB_LAUNCH(k_exp_store, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
         LB_LAUNCH(k_exp_sizes, nblk(D), TPB, 0, st, b->d_docs, D, xt, d_tmp_a, d_tmp_b);
         tm.kernel_launches += 2;

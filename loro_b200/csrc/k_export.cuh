@@ -432,9 +432,7 @@ __device__ inline void segment_summaries(const ExportTables& t, const DocInfo& d
 
 // thread per change.  pass 0: per-row records, RleVec merge inside the change (XF_HEAD), segment count (XF_SEG marks
 // when no op has to be cut, a synthetic-row count otherwise).  pass 1 (split changes only): synthetic rows, summaries.
-template <int PASS>
-__device__ __forceinline__ void exp_changes_body(DocInfo* __restrict__ docs, u64 n_changes, const ExportTables& t) {
-    const int pass = PASS;
+__global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
     u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_changes) return;
     if (!t.ch_applied[ch]) { if (!pass) { t.ch_nseg[ch] = 0; t.ch_syn[ch] = 0; } return; }
@@ -464,27 +462,23 @@ __device__ __forceinline__ void exp_changes_body(DocInfo* __restrict__ docs, u64
             if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[row] = 0; }
             else { back = o; est_ops += xop_estimate(o); t.r_flag[row] = XF_HEAD; nm++; ndel += o.xk == XK_DEL; last_head = r; }
         }
-        // the common case: the change is its own (only) segment, summarised right here; a change above one block is
-        // left to pass 2 (k_exp_split), so that this kernel stays small
-        bool big = est0 + est_ops > LB_MAX_BLOCK_SIZE;
-        t.r_flag[r0] |= XF_SEG;
-        t.ch_nseg[ch] = big ? 0xFFFFFFFFu : 1u;
-        t.ch_novf[ch] = 0;
-        t.ch_syn[ch] = 0;
-        t.sg_src[ch] = (u32)ch; t.sg_r0[ch] = 0; t.sg_from[ch] = 0; t.sg_atoms[ch] = t.ch_len[ch]; t.sg_est[ch] = est_ops;
-        t.sg_nmops[ch] = nm; t.sg_ndel[ch] = ndel; t.sg_nrows[ch] = nr; t.sg_last_head[ch] = last_head;
+        u32 nseg = 1, nsyn = 0;
+        t.ch_syn[ch] = 0;   // (xop_from_row below must see the decoded rows)
+        if (est0 + est_ops > LB_MAX_BLOCK_SIZE) {
+            XSplit sp = split_change(t, di, (u32)ch, r0, nr, est0, [&](u64 row, u32 a, u32, bool, bool seg) {
+                if (seg && a == 0) t.r_flag[row] |= XF_SEG;   // valid when nothing gets cut (else the synthetic rows carry it)
+            });
+            nseg = sp.nseg;
+            if (sp.sliced && nseg > 1) nsyn = sp.nsyn;   // (a lone "slice" that is the whole op changes nothing)
+        } else t.r_flag[r0] |= XF_SEG;
+        t.ch_nseg[ch] = nseg;
+        t.ch_novf[ch] = nseg - 1;
+        t.ch_syn[ch] = nsyn;
+        if (nseg == 1) {   // the common case: the change is its own (only) segment, summarised right here
+            t.sg_src[ch] = (u32)ch; t.sg_r0[ch] = 0; t.sg_from[ch] = 0; t.sg_atoms[ch] = t.ch_len[ch]; t.sg_est[ch] = est_ops;
+            t.sg_nmops[ch] = nm; t.sg_ndel[ch] = ndel; t.sg_nrows[ch] = nr; t.sg_last_head[ch] = last_head;
+        }
         if (bad) atomicOr(&t.xdoc[doc].flags, 1u);
-        return;
-    }
-    if (pass == 2) {
-        // changes above one block: how many segments, and how many synthetic rows if an op gets cut
-        if (t.ch_nseg[ch] != 0xFFFFFFFFu) return;
-        XSplit sp = split_change(t, di, (u32)ch, r0, nr, est0, [&](u64 row, u32 a, u32, bool, bool seg) {
-            if (seg && a == 0) t.r_flag[row] |= XF_SEG;   // valid when nothing gets cut (else the synthetic rows carry it)
-        });
-        t.ch_nseg[ch] = sp.nseg;
-        t.ch_novf[ch] = sp.nseg - 1;
-        t.ch_syn[ch] = (sp.sliced && sp.nseg > 1) ? sp.nsyn : 0;   // (a lone "slice" that is the whole op changes nothing)
         return;
     }
     // pass 1 (split changes only)
@@ -527,11 +521,6 @@ __device__ __forceinline__ void exp_changes_body(DocInfo* __restrict__ docs, u64
         t.ch_syn[ch] = nsyn;
     }
     segment_summaries(t, di, (u32)ch);
-}
-__global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t) { exp_changes_body<0>(docs, n_changes, t); }
-// the rare, heavy part (changes above one block) lives in its own kernel: pass 2 counts, pass 1 materialises
-__global__ void k_exp_split(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
-    if (pass == 2) exp_changes_body<2>(docs, n_changes, t); else exp_changes_body<1>(docs, n_changes, t);
 }
 
 // ---------------------------------------------------------------------------------------------- B + C: the stores
