@@ -1,17 +1,20 @@
 /* loro_b200 -- C ABI of the B200-native batched CRDT merge engine.
  *
  * Drop-in boundary for ONE hot path of loro-dev/loro: batched `LoroDoc::import` of FastUpdates blobs
- * into fresh documents -> (decode, causal scan, eg-walker merge) -> deep JSON state / import status.
+ * into fresh documents -> (decode, causal scan, eg-walker merge) -> deep JSON state / import status
+ * -> re-export of every document (`export(ExportMode::all_updates)`).
  * The reference has no C FFI for this path; every entry point cites the Rust interface it
  * replaces (paths relative to /root/reference):
  *
  *   lb_import_batch          crates/loro/src/lib.rs:639  LoroDoc::import(&self, &[u8]) -> Result<ImportStatus>
- *                            crates/loro/src/lib.rs:425  LoroDoc::import_batch (one fresh doc per blob here)
+ *                            crates/loro/src/lib.rs:425  LoroDoc::import_batch (blobs sharing a doc_id -> one document)
  *                            crates/loro-internal/src/loro.rs:562-643 (header/checksum/mode checks first)
  *   lb_doc_status            crates/loro-internal/src/encoding.rs:226-230 ImportStatus{success,pending}
  *                            crates/loro-common/src/error.rs:8-105 (LoroError variants -> lb_doc_code)
  *   lb_doc_json              crates/loro/src/lib.rs:866  LoroDoc::get_deep_value() (serde_json text, keys sorted)
  *   lb_doc_vv                crates/loro/src/lib.rs:816  LoroDoc::oplog_vv()
+ *   lb_doc_export_updates    crates/loro/src/lib.rs:1235 LoroDoc::export(ExportMode::all_updates())
+ *                            crates/loro-internal/src/encoding.rs:350-416, oplog/change_store.rs:494-576
  *   lb_batch_counters        crates/loro-internal/src/loro.rs:1458 len_ops / len_changes (summed over the batch)
  *
  * Conventions (mirroring the reference): input buffers are borrowed for the duration of the call only;
@@ -103,7 +106,8 @@ typedef struct lb_timings { /* device time per phase in milliseconds (CUDA event
 
 typedef struct lb_batch lb_batch;
 
-/* Import a batch of FastUpdates blobs, one fresh document per blob, from HOST memory. */
+/* Import a batch of FastUpdates blobs from HOST memory: one fresh document per distinct doc_id (documents are
+ * numbered in order of first appearance; lb_doc_count tells how many there are). */
 lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out);
 
 /* Same, with the blobs already resident in device memory: `d_bytes` is one device buffer holding all blobs,

@@ -23,6 +23,13 @@ def reseal(blob):
 def main(lib, seed, n):
     rnd = random.Random(seed)
     base = [workloads.make_doc_history(100 + i, n_sites=3, n_ops=120)[0] for i in range(4)]
+    if os.environ.get("LB_FUZZ_WIDE"):   # more shapes: many sites, longer histories, an insert larger than a block
+        from oracle import OracleDoc
+        base += [workloads.make_doc_history(300 + i, n_sites=2 + i, n_ops=200 + 50 * i, sync_prob=0.1)[0] for i in range(4)]
+        big = OracleDoc(9)
+        big.text_insert(big.get_text("t"), 0, "w\u00e9 " * 2500)
+        big.list_insert(big.get_list("l"), 0, *list(range(1500)))
+        base.append(big.export_updates())
     ok = 0
     for _ in range(n):
         b = bytearray(rnd.choice(base))
