@@ -446,6 +446,14 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             t.op_len[row] = (u32)ln;
             t.op_counter[row] = counter;
             t.op_change[row] = (u32)(bi.ch0 + change);
+            if ((u8)vt == VK_LORO_VALUE && t.cid_type[bi.cid0 + (u32)acc_c] == CT_LIST) {
+                // a List insert carries LoroValue::List with exactly `len` items (outdated_encode_reordered.rs:246-262,
+                // the reference fails the import otherwise): later phases address the items through `len`
+                Cur pk = v;
+                u8 k = pk.get();
+                u64 n_items = pk.varint();
+                if (k != 7 || n_items != (u64)ln) { err = err ? err : LB_ERR(DOC_ERR_CORRUPT); break; }
+            }
             const u8* v0 = v.p;
             // text/list payloads: point past the length prefix where that helps the consumers
             skip_value(v, (u8)vt, &n_maps);

@@ -241,8 +241,18 @@ __device__ __forceinline__ void xr_payload(const ExportTables& t, u64 row, u32 x
     if (t.has_syn && row >= t.n_rows) { *p = t.bytes + t.s_voff[row - t.n_rows]; *n = t.s_vlen[row - t.n_rows]; return; }
     const u8* v = t.bytes + t.op_val_off[row];
     u32 vl = t.op_val_len[row];
-    if (xk == XK_LIST) { u32 skip = 1 + varint_len(t.op_len[row]); *p = v + skip; *n = vl - skip; }   // `07` + item count
-    else if (xk == XK_TEXT) { u32 nb = t.r_bytes[row]; *p = v + varint_len(nb); *n = nb; }
+    if (xk == XK_LIST) {            // `07` + item count (parsed, not assumed minimal)
+        Cur c(v, vl);
+        (void)c.get();
+        (void)c.varint();
+        *p = c.p;
+        *n = (u32)c.left();
+    } else if (xk == XK_TEXT) {     // byte length + bytes
+        Cur c(v, vl);
+        (void)c.varint();
+        *p = c.p;
+        *n = (u32)c.left();
+    }
     else if (xk == XK_MAPSET) { *p = v; *n = vl; }
     else { *p = v; *n = 0; }
 }

@@ -10,10 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU = os.path.join(HERE, "emu", "libloro_b200_emu.so")
 
 
-@pytest.mark.parametrize("seed", [21, 23])
-def test_mutated_blobs_stay_inside_their_tables(seed):
+@pytest.mark.parametrize("seed,wide", [(21, False), (23, False), (61, True)])
+def test_mutated_blobs_stay_inside_their_tables(seed, wide):
     subprocess.check_call([os.path.join(HERE, "emu", "build_emu.sh")])
     env = dict(os.environ, LB_EMU_GUARD="1", LB_EMU_THREADS="1")
+    if wide:
+        env["LB_FUZZ_WIDE"] = "1"   # more document shapes (seed 61 used to find a list insert whose item count lied)
     out = subprocess.run([sys.executable, os.path.join(HERE, "tools", "fuzz_emu.py"), EMU, str(seed), "150"],
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]

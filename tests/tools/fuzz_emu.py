@@ -42,7 +42,10 @@ def main(lib, seed, n):
                 b[i] = rnd.randrange(256)
             else:
                 b[i] ^= 1 << rnd.randrange(8)
-        r = loro_b200.import_batch([reseal(b)], flags=api.LB_FLAG_EXPORT, lib_path=lib)
+        blob = reseal(b)
+        if os.environ.get("LB_FUZZ_SAVE"):
+            open(os.environ["LB_FUZZ_SAVE"], "wb").write(blob)
+        r = loro_b200.import_batch([blob], flags=api.LB_FLAG_EXPORT, lib_path=lib)
         if r.status(0).code == 0:
             ok += 1
             r.json_bytes(0)
