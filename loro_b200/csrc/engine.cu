@@ -296,7 +296,7 @@ void pipeline(lb_batch* b) {
     rt.ch_applied = dv.alloc<u8>(NCH, true);
     rt.ch_lamport = dv.alloc<u32>(NCH, true);
     rt.ch_walk = dv.alloc<u32>(NCH);
-    rt.ch_pos = dv.alloc<u32>(NCH);
+    rt.ch_pos = dv.alloc<u32>(NCH, true);
     LB_LAUNCH(k_doc_tables, nblk(D, 64), 64, 0, st, b->d_bytes, b->d_docs, D, blk, rt);
     u32* d_tmp_a = dv.alloc<u32>(D + 1, true);
     u32* d_tmp_b = dv.alloc<u32>(D + 1, true);

@@ -461,7 +461,10 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             t.op_val_len[row] = (u32)(v.p - v0);
             t.op_del[row] = (u8)vt == VK_DELETE_SEQ ? (u32)(bi.del0 + ndel++) : 0xFFFFFFFFu;
             counter += (i32)ln;
-            if (counter >= next_boundary) {
+            // a row never straddles a change boundary: the reference's encoder cuts ops at changes, and everything
+            // downstream (atom tables, pending ranges) trusts ch_len -- a blob that disagrees is corrupt
+            if (counter > next_boundary) { err = err ? err : LB_ERR(DOC_ERR_CORRUPT); break; }
+            if (counter == next_boundary) {
                 t.ch_nops[bi.ch0 + change] = r + 1 - ch_first_row;
                 change++;
                 ch_first_row = r + 1;

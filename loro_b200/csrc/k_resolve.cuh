@@ -224,7 +224,11 @@ __device__ inline bool lamport_of(const DocInfo& di, const ResolveTables& t, u32
     // duplicates (the same change delivered twice inside an import_batch) sort next to each other: the first one
     // is the one that was applied
     while (lo > 0 && t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + lo - 1]] == t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + lo]]) lo--;
+    // a re-delivered or sliced copy (export from a version vector cuts a change: A[3..10) next to A[0..10)) was
+    // dropped, not applied: the applied change that covers c sorts before it
+    while (lo > 0 && !t.ch_applied[t.ch_order[di.ch0 + dp.ch_first + lo]]) lo--;
     u32 ch = t.ch_order[di.ch0 + dp.ch_first + lo];
+    if (!t.ch_applied[ch] || c < t.ch_counter[ch] || c >= t.ch_counter[ch] + (i32)t.ch_len[ch]) return false;
     *out = t.ch_lamport[ch] + (u32)(c - t.ch_counter[ch]);
     *ch_out = ch;
     return true;

@@ -204,3 +204,63 @@ def test_import_batch_groups_blobs_by_doc_id():
         ref.import_(p)
     assert b2.n_docs == 1 and b2.json_bytes(0) == ref.json_text()
     assert b2.oplog_vv(0) == ref.oplog_vv()
+
+
+def test_import_batch_full_blob_plus_overlapping_sliced_blob():
+    """A full history next to `export(updates(vv))` of the same history: the sliced copy A[3..n) of a merged change
+    is a duplicate that must be dropped, and a dependency on an atom it covers resolves to the applied original
+    (round-1 advisor finding: lamport_of picked the dropped record)."""
+    import loro_b200
+    a, b = OracleDoc(1), OracleDoc(2)
+    t = a.get_text("t")
+    a.text_insert(t, 0, "0123456789")
+    a.commit()
+    workloads.merge(b, a)
+    tb = b.get_text("t")
+    b.text_insert(tb, 5, "xyz")      # depends on 1@9 through the frontier
+    b.commit()
+    workloads.merge(a, b)
+    a.text_insert(t, 2, "Q")
+    a.commit()
+    full = a.export_updates()
+    sliced = a.export_updates({1: 3})
+    ref = OracleDoc(9)
+    ref.import_(full)
+    ref.import_(sliced)
+    for blobs in ([full, sliced], [sliced, full]):
+        r = loro_b200.import_batch(blobs, doc_ids=[5, 5], lib_path=EMU)
+        assert r.n_docs == 1 and r.status(0).code == 0
+        assert r.json_bytes(0) == ref.json_text()
+        assert r.oplog_vv(0) == ref.oplog_vv()
+
+
+def test_rows_straddling_change_boundary_are_corrupt():
+    """A checksummed block whose change lengths disagree with its op rows (advisor finding: an out-of-bounds atom
+    write of attacker-chosen size) must fail the document, not the batch."""
+    import struct
+    import loro_b200
+    from loro_b200 import api
+    a = OracleDoc(1)
+    t = a.get_text("t")
+    a.text_insert(t, 0, "x" * 800)
+    a.commit()
+    b = OracleDoc(2)
+    b.text_insert(b.get_text("t"), 0, "y")
+    b.commit()
+    workloads.merge(a, b)
+    a.text_insert(t, 3, "abcde")     # second change of peer 1 in the same block (has a foreign dep -> no merge)
+    a.commit()
+    blob = bytearray(a.export_updates())
+    # find the `a0 06` (= 800) change-length varint of the header and patch it to 1, then re-seal
+    i = blob.find(bytes([0xA0, 0x06]), 22)
+    assert i > 0
+    patched = blob[:i] + bytes([0x01]) + blob[i + 2:]
+    # the block and section length prefixes shrink by one byte: rebuild them by re-framing through the oracle's dump
+    # is overkill -- instead patch in place keeping the length (0x81 0x00 is a non-canonical varint for 1)
+    patched = blob[:i] + bytes([0x81, 0x00]) + blob[i + 2:]
+    h = oracle.i64s(oracle.codec("xxh32", bytes(patched[20:]), 0x4F524F4C))[0] & 0xFFFFFFFF
+    patched = bytes(patched[:16]) + struct.pack("<I", h) + bytes(patched[20:])
+    good = a.export_updates()
+    r = loro_b200.import_batch([patched, good], flags=api.LB_FLAG_EXPORT, lib_path=EMU)
+    assert r.status(0).code in (1, 4), r.status(0)
+    assert r.status(1).code == 0
