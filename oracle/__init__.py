@@ -53,6 +53,14 @@ def lib():
         L.lo_map_delete.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, sz]
         L.lo_child_container.argtypes = [vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
         L.lo_next_counter.argtypes = [vp]
+        L.lo_tree_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_int)]
+        L.lo_tree_move.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+                                   ctypes.c_int, ctypes.c_int]
+        L.lo_tree_delete.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
+        L.lo_tree_meta.argtypes = [vp, ctypes.c_uint64, ctypes.c_int]
+        L.lo_tree_nodes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int),
+                                    ctypes.c_int]
         L.lo_commit.argtypes = [vp]
         L.lo_export.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int32),
                                 ctypes.POINTER(vp), ctypes.POINTER(sz)]
@@ -124,6 +132,34 @@ class OracleDoc:
     def get_text(self, name): return self.container(name, CT_TEXT)
     def get_list(self, name): return self.container(name, CT_LIST)
     def get_map(self, name): return self.container(name, CT_MAP)
+    def get_tree(self, name): return self.container(name, CT_TREE)
+
+    # ---- movable tree (handler/tree.rs): nodes are (peer, counter) TreeIDs, parent None = root
+    def tree_create(self, c, parent=None, index=-1):
+        out = ctypes.c_int()
+        pp, pc = parent if parent else (0, 0)
+        if lib().lo_tree_create(self._d, c, 0 if parent else 1, pp, pc, index, ctypes.byref(out)) != 0:
+            raise IndexError("tree_create rejected")
+        return (self.peer, out.value)
+
+    def tree_move(self, c, target, parent=None, index=-1):
+        pp, pc = parent if parent else (0, 0)
+        if lib().lo_tree_move(self._d, c, target[0], target[1], 0 if parent else 1, pp, pc, index) != 0:
+            raise IndexError("tree_move rejected (cycle, dead node or index out of range)")
+
+    def tree_delete(self, c, target):
+        if lib().lo_tree_delete(self._d, c, target[0], target[1]) != 0:
+            raise IndexError("tree_delete rejected")
+
+    def tree_meta(self, target):
+        return lib().lo_tree_meta(self._d, target[0], target[1])
+
+    def tree_nodes(self, c):
+        n = lib().lo_tree_nodes(self._d, c, None, None, 0)
+        peers = (ctypes.c_uint64 * max(n, 1))()
+        ctrs = (ctypes.c_int * max(n, 1))()
+        lib().lo_tree_nodes(self._d, c, peers, ctrs, n)
+        return [(int(peers[i]), int(ctrs[i])) for i in range(n)]
 
     def text_insert(self, c, pos, s):
         b = s.encode()

@@ -95,6 +95,32 @@ int lo_child_container(void* d, uint64_t peer, int counter, int type) {
     return ((Doc*)d)->register_container(c);
 }
 int lo_next_counter(void* d) { return ((Doc*)d)->next_counter(); }
+// local tree ops: a parent is (root flag, peer, counter); index < 0 appends.  0 ok, -1 rejected.
+int lo_tree_create(void* d, int cidx, int parent_root, uint64_t ppeer, int pctr, int index, int* out_ctr) {
+    ID out;
+    if (!((Doc*)d)->tree_create(cidx, parent_root != 0, ID{ppeer, pctr}, index, &out)) return -1;
+    if (out_ctr) *out_ctr = out.counter;
+    return 0;
+}
+int lo_tree_move(void* d, int cidx, uint64_t tpeer, int tctr, int parent_root, uint64_t ppeer, int pctr, int index) {
+    return ((Doc*)d)->tree_move(cidx, ID{tpeer, tctr}, parent_root != 0, ID{ppeer, pctr}, index) ? 0 : -1;
+}
+int lo_tree_delete(void* d, int cidx, uint64_t tpeer, int tctr) {
+    return ((Doc*)d)->tree_delete(cidx, ID{tpeer, tctr}) ? 0 : -1;
+}
+int lo_tree_meta(void* d, uint64_t tpeer, int tctr) { return ((Doc*)d)->tree_meta(ID{tpeer, tctr}); }
+// alive nodes of a tree container as "peer:ctr" pairs (workload generation): writes up to cap ids, returns the count
+int lo_tree_nodes(void* d, int cidx, uint64_t* peers, int* ctrs, int cap) {
+    Doc* doc = (Doc*)d;
+    doc->ensure_state();
+    int n = 0;
+    for (auto& x : doc->cstate(cidx).tree) {
+        if (x.deleted) continue;
+        if (n < cap) { peers[n] = x.id.peer; ctrs[n] = x.id.counter; }
+        n++;
+    }
+    return n;
+}
 void lo_commit(void* d) { ((Doc*)d)->commit(); }
 
 int lo_export(void* d, size_t n_from, const uint64_t* peers, const int32_t* counters, uint8_t** out,

@@ -590,11 +590,76 @@ struct TreeNodeState {
     ID id;
     bool parent_null = true;  // root
     ID parent;
-    bool deleted = false;
+    bool deleted = false;         // dead: the node or one of its ancestors sits under DELETED_TREE_ROOT
+    bool direct_deleted = false;  // the node's own parent is DELETED_TREE_ROOT
     std::string position;
     Lamport lamport;  // of the last effective move
     PeerID peer;
 };
+
+// ------------------------------------------------------------------ fractional index (local tree ops only)
+// crates/fractional_index/src/lib.rs:52-127, jitter 0.  Strings hold the full bytes incl. the terminator 0x80.
+namespace fi {
+static const uint8_t TERM = 128;
+inline std::string new_before(const std::string& b) {
+    for (size_t i = 0; i < b.size(); i++) {
+        uint8_t c = (uint8_t)b[i];
+        if (c > TERM) return b.substr(0, i);
+        if (c > 0) { std::string a = b.substr(0, i + 1); a[i] = (char)(c - 1); return a; }
+    }
+    throw std::runtime_error("fractional index: new_before");
+}
+inline std::string new_after(const std::string& b) {
+    for (size_t i = 0; i < b.size(); i++) {
+        uint8_t c = (uint8_t)b[i];
+        if (c < TERM) return b.substr(0, i);
+        if (c < 255) { std::string a = b.substr(0, i + 1); a[i] = (char)(c + 1); return a; }
+    }
+    throw std::runtime_error("fractional index: new_after");
+}
+inline bool new_between(const std::string& l, const std::string& r, std::string* out) {
+    size_t shorter = std::min(l.size(), r.size()) - 1;
+    for (size_t i = 0; i < shorter; i++) {
+        int a = (uint8_t)l[i], b = (uint8_t)r[i];
+        if (a < b - 1) { std::string x = l.substr(0, i + 1); x[i] = (char)(a + (b - a) / 2); *out = x; return true; }
+        if (a == b - 1) { *out = l.substr(0, i + 1) + new_after(l.substr(i + 1)); return true; }
+        if (a > b) return false;
+    }
+    if (l.size() < r.size()) {
+        std::string prefix = r.substr(0, shorter + 1);
+        if ((uint8_t)prefix.back() < TERM) return false;
+        *out = prefix + new_before(r.substr(shorter + 1));
+        return true;
+    }
+    if (l.size() == r.size()) return false;
+    std::string prefix = l.substr(0, shorter + 1);
+    if ((uint8_t)prefix.back() >= TERM) return false;
+    *out = prefix + new_after(l.substr(shorter + 1));
+    return true;
+}
+// FractionalIndex::new (lib.rs:128-136): nullptr = no bound; the result is terminated
+inline bool make(const std::string* lower, const std::string* upper, std::string* out) {
+    std::string body;
+    if (lower && upper) { if (!new_between(*lower, *upper, &body)) return false; }
+    else if (lower) body = new_after(*lower);
+    else if (upper) body = new_before(*upper);
+    else { *out = std::string(1, (char)TERM); return true; }
+    body.push_back((char)TERM);
+    *out = body;
+    return true;
+}
+inline void gen_evenly(const std::string* lower, const std::string* upper, size_t n, std::vector<std::string>& out) {
+    if (n == 0) return;  // lib.rs:155-195
+    size_t mid = n / 2;
+    std::string m;
+    if (!make(lower, upper, &m)) throw std::runtime_error("fractional index: generate_n_evenly");
+    if (n == 1) { out.push_back(m); return; }
+    gen_evenly(lower, &m, mid, out);
+    out.push_back(m);
+    if (n - mid - 1 == 0) return;
+    gen_evenly(&m, upper, n - mid - 1, out);
+}
+}  // namespace fi
 struct ContainerState {
     uint8_t type = 0;
     // list/text
@@ -1131,6 +1196,155 @@ struct Doc : ArenaCtx {
         e.peer = peer;
         return true;
     }
+    // ---------------- local tree ops (handler/tree.rs:292-355,518-723; state/tree_state.rs:175-236,690-723)
+    TreeNodeState* tree_find(ContainerState& st, ID id) {
+        for (auto& n : st.tree)
+            if (n.id == id) return &n;
+        return nullptr;
+    }
+    // children of an alive parent in sibling order (position, lamport, peer)
+    std::vector<TreeNodeState*> tree_children(ContainerState& st, bool root, ID parent) {
+        std::vector<TreeNodeState*> kids;
+        for (auto& n : st.tree)
+            if (!n.deleted && n.parent_null == root && (root || n.parent == parent)) kids.push_back(&n);
+        std::sort(kids.begin(), kids.end(), [](const TreeNodeState* a, const TreeNodeState* b) {
+            if (a->position != b->position) return a->position < b->position;
+            if (a->lamport != b->lamport) return a->lamport < b->lamport;
+            return a->peer < b->peer;
+        });
+        return kids;
+    }
+    bool tree_is_ancestor(ContainerState& st, ID anc, bool node_root, ID node) {  // tree_state.rs:727-747
+        if (!tree_find(st, anc)) return false;
+        while (!node_root) {
+            if (node == anc) return true;
+            TreeNodeState* n = tree_find(st, node);
+            if (!n || n->direct_deleted) return false;
+            node_root = n->parent_null;
+            node = n->parent;
+        }
+        return false;
+    }
+    // NodeChildren::generate_fi_at (tree_state.rs:175-236): positions for `target` at index `pos` among `kids`
+    // (the target itself already taken out); more than one entry = siblings with equal positions get new ones
+    std::vector<std::pair<ID, std::string>> tree_positions_at(const std::vector<TreeNodeState*>& kids, size_t pos, ID target) {
+        std::vector<std::pair<ID, std::string>> out;
+        if (kids.empty()) { out.push_back({target, std::string(1, (char)fi::TERM)}); return out; }
+        const std::string* left = pos > 0 ? &kids[pos - 1]->position : nullptr;
+        const std::string* right = pos < kids.size() ? &kids[pos]->position : nullptr;
+        std::vector<ID> reset;
+        const std::string* next_right = nullptr;
+        if (left && right && *left == *right) {
+            reset.push_back(kids[pos]->id);
+            for (size_t i = pos + 1; i < kids.size(); i++) {
+                if (kids[i]->position == *left) reset.push_back(kids[i]->id);
+                else { next_right = &kids[i]->position; break; }
+            }
+        }
+        if (reset.empty()) {
+            std::string p;
+            if (!fi::make(left, right, &p)) throw std::runtime_error("fractional index: no room");
+            out.push_back({target, p});
+            return out;
+        }
+        std::vector<std::string> ps;
+        fi::gen_evenly(left, next_right, reset.size() + 1, ps);
+        out.push_back({target, ps[0]});
+        for (size_t i = 0; i < reset.size(); i++) out.push_back({reset[i], ps[i + 1]});
+        return out;
+    }
+    void tree_push_op(int cidx, OpKind kind, ID target, bool parent_root, ID parent, const std::string& position) {
+        Op op;
+        op.cidx = cidx;
+        op.kind = kind;
+        op.target = target;
+        op.parent_null = parent_root;
+        op.parent = parent;
+        op.position = position;
+        txn_begin();
+        Counter c0 = next_counter();
+        Lamport l = txn.lamport + (Lamport)(c0 - txn.id.counter);
+        push_local(op);
+        ContainerState& st = cstate(cidx);
+        TreeNodeState* n = tree_find(st, target);
+        if (!n) { st.tree.push_back(TreeNodeState()); n = &st.tree.back(); n->id = target; }
+        n->lamport = l;
+        n->peer = peer;
+        if (kind == OP_TREE_DELETE) {
+            n->direct_deleted = true;
+        } else {
+            n->direct_deleted = false;
+            n->parent_null = parent_root;
+            n->parent = parent;
+            n->position = position;
+        }
+        // liveness of everything below a deleted (or revived) node
+        for (auto& x : st.tree) {
+            bool dead = false;
+            const TreeNodeState* cur = &x;
+            for (int guard = 0; guard < 1000000; guard++) {
+                if (cur->direct_deleted) { dead = true; break; }
+                if (cur->parent_null) break;
+                cur = tree_find(st, cur->parent);
+                if (!cur) { dead = true; break; }
+            }
+            x.deleted = dead;
+        }
+    }
+    // index < 0 = append.  Returns false when the request is invalid (dead / missing parent, index out of range).
+    bool tree_create(int cidx, bool parent_root, ID parent, int index, ID* out) {
+        ensure_state();
+        ContainerState& st = cstate(cidx);
+        if (!parent_root) { TreeNodeState* p = tree_find(st, parent); if (!p || p->deleted) return false; }
+        auto kids = tree_children(st, parent_root, parent);
+        size_t pos = index < 0 ? kids.size() : (size_t)index;
+        if (pos > kids.size()) return false;
+        ID target{peer, next_counter()};
+        auto ps = tree_positions_at(kids, pos, target);
+        for (size_t i = 0; i < ps.size(); i++)
+            tree_push_op(cidx, i == 0 ? OP_TREE_CREATE : OP_TREE_MOVE, ps[i].first, parent_root, parent, ps[i].second);
+        if (out) *out = target;
+        return true;
+    }
+    bool tree_move(int cidx, ID target, bool parent_root, ID parent, int index) {
+        ensure_state();
+        ContainerState& st = cstate(cidx);
+        TreeNodeState* t = tree_find(st, target);
+        if (!t || t->deleted) return false;
+        if (!parent_root) { TreeNodeState* p = tree_find(st, parent); if (!p || p->deleted) return false; }
+        if (tree_is_ancestor(st, target, parent_root, parent)) return false;  // CyclicMoveError
+        auto kids = tree_children(st, parent_root, parent);
+        bool already = t->parent_null == parent_root && (parent_root || t->parent == parent);
+        size_t len = kids.size();
+        if (already) {
+            size_t cur = 0;
+            while (kids[cur]->id != target) cur++;
+            if (index >= 0 && cur == (size_t)index) return true;  // nothing to do
+            kids.erase(kids.begin() + cur);
+            len--;
+        }
+        size_t pos = index < 0 ? len : (size_t)index;
+        if (pos > len) return false;
+        auto ps = tree_positions_at(kids, pos, target);
+        for (auto& pr : ps) tree_push_op(cidx, OP_TREE_MOVE, pr.first, parent_root, parent, pr.second);
+        return true;
+    }
+    bool tree_delete(int cidx, ID target) {
+        ensure_state();
+        ContainerState& st = cstate(cidx);
+        TreeNodeState* t = tree_find(st, target);
+        if (!t || t->deleted) return false;
+        tree_push_op(cidx, OP_TREE_DELETE, target, false, ID{DELETED_TREE_ROOT_PEER, DELETED_TREE_ROOT_CTR}, "");
+        return true;
+    }
+    int tree_meta(ID target) {  // TreeID::associated_meta_container (loro-common/src/lib.rs)
+        ContainerID c;
+        c.root = false;
+        c.peer = target.peer;
+        c.counter = target.counter;
+        c.type = CT_MAP;
+        return register_container(c);
+    }
     ContainerState& cstate(int cidx) {
         if (state.size() < containers.size()) state.resize(containers.size());
         ContainerState& s = state[(size_t)cidx];
@@ -1543,10 +1757,10 @@ inline void Doc::replay() {
                 if (op.kind == OP_TREE_DELETE) {
                     auto it = nodes.find(op.target);
                     if (it == nodes.end()) {
-                        n.deleted = true;
+                        n.deleted = n.direct_deleted = true;
                         nodes[op.target] = n;
                     } else {
-                        it->second.deleted = true;
+                        it->second.deleted = it->second.direct_deleted = true;
                         it->second.lamport = m.lamport;
                         it->second.peer = m.peer;
                     }

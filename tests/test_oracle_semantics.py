@@ -226,3 +226,89 @@ def test_n_site_random_sync_converges(seed):
     assert fresh.get_deep_value() == vals[0]
     assert fresh.oplog_vv() == docs[0].oplog_vv()
     assert fresh.export_updates() == full
+
+
+from tests.workloads import make_tree_history  # noqa: E402
+
+
+# ------------------------------------------------------------------ movable tree
+def test_tree_known_answer_loro_rust_test_tree():
+    """crates/loro/tests/loro_rust_test.rs:426-444 (`fn tree`): ids, parents, fractional indexes, meta map."""
+    d = OracleDoc(1)
+    t = d.get_tree("tree")
+    root = d.tree_create(t)
+    root2 = d.tree_create(t)
+    d.tree_move(t, root2, root)
+    d.map_set(d.tree_meta(root), "color", "red")
+    want = [{"parent": None, "meta": {"color": "red"}, "id": "0@1", "index": 0,
+             "children": [{"parent": "0@1", "meta": {}, "id": "1@1", "index": 0, "children": [], "fractional_index": "80"}],
+             "fractional_index": "80"}]
+    assert d.get_deep_value() == {"tree": want}
+    fresh = OracleDoc(7)
+    fresh.import_(d.export_updates())
+    assert fresh.get_deep_value() == {"tree": want}
+
+
+def test_tree_known_answer_fractional_indexes():
+    """crates/loro/tests/loro_rust_test.rs:1418-1530 (latest version of test_tree_checkout_on_shallow_doc): appended
+    siblings get "80" then "8180" (crates/fractional_index/src/lib.rs, jitter 0); ids are the create ops' ids."""
+    d = OracleDoc(0)
+    t = d.get_tree("tree")
+    root = d.tree_create(t)
+    c1 = d.tree_create(t)
+    d.tree_move(t, c1, root)
+    c2 = d.tree_create(t)
+    d.tree_move(t, c2, root)
+    want = {"tree": [{"parent": None, "meta": {}, "id": "0@0", "index": 0, "fractional_index": "80", "children": [
+        {"parent": "0@0", "meta": {}, "id": "1@0", "index": 0, "children": [], "fractional_index": "80"},
+        {"parent": "0@0", "meta": {}, "id": "3@0", "index": 1, "children": [], "fractional_index": "8180"}]}]}
+    assert d.get_deep_value() == want
+    # the intermediate version (checkout to 1@0 in the reference test): two roots "80" / "8180"
+    e = OracleDoc(0)
+    te = e.get_tree("tree")
+    e.tree_create(te)
+    e.tree_create(te)
+    v = e.get_deep_value()["tree"]
+    assert [(n["id"], n["fractional_index"], n["index"]) for n in v] == [("0@0", "80", 0), ("1@0", "8180", 1)]
+
+
+def test_tree_concurrent_cycle_is_resolved_by_lamport_order():
+    """diff_calc/tree.rs:471-508: of two concurrent moves that would form a cycle, the one later in (lamport, peer)
+    order is not effected; both replicas agree."""
+    a, b = OracleDoc(1), OracleDoc(2)
+    ta, tb = a.get_tree("t"), b.get_tree("t")
+    x = a.tree_create(ta)
+    y = a.tree_create(ta)
+    merge(b, a)
+    a.tree_move(ta, x, y)       # x under y   (lamport 2, peer 1)
+    b.tree_move(tb, y, x)       # y under x   (lamport 2, peer 2) -> would close the cycle: ignored
+    merge(a, b)
+    merge(b, a)
+    va, vb = a.get_deep_value()["t"], b.get_deep_value()["t"]
+    assert va == vb
+    assert [n["id"] for n in va] == ["1@1"] and [c["id"] for c in va[0]["children"]] == ["0@1"]
+
+
+def test_tree_delete_hides_subtree_and_move_back_revives():
+    a = OracleDoc(1)
+    t = a.get_tree("t")
+    r = a.tree_create(t)
+    k = a.tree_create(t, r)
+    g = a.tree_create(t, k)
+    a.tree_delete(t, k)
+    assert a.get_deep_value()["t"][0]["children"] == []
+    b = OracleDoc(2)
+    b.import_(a.export_updates())
+    assert b.get_deep_value() == a.get_deep_value()
+    assert g
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_tree_random_sites_converge(seed):
+    blob, js, vv, docs = make_tree_history(500 + seed, n_sites=2 + seed % 3, n_base=25, n_ops=140, mixed=seed % 2 == 0)
+    for d in docs:
+        assert d.json_text() == js
+    again = OracleDoc(3)
+    again.import_(blob)
+    assert again.json_text() == js and again.oplog_vv() == vv
+    assert again.export_updates() == blob   # re-export of an imported full history is byte-identical

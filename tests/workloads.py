@@ -94,3 +94,66 @@ def c1_two_peer_list(seed=1, n_each=1000):
     merge(b, a)
     assert a.json_text() == b.json_text()
     return a.export_updates(), a.json_text()
+
+
+def random_tree_edit(rnd, d, tree, p_create=0.35, p_delete=0.08, p_meta=0.12):
+    """One random movable-tree action (handler/tree.rs): create under a random alive node or the root, move to a
+    random parent / index (cycles are rejected locally, concurrent ones are resolved by the merge), delete,
+    or a write into a node's meta map."""
+    nodes = d.tree_nodes(tree)
+    r = rnd.random()
+    if not nodes or r < p_create:
+        parent = rnd.choice(nodes) if nodes and rnd.random() < 0.8 else None
+        try:
+            d.tree_create(tree, parent, -1 if rnd.random() < 0.5 else 0)
+        except IndexError:
+            pass
+    elif r < p_create + p_delete:
+        d.tree_delete(tree, rnd.choice(nodes))
+    elif r < p_create + p_delete + p_meta:
+        d.map_set(d.tree_meta(rnd.choice(nodes)), "k%d" % rnd.randrange(4), rnd.randint(0, 99))
+    else:
+        t = rnd.choice(nodes)
+        parent = rnd.choice(nodes) if rnd.random() < 0.85 else None
+        try:
+            d.tree_move(tree, t, parent, -1 if rnd.random() < 0.6 else 0)
+        except IndexError:
+            pass
+
+
+def make_tree_history(seed, n_sites=3, n_base=40, n_ops=120, sync_prob=0.04, commit_prob=0.3, mixed=False):
+    """C5-shaped history: peer 0 builds a base tree of n_base nodes, everybody syncs, then the sites issue
+    concurrent random tree actions (moves that form cycles across sites included).  Returns
+    (blob, expected_json_text, expected_vv, sites)."""
+    rnd = random.Random(seed)
+    peers = [rnd.getrandbits(64) | 1 for _ in range(n_sites)]
+    docs = [OracleDoc(p) for p in peers]
+    trees = [d.get_tree("tree") for d in docs]
+    hs = [(d.get_text("text"), d.get_list("list"), d.get_map("map")) for d in docs] if mixed else None
+    for _ in range(n_base):
+        random_tree_edit(rnd, docs[0], trees[0], p_create=1.0)
+        if rnd.random() < commit_prob:
+            docs[0].commit()
+    for j in range(1, n_sites):
+        merge(docs[j], docs[0])
+    for _ in range(n_ops):
+        i = rnd.randrange(n_sites)
+        if mixed and rnd.random() < 0.3:
+            random_edit(rnd, docs[i], *hs[i])
+        else:
+            random_tree_edit(rnd, docs[i], trees[i], p_create=0.15)
+        if rnd.random() < commit_prob:
+            docs[i].commit()
+        if n_sites > 1 and rnd.random() < sync_prob:
+            j = rnd.randrange(n_sites)
+            if j != i:
+                merge(docs[j], docs[i])
+    for _ in range(2):
+        for i in range(n_sites):
+            for j in range(n_sites):
+                if i != j:
+                    merge(docs[i], docs[j])
+    blob = docs[0].export_updates()
+    fresh = OracleDoc(1)
+    fresh.import_(blob)
+    return blob, fresh.json_text(), fresh.oplog_vv(), docs
