@@ -20,6 +20,7 @@
 #include "k_resolve.cuh"
 #include "k_classify.cuh"
 #include "k_seq.cuh"
+#include "k_tree.cuh"
 #include "k_state.cuh"
 #include "k_export.cuh"
 #include "host_stage.hpp"
@@ -44,6 +45,7 @@ __global__ void k_doc_sizes(const DocInfo* __restrict__ docs, u32 n_docs, u32* _
     const DocInfo& di = docs[d];
     bool ok = di.code == DOC_OK;
     if (which == 0) vvsize[d] = ok ? di.n_changes * di.P : 0;
+    else if (which == 2) vvsize[d] = ok && di.has_tree ? (u32)di.atom_total + di.C : 0;   // tree node slots (k_tree.cuh)
     else {
         atoms[d] = ok ? (u32)di.atom_total : 0;
         mapslots[d] = ok ? di.C * di.K : 0;
@@ -246,9 +248,15 @@ void pipeline(lb_batch* b) {
     run_scans(b, {FIELD_JOB(blk, BlockInfo, n_peers, peer0, B), FIELD_JOB(blk, BlockInfo, n_keys, key0, B),
                   FIELD_JOB(blk, BlockInfo, n_cids, cid0, B), FIELD_JOB(blk, BlockInfo, n_changes, ch0, B),
                   FIELD_JOB(blk, BlockInfo, n_deps, dep0, B), FIELD_JOB(blk, BlockInfo, n_ops, op0, B),
-                  FIELD_JOB(blk, BlockInfo, n_dels, del0, B)});
+                  FIELD_JOB(blk, BlockInfo, n_dels, del0, B), FIELD_JOB(blk, BlockInfo, n_pos, pos0, B),
+                  FIELD_JOB(blk, BlockInfo, pos_bytes, posb0, B), FIELD_JOB(blk, BlockInfo, n_tree, tr0, B)});
     BlockInfo tot = d2h_one(b, blk + B);
     u64 NP = tot.peer0, NK = tot.key0, NC = tot.cid0, NCH = tot.ch0, ND = tot.dep0, NR = tot.op0, NDEL = tot.del0;
+    u64 NPOS = tot.pos0, NPOSB = tot.posb0, NTR = tot.tr0;
+    if (NTR >= 0xFFFFFFFFull || NPOS >= 0xFFFFFFFFull) {
+        g_last_error = "batch too large: tree ops / positions must fit 32 bits";
+        throw lb_status(LB_ERR_INVALID_ARG);
+    }
     if (NR >= 0xFFFFFFFFull || NCH >= 0xFFFFFFFFull) {
         g_last_error = "batch too large: op rows / changes must fit 32 bits";
         throw lb_status(LB_ERR_INVALID_ARG);
@@ -270,6 +278,9 @@ void pipeline(lb_batch* b) {
     t.op_counter = dv.alloc<i32>(NR); t.op_change = dv.alloc<u32>(NR); t.op_val_off = dv.alloc<u64>(NR);
     t.op_val_len = dv.alloc<u32>(NR); t.op_del = dv.alloc<u32>(NR);
     t.del_peer_idx = dv.alloc<u32>(NDEL); t.del_counter = dv.alloc<i32>(NDEL); t.del_len = dv.alloc<i32>(NDEL);
+    t.pos_off = dv.alloc<u64>(NPOS); t.pos_len = dv.alloc<u32>(NPOS); t.pos_pool = dv.alloc<u8>(NPOSB + 8);
+    t.tr_target_peer = dv.alloc<u32>(NTR); t.tr_target_ctr = dv.alloc<i32>(NTR); t.tr_parent_kind = dv.alloc<u8>(NTR);
+    t.tr_parent_peer = dv.alloc<u32>(NTR); t.tr_parent_ctr = dv.alloc<i32>(NTR); t.tr_pos = dv.alloc<u32>(NTR);
     if (B) {
         LB_LAUNCH(k_block_decode, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
         tm.kernel_launches += 1;
@@ -324,6 +335,13 @@ void pipeline(lb_batch* b) {
     ct.op_counter = t.op_counter; ct.op_change = t.op_change;
     ct.op_del = t.op_del; ct.del_peer_idx = t.del_peer_idx; ct.del_counter = t.del_counter; ct.del_len = t.del_len;
     ct.peer_map = rt.peer_map;
+    ct.tr_target_peer = t.tr_target_peer; ct.tr_target_ctr = t.tr_target_ctr; ct.tr_parent_kind = t.tr_parent_kind;
+    ct.tr_parent_peer = t.tr_parent_peer; ct.tr_parent_ctr = t.tr_parent_ctr; ct.tr_pos = t.tr_pos;
+    ct.tr_rec = dv.alloc<uint4>(NTR); ct.tr_key = dv.alloc<u64>(NTR);
+    if (NTR) {   // ops that are not applied keep row = NONE / key = +inf
+        CK(cudaMemsetAsync(ct.tr_rec, 0xFF, sizeof(uint4) * NTR, st));
+        CK(cudaMemsetAsync(ct.tr_key, 0xFF, sizeof(u64) * NTR, st));
+    }
     ct.cid_map = rt.cid_map; ct.key_map = rt.key_map; ct.dcont = dcont; ct.dpeer = b->d_dpeer;
     ct.op_kind = dv.alloc<u8>(NR); ct.op_cidx = dv.alloc<u32>(NR); ct.op_lamport = dv.alloc<u32>(NR);
     ct.atom_row = dv.alloc<u32>(NATOM);
@@ -380,6 +398,23 @@ void pipeline(lb_batch* b) {
         dv.release(sp.leaf); dv.release(sp.node); dv.release(sp.node_parent); dv.release(sp.atom_leaf); dv.release(sp.a_org);
         dv.release(sp.cvv); dv.release(sp.cont_epoch); dv.release(ct.atom_row); dv.release(ct.op_rec);
     }
+    // ------------------------------------------------------------ phase 5b: movable trees
+    TreeTables tt;
+    memset(&tt, 0, sizeof(tt));
+    if (NTR) {
+        LB_LAUNCH(k_doc_sizes, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a, d_tmp_b, d_tmp_c, 2);
+        run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)b->d_docs + offsetof(DocInfo, tree0), 4, sizeof(DocInfo), D}});
+        u64 NTS = d2h_one(b, &b->d_docs[D].tree0);
+        tt.dpeer = b->d_dpeer; tt.blocks = blk; tt.op_cidx = ct.op_cidx; tt.op_lamport = ct.op_lamport;
+        tt.tr_rec = ct.tr_rec; tt.tr_key = ct.tr_key;
+        tt.ts_key = dv.alloc<u64>(NTR); tt.ts_val = dv.alloc<u32>(NTR);
+        tt.pos_off = t.pos_off; tt.pos_len = t.pos_len; tt.pos_pool = t.pos_pool;
+        tt.tn_parent = dv.alloc<u32>(NTS); tt.tn_move = dv.alloc<u32>(NTS); tt.tn_base = dv.alloc<u32>(NTS);
+        tt.tn_cnt = dv.alloc<u32>(NTS); tt.tn_sib = dv.alloc<u32>(NTS); tt.ns_key = dv.alloc<u64>(NTS);
+        tt.tn_child = dv.alloc<u32>(NTS);
+        LB_LAUNCH(k_tree_build, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
+        tm.kernel_launches += 2;
+    }
     mark(b);  // [5] integrate done
     // ------------------------------------------------------------ phase 6: JSON
     StateTables stt;
@@ -389,6 +424,9 @@ void pipeline(lb_batch* b) {
     stt.op_kind = ct.op_kind; stt.op_vtype = t.op_vtype; stt.op_len = t.op_len; stt.op_counter = t.op_counter;
     stt.op_change = t.op_change; stt.op_val_off = t.op_val_off; stt.op_val_len = t.op_val_len; stt.ch_peer = rt.ch_peer;
     stt.out_row = sp.out_row; stt.out_off = sp.out_off; stt.out_len = sp.out_len;
+    stt.blocks = blk; stt.tn_parent = tt.tn_parent; stt.tn_move = tt.tn_move; stt.tn_base = tt.tn_base; stt.tn_cnt = tt.tn_cnt;
+    stt.tn_sib = tt.tn_sib; stt.tn_child = tt.tn_child; stt.tr_rec = ct.tr_rec;
+    stt.pos_off = t.pos_off; stt.pos_len = t.pos_len; stt.pos_pool = t.pos_pool;
     unsigned long long* d_acc = dv.alloc<unsigned long long>(4, true);
     if (!(b->flags & LB_FLAG_NO_JSON)) {
         LB_LAUNCH(k_json, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, stt, (u8*)nullptr, 0);

@@ -14,6 +14,11 @@ struct ClassifyTables {
     const u32* op_cid; const i32* op_prop; const u8* op_vtype; const u32* op_len; const i32* op_counter;
     const u32* op_change;
     const u32* op_del; const u32* del_peer_idx; const i32* del_counter; const i32* del_len; const u32* peer_map;
+    // movable tree: decoded RawTreeMove fields in, resolved records out (k_tree.cuh)
+    const u32* tr_target_peer; const i32* tr_target_ctr; const u8* tr_parent_kind; const u32* tr_parent_peer;
+    const i32* tr_parent_ctr; const u32* tr_pos;
+    u64* tr_key;            // (lamport << 32 | peer rank << 16): the total order of a tree's ops (diff_calc/tree.rs:445-452)
+    uint4* tr_rec;          // x = target atom (document-relative), y = parent atom | TREE_ROOT | TREE_DELETED, z = position, w = row
     const u32* cid_map; const u32* key_map;
     DocContainer* dcont; const DocPeer* dpeer;
     // outputs
@@ -38,7 +43,10 @@ __device__ __forceinline__ u8 classify_op(u8 ctype, u8 vt) {
             if (vt == VK_LORO_VALUE) return OPK_MAP_SET;
             if (vt == VK_DELETE_ONCE) return OPK_MAP_DEL;
             return OPK_UNSUPPORTED;
-        default: return OPK_UNSUPPORTED;  // tree, movable list, counter, unknown
+        case CT_TREE:
+            if (vt == VK_RAW_TREE_MOVE) return OPK_TREE;
+            return OPK_UNSUPPORTED;
+        default: return OPK_UNSUPPORTED;  // movable list, counter, unknown
     }
 }
 
@@ -63,6 +71,32 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
     }
     if (!t.ch_applied[ch]) kind = OPK_SKIP;
     u32 lam = t.ch_lamport[ch] + (u32)(t.op_counter[row] - t.ch_counter[ch]);
+    if (kind == OPK_TREE) {
+        // target and parent must be atoms the document holds: an applied move causally follows the creation of both
+        // nodes (tree ids are the ids of the create ops: loro-common/src/lib.rs TreeID)
+        u32 ti = t.op_del[row];
+        u32 tp = t.peer_map[bi.peer0 + t.tr_target_peer[ti]];
+        i32 tc = t.tr_target_ctr[ti];
+        u8 pk = t.tr_parent_kind[ti];
+        bool ok = tp < di.P && tc >= 0 && tc < t.dpeer[di.peer0 + tp].end_counter;
+        u32 pa = pk == TRP_ROOT ? TREE_ROOT : TREE_DELETED;
+        if (ok && pk == TRP_NODE) {
+            u32 pp = t.peer_map[bi.peer0 + t.tr_parent_peer[ti]];
+            i32 pc = t.tr_parent_ctr[ti];
+            ok = pp < di.P && pc >= 0 && pc < t.dpeer[di.peer0 + pp].end_counter;
+            if (ok) pa = t.dpeer[di.peer0 + pp].atom_base + (u32)pc;
+        }
+        if (!ok) { kind = OPK_SKIP; di.code = LB_ERR(DOC_ERR_CORRUPT); }
+        else {
+            uint4 tr;
+            tr.x = t.dpeer[di.peer0 + tp].atom_base + (u32)tc;
+            tr.y = pa;
+            tr.z = t.tr_pos[ti];
+            tr.w = (u32)row;
+            t.tr_rec[ti] = tr;
+            t.tr_key[ti] = ((u64)lam << 32) | ((u64)t.dpeer[di.peer0 + t.ch_peer[ch]].rank << 16);
+        }
+    }
     {   // tracker record: everything k_seq needs about this row in one 16-byte load
         u32 w = (u32)t.op_prop[row], aux = 0, rev = 0;
         if (kind == OPK_SEQ_DEL) {
@@ -107,6 +141,7 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
             atomicMax(&t.map_best[di.mapslot0 + (u64)cidx * di.K + key], pack);
             break;
         }
+        case OPK_TREE: if (!di.has_tree) di.has_tree = 1; break;   // (every writer stores the same value)
         default:
             atomicAdd(&dc.unsupported, 1u);
             atomicAdd(&di.has_unsupported, 1u);

@@ -149,6 +149,7 @@ __global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restric
     u32 err = 0;
     if (c.err || !c.empty() || bi.n_changes == 0 || bi.n_changes > bi.len) err = LB_ERR(DOC_ERR_DECODE);   // a change costs >= 1 byte
     bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0;
+    bi.n_pos = bi.pos_bytes = bi.n_tree = 0;
     bi.values_bytes = bi.sec_len[7];
     if (!err) {
         u32 N = bi.n_changes;
@@ -188,20 +189,51 @@ __global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restric
         const u8* col[4];
         u32 col_len[4];
         bool ok = columnar_open(b + bi.sec_off[5], bi.sec_len[5], 4, col, col_len);
-        u64 nops = 0, ndel = 0;
+        u64 nops = 0, ndel = 0, ntree = 0;
         if (ok) {
             Cur v(col[2], col_len[2]);
             while (!v.empty() && !v.err) {
                 i64 sl = v.zigzag();
                 if (sl == 0 || sl > (i64)0x7FFFFFFF || sl < -(i64)0x7FFFFFFF) { v.err = 1; break; }
-                if (sl > 0) { u8 x = v.get(); nops += (u64)sl; if (x == VK_DELETE_SEQ) ndel += (u64)sl; }
-                else { for (i64 q = 0; q < -sl && !v.err; q++) { u8 x = v.get(); if (x == VK_DELETE_SEQ) ndel++; } nops += (u64)(-sl); }
+                if (sl > 0) { u8 x = v.get(); nops += (u64)sl; if (x == VK_DELETE_SEQ) ndel += (u64)sl; if (x == VK_RAW_TREE_MOVE) ntree += (u64)sl; }
+                else {
+                    for (i64 q = 0; q < -sl && !v.err; q++) { u8 x = v.get(); if (x == VK_DELETE_SEQ) ndel++; if (x == VK_RAW_TREE_MOVE) ntree++; }
+                    nops += (u64)(-sl);
+                }
                 if (nops > 0x7FFFFFFFull) { v.err = 1; break; }
             }
             if (v.err) ok = false;
         }
         bi.n_ops = (u32)nops;
         bi.n_dels = (u32)ndel;
+        bi.n_tree = (u32)ntree;
+        // positions arena (arena.rs:159-233): column 0 = common prefix lengths (AnyRle<usize>), column 1 = the rests
+        // (varint n, then n length-prefixed byte strings); sizes of the expanded positions are summed here
+        if (ok && bi.sec_len[4]) {
+            const u8* pc[2];
+            u32 pl[2];
+            if (!columnar_open(b + bi.sec_off[4], bi.sec_len[4], 2, pc, pl)) ok = false;
+            else {
+                RleCur pre(pc[0], pl[0], 1);
+                Cur rest(pc[1], pl[1]);
+                u64 np_ = rest.varint(), total = 0, last = 0;
+                if (np_ > bi.sec_len[4]) ok = false;
+                for (u64 q = 0; ok && q < np_; q++) {
+                    i64 common;
+                    if (!pre.next(&common)) { ok = false; break; }
+                    u64 len = rest.varint();
+                    rest.skip(len);
+                    if (rest.err || common < 0 || (u64)common > last) { ok = false; break; }
+                    last = (u64)common + len;
+                    total += last;
+                    if (total > 0x7FFFFFFFull) { ok = false; break; }
+                }
+                i64 extra;
+                if (ok && (pre.next(&extra) || pre.c.err || !rest.empty())) ok = false;
+                bi.n_pos = (u32)np_;
+                bi.pos_bytes = (u32)total;
+            }
+        }
         if (h.err || k.err || cc.err || !ok || nops == 0) err = LB_ERR(DOC_ERR_DECODE);
         // run-length codes let a few bytes announce billions of rows: table sizes come from these counts, so a block
         // whose counts are out of proportion to its bytes is rejected here (one bad blob must not sink the batch).
@@ -209,9 +241,12 @@ __global__ void k_block_count(const u8* __restrict__ bytes, BlockInfo* __restric
         u64 cap = 8ull * bi.len + 64;
         if (nops > cap || ndeps > cap || N > cap || bi.n_cids > cap || bi.counter_len > (1u << 30) || nops > bi.counter_len)
             err = LB_ERR(DOC_ERR_DECODE);
+        // an expanded position is at most the whole arena long: quadratic blow-ups (every entry re-using a long
+        // prefix) are legal but bounded here so that one block cannot claim gigabytes
+        if (bi.pos_bytes > 64u * bi.len + 4096u) err = LB_ERR(DOC_ERR_DECODE);
     }
     bi.err = err;
-    if (err) { bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0; bi.n_changes = 0; }
+    if (err) { bi.n_peers = bi.n_keys = bi.n_cids = bi.n_ops = bi.n_dels = bi.n_deps = 0; bi.n_changes = 0; bi.n_pos = bi.pos_bytes = bi.n_tree = 0; }
     blocks[i] = bi;
 }
 
@@ -233,7 +268,11 @@ struct Tables {
     u64* op_val_off; u32* op_val_len; u32* op_del;  // op_del: index into del tables for DeleteSeq rows
     // delete start ids
     u32* del_peer_idx; i32* del_counter; i32* del_len;
+    // fractional indexes (expanded) + movable-tree ops (op_del of a RawTreeMove row indexes tr_*)
+    u64* pos_off; u32* pos_len; u8* pos_pool;
+    u32* tr_target_peer; i32* tr_target_ctr; u8* tr_parent_kind; u32* tr_parent_peer; i32* tr_parent_ctr; u32* tr_pos;
 };
+enum { TRP_ROOT = 0, TRP_NODE = 1, TRP_DELETED = 2 };
 
 // ---------------------------------------------------------------- pass 2: fill
 // (no register cap: measured on B200, capping at 128 / 80 / 64 registers costs 1.2x / 2.1x / 2.5x in spills)
@@ -418,6 +457,30 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             if (a.c.err || bb.c.err || cc.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
         }
     } else if (bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    // ---- positions: expand the prefix-compressed fractional indexes into the pool (arena.rs:187-204)
+    if (bi.n_pos) {
+        const u8* pc[2];
+        u32 pl[2];
+        columnar_open(b + bi.sec_off[4], bi.sec_len[4], 2, pc, pl);
+        RleCur pre(pc[0], pl[0], 1);
+        Cur rest(pc[1], pl[1]);
+        (void)rest.varint();
+        u64 w = bi.posb0, last_off = 0;
+        u32 last_len = 0;
+        for (u32 q = 0; q < bi.n_pos; q++) {
+            i64 common = 0;
+            pre.next(&common);
+            u32 len = (u32)rest.varint();
+            if (rest.err || (u64)common > last_len || w + (u64)common + len > bi.posb0 + bi.pos_bytes) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
+            for (u32 k = 0; k < (u32)common; k++) t.pos_pool[w + k] = t.pos_pool[last_off + k];
+            for (u32 k = 0; k < len; k++) t.pos_pool[w + (u32)common + k] = rest.get();
+            t.pos_off[bi.pos0 + q] = w;
+            t.pos_len[bi.pos0 + q] = (u32)common + len;
+            last_off = w;
+            last_len = (u32)common + len;
+            w += last_len;
+        }
+    }
     // ---- ops: 4 columns + values walk
     {
         const u8* col[4];
@@ -429,7 +492,7 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         i32 counter = (i32)bi.counter_start;
         u32 change = 0;
         u32 ch_first_row = 0;
-        u32 ndel = 0;
+        u32 ndel = 0, ntree = 0;
         u32 n_maps = 0;
         i32 next_boundary = (i32)bi.counter_start + (i32)t.ch_len[bi.ch0];
         t.ch_op0[bi.ch0] = bi.op0;
@@ -455,11 +518,34 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
                 if (k != 7 || n_items != (u64)ln) { err = err ? err : LB_ERR(DOC_ERR_CORRUPT); break; }
             }
             const u8* v0 = v.p;
-            // text/list payloads: point past the length prefix where that helps the consumers
-            skip_value(v, (u8)vt, &n_maps);
+            u32 aux_idx = 0xFFFFFFFFu;
+            if ((u8)vt == VK_RAW_TREE_MOVE) {
+                // read_raw_tree_move (value.rs:969-989): subject peer idx / counter, position idx, parent (null = root)
+                u64 sp = v.varint(), sc = v.varint(), pi = v.varint();
+                u8 pn = v.get();
+                u64 pp = 0, pcn = 0;
+                if (!pn) { pp = v.varint(); pcn = v.varint(); }
+                if (ntree >= bi.n_tree || sp >= bi.n_peers || (!pn && pp >= bi.n_peers) || sc > 0x7FFFFFFFull || pcn > 0x7FFFFFFFull) {
+                    err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
+                    break;
+                }
+                u8 pk = pn ? TRP_ROOT : TRP_NODE;
+                if (!pn && t.peer_id[bi.peer0 + (u32)pp] == DELETED_ROOT_PEER && (i32)pcn == DELETED_ROOT_CTR) pk = TRP_DELETED;
+                if (pk != TRP_DELETED && pi >= bi.n_pos) { err = err ? err : LB_ERR(DOC_ERR_CORRUPT); break; }
+                u64 ti = bi.tr0 + ntree++;
+                t.tr_target_peer[ti] = (u32)sp;
+                t.tr_target_ctr[ti] = (i32)sc;
+                t.tr_parent_kind[ti] = pk;
+                t.tr_parent_peer[ti] = (u32)pp;
+                t.tr_parent_ctr[ti] = (i32)pcn;
+                t.tr_pos[ti] = pk == TRP_DELETED ? 0xFFFFFFFFu : (u32)(bi.pos0 + pi);
+                aux_idx = (u32)ti;
+            } else
+                skip_value(v, (u8)vt, &n_maps);
             t.op_val_off[row] = bi.off + (u64)(v0 - b);
             t.op_val_len[row] = (u32)(v.p - v0);
-            t.op_del[row] = (u8)vt == VK_DELETE_SEQ ? (u32)(bi.del0 + ndel++) : 0xFFFFFFFFu;
+            if ((u8)vt == VK_DELETE_SEQ) aux_idx = (u32)(bi.del0 + ndel++);
+            t.op_del[row] = aux_idx;
             counter += (i32)ln;
             // a row never straddles a change boundary: the reference's encoder cuts ops at changes, and everything
             // downstream (atom tables, pending ranges) trusts ch_len -- a blob that disagrees is corrupt
@@ -475,7 +561,7 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             }
         }
         if (v.err || !v.empty() || c0.c.err || c1.c.err || c2.c.err || c3.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
-        if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels))
+        if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels || ntree != bi.n_tree))
             err = LB_ERR(DOC_ERR_CORRUPT);
         blocks[i].n_value_maps = n_maps;
     }

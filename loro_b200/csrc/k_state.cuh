@@ -19,6 +19,10 @@ struct StateTables {
     const u64* op_val_off; const u32* op_val_len;
     const u16* ch_peer;
     const u32* out_row; const u32* out_off; const u32* out_len;
+    // movable tree (k_tree.cuh): node tables per document (base DocInfo::tree0) + positions
+    const BlockInfo* blocks;
+    const u32* tn_parent; const u32* tn_move; const u32* tn_base; const u32* tn_cnt; const u32* tn_sib; const u32* tn_child;
+    const uint4* tr_rec; const u64* pos_off; const u32* pos_len; const u8* pos_pool;
 };
 
 struct Sink {
@@ -59,11 +63,13 @@ struct Sink {
     }
 };
 
-enum { FK_LIST = 1, FK_MAP = 2, FK_VLIST = 3, FK_VMAP = 4, FK_ROOT = 5 };
+enum { FK_LIST = 1, FK_MAP = 2, FK_VLIST = 3, FK_VMAP = 4, FK_ROOT = 5, FK_TREE = 6 };
 struct Frame {
     u8 kind;
     u8 first;      // nothing emitted yet at this level
     u32 a, b, c;   // FK_LIST: cidx, run, elem-in-run ; FK_MAP/FK_ROOT: cidx, last key/root (or NONE) ; FK_V*: remaining
+                   // FK_TREE: cidx, slot whose children are being listed, next child index (id_peer: node whose meta
+                   // map was just printed, or NONE)
     const u8* p;   // value cursor (FK_LIST: inside the current run's payload ; FK_V*: nested items)
     u32 id_peer;   // doc peer idx + counter of the op atom that owns the values being printed
     i32 id_ctr;
@@ -183,8 +189,84 @@ struct Emitter {
             case CT_TEXT: emit_text(cidx); return;
             case CT_LIST: out.put('['); f.kind = FK_LIST; push(f); return;
             case CT_MAP: out.put('{'); f.kind = FK_MAP; f.b = 0xFFFFFFFFu; push(f); return;
+            case CT_TREE:
+                out.put('[');
+                if (!di.has_tree) { out.put(']'); return; }   // no applied tree op in the document: no node tables
+                f.kind = FK_TREE; f.b = (u32)di.atom_total + cidx; f.c = 0; f.id_peer = 0xFFFFFFFFu; push(f);
+                return;
             default: out.puts_("null"); return;
         }
+    }
+    // "<counter>@<peer>" of the node stored at atom `a` (ID display: loro-common/src/id.rs:22-26)
+    __device__ void put_tree_id(u32 a) {
+        u32 p = 0;
+        for (u32 q = 0; q < di.P; q++) {
+            const DocPeer& dp = t.dpeer[di.peer0 + q];
+            if (a >= dp.atom_base && a < dp.atom_base + (u32)dp.end_counter) { p = q; break; }
+        }
+        const DocPeer& dp = t.dpeer[di.peer0 + p];
+        out.put('"');
+        out.put_u64(a - dp.atom_base);
+        out.put('@');
+        out.put_u64(dp.id);
+        out.put('"');
+    }
+    // one step of the hierarchy walk (state/tree_state.rs:814-831 get_all_hierarchy_nodes_under + :1424-1452
+    // TreeNodeWithChildren::into_value, keys in ascending order): no per-level frames -- the walk climbs back
+    // through the parent links
+    __device__ void tree_step(Frame& f) {
+        const u64 tb = di.tree0;
+        const u32 A = (u32)di.atom_total;
+        const u64 tr_lo = t.blocks[di.b0].tr0;
+        if (f.id_peer != 0xFFFFFFFFu) {
+            // the meta map of node f.id_peer has been printed: close the node, continue with its next sibling
+            u32 node = f.id_peer;
+            f.id_peer = 0xFFFFFFFFu;
+            u32 par = t.tn_parent[tb + node];
+            out.puts_(",\"parent\":");
+            if (par == TREE_ROOT) out.puts_("null"); else put_tree_id(par);
+            out.put('}');
+            f.b = par == TREE_ROOT ? A + f.a : par;
+            f.c = t.tn_sib[tb + node] + 1;
+            return;
+        }
+        u32 slot = f.b;
+        if (f.c < t.tn_cnt[tb + slot]) {   // open the next child
+            u32 node = t.tn_child[tb + t.tn_base[tb + slot] + f.c];
+            if (f.c) out.put(',');
+            out.puts_("{\"children\":[");
+            f.b = node;
+            f.c = 0;
+            return;
+        }
+        out.put(']');
+        if (slot >= A) { sp--; return; }   // back at the container's root list: done
+        // children of node `slot` are done: the rest of its object
+        u32 node = slot;
+        uint4 rec = t.tr_rec[tr_lo + t.tn_move[tb + node]];
+        out.puts_(",\"fractional_index\":\"");
+        {
+            const char* HEX = "0123456789ABCDEF";   // crates/fractional_index/src/lib.rs:195-205
+            const u8* pb = t.pos_pool + t.pos_off[rec.z];
+            u32 pl = t.pos_len[rec.z];
+            for (u32 k = 0; k < pl; k++) { out.put((u8)HEX[pb[k] >> 4]); out.put((u8)HEX[pb[k] & 15]); }
+        }
+        out.puts_("\",\"id\":");
+        put_tree_id(node);
+        out.puts_(",\"index\":");
+        out.put_u64(t.tn_sib[tb + node]);
+        out.puts_(",\"meta\":");
+        // TreeID::associated_meta_container: the Map whose id is the node's id
+        u32 p = 0;
+        for (u32 q = 0; q < di.P; q++) {
+            const DocPeer& dp = t.dpeer[di.peer0 + q];
+            if (node >= dp.atom_base && node < dp.atom_base + (u32)dp.end_counter) { p = q; break; }
+        }
+        const DocPeer& dp = t.dpeer[di.peer0 + p];
+        f.id_peer = node;
+        int my = sp - 1;
+        open_container(find_child(dp.id, (i32)(node - dp.atom_base), CT_MAP), CT_MAP);
+        (void)my;
     }
     // print a scalar LoroValue (kinds 0-6) at *pp into `o`; false (nothing consumed) for lists, maps, containers
     __device__ bool emit_scalar(Sink& o, const u8** pp, const u8* end) {
@@ -469,6 +551,7 @@ struct Emitter {
                     emit_value(&p, end, f.id_peer, f.id_ctr);
                     break;
                 }
+                case FK_TREE: tree_step(f); break;
                 default: err = LB_ERR(DOC_ERR_CAPACITY);
             }
         }

@@ -17,9 +17,11 @@ struct BlockInfo {
     u32 n_peers, n_keys, n_cids, n_ops, n_dels, n_deps;
     u32 values_bytes;
     u32 n_value_maps;   // LoroValue::Map levels inside the values section (their keys are block-local indices)
-    u32 pad_;
+    u32 n_pos;          // fractional indexes in the positions arena (encoding/arena.rs:159-233)
+    u32 pos_bytes;      // their total size once the common prefixes are expanded
+    u32 n_tree;         // RawTreeMove rows (encoding/value.rs:969-989)
     // exclusive-scan bases into the batch-wide tables (filled by the host after the count pass)
-    u64 peer0, key0, cid0, ch0, dep0, op0, del0;
+    u64 peer0, key0, cid0, ch0, dep0, op0, del0, pos0, posb0, tr0;
 };
 
 // One document of the batch (one blob).
@@ -46,6 +48,9 @@ struct DocInfo {
     u32 n_deps;         // cross-peer deps of all changes (capacity estimate)
     u32 n_blobs;        // blobs imported into this document (import_batch)
     u32 has_unsupported;
+    u32 has_tree;       // any applied movable-tree op (k_tree.cuh)
+    u32 pad2;
+    u64 tree0;          // base into the per-document tree node tables (atom_total + C slots)
     u64 json_off;
     u32 json_len;
     u32 pad;

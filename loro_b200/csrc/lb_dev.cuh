@@ -42,7 +42,13 @@ enum { VK_NULL = 0, VK_TRUE = 1, VK_FALSE = 2, VK_I64 = 3, VK_F64 = 4, VK_STR = 
 // container types (reference: loro-common/src/lib.rs:293-347)
 enum { CT_MAP = 0, CT_LIST = 1, CT_TEXT = 2, CT_TREE = 3, CT_MOVABLE = 4, CT_COUNTER = 5 };
 // engine op classes
-enum { OPK_SKIP = 0, OPK_SEQ_INS = 1, OPK_SEQ_DEL = 2, OPK_MAP_SET = 3, OPK_MAP_DEL = 4, OPK_UNSUPPORTED = 5 };
+enum { OPK_SKIP = 0, OPK_SEQ_INS = 1, OPK_SEQ_DEL = 2, OPK_MAP_SET = 3, OPK_MAP_DEL = 4, OPK_UNSUPPORTED = 5, OPK_TREE = 6 };
+// movable tree: parent slots that are not nodes (reference: state/tree_state.rs:69-77 TreeParentId)
+#define TREE_ROOT 0xFFFFFFFFu
+#define TREE_DELETED 0xFFFFFFFEu
+#define TREE_UNEXIST 0xFFFFFFFDu
+#define DELETED_ROOT_PEER 0xFFFFFFFFFFFFFFFFull   // loro-common/src/lib.rs:631 DELETED_TREE_ROOT
+#define DELETED_ROOT_CTR 0x7FFFFFFF
 
 #define PEER_NONE 0xFFFFu     // "no origin"
 #define PEER_UNKNOWN 0xFFFEu  // the tracker's placeholder span (reference: tracker.rs:38-63)
