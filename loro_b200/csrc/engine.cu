@@ -337,7 +337,7 @@ void pipeline(lb_batch* b) {
     ct.peer_map = rt.peer_map;
     ct.tr_target_peer = t.tr_target_peer; ct.tr_target_ctr = t.tr_target_ctr; ct.tr_parent_kind = t.tr_parent_kind;
     ct.tr_parent_peer = t.tr_parent_peer; ct.tr_parent_ctr = t.tr_parent_ctr; ct.tr_pos = t.tr_pos;
-    ct.tr_rec = dv.alloc<uint4>(NTR); ct.tr_key = dv.alloc<u64>(NTR);
+    ct.tr_rec = dv.alloc<uint4>(NTR); ct.tr_key = dv.alloc<u64>(NTR); ct.tr_ids = dv.alloc<uint4>(NTR);
     if (NTR) {   // ops that are not applied keep row = NONE / key = +inf
         CK(cudaMemsetAsync(ct.tr_rec, 0xFF, sizeof(uint4) * NTR, st));
         CK(cudaMemsetAsync(ct.tr_key, 0xFF, sizeof(u64) * NTR, st));
@@ -469,6 +469,11 @@ void pipeline(lb_batch* b) {
         xt.op_kind = ct.op_kind; xt.op_vtype = t.op_vtype; xt.op_cidx = ct.op_cidx; xt.op_prop = t.op_prop; xt.op_len = t.op_len;
         xt.op_counter = t.op_counter; xt.op_val_off = t.op_val_off; xt.op_val_len = t.op_val_len; xt.op_del = t.op_del;
         xt.op_aux = ct.op_aux; xt.del_counter = t.del_counter; xt.del_len = t.del_len;
+        xt.tr_ids = ct.tr_ids; xt.tr_pos = t.tr_pos; xt.pos_off = t.pos_off; xt.pos_len = t.pos_len; xt.pos_pool = t.pos_pool;
+        if (NTR) {
+            xt.pos_rank = dv.alloc<u32>(NPOS); xt.pos_rep = dv.alloc<u32>(NPOS);
+            xt.ps_key = dv.alloc<u64>(NPOS); xt.ps_val = dv.alloc<u32>(NPOS);
+        }
         xt.x_rec = dv.alloc<uint4>(NR); xt.r_bytes = dv.alloc<u32>(NR); xt.r_flag = dv.alloc<u8>(NR);
         xt.ch_nseg = dv.alloc<u32>(NCH + 1, true); xt.ch_novf = dv.alloc<u32>(NCH + 1, true);
         xt.ch_seg0 = dv.alloc<u64>(NCH + 2, true);
@@ -490,6 +495,7 @@ void pipeline(lb_batch* b) {
         xt.fc_from = dv.alloc<u32>(SEGCAP); xt.fc_atoms = dv.alloc<u32>(SEGCAP); xt.fc_nrows = dv.alloc<u32>(SEGCAP);
         xt.fc_ndel = dv.alloc<u32>(SEGCAP); xt.fc_block = dv.alloc<u8>(SEGCAP);
         LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
+        if (NTR) { LB_LAUNCH(k_exp_posrank, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, xt); tm.kernel_launches += 1; }
         if (NCH) LB_LAUNCH(k_exp_arena, nblk(NCH, 64), 64, 0, st, NCH, xt, b->d_docs);
         run_scans(b, {ScanJob{(const u8*)xt.ch_aval, (u8*)xt.ch_aval0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_astr, (u8*)xt.ch_astr0, 4, 8, NCH}});
         if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);

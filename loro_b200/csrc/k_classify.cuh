@@ -18,6 +18,7 @@ struct ClassifyTables {
     const u32* tr_target_peer; const i32* tr_target_ctr; const u8* tr_parent_kind; const u32* tr_parent_peer;
     const i32* tr_parent_ctr; const u32* tr_pos;
     u64* tr_key;            // (lamport << 32 | peer rank << 16): the total order of a tree's ops (diff_calc/tree.rs:445-452)
+    uint4* tr_ids;          // x = target peer (document level), y = target counter, z = parent kind | parent peer << 2, w = parent counter
     uint4* tr_rec;          // x = target atom (document-relative), y = parent atom | TREE_ROOT | TREE_DELETED, z = position, w = row
     const u32* cid_map; const u32* key_map;
     DocContainer* dcont; const DocPeer* dpeer;
@@ -80,9 +81,9 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
         u8 pk = t.tr_parent_kind[ti];
         bool ok = tp < di.P && tc >= 0 && tc < t.dpeer[di.peer0 + tp].end_counter;
         u32 pa = pk == TRP_ROOT ? TREE_ROOT : TREE_DELETED;
+        u32 pp = pk == TRP_ROOT ? 0u : t.peer_map[bi.peer0 + t.tr_parent_peer[ti]];
+        i32 pc = t.tr_parent_ctr[ti];
         if (ok && pk == TRP_NODE) {
-            u32 pp = t.peer_map[bi.peer0 + t.tr_parent_peer[ti]];
-            i32 pc = t.tr_parent_ctr[ti];
             ok = pp < di.P && pc >= 0 && pc < t.dpeer[di.peer0 + pp].end_counter;
             if (ok) pa = t.dpeer[di.peer0 + pp].atom_base + (u32)pc;
         }
@@ -94,6 +95,9 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
             tr.z = t.tr_pos[ti];
             tr.w = (u32)row;
             t.tr_rec[ti] = tr;
+            uint4 ids;
+            ids.x = tp; ids.y = (u32)tc; ids.z = (u32)pk | (pp << 2); ids.w = (u32)pc;
+            t.tr_ids[ti] = ids;
             t.tr_key[ti] = ((u64)lam << 32) | ((u64)t.dpeer[di.peer0 + t.ch_peer[ch]].rank << 16);
         }
     }

@@ -30,15 +30,15 @@
 #pragma once
 #include "lb_defs.h"
 
-enum { XK_NONE = 0, XK_LIST = 1, XK_TEXT = 2, XK_DEL = 3, XK_MAPSET = 4, XK_MAPDEL = 5 };
+enum { XK_NONE = 0, XK_LIST = 1, XK_TEXT = 2, XK_DEL = 3, XK_MAPSET = 4, XK_MAPDEL = 5, XK_TREE = 6 };
 #define LB_MAX_BLOCK_SIZE 4096   // change_store.rs:37
 #define XF_HEAD 1u               // row starts a (merged) op
 #define XF_SEG 2u                // row starts a segment of a split change
 
 struct XDoc {          // per document
     u32 n_fc, n_mb;    // final changes, output blocks
-    u32 flags;         // bit0: export unsupported for this document
-    u32 pad;
+    u32 flags;         // bit0: export unsupported for this document ; bit1: the document has movable-tree ops
+    u32 n_prank;       // distinct fractional indexes of the document (k_exp_posrank)
     u64 ob0;           // first output block (batch-wide)
     u64 scratch0;      // first scratch word of this doc's blocks
     u64 exp_off;       // offset of the blob in the export buffer
@@ -50,11 +50,11 @@ struct XBlock {        // one output block
     u32 fc0, fc1;      // final-change range (absolute indices into fc_*)
     u32 len;           // encoded bytes (without the ULEB length prefix)
     u32 sec_len[8];
-    u32 col_len[8];    // ops columns 0-3, delete columns 4-6, [7] = register sizes
+    u32 col_len[10];   // ops columns 0-3, delete columns 4-6, [7] = register sizes, [8..9] = position columns
     u64 off;           // offset of the block bytes inside the document's blob
     u64 scratch;       // scratch words of this block
     u32 n_rows, n_dels;            // scratch capacities: rows, delete ops
-    u32 n_ops, n_del_ops, n_cids, pad;   // after the gather: merged ops, merged deletes, containers
+    u32 n_ops, n_del_ops, n_cids, n_pos; // after the gather: merged ops, merged deletes, containers, positions
 };
 
 struct ExportTables {
@@ -67,6 +67,12 @@ struct ExportTables {
     const u8* op_kind; const u8* op_vtype; const u32* op_cidx; const i32* op_prop; const u32* op_len; const i32* op_counter;
     const u64* op_val_off; const u32* op_val_len; const u32* op_del; const u32* op_aux;
     const i32* del_counter; const i32* del_len;
+    // movable tree: decoded RawTreeMove fields (k_decode.cuh) + the document-wide order of the fractional indexes
+    const uint4* tr_ids; const u32* tr_pos;   // (k_classify.cuh) subject / parent at document level ; position entry
+    const u64* pos_off; const u32* pos_len; const u8* pos_pool;
+    u32* pos_rank;     // per position entry: dense rank of its bytes among the document's positions
+    u32* pos_rep;      // per (document position base + rank): one entry holding those bytes
+    u64* ps_key; u32* ps_val;   // sort space of k_exp_posrank
     // per row
     uint4* x_rec;      // resolved op record per row (xop_pack): kind | reversed | container, counter, prop, arena start / target counter
     u32* r_bytes;      // text rows: payload bytes
@@ -124,6 +130,7 @@ __device__ __forceinline__ u32 xop_estimate(const XOp& o) {   // list_op.rs:109-
         case XK_LIST: return 4 * o.atoms;
         case XK_TEXT: return o.f1 - o.f0;
         case XK_DEL: return 8;
+        case XK_TREE: return 8;        // op/content.rs:70-77
         default: return 3;
     }
 }
@@ -211,6 +218,7 @@ __device__ inline XOp xop_resolve(const ExportTables& t, const DocInfo& di, u32 
             o.xk = kind == OPK_MAP_SET ? XK_MAPSET : XK_MAPDEL;
             o.prop = (i32)t.key_map[t.blocks[t.ch_block[ch]].key0 + (u32)o.prop];
             break;
+        case OPK_TREE: o.xk = XK_TREE; o.prop = 0; o.f0 = t.op_del[row]; break;   // f0 = index into the tr_* tables
         default: o.xk = XK_NONE;
     }
     return o;
@@ -295,6 +303,7 @@ __global__ void k_exp_init(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
     memset(&x, 0, sizeof(x));
     if (di.code == DOC_OK) {
         if (di.has_unsupported & 0x7FFFFFFFu) x.flags |= 1;
+        if (di.has_tree) x.flags |= 2;
         for (u32 b = di.b0; b < di.b1; b++)
             if (t.blocks[b].n_value_maps) x.flags |= 1;
     }
@@ -729,7 +738,7 @@ __global__ void k_exp_list(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
     memset(&b, 0, sizeof(b));
     for (u64 k = f0; k < f0 + x.n_fc; k++) {
         if (t.fc_block[k]) {
-            if (idx >= 0) { b.fc1 = (u32)k; xb[x.ob0 + idx] = b; scr += regs + 5 * b.n_rows + 3 * b.n_dels; }
+            if (idx >= 0) { b.fc1 = (u32)k; xb[x.ob0 + idx] = b; scr += regs + (5 + ((x.flags >> 1) & 1u)) * b.n_rows + 3 * b.n_dels; }
             idx++;
             memset(&b, 0, sizeof(b));
             b.doc = d; b.fc0 = (u32)k; b.scratch = scr;
@@ -751,7 +760,7 @@ __global__ void k_exp_sizes(const DocInfo* __restrict__ docs, u32 n_docs, Export
     if (nb) {
         u64 f0 = di.ch0 + t.ch_seg0[di.ch0];
         words = (u64)nb * 2 * (di.P + di.K + di.C);
-        for (u64 k = f0; k < f0 + x.n_fc; k++) words += 5ull * t.fc_nrows[k] + 3ull * t.fc_ndel[k];
+        for (u64 k = f0; k < f0 + x.n_fc; k++) words += (5ull + ((x.flags >> 1) & 1u)) * t.fc_nrows[k] + 3ull * t.fc_ndel[k];
     }
     n_blocks[d] = nb;
     n_scratch[d] = (u32)words;
@@ -892,8 +901,61 @@ __device__ __forceinline__ u8 xk_value_type(u8 xk) {
         case XK_LIST: case XK_MAPSET: return VK_LORO_VALUE;
         case XK_TEXT: return VK_STR;
         case XK_DEL: return VK_DELETE_SEQ;
+        case XK_TREE: return VK_RAW_TREE_MOVE;
         default: return VK_DELETE_ONCE;
     }
+}
+
+// ---------------------------------------------------------------------------------------------- fractional indexes
+// encode_block pre-fills its position register with the block's positions in sorted order (block_encode.rs:156-178).
+// The byte-string sort happens once per document: a warp sorts the document's position entries (first eight bytes as
+// the key, full comparison on ties) and hands every entry the dense rank of its bytes; a block then only sorts ranks.
+__device__ inline int xpos_cmp(const ExportTables& t, u32 a, u32 b) {
+    if (a == b) return 0;
+    const u8* pa = t.pos_pool + t.pos_off[a];
+    const u8* pb = t.pos_pool + t.pos_off[b];
+    u32 la = t.pos_len[a], lb = t.pos_len[b];
+    u32 n = la < lb ? la : lb;
+    for (u32 i = 0; i < n; i++)
+        if (pa[i] != pb[i]) return pa[i] < pb[i] ? -1 : 1;
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+__global__ void k_exp_posrank(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t) {
+    u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    if (di.code != DOC_OK || !di.has_tree) return;
+    const u64 p_lo = t.blocks[di.b0].pos0;
+    const u32 n = (u32)(t.blocks[di.b1].pos0 - p_lo);
+    u64* key = t.ps_key + p_lo;
+    u32* val = t.ps_val + p_lo;
+    for (u32 i = lane; i < n; i += 32) {
+        const u8* pb = t.pos_pool + t.pos_off[p_lo + i];
+        u32 pl = t.pos_len[p_lo + i];
+        u64 k = 0;
+        for (u32 q = 0; q < 8; q++) k = (k << 8) | (q < pl ? pb[q] : 0u);
+        if (k == ~0ull) k--;          // keep +inf free (the sort treats it as padding); ties fall back to the bytes
+        key[i] = k;
+        val[i] = i;
+    }
+    __syncwarp();
+    warp_sort_pairs(key, val, n, lane, [&](u32 a, u32 b) -> bool { return xpos_cmp(t, (u32)p_lo + a, (u32)p_lo + b) < 0; });
+    // dense ranks: a new rank starts wherever the bytes differ from the predecessor's
+    u32 carry = 0;
+    for (u32 j0 = 0; j0 < n; j0 += 32) {
+        u32 j = j0 + (u32)lane;
+        int fresh = 0;
+        if (j < n) fresh = (j == 0 || xpos_cmp(t, (u32)p_lo + val[j - 1], (u32)p_lo + val[j]) != 0) ? 1 : 0;
+        int incl = warp_incl_scan(fresh, lane);
+        if (j < n) {
+            u32 rank = carry + (u32)incl - 1;
+            t.pos_rank[p_lo + val[j]] = rank;
+            if (fresh) t.pos_rep[p_lo + rank] = (u32)p_lo + val[j];
+        }
+        carry += (u32)__shfl_sync(LB_FULL, incl, 31);
+    }
+    if (lane == 0) t.xdoc[d].n_prank = carry;
 }
 
 // thread per output block.  pass 0: gather ops into scratch columns, registers, section sizes ; pass 1: bytes.
@@ -917,6 +979,27 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     u32* d_peer = c_bytes + B.n_rows;          // delete columns, capacity n_dels each
     u32* d_ctr = d_peer + B.n_dels;
     u32* d_len = d_ctr + B.n_dels;
+    const bool has_tree = (t.xdoc[B.doc].flags & 2u) != 0;
+    u32* p_rank = d_len + B.n_dels;            // tree documents only (capacity n_rows): sorted distinct position ranks
+    const u64 pos_lo = has_tree ? t.blocks[di.b0].pos0 : 0;
+    // local index of a fractional index inside this block's position register
+    auto pos_local = [&](u32 gpos) -> u32 {
+        u32 r = t.pos_rank[gpos];
+        u32 lo = 0, hi = B.n_pos;
+        while (lo < hi) { u32 mid = (lo + hi) >> 1; if (p_rank[mid] < r) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    // doc-level peer index + counter of a tree op's subject / parent
+    // bytes of one RawTreeMove value (value.rs write_raw_tree_move): subject, position, parent
+    auto w_tree_value = [&](XSink& s, u32 ti) {
+        uint4 ids = t.tr_ids[ti];
+        u32 pk = ids.z & 3u;
+        s.varint(peers.inv[ids.x]);
+        s.varint(ids.y);
+        s.varint(pk == TRP_DELETED ? 0u : pos_local(t.tr_pos[ti]));
+        s.put(pk == TRP_ROOT ? 1 : 0);
+        if (pk != TRP_ROOT) { s.varint(peers.inv[ids.z >> 2]); s.varint(ids.w); }
+    };
     const u32 fc0 = B.fc0, N = B.fc1 - B.fc0;
     const u32 first_src = t.fc_src[fc0];
     u32 n_dep = 0;
@@ -927,6 +1010,37 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         for (u32 i = 0; i < C; i++) cids.inv[i] = 0xFFFFFFFFu;
         peers.n = keys.n = cids.n = 0;
         peers.reg(t.peer_map[t.blocks[t.ch_block[first_src]].peer0]);   // the author of the block's changes
+        B.n_pos = 0;
+        if (has_tree) {
+            // position register, pre-filled in sorted order (block_encode.rs:156-178): ranks of the block's create /
+            // move ops, heap-sorted, duplicates dropped
+            u32 m = 0;
+            for (u32 j = 0; j < N; j++) {
+                XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
+                u32 left = t.fc_nrows[fc0 + j];
+                while (left) {
+                    uint4 r = xr_rec(t, it.row());
+                    if ((r.x & 7u) == XK_TREE && t.tr_pos[r.w] != 0xFFFFFFFFu) p_rank[m++] = t.pos_rank[t.tr_pos[r.w]];
+                    left--;
+                    if (left) it.next();
+                }
+            }
+            auto sift = [&](u32 root, u32 end) {
+                while (true) {
+                    u32 c = 2 * root + 1;
+                    if (c >= end) break;
+                    if (c + 1 < end && p_rank[c + 1] > p_rank[c]) c++;
+                    if (p_rank[root] >= p_rank[c]) break;
+                    u32 tmp = p_rank[root]; p_rank[root] = p_rank[c]; p_rank[c] = tmp;
+                    root = c;
+                }
+            };
+            for (u32 i = m / 2; i-- > 0;) sift(i, m);
+            for (u32 e = m; e-- > 1;) { u32 tmp = p_rank[0]; p_rank[0] = p_rank[e]; p_rank[e] = tmp; sift(0, e); }
+            u32 w = 0;
+            for (u32 i = 0; i < m; i++) if (i == 0 || p_rank[i] != p_rank[w - 1]) p_rank[w++] = p_rank[i];
+            B.n_pos = w;
+        }
         // ops in order: containers, map keys, delete targets (block_encode.rs:180-236)
         u32 n_ops = 0, n_del = 0, vbytes = 0;
         u32 prev_cidx = 0, prev_prop = 0, prev_dp = 0, prev_dc = 0, prev_dl = 0;   // 32-bit wrap-around deltas
@@ -946,6 +1060,15 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                 c_vt[n_ops] = xk_value_type(o.xk) | ((u32)o.xk << 8);
                 c_atoms[n_ops] = o.atoms;
                 c_bytes[n_ops] = o.xk == XK_TEXT ? o.f1 - o.f0 : first_row;
+                if (o.xk == XK_TREE) {      // encode_tree_op (block_encode.rs:324-362): subject peer, then parent peer
+                    uint4 ids = t.tr_ids[o.f0];
+                    peers.reg(ids.x);
+                    if ((ids.z & 3u) != TRP_ROOT) peers.reg(ids.z >> 2);
+                    XSink cs;
+                    cs.dst = nullptr; cs.n = 0;
+                    w_tree_value(cs, o.f0);
+                    vbytes += (u32)cs.n;
+                }
                 if (o.xk == XK_DEL) {
                     u32 dp = peers.reg(o.f0);
                     d_peer[n_del] = dp - prev_dp; prev_dp = dp;
@@ -1056,6 +1179,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                     xk = c_vt[op] >> 8;
                     if (xk == XK_LIST) { s.put(7); s.varint(c_atoms[op]); }
                     else if (xk == XK_TEXT) s.varint(c_bytes[op]);
+                    else if (xk == XK_TREE) w_tree_value(s, xr_rec(t, row).w);
                     op++;
                 }
                 fresh = false;
@@ -1067,6 +1191,28 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                 }
                 left--;
                 if (left) it.next();
+            }
+        }
+    };
+    // PositionArena::from_positions + encode_v2 (arena.rs:168-183, 218-224): common prefix with the predecessor
+    auto pos_bytes_of = [&](u32 i, const u8** pb) -> u32 { u32 g = t.pos_rep[pos_lo + p_rank[i]]; *pb = t.pos_pool + t.pos_off[g]; return t.pos_len[g]; };
+    auto pos_common = [&](u32 i) -> u32 {
+        if (i == 0) return 0;
+        const u8 *a, *b;
+        u32 la = pos_bytes_of(i - 1, &a), lb = pos_bytes_of(i, &b);
+        u32 n = la < lb ? la : lb, k = 0;
+        while (k < n && a[k] == b[k]) k++;
+        return k;
+    };
+    auto w_poscol = [&](XSink& s, int col) {
+        if (col == 0) enc_anyrle(s, B.n_pos, [&](u32 i) -> i64 { return (i64)pos_common(i); }, WrVarint());
+        else {
+            s.varint(B.n_pos);
+            for (u32 i = 0; i < B.n_pos; i++) {
+                const u8* pb;
+                u32 pl = pos_bytes_of(i, &pb), c = pos_common(i);
+                s.varint(pl - c);
+                s.copy(pb + c, pl - c);
             }
         }
     };
@@ -1082,8 +1228,13 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         s.n = 0; w_meta(s); B.sec_len[1] = (u32)s.n;
         s.n = 0; w_cids(s); B.sec_len[2] = (u32)s.n;
         s.n = 0; w_keys(s); B.sec_len[3] = (u32)s.n;
-        B.sec_len[4] = 0;
-        u32 tot = 2;   // varint(1) varint(4)
+        u32 tot = 0;
+        if (B.n_pos) {
+            tot = 2;   // varint(1) varint(2)
+            for (int c = 0; c < 2; c++) { s.n = 0; w_poscol(s, c); B.col_len[8 + c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
+        }
+        B.sec_len[4] = tot;
+        tot = 2;   // varint(1) varint(4)
         for (int c = 0; c < 4; c++) { s.n = 0; w_opcol(s, c); B.col_len[c] = (u32)s.n; tot += varint_len(s.n) + (u32)s.n; }
         B.sec_len[5] = tot;
         if (n_del) {
@@ -1112,7 +1263,11 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     s.varint(B.sec_len[1]); w_meta(s);
     s.varint(B.sec_len[2]); w_cids(s);
     s.varint(B.sec_len[3]); w_keys(s);
-    s.varint(0);
+    s.varint(B.sec_len[4]);
+    if (B.n_pos) {
+        s.varint(1); s.varint(2);
+        for (int c = 0; c < 2; c++) { s.varint(B.col_len[8 + c]); w_poscol(s, c); }
+    }
     s.varint(B.sec_len[5]);
     s.varint(1); s.varint(4);
     for (int c = 0; c < 4; c++) { s.varint(B.col_len[c]); w_opcol(s, c); }

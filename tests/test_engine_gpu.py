@@ -242,3 +242,64 @@ def test_export_inserts_larger_than_a_block():
     from tests.export_checks import check_export_against_oracle
     from tests.test_export_emu import big_insert_documents
     check_export_against_oracle(big_insert_documents())
+
+
+# ------------------------------------------------------------------ movable tree (SURVEY 8a row a16, config C5 shape)
+def test_tree_known_answer_and_cycles():
+    """loro_rust_test.rs:426-444 through the CUDA path, plus two concurrent moves that would close a cycle."""
+    d = OracleDoc(1)
+    t = d.get_tree("tree")
+    root = d.tree_create(t)
+    root2 = d.tree_create(t)
+    d.tree_move(t, root2, root)
+    d.map_set(d.tree_meta(root), "color", "red")
+    a, b = OracleDoc(1), OracleDoc(2)
+    ta, tb = a.get_tree("t"), b.get_tree("t")
+    x = a.tree_create(ta)
+    y = a.tree_create(ta)
+    workloads.merge(b, a)
+    a.tree_move(ta, x, y)
+    b.tree_move(tb, y, x)
+    workloads.merge(a, b)
+    batch = check_batch_against_oracle([d.export_updates(), a.export_updates()])
+    assert batch.get_deep_value(0) == {"tree": [
+        {"parent": None, "meta": {"color": "red"}, "id": "0@1", "index": 0, "fractional_index": "80", "children": [
+            {"parent": "0@1", "meta": {}, "id": "1@1", "index": 0, "children": [], "fractional_index": "80"}]}]}
+    v = batch.get_deep_value(1)["t"]
+    assert [n["id"] for n in v] == ["1@1"] and [c["id"] for c in v[0]["children"]] == ["0@1"]
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_tree_random_histories_c5_shape(seed):
+    """C5 shape at a size the oracle replays in seconds: a base tree by one peer, then concurrent creates / moves
+    (cycles across peers included) / deletes / meta writes by 2-4 peers; state JSON equal to the oracle's."""
+    blobs, jsons = [], []
+    for k in range(24):
+        blob, js, vv, _ = workloads.make_tree_history(seed * 100 + k, n_sites=2 + (seed + k) % 3, n_base=30 + 10 * (k % 8),
+                                                      n_ops=120 + 20 * (k % 10), mixed=k % 3 == 0)
+        blobs.append(blob)
+        jsons.append(js)
+    check_batch_against_oracle(blobs, expect_json=jsons)
+
+
+def test_tree_export_and_large_tree():
+    from tests.export_checks import check_export_against_oracle
+    import random
+    blobs = [workloads.make_tree_history(900 + s, n_sites=2 + s % 3, n_base=40, n_ops=200, mixed=s % 2 == 0)[0] for s in range(12)]
+    rnd = random.Random(4)
+    a, b = OracleDoc(21), OracleDoc(22)
+    ta, tb = a.get_tree("tree"), b.get_tree("tree")
+    nodes = []
+    for i in range(1500):
+        parent = rnd.choice(nodes) if nodes and rnd.random() < 0.7 else None
+        nodes.append(a.tree_create(ta, parent, -1 if rnd.random() < 0.6 else 0))
+        if i % 7 == 0:
+            a.commit()
+    workloads.merge(b, a)
+    for d, t in ((a, ta), (b, tb)):
+        for _ in range(500):
+            workloads.random_tree_edit(rnd, d, t, p_create=0.2)
+    workloads.merge(a, b)
+    blobs.append(a.export_updates())
+    check_batch_against_oracle(blobs)
+    check_export_against_oracle(blobs)

@@ -81,3 +81,46 @@ def test_tree_equal_positions_and_two_trees():
                 if i != j:
                     workloads.merge(docs[i], docs[j])
     check_batch_against_oracle([docs[0].export_updates()], lib_path=EMU)
+
+
+def test_tree_export_matches_oracle_bytes():
+    """Re-export of tree documents (positions arena with common-prefix compression in sorted order, RawTreeMove
+    values, the DELETED_TREE_ROOT pseudo peer of deletes) is byte-identical to the oracle's and round-trips."""
+    from tests.export_checks import check_export_against_oracle
+    d = OracleDoc(1)
+    t = d.get_tree("tree")
+    root = d.tree_create(t)
+    root2 = d.tree_create(t)
+    d.tree_move(t, root2, root)
+    d.map_set(d.tree_meta(root), "color", "red")
+    d.tree_delete(t, root2)
+    blobs = [d.export_updates()]
+    for seed in range(5):
+        blobs.append(workloads.make_tree_history(900 + seed, n_sites=2 + seed % 3, n_base=25, n_ops=120, mixed=seed % 2 == 0)[0])
+    check_export_against_oracle(blobs, lib_path=EMU)
+
+
+def test_tree_many_nodes_several_blocks_per_peer():
+    """A tree large enough for several change blocks per peer (8 estimated bytes per op, 4 KB blocks): block-local
+    position registers, positions shared between blocks, long sibling lists (the warp-sorted path)."""
+    from tests.export_checks import check_export_against_oracle
+    import random
+    rnd = random.Random(4)
+    a, b = OracleDoc(21), OracleDoc(22)
+    ta, tb = a.get_tree("tree"), b.get_tree("tree")
+    nodes = []
+    for i in range(700):
+        parent = rnd.choice(nodes) if nodes and rnd.random() < 0.7 else None
+        nodes.append(a.tree_create(ta, parent, -1 if rnd.random() < 0.6 else 0))
+        if i % 7 == 0:
+            a.commit()
+    workloads.merge(b, a)
+    for d, t in ((a, ta), (b, tb)):
+        for _ in range(250):
+            workloads.random_tree_edit(rnd, d, t, p_create=0.2)
+    workloads.merge(a, b)
+    workloads.merge(b, a)
+    assert a.json_text() == b.json_text()
+    blob = a.export_updates()
+    check_batch_against_oracle([blob], lib_path=EMU)
+    check_export_against_oracle([blob], lib_path=EMU)
