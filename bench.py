@@ -34,9 +34,14 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--docs", type=int, default=0, help="documents per GPU (0 = as many of the 100k as the host can generate in ~90 s)")
+    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C5"],
+                    help="BASELINE.json config: C3 = 100k docs x 10k mixed List/Map ops, 3 peers (the config the metric is quoted on); "
+                         "C2 = automerge-paper text trace x 4096 docs; C5 = 10k docs x 5k-node movable trees with 3 x 1k concurrent moves")
+    ap.add_argument("--docs", type=int, default=0, help="documents per GPU (0 = the config's figure: C3 100k, C2 4096, C5 10k)")
     ap.add_argument("--ops-per-doc", type=int, default=10000)
     ap.add_argument("--peers", type=int, default=3)
+    ap.add_argument("--tree-nodes", type=int, default=5000, help="C5: nodes of the base tree")
+    ap.add_argument("--tree-moves", type=int, default=1000, help="C5: concurrent moves per peer")
     ap.add_argument("--distinct", type=int, default=0, help="distinct seeded docs generated per GPU; the batch cycles through them (0 = all distinct)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-docs", type=int, default=0)
@@ -114,26 +119,68 @@ class ClockSampler:
 
 
 def default_docs(args, world):
-    """Documents per GPU: BASELINE's C3 figure (100 k) at every N, so that per-GPU work is fixed (weak scaling)."""
-    return args.docs or 100000
+    """Documents per GPU: BASELINE's figure for the config at every N, so that per-GPU work is fixed (weak scaling)."""
+    return args.docs or {"C3": 100000, "C2": 4096, "C5": 10000}[args.config]
+
+
+class TraceBatch:
+    """Config C2: the automerge-paper editing trace (259,778 single-character patches applied to a root Text by one
+    peer, a transaction every 10 patches, exported with all_updates) -- the committed fixture
+    tests/golden/automerge_trace_blob.bin.gz, made by tests/golden/make_golden.py with the oracle.  Every document
+    of the batch is a copy of that blob with its own bytes in HBM."""
+
+    def __init__(self):
+        import gzip
+        import numpy as np
+        blob = gzip.open(os.path.join(ROOT, "tests", "golden", "automerge_trace_blob.bin.gz"), "rb").read()
+        self.n_docs = 1
+        self.bytes = np.zeros(((len(blob) + 15) & ~15) + 64, dtype=np.uint8)
+        self.bytes[:len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        self.offsets = np.zeros(1, dtype=np.uint64)
+        self.lens = np.array([len(blob)], dtype=np.uint32)
+        self.atom_ops = 0   # taken from the engine's counters (sum of change.atom_len)
+        self._blob = blob
+
+    def blob(self, i):
+        return self._blob
+
+
+def workload_text(args, n_docs, extra=""):
+    if args.config == "C2":
+        return (f"C2: automerge-paper text trace (259,778 patches -> one FastUpdates blob of 1 peer) replicated x {n_docs} docs/GPU, "
+                f"each copy with its own bytes in HBM (SURVEY.md 8d){extra}")
+    if args.config == "C5":
+        return (f"C5: {n_docs} docs/GPU x movable tree of {args.tree_nodes} nodes (fan-out <= 8) built by peer 0 + {args.peers} peers x "
+                f"{args.tree_moves} concurrent moves (random target / parent, cycles across peers included), one FastUpdates blob per doc (SURVEY.md 8d){extra}")
+    return (f"C3: {n_docs} docs/GPU x {args.ops_per_doc} mixed List/Map atom ops, {args.peers} concurrent peers, "
+            f"one FastUpdates blob per doc (SURVEY.md 8d){extra}")
 
 
 def affordable_distinct(args, world, n_docs):
     """How many DISTINCT documents this rank's share of the host cores can generate in about 90 s
     (~1.2 M generated atom ops/s/core); the batch is filled by cycling through them (every copy has its own bytes
     in HBM; `distinct_docs_per_gpu` in the config says how many there are)."""
+    if args.config == "C2":
+        return 1
     if args.distinct:
         return min(args.distinct, n_docs)
     cores = max(1, (host_cores() or 1) // max(1, world))
+    if args.config == "C5":   # ~0.7 M generated tree ops/s/core
+        return max(64, min(n_docs, int(cores * 0.7e6 * 90 / (args.tree_nodes + args.peers * args.tree_moves))))
     return max(64, min(n_docs, int(cores * 1.2e6 * 90 / args.ops_per_doc)))
 
 
 def make_workload(args, rank, world, n_docs):
-    from loro_b200.workload import C3Batch
+    from loro_b200.workload import C3Batch, C5Batch
     distinct = affordable_distinct(args, world, n_docs)
     threads = max(1, (host_cores() or 1) // max(1, world))
     t0 = time.time()
-    gen = C3Batch(distinct, n_ops=args.ops_per_doc, n_peers=args.peers, first_doc=rank * n_docs, threads=threads)
+    if args.config == "C2":
+        gen = TraceBatch()
+    elif args.config == "C5":
+        gen = C5Batch(distinct, n_nodes=args.tree_nodes, n_peers=args.peers, n_moves=args.tree_moves, first_doc=rank * n_docs, threads=threads)
+    else:
+        gen = C3Batch(distinct, n_ops=args.ops_per_doc, n_peers=args.peers, first_doc=rank * n_docs, threads=threads)
     return gen, distinct, time.time() - t0
 
 
@@ -143,16 +190,19 @@ def cpu_baseline(args, gen, threads=None):
     import numpy as np
     threads = threads or (host_cores() or 1)
     n = args.cpu_sample_docs or min(gen.n_docs, max(64, min(4096, threads * 48)))
+    if args.config == "C2":
+        n = args.cpu_sample_docs or max(1, min(threads, 16))    # one trace import is ~0.26 M ops: a few copies suffice
     # oracle.bench_import wants contiguous [off[i], off[i+1]) blobs: re-pack exact lengths
-    blobs = [gen.blob(i) for i in range(n)]
+    blobs = [gen.blob(i % gen.n_docs) for i in range(n)]
     buf = b"".join(blobs)
     o = [0]
     for b in blobs:
         o.append(o[-1] + len(b))
     r = oracle.bench_import(np.frombuffer(buf, dtype=np.uint8), o, threads=threads, want_json=True,
                             want_export=not args.no_export)
-    return {"value": r["ops"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} docs of the same C3 workload ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON{"" if args.no_export else " + export(all_updates)"} per doc, one doc per task"}
+    return {"value": r["ops"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port", "ops": r["ops"],
+            "sample": f"{n} docs of the same {args.config} workload ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON{"" if args.no_export else " + export(all_updates)"} per doc, one doc per task; "
+                      "the CPU arm is the C++ restatement of the reference algorithm (oracle/), not the Rust reference (no cargo in the image)"}
 
 
 def run_reference(args):
@@ -164,6 +214,8 @@ def run_reference(args):
     oracle.build()
     threads = host_cores() or 1
     n = args.cpu_sample_docs or max(64, min(4096, threads * 48))
+    if args.config == "C5":
+        n = args.cpu_sample_docs or max(64, min(1024, threads * 24))
     ns = argparse.Namespace(**vars(args))
     ns.distinct = 0
     gen, _, _ = make_workload(ns, 0, 1, n)
@@ -174,11 +226,13 @@ def run_reference(args):
         if s >= warm:
             vals.append(cb)
     total_ops_per_s = statistics.mean(v["value"] for v in vals)
-    ms = 1e3 * (gen.atom_ops / total_ops_per_s)
+    ms = 1e3 * (vals[-1]["ops"] / total_ops_per_s)
+    for v in vals:
+        v.pop("ops", None)
     line = {"impl": "reference", "metric": METRIC, "value": total_ops_per_s, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": f"C3: {n} docs x {args.ops_per_doc} mixed List/Map atom ops, {args.peers} peers (bounded sample of the ours-arm workload)"},
+            "config": {"workload": workload_text(args, n, " -- bounded sample of the ours-arm workload")},
             "cpu_baseline": {"value": total_ops_per_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": total_ops_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -277,7 +331,7 @@ def main():
     for _ in range(args.steps):
         c, tm = step()
         launches += tm["kernel_launches"]
-        for k in ("frame", "decode", "resolve", "classify", "integrate", "materialise", "reexport", "total_device"):
+        for k in ("frame", "decode", "resolve", "classify", "integrate", "tree", "materialise", "reexport", "total_device"):
             phase[k] = phase.get(k, 0.0) + tm[k]
     ev1.record()
     torch.cuda.synchronize()
@@ -333,16 +387,29 @@ def main():
     peak, peak_src = peaks()
     n_steps = args.steps
     rows = c["op_rows"]
-    integ_ms = phase["integrate"] / n_steps
     dec_ms = phase["decode"] / n_steps
-    # list integration = 52 B per run (id, both origins, len read; rank written), runs = op rows
-    integ_bytes = rows * 52
     dec_bytes = tm["decode_bytes_read"] + tm["decode_bytes_written"]
-    roof = {"bound": "hbm", "kernel": "k_seq_integrate", "achieved": integ_bytes / (integ_ms * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": integ_bytes,
-            "share_of_step": integ_ms / (phase["total_device"] / n_steps)}
+    # the dominant kernel = the one behind the longest phase; algorithmic bytes per SURVEY 8d:
+    #   list/text integration 52 B per run (= op row); decode blob + SoA bytes; causal scan 20 B/change + 12 B/dep
+    #   (deps not counted here); materialise JSON bytes written + as many payload bytes read; re-export rows x 13 B read
+    #   + blob bytes written; movable tree 36 B per tree op (ids of subject and parent 24, position ref 4, lamport 4
+    #   read; parent link 4 written)
+    candidates = {
+        "integrate": ("k_seq_integrate", rows * 52, "seq"),
+        "decode": ("k_block_count+k_block_decode", dec_bytes, "decode"),
+        "tree": ("k_tree_build", tm["tree_ops"] * 36, None),
+        "materialise": ("k_json", 2 * c["json_bytes"], None),
+        "reexport": ("k_exp_encode+k_exp_changes", rows * 13 + tm["export_bytes"], None),
+        "resolve": ("k_doc_tables+k_doc_causal", c["changes"] * 20, None),
+    }
+    top = max(candidates, key=lambda k: phase.get(k, 0.0))
+    kname, abytes, facts_key = candidates[top]
+    top_ms = phase[top] / n_steps
+    roof = {"bound": "hbm", "kernel": kname, "achieved": abytes / (top_ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": abytes,
+            "share_of_step": top_ms / (phase["total_device"] / n_steps)}
     roof["frac"] = roof["achieved"] / peak
-    tr = ncu_traffic("seq", rows)
+    tr = ncu_traffic(facts_key, rows) if facts_key else None
     if tr:
         roof["traffic"] = tr["bytes"]
         roof["traffic_source"] = tr["source"]
@@ -356,14 +423,15 @@ def main():
         import oracle
         oracle.build()
         cpu = cpu_baseline(args, gen)
+        cpu.pop("ops", None)
     except Exception as e:  # the bench must still print its line
         cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": f"failed: {e}"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"C3: {n_docs} docs/GPU x {args.ops_per_doc} mixed List/Map atom ops, {args.peers} concurrent peers, "
-                               f"one FastUpdates blob per doc (SURVEY.md 8d); import -> state JSON" + ("" if args.no_export else " -> re-export(all_updates)"),
+        "config": {"workload": workload_text(args, n_docs, "; import -> state JSON" + ("" if args.no_export else " -> re-export(all_updates)")),
+                   "name": args.config,
                    "docs_per_gpu": n_docs, "distinct_docs_per_gpu": distinct, "atom_ops_per_step_per_gpu": atoms_per_step,
                    "op_rows_per_gpu": rows, "blob_bytes_per_gpu": int(lens.sum()), "l2": "inputs_larger_than_L2" if lens.sum() > 126e6 else "inputs fit L2",
                    "generator_seconds": round(gen_s, 1), "host_cores": host_cores()},

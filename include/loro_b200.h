@@ -102,6 +102,9 @@ typedef struct lb_timings { /* device time per phase in milliseconds (CUDA event
     uint64_t decode_bytes_read, decode_bytes_written;
     uint32_t kernel_launches;
     uint64_t export_bytes;             /* bytes written by the re-export phase */
+    float tree;                        /* movable-tree phase (sort, apply, sibling lists) */
+    uint32_t reserved0;
+    uint64_t tree_ops;                 /* RawTreeMove rows decoded */
 } lb_timings;
 
 typedef struct lb_batch lb_batch;

@@ -215,7 +215,7 @@ void pipeline(lb_batch* b) {
     u32 D = (u32)b->n_docs;
     lb_timings& tm = b->timings;
     if (D == 0) {
-        for (int i = 0; i < 7; i++) mark(b);
+        for (int i = 0; i < 8; i++) mark(b);
         b->docs.resize(1);
         return;
     }
@@ -398,6 +398,7 @@ void pipeline(lb_batch* b) {
         dv.release(sp.leaf); dv.release(sp.node); dv.release(sp.node_parent); dv.release(sp.atom_leaf); dv.release(sp.a_org);
         dv.release(sp.cvv); dv.release(sp.cont_epoch); dv.release(ct.atom_row); dv.release(ct.op_rec);
     }
+    mark(b);  // [5] list/text integration done
     // ------------------------------------------------------------ phase 5b: movable trees
     TreeTables tt;
     memset(&tt, 0, sizeof(tt));
@@ -415,7 +416,8 @@ void pipeline(lb_batch* b) {
         LB_LAUNCH(k_tree_build, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
         tm.kernel_launches += 2;
     }
-    mark(b);  // [5] integrate done
+    mark(b);  // [5b] trees done
+    tm.tree_ops = NTR;
     // ------------------------------------------------------------ phase 6: JSON
     StateTables stt;
     memset(&stt, 0, sizeof(stt));
@@ -604,10 +606,11 @@ void timings_from_events(lb_batch* b) {
     t.resolve = el(3, 4);
     t.classify = el(4, 5);
     t.integrate = el(5, 6);
-    t.materialise = el(6, 7);
-    t.reexport = el(7, 8);
-    t.d2h = el(8, 9);
-    t.total_device = el(1, 8);
+    t.tree = el(6, 7);
+    t.materialise = el(7, 8);
+    t.reexport = el(8, 9);
+    t.d2h = el(9, 10);
+    t.total_device = el(1, 9);
 }
 
 lb_status run_batch(lb_batch* b) {

@@ -21,6 +21,8 @@ def _load():
         L = ctypes.CDLL(_LIB)
         L.lw_generate_c3.restype = ctypes.c_void_p
         L.lw_generate_c3.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64] + [ctypes.c_int] * 7
+        L.lw_generate_c5.restype = ctypes.c_void_p
+        L.lw_generate_c5.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64] + [ctypes.c_int] * 7
         L.lw_bytes.restype = ctypes.c_void_p
         L.lw_bytes.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.lw_offsets.restype = ctypes.c_void_p
@@ -36,18 +38,12 @@ def _load():
     return _lib
 
 
-class C3Batch:
-    """Config C3 (SURVEY.md 8d): per doc `n_peers` peers, `n_ops` mixed List/Map atom ops (60 % list insert of an
-    I64 or short Str, 15 % list delete of 1-4, 25 % map set on 16 keys with 10 % deletes); peers fork from a
-    common prefix of `prefix_ops`, edit concurrently in bursts and sync pairwise every ~`sync_every` ops;
-    seed = doc index.  One FastUpdates blob per doc = export(all_updates) of a fully synced replica."""
+class _Batch:
+    """A generated batch: blobs at 16-byte aligned starts inside one buffer (the layout lb_import_batch_device takes)."""
 
-    def __init__(self, n_docs, n_ops=10000, n_peers=3, prefix_ops=1000, sync_every=500, txn_ops=10,
-                 first_doc=0, seed_base=0, want_json=False, threads=None):
+    def _adopt(self, handle, n_docs, want_json):
         L = _load()
-        threads = threads or os.cpu_count() or 1
-        self._h = L.lw_generate_c3(seed_base, first_doc, n_docs, n_ops, n_peers, prefix_ops, sync_every, txn_ops,
-                                   1 if want_json else 0, threads)
+        self._h = handle
         total = ctypes.c_uint64()
         p = L.lw_bytes(self._h, ctypes.byref(total))
         self.n_docs = n_docs
@@ -58,8 +54,6 @@ class C3Batch:
                                           shape=(n_docs,)) if n_docs else np.zeros(0, np.uint32)
         self.atom_ops = L.lw_atoms(self._h)
         self.want_json = want_json
-        self.config = dict(n_docs=n_docs, n_ops=n_ops, n_peers=n_peers, prefix_ops=prefix_ops,
-                           sync_every=sync_every, txn_ops=txn_ops, first_doc=first_doc, seed_base=seed_base)
 
     def blob(self, i):
         o, n = int(self.offsets[i]), int(self.lens[i])
@@ -74,7 +68,7 @@ class C3Batch:
         return ctypes.string_at(p, n.value)
 
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):
             _load().lw_free(self._h)
             self._h = None
             self.bytes = self.offsets = self.lens = None
@@ -84,3 +78,36 @@ class C3Batch:
             self.close()
         except Exception:
             pass
+
+
+class C5Batch(_Batch):
+    """Config C5: per doc peer 0 builds a tree of `n_nodes` nodes (fan-out <= `max_fanout`), then each
+    of the `n_peers` peers issues `n_moves` concurrent moves (random target, random new parent; moves of different
+    peers may close cycles); seed = doc index.  One FastUpdates blob per doc."""
+
+    def __init__(self, n_docs, n_nodes=5000, n_peers=3, n_moves=1000, max_fanout=8, txn_ops=10, first_doc=0,
+                 seed_base=0, want_json=False, threads=None):
+        L = _load()
+        threads = threads or os.cpu_count() or 1
+        h = L.lw_generate_c5(seed_base, first_doc, n_docs, n_nodes, n_peers, n_moves, max_fanout, txn_ops,
+                             1 if want_json else 0, threads)
+        self._adopt(h, n_docs, want_json)
+        self.config = dict(n_docs=n_docs, n_nodes=n_nodes, n_peers=n_peers, n_moves=n_moves, max_fanout=max_fanout,
+                           txn_ops=txn_ops, first_doc=first_doc, seed_base=seed_base)
+
+
+class C3Batch(_Batch):
+    """Config C3 (SURVEY.md 8d): per doc `n_peers` peers, `n_ops` mixed List/Map atom ops (60 % list insert of an
+    I64 or short Str, 15 % list delete of 1-4, 25 % map set on 16 keys with 10 % deletes); peers fork from a
+    common prefix of `prefix_ops`, edit concurrently in bursts and sync pairwise every ~`sync_every` ops;
+    seed = doc index.  One FastUpdates blob per doc = export(all_updates) of a fully synced replica."""
+
+    def __init__(self, n_docs, n_ops=10000, n_peers=3, prefix_ops=1000, sync_every=500, txn_ops=10,
+                 first_doc=0, seed_base=0, want_json=False, threads=None):
+        L = _load()
+        threads = threads or os.cpu_count() or 1
+        h = L.lw_generate_c3(seed_base, first_doc, n_docs, n_ops, n_peers, prefix_ops, sync_every, txn_ops,
+                             1 if want_json else 0, threads)
+        self._adopt(h, n_docs, want_json)
+        self.config = dict(n_docs=n_docs, n_ops=n_ops, n_peers=n_peers, prefix_ops=prefix_ops,
+                           sync_every=sync_every, txn_ops=txn_ops, first_doc=first_doc, seed_base=seed_base)

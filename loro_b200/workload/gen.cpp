@@ -159,7 +159,7 @@ u32 xxh32(const u8* d, size_t len, u32 seed) {
 // ------------------------------------------------------------------ ops / changes
 struct Id { int peer; i32 ctr; bool operator==(const Id& o) const { return peer == o.peer && ctr == o.ctr; } };
 const Id NO_ID{-1, -1};
-enum Kind : u8 { K_LIST_INS, K_LIST_DEL, K_MAP_SET, K_MAP_DEL };
+enum Kind : u8 { K_LIST_INS, K_LIST_DEL, K_MAP_SET, K_MAP_DEL, K_TREE };
 struct Val { bool is_str; i64 i; char s[9]; u8 slen; };
 // values of a list insert: the first value inline (runs are rare with random positions), the rest on the heap
 struct Vals {
@@ -176,6 +176,8 @@ struct Op {
     Id ol, orr;                // origins of the first inserted atom (replication only, not on the wire)
     Id del_start; i32 del_len; // signed
     u8 key; Val mapval;        // map ops
+    Id target, parent;         // tree ops: parent.peer -1 = root, -2 = DELETED_TREE_ROOT
+    std::string position;      // fractional index bytes
     u64 arena_start = 0, arena_end = 0;
     int atoms() const { return kind == K_LIST_INS ? (int)vals.size() : kind == K_LIST_DEL ? (del_len < 0 ? -del_len : del_len) : 1; }
 };
@@ -222,7 +224,7 @@ bool rle_push(std::vector<Op>& ops, const Op& op) {
     ops.push_back(op);
     return false;
 }
-size_t op_estimate(const Op& o) { return o.kind == K_LIST_INS ? 4 * o.vals.size() : o.kind == K_LIST_DEL ? 8 : 3; }
+size_t op_estimate(const Op& o) { return o.kind == K_LIST_INS ? 4 * o.vals.size() : (o.kind == K_LIST_DEL || o.kind == K_TREE) ? 8 : 3; }
 size_t change_estimate(const Change& c) {
     size_t s = 4 + (std::max<size_t>(c.deps.size(), 1) - 1) * 4;
     for (auto& o : c.ops) s += op_estimate(o);
@@ -533,16 +535,24 @@ void write_val(W& w, const Val& v) {
 std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u64>& peer_ids) {
     Reg<u64> peers;
     Reg<std::string> keys;
-    Reg<int> cids;  // 0 = List "list", 1 = Map "map"
+    Reg<int> cids;  // 0 = List "list", 1 = Map "map", 2 = Tree "tree"
     peers.reg(peer_ids[blk[0].peer]);
+    // position register pre-filled in sorted order (reference: block_encode.rs:156-178)
+    std::vector<std::string> positions;
+    for (auto& c : blk)
+        for (auto& op : c.ops)
+            if (op.kind == K_TREE && op.parent.peer != -2) positions.push_back(op.position);
+    std::sort(positions.begin(), positions.end());
+    positions.erase(std::unique(positions.begin(), positions.end()), positions.end());
+    const u64 DEL_PEER = ~0ull;
     std::vector<i64> c_cidx, c_prop, d_peer, d_ctr, d_len;
     std::vector<u64> c_vt, c_len;
     W vw;
     for (auto& c : blk)
         for (auto& op : c.ops) {
-            int cid = (op.kind == K_LIST_INS || op.kind == K_LIST_DEL) ? 0 : 1;
+            int cid = op.kind == K_TREE ? 2 : (op.kind == K_LIST_INS || op.kind == K_LIST_DEL) ? 0 : 1;
             size_t ci = cids.reg(cid);
-            i64 prop = op.pos;
+            i64 prop = op.kind == K_TREE ? 0 : op.pos;
             u64 vt;
             if (cid == 1) {
                 char kb[8];
@@ -561,6 +571,22 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
                     d_len.push_back(op.del_len);
                     break;
                 case K_MAP_SET: vt = 11; write_val(vw, op.mapval); break;
+                case K_TREE: {   // RawTreeMove (reference: encoding/value.rs:969-989, block_encode.rs:324-362)
+                    vt = 16;
+                    vw.varint(peers.reg(peer_ids[op.target.peer]));
+                    vw.varint((u32)op.target.ctr);
+                    if (op.parent.peer == -2) {
+                        size_t pp = peers.reg(DEL_PEER);
+                        vw.varint(0); vw.u8_(0); vw.varint(pp); vw.varint(0x7FFFFFFFu);
+                    } else {
+                        size_t pp = op.parent.peer >= 0 ? peers.reg(peer_ids[op.parent.peer]) : 0;
+                        size_t pi = std::lower_bound(positions.begin(), positions.end(), op.position) - positions.begin();
+                        vw.varint(pi);
+                        vw.u8_(op.parent.peer >= 0 ? 0 : 1);
+                        if (op.parent.peer >= 0) { vw.varint(pp); vw.varint((u32)op.parent.ctr); }
+                    }
+                    break;
+                }
                 default: vt = 8;
             }
             c_cidx.push_back((i64)ci);
@@ -572,8 +598,8 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
     W cw;
     cw.varint(cids.v.size());
     for (int cid : cids.v) {
-        cw.varint(4); cw.u8_(1); cw.u8_(cid == 0 ? 1 : 0); cw.varint(0);
-        cw.zig((i64)keys.reg(cid == 0 ? "list" : "map"));
+        cw.varint(4); cw.u8_(1); cw.u8_(cid == 0 ? 1 : cid == 1 ? 0 : 3); cw.varint(0);
+        cw.zig((i64)keys.reg(cid == 0 ? "list" : cid == 1 ? "map" : "tree"));
     }
     W kw;
     for (auto& k : keys.v) { kw.varint(k.size()); kw.bytes((const u8*)k.data(), k.size()); }
@@ -584,6 +610,23 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
         AnyRle<u64, WrU8> e1(c, WrU8()); for (auto x : c_vt) e1.push(x); e1.finish();
         AnyRle<u64, WrVar> e2(d, WrVar()); for (auto x : c_len) e2.push(x); e2.finish();
         ow.varint(1); ow.varint(4); ow.lenbytes(a.b); ow.lenbytes(b.b); ow.lenbytes(c.b); ow.lenbytes(d.b);
+    }
+    W pw;   // PositionArena (reference: encoding/arena.rs:159-224): common prefix lengths + rests
+    if (!positions.empty()) {
+        W c0, c1;
+        AnyRle<u64, WrVar> e(c0, WrVar());
+        c1.varint(positions.size());
+        const std::string* last = nullptr;
+        for (auto& p : positions) {
+            size_t common = 0;
+            if (last) while (common < last->size() && common < p.size() && (*last)[common] == p[common]) common++;
+            e.push(common);
+            c1.varint(p.size() - common);
+            c1.bytes((const u8*)p.data() + common, p.size() - common);
+            last = &p;
+        }
+        e.finish();
+        pw.varint(1); pw.varint(2); pw.lenbytes(c0.b); pw.lenbytes(c1.b);
     }
     W dw;
     if (!d_peer.empty()) {
@@ -626,7 +669,7 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
     out.varint(l.lamport + (u32)l.atoms() - f.lamport);
     out.varint(blk.size());
     std::vector<u8> empty;
-    out.lenbytes(hw.b); out.lenbytes(meta.b); out.lenbytes(cw.b); out.lenbytes(kw.b); out.lenbytes(empty);
+    out.lenbytes(hw.b); out.lenbytes(meta.b); out.lenbytes(cw.b); out.lenbytes(kw.b); out.lenbytes(pw.b);
     out.lenbytes(ow.b); out.lenbytes(dw.b); out.lenbytes(vw.b);
     return out.b;
 }
@@ -772,6 +815,165 @@ DocOut gen_c3(u64 seed, int n_ops, int n_peers, int prefix_ops, int sync_every, 
     return out;
 }
 
+// ------------------------------------------------------------------ config C5: movable trees
+// fractional index, jitter 0 (reference: crates/fractional_index/src/lib.rs:52-127); strings carry the terminator
+const u8 FI_TERM = 128;
+std::string fi_after(const std::string& b) {
+    for (size_t i = 0; i < b.size(); i++) {
+        u8 c = (u8)b[i];
+        if (c < FI_TERM) return b.substr(0, i);
+        if (c < 255) { std::string a = b.substr(0, i + 1); a[i] = (char)(c + 1); return a; }
+    }
+    return b;
+}
+std::string fi_append_after(const std::string* last) {   // FractionalIndex::new(Some(last), None) / default
+    if (!last) return std::string(1, (char)FI_TERM);
+    std::string a = fi_after(*last);
+    a.push_back((char)FI_TERM);
+    return a;
+}
+struct TNode { int parent = -3; std::string pos; u32 lamport = 0; int peer = 0; };   // parent: node, -1 root, -3 unexist
+struct TreeRep {
+    std::vector<TNode> nodes;                 // indexed by the create op's counter (all creates are peer 0's)
+    std::vector<std::vector<int>> kids;       // per node, sibling order; kids.back() = the root list
+    const std::vector<u64>* peer_ids = nullptr;
+    explicit TreeRep(size_t n) : nodes(n), kids(n + 1) {}
+    std::vector<int>& list_of(int parent) { return parent < 0 ? kids.back() : kids[(size_t)parent]; }
+    bool before(int a, int b) const {
+        const TNode &x = nodes[(size_t)a], &y = nodes[(size_t)b];
+        if (x.pos != y.pos) return x.pos < y.pos;
+        if (x.lamport != y.lamport) return x.lamport < y.lamport;
+        return (*peer_ids)[(size_t)x.peer] < (*peer_ids)[(size_t)y.peer];
+    }
+    bool is_ancestor(int anc, int node) const {   // anc is node or one of its ancestors
+        if (nodes[(size_t)anc].parent == -3) return false;
+        while (node >= 0) {
+            if (node == anc) return true;
+            node = nodes[(size_t)node].parent;
+        }
+        return false;
+    }
+    void place(int t, int parent, const std::string& pos, u32 lamport, int peer) {
+        TNode& n = nodes[(size_t)t];
+        if (n.parent != -3) { auto& old = list_of(n.parent); old.erase(std::find(old.begin(), old.end(), t)); }
+        n.parent = parent; n.pos = pos; n.lamport = lamport; n.peer = peer;
+        auto& l = list_of(parent);
+        size_t i = 0;
+        while (i < l.size() && before(l[i], t)) i++;
+        l.insert(l.begin() + (long)i, t);
+    }
+};
+void tree_json(std::string& o, const TreeRep& tr, int parent, const std::vector<u64>& peer_ids) {
+    static const char* HEX = "0123456789ABCDEF";
+    const auto& l = parent < 0 ? tr.kids.back() : tr.kids[(size_t)parent];
+    o.push_back('[');
+    for (size_t i = 0; i < l.size(); i++) {
+        if (i) o.push_back(',');
+        const TNode& n = tr.nodes[(size_t)l[i]];
+        o += "{\"children\":";
+        tree_json(o, tr, l[i], peer_ids);
+        o += ",\"fractional_index\":\"";
+        for (unsigned char c : n.pos) { o.push_back(HEX[c >> 4]); o.push_back(HEX[c & 15]); }
+        o += "\",\"id\":\"" + std::to_string(l[i]) + "@" + std::to_string(peer_ids[0]) + "\",\"index\":" + std::to_string(i) + ",\"meta\":{},\"parent\":";
+        if (parent < 0) o += "null"; else o += "\"" + std::to_string(parent) + "@" + std::to_string(peer_ids[0]) + "\"";
+        o.push_back('}');
+    }
+    o.push_back(']');
+}
+
+// peer 0 builds a tree of n_nodes (fan-out <= max_fanout), every peer starts from it and
+// issues n_moves moves concurrently (random target, random new parent; cycles between peers' moves are left in --
+// the merge has to resolve them).  One FastUpdates blob = export(all_updates) of a fully synced replica.
+DocOut gen_c5(u64 seed, int n_nodes, int n_peers, int n_moves, int max_fanout, int txn_ops, bool want_json) {
+    DocGen g(n_peers, seed);
+    std::vector<TreeRep> trs((size_t)n_peers, TreeRep((size_t)n_nodes));
+    for (auto& t : trs) t.peer_ids = &g.peer_ids;
+    auto tree_op = [&](int p, int target, int parent) {
+        Replica& r = *g.reps[p];
+        TreeRep& tr = trs[(size_t)p];
+        g.begin(r);
+        Op op{};
+        op.kind = K_TREE;
+        op.ctr = g.next_ctr(r);
+        op.pos = 0;
+        op.target = Id{0, target};
+        op.parent = parent < 0 ? Id{-1, 0} : Id{0, parent};
+        // handler/tree.rs:548-566 `mov`: append after the last child (the target itself not counted)
+        const std::string* last = nullptr;
+        for (int k : tr.list_of(parent)) if (k != target) last = &tr.nodes[(size_t)k].pos;
+        op.position = fi_append_after(last);
+        u32 lam = r.txn.lamport + (u32)(op.ctr - r.txn.ctr);
+        tr.place(target, parent, op.position, lam, p);
+        r.txn.ops.push_back(op);
+    };
+    // base tree by peer 0: node k is created by the op with counter k
+    int since = 0;
+    for (int k = 0; k < n_nodes; k++) {
+        int parent = -1;
+        if (k > 0 && g.rng.unit() < 0.9) {
+            for (int tries = 0; tries < 8; tries++) {
+                int c = (int)g.rng.below((u32)k);
+                if ((int)trs[0].kids[(size_t)c].size() < max_fanout) { parent = c; break; }
+            }
+        }
+        if (parent < 0 && (int)trs[0].kids.back().size() >= max_fanout && k > 0) {
+            // the root list is full too: first node with room
+            for (int c = 0; c < k; c++) if ((int)trs[0].kids[(size_t)c].size() < max_fanout) { parent = c; break; }
+        }
+        tree_op(0, k, parent);
+        if (++since >= txn_ops) { g.commit(*g.reps[0]); since = 0; }
+    }
+    g.commit(*g.reps[0]);
+    for (int p = 1; p < n_peers; p++) {
+        trs[(size_t)p] = trs[0];
+        trs[(size_t)p].peer_ids = &g.peer_ids;
+        Replica& r = *g.reps[p];
+        r.vv = g.reps[0]->vv;
+        r.frontiers = g.reps[0]->frontiers;
+    }
+    // concurrent moves
+    for (int p = 0; p < n_peers; p++) {
+        since = 0;
+        for (int m = 0; m < n_moves; m++) {
+            int target = 0, parent = -1;
+            for (int tries = 0; tries < 16; tries++) {
+                target = (int)g.rng.below((u32)n_nodes);
+                parent = g.rng.unit() < 0.05 ? -1 : (int)g.rng.below((u32)n_nodes);
+                if (parent < 0 || !trs[(size_t)p].is_ancestor(target, parent)) break;   // a local cycle is an API error
+                parent = -1;
+            }
+            tree_op(p, target, parent);
+            if (++since >= txn_ops) { g.commit(*g.reps[p]); since = 0; }
+        }
+        g.commit(*g.reps[p]);
+    }
+    DocOut out;
+    out.atoms = 0;
+    for (int p = 0; p < n_peers; p++) out.atoms += (u64)g.reps[p]->vv[p];
+    if (want_json) {
+        // the merge, independently: every op in (lamport, peer id) order, a move whose new parent sits below the
+        // target is skipped (reference: diff_calc/tree.rs:445-508)
+        struct M { u32 lam; u64 pid; int peer; const Op* op; };
+        std::vector<M> all;
+        for (int p = 0; p < n_peers; p++)
+            for (auto& c : g.log[p])
+                for (auto& op : c.ops) all.push_back(M{c.lamport + (u32)(op.ctr - c.ctr), g.peer_ids[p], p, &op});
+        std::sort(all.begin(), all.end(), [](const M& a, const M& b) { return a.lam != b.lam ? a.lam < b.lam : a.pid < b.pid; });
+        TreeRep fin((size_t)n_nodes);
+        fin.peer_ids = &g.peer_ids;
+        for (auto& m : all) {
+            int parent = m.op->parent.peer < 0 ? -1 : m.op->parent.ctr;
+            if (parent >= 0 && fin.is_ancestor(m.op->target.ctr, parent)) continue;
+            fin.place(m.op->target.ctr, parent, m.op->position, m.lam, m.peer);
+        }
+        out.json = "{\"tree\":";
+        tree_json(out.json, fin, -1, g.peer_ids);
+        out.json += "}";
+    }
+    out.blob = export_all(g);
+    return out;
+}
+
 }  // namespace
 
 extern "C" {
@@ -794,6 +996,33 @@ lw_batch* lw_generate_c3(u64 seed_base, u64 first_doc, u64 n_docs, int n_ops, in
             u64 i = next.fetch_add(1);
             if (i >= n_docs) break;
             docs[i] = gen_c3(seed_base + first_doc + i, n_ops, n_peers, prefix_ops, sync_every, txn_ops, want_json != 0);
+        }
+    };
+    if (threads < 1) threads = 1;
+    std::vector<std::thread> ts;
+    for (int t = 1; t < threads; t++) ts.emplace_back(work);
+    work();
+    for (auto& t : ts) t.join();
+    lw_batch* b = new lw_batch();
+    u64 total = 0;
+    for (auto& d : docs) { b->offs.push_back(total); b->lens.push_back((u32)d.blob.size()); total += (d.blob.size() + 15) & ~(u64)15; b->atoms += d.atoms; }
+    b->bytes.assign(total + 64, 0);
+    for (size_t i = 0; i < docs.size(); i++) {
+        memcpy(b->bytes.data() + b->offs[i], docs[i].blob.data(), docs[i].blob.size());
+        if (want_json) b->json.push_back(std::move(docs[i].json));
+    }
+    return b;
+}
+// Generate docs [first_doc, first_doc + n_docs) of config C5 (seed = doc index + seed_base).
+lw_batch* lw_generate_c5(u64 seed_base, u64 first_doc, u64 n_docs, int n_nodes, int n_peers, int n_moves, int max_fanout,
+                         int txn_ops, int want_json, int threads) {
+    std::vector<DocOut> docs(n_docs);
+    std::atomic<u64> next(0);
+    auto work = [&]() {
+        while (true) {
+            u64 i = next.fetch_add(1);
+            if (i >= n_docs) break;
+            docs[i] = gen_c5(seed_base + first_doc + i, n_nodes, n_peers, n_moves, max_fanout, txn_ops, want_json != 0);
         }
     };
     if (threads < 1) threads = 1;

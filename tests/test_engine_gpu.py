@@ -303,3 +303,16 @@ def test_tree_export_and_large_tree():
     blobs.append(a.export_updates())
     check_batch_against_oracle(blobs)
     check_export_against_oracle(blobs)
+
+
+def test_config_c5_full_size_documents():
+    """BASELINE config C5 at the stated per-document size (5,000-node tree + 3 x 1,000 concurrent moves): the
+    generator's own merge (expected JSON), the oracle and the CUDA path agree on state and on re-exported bytes."""
+    from loro_b200.workload import C5Batch
+    from tests.export_checks import check_export_against_oracle
+    g = C5Batch(12, want_json=True)
+    blobs = g.blobs()
+    want = [g.expected_json(i) for i in range(g.n_docs)]
+    b = check_batch_against_oracle(blobs, expect_json=want)
+    assert b.counters()["atom_ops"] == 12 * 8000
+    check_export_against_oracle(blobs[:4])

@@ -124,3 +124,19 @@ def test_tree_many_nodes_several_blocks_per_peer():
     blob = a.export_updates()
     check_batch_against_oracle([blob], lib_path=EMU)
     check_export_against_oracle([blob], lib_path=EMU)
+
+
+def test_config_c5_generator_documents():
+    """Config C5 shape from the workload generator (its own encoder, its own merge): generator == oracle == kernels,
+    for state and for re-exported bytes."""
+    from loro_b200.workload import C5Batch
+    from tests.export_checks import check_export_against_oracle
+    g = C5Batch(5, n_nodes=400, n_moves=120, want_json=True)
+    blobs = g.blobs()
+    for i, blob in enumerate(blobs):
+        o = OracleDoc(1)
+        o.import_(blob)
+        assert o.json_text() == g.expected_json(i)
+        assert o.export_updates() == blob
+    check_batch_against_oracle(blobs, lib_path=EMU, expect_json=[g.expected_json(i) for i in range(5)])
+    check_export_against_oracle(blobs, lib_path=EMU)
