@@ -413,6 +413,8 @@ void pipeline(lb_batch* b) {
         tt.tn_parent = dv.alloc<u32>(NTS); tt.tn_move = dv.alloc<u32>(NTS); tt.tn_base = dv.alloc<u32>(NTS);
         tt.tn_cnt = dv.alloc<u32>(NTS); tt.tn_sib = dv.alloc<u32>(NTS); tt.ns_key = dv.alloc<u64>(NTS);
         tt.tn_child = dv.alloc<u32>(NTS);
+        tt.tn_root = dv.alloc<u32>(NTS); tt.tn_aopen = dv.alloc<u32>(NTS); tt.tn_aclose = dv.alloc<u32>(NTS);
+        tt.dcont = dcont;
         LB_LAUNCH(k_tree_build, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
         tm.kernel_launches += 2;
     }
@@ -428,6 +430,7 @@ void pipeline(lb_batch* b) {
     stt.out_row = sp.out_row; stt.out_off = sp.out_off; stt.out_len = sp.out_len;
     stt.blocks = blk; stt.tn_parent = tt.tn_parent; stt.tn_move = tt.tn_move; stt.tn_base = tt.tn_base; stt.tn_cnt = tt.tn_cnt;
     stt.tn_sib = tt.tn_sib; stt.tn_child = tt.tn_child; stt.tr_rec = ct.tr_rec;
+    stt.tn_root = tt.tn_root; stt.tn_aopen = tt.tn_aopen; stt.tn_aclose = tt.tn_aclose; stt.ns_key = tt.ns_key;
     stt.pos_off = t.pos_off; stt.pos_len = t.pos_len; stt.pos_pool = t.pos_pool;
     unsigned long long* d_acc = dv.alloc<unsigned long long>(4, true);
     if (!(b->flags & LB_FLAG_NO_JSON)) {

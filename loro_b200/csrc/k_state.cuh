@@ -9,6 +9,7 @@
 #pragma once
 #include "lb_defs.h"
 #include "k_frame.cuh"
+#include "k_tree.cuh"
 
 struct StateTables {
     const u8* bytes;
@@ -22,6 +23,7 @@ struct StateTables {
     // movable tree (k_tree.cuh): node tables per document (base DocInfo::tree0) + positions
     const BlockInfo* blocks;
     const u32* tn_parent; const u32* tn_move; const u32* tn_base; const u32* tn_cnt; const u32* tn_sib; const u32* tn_child;
+    const u32* tn_root; const u32* tn_aopen; const u32* tn_aclose; const u64* ns_key;   // lane-parallel layout (k_tree.cuh)
     const uint4* tr_rec; const u64* pos_off; const u32* pos_len; const u8* pos_pool;
 };
 
@@ -192,24 +194,64 @@ struct Emitter {
             case CT_TREE:
                 out.put('[');
                 if (!di.has_tree) { out.put(']'); return; }   // no applied tree op in the document: no node tables
+                if (di.has_tree & 2u) { emit_tree_parallel(cidx); out.put(']'); return; }
                 f.kind = FK_TREE; f.b = (u32)di.atom_total + cidx; f.c = 0; f.id_peer = 0xFFFFFFFFu; push(f);
                 return;
             default: out.puts_("null"); return;
         }
     }
     // "<counter>@<peer>" of the node stored at atom `a` (ID display: loro-common/src/id.rs:22-26)
-    __device__ void put_tree_id(u32 a) {
+    __device__ void put_tree_id_to(Sink& o, u32 a) {
         u32 p = 0;
         for (u32 q = 0; q < di.P; q++) {
             const DocPeer& dp = t.dpeer[di.peer0 + q];
             if (a >= dp.atom_base && a < dp.atom_base + (u32)dp.end_counter) { p = q; break; }
         }
         const DocPeer& dp = t.dpeer[di.peer0 + p];
-        out.put('"');
-        out.put_u64(a - dp.atom_base);
-        out.put('@');
-        out.put_u64(dp.id);
-        out.put('"');
+        o.put('"');
+        o.put_u64(a - dp.atom_base);
+        o.put('@');
+        o.put_u64(dp.id);
+        o.put('"');
+    }
+    __device__ void put_tree_id(u32 a) { put_tree_id_to(out, a); }
+    __device__ void put_fractional_index(Sink& o, u32 pos) {
+        const char* HEX = "0123456789ABCDEF";   // crates/fractional_index/src/lib.rs:195-205
+        const u8* pb = t.pos_pool + t.pos_off[pos];
+        u32 pl = t.pos_len[pos];
+        for (u32 k = 0; k < pl; k++) { o.put((u8)HEX[pb[k] >> 4]); o.put((u8)HEX[pb[k] & 15]); }
+    }
+    // every node of the hierarchy written by its own lane at the offsets k_tree_build laid out (all meta maps empty);
+    // the caller has printed '[' and prints ']'
+    __device__ void emit_tree_parallel(u32 cidx) {
+        const u64 tb = di.tree0;
+        const u32 A = (u32)di.atom_total, slot = A + cidx;
+        const u64 tr_lo = t.blocks[di.b0].tr0;
+        const u32 total = ((const u32*)(t.ns_key + tb))[slot];
+        if (out.dst) {
+            const u64 start = out.n - 1;   // the container's '['
+            for (u32 a = (u32)lane; a < A; a += 32) {
+                if (t.tn_root[tb + a] != slot) continue;
+                Sink w;
+                w.dst = out.dst; w.flags = 0; w.wr = true;
+                w.n = start + t.tn_aopen[tb + a];
+                u32 sib = t.tn_sib[tb + a], par = t.tn_parent[tb + a];
+                if (sib) w.put(',');
+                w.puts_("{\"children\":[");
+                w.n = start + t.tn_aclose[tb + a];
+                w.puts_("],\"fractional_index\":\"");
+                put_fractional_index(w, t.tr_rec[tr_lo + t.tn_move[tb + a]].z);
+                w.puts_("\",\"id\":");
+                put_tree_id_to(w, a);
+                w.puts_(",\"index\":");
+                w.put_u64(sib);
+                w.puts_(",\"meta\":{},\"parent\":");
+                if (par == TREE_ROOT) w.puts_("null"); else put_tree_id_to(w, par);
+                w.put('}');
+            }
+            __syncwarp();
+        }
+        out.n += total;
     }
     // one step of the hierarchy walk (state/tree_state.rs:814-831 get_all_hierarchy_nodes_under + :1424-1452
     // TreeNodeWithChildren::into_value, keys in ascending order): no per-level frames -- the walk climbs back
@@ -245,12 +287,7 @@ struct Emitter {
         u32 node = slot;
         uint4 rec = t.tr_rec[tr_lo + t.tn_move[tb + node]];
         out.puts_(",\"fractional_index\":\"");
-        {
-            const char* HEX = "0123456789ABCDEF";   // crates/fractional_index/src/lib.rs:195-205
-            const u8* pb = t.pos_pool + t.pos_off[rec.z];
-            u32 pl = t.pos_len[rec.z];
-            for (u32 k = 0; k < pl; k++) { out.put((u8)HEX[pb[k] >> 4]); out.put((u8)HEX[pb[k] & 15]); }
-        }
+        put_fractional_index(out, rec.z);
         out.puts_("\",\"id\":");
         put_tree_id(node);
         out.puts_(",\"index\":");

@@ -36,9 +36,32 @@ struct TreeTables {
     u32* tn_base;             // [slot] first child in tn_child
     u32* tn_cnt;              // [slot] number of children
     u32* tn_sib;              // [node] index among its siblings
-    u64* ns_key;              // [node] sort key: parent slot << 32 | first four position bytes
+    u64* ns_key;              // [slot] sort key: parent slot << 32 | first four position bytes; after the sort the space holds
+                              //        tn_sub (JSON bytes of the subtree, [slot]) and tn_rel (offset among siblings, [node])
     u32* tn_child;            // [node] after the sort: nodes grouped by parent slot, in sibling order
+    // hierarchy JSON layout (k_state.cuh writes the nodes lane-parallel when no node has a meta map with content)
+    u32* tn_root;             // [node] root slot of the tree the node is alive in, TREE_UNEXIST when dead
+    u32* tn_aopen;            // [node] offset of the node's `{"children":[` inside its container's JSON
+    u32* tn_aclose;           // [node] offset of the part after its children
+    const DocContainer* dcont;
 };
+__device__ __forceinline__ u32* tree_sub(const TreeTables& t, const DocInfo& di) { return (u32*)(t.ns_key + di.tree0); }
+
+__device__ __forceinline__ u32 dec_digits(u64 v) { u32 k = 1; while (v >= 10) { v /= 10; k++; } return k; }
+// "<counter>@<peer>" with its quotes
+__device__ inline u32 tree_id_len(const DocPeer* dpeer, u32 P, u32 a) {
+    u32 p = 0;
+    for (u32 q = 0; q < P; q++)
+        if (a >= dpeer[q].atom_base && a < dpeer[q].atom_base + (u32)dpeer[q].end_counter) { p = q; break; }
+    return 3 + dec_digits(a - dpeer[p].atom_base) + dec_digits(dpeer[p].id);
+}
+// bytes of a node's object before / after its children when its meta map is empty (keys in ascending order):
+//   [,]{"children":[   ...   ],"fractional_index":"HEX","id":"c@p","index":N,"meta":{},"parent":null|"c@p"}
+__device__ __forceinline__ u32 tree_open_len(u32 sib) { return 13u + (sib ? 1u : 0u); }
+__device__ inline u32 tree_close_len(const DocPeer* dpeer, u32 P, u32 node, u32 parent, u32 sib, u32 pos_len) {
+    return 1 + 21 + 2 * pos_len + 7 + tree_id_len(dpeer, P, node) + 9 + dec_digits(sib) + 10 + 10 +
+           (parent == TREE_ROOT ? 4u : tree_id_len(dpeer, P, parent)) + 1;
+}
 
 // ---- warp bitonic sort of (key, val) pairs in global memory, any n (partners beyond n act as +inf: with every
 // comparator pointing the same way they never have to move).  `tie(a, b)` orders two vals whose keys are equal.
@@ -63,6 +86,24 @@ __device__ inline void warp_sort_pairs(u64* key, u32* val, u32 n, int lane, Tie 
     }
 }
 struct NoTie { __device__ bool operator()(u32, u32) const { return false; } };
+// same network on values only, ordered by `before(a, b)`
+template <class Before>
+__device__ inline void warp_sort_vals(u32* val, u32 n, int lane, Before before) {
+    if (n < 2) return;
+    for (u32 k = 2; (k >> 1) < n; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            bool flip = j == (k >> 1);
+            for (u32 i = (u32)lane; i < n; i += 32) {
+                u32 l = flip ? (i ^ (k - 1)) : (i ^ j);
+                if (l > i && l < n) {
+                    u32 vi = val[i], vl = val[l];
+                    if (before(vl, vi)) { val[i] = vl; val[l] = vi; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
 
 // lexicographic comparison of two fractional indexes (FractionalIndex derives Ord on its bytes)
 __device__ inline int pos_cmp(const TreeTables& t, u32 pa, u32 pb) {
@@ -87,14 +128,62 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
     u32* parent = t.tn_parent + base;
     u32* move = t.tn_move + base;
     for (u32 i = lane; i < A + C; i += 32) { parent[i] = TREE_UNEXIST; t.tn_cnt[base + i] = 0; t.tn_base[base + i] = 0; }
-    // ---- the document's tree ops (contiguous: blocks of a document are) in (lamport, peer) order
+    // ---- the document's tree ops (contiguous: blocks of a document are) in (lamport, peer) order.
+    // Lamports are recomputed from the dependencies, so they are smaller than the document's atom count: a counting
+    // sort over the lamport (tn_cnt / tn_base double as histogram and offsets) followed by a per-lamport fix of the
+    // few ties replaces the O(n log^2 n) network; a lamport outside the range falls back to the network.
     const u64 tr_lo = t.blocks[di.b0].tr0, tr_hi = t.blocks[di.b1].tr0;
     const u32 n_tr = (u32)(tr_hi - tr_lo);
     u64* skey = t.ts_key + tr_lo;
     u32* sval = t.ts_val + tr_lo;
-    for (u32 i = lane; i < n_tr; i += 32) { skey[i] = t.tr_key[tr_lo + i]; sval[i] = i; }
+    u32* cnt = t.tn_cnt + base;
+    u32* off = t.tn_base + base;
     __syncwarp();
-    warp_sort_pairs(skey, sval, n_tr, lane, NoTie());
+    bool wide = false;
+    for (u32 i = lane; i < n_tr; i += 32) {
+        u64 k = t.tr_key[tr_lo + i];
+        if (k == ~0ull) continue;
+        u32 lam = (u32)(k >> 32);
+        if (lam >= A) wide = true; else atomicAdd(&cnt[lam], 1u);
+    }
+    wide = __any_sync(LB_FULL, wide);
+    if (wide) {
+        for (u32 i = lane; i < A; i += 32) cnt[i] = 0;
+        for (u32 i = lane; i < n_tr; i += 32) { skey[i] = t.tr_key[tr_lo + i]; sval[i] = i; }
+        __syncwarp();
+        warp_sort_pairs(skey, sval, n_tr, lane, NoTie());
+    } else {
+        u32 carry = 0;
+        for (u32 i0 = 0; i0 < A; i0 += 32) {
+            u32 i = i0 + (u32)lane;
+            int c = i < A ? (int)cnt[i] : 0;
+            int incl = warp_incl_scan(c, lane);
+            if (i < A) off[i] = carry + (u32)(incl - c);
+            carry += (u32)__shfl_sync(LB_FULL, incl, 31);
+        }
+        const u32 n_valid = carry;
+        __syncwarp();
+        for (u32 i = lane; i < n_tr; i += 32) {
+            u64 k = t.tr_key[tr_lo + i];
+            if (k == ~0ull) continue;
+            u32 lam = (u32)(k >> 32);
+            u32 pos = off[lam] + (atomicSub(&cnt[lam], 1u) - 1u);
+            skey[pos] = k;
+            sval[pos] = i;
+        }
+        for (u32 i = n_valid + (u32)lane; i < n_tr; i += 32) skey[i] = ~0ull;
+        __syncwarp();
+        for (u32 lam = lane; lam < A; lam += 32) {   // concurrent ops with the same lamport: order by peer
+            u32 b = off[lam], e = lam + 1 < A ? off[lam + 1] : n_valid;
+            for (u32 x = b + 1; x < e; x++) {
+                u64 kx = skey[x]; u32 vx = sval[x];
+                u32 y = x;
+                while (y > b && skey[y - 1] > kx) { skey[y] = skey[y - 1]; sval[y] = sval[y - 1]; y--; }
+                skey[y] = kx; sval[y] = vx;
+            }
+        }
+    }
+    __syncwarp();
     // ---- sequential apply, 32 records per round trip
     bool stop = false;
     for (u32 j0 = 0; j0 < n_tr && !stop; j0 += 32) {
@@ -127,44 +216,146 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
         }
     }
     __syncwarp();
-    // ---- sibling lists: sort the nodes by (parent slot, position, lamport, peer)
+    // ---- sibling lists: nodes bucketed by parent slot (counting sort), every list ordered by NodePosition =
+    // (fractional index bytes, lamport, peer); lists are short (fan-out), so a lane sorts a list by insertion with an
+    // 8-byte position prefix as the first comparison; a list longer than 32 goes through the warp network
     u64* nkey = t.ns_key + base;
     u32* child = t.tn_child + base;
-    for (u32 a = lane; a < A; a += 32) {
+    u32* fill = t.tn_sib + base;
+    for (u32 i = lane; i < A + C; i += 32) { cnt[i] = 0; fill[i] = 0; }
+    __syncwarp();
+    auto slot_of = [&](u32 a) -> u32 {
         u32 p = parent[a];
-        u64 key = ~0ull;
-        if (p != TREE_UNEXIST && p != TREE_DELETED) {
-            uint4 rec = t.tr_rec[tr_lo + move[a]];
-            u32 slot = p == TREE_ROOT ? A + t.op_cidx[rec.w] : p;
-            const u8* pb = t.pos_pool + t.pos_off[rec.z];
-            u32 pl = t.pos_len[rec.z];
-            u32 pre = 0;
-            for (u32 k = 0; k < 4; k++) pre = (pre << 8) | (k < pl ? pb[k] : 0u);
-            key = ((u64)slot << 32) | pre;
-        }
-        nkey[a] = key;
-        child[a] = a;
+        if (p == TREE_UNEXIST || p == TREE_DELETED) return TREE_UNEXIST;
+        return p == TREE_ROOT ? A + t.op_cidx[t.tr_rec[tr_lo + move[a]].w] : p;
+    };
+    for (u32 a = lane; a < A; a += 32) {
+        u32 sl = slot_of(a);
+        if (sl == TREE_UNEXIST) continue;
+        atomicAdd(&cnt[sl], 1u);
+        u32 pz = t.tr_rec[tr_lo + move[a]].z;
+        const u8* pb = t.pos_pool + t.pos_off[pz];
+        u32 pl = t.pos_len[pz];
+        u64 pre = 0;
+        for (u32 k = 0; k < 8; k++) pre = (pre << 8) | (k < pl ? pb[k] : 0u);
+        nkey[a] = pre;
     }
     __syncwarp();
-    warp_sort_pairs(nkey, child, A, lane, [&](u32 a, u32 b) -> bool {   // a before b ?
+    {
+        u32 carry = 0;
+        for (u32 i0 = 0; i0 < A + C; i0 += 32) {
+            u32 i = i0 + (u32)lane;
+            int c = i < A + C ? (int)cnt[i] : 0;
+            int incl = warp_incl_scan(c, lane);
+            if (i < A + C) off[i] = carry + (u32)(incl - c);
+            carry += (u32)__shfl_sync(LB_FULL, incl, 31);
+        }
+    }
+    __syncwarp();
+    for (u32 a = lane; a < A; a += 32) {
+        u32 sl = slot_of(a);
+        if (sl != TREE_UNEXIST) child[off[sl] + atomicAdd(&fill[sl], 1u)] = a;
+    }
+    __syncwarp();
+    auto before = [&](u32 a, u32 b) -> bool {   // NodePosition order (tree_state.rs:61-67)
+        u64 ka = nkey[a], kb = nkey[b];
+        if (ka != kb) return ka < kb;
         uint4 ra = t.tr_rec[tr_lo + move[a]], rb = t.tr_rec[tr_lo + move[b]];
         int c = pos_cmp(t, ra.z, rb.z);
         if (c) return c < 0;
-        return t.tr_key[tr_lo + move[a]] < t.tr_key[tr_lo + move[b]];   // (lamport, peer): NodePosition.idlp
-    });
-    // ---- slot -> (first child, count), node -> sibling index
-    for (u32 j = lane; j < A; j += 32) {
-        u64 k = nkey[j];
-        if (k == ~0ull) continue;
-        u32 slot = (u32)(k >> 32);
-        if (j == 0 || (u32)(nkey[j - 1] >> 32) != slot) t.tn_base[base + slot] = j;
+        return t.tr_key[tr_lo + move[a]] < t.tr_key[tr_lo + move[b]];
+    };
+    bool big = false;
+    for (u32 sl = lane; sl < A + C; sl += 32) {
+        u32 n = cnt[sl], b0 = off[sl];
+        if (n > 32) { big = true; continue; }
+        for (u32 x = 1; x < n; x++) {
+            u32 vx = child[b0 + x], y = x;
+            while (y > 0 && before(vx, child[b0 + y - 1])) { child[b0 + y] = child[b0 + y - 1]; y--; }
+            child[b0 + y] = vx;
+        }
+    }
+    if (__any_sync(LB_FULL, big)) {
+        for (u32 s0 = 0; s0 < A + C; s0 += 32) {
+            u32 sl = s0 + (u32)lane;
+            unsigned m = __ballot_sync(LB_FULL, sl < A + C && cnt[sl] > 32);
+            while (m) {
+                int q = __ffs(m) - 1;
+                m &= m - 1;
+                u32 bs = s0 + (u32)q;
+                warp_sort_vals(child + off[bs], cnt[bs], lane, before);
+            }
+        }
     }
     __syncwarp();
-    for (u32 j = lane; j < A; j += 32) {
-        u64 k = nkey[j];
-        if (k == ~0ull) continue;
-        u32 slot = (u32)(k >> 32);
-        t.tn_sib[base + child[j]] = j - t.tn_base[base + slot];
-        if (j + 1 == A || (u32)(nkey[j + 1] >> 32) != slot) t.tn_cnt[base + slot] = j + 1 - t.tn_base[base + slot];
+    for (u32 sl = lane; sl < A + C; sl += 32) {
+        u32 n = cnt[sl], b0 = off[sl];
+        for (u32 x = 0; x < n; x++) t.tn_sib[base + child[b0 + x]] = x;
     }
+    __syncwarp();
+    // ---- JSON layout of the hierarchy (meta maps assumed empty; a document where a node's meta map exists keeps
+    // the serial walk).  The sort keys are dead: their space becomes sub[] / rel[].
+    const DocPeer* dpeer = t.dpeer + di.peer0;
+    const u32 P = di.P;
+    bool has_meta = false;
+    for (u32 c = lane; c < C; c += 32) {
+        const DocContainer& dc = t.dcont[di.cid0 + c];
+        if (dc.is_root || dc.type != CT_MAP || dc.key_or_peer >= P) continue;
+        const DocPeer& dp = dpeer[dc.key_or_peer];
+        if (dc.counter >= 0 && dc.counter < dp.end_counter && parent[dp.atom_base + (u32)dc.counter] != TREE_UNEXIST) has_meta = true;
+    }
+    has_meta = __any_sync(LB_FULL, has_meta);
+    u32* sub = (u32*)nkey;
+    u32* rel = sub + (A + C);
+    u32* root = t.tn_root + base;
+    for (u32 i = lane; i < A + C; i += 32) sub[i] = 0;
+    __syncwarp();
+    // alive nodes, their own bytes added to every ancestor and to the root slot
+    for (u32 a = lane; a < A; a += 32) {
+        u32 r = TREE_UNEXIST;
+        u32 p = parent[a];
+        if (p != TREE_UNEXIST && p != TREE_DELETED) {
+            u32 cur = a;
+            for (u32 guard = 0; guard <= A; guard++) {
+                u32 pp = parent[cur];
+                if (pp >= TREE_UNEXIST) { if (pp == TREE_ROOT) r = A + t.op_cidx[t.tr_rec[tr_lo + move[cur]].w]; break; }
+                cur = pp;
+            }
+        }
+        root[a] = r;
+        if (r == TREE_UNEXIST) continue;
+        u32 sib = t.tn_sib[base + a];
+        u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, p, sib, t.pos_len[t.tr_rec[tr_lo + move[a]].z]);
+        u32 cur = a;
+        for (u32 guard = 0; guard <= A; guard++) {
+            atomicAdd(&sub[cur], own);
+            u32 pp = parent[cur];
+            if (pp >= TREE_UNEXIST) break;
+            cur = pp;
+        }
+        atomicAdd(&sub[r], own);
+    }
+    __syncwarp();
+    // offset of every child inside its parent's children list (lane per list)
+    for (u32 s = lane; s < A + C; s += 32) {
+        u32 n = t.tn_cnt[base + s], b0 = t.tn_base[base + s], acc = 0;
+        for (u32 i = 0; i < n; i++) { u32 c = child[b0 + i]; rel[c] = acc; acc += sub[c]; }
+    }
+    __syncwarp();
+    for (u32 a = lane; a < A; a += 32) {
+        if (root[a] == TREE_UNEXIST) continue;
+        u32 o = 1, cur = a;   // 1 = the container's '['
+        for (u32 guard = 0; guard <= A; guard++) {
+            o += rel[cur];
+            u32 pp = parent[cur];
+            if (pp >= TREE_UNEXIST) break;
+            o += tree_open_len(t.tn_sib[base + pp]);
+            cur = pp;
+        }
+        u32 sib = t.tn_sib[base + a];
+        u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, parent[a], sib, t.pos_len[t.tr_rec[tr_lo + move[a]].z]);
+        t.tn_aopen[base + a] = o;
+        t.tn_aclose[base + a] = o + tree_open_len(sib) + (sub[a] - own);
+    }
+    if (lane == 0) docs[d].has_tree = has_meta ? 1u : 3u;   // bit1: the lane-parallel JSON layout is valid
 }

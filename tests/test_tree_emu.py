@@ -140,3 +140,23 @@ def test_config_c5_generator_documents():
         assert o.export_updates() == blob
     check_batch_against_oracle(blobs, lib_path=EMU, expect_json=[g.expected_json(i) for i in range(5)])
     check_export_against_oracle(blobs, lib_path=EMU)
+
+
+def test_tree_long_sibling_list_with_equal_positions():
+    """More than 32 children under one parent, appended concurrently by three peers (equal fractional indexes
+    across peers): the warp-sorted sibling path, ties broken by (lamport, peer)."""
+    docs = [OracleDoc(30 + i) for i in range(3)]
+    ts = [d.get_tree("t") for d in docs]
+    r = docs[0].tree_create(ts[0])
+    for j in (1, 2):
+        workloads.merge(docs[j], docs[0])
+    for i, d in enumerate(docs):
+        for _ in range(20):
+            d.tree_create(ts[i], r)
+    for _ in range(2):
+        for i in range(3):
+            for j in range(3):
+                if i != j:
+                    workloads.merge(docs[i], docs[j])
+    b = check_batch_against_oracle([docs[0].export_updates()], lib_path=EMU)
+    assert len(b.get_deep_value(0)["t"][0]["children"]) == 60
