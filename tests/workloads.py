@@ -14,7 +14,35 @@ def merge(a, b):
     return a.import_(b.export_updates(a.oplog_vv()))
 
 
-def random_edit(rnd, d, text, lst, mp, weights=(0.35, 0.15, 0.25, 0.10, 0.12, 0.03), unicode_=True):
+def random_child_edit(rnd, d, lst, mp):
+    """Child containers (handler.rs insert_container): created inside the root map or list, then edited like roots;
+    state.rs:1039 get_container_deep_value inlines them in the parent's JSON."""
+    if not hasattr(d, "_kids"):
+        d._kids = []   # child container handles this site created
+    kids = d._kids
+    if not kids or rnd.random() < 0.3:
+        ctype = rnd.choice([oracle.CT_TEXT, oracle.CT_LIST, oracle.CT_MAP])
+        if rnd.random() < 0.5:
+            h = d.map_set_container(mp, "c%d" % rnd.randrange(6), ctype)
+        else:
+            h = d.list_insert_container(lst, rnd.randint(0, d.seq_len(lst)), ctype)
+        kids.append((h, ctype))
+        return
+    h, ctype = rnd.choice(kids)
+    if ctype == oracle.CT_TEXT:
+        d.text_insert(h, rnd.randint(0, d.seq_len(h)), "".join(rnd.choice("child xyz") for _ in range(rnd.randint(1, 4))))
+    elif ctype == oracle.CT_LIST:
+        if rnd.random() < 0.2 and len(kids) < 12:   # a grandchild
+            kids.append((d.list_insert_container(h, rnd.randint(0, d.seq_len(h)), oracle.CT_MAP), oracle.CT_MAP))
+        else:
+            d.list_insert(h, rnd.randint(0, d.seq_len(h)), rnd.randint(0, 9))
+    else:
+        d.map_set(h, "k%d" % rnd.randrange(3), rnd.randint(0, 99))
+
+
+def random_edit(rnd, d, text, lst, mp, weights=(0.35, 0.15, 0.25, 0.10, 0.12, 0.03), unicode_=True, children=0.04):
+    if children and rnd.random() < children:
+        return random_child_edit(rnd, d, lst, mp)
     r = rnd.random()
     w = weights
     alphabet = "abcdefg xyz\"\\\n" + ("é中😀" if unicode_ else "")
