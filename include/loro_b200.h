@@ -13,6 +13,7 @@
  *                            crates/loro-common/src/error.rs:8-105 (LoroError variants -> lb_doc_code)
  *   lb_doc_json              crates/loro/src/lib.rs:866  LoroDoc::get_deep_value() (serde_json text, keys sorted)
  *   lb_doc_vv                crates/loro/src/lib.rs:816  LoroDoc::oplog_vv()
+ *   lb_doc_frontiers         crates/loro/src/lib.rs:881  LoroDoc::oplog_frontiers()
  *   lb_doc_export_updates    crates/loro/src/lib.rs:1235 LoroDoc::export(ExportMode::all_updates())
  *                            crates/loro-internal/src/encoding.rs:350-416, oplog/change_store.rs:494-576
  *   lb_batch_counters        crates/loro-internal/src/loro.rs:1458 len_ops / len_changes (summed over the batch)
@@ -123,6 +124,9 @@ size_t lb_doc_count(const lb_batch* b);
 lb_status lb_doc_status(const lb_batch* b, size_t doc, lb_import_status* out);
 lb_status lb_doc_json(const lb_batch* b, size_t doc, const char** utf8, size_t* len);
 lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n); /* start=0,end=vv[peer] */
+/* LoroDoc::oplog_frontiers() (crates/loro/src/lib.rs:881; version/frontiers.rs:233-246): the heads of the causal graph,
+ * one span [counter, counter + 1) per head id. */
+lb_status lb_doc_frontiers(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n);
 /* LoroDoc::export(ExportMode::all_updates()) of document `doc` (crates/loro/src/lib.rs:1235, encoding.rs:350-416):
  * the FastUpdates blob a fresh reference document would export after importing the same input.  Needs
  * LB_FLAG_EXPORT at import time.  `from` (a version vector) must be NULL / 0 for now: only all_updates.

@@ -84,6 +84,7 @@ def load_library(path=None):
     L.lb_doc_export_updates.argtypes = [vp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
     L.lb_doc_vv.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(_IdSpan)), ctypes.POINTER(ctypes.c_size_t)]
+    L.lb_doc_frontiers.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(_IdSpan)), ctypes.POINTER(ctypes.c_size_t)]
     L.lb_batch_counters.argtypes = [vp, ctypes.POINTER(_Counters)]
     L.lb_batch_timings.argtypes = [vp, ctypes.POINTER(_Timings)]
     L.lb_last_error.restype = ctypes.c_char_p
@@ -169,6 +170,13 @@ class Batch:
         n = ctypes.c_size_t()
         _check(self._L, self._L.lb_doc_vv(self._h, i, ctypes.byref(spans), ctypes.byref(n)), "lb_doc_vv")
         return {spans[k].peer: spans[k].end for k in range(n.value)}
+
+    def oplog_frontiers(self, i):
+        """LoroDoc::oplog_frontiers(): sorted list of (peer, counter) head ids."""
+        spans = ctypes.POINTER(_IdSpan)()
+        n = ctypes.c_size_t()
+        _check(self._L, self._L.lb_doc_frontiers(self._h, i, ctypes.byref(spans), ctypes.byref(n)), "lb_doc_frontiers")
+        return sorted((spans[k].peer, spans[k].start) for k in range(n.value))
 
     def counters(self):
         c = _Counters()

@@ -169,7 +169,7 @@ struct lb_batch {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t json_ev = nullptr;
     std::thread json_thread;
-    std::vector<std::vector<lb_id_span>> success, pending, vv;
+    std::vector<std::vector<lb_id_span>> success, pending, vv, frontiers;
     std::vector<uint64_t> doc_ids;
     lb_counters counters{};
     lb_timings timings{};
@@ -319,8 +319,9 @@ void pipeline(lb_batch* b) {
     rt.ch_vv = dv.alloc<i32>(VV);
     u32* d_cursor = dv.alloc<u32>(NP);
     LB_LAUNCH(k_doc_causal, nblk(D, 64), 64, 0, st, b->d_docs, D, blk, rt, d_cursor);
+    LB_LAUNCH(k_doc_frontiers, nblk(D, 64), 64, 0, st, b->d_docs, D, rt);
     LB_LAUNCH(k_doc_sizes, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a, d_tmp_b, d_tmp_c, 1);
-    tm.kernel_launches += 2;
+    tm.kernel_launches += 3;
     run_scans(b, {ScanJob{(const u8*)d_tmp_b, (u8*)b->d_docs + offsetof(DocInfo, atom0), 4, sizeof(DocInfo), D},
                   ScanJob{(const u8*)d_tmp_c, (u8*)b->d_docs + offsetof(DocInfo, mapslot0), 4, sizeof(DocInfo), D}});
     DocInfo dtot = d2h_one(b, &b->d_docs[D]);
@@ -581,6 +582,7 @@ void build_status(lb_batch* b) {
     b->success.assign(D, {});
     b->pending.assign(D, {});
     b->vv.assign(D, {});
+    b->frontiers.assign(D, {});
     for (size_t d = 0; d < D; d++) {
         DocInfo& di = b->docs[d];
         if (di.code == DOC_OK && di.has_unsupported) di.code = DOC_ERR_UNSUPPORTED;
@@ -592,6 +594,7 @@ void build_status(lb_batch* b) {
                 b->vv[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
             }
             if (dp.pend_hi > dp.pend_lo) b->pending[d].push_back(lb_id_span{dp.id, dp.pend_lo, dp.pend_hi});
+            if (dp.is_head && dp.end_counter > 0) b->frontiers[d].push_back(lb_id_span{dp.id, dp.end_counter - 1, dp.end_counter});
         }
     }
 }
@@ -847,6 +850,13 @@ lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, siz
     if (!b || !spans || !n || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
     *spans = b->vv[doc].data();
     *n = b->vv[doc].size();
+    return LB_OK;
+}
+
+lb_status lb_doc_frontiers(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n) {
+    if (!b || !spans || !n || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
+    *spans = b->frontiers[doc].data();
+    *n = b->frontiers[doc].size();
     return LB_OK;
 }
 

@@ -341,3 +341,29 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
     di.atom_total = base;
     docs[d] = di;
 }
+
+// thread per doc: frontiers = the heads of the causal graph (reference: version/frontiers.rs:233-246
+// update_frontiers_on_new_change, oplog/loro_dag.rs:251-269).  The last id of peer p is a head unless it lies in the
+// causal past of another peer's change; version vectors grow along a peer's chain, so looking at every peer's LAST
+// applied change is enough.
+__global__ void k_doc_frontiers(const DocInfo* __restrict__ docs, u32 n_docs, ResolveTables t) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    if (di.code != DOC_OK) return;
+    u32 P = di.P;
+    for (u32 p = 0; p < P; p++) t.dpeer[di.peer0 + p].is_head = t.dpeer[di.peer0 + p].end_counter > 0 ? 1u : 0u;
+    for (u32 q = 0; q < P; q++) {
+        const DocPeer& dq = t.dpeer[di.peer0 + q];
+        // last applied change of q
+        u32 last = 0xFFFFFFFFu;
+        for (u32 k = dq.ch_count; k-- > 0;) {
+            u32 ch = t.ch_order[di.ch0 + dq.ch_first + k];
+            if (t.ch_applied[ch]) { last = ch; break; }
+        }
+        if (last == 0xFFFFFFFFu) continue;
+        const i32* v = t.ch_vv + di.vv0 + (u64)t.ch_pos[last] * P;
+        for (u32 p = 0; p < P; p++)
+            if (p != q && v[p] >= t.dpeer[di.peer0 + p].end_counter && t.dpeer[di.peer0 + p].end_counter > 0) t.dpeer[di.peer0 + p].is_head = 0;
+    }
+}

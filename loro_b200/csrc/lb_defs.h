@@ -67,6 +67,8 @@ struct DocPeer {
     u32 ch_first;      // index into doc_change_order of this peer's first change
     u32 ch_count;
     i32 pend_lo, pend_hi;  // pending counter range (lo<hi when any)
+    u32 is_head;           // the peer's last imported id is a frontier of the document (version/frontiers.rs:233-246)
+    u32 pad_;
 };
 
 // doc-level container entry (reference: ContainerID, loro-common/src/lib.rs:114-180)

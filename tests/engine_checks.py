@@ -27,6 +27,7 @@ def check_batch_against_oracle(blobs, lib_path=None, expect_json=None):
         assert st.code == 0, (i, st)
         assert batch.json_bytes(i) == (expect_json[i] if expect_json else o.json_text()), i
         assert batch.oplog_vv(i) == o.oplog_vv(), i
+        assert batch.oplog_frontiers(i) == sorted(o.frontiers()), (i, batch.oplog_frontiers(i), o.frontiers())
         assert st.success == ost["success"], (i, st.success, ost["success"])
         assert st.pending == ost["pending"], (i, st.pending, ost["pending"])
     return batch
