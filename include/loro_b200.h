@@ -106,6 +106,9 @@ typedef struct lb_timings { /* device time per phase in milliseconds (CUDA event
     float tree;                        /* movable-tree phase (sort, apply, sibling lists) */
     uint32_t reserved0;
     uint64_t tree_ops;                 /* RawTreeMove rows decoded */
+    /* change blocks by decode path: lane-parallel rows / staged in shared memory with the rows on one lane /
+     * larger than the staging buffer (k_decode_warp.cuh) */
+    uint64_t decode_fast_blocks, decode_lane_blocks, decode_unstaged_blocks;
 } lb_timings;
 
 typedef struct lb_batch lb_batch;

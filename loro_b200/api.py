@@ -54,7 +54,9 @@ class _Timings(ctypes.Structure):
                                                "materialise", "d2h", "total_device", "reexport")] + \
                [("decode_bytes_read", ctypes.c_uint64), ("decode_bytes_written", ctypes.c_uint64),
                 ("kernel_launches", ctypes.c_uint32), ("export_bytes", ctypes.c_uint64),
-                ("tree", ctypes.c_float), ("reserved0", ctypes.c_uint32), ("tree_ops", ctypes.c_uint64)]
+                ("tree", ctypes.c_float), ("reserved0", ctypes.c_uint32), ("tree_ops", ctypes.c_uint64),
+                ("decode_fast_blocks", ctypes.c_uint64), ("decode_lane_blocks", ctypes.c_uint64),
+                ("decode_unstaged_blocks", ctypes.c_uint64)]
 
 
 _libs = {}

@@ -17,6 +17,7 @@
 #include "lb_defs.h"
 #include "k_frame.cuh"
 #include "k_decode.cuh"
+#include "k_decode_warp.cuh"
 #include "k_resolve.cuh"
 #include "k_classify.cuh"
 #include "k_seq.cuh"
@@ -281,8 +282,22 @@ void pipeline(lb_batch* b) {
     t.pos_off = dv.alloc<u64>(NPOS); t.pos_len = dv.alloc<u32>(NPOS); t.pos_pool = dv.alloc<u8>(NPOSB + 8);
     t.tr_target_peer = dv.alloc<u32>(NTR); t.tr_target_ctr = dv.alloc<i32>(NTR); t.tr_parent_kind = dv.alloc<u8>(NTR);
     t.tr_parent_peer = dv.alloc<u32>(NTR); t.tr_parent_ctr = dv.alloc<i32>(NTR); t.tr_pos = dv.alloc<u32>(NTR);
+    t.dw_stats = dv.alloc<unsigned long long>(4, true);
     if (B) {
-        LB_LAUNCH(k_block_decode, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
+        // decoder variants (A/B switch LB_DECODE = rows | cols | warp): thread per block with all cursors at once,
+        // thread per block one column at a time (default), warp per block on TMA-staged shared memory
+        static const char* mode_env = getenv("LB_DECODE");
+        static const int mode = !mode_env ? 1 : (!strcmp(mode_env, "rows") ? 0 : (!strcmp(mode_env, "warp") ? 2 : 1));
+        if (mode == 0) LB_LAUNCH(k_block_decode, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
+        else if (mode == 1) LB_LAUNCH(k_block_decode_cols, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
+        else {
+            const size_t smem = sizeof(DwWarp) * DW_WARPS;
+#ifndef LB_SIMT_EMU
+            static bool attr_set = false;
+            if (!attr_set) { CK(cudaFuncSetAttribute(k_block_decode_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+#endif
+            LB_LAUNCH(k_block_decode_warp, nblk(B, DW_WARPS), 32 * DW_WARPS, smem, st, b->d_bytes, blk, B, t);
+        }
         tm.kernel_launches += 1;
     }
     mark(b);  // [2] decode done
@@ -339,10 +354,6 @@ void pipeline(lb_batch* b) {
     ct.tr_target_peer = t.tr_target_peer; ct.tr_target_ctr = t.tr_target_ctr; ct.tr_parent_kind = t.tr_parent_kind;
     ct.tr_parent_peer = t.tr_parent_peer; ct.tr_parent_ctr = t.tr_parent_ctr; ct.tr_pos = t.tr_pos;
     ct.tr_rec = dv.alloc<uint4>(NTR); ct.tr_key = dv.alloc<u64>(NTR); ct.tr_ids = dv.alloc<uint4>(NTR);
-    if (NTR) {   // ops that are not applied keep row = NONE / key = +inf
-        CK(cudaMemsetAsync(ct.tr_rec, 0xFF, sizeof(uint4) * NTR, st));
-        CK(cudaMemsetAsync(ct.tr_key, 0xFF, sizeof(u64) * NTR, st));
-    }
     ct.cid_map = rt.cid_map; ct.key_map = rt.key_map; ct.dcont = dcont; ct.dpeer = b->d_dpeer;
     ct.op_kind = dv.alloc<u8>(NR); ct.op_cidx = dv.alloc<u32>(NR); ct.op_lamport = dv.alloc<u32>(NR);
     ct.atom_row = dv.alloc<u32>(NATOM);
@@ -557,6 +568,8 @@ void pipeline(lb_batch* b) {
     if (NP) CK(cudaMemcpyAsync(b->dpeer.data(), b->d_dpeer, sizeof(DocPeer) * NP, cudaMemcpyDeviceToHost, st));
     unsigned long long acc[4];
     CK(cudaMemcpyAsync(acc, d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
+    unsigned long long dws[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(dws, t.dw_stats, sizeof(dws), cudaMemcpyDeviceToHost, st));
     if (b->d_xdoc) {
         b->xdocs.resize(D);
         CK(cudaMemcpyAsync(b->xdocs.data(), b->d_xdoc, sizeof(XDoc) * D, cudaMemcpyDeviceToHost, st));
@@ -572,6 +585,7 @@ void pipeline(lb_batch* b) {
     c.atom_ops = acc[1];
     c.pending_changes = acc[2];
     c.state_hash = acc[0];
+    tm.decode_fast_blocks = dws[0]; tm.decode_lane_blocks = dws[1]; tm.decode_unstaged_blocks = dws[2];
     c.json_bytes = 0;
     for (u32 d = 0; d < D; d++) c.json_bytes += b->docs[d].json_len;
     (void)NDEL;
@@ -960,4 +974,12 @@ void lb_batch_free(lb_batch* b) {
     delete b;
 }
 
+#ifdef LB_SIMT_EMU
+// test hook of the emulated build only: the device-side f64 formatter on the host (tests/test_f64_format.py)
+int lb_emu_format_f64(double d, char* out) {
+    u64 bits;
+    memcpy(&bits, &d, 8);
+    return f64_format(bits, out);
+}
+#endif
 }  // extern "C"

@@ -72,6 +72,13 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
     }
     if (!t.ch_applied[ch]) kind = OPK_SKIP;
     u32 lam = t.ch_lamport[ch] + (u32)(t.op_counter[row] - t.ch_counter[ch]);
+    if (kind != OPK_TREE && t.op_vtype[row] == VK_RAW_TREE_MOVE) {
+        // a RawTreeMove row that is not an applied op of a Tree container: its slot of the tree tables says so (the
+        // tree kernel skips it; the tables are not pre-filled)
+        u32 ti = t.op_del[row];
+        t.tr_rec[ti].w = 0xFFFFFFFFu;
+        t.tr_key[ti] = ~0ull;
+    }
     if (kind == OPK_TREE) {
         // target and parent must be atoms the document holds: an applied move causally follows the creation of both
         // nodes (tree ids are the ids of the create ops: loro-common/src/lib.rs TreeID)
@@ -87,7 +94,7 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
             ok = pp < di.P && pc >= 0 && pc < t.dpeer[di.peer0 + pp].end_counter;
             if (ok) pa = t.dpeer[di.peer0 + pp].atom_base + (u32)pc;
         }
-        if (!ok) { kind = OPK_SKIP; di.code = LB_ERR(DOC_ERR_CORRUPT); }
+        if (!ok) { kind = OPK_SKIP; di.code = LB_ERR(DOC_ERR_CORRUPT); t.tr_rec[ti].w = 0xFFFFFFFFu; t.tr_key[ti] = ~0ull; }
         else {
             uint4 tr;
             tr.x = t.dpeer[di.peer0 + tp].atom_base + (u32)tc;

@@ -271,18 +271,19 @@ struct Tables {
     // fractional indexes (expanded) + movable-tree ops (op_del of a RawTreeMove row indexes tr_*)
     u64* pos_off; u32* pos_len; u8* pos_pool;
     u32* tr_target_peer; i32* tr_target_ctr; u8* tr_parent_kind; u32* tr_parent_peer; i32* tr_parent_ctr; u32* tr_pos;
+    unsigned long long* dw_stats;   // [0] blocks decoded lane-parallel, [1] staged but rows on one lane, [2] not staged
 };
 enum { TRP_ROOT = 0, TRP_NODE = 1, TRP_DELETED = 2 };
 
 // ---------------------------------------------------------------- pass 2: fill
-// (no register cap: measured on B200, capping at 128 / 80 / 64 registers costs 1.2x / 2.1x / 2.5x in spills)
-__global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks,
-                               Tables t) {
-    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_blocks) return;
-    BlockInfo bi = blocks[i];
-    if (bi.err) return;
-    const u8* b = bytes + bi.off;
+// The block decoder in three single-thread pieces (`b` = the block's bytes, in global or in shared memory):
+//   decode_block_small  header, change meta, keys, cids, positions   (tens of bytes per block)
+//   decode_block_rows   delete-start ids, the four ops columns, the values walk   (the bulk)
+//   decode_block_fail   a failed block still leaves its rows pointing at its own changes
+// k_block_decode runs them one thread per block (blocks larger than the staging buffer, and the emulated build's
+// reference path); k_block_decode_warp (k_decode_warp.cuh) stages the block in shared memory and replaces
+// decode_block_rows by lane-parallel column expansion and value-chain resolution.
+__device__ inline u32 decode_block_small(const u8* b, const BlockInfo& bi, u64 i, const Tables& t) {
     u32 N = bi.n_changes;
     u32 err = 0;
     // ---- header
@@ -437,26 +438,6 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         }
         if (c.err || !c.empty()) err = err ? err : LB_ERR(DOC_ERR_DECODE);
     }
-    // ---- delete start ids (3 DeltaRle columns)
-    if (bi.sec_len[6]) {
-        const u8* col[3];
-        u32 cl[3];
-        if (!columnar_open(b + bi.sec_off[6], bi.sec_len[6], 3, col, cl)) err = err ? err : LB_ERR(DOC_ERR_DECODE);
-        else {
-            RleCur a(col[0], cl[0], 2), bb(col[1], cl[1], 2), cc(col[2], cl[2], 2);
-            i64 pa = 0, pb = 0, pc = 0;
-            for (u32 q = 0; q < bi.n_dels; q++) {
-                i64 x, y, z;
-                if (!a.next(&x) || !bb.next(&y) || !cc.next(&z)) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
-                pa += x; pb += y; pc += z;
-                if (pa < 0 || (u64)pa >= bi.n_peers || pc == 0) err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
-                t.del_peer_idx[bi.del0 + q] = (u32)pa;
-                t.del_counter[bi.del0 + q] = (i32)pb;
-                t.del_len[bi.del0 + q] = (i32)pc;
-            }
-            if (a.c.err || bb.c.err || cc.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
-        }
-    } else if (bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
     // ---- positions: expand the prefix-compressed fractional indexes into the pool (arena.rs:187-204)
     if (bi.n_pos) {
         const u8* pc[2];
@@ -481,6 +462,31 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
             w += last_len;
         }
     }
+    return err;
+}
+
+__device__ inline u32 decode_block_rows(const u8* b, const BlockInfo& bi, const Tables& t, u32 err, u32* n_maps_out) {
+    u32 N = bi.n_changes;
+    // ---- delete start ids (3 DeltaRle columns)
+    if (bi.sec_len[6]) {
+        const u8* col[3];
+        u32 cl[3];
+        if (!columnar_open(b + bi.sec_off[6], bi.sec_len[6], 3, col, cl)) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        else {
+            RleCur a(col[0], cl[0], 2), bb(col[1], cl[1], 2), cc(col[2], cl[2], 2);
+            i64 pa = 0, pb = 0, pc = 0;
+            for (u32 q = 0; q < bi.n_dels; q++) {
+                i64 x, y, z;
+                if (!a.next(&x) || !bb.next(&y) || !cc.next(&z)) { err = err ? err : LB_ERR(DOC_ERR_DECODE); break; }
+                pa += x; pb += y; pc += z;
+                if (pa < 0 || (u64)pa >= bi.n_peers || pc == 0) err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
+                t.del_peer_idx[bi.del0 + q] = (u32)pa;
+                t.del_counter[bi.del0 + q] = (i32)pb;
+                t.del_len[bi.del0 + q] = (i32)pc;
+            }
+            if (a.c.err || bb.c.err || cc.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        }
+    } else if (bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
     // ---- ops: 4 columns + values walk
     {
         const u8* col[4];
@@ -563,13 +569,163 @@ __global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restri
         if (v.err || !v.empty() || c0.c.err || c1.c.err || c2.c.err || c3.c.err) err = err ? err : LB_ERR(DOC_ERR_DECODE);
         if (!err && (change != N || counter != (i32)(bi.counter_start + bi.counter_len) || ndel != bi.n_dels || ntree != bi.n_tree))
             err = LB_ERR(DOC_ERR_CORRUPT);
-        blocks[i].n_value_maps = n_maps;
+        *n_maps_out = n_maps;
     }
-    if (err) {
+    return err;
+}
+
+// ---- the rows again, one COLUMN at a time: a thread has a single byte cursor alive at any moment, so its cache
+// lines stay resident in L1 between windows (seven cursors 4 KB apart thrashed it: 26 % sector hits in
+// profiles/r1_ncu_decode.md), the loop bodies need a fraction of the registers, and consecutive stores of a thread
+// fall into the same 32-byte sector back to back.  The values walk reads the kind / length / container of a row back
+// from the tables the column passes just wrote (sequential per thread).  Same results, same error codes.
+template <int MODE, class Emit>
+__device__ __forceinline__ u32 column_pass(const u8* col, u32 len, u32 n, Emit emit) {   // returns rows emitted, ~0u on malformed input
+    RleCur c(col, len, MODE);
+    i64 acc = 0;
+    u32 r = 0;
+    for (; r < n; r++) {
+        i64 v;
+        if (!c.next(&v)) break;
+        if (MODE == 2) { acc += v; v = acc; }
+        emit(r, v);
+    }
+    if (c.c.err) return 0xFFFFFFFFu;
+    i64 extra;
+    if (r == n && c.next(&extra)) return 0xFFFFFFFFu;   // more rows than announced
+    return r;
+}
+__device__ inline u32 decode_block_rows_cols(const u8* b, const BlockInfo& bi, const Tables& t, u32 err, u32* n_maps_out) {
+    const u32 N = bi.n_changes, R = bi.n_ops;
+    // ---- delete start ids
+    if (bi.sec_len[6]) {
+        const u8* col[3];
+        u32 cl[3];
+        if (!columnar_open(b + bi.sec_off[6], bi.sec_len[6], 3, col, cl)) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        else {
+            const u64 d0 = bi.del0;
+            const u32 np = bi.n_peers;
+            bool corrupt = false;
+            u32 n0 = column_pass<2>(col[0], cl[0], bi.n_dels, [&](u32 r, i64 v) { if (v < 0 || (u64)v >= np) corrupt = true; t.del_peer_idx[d0 + r] = (u32)v; });
+            u32 n1 = column_pass<2>(col[1], cl[1], bi.n_dels, [&](u32 r, i64 v) { t.del_counter[d0 + r] = (i32)v; });
+            u32 n2 = column_pass<2>(col[2], cl[2], bi.n_dels, [&](u32 r, i64 v) { if (v == 0) corrupt = true; t.del_len[d0 + r] = (i32)v; });
+            if (n0 != bi.n_dels || n1 != bi.n_dels || n2 != bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+            else if (corrupt) err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
+        }
+    } else if (bi.n_dels) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+    // ---- ops columns
+    const u8* col[4];
+    u32 cl[4];
+    columnar_open(b + bi.sec_off[5], bi.sec_len[5], 4, col, cl);   // (validated by the count pass)
+    const u64 r0 = bi.op0;
+    {
+        const u32 nc = bi.n_cids;
+        bool corrupt = false;
+        u32 n0 = column_pass<2>(col[0], cl[0], R, [&](u32 r, i64 v) { if (v < 0 || (u64)v >= nc) { corrupt = true; v = 0; } t.op_cid[r0 + r] = (u32)v; });
+        u32 n1 = column_pass<2>(col[1], cl[1], R, [&](u32 r, i64 v) { t.op_prop[r0 + r] = (i32)v; });
+        u32 n2 = column_pass<0>(col[2], cl[2], R, [&](u32 r, i64 v) { t.op_vtype[r0 + r] = (u8)v; });
+        // lengths: counters and the change of every row fall out of the same pass
+        i32 counter = (i32)bi.counter_start;
+        u32 change = 0, ch_first_row = 0;
+        i32 next_boundary = (i32)bi.counter_start + (i32)t.ch_len[bi.ch0];
+        t.ch_op0[bi.ch0] = r0;
+        bool straddle = false;
+        u32 n3 = column_pass<1>(col[3], cl[3], R, [&](u32 r, i64 v) {
+            if (v <= 0 || v > 0x7FFFFFFF || change >= N) { corrupt = true; v = 1; }
+            t.op_len[r0 + r] = (u32)v;
+            t.op_counter[r0 + r] = counter;
+            t.op_change[r0 + r] = (u32)(bi.ch0 + (change < N ? change : N - 1));
+            counter += (i32)v;
+            if (counter > next_boundary) straddle = true;
+            if (counter == next_boundary && change < N) {
+                t.ch_nops[bi.ch0 + change] = r + 1 - ch_first_row;
+                change++;
+                ch_first_row = r + 1;
+                if (change < N) { t.ch_op0[bi.ch0 + change] = r0 + r + 1; next_boundary += (i32)t.ch_len[bi.ch0 + change]; }
+            }
+        });
+        if (n0 != R || n1 != R || n2 != R || n3 != R) err = err ? err : LB_ERR(DOC_ERR_DECODE);
+        else if (corrupt || straddle || change != N || counter != (i32)(bi.counter_start + bi.counter_len)) err = err ? err : LB_ERR(DOC_ERR_CORRUPT);
+    }
+    if (err) return err;
+    // ---- values walk
+    Cur v(b + bi.sec_off[7], bi.sec_len[7]);
+    u32 ndel = 0, ntree = 0, n_maps = 0;
+    for (u32 r = 0; r < R; r++) {
+        const u64 row = r0 + r;
+        const u8 vt = t.op_vtype[row];
+        if (vt == VK_LORO_VALUE && t.cid_type[bi.cid0 + t.op_cid[row]] == CT_LIST) {
+            Cur pk = v;
+            u8 k = pk.get();
+            u64 n_items = pk.varint();
+            if (k != 7 || n_items != (u64)t.op_len[row]) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
+        }
+        const u8* v0 = v.p;
+        u32 aux_idx = 0xFFFFFFFFu;
+        if (vt == VK_RAW_TREE_MOVE) {
+            u64 sp = v.varint(), sc = v.varint(), pi = v.varint();
+            u8 pn = v.get();
+            u64 pp = 0, pcn = 0;
+            if (!pn) { pp = v.varint(); pcn = v.varint(); }
+            if (ntree >= bi.n_tree || sp >= bi.n_peers || (!pn && pp >= bi.n_peers) || sc > 0x7FFFFFFFull || pcn > 0x7FFFFFFFull) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
+            u8 pk = pn ? TRP_ROOT : TRP_NODE;
+            if (!pn && t.peer_id[bi.peer0 + (u32)pp] == DELETED_ROOT_PEER && (i32)pcn == DELETED_ROOT_CTR) pk = TRP_DELETED;
+            if (pk != TRP_DELETED && pi >= bi.n_pos) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
+            u64 ti = bi.tr0 + ntree++;
+            t.tr_target_peer[ti] = (u32)sp;
+            t.tr_target_ctr[ti] = (i32)sc;
+            t.tr_parent_kind[ti] = pk;
+            t.tr_parent_peer[ti] = (u32)pp;
+            t.tr_parent_ctr[ti] = (i32)pcn;
+            t.tr_pos[ti] = pk == TRP_DELETED ? 0xFFFFFFFFu : (u32)(bi.pos0 + pi);
+            aux_idx = (u32)ti;
+        } else
+            skip_value(v, vt, &n_maps);
+        t.op_val_off[row] = bi.off + (u64)(v0 - b);
+        t.op_val_len[row] = (u32)(v.p - v0);
+        if (vt == VK_DELETE_SEQ) aux_idx = (u32)(bi.del0 + ndel++);
+        t.op_del[row] = aux_idx;
+    }
+    if (!err && (v.err || !v.empty())) err = LB_ERR(DOC_ERR_DECODE);
+    if (!err && (ndel != bi.n_dels || ntree != bi.n_tree)) err = LB_ERR(DOC_ERR_CORRUPT);
+    *n_maps_out = n_maps;
+    return err;
+}
+
+__device__ inline void decode_block_fail(const BlockInfo& bi, u64 i, const Tables& t, BlockInfo* blocks, u32 err) {
+    {
         // row-parallel kernels find their document through op_change: every row of a failed block must point
         // at one of the block's own changes, whatever the walk above managed to write
         for (u32 r = 0; r < bi.n_ops; r++) t.op_change[bi.op0 + r] = (u32)bi.ch0;
-        for (u32 k = 0; k < N; k++) t.ch_block[bi.ch0 + k] = (u32)i;
+        for (u32 k = 0; k < bi.n_changes; k++) t.ch_block[bi.ch0 + k] = (u32)i;
         blocks[i].err = err;
     }
+}
+
+// (no register cap: measured on B200, capping at 128 / 80 / 64 registers costs 1.2x / 2.1x / 2.5x in spills)
+__global__ void k_block_decode(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks,
+                               Tables t) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    BlockInfo bi = blocks[i];
+    if (bi.err) return;
+    const u8* b = bytes + bi.off;
+    u32 n_maps = 0;
+    u32 err = decode_block_small(b, bi, i, t);
+    err = decode_block_rows(b, bi, t, err, &n_maps);
+    blocks[i].n_value_maps = n_maps;
+    if (err) decode_block_fail(bi, i, t, blocks, err);
+}
+// thread per block, one column at a time
+__global__ void k_block_decode_cols(const u8* __restrict__ bytes, BlockInfo* __restrict__ blocks, u64 n_blocks, Tables t) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_blocks) return;
+    BlockInfo bi = blocks[i];
+    if (bi.err) return;
+    const u8* b = bytes + bi.off;
+    u32 n_maps = 0;
+    u32 err = decode_block_small(b, bi, i, t);
+    err = decode_block_rows_cols(b, bi, t, err, &n_maps);
+    blocks[i].n_value_maps = n_maps;
+    if (err) decode_block_fail(bi, i, t, blocks, err);
 }

@@ -10,6 +10,7 @@
 #include "lb_defs.h"
 #include "k_frame.cuh"
 #include "k_tree.cuh"
+#include "lb_f64.cuh"
 
 struct StateTables {
     const u8* bytes;
@@ -317,15 +318,9 @@ struct Emitter {
             case 4: {
                 u64 bits = 0;
                 for (int i = 0; i < 8; i++) bits = (bits << 8) | c.get();
-                double d = __longlong_as_double((long long)bits);
-                // exact only for integral values below 2^53 (serde_json prints "x.0"); flag the rest
-                if (d == d && d > -9.0e15 && d < 9.0e15 && (double)(i64)d == d && !(d == 0 && (bits >> 63))) {
-                    o.put_i64((i64)d);
-                    o.puts_(".0");
-                } else {
-                    o.flags |= 1;
-                    o.puts_("null");
-                }
+                char buf[32];   // shortest round-trip text, as serde_json (ryu) prints it: lb_f64.cuh
+                int n = f64_format(bits, buf);
+                for (int i = 0; i < n; i++) o.put((u8)buf[i]);
                 break;
             }
             case 5: {

@@ -378,7 +378,13 @@ int lo_codec(const char* op, const uint8_t* in, size_t n, int64_t arg, uint8_t**
         Reader r(in, n);
         Writer w;
         std::vector<int64_t> vals;
-        if (name == "xxh32") {
+        if (name == "f64_json") {   // serde_json text of a double (doc.hpp json_f64): checker for the device formatter
+            double d;
+            std::memcpy(&d, in, 8);
+            std::string o;
+            json_f64(o, d);
+            *out = dup_bytes(std::vector<uint8_t>(o.begin(), o.end()), len);
+        } else if (name == "xxh32") {
             vals.push_back(xxh32(in, n, (uint32_t)arg));
             *out = dup_bytes(wr_i64s(vals), len);
         } else if (name == "varint_dec") { vals.push_back((int64_t)r.varint()); vals.push_back((int64_t)(n - r.remaining())); *out = dup_bytes(wr_i64s(vals), len); }

@@ -23,6 +23,10 @@ def reseal(blob):
 def main(lib, seed, n):
     rnd = random.Random(seed)
     base = [workloads.make_doc_history(100 + i, n_sites=3, n_ops=120)[0] for i in range(4)]
+    # documents whose blocks carry one kind of payload: the lane-parallel decode path (k_decode_warp.cuh) and the tree kernels
+    from loro_b200.workload import C3Batch, C5Batch
+    base += C3Batch(2, n_ops=400, prefix_ops=60, sync_every=80).blobs() + C5Batch(2, n_nodes=120, n_moves=40).blobs()
+    base += [workloads.make_tree_history(7, n_sites=3, n_base=20, n_ops=60)[0]]
     if os.environ.get("LB_FUZZ_WIDE"):   # more shapes: many sites, longer histories, an insert larger than a block
         from oracle import OracleDoc
         base += [workloads.make_doc_history(300 + i, n_sites=2 + i, n_ops=200 + 50 * i, sync_prob=0.1)[0] for i in range(4)]
