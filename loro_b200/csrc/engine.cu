@@ -439,6 +439,7 @@ void pipeline(lb_batch* b) {
     stt.dkey_off = rt.dkey_off; stt.dkey_len = rt.dkey_len; stt.map_row = ct.map_row; stt.map_best = ct.map_best;
     stt.op_kind = ct.op_kind; stt.op_vtype = t.op_vtype; stt.op_len = t.op_len; stt.op_counter = t.op_counter;
     stt.op_change = t.op_change; stt.op_val_off = t.op_val_off; stt.op_val_len = t.op_val_len; stt.ch_peer = rt.ch_peer;
+    stt.ch_block = t.ch_block; stt.bkey_off = t.key_off; stt.bkey_len = t.key_len;
     stt.out_row = sp.out_row; stt.out_off = sp.out_off; stt.out_len = sp.out_len;
     stt.blocks = blk; stt.tn_parent = tt.tn_parent; stt.tn_move = tt.tn_move; stt.tn_base = tt.tn_base; stt.tn_cnt = tt.tn_cnt;
     stt.tn_sib = tt.tn_sib; stt.tn_child = tt.tn_child; stt.tr_rec = ct.tr_rec;

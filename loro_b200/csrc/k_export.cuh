@@ -37,7 +37,8 @@ enum { XK_NONE = 0, XK_LIST = 1, XK_TEXT = 2, XK_DEL = 3, XK_MAPSET = 4, XK_MAPD
 
 struct XDoc {          // per document
     u32 n_fc, n_mb;    // final changes, output blocks
-    u32 flags;         // bit0: export unsupported for this document ; bit1: the document has movable-tree ops
+    u32 flags;         // bit0: export unsupported for this document ; bit1: the document has movable-tree ops ;
+                       // bit2: some value holds a nested map (its keys are indices into the block's key arena)
     u32 n_prank;       // distinct fractional indexes of the document (k_exp_posrank)
     u64 ob0;           // first output block (batch-wide)
     u64 scratch0;      // first scratch word of this doc's blocks
@@ -305,7 +306,7 @@ __global__ void k_exp_init(const DocInfo* __restrict__ docs, u32 n_docs, ExportT
         if (di.has_unsupported & 0x7FFFFFFFu) x.flags |= 1;
         if (di.has_tree) x.flags |= 2;
         for (u32 b = di.b0; b < di.b1; b++)
-            if (t.blocks[b].n_value_maps) x.flags |= 1;
+            if (t.blocks[b].n_value_maps) x.flags |= 4;   // payloads with nested maps: key indices are re-registered
     }
     t.xdoc[d] = x;
 }
@@ -880,6 +881,42 @@ struct XReg {
         return n++;
     }
 };
+// LoroValues [p, p + n) copied into `s` with the key indices of nested maps translated from the source block's key
+// arena (doc-level key = key_map[src_key0 + idx]) to the output block's register (write_loro_value registers a map's
+// keys as it meets them: encoding/value.rs:1027-1036).  reg = true: first use registers (the sizing pass).
+__device__ inline void xvalue_copy(XSink& s, const u8* p, u32 n, const ExportTables& t, u64 src_key0, XReg& keys, bool reg) {
+    Cur c(p, n);
+    u32 stack[24];
+    int sp = 0;
+    while (!c.err) {
+        while (sp > 0 && (stack[sp - 1] & 0x7fffffffu) == 0) sp--;
+        if (sp == 0 && c.empty()) return;
+        if (sp > 0) {
+            stack[sp - 1]--;
+            if (stack[sp - 1] & 0x80000000u) {
+                u32 dk = t.key_map[src_key0 + (u32)c.varint()];
+                s.varint(reg ? keys.reg(dk) : keys.inv[dk]);
+            }
+        }
+        u8 kind = c.get();
+        s.put(kind);
+        switch (kind) {
+            case 0: case 1: case 2: break;
+            case 3: { const u8* a = c.p; (void)c.sleb(); s.copy(a, (u64)(c.p - a)); break; }
+            case 4: { const u8* a = c.p; c.skip(8); s.copy(a, (u64)(c.p - a)); break; }
+            case 5: case 6: { const u8* a = c.p; u64 l = c.varint(); c.skip(l); s.copy(a, (u64)(c.p - a)); break; }
+            case 7: case 8: {
+                u64 cnt = c.varint();
+                s.varint(cnt);
+                if (sp >= 24 || cnt > (1u << 28)) return;
+                stack[sp++] = (u32)cnt | (kind == 8 ? 0x80000000u : 0u);
+                break;
+            }
+            case 9: s.put(c.get()); break;
+            default: return;
+        }
+    }
+}
 // cross-peer deps of the block's changes as one flat sequence (cursor: accesses are almost monotonic)
 struct XDeps {
     const ExportTables& t; u32 fc0, N; u32 j; u32 base;
@@ -980,6 +1017,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
     u32* d_ctr = d_peer + B.n_dels;
     u32* d_len = d_ctr + B.n_dels;
     const bool has_tree = (t.xdoc[B.doc].flags & 2u) != 0;
+    const bool has_maps = (t.xdoc[B.doc].flags & 4u) != 0;
     u32* p_rank = d_len + B.n_dels;            // tree documents only (capacity n_rows): sorted distinct position ranks
     const u64 pos_lo = has_tree ? t.blocks[di.b0].pos0 : 0;
     // local index of a fractional index inside this block's position register
@@ -1049,12 +1087,30 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             u32 left = t.fc_nrows[fc0 + j];
             while (left) {
                 u32 first_row = (u32)it.row();
-                XOp o = xop_gather(t, di, it, left, &vbytes);
+                XRows it0 = it;
+                const u32 left0 = left;
+                XOp o = xop_gather(t, di, it, left, has_maps ? nullptr : &vbytes);
                 if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
                 else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
                 // DeltaRle columns are stored as deltas right away (the encoders then read every value once)
                 u32 lc = cids.reg(o.cidx);
                 u32 lp = (o.xk == XK_MAPSET || o.xk == XK_MAPDEL) ? keys.reg((u32)o.prop) : (u32)o.prop;
+                if (has_maps) {   // payload sizes after the op's own registrations: nested keys register in value order
+                    u32 k = left0 - left;
+                    while (k) {
+                        const u8* pp;
+                        u32 pn;
+                        xr_payload(t, it0.row(), o.xk, &pp, &pn);
+                        if (o.xk == XK_LIST || o.xk == XK_MAPSET) {
+                            XSink cs;
+                            cs.dst = nullptr; cs.n = 0;
+                            xvalue_copy(cs, pp, pn, t, t.blocks[t.ch_block[it0.ch]].key0, keys, true);
+                            vbytes += (u32)cs.n;
+                        } else vbytes += pn;
+                        k--;
+                        if (k) it0.next();
+                    }
+                }
                 c_cidx[n_ops] = lc - prev_cidx; prev_cidx = lc;
                 c_prop[n_ops] = lp - prev_prop; prev_prop = lp;
                 c_vt[n_ops] = xk_value_type(o.xk) | ((u32)o.xk << 8);
@@ -1187,7 +1243,8 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                     const u8* pp;
                     u32 pn;
                     xr_payload(t, row, xk, &pp, &pn);
-                    s.copy(pp, pn);
+                    if (has_maps && xk != XK_TEXT) xvalue_copy(s, pp, pn, t, t.blocks[t.ch_block[it.ch]].key0, keys, false);
+                    else s.copy(pp, pn);
                 }
                 left--;
                 if (left) it.next();

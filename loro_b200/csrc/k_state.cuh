@@ -20,6 +20,7 @@ struct StateTables {
     const u8* op_kind; const u8* op_vtype; const u32* op_len; const i32* op_counter; const u32* op_change;
     const u64* op_val_off; const u32* op_val_len;
     const u16* ch_peer;
+    const u32* ch_block; const u64* bkey_off; const u32* bkey_len;   // keys of nested map values index the block's key arena
     const u32* out_row; const u32* out_off; const u32* out_len;
     // movable tree (k_tree.cuh): node tables per document (base DocInfo::tree0) + positions
     const BlockInfo* blocks;
@@ -87,7 +88,8 @@ struct Emitter {
     int sp;
     u32 err;
     int lane;
-    __device__ Emitter(const StateTables& t_, const DocInfo& di_, Sink& o, int lane_) : t(t_), di(di_), out(o), sp(0), err(0), lane(lane_) {}
+    u32 cur_blk;   // block of the op whose value is being printed (nested map keys are block-local indices)
+    __device__ Emitter(const StateTables& t_, const DocInfo& di_, Sink& o, int lane_) : t(t_), di(di_), out(o), sp(0), err(0), lane(lane_), cur_blk(0) {}
 
     __device__ int cmp_bytes(const u8* a, u32 al, const u8* b, u32 bl) {
         u32 n = al < bl ? al : bl;
@@ -356,12 +358,12 @@ struct Emitter {
             case 7: case 8: {
                 u64 n = c.varint();
                 out.put(kind == 7 ? '[' : '{');
-                if (kind == 8) out.flags |= 1;  // nested map values: key order not canonicalised here
                 Frame f;
                 f.kind = kind == 7 ? FK_VLIST : FK_VMAP;
                 f.first = 1;
                 f.a = (u32)n;
-                f.b = f.c = 0;
+                f.b = cur_blk;
+                f.c = 0xFFFFFFFFu;   // FK_VMAP: block-local index of the last key printed
                 f.p = c.p;
                 f.id_peer = id_peer;
                 f.id_ctr = id_ctr;
@@ -514,6 +516,7 @@ struct Emitter {
                     f.c++;
                     bool run_done = f.c >= len;
                     int my = sp - 1;
+                    cur_blk = t.ch_block[t.op_change[row]];
                     emit_value(&p, end, id_peer, id_ctr);
                     // a pushed nested-value frame consumes bytes we cannot see here; re-derive the cursor lazily
                     if (sp - 1 != my) st[my].p = nullptr; else st[my].p = p;
@@ -545,41 +548,64 @@ struct Emitter {
                     out.put(':');
                     u32 row = t.map_row[di.mapslot0 + (u64)f.a * di.K + best];
                     const u8* p = t.bytes + t.op_val_off[row];
+                    cur_blk = t.ch_block[t.op_change[row]];
                     emit_value(&p, p + t.op_val_len[row], t.ch_peer[t.op_change[row]], t.op_counter[row]);
                     break;
                 }
-                case FK_VLIST: case FK_VMAP: {
-                    if (f.a == 0) {
-                        out.put(f.kind == FK_VLIST ? ']' : '}');
-                        sp--;
-                        break;
+                case FK_VMAP: {
+                    // LoroValue::Map inside a value (encoding/value.rs:1027-1036): entries = (key index into the block's
+                    // key arena, value).  Printed in ascending key order like every object here; of two entries with
+                    // the same key the later one wins.  Each step re-scans the entries for the next key.
+                    const BlockInfo& vb = t.blocks[f.b];
+                    const u8* best_val = nullptr;
+                    u32 best = 0xFFFFFFFFu;
+                    {
+                        Cur c(f.p, (size_t)(1u << 30));
+                        for (u32 i = 0; i < f.a && !c.err; i++) {
+                            u64 ki = c.varint();
+                            const u8* val = c.p;
+                            u8 k = c.get();
+                            skip_loro_value_content(c, k, nullptr);
+                            if (ki >= vb.n_keys) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
+                            const u8* kb = t.bytes + t.bkey_off[vb.key0 + ki];
+                            u32 kl = t.bkey_len[vb.key0 + ki];
+                            if (f.c != 0xFFFFFFFFu &&
+                                cmp_bytes(kb, kl, t.bytes + t.bkey_off[vb.key0 + f.c], t.bkey_len[vb.key0 + f.c]) <= 0) continue;
+                            if (best == 0xFFFFFFFFu ||
+                                cmp_bytes(kb, kl, t.bytes + t.bkey_off[vb.key0 + best], t.bkey_len[vb.key0 + best]) <= 0) { best = (u32)ki; best_val = val; }
+                        }
+                        if (c.err) err = LB_ERR(DOC_ERR_CORRUPT);
                     }
-                    // nested values never contain frames that outlive their bytes: re-walk is not needed because
-                    // a child frame pushed from here is itself a FK_V* frame that advances our cursor when it pops
+                    if (err) break;
+                    if (best == 0xFFFFFFFFu) { out.put('}'); sp--; break; }
+                    if (!f.first) out.put(',');
+                    f.first = 0;
+                    f.c = best;
+                    out.put('"');
+                    out.put_escaped(t.bytes + t.bkey_off[vb.key0 + best], t.bkey_len[vb.key0 + best]);
+                    out.put('"');
+                    out.put(':');
+                    cur_blk = f.b;
+                    const u8* p = best_val;
+                    emit_value(&p, p + (1u << 30), f.id_peer, f.id_ctr);
+                    break;
+                }
+                case FK_VLIST: {
+                    if (f.a == 0) { out.put(']'); sp--; break; }
                     if (!f.first) out.put(',');
                     f.first = 0;
                     f.a--;
                     const u8* p = f.p;
                     const u8* end = p + (1u << 30);
-                    if (f.kind == FK_VMAP) {
-                        Cur c(p, (size_t)(1u << 30));
-                        u64 ki = c.varint();
-                        p = c.p;
-                        // keys of nested maps index the *block* key arena: not resolvable here without the
-                        // block; flagged (out.flags bit0) and printed as the index
-                        out.put('"');
-                        out.put_u64(ki);
-                        out.put('"');
-                        out.put(':');
-                    }
                     int my = sp - 1;
-                    // skip over the value to find where the next sibling starts (needed if a child frame is pushed)
+                    // where the next sibling starts (a child frame may be pushed by emit_value)
                     {
                         Cur sk(p, (size_t)(1u << 30));
                         u8 k = sk.get();
                         skip_loro_value_content(sk, k, nullptr);
                         st[my].p = sk.p;
                     }
+                    cur_blk = f.b;
                     emit_value(&p, end, f.id_peer, f.id_ctr);
                     break;
                 }

@@ -47,6 +47,8 @@ def lib():
                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(sz)]
         L.lo_seq_delete.argtypes = [vp, ctypes.c_int, sz, sz]
+        L.lo_list_insert_tagged.argtypes = [vp, ctypes.c_int, sz, sz, ctypes.c_char_p]
+        L.lo_map_set_tagged.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, sz, ctypes.c_char_p]
         L.lo_seq_len.argtypes = [vp, ctypes.c_int]
         L.lo_map_set.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, sz, ctypes.c_int, ctypes.c_int64,
                                  ctypes.c_double, ctypes.c_char_p, sz]
@@ -186,7 +188,36 @@ class OracleDoc:
             else: raise TypeError(v)
         return n, kinds, ints, f64s, strs, slens
 
+    @staticmethod
+    def _tagged(v):
+        import struct
+        if v is None: return b"\x00"
+        if v is True: return b"\x01"
+        if v is False: return b"\x02"
+        if isinstance(v, int): return b"\x03" + struct.pack("<q", v)
+        if isinstance(v, float): return b"\x04" + struct.pack("<d", v)
+        if isinstance(v, str):
+            b = v.encode()
+            return b"\x05" + struct.pack("<I", len(b)) + b
+        if isinstance(v, bytes): return b"\x06" + struct.pack("<I", len(v)) + v
+        if isinstance(v, (list, tuple)): return b"\x07" + struct.pack("<I", len(v)) + b"".join(OracleDoc._tagged(x) for x in v)
+        if isinstance(v, dict):
+            out = b"\x08" + struct.pack("<I", len(v))
+            for k, x in v.items():
+                kb = k.encode()
+                out += struct.pack("<I", len(kb)) + kb + OracleDoc._tagged(x)
+            return out
+        raise TypeError(v)
+
+    @staticmethod
+    def _nested(values):
+        return any(isinstance(v, (list, dict)) for v in values)
+
     def list_insert(self, c, pos, *values):
+        if self._nested(values):   # LoroValue::List / Map items (encoding/value.rs:1027-1036)
+            if lib().lo_list_insert_tagged(self._d, c, pos, len(values), b"".join(self._tagged(v) for v in values)) != 0:
+                raise IndexError("list_insert out of range")
+            return
         n, kinds, ints, f64s, strs, slens = self._vals(values)
         if lib().lo_list_insert(self._d, c, pos, n, kinds, ints, f64s, strs, slens) != 0:
             raise IndexError("list_insert out of range")
@@ -205,6 +236,9 @@ class OracleDoc:
 
     def map_set(self, c, key, v):
         k = key.encode()
+        if self._nested([v]):
+            lib().lo_map_set_tagged(self._d, c, k, len(k), self._tagged(v))
+            return
         n, kinds, ints, f64s, strs, slens = self._vals([v])
         lib().lo_map_set(self._d, c, k, len(k), kinds[0], ints[0], f64s[0], strs[0] or b"", slens[0])
 

@@ -69,6 +69,41 @@ int lo_list_insert(void* d, int cidx, size_t pos, size_t n, const int* kinds, co
                                 slens ? slens[i] : 0));
     return ((Doc*)d)->list_insert(cidx, pos, vals) ? 0 : -1;
 }
+// nested values from Python: tag byte 0 null, 1 true, 2 false, 3 i64 (8 bytes LE), 4 f64 (8 bytes LE), 5 str / 6 binary
+// (u32 length + bytes), 7 list (u32 n + items), 8 map (u32 n + n x (u32 key length, key, value))
+static Value parse_tagged(const uint8_t*& p) {
+    Value v;
+    uint8_t tag = *p++;
+    auto u32_ = [&]() { uint32_t x; std::memcpy(&x, p, 4); p += 4; return x; };
+    switch (tag) {
+        case 0: v.k = Value::Null; break;
+        case 1: v.k = Value::True; break;
+        case 2: v.k = Value::False; break;
+        case 3: { int64_t x; std::memcpy(&x, p, 8); p += 8; v = Value::i64(x); break; }
+        case 4: { double x; std::memcpy(&x, p, 8); p += 8; v = Value::f64(x); break; }
+        case 5: case 6: { uint32_t n = u32_(); v = Value::str(std::string((const char*)p, n)); if (tag == 6) v.k = Value::Binary; p += n; break; }
+        case 7: { uint32_t n = u32_(); v.k = Value::List; for (uint32_t i = 0; i < n; i++) v.list.push_back(parse_tagged(p)); break; }
+        case 8: {
+            uint32_t n = u32_();
+            v.k = Value::Map;
+            for (uint32_t i = 0; i < n; i++) { uint32_t kl = u32_(); std::string key((const char*)p, kl); p += kl; v.map.push_back({key, parse_tagged(p)}); }
+            break;
+        }
+        default: v.k = Value::Null;
+    }
+    return v;
+}
+int lo_list_insert_tagged(void* d, int cidx, size_t pos, size_t n, const uint8_t* buf) {
+    std::vector<Value> vals;
+    const uint8_t* p = buf;
+    for (size_t i = 0; i < n; i++) vals.push_back(parse_tagged(p));
+    return ((Doc*)d)->list_insert(cidx, pos, vals) ? 0 : -1;
+}
+int lo_map_set_tagged(void* d, int cidx, const char* key, size_t klen, const uint8_t* buf) {
+    const uint8_t* p = buf;
+    Value v = parse_tagged(p);
+    return ((Doc*)d)->map_set(cidx, std::string(key, klen), &v) ? 0 : -1;
+}
 int lo_seq_delete(void* d, int cidx, size_t pos, size_t len) {
     return ((Doc*)d)->seq_delete(cidx, pos, len) ? 0 : -1;
 }

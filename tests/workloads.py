@@ -67,8 +67,10 @@ def random_edit(rnd, d, text, lst, mp, weights=(0.35, 0.15, 0.25, 0.10, 0.12, 0.
                 vals.append(None)
             elif k < 0.95:
                 vals.append(rnd.random() < 0.5)
-            else:
-                vals.append(float(rnd.randint(-1000, 1000)))
+            elif k < 0.98:
+                vals.append(rnd.choice([float(rnd.randint(-1000, 1000)), rnd.uniform(-1e3, 1e3), rnd.random() * 10.0 ** rnd.randint(-12, 25)]))
+            else:   # nested LoroValue::List / Map (keys index the block's key arena on the wire)
+                vals.append(rnd.choice([{"n%d" % rnd.randrange(3): rnd.randint(0, 9), "m": {"deep": [1, {"x": None}]}}, [1, [2.5, "s"], {}]]))
         d.list_insert(lst, rnd.randint(0, n), *vals)
     elif r < w[0] + w[1] + w[2] + w[3]:
         n = d.seq_len(lst)
@@ -76,7 +78,10 @@ def random_edit(rnd, d, text, lst, mp, weights=(0.35, 0.15, 0.25, 0.10, 0.12, 0.
             p = rnd.randrange(n)
             d.delete(lst, p, min(rnd.randint(1, 4), n - p))
     elif r < 1 - w[5]:
-        d.map_set(mp, "k%d" % rnd.randrange(16), rnd.randint(0, 999) if rnd.random() < 0.8 else "v%d" % rnd.randrange(9))
+        r2 = rnd.random()
+        v = rnd.randint(0, 999) if r2 < 0.75 else ("v%d" % rnd.randrange(9) if r2 < 0.9 else
+                                                   (rnd.uniform(-5, 5) if r2 < 0.95 else {"a": [rnd.randint(0, 3)], "k%d" % rnd.randrange(16): {"b": 0.5}}))
+        d.map_set(mp, "k%d" % rnd.randrange(16), v)
     else:
         d.map_delete(mp, "k%d" % rnd.randrange(16))
 
