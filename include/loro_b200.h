@@ -130,10 +130,13 @@ lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, siz
 /* LoroDoc::oplog_frontiers() (crates/loro/src/lib.rs:881; version/frontiers.rs:233-246): the heads of the causal graph,
  * one span [counter, counter + 1) per head id. */
 lb_status lb_doc_frontiers(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n);
-/* LoroDoc::export(ExportMode::all_updates()) of document `doc` (crates/loro/src/lib.rs:1235, encoding.rs:350-416):
- * the FastUpdates blob a fresh reference document would export after importing the same input.  Needs
- * LB_FLAG_EXPORT at import time.  `from` (a version vector) must be NULL / 0 for now: only all_updates.
- * LB_ERR_UNSUPPORTED: the document uses something the export phase does not cover yet (lb_last_error). */
+/* LoroDoc::export(ExportMode::updates(from)) of document `doc` (crates/loro/src/lib.rs:1235, encoding.rs:79-83, 350-416,
+ * oplog/change_store.rs:494-528): the FastUpdates blob a fresh reference document would export after importing the same
+ * input.  `from` = NULL / n_from = 0 is ExportMode::all_updates() (computed for every document at import time);
+ * otherwise `from` is a version vector (one span per peer, `end` = the first counter the receiver lacks; peers not
+ * listed start at 0) and the stored changes are cut there (Change::slice) -- computed on demand, the returned buffer
+ * stays valid until the next from-export of the same document or lb_batch_free.  Needs LB_FLAG_EXPORT at import time.
+ * LB_ERR_UNSUPPORTED: the document uses something the export phase does not cover (lb_last_error). */
 lb_status lb_doc_export_updates(const lb_batch* b, size_t doc, const lb_id_span* from, size_t n_from,
                                 const uint8_t** bytes, size_t* len);
 lb_status lb_batch_counters(const lb_batch* b, lb_counters* out);

@@ -83,7 +83,7 @@ def load_library(path=None):
     L.lb_doc_count.argtypes = [vp]
     L.lb_doc_status.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(_Status)]
     L.lb_doc_json.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t)]
-    L.lb_doc_export_updates.argtypes = [vp, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+    L.lb_doc_export_updates.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(_IdSpan), ctypes.c_size_t,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
     L.lb_doc_vv.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(_IdSpan)), ctypes.POINTER(ctypes.c_size_t)]
     L.lb_doc_frontiers.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(_IdSpan)), ctypes.POINTER(ctypes.c_size_t)]
@@ -147,11 +147,20 @@ class Batch:
         pen = {st.pending[k].peer: (st.pending[k].start, st.pending[k].end) for k in range(st.n_pending)}
         return ImportStatus(st.code, suc, pen or None)
 
-    def export_updates(self, i):
-        """LoroDoc::export(ExportMode::all_updates()) of document i (needs flags=LB_FLAG_EXPORT at import)."""
+    def export_updates(self, i, from_vv=None):
+        """LoroDoc::export(ExportMode::updates(from_vv)) of document i, all_updates when from_vv is None
+        (needs flags=LB_FLAG_EXPORT at import).  from_vv: {peer: first counter the receiver lacks}."""
         p = ctypes.c_void_p()
         n = ctypes.c_size_t()
-        _check(self._L, self._L.lb_doc_export_updates(self._h, i, None, 0, ctypes.byref(p), ctypes.byref(n)),
+        spans, k = None, 0
+        if from_vv:
+            k = len(from_vv)
+            spans = (_IdSpan * k)()
+            for j, (peer, ctr) in enumerate(from_vv.items()):
+                spans[j].peer = peer
+                spans[j].start = 0
+                spans[j].end = ctr
+        _check(self._L, self._L.lb_doc_export_updates(self._h, i, spans, k, ctypes.byref(p), ctypes.byref(n)),
                "lb_doc_export_updates")
         return ctypes.string_at(p.value, n.value)
 

@@ -155,6 +155,9 @@ struct lb_batch {
     XDoc* d_xdoc = nullptr;
     u64 export_total = 0;
     std::vector<XDoc> xdocs;
+    ExportTables xt{};            // phase-7 tables kept for export(updates(from)) on demand
+    bool have_xt = false;
+    std::unordered_map<size_t, std::vector<uint8_t>> from_exports;   // last on-demand export per document
     uint8_t* exported = nullptr;  // malloc'ed host copy (lbstage::download)
     bool export_fetched = false;
     u64 n_blocks = 0, n_changes = 0, n_rows = 0, n_peers_tot = 0, json_total = 0;
@@ -511,7 +514,8 @@ void pipeline(lb_batch* b) {
         xt.sg_ndel = dv.alloc<u32>(SEGCAP); xt.sg_nrows = dv.alloc<u32>(SEGCAP); xt.sg_last_head = dv.alloc<u32>(SEGCAP);
         xt.fc_src = dv.alloc<u32>(SEGCAP); xt.fc_pos = dv.alloc<u32>(SEGCAP); xt.fc_r0 = dv.alloc<u32>(SEGCAP);
         xt.fc_from = dv.alloc<u32>(SEGCAP); xt.fc_atoms = dv.alloc<u32>(SEGCAP); xt.fc_nrows = dv.alloc<u32>(SEGCAP);
-        xt.fc_ndel = dv.alloc<u32>(SEGCAP); xt.fc_block = dv.alloc<u8>(SEGCAP);
+        xt.fc_ndel = dv.alloc<u32>(SEGCAP); xt.fc_block = dv.alloc<u8>(SEGCAP); xt.fc_skip = dv.alloc<u32>(SEGCAP, true);
+        xt.only_doc = 0xFFFFFFFFu; xt.from_ctr = nullptr;
         LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
         if (NTR) { LB_LAUNCH(k_exp_posrank, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, xt); tm.kernel_launches += 1; }
         if (NCH) LB_LAUNCH(k_exp_arena, nblk(NCH, 64), 64, 0, st, NCH, xt, b->d_docs);
@@ -533,8 +537,8 @@ void pipeline(lb_batch* b) {
                 dv.release(*pp);
                 *pp = nw;
             }
-            u32** fcs[7] = {&xt.fc_src, &xt.fc_pos, &xt.fc_r0, &xt.fc_from, &xt.fc_atoms, &xt.fc_nrows, &xt.fc_ndel};
-            for (auto pp : fcs) { dv.release(*pp); *pp = dv.alloc<u32>(cap); }
+            u32** fcs[8] = {&xt.fc_src, &xt.fc_pos, &xt.fc_r0, &xt.fc_from, &xt.fc_atoms, &xt.fc_nrows, &xt.fc_ndel, &xt.fc_skip};
+            for (auto pp : fcs) { dv.release(*pp); *pp = dv.alloc<u32>(cap, true); }
             dv.release(xt.fc_block);
             xt.fc_block = dv.alloc<u8>(cap);
         }
@@ -560,6 +564,8 @@ void pipeline(lb_batch* b) {
         LB_LAUNCH(k_exp_finish, nblk(D), TPB, 0, st, b->d_docs, D, xt, b->d_export);
         tm.kernel_launches += 2;
         tm.export_bytes = XT;
+        b->xt = xt;
+        b->have_xt = true;
     }
     mark(b);  // [7] export done
     // ------------------------------------------------------------ results to host
@@ -703,6 +709,66 @@ void init_batch(lb_batch* b) {
     CK(cudaStreamCreate(&b->dev.stream));
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&b->ev[i]));
     b->ev_created = true;
+}
+
+// export(ExportMode::updates(from)) of one document (encoding.rs:79-83 ; change_store.rs:494-528 export_blocks_from):
+// the import store is rebuilt for that document only, its changes are cut at `from` (Change::slice) on their way into
+// the fresh export store, and the result is encoded like the import-time export.  The phase-7 tables of the batch are
+// reused; only the per-call pieces (cut positions, block list, scratch, output) are allocated.
+lb_status export_from(lb_batch* b, size_t doc, const lb_id_span* from, size_t n_from, std::vector<uint8_t>& out) {
+    try {
+        Dev& dv = b->dev;
+        cudaStream_t st = dv.stream;
+        const u32 D = (u32)b->n_docs;
+        const u64 NCH = b->n_changes;
+        const DocInfo& di = b->docs[doc];
+        ExportTables xt = b->xt;
+        std::vector<i32> h_from(b->n_peers_tot + 1, 0);
+        for (size_t k = 0; k < n_from; k++)
+            for (u32 p = 0; p < di.P; p++)
+                if (b->dpeer[di.peer0 + p].id == from[k].peer) h_from[di.peer0 + p] = from[k].end;
+        i32* d_from = dv.alloc<i32>(b->n_peers_tot + 1);
+        CK(cudaMemcpyAsync(d_from, h_from.data(), sizeof(i32) * (b->n_peers_tot + 1), cudaMemcpyHostToDevice, st));
+        xt.from_ctr = d_from;
+        xt.only_doc = (u32)doc;
+        XDoc* xdoc = dv.alloc<XDoc>(D + 1, true);
+        xt.xdoc = xdoc;
+        u32* tmp_a = dv.alloc<u32>(D + 1, true);
+        u32* tmp_b = dv.alloc<u32>(D + 1, true);
+        LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
+        if (NCH) {
+            LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
+            LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 1);
+        }
+        LB_LAUNCH(k_exp_store, nblk(D, 64), 64, 0, st, b->d_docs, D, xt);
+        LB_LAUNCH(k_exp_sizes, nblk(D), TPB, 0, st, b->d_docs, D, xt, tmp_a, tmp_b);
+        run_scans(b, {ScanJob{(const u8*)tmp_a, (u8*)xdoc + offsetof(XDoc, ob0), 4, sizeof(XDoc), D},
+                      ScanJob{(const u8*)tmp_b, (u8*)xdoc + offsetof(XDoc, scratch0), 4, sizeof(XDoc), D}});
+        XDoc xtot = d2h_one(b, xdoc + D);
+        u64 NOB = xtot.ob0, NSCR = xtot.scratch0;
+        XBlock* xb = dv.alloc<XBlock>(NOB + 1);
+        u32* xscratch = dv.alloc<u32>(NSCR + 1);
+        LB_LAUNCH(k_exp_list, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb);
+        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, (u8*)nullptr, 0);
+        LB_LAUNCH(k_exp_layout, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb, tmp_a);
+        run_scans(b, {ScanJob{(const u8*)tmp_a, (u8*)xdoc + offsetof(XDoc, exp_off), 4, sizeof(XDoc), D}});
+        u64 XT = d2h_one(b, &xdoc[D].exp_off);
+        u8* d_out = dv.alloc<u8>(XT + 16, true);
+        if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, d_out, 1);
+        LB_LAUNCH(k_exp_finish, nblk(D), TPB, 0, st, b->d_docs, D, xt, d_out);
+        XDoc x = d2h_one(b, xdoc + doc);
+        lb_status rc = LB_OK;
+        if ((x.flags & 1) || x.exp_len == 0) { g_last_error = "document uses features the export phase does not cover"; rc = LB_ERR_UNSUPPORTED; }
+        else {
+            out.resize(x.exp_len);
+            CK(cudaMemcpyAsync(out.data(), d_out + x.exp_off, x.exp_len, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        dv.release(d_from); dv.release(xdoc); dv.release(tmp_a); dv.release(tmp_b); dv.release(xb); dv.release(xscratch); dv.release(d_out);
+        return rc;
+    } catch (lb_status s) {
+        return s;
+    }
 }
 
 }  // namespace
@@ -906,8 +972,16 @@ lb_status lb_doc_export_updates(const lb_batch* cb, size_t doc, const lb_id_span
     lb_batch* b = const_cast<lb_batch*>(cb);
     if (!b || !bytes || !len || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
     if (!(b->flags & LB_FLAG_EXPORT)) { g_last_error = "batch was imported without LB_FLAG_EXPORT"; return LB_ERR_INVALID_ARG; }
-    if (from || n_from) { g_last_error = "only all_updates (from = NULL) is exported"; return LB_ERR_UNSUPPORTED; }
     if (b->docs[doc].code != DOC_OK) { g_last_error = "document failed to import"; return LB_ERR_INVALID_ARG; }
+    if (from && n_from) {   // export(ExportMode::updates(from)): computed on demand for this document
+        if (!b->have_xt) { g_last_error = "batch holds no export tables"; return LB_ERR_INVALID_ARG; }
+        std::vector<uint8_t>& buf = b->from_exports[doc];
+        lb_status rc = export_from(b, doc, from, n_from, buf);
+        if (rc != LB_OK) return rc;
+        *bytes = buf.data();
+        *len = buf.size();
+        return LB_OK;
+    }
     const XDoc& x = b->xdocs[doc];
     if ((x.flags & 1) || x.exp_len == 0) { g_last_error = "document uses features the export phase does not cover"; return LB_ERR_UNSUPPORTED; }
     if (!b->export_fetched) {

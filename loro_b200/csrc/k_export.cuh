@@ -93,6 +93,11 @@ struct ExportTables {
     u32* sg_src; u32* sg_r0; u32* sg_from; u32* sg_atoms; u32* sg_est; u32* sg_nmops; u32* sg_ndel; u32* sg_nrows; u32* sg_last_head;
     // final changes (same index space: a document never ends up with more changes than segments)
     u32* fc_src; u32* fc_pos; u32* fc_r0; u32* fc_from; u32* fc_atoms; u32* fc_nrows; u32* fc_ndel; u8* fc_block;
+    u32* fc_skip;      // atoms of the change's first row that lie before the `from` version (Op::slice)
+    // export(ExportMode::updates(from)) of ONE document on demand (lb_doc_export_updates): only_doc != ~0 restricts
+    // every kernel to that document; from_ctr[doc peer slot] = first counter to export (encoding.rs:79-83,
+    // change_store.rs:494-528 export_blocks_from, change.rs:203-258 Change::slice)
+    u32 only_doc; const i32* from_ctr;
     XDoc* xdoc;
 };
 
@@ -291,6 +296,41 @@ __device__ inline u32 text_byte_index(const u8* p, u32 nb, u32 n, u32 k) {
     }
     return i;
 }
+// payload of a row without its first `skip` atoms (list items / unicode scalar values)
+__device__ inline void xr_payload_skip(const ExportTables& t, u64 row, u32 xk, u32 skip, const u8** p, u32* n) {
+    xr_payload(t, row, xk, p, n);
+    if (!skip) return;
+    u32 off = 0;
+    if (xk == XK_TEXT) off = text_byte_index(*p, *n, xr_len(t, row), skip);
+    else if (xk == XK_LIST) {
+        Cur c(*p, *n);
+        for (u32 k = 0; k < skip && !c.err; k++) { u8 kk = c.get(); skip_loro_value_content(c, kk, nullptr); }
+        off = (u32)(c.p - *p);
+    }
+    *p += off;
+    *n -= off;
+}
+// Op::slice(skip, len) of the op made from `row` (op.rs:161-172, list_op.rs:603-658, 251-278, 436-444)
+__device__ inline void xop_slice_front(const ExportTables& t, XOp& o, u64 row, u32 skip) {
+    if (!skip) return;
+    switch (o.xk) {
+        case XK_LIST: o.prop += (i32)skip; o.f0 += skip; break;
+        case XK_TEXT: {
+            const u8* pp; u32 pn;
+            xr_payload(t, row, XK_TEXT, &pp, &pn);
+            o.prop += (i32)skip;
+            o.f0 += text_byte_index(pp, pn, o.atoms, skip);
+            break;
+        }
+        case XK_DEL:
+            if (o.f2 > 0) { o.f1 += skip; o.f2 -= (i32)skip; }
+            else { o.prop -= (i32)skip; o.f2 += (i32)skip; }
+            break;
+        default: return;   // one-atom ops are never cut
+    }
+    o.ctr += (i32)skip;
+    o.atoms -= skip;
+}
 
 // ---------------------------------------------------------------------------------------------- X1: arenas
 // The importing document allocates arena space while it decodes (block_encode.rs:619-657): the position of a row's
@@ -455,6 +495,7 @@ __device__ inline void segment_summaries(const ExportTables& t, const DocInfo& d
 __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
     u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_changes) return;
+    if (t.only_doc != 0xFFFFFFFFu && t.blocks[t.ch_block[ch]].doc != t.only_doc) return;
     if (!t.ch_applied[ch]) { if (!pass) { t.ch_nseg[ch] = 0; t.ch_syn[ch] = 0; } return; }
     u32 doc = t.blocks[t.ch_block[ch]].doc;
     const DocInfo& di = docs[doc];
@@ -548,6 +589,7 @@ struct XEntry {        // a change on its way through a store: one segment, or a
     u32 src, from;     // metadata of its first segment: source change + atom offset (deps, lamport, timestamp, message)
     u32 pos, r0;       // where its rows start: position in ch_order (absolute) + row inside that change
     u32 atoms, est_ops, nmops, ndel, nrows;
+    u32 skip;          // atoms of the first row already known to the importer of this export (from-version cut)
     u32 lh_ch, lh_row; // last op: source change + row (inside that change) of its first row ...
     XOp last;          // ... or, once the entry has been through a store, the accumulated op itself
     bool last_valid;
@@ -589,9 +631,10 @@ __device__ __forceinline__ u32 row_value_bytes(const ExportTables& t, const XOp&
     xr_payload(t, row, o.xk, &p, &n);
     return n;
 }
-__device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows& it, u32& left, u32* vbytes = nullptr) {
+__device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows& it, u32& left, u32* vbytes = nullptr, u32 skip = 0) {
     XOp o = xop_from_row(t, di, it.ch, it.row());
-    if (vbytes) *vbytes += row_value_bytes(t, o, it.row());
+    if (skip) xop_slice_front(t, o, it.row(), skip);
+    if (vbytes) { const u8* pp; u32 pn; xr_payload_skip(t, it.row(), o.xk, skip, &pp, &pn); *vbytes += pn; }
     left--;
     if (left) it.next();
     while (left && !(xr_flag(t, it.row()) & XF_HEAD)) {
@@ -628,16 +671,18 @@ __device__ inline bool xstore_push(const ExportTables& t, const DocInfo& di, XSt
         if (can && is_full && E.nmops == 1) {
             XRows it(t, E.pos, E.r0);
             u32 left = E.nrows;
-            single = xop_mergable(s.back, xop_gather(t, di, it, left));
+            single = xop_mergable(s.back, xop_gather(t, di, it, left, nullptr, E.skip));
         }
         if (can && (!is_full || single)) {
             // the ops of E are pushed onto the last change (RleVec::push): a prefix of them may merge into its last op
             XRows it(t, E.pos, E.r0);
             u32 left = E.nrows;
             u32 merged = 0, merged_sz = 0, merged_del = 0;
+            bool first_op = true;
             while (left) {
                 u64 head_row = it.row();
-                XOp o = xop_gather(t, di, it, left);
+                XOp o = xop_gather(t, di, it, left, nullptr, first_op ? E.skip : 0u);
+                first_op = false;
                 if (!xop_mergable(s.back, o)) break;
                 merged_sz += xop_estimate(o);
                 merged_del += o.xk == XK_DEL;
@@ -666,6 +711,50 @@ __device__ inline bool xstore_push(const ExportTables& t, const DocInfo& di, XSt
     return closed;
 }
 
+// Change::slice at the `from` version (change_store.rs:505-521, change.rs:203-258): entry E covers counters
+// [c0, c0 + atoms) of its peer; what lies before `start` is dropped.  false = nothing left.
+__device__ inline bool xentry_cut(const ExportTables& t, const DocInfo& di, XEntry& E, i32 start) {
+    i32 c0 = t.ch_counter[E.src] + (i32)E.from;
+    if (start <= c0) return true;
+    if (start >= c0 + (i32)E.atoms) return false;
+    u32 cut = (u32)(start - c0);
+    XRows it(t, E.pos, E.r0);
+    u32 left = E.nrows, acc = E.skip ? 0u : 0u;
+    while (left) {
+        u32 len = xr_len(t, it.row());
+        if (acc + len > cut) break;
+        acc += len;
+        left--;
+        if (left) it.next();
+    }
+    E.pos = it.pos;
+    E.r0 = it.r;
+    E.nrows = left;
+    E.skip = cut - acc;
+    E.from += cut;
+    E.atoms -= cut;
+    // fresh summary of what is left: size estimate, ops, deletes, last op
+    XRows it2(t, E.pos, E.r0);
+    u32 l = left, est = 0, nm = 0, nd = 0;
+    XOp last;
+    last.xk = XK_NONE;
+    bool first = true;
+    while (l) {
+        XOp o = xop_gather(t, di, it2, l, nullptr, first ? E.skip : 0u);
+        first = false;
+        est += xop_estimate(o);
+        nm++;
+        nd += o.xk == XK_DEL;
+        last = o;
+    }
+    E.est_ops = est;
+    E.nmops = nm;
+    E.ndel = nd;
+    E.last = last;
+    E.last_valid = true;
+    return true;
+}
+
 // thread per document
 __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -673,13 +762,14 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
     const DocInfo& di = docs[d];
     if (di.code != DOC_OK) return;
     XDoc x = t.xdoc[d];
+    if (t.only_doc != 0xFFFFFFFFu && d != t.only_doc) { x.n_fc = x.n_mb = 0; t.xdoc[d] = x; return; }
     if (x.flags & 1) { t.xdoc[d] = x; return; }
     u64 w = di.ch0 + t.ch_seg0[di.ch0];   // as many slots as the document has segments
     u64 w0 = w;
     u32 n_mb = 0;
     auto emit = [&](const XEntry& e, bool starts_block) {
         t.fc_src[w] = e.src; t.fc_pos[w] = e.pos; t.fc_r0[w] = e.r0; t.fc_from[w] = e.from; t.fc_atoms[w] = e.atoms;
-        t.fc_nrows[w] = e.nrows; t.fc_ndel[w] = e.ndel; t.fc_block[w] = starts_block ? 1 : 0;
+        t.fc_nrows[w] = e.nrows; t.fc_ndel[w] = e.ndel; t.fc_block[w] = starts_block ? 1 : 0; t.fc_skip[w] = e.skip;
         n_mb += starts_block;
         w++;
     };
@@ -688,6 +778,8 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
         while (p < di.P && t.dpeer[di.peer0 + p].rank != rank) p++;
         if (p == di.P) break;
         const DocPeer& dp = t.dpeer[di.peer0 + p];
+        const i32 start = t.from_ctr ? t.from_ctr[di.peer0 + p] : 0;
+        if (start >= dp.end_counter) continue;   // the importer of this export already has the whole peer
         XStore s1, s2;   // import store, export store
         s1.have_block = s1.open_valid = s1.open_starts_block = false; s1.blk_est = 0;
         s2 = s1;
@@ -702,11 +794,11 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
                 XEntry E;
                 E.src = ch; E.from = t.sg_from[sg]; E.pos = pos; E.r0 = t.sg_r0[sg]; E.atoms = t.sg_atoms[sg];
                 E.est_ops = t.sg_est[sg]; E.nmops = t.sg_nmops[sg]; E.ndel = t.sg_ndel[sg]; E.nrows = t.sg_nrows[sg];
-                E.lh_ch = ch; E.lh_row = t.sg_last_head[sg]; E.last_valid = false;
+                E.lh_ch = ch; E.lh_row = t.sg_last_head[sg]; E.last_valid = false; E.skip = 0;
                 if (xstore_push(t, di, s1, E, done, done_blk)) {
                     XEntry d2;
                     bool d2_blk = false;
-                    if (xstore_push(t, di, s2, done, d2, d2_blk)) emit(d2, d2_blk);
+                    if ((start <= 0 || xentry_cut(t, di, done, start)) && xstore_push(t, di, s2, done, d2, d2_blk)) emit(d2, d2_blk);
                 }
             }
         }
@@ -715,7 +807,7 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
             bool d2_blk = false;
             s1.open.last = s1.back;
             s1.open.last_valid = true;
-            if (xstore_push(t, di, s2, s1.open, d2, d2_blk)) emit(d2, d2_blk);
+            if ((start <= 0 || xentry_cut(t, di, s1.open, start)) && xstore_push(t, di, s2, s1.open, d2, d2_blk)) emit(d2, d2_blk);
         }
         if (s2.open_valid) emit(s2.open, s2.open_starts_block);
     }
@@ -1085,11 +1177,14 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         for (u32 j = 0; j < N; j++) {
             XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
             u32 left = t.fc_nrows[fc0 + j];
+            u32 skip = t.fc_skip[fc0 + j];   // only the first op of a change cut at the `from` version
             while (left) {
                 u32 first_row = (u32)it.row();
                 XRows it0 = it;
                 const u32 left0 = left;
-                XOp o = xop_gather(t, di, it, left, has_maps ? nullptr : &vbytes);
+                const u32 skip0 = skip;
+                XOp o = xop_gather(t, di, it, left, has_maps ? nullptr : &vbytes, skip);
+                skip = 0;
                 if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
                 else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
                 // DeltaRle columns are stored as deltas right away (the encoders then read every value once)
@@ -1100,7 +1195,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                     while (k) {
                         const u8* pp;
                         u32 pn;
-                        xr_payload(t, it0.row(), o.xk, &pp, &pn);
+                        xr_payload_skip(t, it0.row(), o.xk, k == left0 - left ? skip0 : 0u, &pp, &pn);
                         if (o.xk == XK_LIST || o.xk == XK_MAPSET) {
                             XSink cs;
                             cs.dst = nullptr; cs.n = 0;
@@ -1228,6 +1323,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         for (u32 j = 0; j < N; j++) {
             XRows it(t, t.fc_pos[fc0 + j], t.fc_r0[fc0 + j]);
             u32 left = t.fc_nrows[fc0 + j];
+            u32 skip = t.fc_skip[fc0 + j];
             bool fresh = true;
             while (left) {
                 u64 row = it.row();
@@ -1242,10 +1338,11 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                 if (xk == XK_LIST || xk == XK_TEXT || xk == XK_MAPSET) {
                     const u8* pp;
                     u32 pn;
-                    xr_payload(t, row, xk, &pp, &pn);
+                    xr_payload_skip(t, row, xk, skip, &pp, &pn);
                     if (has_maps && xk != XK_TEXT) xvalue_copy(s, pp, pn, t, t.blocks[t.ch_block[it.ch]].key0, keys, false);
                     else s.copy(pp, pn);
                 }
+                skip = 0;
                 left--;
                 if (left) it.next();
             }

@@ -26,3 +26,29 @@ def check_export_against_oracle(blobs, lib_path=None, reimport=True):
             assert again.oplog_vv(i) == batch.oplog_vv(i), i
             assert again.export_updates(i) == outs[i], i
     return batch
+
+
+def check_export_from_versions(blob, lib_path=None, seed=0, trials=6):
+    """export(ExportMode::updates(from)) for random `from` version vectors: bytes equal to the oracle's export of a
+    document that imported the same blob; importing them into a replica at `from` yields the full state."""
+    import random
+    import loro_b200
+    from loro_b200 import api
+    rnd = random.Random(seed)
+    ref = OracleDoc(0xABCDEF)
+    ref.import_(blob)
+    vv = ref.oplog_vv()
+    batch = loro_b200.import_batch([blob], flags=api.LB_FLAG_EXPORT, lib_path=lib_path)
+    for trial in range(trials):
+        frm = {p: rnd.randint(0, c) for p, c in vv.items() if rnd.random() < 0.8}
+        if trial == 0:
+            frm = dict(vv)                      # nothing to send: header-only blob
+        elif trial == 1:
+            frm = {p: 1 for p in vv}            # cut inside every peer's first op
+        want = ref.export_updates(frm)
+        got = batch.export_updates(0, frm)
+        if got != want:
+            k = next((j for j in range(min(len(got), len(want))) if got[j] != want[j]), min(len(got), len(want)))
+            raise AssertionError(f"export from {frm}: differs from the oracle at byte {k} (lens {len(got)} / {len(want)})")
+    assert batch.export_updates(0) == ref.export_updates()   # the import-time all_updates export is untouched
+    return batch

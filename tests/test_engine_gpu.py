@@ -316,3 +316,41 @@ def test_config_c5_full_size_documents():
     b = check_batch_against_oracle(blobs, expect_json=want)
     assert b.counters()["atom_ops"] == 12 * 8000
     check_export_against_oracle(blobs[:4])
+
+
+def test_export_from_version_vector_and_c1_end_to_end():
+    """lb_doc_export_updates(from): export(ExportMode::updates(vv)) on the CUDA path, byte-equal to the oracle; config C1
+    (A exports updates(vv_B), B imports) driven by the engine."""
+    import random
+    import loro_b200
+    from loro_b200 import api
+    from tests.export_checks import check_export_from_versions
+    for seed in range(4):
+        check_export_from_versions(workloads.make_doc_history(7100 + seed, n_sites=2 + seed % 3, n_ops=300)[0], seed=seed)
+    check_export_from_versions(workloads.make_tree_history(41, n_sites=3, n_base=40, n_ops=150, mixed=True)[0], seed=9)
+    rnd = random.Random(3)
+    a, b = OracleDoc(1), OracleDoc(2)
+    la, lb = a.get_list("list"), b.get_list("list")
+    for k in range(1000):
+        a.list_insert(la, rnd.randint(0, a.seq_len(la)), rnd.randint(-10**6, 10**6))
+        b.list_insert(lb, rnd.randint(0, b.seq_len(lb)), rnd.randint(-10**6, 10**6))
+        if k % 10 == 9:
+            a.commit(); b.commit()
+    workloads.merge(a, b)
+    batch = loro_b200.import_batch([a.export_updates()], flags=api.LB_FLAG_EXPORT)
+    update_for_b = batch.export_updates(0, b.oplog_vv())
+    assert update_for_b == a.export_updates(b.oplog_vv())
+    b.import_(update_for_b)
+    assert b.json_text() == a.json_text() == batch.json_bytes(0)
+
+
+def test_nested_values_and_floats():
+    from tests.export_checks import check_export_against_oracle
+    a = OracleDoc(1)
+    l, m = a.get_list("l"), a.get_map("m")
+    a.list_insert(l, 0, {"b": 1, "a": [1, 2, {"z": None, "y": 2.5}]}, [1, [2, [3]]], 7, 0.1, -1e-7, 1e21, 5e-324)
+    a.map_set(m, "k", {"x": {"y": {"z": "deep"}}, "w": [True, False], "aa": {}})
+    a.map_set(m, "f", 3.14159)
+    blob = a.export_updates()
+    check_batch_against_oracle([blob])
+    check_export_against_oracle([blob])

@@ -141,3 +141,45 @@ def test_export_with_pending_changes_and_after_import_batch():
         g = loro_b200.import_batch(parts, doc_ids=[1] * len(parts), flags=api.LB_FLAG_EXPORT, lib_path=EMU)
         assert g.json_bytes(0) == ref.json_text()
         assert g.export_updates(0) == ref.export_updates(), seed
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_export_from_version_vector(seed):
+    """lb_doc_export_updates(from): Change::slice / Op::slice at arbitrary cut points (text incl. multi-byte UTF-8, list
+    items, delete spans in both directions, nested values, child containers)."""
+    from tests.export_checks import check_export_from_versions
+    blob = workloads.make_doc_history(7000 + seed, n_sites=2 + seed, n_ops=220)[0]
+    check_export_from_versions(blob, lib_path=EMU, seed=seed)
+
+
+def test_c1_driven_by_the_engine():
+    """BASELINE config C1 end to end: A and B each insert into a List; A's side of the sync -- export(updates(vv_B)) --
+    comes out of the engine byte-identical to the reference path's, and B converges after importing it."""
+    import random
+    import loro_b200
+    from loro_b200 import api
+    rnd = random.Random(3)
+    a, b = OracleDoc(1), OracleDoc(2)
+    la, lb = a.get_list("list"), b.get_list("list")
+    for k in range(150):
+        a.list_insert(la, rnd.randint(0, a.seq_len(la)), rnd.randint(-10**6, 10**6))
+        b.list_insert(lb, rnd.randint(0, b.seq_len(lb)), rnd.randint(-10**6, 10**6))
+        if k % 10 == 9:
+            a.commit(); b.commit()
+    workloads.merge(a, b)                                  # A now holds both histories
+    batch = loro_b200.import_batch([a.export_updates()], flags=api.LB_FLAG_EXPORT, lib_path=EMU)
+    update_for_b = batch.export_updates(0, b.oplog_vv())
+    assert update_for_b == a.export_updates(b.oplog_vv())
+    b.import_(update_for_b)
+    assert b.json_text() == a.json_text() == batch.json_bytes(0)
+
+
+def test_export_from_cut_inside_pasted_inserts_and_trees():
+    from tests.export_checks import check_export_from_versions
+    big = OracleDoc(9)
+    big.text_insert(big.get_text("t"), 0, "wé " * 2500)           # one insert, several blocks
+    big.list_insert(big.get_list("l"), 0, *list(range(1500)))
+    big.commit()
+    big.text_insert(big.get_text("t"), 10, "tail")
+    check_export_from_versions(big.export_updates(), lib_path=EMU, seed=1)
+    check_export_from_versions(workloads.make_tree_history(31, n_sites=3, n_base=25, n_ops=90, mixed=True)[0], lib_path=EMU, seed=2)
