@@ -34,9 +34,13 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C5"],
+    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"],
                     help="BASELINE.json config: C3 = 100k docs x 10k mixed List/Map ops, 3 peers (the config the metric is quoted on); "
-                         "C2 = automerge-paper text trace x 4096 docs; C5 = 10k docs x 5k-node movable trees with 3 x 1k concurrent moves")
+                         "C2 = automerge-paper text trace x 4096 docs; C4 = ONE rich-text doc, 1M chars + 64 peers x 50k concurrent edits "
+                         "(does not shard: every GPU runs a replica); C5 = 10k docs x 5k-node movable trees with 3 x 1k concurrent moves")
+    ap.add_argument("--c4-base", type=int, default=1000000)
+    ap.add_argument("--c4-peers", type=int, default=64)
+    ap.add_argument("--c4-edits", type=int, default=50000)
     ap.add_argument("--docs", type=int, default=0, help="documents per GPU (0 = the config's figure: C3 100k, C2 4096, C5 10k)")
     ap.add_argument("--ops-per-doc", type=int, default=10000)
     ap.add_argument("--peers", type=int, default=3)
@@ -120,7 +124,7 @@ class ClockSampler:
 
 def default_docs(args, world):
     """Documents per GPU: BASELINE's figure for the config at every N, so that per-GPU work is fixed (weak scaling)."""
-    return args.docs or {"C3": 100000, "C2": 4096, "C5": 10000}[args.config]
+    return args.docs or {"C3": 100000, "C2": 4096, "C4": 1, "C5": 10000}[args.config]
 
 
 class TraceBatch:
@@ -149,6 +153,9 @@ def workload_text(args, n_docs, extra=""):
     if args.config == "C2":
         return (f"C2: automerge-paper text trace (259,778 patches -> one FastUpdates blob of 1 peer) replicated x {n_docs} docs/GPU, "
                 f"each copy with its own bytes in HBM (SURVEY.md 8d){extra}")
+    if args.config == "C4":
+        return (f"C4: {n_docs} rich-text document(s)/GPU (replicas: a single document does not shard), {args.c4_base} ASCII chars by peer 0 + "
+                f"{args.c4_peers} peers x {args.c4_edits} concurrent edits (70 % insert 1-8 chars, 30 % delete 1-8), never synced (SURVEY.md 8d){extra}")
     if args.config == "C5":
         return (f"C5: {n_docs} docs/GPU x movable tree of {args.tree_nodes} nodes (fan-out <= 8) built by peer 0 + {args.peers} peers x "
                 f"{args.tree_moves} concurrent moves (random target / parent, cycles across peers included), one FastUpdates blob per doc (SURVEY.md 8d){extra}")
@@ -160,7 +167,7 @@ def affordable_distinct(args, world, n_docs):
     """How many DISTINCT documents this rank's share of the host cores can generate in about 90 s
     (~1.2 M generated atom ops/s/core); the batch is filled by cycling through them (every copy has its own bytes
     in HBM; `distinct_docs_per_gpu` in the config says how many there are)."""
-    if args.config == "C2":
+    if args.config in ("C2", "C4"):
         return 1
     if args.distinct:
         return min(args.distinct, n_docs)
@@ -171,12 +178,14 @@ def affordable_distinct(args, world, n_docs):
 
 
 def make_workload(args, rank, world, n_docs):
-    from loro_b200.workload import C3Batch, C5Batch
+    from loro_b200.workload import C3Batch, C4Doc, C5Batch
     distinct = affordable_distinct(args, world, n_docs)
     threads = max(1, (host_cores() or 1) // max(1, world))
     t0 = time.time()
     if args.config == "C2":
         gen = TraceBatch()
+    elif args.config == "C4":
+        gen = C4Doc(args.c4_base, args.c4_peers, args.c4_edits, seed=rank)
     elif args.config == "C5":
         gen = C5Batch(distinct, n_nodes=args.tree_nodes, n_peers=args.peers, n_moves=args.tree_moves, first_doc=rank * n_docs, threads=threads)
     else:
@@ -192,6 +201,15 @@ def cpu_baseline(args, gen, threads=None):
     n = args.cpu_sample_docs or min(gen.n_docs, max(64, min(4096, threads * 48)))
     if args.config == "C2":
         n = args.cpu_sample_docs or max(1, min(threads, 16))    # one trace import is ~0.26 M ops: a few copies suffice
+    if args.config == "C4":
+        # the full document takes the restated CPU path far longer than the bench may run: a reduced instance of the
+        # same generator (100 k base chars, 16 peers x 3000 edits) on one core -- a single document has one task
+        from loro_b200.workload import C4Doc
+        gen = C4Doc(min(args.c4_base, 100000), min(args.c4_peers, 16), min(args.c4_edits, 3000), seed=0)
+        n, threads = 1, 1
+        reduced = f" -- REDUCED instance ({gen.config['base_chars']} base chars, {gen.config['n_peers']} peers x {gen.config['edits']} edits)"
+    else:
+        reduced = ""
     # oracle.bench_import wants contiguous [off[i], off[i+1]) blobs: re-pack exact lengths
     blobs = [gen.blob(i % gen.n_docs) for i in range(n)]
     buf = b"".join(blobs)
@@ -201,7 +219,7 @@ def cpu_baseline(args, gen, threads=None):
     r = oracle.bench_import(np.frombuffer(buf, dtype=np.uint8), o, threads=threads, want_json=True,
                             want_export=not args.no_export)
     return {"value": r["ops"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port", "ops": r["ops"],
-            "sample": f"{n} docs of the same {args.config} workload ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON{"" if args.no_export else " + export(all_updates)"} per doc, one doc per task; "
+            "sample": f"{n} docs of the same {args.config} workload{reduced} ({r['ops']} atom ops, {r['seconds']:.2f} s), import + deep JSON{"" if args.no_export else " + export(all_updates)"} per doc, one doc per task; "
                       "the CPU arm is the C++ restatement of the reference algorithm (oracle/), not the Rust reference (no cargo in the image)"}
 
 
@@ -216,6 +234,8 @@ def run_reference(args):
     n = args.cpu_sample_docs or max(64, min(4096, threads * 48))
     if args.config == "C5":
         n = args.cpu_sample_docs or max(64, min(1024, threads * 24))
+    if args.config == "C4":
+        n = 1
     ns = argparse.Namespace(**vars(args))
     ns.distinct = 0
     gen, _, _ = make_workload(ns, 0, 1, n)
@@ -233,7 +253,7 @@ def run_reference(args):
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": workload_text(args, n, " -- bounded sample of the ours-arm workload")},
-            "cpu_baseline": {"value": total_ops_per_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+            "cpu_baseline": {"value": total_ops_per_s, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": total_ops_per_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

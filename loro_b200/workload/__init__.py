@@ -23,6 +23,8 @@ def _load():
         L.lw_generate_c3.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64] + [ctypes.c_int] * 7
         L.lw_generate_c5.restype = ctypes.c_void_p
         L.lw_generate_c5.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64] + [ctypes.c_int] * 7
+        L.lw_generate_c4.restype = ctypes.c_void_p
+        L.lw_generate_c4.argtypes = [ctypes.c_uint64] + [ctypes.c_int] * 4
         L.lw_bytes.restype = ctypes.c_void_p
         L.lw_bytes.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
         L.lw_offsets.restype = ctypes.c_void_p
@@ -78,6 +80,17 @@ class _Batch:
             self.close()
         except Exception:
             pass
+
+
+class C4Doc(_Batch):
+    """Config C4: ONE Text document -- peer 0 inserts `base_chars` ASCII characters, then `n_peers` peers
+    each make `edits` edits (70 % insert of 1-8 characters, 30 % delete of 1-8) on their own copy of that base without
+    ever syncing; the blob holds all branches (what export(all_updates) of a replica that received everything yields)."""
+
+    def __init__(self, base_chars=1000000, n_peers=64, edits=50000, txn_ops=10, seed=0):
+        h = _load().lw_generate_c4(seed, base_chars, n_peers, edits, txn_ops)
+        self._adopt(h, 1, False)
+        self.config = dict(base_chars=base_chars, n_peers=n_peers, edits=edits, txn_ops=txn_ops, seed=seed)
 
 
 class C5Batch(_Batch):

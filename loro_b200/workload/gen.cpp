@@ -159,7 +159,7 @@ u32 xxh32(const u8* d, size_t len, u32 seed) {
 // ------------------------------------------------------------------ ops / changes
 struct Id { int peer; i32 ctr; bool operator==(const Id& o) const { return peer == o.peer && ctr == o.ctr; } };
 const Id NO_ID{-1, -1};
-enum Kind : u8 { K_LIST_INS, K_LIST_DEL, K_MAP_SET, K_MAP_DEL, K_TREE };
+enum Kind : u8 { K_LIST_INS, K_LIST_DEL, K_MAP_SET, K_MAP_DEL, K_TREE, K_TEXT_INS, K_TEXT_DEL };
 struct Val { bool is_str; i64 i; char s[9]; u8 slen; };
 // values of a list insert: the first value inline (runs are rare with random positions), the rest on the heap
 struct Vals {
@@ -178,8 +178,13 @@ struct Op {
     u8 key; Val mapval;        // map ops
     Id target, parent;         // tree ops: parent.peer -1 = root, -2 = DELETED_TREE_ROOT
     std::string position;      // fractional index bytes
+    std::string text;          // text insert (ASCII here: unicode length == bytes)
+    u32 arena_gen = 0;         // string arena buffer generation (append-only buffer, capacity doubling from 32)
     u64 arena_start = 0, arena_end = 0;
-    int atoms() const { return kind == K_LIST_INS ? (int)vals.size() : kind == K_LIST_DEL ? (del_len < 0 ? -del_len : del_len) : 1; }
+    int atoms() const {
+        return kind == K_LIST_INS ? (int)vals.size() : (kind == K_LIST_DEL || kind == K_TEXT_DEL) ? (del_len < 0 ? -del_len : del_len)
+               : kind == K_TEXT_INS ? (int)text.size() : 1;
+    }
 };
 struct Change {
     int peer; i32 ctr; u32 lamport; std::vector<Id> deps; std::vector<Op> ops;
@@ -211,20 +216,24 @@ void del_merge(Op& a, const Op& b) {
 bool op_mergable(const Op& a, const Op& b) {
     if (a.kind != b.kind || a.ctr + a.atoms() != b.ctr) return false;
     if (a.kind == K_LIST_INS) return a.pos + (i32)a.vals.size() == b.pos && a.arena_end == b.arena_start;
-    if (a.kind == K_LIST_DEL) return del_mergable(a, b);
+    if (a.kind == K_TEXT_INS) return a.pos + (i32)a.text.size() == b.pos && a.arena_end == b.arena_start && a.arena_gen == b.arena_gen;
+    if (a.kind == K_LIST_DEL || a.kind == K_TEXT_DEL) return del_mergable(a, b);
     return false;
 }
 bool rle_push(std::vector<Op>& ops, const Op& op) {
     if (!ops.empty() && op_mergable(ops.back(), op)) {
         Op& a = ops.back();
         if (a.kind == K_LIST_INS) { a.vals.append(op.vals); a.arena_end = op.arena_end; }
+        else if (a.kind == K_TEXT_INS) { a.text += op.text; a.arena_end = op.arena_end; }
         else del_merge(a, op);
         return true;
     }
     ops.push_back(op);
     return false;
 }
-size_t op_estimate(const Op& o) { return o.kind == K_LIST_INS ? 4 * o.vals.size() : (o.kind == K_LIST_DEL || o.kind == K_TREE) ? 8 : 3; }
+size_t op_estimate(const Op& o) {
+    return o.kind == K_LIST_INS ? 4 * o.vals.size() : o.kind == K_TEXT_INS ? o.text.size() : (o.kind == K_LIST_DEL || o.kind == K_TREE || o.kind == K_TEXT_DEL) ? 8 : 3;
+}
 size_t change_estimate(const Change& c) {
     size_t s = 4 + (std::max<size_t>(c.deps.size(), 1) - 1) * 4;
     for (auto& o : c.ops) s += op_estimate(o);
@@ -550,11 +559,11 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
     W vw;
     for (auto& c : blk)
         for (auto& op : c.ops) {
-            int cid = op.kind == K_TREE ? 2 : (op.kind == K_LIST_INS || op.kind == K_LIST_DEL) ? 0 : 1;
+            int cid = op.kind == K_TREE ? 2 : (op.kind == K_TEXT_INS || op.kind == K_TEXT_DEL) ? 3 : (op.kind == K_LIST_INS || op.kind == K_LIST_DEL) ? 0 : 1;
             size_t ci = cids.reg(cid);
             i64 prop = op.kind == K_TREE ? 0 : op.pos;
             u64 vt;
-            if (cid == 1) {
+            if (cid == 1) {   // map ops: the key
                 char kb[8];
                 int n = snprintf(kb, sizeof kb, "k%d", (int)op.key);
                 prop = (i64)keys.reg(std::string(kb, n));
@@ -564,7 +573,10 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
                     vt = 11; vw.u8_(7); vw.varint(op.vals.size());
                     for (size_t q = 0; q < op.vals.size(); q++) write_val(vw, op.vals[q]);
                     break;
-                case K_LIST_DEL:
+                case K_TEXT_INS:
+                    vt = 5; vw.varint(op.text.size()); vw.bytes((const u8*)op.text.data(), op.text.size());
+                    break;
+                case K_LIST_DEL: case K_TEXT_DEL:
                     vt = 9;
                     d_peer.push_back((i64)peers.reg(peer_ids[op.del_start.peer]));
                     d_ctr.push_back(op.del_start.ctr);
@@ -598,8 +610,8 @@ std::vector<u8> encode_block(const std::vector<Change>& blk, const std::vector<u
     W cw;
     cw.varint(cids.v.size());
     for (int cid : cids.v) {
-        cw.varint(4); cw.u8_(1); cw.u8_(cid == 0 ? 1 : cid == 1 ? 0 : 3); cw.varint(0);
-        cw.zig((i64)keys.reg(cid == 0 ? "list" : cid == 1 ? "map" : "tree"));
+        cw.varint(4); cw.u8_(1); cw.u8_(cid == 0 ? 1 : cid == 1 ? 0 : cid == 2 ? 3 : 2); cw.varint(0);
+        cw.zig((i64)keys.reg(cid == 0 ? "list" : cid == 1 ? "map" : cid == 2 ? "tree" : "text"));
     }
     W kw;
     for (auto& k : keys.v) { kw.varint(k.size()); kw.bytes((const u8*)k.data(), k.size()); }
@@ -974,6 +986,188 @@ DocOut gen_c5(u64 seed, int n_nodes, int n_peers, int n_moves, int max_fanout, i
     return out;
 }
 
+// ------------------------------------------------------------------ config C4: one rich-text document, many peers
+// A replica's view of the text: the visible characters as runs of consecutive ids, in blocks (positions are looked
+// up by scanning block totals).  Peers never sync in this config, so a replica holds the base plus its own edits and
+// deleted characters simply leave the view.
+struct TRun { int peer; i32 ctr; i32 len; };
+struct TextView {
+    std::vector<std::vector<TRun>> blocks;
+    std::vector<i32> tot;
+    i32 total = 0;
+    void init(int peer, i32 len) { blocks.assign(1, {TRun{peer, 0, len}}); tot.assign(1, len); total = len; }
+    void rebalance(size_t b) {
+        if (blocks[b].size() <= 128) return;
+        size_t half = blocks[b].size() / 2;
+        std::vector<TRun> hi(blocks[b].begin() + (long)half, blocks[b].end());
+        blocks[b].resize(half);
+        i32 t = 0;
+        for (auto& r : hi) t += r.len;
+        blocks.insert(blocks.begin() + (long)b + 1, std::move(hi));
+        tot.insert(tot.begin() + (long)b + 1, t);
+        tot[b] -= t;
+    }
+    // (block, run, offset) of visible position pos (the run that contains character pos; end = past the last run)
+    void locate(i32 pos, size_t* b, size_t* r, i32* off) const {
+        size_t bi = 0;
+        while (bi + 1 < blocks.size() && pos >= tot[bi]) { pos -= tot[bi]; bi++; }
+        size_t ri = 0;
+        while (ri < blocks[bi].size() && pos >= blocks[bi][ri].len) { pos -= blocks[bi][ri].len; ri++; }
+        *b = bi; *r = ri; *off = pos;
+    }
+    void insert(i32 pos, TRun nw) {
+        size_t b, r; i32 off;
+        locate(pos, &b, &r, &off);
+        auto& v = blocks[b];
+        if (r < v.size() && off > 0) {   // split the run under the cursor
+            TRun tail{v[r].peer, v[r].ctr + off, v[r].len - off};
+            v[r].len = off;
+            v.insert(v.begin() + (long)r + 1, tail);
+            r++;
+        }
+        v.insert(v.begin() + (long)r, nw);
+        tot[b] += nw.len;
+        total += nw.len;
+        rebalance(b);
+    }
+    // remove [pos, pos + len): the id spans that disappear, left to right
+    void erase(i32 pos, i32 len, std::vector<TRun>* gone) {
+        while (len > 0) {
+            size_t b, r; i32 off;
+            locate(pos, &b, &r, &off);
+            auto& v = blocks[b];
+            TRun& x = v[r];
+            i32 take = std::min(len, x.len - off);
+            gone->push_back(TRun{x.peer, x.ctr + off, take});
+            if (off == 0 && take == x.len) v.erase(v.begin() + (long)r);
+            else if (off == 0) { x.ctr += take; x.len -= take; }
+            else if (off + take == x.len) x.len = off;
+            else {
+                TRun tail{x.peer, x.ctr + off + take, x.len - off - take};
+                x.len = off;
+                v.insert(v.begin() + (long)r + 1, tail);
+            }
+            tot[b] -= take;
+            total -= take;
+            len -= take;
+            if (v.empty() && blocks.size() > 1) { blocks.erase(blocks.begin() + (long)b); tot.erase(tot.begin() + (long)b); }
+        }
+    }
+};
+
+// peer 0 inserts `base_chars` ASCII characters (one op), then `n_peers` other peers each make
+// `edits` edits on their own copy of that base (70 % insert of 1-8 characters, 30 % delete of 1-8), never syncing:
+// one document whose merge has n_peers fully concurrent branches.  Deletes are emitted the way the text handler does
+// (handler.rs:1897-1957): one op per run of consecutive ids, rightmost first.
+DocOut gen_c4(u64 seed, int base_chars, int n_peers, int edits, int txn_ops) {
+    const int np = n_peers + 1;
+    DocGen g(np, seed);
+    {   // the base, one change of one op
+        Replica& r0 = *g.reps[0];
+        g.begin(r0);
+        Op op{};
+        op.kind = K_TEXT_INS;
+        op.ctr = 0;
+        op.pos = 0;
+        op.text.resize((size_t)base_chars);
+        for (int i = 0; i < base_chars; i++) op.text[(size_t)i] = "abcdefghijklmnopqrstuvwxyz     .,\n"[g.rng.below(35)];
+        op.arena_start = 0;
+        op.arena_end = (u64)base_chars;
+        r0.txn.ops.push_back(op);
+        g.commit(r0);
+    }
+    std::vector<std::thread> ts;
+    std::vector<std::vector<Change>> logs((size_t)np);
+    std::atomic<int> next(1);
+    const std::vector<Id> base_frontier = g.reps[0]->frontiers;
+    const u32 base_lamport_end = (u32)base_chars;
+    auto work = [&]() {
+        while (true) {
+            int p = next.fetch_add(1);
+            if (p >= np) break;
+            Rng rng(seed * 1000003ull + (u64)p);
+            TextView view;
+            view.init(0, base_chars);
+            std::vector<Change>& log = logs[(size_t)p];
+            Change txn;
+            bool open = false;
+            i32 ctr = 0;
+            u32 lamport = base_lamport_end;   // every change of this peer follows the base (and its own predecessor)
+            u64 arena = 0, cap = 0;
+            u32 gen = 0;
+            int since = 0;
+            auto begin = [&]() {
+                if (open) return;
+                txn = Change();
+                txn.peer = p;
+                txn.ctr = ctr;
+                txn.lamport = lamport;
+                if (ctr == 0) txn.deps = base_frontier; else txn.deps = {Id{p, ctr - 1}};
+                open = true;
+            };
+            auto commit = [&]() {
+                if (!open) return;
+                open = false;
+                if (txn.ops.empty()) return;
+                lamport += (u32)txn.atoms();
+                log.push_back(std::move(txn));
+            };
+            for (int e = 0; e < edits; e++) {
+                begin();
+                if (rng.unit() < 0.7 || view.total < 8) {
+                    int len = 1 + (int)rng.below(8);
+                    Op op{};
+                    op.kind = K_TEXT_INS;
+                    op.ctr = ctr;
+                    op.pos = (i32)rng.below((u32)view.total + 1);
+                    op.text.resize((size_t)len);
+                    for (int i = 0; i < len; i++) op.text[(size_t)i] = "ABCDEFGHIJKLMNOPQRSTUVWXYZ"[rng.below(26)];
+                    // local string arena: contiguous allocations, the buffer doubles from 32 (same model as the checker)
+                    op.arena_start = arena;
+                    if (arena + (u64)len > cap) { u64 nc = std::max<u64>(cap * 2, 32); while (nc < arena + (u64)len) nc *= 2; cap = nc; gen++; }
+                    arena += (u64)len;
+                    op.arena_end = arena;
+                    op.arena_gen = gen;
+                    view.insert(op.pos, TRun{p, ctr, len});
+                    ctr += len;
+                    rle_push(txn.ops, op);
+                } else {
+                    int len = 1 + (int)rng.below(8);
+                    i32 pos = (i32)rng.below((u32)(view.total - len + 1));
+                    std::vector<TRun> gone;
+                    view.erase(pos, len, &gone);
+                    i32 end = pos + len;
+                    for (size_t k = gone.size(); k-- > 0;) {   // rightmost run first
+                        Op op{};
+                        op.kind = K_TEXT_DEL;
+                        op.ctr = ctr;
+                        op.pos = end - gone[k].len;
+                        op.del_start = Id{gone[k].peer, gone[k].ctr};
+                        op.del_len = gone[k].len;
+                        end -= gone[k].len;
+                        ctr += gone[k].len;
+                        rle_push(txn.ops, op);
+                    }
+                }
+                if (++since >= txn_ops) { commit(); since = 0; }
+            }
+            commit();
+        }
+    };
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    for (unsigned t = 1; t < hw && t < (unsigned)np; t++) ts.emplace_back(work);
+    work();
+    for (auto& t : ts) t.join();
+    DocOut out;
+    out.atoms = (u64)base_chars;
+    for (int p = 1; p < np; p++) {
+        for (auto& c : logs[(size_t)p]) out.atoms += (u64)c.atoms();
+        g.log[(size_t)p] = std::move(logs[(size_t)p]);
+    }
+    out.blob = export_all(g);
+    return out;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1038,6 +1232,17 @@ lw_batch* lw_generate_c5(u64 seed_base, u64 first_doc, u64 n_docs, int n_nodes, 
         memcpy(b->bytes.data() + b->offs[i], docs[i].blob.data(), docs[i].blob.size());
         if (want_json) b->json.push_back(std::move(docs[i].json));
     }
+    return b;
+}
+// Config C4: ONE document (seed picks it).
+lw_batch* lw_generate_c4(u64 seed, int base_chars, int n_peers, int edits, int txn_ops) {
+    DocOut d = gen_c4(seed, base_chars, n_peers, edits, txn_ops);
+    lw_batch* b = new lw_batch();
+    b->offs.push_back(0);
+    b->lens.push_back((u32)d.blob.size());
+    b->atoms = d.atoms;
+    b->bytes.assign(((d.blob.size() + 15) & ~(size_t)15) + 64, 0);
+    memcpy(b->bytes.data(), d.blob.data(), d.blob.size());
     return b;
 }
 const u8* lw_bytes(lw_batch* b, u64* total) { *total = b->bytes.size(); return b->bytes.data(); }

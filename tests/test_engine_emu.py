@@ -264,3 +264,19 @@ def test_rows_straddling_change_boundary_are_corrupt():
     r = loro_b200.import_batch([patched, good], flags=api.LB_FLAG_EXPORT, lib_path=EMU)
     assert r.status(0).code in (1, 4), r.status(0)
     assert r.status(1).code == 0
+
+
+def test_config_c4_shape_many_fully_concurrent_branches():
+    """BASELINE config C4 in small: one Text document, a pasted base and 40 peers (more than a warp has lanes) that
+    edit their own copy of it without ever syncing -- one merge of 40 fully concurrent branches; state and re-exported
+    bytes equal the oracle's, and the generator's own encoder agrees with the oracle's export byte for byte."""
+    from loro_b200.workload import C4Doc
+    from tests.export_checks import check_export_against_oracle
+    g = C4Doc(base_chars=6000, n_peers=40, edits=120)
+    blob = g.blob(0)
+    o = OracleDoc(1)
+    o.import_(blob)
+    assert not o.inconsistent_delete() and o.export_updates() == blob
+    b = check_batch_against_oracle([blob], lib_path=EMU)
+    assert b.counters()["atom_ops"] == g.atom_ops
+    check_export_against_oracle([blob], lib_path=EMU)

@@ -354,3 +354,17 @@ def test_nested_values_and_floats():
     blob = a.export_updates()
     check_batch_against_oracle([blob])
     check_export_against_oracle([blob])
+
+
+def test_config_c4_reduced_and_round_trip():
+    """BASELINE config C4 (single rich-text document, 64 concurrent peers) at a size the oracle replays in seconds:
+    state JSON and exported bytes equal the oracle's; importing the export again gives the same state hash."""
+    import loro_b200
+    from loro_b200 import api
+    from loro_b200.workload import C4Doc
+    from tests.export_checks import check_export_against_oracle
+    g = C4Doc(base_chars=100000, n_peers=64, edits=800)
+    blob = g.blob(0)
+    b = check_batch_against_oracle([blob])
+    assert b.counters()["atom_ops"] == g.atom_ops
+    check_export_against_oracle([blob])
