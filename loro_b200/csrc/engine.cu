@@ -160,7 +160,7 @@ struct lb_batch {
     std::unordered_map<size_t, std::vector<uint8_t>> from_exports;   // last on-demand export per document
     uint8_t* exported = nullptr;  // malloc'ed host copy (lbstage::download)
     bool export_fetched = false;
-    u64 n_blocks = 0, n_changes = 0, n_rows = 0, n_peers_tot = 0, json_total = 0;
+    u64 n_blocks = 0, n_changes = 0, n_rows = 0, n_peers_tot = 0, json_total = 0, n_deps = 0;
     Tables tb{};
     // host results
     std::vector<DocInfo> docs;
@@ -268,6 +268,7 @@ void pipeline(lb_batch* b) {
     b->n_changes = NCH;
     b->n_rows = NR;
     b->n_peers_tot = NP;
+    b->n_deps = ND;
     Tables& t = b->tb;
     t.peer_id = dv.alloc<u64>(NP);
     t.key_off = dv.alloc<u64>(NK); t.key_len = dv.alloc<u32>(NK);
@@ -1022,7 +1023,19 @@ lb_status lb_debug_table(const lb_batch* b, const char* name, void* dst, size_t 
     TAB("op_len", t.op_len, b->n_rows) TAB("op_counter", t.op_counter, b->n_rows)
     TAB("ch_counter", t.ch_counter, b->n_changes) TAB("ch_len", t.ch_len, b->n_changes)
     TAB("ch_lamport", t.ch_lamport, b->n_changes) TAB("ch_ts", t.ch_ts, b->n_changes)
+    TAB("dep_peer", t.dep_peer_idx, b->n_deps) TAB("dep_counter", t.dep_counter, b->n_deps)
 #undef TAB
+    if (nm == "blk_doc" || nm == "blk_nchanges") {   // fields of the block descriptors
+        *n_elems = b->n_blocks;
+        *elem_size = 4;
+        if (dst) {
+            if (dst_bytes < b->n_blocks * 4) { g_last_error = "buffer too small"; return LB_ERR_INVALID_ARG; }
+            std::vector<BlockInfo> hb(b->n_blocks);
+            if (b->n_blocks && cudaMemcpy(hb.data(), b->d_blocks, sizeof(BlockInfo) * b->n_blocks, cudaMemcpyDeviceToHost) != cudaSuccess) return LB_ERR_CUDA;
+            for (size_t i = 0; i < hb.size(); i++) ((u32*)dst)[i] = nm == "blk_doc" ? hb[i].doc : hb[i].n_changes;
+        }
+        return LB_OK;
+    }
     if (!src) { g_last_error = "unknown table"; return LB_ERR_INVALID_ARG; }
     *n_elems = n;
     *elem_size = es;

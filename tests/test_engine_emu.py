@@ -280,3 +280,37 @@ def test_config_c4_shape_many_fully_concurrent_branches():
     b = check_batch_against_oracle([blob], lib_path=EMU)
     assert b.counters()["atom_ops"] == g.atom_ops
     check_export_against_oracle([blob], lib_path=EMU)
+
+
+def test_decode_tables_against_the_oracle_decoder():
+    """Decode SoA, table by table (lb_debug_table): every row / change / dependency column the decode kernels write
+    equals what the oracle's block decoder reads from the same blobs -- a decode fault is localised here, not only
+    through the state JSON and the re-exported bytes downstream."""
+    import numpy as np
+    import loro_b200
+    from loro_b200 import api
+    blobs = [workloads.make_doc_history(8100 + s, n_sites=3, n_ops=180)[0] for s in range(3)]
+    blobs.append(workloads.make_tree_history(8200, n_sites=3, n_base=20, n_ops=70)[0])
+    b = loro_b200.import_batch(blobs, flags=api.LB_FLAG_KEEP_DEVICE, lib_path=EMU)
+    want = {k: [] for k in ("op_prop", "op_len", "op_counter", "op_vtype", "ch_counter", "ch_len", "ch_lamport", "ch_ts",
+                            "dep_counter", "blk_doc", "blk_nchanges")}
+    vt_of = {"insert_text": 5, "insert": 11, "map_set": 11, "map_del": 8, "delete": 9, "tree_create": 16, "tree_move": 16, "tree_delete": 16}
+    for d, blob in enumerate(blobs):
+        for blk in oracle.decode_dump(blob)["blocks"]:
+            want["blk_doc"].append(d)
+            want["blk_nchanges"].append(blk["n_changes"])
+            for ch in blk["changes"]:
+                want["ch_counter"].append(ch["counter"])
+                want["ch_lamport"].append(ch["lamport"])
+                want["ch_ts"].append(ch["timestamp"])
+                want["ch_len"].append(ch["ops"][-1]["counter"] + ch["ops"][-1]["len"] - ch["counter"])
+                want["dep_counter"] += [c for p, c in ch["deps"] if str(p) != str(ch["peer"])]
+                for op in ch["ops"]:
+                    want["op_prop"].append(op["prop"])
+                    want["op_len"].append(op["len"])
+                    want["op_counter"].append(op["counter"])
+                    want["op_vtype"].append(vt_of[op["kind"]])
+    for name, w in want.items():
+        got = b.debug_table(name)
+        assert len(got) == len(w), (name, len(got), len(w))
+        assert np.array_equal(np.asarray(got, dtype=np.int64), np.asarray(w, dtype=np.int64)), name
