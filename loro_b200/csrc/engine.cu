@@ -327,6 +327,7 @@ void pipeline(lb_batch* b) {
     rt.ch_lamport = dv.alloc<u32>(NCH, true);
     rt.ch_walk = dv.alloc<u32>(NCH);
     rt.ch_pos = dv.alloc<u32>(NCH, true);
+    rt.ch_trim = dv.alloc<u32>(NCH, true);
     LB_LAUNCH(k_doc_tables, nblk(D, 64), 64, 0, st, b->d_bytes, b->d_docs, D, blk, rt);
     u32* d_tmp_a = dv.alloc<u32>(D + 1, true);
     u32* d_tmp_b = dv.alloc<u32>(D + 1, true);
@@ -350,7 +351,7 @@ void pipeline(lb_batch* b) {
     ClassifyTables ct;
     memset(&ct, 0, sizeof(ct));
     ct.blocks = blk; ct.ch_block = t.ch_block; ct.ch_applied = rt.ch_applied; ct.ch_lamport = rt.ch_lamport;
-    ct.ch_counter = t.ch_counter; ct.ch_peer = rt.ch_peer;
+    ct.ch_counter = t.ch_counter; ct.ch_peer = rt.ch_peer; ct.ch_trim = rt.ch_trim;
     ct.op_cid = t.op_cid; ct.op_prop = t.op_prop; ct.op_vtype = t.op_vtype; ct.op_len = t.op_len;
     ct.op_counter = t.op_counter; ct.op_change = t.op_change;
     ct.op_del = t.op_del; ct.del_peer_idx = t.del_peer_idx; ct.del_counter = t.del_counter; ct.del_len = t.del_len;
@@ -513,6 +514,7 @@ void pipeline(lb_batch* b) {
         xt.sg_src = dv.alloc<u32>(SEGCAP); xt.sg_r0 = dv.alloc<u32>(SEGCAP); xt.sg_from = dv.alloc<u32>(SEGCAP);
         xt.sg_atoms = dv.alloc<u32>(SEGCAP); xt.sg_est = dv.alloc<u32>(SEGCAP); xt.sg_nmops = dv.alloc<u32>(SEGCAP);
         xt.sg_ndel = dv.alloc<u32>(SEGCAP); xt.sg_nrows = dv.alloc<u32>(SEGCAP); xt.sg_last_head = dv.alloc<u32>(SEGCAP);
+        xt.sg_skip = dv.alloc<u32>(SEGCAP, true); xt.ch_trim = rt.ch_trim;
         xt.fc_src = dv.alloc<u32>(SEGCAP); xt.fc_pos = dv.alloc<u32>(SEGCAP); xt.fc_r0 = dv.alloc<u32>(SEGCAP);
         xt.fc_from = dv.alloc<u32>(SEGCAP); xt.fc_atoms = dv.alloc<u32>(SEGCAP); xt.fc_nrows = dv.alloc<u32>(SEGCAP);
         xt.fc_ndel = dv.alloc<u32>(SEGCAP); xt.fc_block = dv.alloc<u8>(SEGCAP); xt.fc_skip = dv.alloc<u32>(SEGCAP, true);
@@ -531,7 +533,7 @@ void pipeline(lb_batch* b) {
         xt.s_flag = dv.alloc<u8>(NSYN); xt.s_voff = dv.alloc<u64>(NSYN); xt.s_vlen = dv.alloc<u32>(NSYN); xt.s_aux = dv.alloc<u32>(NSYN);
         if (NCH + NOVF > SEGCAP) {   // unusually many split changes: grow the tables, keep what pass 0 wrote
             u64 cap = NCH + NOVF;
-            u32** sgs[9] = {&xt.sg_src, &xt.sg_r0, &xt.sg_from, &xt.sg_atoms, &xt.sg_est, &xt.sg_nmops, &xt.sg_ndel, &xt.sg_nrows, &xt.sg_last_head};
+            u32** sgs[10] = {&xt.sg_src, &xt.sg_r0, &xt.sg_from, &xt.sg_atoms, &xt.sg_est, &xt.sg_nmops, &xt.sg_ndel, &xt.sg_nrows, &xt.sg_last_head, &xt.sg_skip};
             for (auto pp : sgs) {
                 u32* nw = dv.alloc<u32>(cap);
                 CK(cudaMemcpyAsync(nw, *pp, sizeof(u32) * NCH, cudaMemcpyDeviceToDevice, st));

@@ -11,6 +11,7 @@
 struct ClassifyTables {
     const BlockInfo* blocks;
     const u32* ch_block; const u8* ch_applied; const u32* ch_lamport; const i32* ch_counter; const u16* ch_peer;
+    const u32* ch_trim;     // atoms at the head of the change the document already had (k_doc_causal)
     const u32* op_cid; const i32* op_prop; const u8* op_vtype; const u32* op_len; const i32* op_counter;
     const u32* op_change;
     const u32* op_del; const u32* del_peer_idx; const i32* del_counter; const i32* del_len; const u32* peer_map;
@@ -71,6 +72,14 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
         di.code = LB_ERR(DOC_ERR_CORRUPT);      // (any thread may write it: every writer stores the same code)
     }
     if (!t.ch_applied[ch]) kind = OPK_SKIP;
+    // a change whose head was already known arrives as a slice: rows before the cut are dropped, the row under the cut
+    // loses its first `cut_skip` atoms (Op::slice, list_op.rs:603-658)
+    u32 cut_skip = 0;
+    if (t.ch_trim[ch]) {
+        i32 cut = t.ch_counter[ch] + (i32)t.ch_trim[ch];
+        if (t.op_counter[row] + (i32)t.op_len[row] <= cut) kind = OPK_SKIP;
+        else if (t.op_counter[row] < cut) cut_skip = (u32)(cut - t.op_counter[row]);
+    }
     u32 lam = t.ch_lamport[ch] + (u32)(t.op_counter[row] - t.ch_counter[ch]);
     if (kind != OPK_TREE && t.op_vtype[row] == VK_RAW_TREE_MOVE) {
         // a RawTreeMove row that is not an applied op of a Tree container: its slot of the tree tables says so (the
@@ -121,11 +130,12 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
             w = (u32)tc;
             aux = tp;
             rev = dlen < 0 ? 1u : 0u;
-        }
+            if (cut_skip && !rev) w += cut_skip;   // forward span: the first targets go with the dropped atoms
+        } else if (kind == OPK_SEQ_INS) w += cut_skip;   // insert position of the first kept atom
         uint4 rec;
         rec.x = (u32)kind | (rev << 3) | (cidx << 4);
-        rec.y = (u32)t.op_counter[row];
-        rec.z = t.op_len[row];
+        rec.y = (u32)t.op_counter[row] + cut_skip;
+        rec.z = t.op_len[row] - cut_skip;
         rec.w = w;
         t.op_rec[row] = rec;
         t.op_aux[row] = aux;
@@ -134,10 +144,10 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
     t.op_cidx[row] = cidx;
     t.op_lamport[row] = lam;
     if (kind == OPK_SKIP) return;
-    u32 len = t.op_len[row];
+    u32 len = t.op_len[row] - cut_skip;
     const DocPeer& dp = t.dpeer[di.peer0 + t.ch_peer[ch]];
     // atom -> row index (used by the tracker to resolve ids; reference: id_to_cursor.rs)
-    u64 a0 = di.atom0 + dp.atom_base + (u32)t.op_counter[row];
+    u64 a0 = di.atom0 + dp.atom_base + (u32)t.op_counter[row] + cut_skip;
     for (u32 k = 0; k < len; k++) t.atom_row[a0 + k] = (u32)row;
     switch (kind) {
         case OPK_SEQ_INS:

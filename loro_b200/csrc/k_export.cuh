@@ -91,6 +91,8 @@ struct ExportTables {
     u64* ch_seg0;      // scan of ch_novf
     // per segment
     u32* sg_src; u32* sg_r0; u32* sg_from; u32* sg_atoms; u32* sg_est; u32* sg_nmops; u32* sg_ndel; u32* sg_nrows; u32* sg_last_head;
+    u32* sg_skip;      // atoms of the segment's first row the document already had (import-side trim, k_doc_causal)
+    const u32* ch_trim;
     // final changes (same index space: a document never ends up with more changes than segments)
     u32* fc_src; u32* fc_pos; u32* fc_r0; u32* fc_from; u32* fc_atoms; u32* fc_nrows; u32* fc_ndel; u8* fc_block;
     u32* fc_skip;      // atoms of the change's first row that lie before the `from` version (Op::slice)
@@ -484,7 +486,7 @@ __device__ inline void segment_summaries(const ExportTables& t, const DocInfo& d
             r = r1;
         } while (r < nr && !(xr_flag(t, row0 + r) & XF_SEG));
         t.sg_src[sg] = ch; t.sg_r0[sg] = r_start; t.sg_from[sg] = from; t.sg_atoms[sg] = atoms; t.sg_est[sg] = est;
-        t.sg_nmops[sg] = nm; t.sg_ndel[sg] = ndel; t.sg_nrows[sg] = r - r_start; t.sg_last_head[sg] = last_head;
+        t.sg_nmops[sg] = nm; t.sg_ndel[sg] = ndel; t.sg_nrows[sg] = r - r_start; t.sg_last_head[sg] = last_head; t.sg_skip[sg] = 0;
         from += atoms;
         sg = sg_next++;
     }
@@ -510,34 +512,51 @@ __global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportT
         back.xk = XK_NONE;
         u32 est_ops = 0, nm = 0, ndel = 0, last_head = 0;
         bool bad = false;
+        // a change whose head the document already had entered the store as a slice (oplog.rs:181-196): rows before the
+        // cut are not part of it, the row under the cut loses its first atoms
+        const u32 trim = t.ch_trim[ch];
+        const i32 cut = t.ch_counter[ch] + (i32)trim;
+        u32 r_first = 0, skip = 0;
         for (u32 r = 0; r < nr; r++) {
             u64 row = r0 + r;
             u32 astart = 0;
-            if (t.op_kind[row] == OPK_SEQ_INS) {
-                if (t.dcont[di.cid0 + t.op_cidx[row]].type == CT_TEXT) { astart = strs; strs += t.r_bytes[row]; }
-                else { astart = vals; vals += t.op_len[row]; }
+            {   // every decoded insert allocated arena space, kept or not (same rule as k_exp_arena)
+                u8 ctype = t.dcont[di.cid0 + t.op_cidx[row]].type;
+                u8 vt = t.op_vtype[row];
+                if (ctype == CT_TEXT && vt == VK_STR) { astart = strs; strs += t.r_bytes[row]; }
+                else if (ctype == CT_LIST && vt == VK_LORO_VALUE) { astart = vals; vals += t.op_len[row]; }
+            }
+            if (trim && t.op_counter[row] + (i32)t.op_len[row] <= cut) {
+                t.x_rec[row] = mk4(0, 0, 0, 0);
+                t.r_flag[row] = 0;
+                r_first = r + 1;
+                continue;
             }
             XOp o = xop_resolve(t, di, (u32)ch, row, astart);
             t.x_rec[row] = xop_pack(o);
             if (o.xk == XK_NONE) bad = true;
-            if (r > 0 && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[row] = 0; }
+            if (r == r_first && trim && t.op_counter[row] < cut) { skip = (u32)(cut - t.op_counter[row]); xop_slice_front(t, o, row, skip); }
+            if (r > r_first && xop_mergable(back, o)) { est_ops -= xop_estimate(back); xop_merge(back, o); est_ops += xop_estimate(back); t.r_flag[row] = 0; }
             else { back = o; est_ops += xop_estimate(o); t.r_flag[row] = XF_HEAD; nm++; ndel += o.xk == XK_DEL; last_head = r; }
         }
         u32 nseg = 1, nsyn = 0;
         t.ch_syn[ch] = 0;   // (xop_from_row below must see the decoded rows)
-        if (est0 + est_ops > LB_MAX_BLOCK_SIZE) {
+        if (trim && est0 + est_ops > LB_MAX_BLOCK_SIZE) {
+            bad = true;   // a trimmed change that also has to be split over several blocks: not covered
+            t.r_flag[r0 + (r_first < nr ? r_first : 0)] |= XF_SEG;
+        } else if (est0 + est_ops > LB_MAX_BLOCK_SIZE) {
             XSplit sp = split_change(t, di, (u32)ch, r0, nr, est0, [&](u64 row, u32 a, u32, bool, bool seg) {
                 if (seg && a == 0) t.r_flag[row] |= XF_SEG;   // valid when nothing gets cut (else the synthetic rows carry it)
             });
             nseg = sp.nseg;
             if (sp.sliced && nseg > 1) nsyn = sp.nsyn;   // (a lone "slice" that is the whole op changes nothing)
-        } else t.r_flag[r0] |= XF_SEG;
+        } else t.r_flag[r0 + (r_first < nr ? r_first : 0)] |= XF_SEG;
         t.ch_nseg[ch] = nseg;
         t.ch_novf[ch] = nseg - 1;
         t.ch_syn[ch] = nsyn;
         if (nseg == 1) {   // the common case: the change is its own (only) segment, summarised right here
-            t.sg_src[ch] = (u32)ch; t.sg_r0[ch] = 0; t.sg_from[ch] = 0; t.sg_atoms[ch] = t.ch_len[ch]; t.sg_est[ch] = est_ops;
-            t.sg_nmops[ch] = nm; t.sg_ndel[ch] = ndel; t.sg_nrows[ch] = nr; t.sg_last_head[ch] = last_head;
+            t.sg_src[ch] = (u32)ch; t.sg_r0[ch] = r_first; t.sg_from[ch] = trim; t.sg_atoms[ch] = t.ch_len[ch] - trim; t.sg_est[ch] = est_ops;
+            t.sg_nmops[ch] = nm; t.sg_ndel[ch] = ndel; t.sg_nrows[ch] = nr - r_first; t.sg_last_head[ch] = last_head; t.sg_skip[ch] = skip;
         }
         if (bad) atomicOr(&t.xdoc[doc].flags, 1u);
         return;
@@ -615,12 +634,20 @@ __device__ __forceinline__ u32 xentry_ndeps(const ExportTables& t, const XEntry&
 // cursor over the rows of an entry in store order (rows of consecutive applied changes of the peer)
 struct XRows {
     const ExportTables& t; u32 pos; u32 r; u32 ch; u32 nr; u64 row0;
-    __device__ XRows(const ExportTables& t_, u32 pos_, u32 r_) : t(t_), pos(pos_), r(r_) { load(); }
+    u32 skip;   // atoms of the CURRENT row that are not part of the store (first kept row of a trimmed change); the
+                // creator of the cursor knows the skip of the row it starts on (entry / final-change records)
+    __device__ XRows(const ExportTables& t_, u32 pos_, u32 r_) : t(t_), pos(pos_), r(r_), skip(0) { load(); }
     __device__ void load() { ch = t.ch_order[pos]; change_rows(t, ch, &row0, &nr); }
     __device__ u64 row() const { return row0 + r; }
     __device__ void next() {
         r++;
-        while (r >= nr) { pos++; r = 0; ch = t.ch_order[pos]; if (!t.ch_applied[ch]) { nr = 0; continue; } change_rows(t, ch, &row0, &nr); }
+        skip = 0;
+        while (r >= nr) {
+            pos++; r = 0; ch = t.ch_order[pos];
+            if (!t.ch_applied[ch]) { nr = 0; continue; }
+            change_rows(t, ch, &row0, &nr);
+            if (t.ch_trim[ch]) { r = t.sg_r0[ch]; skip = t.sg_skip[ch]; }   // a trimmed change starts at its first kept row
+        }
     }
 };
 // accumulate the merged op that starts at the cursor (consumes its rows, at most `left` of them)
@@ -638,8 +665,10 @@ __device__ inline XOp xop_gather(const ExportTables& t, const DocInfo& di, XRows
     left--;
     if (left) it.next();
     while (left && !(xr_flag(t, it.row()) & XF_HEAD)) {
-        if (vbytes) *vbytes += row_value_bytes(t, o, it.row());
-        xop_merge(o, xop_from_row(t, di, it.ch, it.row()));
+        if (vbytes) { const u8* pp; u32 pn; xr_payload_skip(t, it.row(), o.xk, it.skip, &pp, &pn); *vbytes += pn; }
+        XOp x = xop_from_row(t, di, it.ch, it.row());
+        if (it.skip) xop_slice_front(t, x, it.row(), it.skip);
+        xop_merge(o, x);
         left--;
         if (left) it.next();
     }
@@ -652,6 +681,7 @@ __device__ inline XOp xentry_last_op(const ExportTables& t, const DocInfo& di, c
     u32 nr;
     change_rows(t, E.lh_ch, &row0, &nr);
     XOp o = xop_from_row(t, di, E.lh_ch, row0 + E.lh_row);
+    if (E.skip && E.lh_row == E.r0 && E.lh_ch == t.ch_order[E.pos]) xop_slice_front(t, o, row0 + E.lh_row, E.skip);
     u32 r = E.lh_row + 1;
     while (r < nr && !(xr_flag(t, row0 + r) & (XF_HEAD | XF_SEG))) { xop_merge(o, xop_from_row(t, di, E.lh_ch, row0 + r)); r++; }
     return o;
@@ -681,7 +711,7 @@ __device__ inline bool xstore_push(const ExportTables& t, const DocInfo& di, XSt
             bool first_op = true;
             while (left) {
                 u64 head_row = it.row();
-                XOp o = xop_gather(t, di, it, left, nullptr, first_op ? E.skip : 0u);
+                XOp o = xop_gather(t, di, it, left, nullptr, first_op ? E.skip : it.skip);
                 first_op = false;
                 if (!xop_mergable(s.back, o)) break;
                 merged_sz += xop_estimate(o);
@@ -719,18 +749,18 @@ __device__ inline bool xentry_cut(const ExportTables& t, const DocInfo& di, XEnt
     if (start >= c0 + (i32)E.atoms) return false;
     u32 cut = (u32)(start - c0);
     XRows it(t, E.pos, E.r0);
-    u32 left = E.nrows, acc = E.skip ? 0u : 0u;
+    u32 left = E.nrows, acc = 0, lead = E.skip;   // `lead`: atoms of the current row already outside the entry
     while (left) {
-        u32 len = xr_len(t, it.row());
+        u32 len = xr_len(t, it.row()) - lead;
         if (acc + len > cut) break;
         acc += len;
         left--;
-        if (left) it.next();
+        if (left) { it.next(); lead = it.skip; } else lead = 0;
     }
     E.pos = it.pos;
     E.r0 = it.r;
     E.nrows = left;
-    E.skip = cut - acc;
+    E.skip = lead + (cut - acc);
     E.from += cut;
     E.atoms -= cut;
     // fresh summary of what is left: size estimate, ops, deletes, last op
@@ -740,7 +770,7 @@ __device__ inline bool xentry_cut(const ExportTables& t, const DocInfo& di, XEnt
     last.xk = XK_NONE;
     bool first = true;
     while (l) {
-        XOp o = xop_gather(t, di, it2, l, nullptr, first ? E.skip : 0u);
+        XOp o = xop_gather(t, di, it2, l, nullptr, first ? E.skip : it2.skip);
         first = false;
         est += xop_estimate(o);
         nm++;
@@ -794,7 +824,7 @@ __global__ void k_exp_store(const DocInfo* __restrict__ docs, u32 n_docs, Export
                 XEntry E;
                 E.src = ch; E.from = t.sg_from[sg]; E.pos = pos; E.r0 = t.sg_r0[sg]; E.atoms = t.sg_atoms[sg];
                 E.est_ops = t.sg_est[sg]; E.nmops = t.sg_nmops[sg]; E.ndel = t.sg_ndel[sg]; E.nrows = t.sg_nrows[sg];
-                E.lh_ch = ch; E.lh_row = t.sg_last_head[sg]; E.last_valid = false; E.skip = 0;
+                E.lh_ch = ch; E.lh_row = t.sg_last_head[sg]; E.last_valid = false; E.skip = t.sg_skip[sg];
                 if (xstore_push(t, di, s1, E, done, done_blk)) {
                     XEntry d2;
                     bool d2_blk = false;
@@ -1184,7 +1214,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                 const u32 left0 = left;
                 const u32 skip0 = skip;
                 XOp o = xop_gather(t, di, it, left, has_maps ? nullptr : &vbytes, skip);
-                skip = 0;
+                skip = left ? it.skip : 0u;   // (the next op may start on the first kept row of a trimmed change)
                 if (o.xk == XK_LIST) vbytes += 1 + varint_len(o.atoms);
                 else if (o.xk == XK_TEXT) vbytes += varint_len(o.f1 - o.f0);
                 // DeltaRle columns are stored as deltas right away (the encoders then read every value once)
@@ -1195,7 +1225,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                     while (k) {
                         const u8* pp;
                         u32 pn;
-                        xr_payload_skip(t, it0.row(), o.xk, k == left0 - left ? skip0 : 0u, &pp, &pn);
+                        xr_payload_skip(t, it0.row(), o.xk, k == left0 - left ? skip0 : it0.skip, &pp, &pn);
                         if (o.xk == XK_LIST || o.xk == XK_MAPSET) {
                             XSink cs;
                             cs.dst = nullptr; cs.n = 0;
@@ -1342,9 +1372,8 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
                     if (has_maps && xk != XK_TEXT) xvalue_copy(s, pp, pn, t, t.blocks[t.ch_block[it.ch]].key0, keys, false);
                     else s.copy(pp, pn);
                 }
-                skip = 0;
                 left--;
-                if (left) it.next();
+                if (left) { it.next(); skip = it.skip; }
             }
         }
     };

@@ -33,6 +33,8 @@ struct ResolveTables {
     u32* ch_walk;        // per doc: applied changes in replay order
     i32* ch_vv;          // per doc: n_changes * P
     u32* ch_pos;         // per change: its position in the doc's ch_order (= row of ch_vv)
+    u32* ch_trim;        // per change: leading atoms the document already had when the change arrived
+                         // (OpLog::trim_the_known_part_of_change, oplog.rs:181-196: the rest is applied as a slice)
 };
 
 __device__ inline bool bytes_eq(const u8* a, const u8* b, u32 n) {
@@ -264,7 +266,16 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
             if (ctr != dp.end_counter) {
                 if (ctr < dp.end_counter) {  // overlapping duplicate: drop if fully covered
                     if (ctr + (i32)t.ch_len[ch] <= dp.end_counter) { cursor[p]++; step--; continue; }
-                    di.code = LB_ERR(DOC_ERR_UNSUPPORTED);  // partial overlap needs op slicing (multi-blob docs)
+                    // partial overlap (an update exported from an older version vector): the known part is trimmed and
+                    // the rest applies as Change::slice -- it depends on its own predecessor only (change.rs:248-252)
+                    u32 l, c2;
+                    if (!lamport_of(di, t, p, dp.end_counter - 1, &l, &c2)) continue;
+                    u32 lam_t = l + 1;
+                    if (step == 0) { pick = p; pick_lam = lam_t; pick_ch = ch; break; }
+                    if (pick == 0xFFFFFFFFu || lam_t < pick_lam ||
+                        (lam_t == pick_lam && t.dpeer[di.peer0 + p].rank < t.dpeer[di.peer0 + pick].rank)) {
+                        pick = p; pick_lam = lam_t; pick_ch = ch;
+                    }
                 }
                 continue;  // gap: predecessor missing -> pending
             }
@@ -296,15 +307,17 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
         u32 ch = pick_ch;
         DocPeer& dp = t.dpeer[di.peer0 + pick];
         i32 ctr = t.ch_counter[ch];
+        const u32 trim = ctr < dp.end_counter ? (u32)(dp.end_counter - ctr) : 0u;
         u32 local = dp.ch_first + cursor[pick];  // row of this change in the doc's ch_vv
         i32* v = t.ch_vv + di.vv0 + (u64)local * P;
         for (u32 q = 0; q < P; q++) v[q] = 0;
         const BlockInfo& bi = blocks[t.ch_block[ch]];
-        u32 ndeps = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1 : 0);
+        u32 ndeps = trim ? 1u : t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1 : 0);
         for (u32 k = 0; k < ndeps; k++) {
             u32 dpi;
             i32 dc;
-            if (k == t.ch_ndeps[ch]) { dpi = pick; dc = ctr - 1; }
+            if (trim) { dpi = pick; dc = dp.end_counter - 1; }
+            else if (k == t.ch_ndeps[ch]) { dpi = pick; dc = ctr - 1; }
             else { dpi = t.peer_map[bi.peer0 + t.dep_peer_idx[t.ch_dep0[ch] + k]]; dc = t.dep_counter[t.ch_dep0[ch] + k]; }
             u32 l = 0, dch = ch;
             lamport_of(di, t, dpi, dc, &l, &dch);
@@ -312,12 +325,13 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
             for (u32 q = 0; q < P; q++) if (dv[q] > v[q]) v[q] = dv[q];
             if (dc + 1 > v[dpi]) v[dpi] = dc + 1;
         }
-        t.ch_lamport[ch] = pick_lam;
+        t.ch_lamport[ch] = pick_lam - trim;   // lamport of the change's (trimmed) first atom: counters and lamports run in step
+        t.ch_trim[ch] = trim;
         t.ch_applied[ch] = 1;
         t.ch_pos[ch] = local;
         t.ch_walk[di.ch0 + walk_n++] = ch;
         dp.end_counter = ctr + (i32)t.ch_len[ch];
-        di.atom_ops += t.ch_len[ch];
+        di.atom_ops += t.ch_len[ch] - trim;
         cursor[pick]++;
         cur = pick;
     }

@@ -314,3 +314,25 @@ def test_decode_tables_against_the_oracle_decoder():
         got = b.debug_table(name)
         assert len(got) == len(w), (name, len(got), len(w))
         assert np.array_equal(np.asarray(got, dtype=np.int64), np.asarray(w, dtype=np.int64)), name
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_partially_known_changes_are_trimmed(seed):
+    """import_batch of two blobs whose changes overlap in the middle of an op (oplog.rs:181-196, change.rs:203-258):
+    the known head is trimmed on import; state, version, export(all_updates) and export(updates(vv)) equal the oracle's
+    for both arrival orders."""
+    import loro_b200
+    from loro_b200 import api
+    e1, e2, n = workloads.overlapping_update_blobs(seed)
+    assert n > 0
+    for blobs in ([e1, e2], [e2, e1]):
+        ref = OracleDoc(7)
+        for bl in workloads.import_batch_order(blobs):
+            ref.import_(bl)
+        bt = loro_b200.import_batch(blobs, doc_ids=[1, 1], flags=api.LB_FLAG_EXPORT, lib_path=EMU)
+        assert bt.status(0).code == 0
+        assert bt.json_bytes(0) == ref.json_text()
+        assert bt.oplog_vv(0) == ref.oplog_vv()
+        assert bt.export_updates(0) == ref.export_updates()
+        frm = {p: c // 2 for p, c in ref.oplog_vv().items()}
+        assert bt.export_updates(0, frm) == ref.export_updates(frm)

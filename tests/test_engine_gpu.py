@@ -368,3 +368,22 @@ def test_config_c4_reduced_and_round_trip():
     b = check_batch_against_oracle([blob])
     assert b.counters()["atom_ops"] == g.atom_ops
     check_export_against_oracle([blob])
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_partially_known_changes_are_trimmed(seed):
+    import loro_b200
+    from loro_b200 import api
+    e1, e2, n = workloads.overlapping_update_blobs(50 + seed)
+    assert n > 0
+    for blobs in ([e1, e2], [e2, e1]):
+        ref = OracleDoc(7)
+        for bl in workloads.import_batch_order(blobs):
+            ref.import_(bl)
+        bt = loro_b200.import_batch(blobs, doc_ids=[1, 1], flags=api.LB_FLAG_EXPORT)
+        assert bt.status(0).code == 0
+        assert bt.json_bytes(0) == ref.json_text()
+        assert bt.oplog_vv(0) == ref.oplog_vv()
+        assert bt.export_updates(0) == ref.export_updates()
+        frm = {p: c // 2 for p, c in ref.oplog_vv().items()}
+        assert bt.export_updates(0, frm) == ref.export_updates(frm)

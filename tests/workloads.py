@@ -190,3 +190,46 @@ def make_tree_history(seed, n_sites=3, n_base=40, n_ops=120, sync_prob=0.04, com
     fresh = OracleDoc(1)
     fresh.import_(blob)
     return blob, fresh.json_text(), fresh.oplog_vv(), docs
+
+
+def overlapping_update_blobs(seed):
+    """Two blobs of one history whose changes overlap PARTIALLY: an early full export, then -- after the author kept
+    editing, so that its stored change grew past that export -- an update cut from an older version.  Importing both
+    makes the second arrive with a known head (OpLog::trim_the_known_part_of_change, oplog.rs:181-196).
+    Returns (blob_early, blob_late, n_partial_overlaps)."""
+    rnd = random.Random(seed)
+    a, b = OracleDoc(100), OracleDoc(101)
+    ha = (a.get_text("text"), a.get_list("list"), a.get_map("map"))
+    hb = (b.get_text("text"), b.get_list("list"), b.get_map("map"))
+    for _ in range(30):
+        random_edit(rnd, a, *ha)
+        random_edit(rnd, b, *hb)
+        if rnd.random() < 0.3:
+            a.commit(); b.commit()
+    merge(a, b); merge(b, a)
+    for _ in range(25):
+        random_edit(rnd, a, *ha, children=0)
+        if rnd.random() < 0.3:
+            a.commit()
+    a.commit()
+    e1, vv1 = a.export_updates(), a.oplog_vv()
+    for _ in range(25):
+        random_edit(rnd, a, *ha, children=0)
+        if rnd.random() < 0.3:
+            a.commit()
+    a.commit()
+    e2 = a.export_updates({p: max(0, c - rnd.randint(1, 15)) for p, c in vv1.items()})
+    n = 0
+    for bl in oracle.decode_dump(e2)["blocks"]:
+        for ch in bl["changes"]:
+            end = ch["ops"][-1]["counter"] + ch["ops"][-1]["len"]
+            if ch["counter"] < vv1.get(int(ch["peer"]), 0) < end:
+                n += 1
+    return e1, e2, n
+
+
+def import_batch_order(blobs):
+    """LoroDoc::import_batch imports its blobs sorted by number of changes, descending, stably (loro.rs:1194-1202)."""
+    def n_changes(blob):
+        return sum(len(bl["changes"]) for bl in oracle.decode_dump(blob)["blocks"])
+    return sorted(blobs, key=lambda x: -n_changes(x))
