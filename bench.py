@@ -301,6 +301,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    # one rank per GPU: keep the rank's host buffers, the pinned staging ring and the gather threads on the NUMA node
+    # of its GPU (the host side limited e2e scaling at 8 ranks in round 1)
+    numa_bound = loro_b200.numa_bind(local) if world > 1 else False
     n_docs = default_docs(args, world)
     gen, distinct, gen_s = make_workload(args, rank, world, n_docs)
     # lay the batch out in HBM: cycle through the distinct docs (each copy has its own bytes in HBM)
@@ -454,7 +457,7 @@ def main():
                    "name": args.config,
                    "docs_per_gpu": n_docs, "distinct_docs_per_gpu": distinct, "atom_ops_per_step_per_gpu": atoms_per_step,
                    "op_rows_per_gpu": rows, "blob_bytes_per_gpu": int(lens.sum()), "l2": "inputs_larger_than_L2" if lens.sum() > 126e6 else "inputs fit L2",
-                   "generator_seconds": round(gen_s, 1), "host_cores": host_cores()},
+                   "generator_seconds": round(gen_s, 1), "host_cores": host_cores(), "numa_bound": bool(numa_bound)},
         "phases_ms": {k: v / n_steps for k, v in phase.items()}, "wall_ms_per_step": wall_ms / n_steps,
         "roofline": roof, "decode_roofline": dec_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,

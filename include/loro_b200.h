@@ -49,11 +49,12 @@ typedef enum lb_doc_code {
     LB_DOC_OK = 0,
     LB_DOC_ERR_DECODE = 1,          /* LoroError::DecodeError (short blob, bad magic, malformed block)  */
     LB_DOC_ERR_CHECKSUM = 2,        /* LoroError::DecodeChecksumMismatchError                            */
-    LB_DOC_ERR_MODE = 3,            /* IncompatibleFutureEncodingError / ImportUnsupportedEncodingMode;  */
-                                    /* also FastSnapshot (mode 3): not on this path yet    */
+    LB_DOC_ERR_MODE = 3,            /* IncompatibleFutureEncodingError / ImportUnsupportedEncodingMode   */
+                                    /* (a mode other than FastSnapshot 3 / FastUpdates 4)                */
     LB_DOC_ERR_CORRUPT = 4,         /* LoroError::DecodeDataCorruptionError                               */
-    LB_DOC_ERR_UNSUPPORTED = 5,     /* well-formed, but uses ops the engine does not merge yet            */
-                                    /* (rich-text styles, movable list, counter, tree)                    */
+    LB_DOC_ERR_UNSUPPORTED = 5,     /* well-formed, but outside this path: an intact FastSnapshot blob    */
+                                    /* (mode 3), or ops the engine does not merge yet        */
+                                    /* (rich-text styles, movable list, counter)                          */
     LB_DOC_ERR_CAPACITY = 6         /* internal capacity bound exceeded (engine bug or adversarial input) */
 } lb_doc_code;
 
@@ -142,6 +143,10 @@ lb_status lb_doc_export_updates(const lb_batch* b, size_t doc, const lb_id_span*
 lb_status lb_batch_counters(const lb_batch* b, lb_counters* out);
 lb_status lb_batch_timings(const lb_batch* b, lb_timings* out);
 const char* lb_last_error(void); /* thread-local, human readable */
+/* One process per GPU: pin the calling thread -- and the staging / download threads the engine creates from it -- to
+ * the CPUs of the NUMA node `device` is attached to (sysfs).  Call before building the input buffers so that they,
+ * the pinned staging ring and the gather threads all sit next to the GPU.  LB_ERR_UNSUPPORTED: topology unknown. */
+lb_status lb_numa_bind(int device);
 void lb_batch_free(lb_batch* b);
 
 /* test hooks (need LB_FLAG_KEEP_DEVICE): copy one decoded SoA table to the host.

@@ -4,12 +4,13 @@ Host-side mirror of the reference's public API for that path (crates/loro/src/li
   LoroDoc::import / import_batch  ->  import_batch(blobs)            (one fresh document per blob)
   ImportStatus                    ->  Batch.status(i)
   LoroDoc::get_deep_value         ->  Batch.get_deep_value(i)
-  LoroDoc::oplog_vv               ->  Batch.oplog_vv(i)
+  LoroDoc::oplog_vv / oplog_frontiers ->  Batch.oplog_vv(i) / Batch.oplog_frontiers(i)
+  LoroDoc::export(ExportMode)     ->  Batch.export_updates(i, from_vv=None)   (all_updates / updates(from))
 All compute runs in the CUDA library built from loro_b200/csrc (C ABI: include/loro_b200.h).  There is no
 CPU fallback: importing a batch without the built library or without a CUDA device raises.
 """
 from .api import (Batch, DocError, EngineUnavailable, ImportStatus, import_batch, import_batch_device,
-                  library_path, load_library, pack_blobs)
+                  library_path, load_library, numa_bind, pack_blobs)
 
 __all__ = ["Batch", "DocError", "EngineUnavailable", "ImportStatus", "import_batch", "import_batch_device",
-           "library_path", "load_library", "pack_blobs"]
+           "library_path", "load_library", "numa_bind", "pack_blobs"]

@@ -255,6 +255,14 @@ def import_batch_device(d_bytes_ptr, offsets, lens, device=0, flags=0, lib_path=
     return Batch(L, h.value, keep=keep)
 
 
+def numa_bind(device=0, lib_path=None):
+    """Pin this process (its current thread and the threads created from it) to the CPUs of the NUMA node of `device`.
+    Returns True when the binding was applied."""
+    L = load_library(lib_path)
+    L.lb_numa_bind.argtypes = [ctypes.c_int]
+    return L.lb_numa_bind(device) == 0
+
+
 def pack_blobs(blobs):
     """Concatenate blobs at 16-byte aligned starts -> (bytes, offsets, lens) for import_batch_device."""
     import numpy as np

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <cstdio>
 #include <cstdlib>
+#include <sched.h>
 
 #include "lb_defs.h"
 #include "k_frame.cuh"
@@ -352,6 +353,7 @@ void pipeline(lb_batch* b) {
     memset(&ct, 0, sizeof(ct));
     ct.blocks = blk; ct.ch_block = t.ch_block; ct.ch_applied = rt.ch_applied; ct.ch_lamport = rt.ch_lamport;
     ct.ch_counter = t.ch_counter; ct.ch_peer = rt.ch_peer; ct.ch_trim = rt.ch_trim;
+    ct.bytes = b->d_bytes; ct.op_val_off = t.op_val_off; ct.op_val_len = t.op_val_len;
     ct.op_cid = t.op_cid; ct.op_prop = t.op_prop; ct.op_vtype = t.op_vtype; ct.op_len = t.op_len;
     ct.op_counter = t.op_counter; ct.op_change = t.op_change;
     ct.op_del = t.op_del; ct.del_peer_idx = t.del_peer_idx; ct.del_counter = t.del_counter; ct.del_len = t.del_len;
@@ -432,7 +434,12 @@ void pipeline(lb_batch* b) {
         tt.tn_child = dv.alloc<u32>(NTS);
         tt.tn_root = dv.alloc<u32>(NTS); tt.tn_aopen = dv.alloc<u32>(NTS); tt.tn_aclose = dv.alloc<u32>(NTS);
         tt.dcont = dcont;
-        LB_LAUNCH(k_tree_build, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
+        const size_t tree_smem = (size_t)TREE_WARPS * TREE_S_NODES * sizeof(u16);
+#ifndef LB_SIMT_EMU
+        static bool tree_attr_set = false;
+        if (!tree_attr_set) { CK(cudaFuncSetAttribute(k_tree_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem)); tree_attr_set = true; }
+#endif
+        LB_LAUNCH(k_tree_build, nblk((u64)D * 32, 32 * TREE_WARPS), 32 * TREE_WARPS, tree_smem, st, b->d_docs, D, tt);
         tm.kernel_launches += 2;
     }
     mark(b);  // [5b] trees done
@@ -1062,6 +1069,52 @@ void lb_batch_free(lb_batch* b) {
     lbstage::host_cache().give(b->json);
     lbstage::host_cache().give(b->exported);
     delete b;
+}
+
+// Pin the CALLING thread (and every thread it creates afterwards: the staging workers, the JSON download thread) to
+// the CPUs of the NUMA node the device hangs off, so that the pinned staging ring and the gather threads of a rank stay
+// next to its GPU.  One process per GPU calls this once, before it builds its input buffers.  LB_ERR_UNSUPPORTED when
+// the topology cannot be read (no sysfs entry, single node): nothing is changed.
+lb_status lb_numa_bind(int device) {
+#ifdef LB_SIMT_EMU
+    (void)device;
+    g_last_error = "no topology in the emulated build";
+    return LB_ERR_UNSUPPORTED;
+#else
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { g_last_error = "cudaDeviceGetPCIBusId failed"; return LB_ERR_CUDA; }
+    for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    int node = -1;
+    if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) { g_last_error = "no NUMA node recorded for " + std::string(bus); return LB_ERR_UNSUPPORTED; }
+    path = "/sys/devices/system/node/node" + std::to_string(node) + "/cpulist";
+    f = fopen(path.c_str(), "r");
+    if (!f) { g_last_error = "cannot read " + path; return LB_ERR_UNSUPPORTED; }
+    char list[1024] = {0};
+    if (!fgets(list, sizeof(list), f)) list[0] = 0;
+    fclose(f);
+    cpu_set_t want, have;
+    CPU_ZERO(&want);
+    for (char* p = list; *p;) {   // "0-31,64-95"
+        char* e;
+        long a = strtol(p, &e, 10), b_ = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b_ = strtol(p, &e, 10); }
+        for (long c = a; c <= b_ && c < CPU_SETSIZE; c++) CPU_SET((int)c, &want);
+        p = *e == ',' ? e + 1 : e;
+        if (*e != ',' ) break;
+    }
+    if (sched_getaffinity(0, sizeof(have), &have) == 0) {   // stay inside what the container allows
+        cpu_set_t both;
+        CPU_AND(&both, &want, &have);
+        if (CPU_COUNT(&both) == 0) { g_last_error = "the device's NUMA node has no CPU this process may use"; return LB_ERR_UNSUPPORTED; }
+        want = both;
+    }
+    if (sched_setaffinity(0, sizeof(want), &want) != 0) { g_last_error = "sched_setaffinity failed"; return LB_ERR_UNSUPPORTED; }
+    return LB_OK;
+#endif
 }
 
 #ifdef LB_SIMT_EMU

@@ -12,6 +12,7 @@ struct ClassifyTables {
     const BlockInfo* blocks;
     const u32* ch_block; const u8* ch_applied; const u32* ch_lamport; const i32* ch_counter; const u16* ch_peer;
     const u32* ch_trim;     // atoms at the head of the change the document already had (k_doc_causal)
+    const u8* bytes; const u64* op_val_off; const u32* op_val_len;   // value payloads (List insert: item count check)
     const u32* op_cid; const i32* op_prop; const u8* op_vtype; const u32* op_len; const i32* op_counter;
     const u32* op_change;
     const u32* op_del; const u32* del_peer_idx; const i32* del_counter; const i32* del_len; const u32* peer_map;
@@ -67,6 +68,14 @@ __global__ void k_op_classify(DocInfo* __restrict__ docs, u64 n_rows, ClassifyTa
     u32 cidx = t.cid_map[bi.cid0 + t.op_cid[row]];
     DocContainer& dc = t.dcont[di.cid0 + cidx];
     u8 kind = classify_op(dc.type, t.op_vtype[row]);
+    if (kind == OPK_SEQ_INS && dc.type == CT_LIST) {
+        // a List insert carries LoroValue::List with exactly `len` items (outdated_encode_reordered.rs:246-262: the
+        // reference fails the import otherwise); later phases address the items through `len`
+        Cur pk(t.bytes + t.op_val_off[row], t.op_val_len[row]);
+        u8 k = pk.get();
+        u64 n_items = pk.varint();
+        if (pk.err || k != 7 || n_items != (u64)t.op_len[row]) { kind = OPK_SKIP; di.code = LB_ERR(DOC_ERR_CORRUPT); }
+    }
     if ((kind == OPK_MAP_SET || kind == OPK_MAP_DEL) && (u32)t.op_prop[row] >= bi.n_keys) {
         kind = OPK_SKIP;                       // a map op whose key index is outside the block's key arena
         di.code = LB_ERR(DOC_ERR_CORRUPT);      // (any thread may write it: every writer stores the same code)

@@ -654,12 +654,8 @@ __device__ inline u32 decode_block_rows_cols(const u8* b, const BlockInfo& bi, c
     for (u32 r = 0; r < R; r++) {
         const u64 row = r0 + r;
         const u8 vt = t.op_vtype[row];
-        if (vt == VK_LORO_VALUE && t.cid_type[bi.cid0 + t.op_cid[row]] == CT_LIST) {
-            Cur pk = v;
-            u8 k = pk.get();
-            u64 n_items = pk.varint();
-            if (k != 7 || n_items != (u64)t.op_len[row]) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
-        }
+        // (that a List insert carries exactly `len` items is checked row-parallel by k_op_classify: here it would cost
+        //  two dependent table reads per row -- 19 % of this kernel's stalls in profiles/r2_ncu_decode.md)
         const u8* v0 = v.p;
         u32 aux_idx = 0xFFFFFFFFu;
         if (vt == VK_RAW_TREE_MOVE) {

@@ -106,12 +106,30 @@ struct ExportTables {
 // ---------------------------------------------------------------------------------------------- byte sink
 struct XSink {
     u8* dst;   // nullptr = counting
-    u64 n;
-    __device__ __forceinline__ void put(u8 c) { if (dst) dst[n] = c; n++; }
+    u64 n;     // bytes produced (the last `k` of them still sit in `acc` when writing)
+    u64 acc;   // up to eight bytes on their way out as ONE store (single-byte stores were a third of the encoder's
+    u32 k;     //   instructions in profiles/r2_ncu_expenc.md); flush() before anyone else writes or the sink dies
+    __device__ __forceinline__ XSink() : dst(nullptr), n(0), acc(0), k(0) {}
+    __device__ __forceinline__ void put(u8 c) {
+        if (dst) {
+            if (k == 0 && ((uintptr_t)(dst + n) & 7)) dst[n] = c;   // head bytes up to the first 8-byte boundary
+            else {
+                acc |= (u64)c << (8 * k);
+                if (++k == 8) { *(u64*)(dst + n - 7) = acc; acc = 0; k = 0; }
+            }
+        }
+        n++;
+    }
+    __device__ __forceinline__ void flush() {
+        if (dst) for (u32 i = 0; i < k; i++) dst[n - k + i] = (u8)(acc >> (8 * i));
+        acc = 0;
+        k = 0;
+    }
     __device__ __forceinline__ void varint(u64 v) { while (v >= 0x80) { put((u8)(v | 0x80)); v >>= 7; } put((u8)v); }
     __device__ __forceinline__ void zigzag(i64 v) { varint(((u64)v << 1) ^ (u64)(v >> 63)); }
     __device__ __forceinline__ void copy(const u8* s, u64 len) {
         if (dst) {
+            flush();
             u8* d = dst + n;
             u64 i = 0;
             while (i < len && ((uintptr_t)(d + i) & 3)) { d[i] = s[i]; i++; }
@@ -992,6 +1010,19 @@ __device__ inline void enc_dod(XSink& s, u32 n, F val) {
     if (bw.nbits) s.put((u8)((bw.cur & 0xFF) << (8 - bw.nbits)));
 }
 
+// four consecutive scratch words behind one aligned 16-byte load
+struct XWin {
+    const u32* p;
+    const u32* at;   // aligned address held in `w` (nullptr = none)
+    uint4 w;
+    __device__ XWin() : p(nullptr), at(nullptr) {}
+    __device__ __forceinline__ u32 get(u32 i) {
+        const u32* a = (const u32*)((uintptr_t)(p + i) & ~(uintptr_t)15);
+        if (a != at) { w = *(const uint4*)a; at = a; }
+        switch ((u32)((p + i) - a)) { case 0: return w.x; case 1: return w.y; case 2: return w.z; default: return w.w; }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------- encode
 // First-use registers of one block (encoding/value_register.rs): order lists + inverse maps in scratch.
 struct XReg {
@@ -1331,21 +1362,22 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             s.copy(t.bytes + t.dkey_off[di.key0 + k], t.dkey_len[di.key0 + k]);
         }
     };
-    // stored deltas are 32-bit differences of i32 / small u32 values: sign-extend to the true delta
+    // stored deltas are 32-bit differences of i32 / small u32 values: sign-extend to the true delta.  The scratch
+    // columns are read through a four-value window (one 16-byte load per window: the encoders' run / literal scans
+    // are chains of dependent reads, 30 % of the stall samples in profiles/r2_ncu_expenc.md).
     auto w_opcol = [&](XSink& s, int col) {
+        XWin w;
         switch (col) {
-            case 0: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_cidx[i]; }, WrZigzag()); break;
-            case 1: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_prop[i]; }, WrZigzag()); break;
-            case 2: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(c_vt[i] & 0xFFu); }, WrByte()); break;
-            default: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_atoms[i]; }, WrVarint());
+            case 0: w.p = c_cidx; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)w.get(i); }, WrZigzag()); break;
+            case 1: w.p = c_prop; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)w.get(i); }, WrZigzag()); break;
+            case 2: w.p = c_vt; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(w.get(i) & 0xFFu); }, WrByte()); break;
+            default: w.p = c_atoms; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)w.get(i); }, WrVarint());
         }
     };
     auto w_delcol = [&](XSink& s, int col) {
-        switch (col) {
-            case 0: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_peer[i]; }, WrZigzag()); break;
-            case 1: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_ctr[i]; }, WrZigzag()); break;
-            default: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_len[i]; }, WrZigzag());
-        }
+        XWin w;
+        w.p = col == 0 ? d_peer : (col == 1 ? d_ctr : d_len);
+        enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)w.get(i); }, WrZigzag());
     };
     auto w_values = [&](XSink& s) {
         u32 op = 0;
@@ -1460,6 +1492,7 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         for (int c = 0; c < 3; c++) { s.varint(B.col_len[4 + c]); w_delcol(s, c); }
     }
     s.varint(B.sec_len[7]); w_values(s);
+    s.flush();
 }
 
 // thread per document: block offsets inside the blob, blob length (after encode pass 0)

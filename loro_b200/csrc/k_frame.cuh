@@ -75,10 +75,14 @@ __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restric
     else if (b[0] != 'l' || b[1] != 'o' || b[2] != 'r' || b[3] != 'o') code = LB_ERR(DOC_ERR_DECODE);
     else {
         u32 mode = ((u32)b[20] << 8) | b[21];
-        if (mode != 4) code = LB_ERR(DOC_ERR_MODE);
+        // the reference verifies the checksum of every mode it knows before looking further (encoding.rs:299-330), so a
+        // damaged snapshot is a checksum error; an intact FastSnapshot (mode 3) is a scope limit of this engine, not an
+        // unknown encoding
+        if (mode != 3 && mode != 4) code = LB_ERR(DOC_ERR_MODE);
         else {
             u32 expect = (u32)b[16] | ((u32)b[17] << 8) | ((u32)b[18] << 16) | ((u32)b[19] << 24);
             if (xxh32_dev(b + 20, n - 20, XX_SEED_LORO) != expect) code = LB_ERR(DOC_ERR_CHECKSUM);
+            else if (mode == 3) code = LB_ERR(DOC_ERR_UNSUPPORTED);
             else {
                 Cur c(b + 22, n - 22);
                 while (!c.empty()) {

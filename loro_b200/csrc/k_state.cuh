@@ -224,6 +224,18 @@ struct Emitter {
         u32 pl = t.pos_len[pos];
         for (u32 k = 0; k < pl; k++) { o.put((u8)HEX[pb[k] >> 4]); o.put((u8)HEX[pb[k] & 15]); }
     }
+    // n bytes of a thread-local buffer to global memory: single bytes up to the first 8-byte boundary, then whole words
+    __device__ static void copy_out(u8* dst, const u8* src, u32 n) {
+        u32 i = 0;
+        while (i < n && ((uintptr_t)(dst + i) & 7)) { dst[i] = src[i]; i++; }
+        for (; i + 8 <= n; i += 8) {
+            u64 v = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) v |= (u64)src[i + q] << (8 * q);
+            *(u64*)(dst + i) = v;
+        }
+        for (; i < n; i++) dst[i] = src[i];
+    }
     // every node of the hierarchy written by its own lane at the offsets k_tree_build laid out (all meta maps empty);
     // the caller has printed '[' and prints ']'
     __device__ void emit_tree_parallel(u32 cidx) {
@@ -235,15 +247,23 @@ struct Emitter {
             const u64 start = out.n - 1;   // the container's '['
             for (u32 a = (u32)lane; a < A; a += 32) {
                 if (t.tn_root[tb + a] != slot) continue;
+                // the node's two pieces are composed in a thread-local buffer and leave as 8-byte stores: byte stores
+                // of 32 lanes into 32 different sectors were the whole cost of this kernel (6.5 GB of JSON in config C5)
+                u8 buf[216];
+                const u32 pos = t.tr_rec[tr_lo + t.tn_move[tb + a]].z;
+                const bool direct = t.pos_len[pos] > 32;     // an unusually long fractional index: write in place
                 Sink w;
-                w.dst = out.dst; w.flags = 0; w.wr = true;
-                w.n = start + t.tn_aopen[tb + a];
+                w.flags = 0; w.wr = true;
+                w.dst = direct ? out.dst + start + t.tn_aopen[tb + a] : buf;
+                w.n = 0;
                 u32 sib = t.tn_sib[tb + a], par = t.tn_parent[tb + a];
                 if (sib) w.put(',');
                 w.puts_("{\"children\":[");
-                w.n = start + t.tn_aclose[tb + a];
+                if (!direct) copy_out(out.dst + start + t.tn_aopen[tb + a], buf, (u32)w.n);
+                w.dst = direct ? out.dst + start + t.tn_aclose[tb + a] : buf;
+                w.n = 0;
                 w.puts_("],\"fractional_index\":\"");
-                put_fractional_index(w, t.tr_rec[tr_lo + t.tn_move[tb + a]].z);
+                put_fractional_index(w, pos);
                 w.puts_("\",\"id\":");
                 put_tree_id_to(w, a);
                 w.puts_(",\"index\":");
@@ -251,6 +271,7 @@ struct Emitter {
                 w.puts_(",\"meta\":{},\"parent\":");
                 if (par == TREE_ROOT) w.puts_("null"); else put_tree_id_to(w, par);
                 w.put('}');
+                if (!direct) copy_out(out.dst + start + t.tn_aclose[tb + a], buf, (u32)w.n);
             }
             __syncwarp();
         }

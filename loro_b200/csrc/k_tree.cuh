@@ -47,7 +47,17 @@ struct TreeTables {
 };
 __device__ __forceinline__ u32* tree_sub(const TreeTables& t, const DocInfo& di) { return (u32*)(t.ns_key + di.tree0); }
 
-__device__ __forceinline__ u32 dec_digits(u64 v) { u32 k = 1; while (v >= 10) { v /= 10; k++; } return k; }
+// decimal digits of v: compare against powers of ten around the estimate from the bit length (no 64-bit divisions)
+__device__ __forceinline__ u32 dec_digits(u64 v) {
+    const u64 P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+                         10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull,
+                         1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
+                         10000000000000000000ull};
+    if (v == 0) return 1;
+    u32 bits = 64u - (u32)__clzll((long long)v);
+    u32 k = (bits * 1233u) >> 12;          // floor(log10(2^bits)) : k or k + 1 digits
+    return k + (v >= P10[k] ? 1u : 0u);
+}
 // "<counter>@<peer>" with its quotes
 __device__ inline u32 tree_id_len(const DocPeer* dpeer, u32 P, u32 a) {
     u32 p = 0;
@@ -117,7 +127,27 @@ __device__ inline int pos_cmp(const TreeTables& t, u32 pa, u32 pb) {
     return la < lb ? -1 : (la > lb ? 1 : 0);
 }
 
-__global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
+// node -> parent links of the document the warp works on: in shared memory (16-bit) when the document has fewer than
+// TREE_S_NODES atoms -- the apply and the layout passes are chains of dependent parent look-ups, an order of magnitude
+// shorter from shared memory than from L2 (profiles/r2_ncu_tree.md: 45 % of the stalls) -- else in the global table
+#define TREE_WARPS 4
+#define TREE_S_NODES 10240
+struct ParentArr {
+    u16* s;      // nullptr: global only
+    u32* g;
+    __device__ __forceinline__ u32 get(u32 i) const {
+        if (!s) return g[i];
+        u16 v = s[i];
+        return v >= 0xFFFDu ? 0xFFFF0000u | v : (u32)v;
+    }
+    __device__ __forceinline__ void set(u32 i, u32 v) const { if (s) s[i] = (u16)v; else g[i] = v; }   // (special values keep their low 16 bits)
+};
+__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
+#ifdef LB_SIMT_EMU
+    LB_DYN_SMEM(u16, tree_smem);
+#else
+    extern __shared__ __align__(16) u16 tree_smem[];
+#endif
     u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
@@ -125,9 +155,11 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
     if (di.code != DOC_OK || !di.has_tree) return;
     const u32 A = (u32)di.atom_total, C = di.C;
     const u64 base = di.tree0;
-    u32* parent = t.tn_parent + base;
+    ParentArr parent;
+    parent.g = t.tn_parent + base;
+    parent.s = A <= TREE_S_NODES ? tree_smem + (threadIdx.x >> 5) * TREE_S_NODES : nullptr;
     u32* move = t.tn_move + base;
-    for (u32 i = lane; i < A + C; i += 32) { parent[i] = TREE_UNEXIST; t.tn_cnt[base + i] = 0; t.tn_base[base + i] = 0; }
+    for (u32 i = lane; i < A + C; i += 32) { if (i < A) parent.set(i, TREE_UNEXIST); t.tn_cnt[base + i] = 0; t.tn_base[base + i] = 0; }
     // ---- the document's tree ops (contiguous: blocks of a document are) in (lamport, peer) order.
     // Lamports are recomputed from the dependencies, so they are smaller than the document's atom count: a counting
     // sort over the lamport (tn_cnt / tn_base double as histogram and offsets) followed by a per-lamport fix of the
@@ -200,18 +232,18 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
             u32 np = __shfl_sync(LB_FULL, rec.y, (int)s);
             u32 ti = __shfl_sync(LB_FULL, ti_l, (int)s);
             bool effected = true;
-            if (np < TREE_UNEXIST && parent[target] != TREE_UNEXIST) {
+            if (np < TREE_UNEXIST && parent.get(target) != TREE_UNEXIST) {
                 // is the target an ancestor of (or equal to) the new parent?  (tree.rs:477-508, tree_state.rs:727-747)
                 u32 cur = np;
                 for (u32 guard = 0; guard <= A; guard++) {
                     if (cur == target) { effected = false; break; }
-                    u32 pp = parent[cur];
+                    u32 pp = parent.get(cur);
                     if (pp >= TREE_UNEXIST) break;
                     cur = pp;
                 }
             }
             __syncwarp();
-            if (effected && lane == 0) { parent[target] = np; move[target] = ti; }
+            if (effected && lane == 0) { parent.set(target, np); move[target] = ti; }
             __syncwarp();
         }
     }
@@ -225,7 +257,7 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
     for (u32 i = lane; i < A + C; i += 32) { cnt[i] = 0; fill[i] = 0; }
     __syncwarp();
     auto slot_of = [&](u32 a) -> u32 {
-        u32 p = parent[a];
+        u32 p = parent.get(a);
         if (p == TREE_UNEXIST || p == TREE_DELETED) return TREE_UNEXIST;
         return p == TREE_ROOT ? A + t.op_cidx[t.tr_rec[tr_lo + move[a]].w] : p;
     };
@@ -302,7 +334,7 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
         const DocContainer& dc = t.dcont[di.cid0 + c];
         if (dc.is_root || dc.type != CT_MAP || dc.key_or_peer >= P) continue;
         const DocPeer& dp = dpeer[dc.key_or_peer];
-        if (dc.counter >= 0 && dc.counter < dp.end_counter && parent[dp.atom_base + (u32)dc.counter] != TREE_UNEXIST) has_meta = true;
+        if (dc.counter >= 0 && dc.counter < dp.end_counter && parent.get(dp.atom_base + (u32)dc.counter) != TREE_UNEXIST) has_meta = true;
     }
     has_meta = __any_sync(LB_FULL, has_meta);
     u32* sub = (u32*)nkey;
@@ -313,11 +345,11 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
     // alive nodes, their own bytes added to every ancestor and to the root slot
     for (u32 a = lane; a < A; a += 32) {
         u32 r = TREE_UNEXIST;
-        u32 p = parent[a];
+        u32 p = parent.get(a);
         if (p != TREE_UNEXIST && p != TREE_DELETED) {
             u32 cur = a;
             for (u32 guard = 0; guard <= A; guard++) {
-                u32 pp = parent[cur];
+                u32 pp = parent.get(cur);
                 if (pp >= TREE_UNEXIST) { if (pp == TREE_ROOT) r = A + t.op_cidx[t.tr_rec[tr_lo + move[cur]].w]; break; }
                 cur = pp;
             }
@@ -329,7 +361,7 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
         u32 cur = a;
         for (u32 guard = 0; guard <= A; guard++) {
             atomicAdd(&sub[cur], own);
-            u32 pp = parent[cur];
+            u32 pp = parent.get(cur);
             if (pp >= TREE_UNEXIST) break;
             cur = pp;
         }
@@ -347,15 +379,19 @@ __global__ void k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables 
         u32 o = 1, cur = a;   // 1 = the container's '['
         for (u32 guard = 0; guard <= A; guard++) {
             o += rel[cur];
-            u32 pp = parent[cur];
+            u32 pp = parent.get(cur);
             if (pp >= TREE_UNEXIST) break;
             o += tree_open_len(t.tn_sib[base + pp]);
             cur = pp;
         }
         u32 sib = t.tn_sib[base + a];
-        u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, parent[a], sib, t.pos_len[t.tr_rec[tr_lo + move[a]].z]);
+        u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, parent.get(a), sib, t.pos_len[t.tr_rec[tr_lo + move[a]].z]);
         t.tn_aopen[base + a] = o;
         t.tn_aclose[base + a] = o + tree_open_len(sib) + (sub[a] - own);
+    }
+    if (parent.s) {   // the JSON walk reads the links from the global table
+        __syncwarp();
+        for (u32 i = lane; i < A; i += 32) parent.g[i] = parent.get(i);
     }
     if (lane == 0) docs[d].has_tree = has_meta ? 1u : 3u;   // bit1: the lane-parallel JSON layout is valid
 }

@@ -21,7 +21,7 @@ def check_batch_against_oracle(blobs, lib_path=None, expect_json=None):
         st = batch.status(i)
         if ocode:
             # oracle codes: 1 short, 2 magic, 3 checksum, 4 mode, 10 decode, 11 snapshot mode
-            want = {1: 1, 2: 1, 3: 2, 4: 3, 10: (1, 4), 11: 3}[ocode]
+            want = {1: 1, 2: 1, 3: 2, 4: 3, 10: (1, 4), 11: 5}[ocode]
             assert st.code == want or (isinstance(want, tuple) and st.code in want), (i, st, ocode)
             continue
         assert st.code == 0, (i, st)

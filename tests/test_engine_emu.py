@@ -336,3 +336,24 @@ def test_partially_known_changes_are_trimmed(seed):
         assert bt.export_updates(0) == ref.export_updates()
         frm = {p: c // 2 for p, c in ref.oplog_vv().items()}
         assert bt.export_updates(0, frm) == ref.export_updates(frm)
+
+
+def test_snapshot_blobs_and_unknown_modes():
+    """Header checks in the reference's order (encoding.rs:299-330): the checksum of a known mode is verified first, an
+    intact FastSnapshot (mode 3) is reported as outside this path (code 5), an unknown mode as incompatible (code 3)."""
+    import struct
+    import loro_b200
+    a = OracleDoc(1)
+    a.text_insert(a.get_text("t"), 0, "abc")
+    good = a.export_updates()
+
+    def with_mode(blob, mode, reseal=True):
+        b = bytearray(blob)
+        b[20], b[21] = mode >> 8, mode & 255
+        if reseal:
+            h = oracle.i64s(oracle.codec("xxh32", bytes(b[20:]), 0x4F524F4C))[0] & 0xFFFFFFFF
+            b[16:20] = struct.pack("<I", h)
+        return bytes(b)
+    snap_ok, snap_bad, future = with_mode(good, 3), with_mode(good, 3, reseal=False), with_mode(good, 9)
+    b = loro_b200.import_batch([snap_ok, snap_bad, future, good], lib_path=EMU)
+    assert [b.status(i).code for i in range(4)] == [5, 2, 3, 0]
