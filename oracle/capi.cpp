@@ -413,7 +413,18 @@ int lo_codec(const char* op, const uint8_t* in, size_t n, int64_t arg, uint8_t**
         Reader r(in, n);
         Writer w;
         std::vector<int64_t> vals;
-        if (name == "f64_json") {   // serde_json text of a double (doc.hpp json_f64): checker for the device formatter
+        if (name == "str_arena_gens") {   // generation of the string arena buffer after each allocation (doc.hpp alloc_str)
+            Doc d(1);
+            std::vector<int64_t> lens = rd_i64s(in, n);
+            for (int64_t l : lens) {
+                Op op;
+                op.text.assign((size_t)l, 'x');
+                op.unicode_len = (uint32_t)l;
+                d.alloc_str(op);
+                vals.push_back(op.arena_gen);
+            }
+            *out = dup_bytes(wr_i64s(vals), len);
+        } else if (name == "f64_json") {   // serde_json text of a double (doc.hpp json_f64): checker for the device formatter
             double d;
             std::memcpy(&d, in, 8);
             std::string o;

@@ -6,6 +6,7 @@
   README.md:75-120                                   two-doc sync example
   crates/loro/tests/issue.rs:257-264                 duplicate import is a no-op
 """
+import os
 import random
 
 import pytest
@@ -312,3 +313,36 @@ def test_tree_random_sites_converge(seed):
     again.import_(blob)
     assert again.json_text() == js and again.oplog_vv() == vv
     assert again.export_updates() == blob   # re-export of an imported full history is byte-identical
+
+
+def test_string_arena_growth_model_against_golden_blocks(golden_dir):
+    """Whether two adjacent text inserts re-merge depends on the append-only string buffer of the importing document
+    (a new buffer generation whenever the cumulative size outgrows the capacity, doubling from 32: arena/str_arena.rs +
+    append-only-bytes 0.1.12, not in the tree).  Two peers of the in-tree snapshot `issue_import.base64.txt` typed into
+    otherwise idle documents, so their blocks show where the reference's own buffer switched generation: adjacent,
+    position-contiguous inserts left UNMERGED at cumulative sizes 32 and 64 (peer 8945398470050628706) and across 64
+    (peer 14116964593806747582).  The oracle's model (doc.hpp alloc_str) predicts exactly those cuts."""
+    import base64
+    import json
+    blocks = json.load(open(os.path.join(golden_dir, "snapshot_blocks.json")))
+    seqs = {}
+    for e in blocks:
+        if not e["source"].startswith("issue_import"):
+            continue
+        d = oracle.decode_dump(base64.b64decode(e["block"]), raw_block=True)
+        for b in d.get("blocks", [d] if "changes" in d else []):
+            for ch in b["changes"]:
+                for op in ch["ops"]:
+                    if op["kind"] == "insert_text":
+                        seqs.setdefault(ch["peer"], []).append((op["counter"], op["prop"], op["len"], len(op["text"].encode())))
+    for peer, cuts in (("8945398470050628706", {32, 64}), ("14116964593806747582", {34})):
+        ops = sorted(seqs[peer])
+        gens = oracle.i64s(oracle.codec("str_arena_gens", oracle.pack_i64s([o[3] for o in ops])))
+        cum, seen = 0, set()
+        for (a, ga), (b, gb) in zip(zip(ops, gens), zip(ops[1:], gens[1:])):
+            cum += a[3]
+            adjacent = b[0] == a[0] + a[2] and b[1] == a[1] + a[2]     # counter- and position-contiguous: mergeable but for the buffer
+            if adjacent:
+                assert ga != gb, (peer, cum)      # the reference left them apart: the model must put them in different buffers
+                seen.add(cum)
+        assert seen == cuts, (peer, seen)
