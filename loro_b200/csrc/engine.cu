@@ -6,6 +6,7 @@
 #include "../../include/loro_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -188,6 +189,8 @@ namespace {
 const int TPB = 128;
 inline unsigned nblk(u64 n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
+// LB_PHASE_TRACE=1: host wall clock between named points (each one synchronises the stream: diagnosis only)
+void trace_point(lb_batch* b, const char* name);
 void mark(lb_batch* b) {
     if (b->n_ev < 16) CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));
 }
@@ -198,6 +201,16 @@ T d2h_one(lb_batch* b, const T* src) {
     CK(cudaMemcpyAsync(&v, src, sizeof(T), cudaMemcpyDeviceToHost, b->dev.stream));
     CK(cudaStreamSynchronize(b->dev.stream));
     return v;
+}
+
+void trace_point(lb_batch* b, const char* name) {
+    static const bool on = getenv("LB_PHASE_TRACE") != nullptr;
+    if (!on) return;
+    static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(b->dev.stream);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trace] %-24s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
 }
 
 void run_scans(lb_batch* b, std::vector<ScanJob> jobs) {
@@ -234,7 +247,7 @@ void pipeline(lb_batch* b) {
     u32* d_doc_blob0 = dv.alloc<u32>(D + 2);
     CK(cudaMemcpyAsync(d_blob_doc, b->blob_doc.data(), sizeof(u32) * Q, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_doc_blob0, b->doc_blob0.data(), sizeof(u32) * (D + 1), cudaMemcpyHostToDevice, st));
-    LB_LAUNCH(k_frame_count, nblk(Q), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_code, d_blob_nblocks);
+    LB_LAUNCH(k_frame_count, nblk((u64)Q * 32, 128), 128, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_code, d_blob_nblocks);
     run_scans(b, {ScanJob{(const u8*)d_blob_nblocks, (u8*)d_blob_block0, 4, 8, Q}});
     LB_LAUNCH(k_frame_docs, nblk(D), TPB, 0, st, D, d_doc_blob0, d_blob_code, d_blob_block0, b->d_docs);
     tm.kernel_launches += 2;
@@ -437,9 +450,12 @@ void pipeline(lb_batch* b) {
         const size_t tree_smem = (size_t)TREE_WARPS * TREE_S_NODES * sizeof(u16);
 #ifndef LB_SIMT_EMU
         static bool tree_attr_set = false;
-        if (!tree_attr_set) { CK(cudaFuncSetAttribute(k_tree_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem)); tree_attr_set = true; }
+        if (!tree_attr_set) { CK(cudaFuncSetAttribute(k_tree_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem)); tree_attr_set = true; }
 #endif
-        LB_LAUNCH(k_tree_build, nblk((u64)D * 32, 32 * TREE_WARPS), 32 * TREE_WARPS, tree_smem, st, b->d_docs, D, tt);
+        LB_LAUNCH(k_tree_sort, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
+        LB_LAUNCH(k_tree_apply, nblk((u64)D * 32, 32 * TREE_WARPS), 32 * TREE_WARPS, tree_smem, st, b->d_docs, D, tt);
+        LB_LAUNCH(k_tree_layout, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
+        tm.kernel_launches += 2;
         tm.kernel_launches += 2;
     }
     mark(b);  // [5b] trees done
@@ -469,7 +485,7 @@ void pipeline(lb_batch* b) {
         LB_LAUNCH(k_json, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, stt, b->d_json, 1);
         tm.kernel_launches += 1;
     }
-    LB_LAUNCH(k_doc_hash, nblk(D), TPB, 0, st, b->d_docs, D, (const u8*)b->d_json, d_acc);
+    LB_LAUNCH(k_doc_hash, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, (const u8*)b->d_json, d_acc);
     tm.kernel_launches += 1;
     mark(b);  // [6] materialise done
     if (b->eager_json && b->json_total && !(b->flags & LB_FLAG_NO_JSON)) {
@@ -487,6 +503,7 @@ void pipeline(lb_batch* b) {
     }
     // ------------------------------------------------------------ phase 7: re-export (all_updates per document)
     if (b->flags & LB_FLAG_EXPORT) {
+        trace_point(b, "before export");
         ExportTables xt;
         memset(&xt, 0, sizeof(xt));
         xt.bytes = b->d_bytes; xt.blocks = blk; xt.dpeer = b->d_dpeer; xt.dcont = dcont;
@@ -526,12 +543,15 @@ void pipeline(lb_batch* b) {
         xt.fc_from = dv.alloc<u32>(SEGCAP); xt.fc_atoms = dv.alloc<u32>(SEGCAP); xt.fc_nrows = dv.alloc<u32>(SEGCAP);
         xt.fc_ndel = dv.alloc<u32>(SEGCAP); xt.fc_block = dv.alloc<u8>(SEGCAP); xt.fc_skip = dv.alloc<u32>(SEGCAP, true);
         xt.only_doc = 0xFFFFFFFFu; xt.from_ctr = nullptr;
+        trace_point(b, "export allocs");
         LB_LAUNCH(k_exp_init, nblk(D), TPB, 0, st, b->d_docs, D, xt);
         if (NTR) { LB_LAUNCH(k_exp_posrank, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, xt); tm.kernel_launches += 1; }
         if (NCH) LB_LAUNCH(k_exp_arena, nblk(NCH, 64), 64, 0, st, NCH, xt, b->d_docs);
         run_scans(b, {ScanJob{(const u8*)xt.ch_aval, (u8*)xt.ch_aval0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_astr, (u8*)xt.ch_astr0, 4, 8, NCH}});
+        trace_point(b, "posrank+arena");
         if (NCH) LB_LAUNCH(k_exp_changes, nblk(NCH, 64), 64, 0, st, b->d_docs, NCH, xt, 0);
         tm.kernel_launches += 3;
+        trace_point(b, "changes pass 0");
         run_scans(b, {ScanJob{(const u8*)xt.ch_novf, (u8*)xt.ch_seg0, 4, 8, NCH}, ScanJob{(const u8*)xt.ch_syn, (u8*)xt.ch_syn0, 4, 8, NCH}});
         u64 NOVF = d2h_one(b, xt.ch_seg0 + NCH);
         u64 NSYN = d2h_one(b, xt.ch_syn0 + NCH);
@@ -562,17 +582,23 @@ void pipeline(lb_batch* b) {
         u64 NOB = xtot.ob0, NSCR = xtot.scratch0;
         XBlock* xb = dv.alloc<XBlock>(NOB + 1);
         u32* xscratch = dv.alloc<u32>(NSCR + 1);
+        trace_point(b, "store+sizes");
         LB_LAUNCH(k_exp_list, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb);
         if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, (u8*)nullptr, 0);
         LB_LAUNCH(k_exp_layout, nblk(D), TPB, 0, st, b->d_docs, D, xt, xb, d_tmp_a);
         tm.kernel_launches += 3;
+        trace_point(b, "encode pass 0");
         run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)xt.xdoc + offsetof(XDoc, exp_off), 4, sizeof(XDoc), D}});
         u64 XT = d2h_one(b, &xt.xdoc[D].exp_off);
         b->export_total = XT;
+        trace_point(b, "layout scan + size d2h");
         b->d_export = dv.alloc<u8>(XT + 16, true);
+        trace_point(b, "export buffer alloc+zero");
         if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, b->d_export, 1);
-        LB_LAUNCH(k_exp_finish, nblk(D), TPB, 0, st, b->d_docs, D, xt, b->d_export);
+        trace_point(b, "encode pass 1 kernel");
+        LB_LAUNCH(k_exp_finish, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, xt, b->d_export);
         tm.kernel_launches += 2;
+        trace_point(b, "encode pass 1");
         tm.export_bytes = XT;
         b->xt = xt;
         b->have_xt = true;
@@ -765,7 +791,7 @@ lb_status export_from(lb_batch* b, size_t doc, const lb_id_span* from, size_t n_
         u64 XT = d2h_one(b, &xdoc[D].exp_off);
         u8* d_out = dv.alloc<u8>(XT + 16, true);
         if (NOB) LB_LAUNCH(k_exp_encode, nblk(NOB, 64), 64, 0, st, b->d_docs, NOB, xt, xb, xscratch, d_out, 1);
-        LB_LAUNCH(k_exp_finish, nblk(D), TPB, 0, st, b->d_docs, D, xt, d_out);
+        LB_LAUNCH(k_exp_finish, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, xt, d_out);
         XDoc x = d2h_one(b, xdoc + doc);
         lb_status rc = LB_OK;
         if ((x.flags & 1) || x.exp_len == 0) { g_last_error = "document uses features the export phase does not cover"; rc = LB_ERR_UNSUPPORTED; }

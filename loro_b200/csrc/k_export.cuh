@@ -106,30 +106,15 @@ struct ExportTables {
 // ---------------------------------------------------------------------------------------------- byte sink
 struct XSink {
     u8* dst;   // nullptr = counting
-    u64 n;     // bytes produced (the last `k` of them still sit in `acc` when writing)
-    u64 acc;   // up to eight bytes on their way out as ONE store (single-byte stores were a third of the encoder's
-    u32 k;     //   instructions in profiles/r2_ncu_expenc.md); flush() before anyone else writes or the sink dies
-    __device__ __forceinline__ XSink() : dst(nullptr), n(0), acc(0), k(0) {}
-    __device__ __forceinline__ void put(u8 c) {
-        if (dst) {
-            if (k == 0 && ((uintptr_t)(dst + n) & 7)) dst[n] = c;   // head bytes up to the first 8-byte boundary
-            else {
-                acc |= (u64)c << (8 * k);
-                if (++k == 8) { *(u64*)(dst + n - 7) = acc; acc = 0; k = 0; }
-            }
-        }
-        n++;
-    }
-    __device__ __forceinline__ void flush() {
-        if (dst) for (u32 i = 0; i < k; i++) dst[n - k + i] = (u8)(acc >> (8 * i));
-        acc = 0;
-        k = 0;
-    }
+    u64 n;
+    // (measured on B200 and rejected: collecting eight bytes per store and reading the scratch columns through a
+    //  four-word window made the encoder 20 % SLOWER -- it is bound by dependent-load latency at 25 % occupancy, and
+    //  both add instructions and registers to every byte)
+    __device__ __forceinline__ void put(u8 c) { if (dst) dst[n] = c; n++; }
     __device__ __forceinline__ void varint(u64 v) { while (v >= 0x80) { put((u8)(v | 0x80)); v >>= 7; } put((u8)v); }
     __device__ __forceinline__ void zigzag(i64 v) { varint(((u64)v << 1) ^ (u64)(v >> 63)); }
     __device__ __forceinline__ void copy(const u8* s, u64 len) {
         if (dst) {
-            flush();
             u8* d = dst + n;
             u64 i = 0;
             while (i < len && ((uintptr_t)(d + i) & 3)) { d[i] = s[i]; i++; }
@@ -1010,19 +995,6 @@ __device__ inline void enc_dod(XSink& s, u32 n, F val) {
     if (bw.nbits) s.put((u8)((bw.cur & 0xFF) << (8 - bw.nbits)));
 }
 
-// four consecutive scratch words behind one aligned 16-byte load
-struct XWin {
-    const u32* p;
-    const u32* at;   // aligned address held in `w` (nullptr = none)
-    uint4 w;
-    __device__ XWin() : p(nullptr), at(nullptr) {}
-    __device__ __forceinline__ u32 get(u32 i) {
-        const u32* a = (const u32*)((uintptr_t)(p + i) & ~(uintptr_t)15);
-        if (a != at) { w = *(const uint4*)a; at = a; }
-        switch ((u32)((p + i) - a)) { case 0: return w.x; case 1: return w.y; case 2: return w.z; default: return w.w; }
-    }
-};
-
 // ---------------------------------------------------------------------------------------------- encode
 // First-use registers of one block (encoding/value_register.rs): order lists + inverse maps in scratch.
 struct XReg {
@@ -1362,22 +1334,21 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
             s.copy(t.bytes + t.dkey_off[di.key0 + k], t.dkey_len[di.key0 + k]);
         }
     };
-    // stored deltas are 32-bit differences of i32 / small u32 values: sign-extend to the true delta.  The scratch
-    // columns are read through a four-value window (one 16-byte load per window: the encoders' run / literal scans
-    // are chains of dependent reads, 30 % of the stall samples in profiles/r2_ncu_expenc.md).
+    // stored deltas are 32-bit differences of i32 / small u32 values: sign-extend to the true delta
     auto w_opcol = [&](XSink& s, int col) {
-        XWin w;
         switch (col) {
-            case 0: w.p = c_cidx; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)w.get(i); }, WrZigzag()); break;
-            case 1: w.p = c_prop; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)w.get(i); }, WrZigzag()); break;
-            case 2: w.p = c_vt; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(w.get(i) & 0xFFu); }, WrByte()); break;
-            default: w.p = c_atoms; enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)w.get(i); }, WrVarint());
+            case 0: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_cidx[i]; }, WrZigzag()); break;
+            case 1: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(i32)c_prop[i]; }, WrZigzag()); break;
+            case 2: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)(c_vt[i] & 0xFFu); }, WrByte()); break;
+            default: enc_anyrle(s, n_ops, [&](u32 i) -> i64 { return (i64)c_atoms[i]; }, WrVarint());
         }
     };
     auto w_delcol = [&](XSink& s, int col) {
-        XWin w;
-        w.p = col == 0 ? d_peer : (col == 1 ? d_ctr : d_len);
-        enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)w.get(i); }, WrZigzag());
+        switch (col) {
+            case 0: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_peer[i]; }, WrZigzag()); break;
+            case 1: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_ctr[i]; }, WrZigzag()); break;
+            default: enc_anyrle(s, n_del, [&](u32 i) -> i64 { return (i64)(i32)d_len[i]; }, WrZigzag());
+        }
     };
     auto w_values = [&](XSink& s) {
         u32 op = 0;
@@ -1492,7 +1463,6 @@ __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, Exp
         for (int c = 0; c < 3; c++) { s.varint(B.col_len[4 + c]); w_delcol(s, c); }
     }
     s.varint(B.sec_len[7]); w_values(s);
-    s.flush();
 }
 
 // thread per document: block offsets inside the blob, blob length (after encode pass 0)
@@ -1517,14 +1487,18 @@ __global__ void k_exp_layout(const DocInfo* __restrict__ docs, u32 n_docs, Expor
 
 // thread per document: header, mode, checksum (encoding.rs:397-416)
 __global__ void k_exp_finish(const DocInfo* __restrict__ docs, u32 n_docs, ExportTables t, u8* __restrict__ out) {
-    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // warp per document: the checksum walks the whole blob
+    int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
     const XDoc& x = t.xdoc[d];
     if (x.exp_len == 0) return;
     u8* b = out + x.exp_off;
-    b[0] = 'l'; b[1] = 'o'; b[2] = 'r'; b[3] = 'o';
-    for (int i = 4; i < 20; i++) b[i] = 0;
-    b[20] = 0; b[21] = 4;   // FastUpdates, big endian
-    u32 h = xxh32_dev(b + 20, x.exp_len - 20, XX_SEED_LORO);
-    b[16] = (u8)h; b[17] = (u8)(h >> 8); b[18] = (u8)(h >> 16); b[19] = (u8)(h >> 24);
+    if (lane == 0) {
+        b[0] = 'l'; b[1] = 'o'; b[2] = 'r'; b[3] = 'o';
+        for (int i = 4; i < 20; i++) b[i] = 0;
+        b[20] = 0; b[21] = 4;   // FastUpdates, big endian
+    }
+    __syncwarp();
+    u32 h = xxh32_warp(b + 20, x.exp_len - 20, XX_SEED_LORO, lane);
+    if (lane == 0) { b[16] = (u8)h; b[17] = (u8)(h >> 8); b[18] = (u8)(h >> 16); b[19] = (u8)(h >> 24); }
 }

@@ -13,11 +13,10 @@ __device__ __forceinline__ u32 ld32(const u8* p) {  // p is 4-byte aligned
     return *(const u32*)p;
 }
 
-__device__ u32 xxh32_dev(const u8* d, size_t len, u32 seed) {
-    size_t off = 0;
+// the digest once the stripes before `off` are folded into v1..v4 (off == 0: nothing folded yet)
+__device__ inline u32 xxh32_tail(const u8* d, size_t len, u32 seed, size_t off, u32 v1, u32 v2, u32 v3, u32 v4) {
     u32 h;
     if (len >= 16) {
-        u32 v1 = seed + XXP1 + XXP2, v2 = seed + XXP2, v3 = seed, v4 = seed - XXP1;
         size_t limit = len - 16;
         // 64-byte steps: 16 independent loads issued before the dependent multiply chains
         while (off + 64 <= len) {
@@ -60,12 +59,50 @@ __device__ u32 xxh32_dev(const u8* d, size_t len, u32 seed) {
     h ^= h >> 16;
     return h;
 }
+__device__ u32 xxh32_dev(const u8* d, size_t len, u32 seed) {
+    return xxh32_tail(d, len, seed, 0, seed + XXP1 + XXP2, seed + XXP2, seed, seed - XXP1);
+}
+// The same digest computed by a warp (every lane returns it).  The recurrence stays sequential -- four accumulators,
+// one step per 16-byte stripe -- but the bytes arrive as coalesced 128-byte loads: lane L holds words L, L+32, L+64,
+// L+96 of a 512-byte piece, i.e. component L&3 of stripes (L>>2) + 8k, and the lanes with (L&3) == c all run
+// accumulator c, fetching stripe s from lane ((s&7)<<2)|c by shuffle.  A thread walking a 600 KB document alone
+// waits for memory at every stripe; here the loads of the next piece are in flight while the chain runs.
+__device__ inline u32 xxh32_warp(const u8* d, size_t len, u32 seed, int lane) {
+    const int c = lane & 3;
+    u32 v = c == 0 ? seed + XXP1 + XXP2 : c == 1 ? seed + XXP2 : c == 2 ? seed : seed - XXP1;
+    size_t off = 0;
+    if (len >= 1024) {
+        u32 w0 = ld32(d + 4 * lane), w1 = ld32(d + 4 * (lane + 32)), w2 = ld32(d + 4 * (lane + 64)), w3 = ld32(d + 4 * (lane + 96));
+        while (off + 512 <= len) {
+            u32 n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+            if (off + 1024 <= len) {   // the next piece, before the chain of this one
+                const u8* q = d + off + 512;
+                n0 = ld32(q + 4 * lane); n1 = ld32(q + 4 * (lane + 32)); n2 = ld32(q + 4 * (lane + 64)); n3 = ld32(q + 4 * (lane + 96));
+            }
+#pragma unroll
+            for (int s = 0; s < 8; s++) v = rotl32(v + __shfl_sync(LB_FULL, w0, (s << 2) | c) * XXP2, 13) * XXP1;
+#pragma unroll
+            for (int s = 0; s < 8; s++) v = rotl32(v + __shfl_sync(LB_FULL, w1, (s << 2) | c) * XXP2, 13) * XXP1;
+#pragma unroll
+            for (int s = 0; s < 8; s++) v = rotl32(v + __shfl_sync(LB_FULL, w2, (s << 2) | c) * XXP2, 13) * XXP1;
+#pragma unroll
+            for (int s = 0; s < 8; s++) v = rotl32(v + __shfl_sync(LB_FULL, w3, (s << 2) | c) * XXP2, 13) * XXP1;
+            w0 = n0; w1 = n1; w2 = n2; w3 = n3;
+            off += 512;
+        }
+    }
+    u32 v1 = __shfl_sync(LB_FULL, v, 0), v2 = __shfl_sync(LB_FULL, v, 1), v3 = __shfl_sync(LB_FULL, v, 2), v4 = __shfl_sync(LB_FULL, v, 3);
+    u32 h = 0;
+    if (lane == 0) h = xxh32_tail(d, len, seed, off, v1, v2, v3, v4);
+    return __shfl_sync(LB_FULL, h, 0);
+}
 
-// thread per blob: validate header + checksum, count blocks.
+// warp per blob: validate header + checksum (warp-cooperative xxHash32), count blocks (lane 0).
 __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restrict__ offs,
                               const u32* __restrict__ lens, u32 n_blobs, u32* __restrict__ blob_code,
                               u32* __restrict__ blob_nblocks) {
-    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
     if (q >= n_blobs) return;
     const u8* b = bytes + offs[q];   // blob starts are 16-byte aligned
     size_t n = lens[q];
@@ -81,9 +118,9 @@ __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restric
         if (mode != 3 && mode != 4) code = LB_ERR(DOC_ERR_MODE);
         else {
             u32 expect = (u32)b[16] | ((u32)b[17] << 8) | ((u32)b[18] << 16) | ((u32)b[19] << 24);
-            if (xxh32_dev(b + 20, n - 20, XX_SEED_LORO) != expect) code = LB_ERR(DOC_ERR_CHECKSUM);
+            if (xxh32_warp(b + 20, n - 20, XX_SEED_LORO, lane) != expect) code = LB_ERR(DOC_ERR_CHECKSUM);
             else if (mode == 3) code = LB_ERR(DOC_ERR_UNSUPPORTED);
-            else {
+            else if (lane == 0) {
                 Cur c(b + 22, n - 22);
                 while (!c.empty()) {
                     u64 len = c.varint();
@@ -95,6 +132,7 @@ __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restric
             }
         }
     }
+    if (lane) return;
     blob_code[q] = code;
     blob_nblocks[q] = code == DOC_OK ? nb : 0;
 }

@@ -134,7 +134,7 @@ struct Emitter {
         return s;
     }
     // text of a Text container: concatenation of the visible runs; with many runs the lanes split them
-    __device__ void emit_text(u32 cidx) {
+    __device__ __noinline__ void emit_text(u32 cidx) {
         const DocContainer& dc = t.dcont[di.cid0 + cidx];
         out.put('"');
         if (dc.n_out >= 64) {
@@ -204,7 +204,7 @@ struct Emitter {
         }
     }
     // "<counter>@<peer>" of the node stored at atom `a` (ID display: loro-common/src/id.rs:22-26)
-    __device__ void put_tree_id_to(Sink& o, u32 a) {
+    __device__ __noinline__ void put_tree_id_to(Sink& o, u32 a) {
         u32 p = 0;
         for (u32 q = 0; q < di.P; q++) {
             const DocPeer& dp = t.dpeer[di.peer0 + q];
@@ -225,7 +225,7 @@ struct Emitter {
         for (u32 k = 0; k < pl; k++) { o.put((u8)HEX[pb[k] >> 4]); o.put((u8)HEX[pb[k] & 15]); }
     }
     // n bytes of a thread-local buffer to global memory: single bytes up to the first 8-byte boundary, then whole words
-    __device__ static void copy_out(u8* dst, const u8* src, u32 n) {
+    __device__ __noinline__ static void copy_out(u8* dst, const u8* src, u32 n) {
         u32 i = 0;
         while (i < n && ((uintptr_t)(dst + i) & 7)) { dst[i] = src[i]; i++; }
         for (; i + 8 <= n; i += 8) {
@@ -238,7 +238,7 @@ struct Emitter {
     }
     // every node of the hierarchy written by its own lane at the offsets k_tree_build laid out (all meta maps empty);
     // the caller has printed '[' and prints ']'
-    __device__ void emit_tree_parallel(u32 cidx) {
+    __device__ __noinline__ void emit_tree_parallel(u32 cidx) {
         const u64 tb = di.tree0;
         const u32 A = (u32)di.atom_total, slot = A + cidx;
         const u64 tr_lo = t.blocks[di.b0].tr0;
@@ -280,7 +280,7 @@ struct Emitter {
     // one step of the hierarchy walk (state/tree_state.rs:814-831 get_all_hierarchy_nodes_under + :1424-1452
     // TreeNodeWithChildren::into_value, keys in ascending order): no per-level frames -- the walk climbs back
     // through the parent links
-    __device__ void tree_step(Frame& f) {
+    __device__ __noinline__ void tree_step(Frame& f) {
         const u64 tb = di.tree0;
         const u32 A = (u32)di.atom_total;
         const u64 tr_lo = t.blocks[di.b0].tr0;
@@ -422,7 +422,7 @@ struct Emitter {
     }
 
     // ---- one warp per document: the runs of a scalar-only list are split over the lanes (sizes, scan, write)
-    __device__ bool coop_list(u32 cidx) {
+    __device__ __noinline__ bool coop_list(u32 cidx) {
         const DocContainer& dc = t.dcont[di.cid0 + cidx];
         u32 n_out = dc.n_out;
         if (n_out < 64) return false;
@@ -472,6 +472,44 @@ struct Emitter {
         return true;
     }
 
+    // one step of a nested LoroValue::Map (kept out of line: the walk is rare and register hungry)
+    __device__ __noinline__ void vmap_step(Frame& f) {
+            // LoroValue::Map inside a value (encoding/value.rs:1027-1036): entries = (key index into the block's
+            // key arena, value).  Printed in ascending key order like every object here; of two entries with
+            // the same key the later one wins.  Each step re-scans the entries for the next key.
+            const BlockInfo& vb = t.blocks[f.b];
+            const u8* best_val = nullptr;
+            u32 best = 0xFFFFFFFFu;
+            {
+                Cur c(f.p, (size_t)(1u << 30));
+                for (u32 i = 0; i < f.a && !c.err; i++) {
+                    u64 ki = c.varint();
+                    const u8* val = c.p;
+                    u8 k = c.get();
+                    skip_loro_value_content(c, k, nullptr);
+                    if (ki >= vb.n_keys) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
+                    const u8* kb = t.bytes + t.bkey_off[vb.key0 + ki];
+                    u32 kl = t.bkey_len[vb.key0 + ki];
+                    if (f.c != 0xFFFFFFFFu &&
+                        cmp_bytes(kb, kl, t.bytes + t.bkey_off[vb.key0 + f.c], t.bkey_len[vb.key0 + f.c]) <= 0) continue;
+                    if (best == 0xFFFFFFFFu ||
+                        cmp_bytes(kb, kl, t.bytes + t.bkey_off[vb.key0 + best], t.bkey_len[vb.key0 + best]) <= 0) { best = (u32)ki; best_val = val; }
+                }
+                if (c.err) err = LB_ERR(DOC_ERR_CORRUPT);
+            }
+            if (err) return;
+            if (best == 0xFFFFFFFFu) { out.put('}'); sp--; return; }
+            if (!f.first) out.put(',');
+            f.first = 0;
+            f.c = best;
+            out.put('"');
+            out.put_escaped(t.bytes + t.bkey_off[vb.key0 + best], t.bkey_len[vb.key0 + best]);
+            out.put('"');
+            out.put(':');
+            cur_blk = f.b;
+            const u8* p = best_val;
+            emit_value(&p, p + (1u << 30), f.id_peer, f.id_ctr);
+    }
     __device__ void run(void) {
         // root frame: iterate root containers in ascending name order
         out.put('{');
@@ -573,44 +611,7 @@ struct Emitter {
                     emit_value(&p, p + t.op_val_len[row], t.ch_peer[t.op_change[row]], t.op_counter[row]);
                     break;
                 }
-                case FK_VMAP: {
-                    // LoroValue::Map inside a value (encoding/value.rs:1027-1036): entries = (key index into the block's
-                    // key arena, value).  Printed in ascending key order like every object here; of two entries with
-                    // the same key the later one wins.  Each step re-scans the entries for the next key.
-                    const BlockInfo& vb = t.blocks[f.b];
-                    const u8* best_val = nullptr;
-                    u32 best = 0xFFFFFFFFu;
-                    {
-                        Cur c(f.p, (size_t)(1u << 30));
-                        for (u32 i = 0; i < f.a && !c.err; i++) {
-                            u64 ki = c.varint();
-                            const u8* val = c.p;
-                            u8 k = c.get();
-                            skip_loro_value_content(c, k, nullptr);
-                            if (ki >= vb.n_keys) { err = LB_ERR(DOC_ERR_CORRUPT); break; }
-                            const u8* kb = t.bytes + t.bkey_off[vb.key0 + ki];
-                            u32 kl = t.bkey_len[vb.key0 + ki];
-                            if (f.c != 0xFFFFFFFFu &&
-                                cmp_bytes(kb, kl, t.bytes + t.bkey_off[vb.key0 + f.c], t.bkey_len[vb.key0 + f.c]) <= 0) continue;
-                            if (best == 0xFFFFFFFFu ||
-                                cmp_bytes(kb, kl, t.bytes + t.bkey_off[vb.key0 + best], t.bkey_len[vb.key0 + best]) <= 0) { best = (u32)ki; best_val = val; }
-                        }
-                        if (c.err) err = LB_ERR(DOC_ERR_CORRUPT);
-                    }
-                    if (err) break;
-                    if (best == 0xFFFFFFFFu) { out.put('}'); sp--; break; }
-                    if (!f.first) out.put(',');
-                    f.first = 0;
-                    f.c = best;
-                    out.put('"');
-                    out.put_escaped(t.bytes + t.bkey_off[vb.key0 + best], t.bkey_len[vb.key0 + best]);
-                    out.put('"');
-                    out.put(':');
-                    cur_blk = f.b;
-                    const u8* p = best_val;
-                    emit_value(&p, p + (1u << 30), f.id_peer, f.id_ctr);
-                    break;
-                }
+                case FK_VMAP: vmap_step(f); break;
                 case FK_VLIST: {
                     if (f.a == 0) { out.put(']'); sp--; break; }
                     if (!f.first) out.put(',');
@@ -638,7 +639,7 @@ struct Emitter {
 };
 
 // pass = 0: count bytes into docs[d].json_len ; pass = 1: write at docs[d].json_off
-__global__ void k_json(DocInfo* __restrict__ docs, u32 n_docs, StateTables t, u8* __restrict__ json, int pass) {
+__global__ void __launch_bounds__(128, 8) k_json(DocInfo* __restrict__ docs, u32 n_docs, StateTables t, u8* __restrict__ json, int pass) {
     u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per document
     int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
@@ -666,15 +667,17 @@ __global__ void k_json_padlen(const DocInfo* __restrict__ docs, u32 n_docs, u32*
     padded[d] = (docs[d].json_len + 3u) & ~3u;
 }
 
-// thread per doc: order-independent state hash + counters
+// warp per doc: order-independent state hash + counters
 __global__ void k_doc_hash(const DocInfo* __restrict__ docs, u32 n_docs, const u8* __restrict__ json,
                            unsigned long long* __restrict__ acc /* [0]=hash xor, [1]=atom ops, [2]=pending, [3]=ok docs */) {
-    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
     const DocInfo& di = docs[d];
     if (di.code != DOC_OK) return;
     unsigned long long h = 0;
-    if (json) h = ((unsigned long long)xxh32_dev(json + di.json_off, di.json_len, 0) << 32) | di.json_len;
+    if (json) h = ((unsigned long long)xxh32_warp(json + di.json_off, di.json_len, 0, lane) << 32) | di.json_len;
+    if (lane) return;
     atomicXor(&acc[0], h);
     atomicAdd(&acc[1], (unsigned long long)di.atom_ops);
     atomicAdd(&acc[2], (unsigned long long)di.n_pending);

@@ -48,15 +48,15 @@ struct TreeTables {
 __device__ __forceinline__ u32* tree_sub(const TreeTables& t, const DocInfo& di) { return (u32*)(t.ns_key + di.tree0); }
 
 // decimal digits of v: compare against powers of ten around the estimate from the bit length (no 64-bit divisions)
-__device__ __forceinline__ u32 dec_digits(u64 v) {
-    const u64 P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+__device__ const u64 LB_P10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
                          10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull,
                          1000000000000000ull, 10000000000000000ull, 100000000000000000ull, 1000000000000000000ull,
                          10000000000000000000ull};
+__device__ __forceinline__ u32 dec_digits(u64 v) {
     if (v == 0) return 1;
     u32 bits = 64u - (u32)__clzll((long long)v);
     u32 k = (bits * 1233u) >> 12;          // floor(log10(2^bits)) : k or k + 1 digits
-    return k + (v >= P10[k] ? 1u : 0u);
+    return k + (v >= LB_P10[k] ? 1u : 0u);
 }
 // "<counter>@<peer>" with its quotes
 __device__ inline u32 tree_id_len(const DocPeer* dpeer, u32 P, u32 a) {
@@ -127,10 +127,14 @@ __device__ inline int pos_cmp(const TreeTables& t, u32 pa, u32 pb) {
     return la < lb ? -1 : (la > lb ? 1 : 0);
 }
 
-// node -> parent links of the document the warp works on: in shared memory (16-bit) when the document has fewer than
-// TREE_S_NODES atoms -- the apply and the layout passes are chains of dependent parent look-ups, an order of magnitude
-// shorter from shared memory than from L2 (profiles/r2_ncu_tree.md: 45 % of the stalls) -- else in the global table
-#define TREE_WARPS 4
+// Three kernels, one warp per document each:
+//   k_tree_sort    the document's tree ops in (lamport, peer) order (counting sort on global scratch)
+//   k_tree_apply   the sequential apply -- ONE chain of dependent parent look-ups per warp, so the links live in shared
+//                  memory (16-bit, documents with fewer than TREE_S_NODES atoms) and few warps per SM are enough
+//   k_tree_layout  sibling lists and the JSON layout: lane-parallel walks, best at full occupancy, links from global
+// (one kernel holding the shared-memory links through all three steps was measured: the low occupancy it forces on the
+//  lane-parallel steps cost more than the fast links gained -- 119 ms instead of 65 ms on config C5.)
+#define TREE_WARPS 2
 #define TREE_S_NODES 10240
 struct ParentArr {
     u16* s;      // nullptr: global only
@@ -142,12 +146,8 @@ struct ParentArr {
     }
     __device__ __forceinline__ void set(u32 i, u32 v) const { if (s) s[i] = (u16)v; else g[i] = v; }   // (special values keep their low 16 bits)
 };
-__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
-#ifdef LB_SIMT_EMU
-    LB_DYN_SMEM(u16, tree_smem);
-#else
-    extern __shared__ __align__(16) u16 tree_smem[];
-#endif
+
+__global__ void k_tree_sort(const DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
     u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
@@ -155,11 +155,7 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restr
     if (di.code != DOC_OK || !di.has_tree) return;
     const u32 A = (u32)di.atom_total, C = di.C;
     const u64 base = di.tree0;
-    ParentArr parent;
-    parent.g = t.tn_parent + base;
-    parent.s = A <= TREE_S_NODES ? tree_smem + (threadIdx.x >> 5) * TREE_S_NODES : nullptr;
-    u32* move = t.tn_move + base;
-    for (u32 i = lane; i < A + C; i += 32) { if (i < A) parent.set(i, TREE_UNEXIST); t.tn_cnt[base + i] = 0; t.tn_base[base + i] = 0; }
+    for (u32 i = lane; i < A + C; i += 32) { t.tn_cnt[base + i] = 0; t.tn_base[base + i] = 0; }
     // ---- the document's tree ops (contiguous: blocks of a document are) in (lamport, peer) order.
     // Lamports are recomputed from the dependencies, so they are smaller than the document's atom count: a counting
     // sort over the lamport (tn_cnt / tn_base double as histogram and offsets) followed by a per-lamport fix of the
@@ -216,6 +212,31 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restr
         }
     }
     __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_apply(const DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
+#ifdef LB_SIMT_EMU
+    LB_DYN_SMEM(u16, tree_smem);
+#else
+    extern __shared__ __align__(16) u16 tree_smem[];
+#endif
+    u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    if (di.code != DOC_OK || !di.has_tree) return;
+    const u32 A = (u32)di.atom_total;
+    const u64 base = di.tree0;
+    ParentArr parent;
+    parent.g = t.tn_parent + base;
+    parent.s = A <= TREE_S_NODES ? tree_smem + (threadIdx.x >> 5) * TREE_S_NODES : nullptr;
+    u32* move = t.tn_move + base;
+    for (u32 i = lane; i < A; i += 32) parent.set(i, TREE_UNEXIST);
+    const u64 tr_lo = t.blocks[di.b0].tr0, tr_hi = t.blocks[di.b1].tr0;
+    const u32 n_tr = (u32)(tr_hi - tr_lo);
+    const u64* skey = t.ts_key + tr_lo;
+    const u32* sval = t.ts_val + tr_lo;
+    __syncwarp();
     // ---- sequential apply, 32 records per round trip
     bool stop = false;
     for (u32 j0 = 0; j0 < n_tr && !stop; j0 += 32) {
@@ -248,26 +269,48 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restr
         }
     }
     __syncwarp();
+    __syncwarp();
+    if (parent.s) for (u32 i = lane; i < A; i += 32) parent.g[i] = parent.get(i);   // the later passes read the global table
+}
+
+__global__ void k_tree_layout(DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
+    u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    if (di.code != DOC_OK || !di.has_tree) return;
+    const u32 A = (u32)di.atom_total, C = di.C;
+    const u64 base = di.tree0;
+    const u32* parent = t.tn_parent + base;
+    const u32* move = t.tn_move + base;
+    u32* cnt = t.tn_cnt + base;
+    u32* off = t.tn_base + base;
+    const u64 tr_lo = t.blocks[di.b0].tr0, tr_hi = t.blocks[di.b1].tr0;
     // ---- sibling lists: nodes bucketed by parent slot (counting sort), every list ordered by NodePosition =
     // (fractional index bytes, lamport, peer); lists are short (fan-out), so a lane sorts a list by insertion with an
-    // 8-byte position prefix as the first comparison; a list longer than 32 goes through the warp network
+    // 8-byte position prefix as the first comparison; a list longer than 32 goes through the warp network.
+    // Every pass below touches a node a constant number of times: the passes that used to climb the parent chain per
+    // node (root of the tree, subtree sizes, offsets) made 80 scattered sector reads per node -- with a few GB of
+    // node tables resident across the chip they all went to HBM, and they were the kernel's whole time.
     u64* nkey = t.ns_key + base;
     u32* child = t.tn_child + base;
     u32* fill = t.tn_sib + base;
+    u32* root = t.tn_root + base;
+    u32* slot_tmp = t.tn_aclose + base;   // parent slot of a node until the lists are built
+    u32* plen_tmp = t.tn_aopen + base;    // length of the node's fractional index until the offsets are written
     for (u32 i = lane; i < A + C; i += 32) { cnt[i] = 0; fill[i] = 0; }
     __syncwarp();
-    auto slot_of = [&](u32 a) -> u32 {
-        u32 p = parent.get(a);
-        if (p == TREE_UNEXIST || p == TREE_DELETED) return TREE_UNEXIST;
-        return p == TREE_ROOT ? A + t.op_cidx[t.tr_rec[tr_lo + move[a]].w] : p;
-    };
     for (u32 a = lane; a < A; a += 32) {
-        u32 sl = slot_of(a);
-        if (sl == TREE_UNEXIST) continue;
+        u32 p = parent[a];
+        root[a] = TREE_UNEXIST;
+        if (p == TREE_UNEXIST || p == TREE_DELETED) { slot_tmp[a] = TREE_UNEXIST; continue; }
+        uint4 rec = t.tr_rec[tr_lo + move[a]];
+        u32 sl = p == TREE_ROOT ? A + t.op_cidx[rec.w] : p;
+        slot_tmp[a] = sl;
         atomicAdd(&cnt[sl], 1u);
-        u32 pz = t.tr_rec[tr_lo + move[a]].z;
-        const u8* pb = t.pos_pool + t.pos_off[pz];
-        u32 pl = t.pos_len[pz];
+        const u8* pb = t.pos_pool + t.pos_off[rec.z];
+        u32 pl = t.pos_len[rec.z];
+        plen_tmp[a] = pl;
         u64 pre = 0;
         for (u32 k = 0; k < 8; k++) pre = (pre << 8) | (k < pl ? pb[k] : 0u);
         nkey[a] = pre;
@@ -285,7 +328,7 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restr
     }
     __syncwarp();
     for (u32 a = lane; a < A; a += 32) {
-        u32 sl = slot_of(a);
+        u32 sl = slot_tmp[a];
         if (sl != TREE_UNEXIST) child[off[sl] + atomicAdd(&fill[sl], 1u)] = a;
     }
     __syncwarp();
@@ -334,64 +377,81 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_build(DocInfo* __restr
         const DocContainer& dc = t.dcont[di.cid0 + c];
         if (dc.is_root || dc.type != CT_MAP || dc.key_or_peer >= P) continue;
         const DocPeer& dp = dpeer[dc.key_or_peer];
-        if (dc.counter >= 0 && dc.counter < dp.end_counter && parent.get(dp.atom_base + (u32)dc.counter) != TREE_UNEXIST) has_meta = true;
+        if (dc.counter >= 0 && dc.counter < dp.end_counter && parent[dp.atom_base + (u32)dc.counter] != TREE_UNEXIST) has_meta = true;
     }
     has_meta = __any_sync(LB_FULL, has_meta);
     u32* sub = (u32*)nkey;
     u32* rel = sub + (A + C);
-    u32* root = t.tn_root + base;
-    for (u32 i = lane; i < A + C; i += 32) sub[i] = 0;
-    __syncwarp();
-    // alive nodes, their own bytes added to every ancestor and to the root slot
-    for (u32 a = lane; a < A; a += 32) {
-        u32 r = TREE_UNEXIST;
-        u32 p = parent.get(a);
-        if (p != TREE_UNEXIST && p != TREE_DELETED) {
-            u32 cur = a;
-            for (u32 guard = 0; guard <= A; guard++) {
-                u32 pp = parent.get(cur);
-                if (pp >= TREE_UNEXIST) { if (pp == TREE_ROOT) r = A + t.op_cidx[t.tr_rec[tr_lo + move[cur]].w]; break; }
-                cur = pp;
-            }
+    // alive nodes level by level (breadth first from the root slots; the children of a node stay adjacent and in
+    // sibling order): order[] / lvl[] live in the sort space of k_tree_sort, which the apply has finished with --
+    // a node has a create op, so there are at most n_tr nodes and n_tr levels
+    u32* order = t.ts_val + tr_lo;
+    u32* lvl = (u32*)(t.ts_key + tr_lo);
+    const u32 n_tr = (u32)(tr_hi - tr_lo);
+    u32 n_lvl = 0, lo = 0, hi = 0;
+    {   // level 0: the children of every root slot
+        u32 carry = 0;
+        for (u32 c0 = 0; c0 < C; c0 += 32) {
+            u32 c = c0 + (u32)lane;
+            u32 n = c < C ? cnt[A + c] : 0u;
+            int incl = warp_incl_scan((int)n, lane);
+            u32 w = carry + (u32)incl - n;
+            if (n) { u32 b0 = off[A + c]; for (u32 k = 0; k < n; k++) { u32 x = child[b0 + k]; order[w + k] = x; root[x] = A + c; } }
+            carry += (u32)__shfl_sync(LB_FULL, incl, 31);
         }
-        root[a] = r;
-        if (r == TREE_UNEXIST) continue;
-        u32 sib = t.tn_sib[base + a];
-        u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, p, sib, t.pos_len[t.tr_rec[tr_lo + move[a]].z]);
-        u32 cur = a;
-        for (u32 guard = 0; guard <= A; guard++) {
-            atomicAdd(&sub[cur], own);
-            u32 pp = parent.get(cur);
-            if (pp >= TREE_UNEXIST) break;
-            cur = pp;
-        }
-        atomicAdd(&sub[r], own);
+        hi = carry;
     }
     __syncwarp();
-    // offset of every child inside its parent's children list (lane per list)
-    for (u32 s = lane; s < A + C; s += 32) {
-        u32 n = t.tn_cnt[base + s], b0 = t.tn_base[base + s], acc = 0;
-        for (u32 i = 0; i < n; i++) { u32 c = child[b0 + i]; rel[c] = acc; acc += sub[c]; }
-    }
-    __syncwarp();
-    for (u32 a = lane; a < A; a += 32) {
-        if (root[a] == TREE_UNEXIST) continue;
-        u32 o = 1, cur = a;   // 1 = the container's '['
-        for (u32 guard = 0; guard <= A; guard++) {
-            o += rel[cur];
-            u32 pp = parent.get(cur);
-            if (pp >= TREE_UNEXIST) break;
-            o += tree_open_len(t.tn_sib[base + pp]);
-            cur = pp;
+    while (hi > lo && n_lvl + 1 < 2 * n_tr) {
+        if (lane == 0) lvl[n_lvl] = lo;
+        n_lvl++;
+        u32 carry = hi;
+        for (u32 i0 = lo; i0 < hi; i0 += 32) {
+            u32 i = i0 + (u32)lane;
+            u32 p = i < hi ? order[i] : 0u;
+            u32 n = i < hi ? cnt[p] : 0u;
+            int incl = warp_incl_scan((int)n, lane);
+            u32 w = carry + (u32)incl - n;
+            if (n) { u32 b0 = off[p], r = root[p]; for (u32 k = 0; k < n; k++) { u32 x = child[b0 + k]; order[w + k] = x; root[x] = r; } }
+            carry += (u32)__shfl_sync(LB_FULL, incl, 31);
         }
-        u32 sib = t.tn_sib[base + a];
-        u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, parent.get(a), sib, t.pos_len[t.tr_rec[tr_lo + move[a]].z]);
-        t.tn_aopen[base + a] = o;
-        t.tn_aclose[base + a] = o + tree_open_len(sib) + (sub[a] - own);
-    }
-    if (parent.s) {   // the JSON walk reads the links from the global table
+        lo = hi;
+        hi = carry;
         __syncwarp();
-        for (u32 i = lane; i < A; i += 32) parent.g[i] = parent.get(i);
+    }
+    if (lane == 0) lvl[n_lvl] = lo;   // == number of alive nodes
+    __syncwarp();
+    // bottom-up: JSON bytes of every subtree, offset of every child inside its parent's children list
+    for (u32 L = n_lvl; L-- > 0;) {
+        const u32 l0 = lvl[L], l1 = lvl[L + 1];
+        for (u32 i = l0 + (u32)lane; i < l1; i += 32) {
+            u32 a = order[i];
+            u32 sib = t.tn_sib[base + a];
+            u32 own = tree_open_len(sib) + tree_close_len(dpeer, P, a, parent[a], sib, plen_tmp[a]);
+            u32 n = cnt[a], b0 = off[a], acc = 0;
+            for (u32 k = 0; k < n; k++) { u32 c = child[b0 + k]; rel[c] = acc; acc += sub[c]; }
+            sub[a] = own + acc;
+            slot_tmp[a] = acc;   // bytes of the children: the distance between the node's two pieces
+        }
+        __syncwarp();
+    }
+    for (u32 c = lane; c < C; c += 32) {
+        u32 n = cnt[A + c], b0 = off[A + c], acc = 0;
+        for (u32 k = 0; k < n; k++) { u32 x = child[b0 + k]; rel[x] = acc; acc += sub[x]; }
+        sub[A + c] = acc;
+    }
+    __syncwarp();
+    // top-down: absolute offsets (1 = the container's '[')
+    for (u32 L = 0; L < n_lvl; L++) {
+        const u32 l0 = lvl[L], l1 = lvl[L + 1];
+        for (u32 i = l0 + (u32)lane; i < l1; i += 32) {
+            u32 a = order[i];
+            u32 p = parent[a];
+            u32 o = p == TREE_ROOT ? 1u + rel[a] : t.tn_aopen[base + p] + tree_open_len(t.tn_sib[base + p]) + rel[a];
+            t.tn_aopen[base + a] = o;
+            t.tn_aclose[base + a] = o + tree_open_len(t.tn_sib[base + a]) + slot_tmp[a];
+        }
+        __syncwarp();
     }
     if (lane == 0) docs[d].has_tree = has_meta ? 1u : 3u;   // bit1: the lane-parallel JSON layout is valid
 }
