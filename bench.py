@@ -354,7 +354,8 @@ def main():
     for _ in range(args.steps):
         c, tm = step()
         launches += tm["kernel_launches"]
-        for k in ("frame", "decode", "resolve", "classify", "integrate", "tree", "materialise", "reexport", "total_device"):
+        for k in ("frame", "decode", "resolve", "classify", "integrate", "tree", "materialise", "reexport", "total_device",
+                  "alloc_host_ms"):
             phase[k] = phase.get(k, 0.0) + tm[k]
     ev1.record()
     torch.cuda.synchronize()

@@ -110,6 +110,11 @@ typedef struct lb_timings { /* device time per phase in milliseconds (CUDA event
     /* change blocks by decode path: lane-parallel rows / staged in shared memory with the rows on one lane /
      * larger than the staging buffer (k_decode_warp.cuh) */
     uint64_t decode_fast_blocks, decode_lane_blocks, decode_unstaged_blocks;
+    /* host milliseconds spent inside the device allocator while the batch was built (they are part of the wall time of
+     * a step but of no device phase) and the bytes it handed out */
+    float alloc_host_ms;
+    uint32_t reserved1;
+    uint64_t device_bytes;
 } lb_timings;
 
 typedef struct lb_batch lb_batch;
@@ -143,6 +148,10 @@ lb_status lb_doc_export_updates(const lb_batch* b, size_t doc, const lb_id_span*
 lb_status lb_batch_counters(const lb_batch* b, lb_counters* out);
 lb_status lb_batch_timings(const lb_batch* b, lb_timings* out);
 const char* lb_last_error(void); /* thread-local, human readable */
+/* Device blocks that lived until lb_batch_free are kept (per device, by size class, at most LB_DEV_CACHE_GB gigabytes,
+ * default 120) for the next batch of similar shape; this gives them back to the driver. */
+lb_status lb_device_trim(int device);
+
 /* One process per GPU: pin the calling thread -- and the staging / download threads the engine creates from it -- to
  * the CPUs of the NUMA node `device` is attached to (sysfs).  Call before building the input buffers so that they,
  * the pinned staging ring and the gather threads all sit next to the GPU.  LB_ERR_UNSUPPORTED: topology unknown. */

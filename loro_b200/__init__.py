@@ -10,7 +10,7 @@ All compute runs in the CUDA library built from loro_b200/csrc (C ABI: include/l
 CPU fallback: importing a batch without the built library or without a CUDA device raises.
 """
 from .api import (Batch, DocError, EngineUnavailable, ImportStatus, import_batch, import_batch_device,
-                  library_path, load_library, numa_bind, pack_blobs)
+                  library_path, load_library, numa_bind, device_trim, pack_blobs)
 
 __all__ = ["Batch", "DocError", "EngineUnavailable", "ImportStatus", "import_batch", "import_batch_device",
-           "library_path", "load_library", "numa_bind", "pack_blobs"]
+           "library_path", "load_library", "numa_bind", "device_trim", "pack_blobs"]

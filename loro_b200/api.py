@@ -56,7 +56,8 @@ class _Timings(ctypes.Structure):
                 ("kernel_launches", ctypes.c_uint32), ("export_bytes", ctypes.c_uint64),
                 ("tree", ctypes.c_float), ("reserved0", ctypes.c_uint32), ("tree_ops", ctypes.c_uint64),
                 ("decode_fast_blocks", ctypes.c_uint64), ("decode_lane_blocks", ctypes.c_uint64),
-                ("decode_unstaged_blocks", ctypes.c_uint64)]
+                ("decode_unstaged_blocks", ctypes.c_uint64),
+                ("alloc_host_ms", ctypes.c_float), ("reserved1", ctypes.c_uint32), ("device_bytes", ctypes.c_uint64)]
 
 
 _libs = {}
@@ -253,6 +254,12 @@ def import_batch_device(d_bytes_ptr, offsets, lens, device=0, flags=0, lib_path=
     _check(L, L.lb_import_batch_device(ctypes.c_void_p(d_bytes_ptr), offs, ls, n, ctypes.byref(opt), ctypes.byref(h)),
            "lb_import_batch_device")
     return Batch(L, h.value, keep=keep)
+
+
+def device_trim(device=0, lib_path=None):
+    """Release the device blocks the engine keeps for the next batch (lb_device_trim)."""
+    L = load_library(lib_path)
+    _check(L, L.lb_device_trim(int(device)), "lb_device_trim")
 
 
 def numa_bind(device=0, lib_path=None):

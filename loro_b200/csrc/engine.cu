@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -98,23 +99,85 @@ __global__ void k_excl_scan_multi(ScanJobs jobs) {
 
 namespace {
 
+// Device blocks that lived until their batch was freed are kept per device, by size class, and handed to the next batch
+// that asks for the same class: a service imports batch after batch of similar shape, and the stream-ordered pool took
+// up to hundreds of milliseconds (host-blocking) to find or map room for the multi-GB row tables of a step -- 68 ms per
+// step on config C5.  Blocks a batch gives back early (Dev::release) still go to the pool, so their memory stays
+// available to every later size.  lb_device_trim() empties the cache.
+struct BlockCache {
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void*>> free_;
+    size_t bytes = 0;
+};
+BlockCache& block_cache(int device) {
+    static BlockCache caches[64];
+    return caches[(unsigned)device % 64];
+}
+size_t cache_cap_bytes() {
+    static const size_t cap = [] {
+        const char* e = getenv("LB_DEV_CACHE_GB");
+        return (size_t)((e ? atof(e) : 120.0) * 1e9);
+    }();
+    return cap;
+}
+inline size_t size_class(size_t sz) {   // 8 classes per power of two (at most 12.5 % above the request), 256-byte granules
+    sz = (sz + 255) & ~(size_t)255;
+#ifndef LB_SIMT_EMU
+    if (sz > 4096) {
+        int e = 63 - __builtin_clzll((unsigned long long)(sz - 1));
+        size_t step = (size_t)1 << (e - 3);
+        sz = (sz + step - 1) & ~(step - 1);
+    }
+#endif
+    return sz;
+}
+void cache_flush(int device, cudaStream_t st) {
+    BlockCache& bc = block_cache(device);
+    std::lock_guard<std::mutex> g(bc.mu);
+    for (auto& kv : bc.free_) for (void* p : kv.second) cudaFreeAsync(p, st);
+    bc.free_.clear();
+    bc.bytes = 0;
+}
+
 struct Dev {  // owns every device allocation of a batch
     cudaStream_t stream = nullptr;
-    std::vector<void*> ptrs;
+    int device = 0;
+    std::vector<std::pair<void*, size_t>> ptrs;
     size_t bytes = 0;
+    double alloc_ms = 0;   // host time inside the allocator (it blocks when the pool has to map memory)
     template <class T>
     T* alloc(size_t n, bool zero = false) {
         void* p = nullptr;
-        size_t sz = (n ? n : 1) * sizeof(T);
-        sz = (sz + 255) & ~(size_t)255;
-        cudaError_t e = cudaMallocAsync(&p, sz, stream);
-        if (e != cudaSuccess) {
-            g_last_error = std::string("cudaMallocAsync(") + std::to_string(sz) + "): " + cudaGetErrorString(e);
-            throw lb_status(LB_ERR_OOM);
+        const size_t want = (n ? n : 1) * sizeof(T);
+        const size_t sz = size_class(want);
+        auto t0 = std::chrono::steady_clock::now();
+#ifndef LB_SIMT_EMU
+        {
+            BlockCache& bc = block_cache(device);
+            std::lock_guard<std::mutex> g(bc.mu);
+            auto it = bc.free_.find(sz);
+            if (it != bc.free_.end() && !it->second.empty()) { p = it->second.back(); it->second.pop_back(); bc.bytes -= sz; }
         }
-        ptrs.push_back(p);
+#endif
+        if (!p) {
+            cudaError_t e = cudaMallocAsync(&p, sz, stream);
+            if (e != cudaSuccess) {   // out of memory with blocks parked in the cache: give them back and try once more
+                cudaGetLastError();
+                cache_flush(device, stream);
+                cudaStreamSynchronize(stream);
+                e = cudaMallocAsync(&p, sz, stream);
+            }
+            if (e != cudaSuccess) {
+                g_last_error = std::string("cudaMallocAsync(") + std::to_string(sz) + "): " + cudaGetErrorString(e);
+                throw lb_status(LB_ERR_OOM);
+            }
+        }
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        alloc_ms += ms;
+        if (ms > 1.0 && getenv("LB_PHASE_TRACE")) fprintf(stderr, "[trace] slow alloc: %zu bytes took %.3f ms\n", sz, ms);
+        ptrs.push_back({p, sz});
         bytes += sz;
-        if (zero) CK(cudaMemsetAsync(p, 0, sz, stream));
+        if (zero) CK(cudaMemsetAsync(p, 0, want, stream));
         return (T*)p;
     }
     // give a table back to the stream-ordered pool as soon as its last consumer has been enqueued
@@ -122,7 +185,7 @@ struct Dev {  // owns every device allocation of a batch
     void release(T*& p) {
         if (!p) return;
         for (size_t i = 0; i < ptrs.size(); i++)
-            if (ptrs[i] == (void*)p) {
+            if (ptrs[i].first == (void*)p) {
                 cudaFreeAsync((void*)p, stream);
                 ptrs[i] = ptrs.back();
                 ptrs.pop_back();
@@ -130,8 +193,18 @@ struct Dev {  // owns every device allocation of a batch
             }
         p = nullptr;
     }
+    // the batch is gone and its stream has been synchronised: the blocks are free for any stream
     void free_all() {
-        for (void* p : ptrs) cudaFreeAsync(p, stream);
+#ifndef LB_SIMT_EMU
+        BlockCache& bc = block_cache(device);
+        std::lock_guard<std::mutex> g(bc.mu);
+        for (auto& pr : ptrs) {
+            if (bc.bytes + pr.second <= cache_cap_bytes()) { bc.free_[pr.second].push_back(pr.first); bc.bytes += pr.second; }
+            else cudaFreeAsync(pr.first, stream);
+        }
+#else
+        for (auto& pr : ptrs) cudaFreeAsync(pr.first, stream);
+#endif
         ptrs.clear();
     }
 };
@@ -742,6 +815,7 @@ lb_status check_device(const lb_options* opt) {
 }
 
 void init_batch(lb_batch* b) {
+    b->dev.device = b->device;
     CK(cudaStreamCreate(&b->dev.stream));
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&b->ev[i]));
     b->ev_created = true;
@@ -918,6 +992,7 @@ lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets
     lb_batch* b = new lb_batch();
     b->n_docs = n_docs;
     b->flags = opt ? opt->flags : 0;
+    b->device = opt ? opt->device : 0;
     try {
         init_batch(b);
         std::vector<u64> offs(n_docs + 1);
@@ -1042,6 +1117,8 @@ lb_status lb_batch_counters(const lb_batch* b, lb_counters* out) {
 lb_status lb_batch_timings(const lb_batch* b, lb_timings* out) {
     if (!b || !out) return LB_ERR_INVALID_ARG;
     *out = b->timings;
+    out->alloc_host_ms = (float)b->dev.alloc_ms;
+    out->device_bytes = b->dev.bytes;
     return LB_OK;
 }
 
@@ -1086,6 +1163,7 @@ void lb_batch_free(lb_batch* b) {
     if (b->json_thread.joinable()) b->json_thread.join();
     if (b->json_ev) cudaEventDestroy(b->json_ev);
     if (b->stream2) cudaStreamDestroy(b->stream2);
+    if (b->ev_created) cudaStreamSynchronize(b->dev.stream);   // the cached blocks must be idle
     b->dev.free_all();
     if (b->ev_created) {   // the stream exists whenever the events do (init_batch)
         cudaStreamSynchronize(b->dev.stream);
@@ -1095,6 +1173,18 @@ void lb_batch_free(lb_batch* b) {
     lbstage::host_cache().give(b->json);
     lbstage::host_cache().give(b->exported);
     delete b;
+}
+
+// Give the device blocks kept for the next batch (BlockCache) back to the driver.
+lb_status lb_device_trim(int device) {
+    lb_options o;
+    memset(&o, 0, sizeof(o));
+    o.device = device;
+    lb_status st = check_device(&o);
+    if (st != LB_OK) return st;
+    cache_flush(device, nullptr);
+    cudaStreamSynchronize(nullptr);
+    return LB_OK;
 }
 
 // Pin the CALLING thread (and every thread it creates afterwards: the staging workers, the JSON download thread) to

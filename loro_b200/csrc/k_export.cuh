@@ -497,7 +497,12 @@ __device__ inline void segment_summaries(const ExportTables& t, const DocInfo& d
 
 // thread per change.  pass 0: per-row records, RleVec merge inside the change (XF_HEAD), segment count (XF_SEG marks
 // when no op has to be cut, a synthetic-row count otherwise).  pass 1 (split changes only): synthetic rows, summaries.
-__global__ void k_exp_changes(DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
+#ifdef LB_XCHG_MINB
+__global__ void __launch_bounds__(64, LB_XCHG_MINB) k_exp_changes(
+#else
+__global__ void k_exp_changes(
+#endif
+    DocInfo* __restrict__ docs, u64 n_changes, ExportTables t, int pass) {
     u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= n_changes) return;
     if (t.only_doc != 0xFFFFFFFFu && t.blocks[t.ch_block[ch]].doc != t.only_doc) return;
@@ -1121,7 +1126,12 @@ __global__ void k_exp_posrank(const DocInfo* __restrict__ docs, u32 n_docs, Expo
 }
 
 // thread per output block.  pass 0: gather ops into scratch columns, registers, section sizes ; pass 1: bytes.
-__global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
+#ifdef LB_XENC_MINB
+__global__ void __launch_bounds__(64, LB_XENC_MINB) k_exp_encode(
+#else
+__global__ void k_exp_encode(
+#endif
+    const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
                              u32* __restrict__ scratch, u8* __restrict__ out, int pass) {
     u64 bi_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (bi_ >= n_blocks) return;
