@@ -49,7 +49,10 @@ __global__ void k_doc_sizes(const DocInfo* __restrict__ docs, u32 n_docs, u32* _
     const DocInfo& di = docs[d];
     bool ok = di.code == DOC_OK;
     if (which == 0) vvsize[d] = ok ? di.n_changes * di.P : 0;
-    else if (which == 2) vvsize[d] = ok && di.has_tree ? (u32)di.atom_total + di.C : 0;   // tree node slots (k_tree.cuh)
+    else if (which == 2) {   // tree node slots (k_tree.cuh) ; atoms[n_docs] collects the largest tree document
+        vvsize[d] = ok && di.has_tree ? (u32)di.atom_total + di.C : 0;
+        if (ok && di.has_tree) atomicMax(&atoms[n_docs], (u32)di.atom_total);
+    }
     else {
         atoms[d] = ok ? (u32)di.atom_total : 0;
         mapslots[d] = ok ? di.C * di.K : 0;
@@ -508,28 +511,38 @@ void pipeline(lb_batch* b) {
     TreeTables tt;
     memset(&tt, 0, sizeof(tt));
     if (NTR) {
+        CK(cudaMemsetAsync(d_tmp_b + D, 0, sizeof(u32), st));
         LB_LAUNCH(k_doc_sizes, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a, d_tmp_b, d_tmp_c, 2);
         run_scans(b, {ScanJob{(const u8*)d_tmp_a, (u8*)b->d_docs + offsetof(DocInfo, tree0), 4, sizeof(DocInfo), D}});
         u64 NTS = d2h_one(b, &b->d_docs[D].tree0);
+        const u32 max_atoms = d2h_one(b, d_tmp_b + D);
         tt.dpeer = b->d_dpeer; tt.blocks = blk; tt.op_cidx = ct.op_cidx; tt.op_lamport = ct.op_lamport;
         tt.tr_rec = ct.tr_rec; tt.tr_key = ct.tr_key;
-        tt.ts_key = dv.alloc<u64>(NTR); tt.ts_val = dv.alloc<u32>(NTR);
+        tt.ts_key = dv.alloc<u64>(NTR); tt.ts_val = dv.alloc<u32>(NTR); tt.ts_rec = dv.alloc<uint4>(NTR);
         tt.pos_off = t.pos_off; tt.pos_len = t.pos_len; tt.pos_pool = t.pos_pool;
         tt.tn_parent = dv.alloc<u32>(NTS); tt.tn_move = dv.alloc<u32>(NTS); tt.tn_base = dv.alloc<u32>(NTS);
         tt.tn_cnt = dv.alloc<u32>(NTS); tt.tn_sib = dv.alloc<u32>(NTS); tt.ns_key = dv.alloc<u64>(NTS);
         tt.tn_child = dv.alloc<u32>(NTS);
         tt.tn_root = dv.alloc<u32>(NTS); tt.tn_aopen = dv.alloc<u32>(NTS); tt.tn_aclose = dv.alloc<u32>(NTS);
         tt.dcont = dcont;
-        const size_t tree_smem = (size_t)TREE_WARPS * TREE_S_NODES * sizeof(u16);
+        // 16-bit parent links of one document in shared memory, sized for the largest tree document of the batch:
+        // the number of resident documents (one sequential chain each) is what the apply kernel's speed depends on
+        u32 s_nodes = max_atoms < TREE_S_NODES_MAX ? max_atoms : (u32)TREE_S_NODES_MAX;
+        s_nodes = (s_nodes + 63u) & ~63u;
+        const size_t tree_smem = (size_t)TREE_WARPS * s_nodes * sizeof(u16);
 #ifndef LB_SIMT_EMU
-        static bool tree_attr_set = false;
-        if (!tree_attr_set) { CK(cudaFuncSetAttribute(k_tree_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem)); tree_attr_set = true; }
+        CK(cudaFuncSetAttribute(k_tree_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem));
+        CK(cudaFuncSetAttribute(k_tree_apply, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        if (getenv("LB_PHASE_TRACE")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tree_apply, 32 * TREE_WARPS, tree_smem);
+            fprintf(stderr, "[trace] k_tree_apply: %zu bytes of shared memory per document, %d documents resident per SM\n", tree_smem, nb);
+        }
 #endif
         LB_LAUNCH(k_tree_sort, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
-        LB_LAUNCH(k_tree_apply, nblk((u64)D * 32, 32 * TREE_WARPS), 32 * TREE_WARPS, tree_smem, st, b->d_docs, D, tt);
+        LB_LAUNCH(k_tree_apply, nblk((u64)D * 32, 32 * TREE_WARPS), 32 * TREE_WARPS, tree_smem, st, b->d_docs, D, tt, s_nodes);
         LB_LAUNCH(k_tree_layout, nblk((u64)D * 32, 128), 128, 0, st, b->d_docs, D, tt);
-        tm.kernel_launches += 2;
-        tm.kernel_launches += 2;
+        tm.kernel_launches += 4;
     }
     mark(b);  // [5b] trees done
     tm.tree_ops = NTR;

@@ -80,6 +80,15 @@ struct Frame {
 };
 #define MAX_FRAMES 24
 
+// per warp: the document's first peers with their ids as decimal text (tree node ids are "<counter>@<peer>": two per node,
+// and formatting a 64-bit peer id costs twenty 64-bit divisions -- done once per peer instead of twice per node)
+#define TREE_TXT_PEERS 8
+struct TreeEmitSmem {
+    u32 base[TREE_TXT_PEERS], end[TREE_TXT_PEERS];
+    u8 len[TREE_TXT_PEERS];
+    u8 txt[TREE_TXT_PEERS][20];
+};
+
 struct Emitter {
     const StateTables& t;
     const DocInfo& di;
@@ -89,7 +98,8 @@ struct Emitter {
     u32 err;
     int lane;
     u32 cur_blk;   // block of the op whose value is being printed (nested map keys are block-local indices)
-    __device__ Emitter(const StateTables& t_, const DocInfo& di_, Sink& o, int lane_) : t(t_), di(di_), out(o), sp(0), err(0), lane(lane_), cur_blk(0) {}
+    TreeEmitSmem* tsm;
+    __device__ Emitter(const StateTables& t_, const DocInfo& di_, Sink& o, int lane_, TreeEmitSmem* tsm_) : t(t_), di(di_), out(o), sp(0), err(0), lane(lane_), cur_blk(0), tsm(tsm_) {}
 
     __device__ int cmp_bytes(const u8* a, u32 al, const u8* b, u32 bl) {
         u32 n = al < bl ? al : bl;
@@ -236,7 +246,23 @@ struct Emitter {
         }
         for (; i < n; i++) dst[i] = src[i];
     }
-    // every node of the hierarchy written by its own lane at the offsets k_tree_build laid out (all meta maps empty);
+    __device__ __forceinline__ static void put_u32_to(Sink& o, u32 v) {   // 32-bit divisions by a constant: multiply + shift
+        char tmp[10];
+        int k = 0;
+        do { tmp[k++] = (char)('0' + v % 10u); v /= 10u; } while (v);
+        while (k) o.put((u8)tmp[--k]);
+    }
+    // "<counter>@<peer>" from the per-warp peer table (the caller checked di.P <= TREE_TXT_PEERS)
+    __device__ __forceinline__ void put_tree_id_fast(Sink& o, u32 a) {
+        u32 p = 0;
+        for (u32 q = 0; q < di.P; q++) if (a >= tsm->base[q] && a < tsm->end[q]) { p = q; break; }
+        o.put('"');
+        put_u32_to(o, a - tsm->base[p]);
+        o.put('@');
+        for (u32 k = 0; k < tsm->len[p]; k++) o.put(tsm->txt[p][k]);
+        o.put('"');
+    }
+    // every node of the hierarchy written by its own lane at the offsets k_tree_layout laid out (all meta maps empty);
     // the caller has printed '[' and prints ']'
     __device__ __noinline__ void emit_tree_parallel(u32 cidx) {
         const u64 tb = di.tree0;
@@ -244,6 +270,22 @@ struct Emitter {
         const u64 tr_lo = t.blocks[di.b0].tr0;
         const u32 total = ((const u32*)(t.ns_key + tb))[slot];
         if (out.dst) {
+            const bool fast = di.P <= TREE_TXT_PEERS;
+            if (fast) {
+                __syncwarp();
+                if ((u32)lane < di.P) {
+                    const DocPeer& dp = t.dpeer[di.peer0 + lane];
+                    tsm->base[lane] = dp.atom_base;
+                    tsm->end[lane] = dp.atom_base + (u32)dp.end_counter;
+                    char tmp[20];
+                    int k = 0;
+                    u64 v = dp.id;
+                    do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+                    tsm->len[lane] = (u8)k;
+                    for (int i = 0; i < k; i++) tsm->txt[lane][i] = (u8)tmp[k - 1 - i];
+                }
+                __syncwarp();
+            }
             const u64 start = out.n - 1;   // the container's '['
             for (u32 a = (u32)lane; a < A; a += 32) {
                 if (t.tn_root[tb + a] != slot) continue;
@@ -265,11 +307,13 @@ struct Emitter {
                 w.puts_("],\"fractional_index\":\"");
                 put_fractional_index(w, pos);
                 w.puts_("\",\"id\":");
-                put_tree_id_to(w, a);
+                if (fast) put_tree_id_fast(w, a); else put_tree_id_to(w, a);
                 w.puts_(",\"index\":");
-                w.put_u64(sib);
+                put_u32_to(w, sib);
                 w.puts_(",\"meta\":{},\"parent\":");
-                if (par == TREE_ROOT) w.puts_("null"); else put_tree_id_to(w, par);
+                if (par == TREE_ROOT) w.puts_("null");
+                else if (fast) put_tree_id_fast(w, par);
+                else put_tree_id_to(w, par);
                 w.put('}');
                 if (!direct) copy_out(out.dst + start + t.tn_aclose[tb + a], buf, (u32)w.n);
             }
@@ -640,6 +684,7 @@ struct Emitter {
 
 // pass = 0: count bytes into docs[d].json_len ; pass = 1: write at docs[d].json_off
 __global__ void __launch_bounds__(128, 8) k_json(DocInfo* __restrict__ docs, u32 n_docs, StateTables t, u8* __restrict__ json, int pass) {
+    __shared__ TreeEmitSmem tsm[4];   // 128 threads: one entry per warp
     u32 d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per document
     int lane = threadIdx.x & 31;
     if (d >= n_docs) return;
@@ -650,7 +695,7 @@ __global__ void __launch_bounds__(128, 8) k_json(DocInfo* __restrict__ docs, u32
     s.n = 0;
     s.flags = 0;
     s.wr = lane == 0;
-    Emitter e(t, di, s, lane);
+    Emitter e(t, di, s, lane, &tsm[(threadIdx.x >> 5) & 3]);
     e.run();
     __syncwarp();
     if (!pass && lane == 0) {

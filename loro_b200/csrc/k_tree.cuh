@@ -28,6 +28,7 @@ struct TreeTables {
     const uint4* tr_rec;      // per tree op (k_op_classify): target atom, parent atom | TREE_ROOT | TREE_DELETED, position, row
     const u64* tr_key;        // (lamport << 32 | peer rank << 16), ~0 for ops that are not applied
     u64* ts_key; u32* ts_val; // sort space, one entry per tree op
+    uint4* ts_rec;            // the records in apply order (w = 0xFFFFFFFF from the first op that is not applied)
     const u64* pos_off; const u32* pos_len; const u8* pos_pool;
     // per document: S = atom_total + C slots starting at DocInfo::tree0.  Slots [0, atom_total) are nodes, slot
     // atom_total + c is the root of tree container c.
@@ -134,8 +135,8 @@ __device__ inline int pos_cmp(const TreeTables& t, u32 pa, u32 pb) {
 //   k_tree_layout  sibling lists and the JSON layout: lane-parallel walks, best at full occupancy, links from global
 // (one kernel holding the shared-memory links through all three steps was measured: the low occupancy it forces on the
 //  lane-parallel steps cost more than the fast links gained -- 119 ms instead of 65 ms on config C5.)
-#define TREE_WARPS 2
-#define TREE_S_NODES 10240
+#define TREE_WARPS 1          // one document per CTA: the shared-memory size per document decides how many are resident
+#define TREE_S_NODES_MAX 32768 // larger documents keep their links in global memory
 struct ParentArr {
     u16* s;      // nullptr: global only
     u32* g;
@@ -212,9 +213,17 @@ __global__ void k_tree_sort(const DocInfo* __restrict__ docs, u32 n_docs, TreeTa
         }
     }
     __syncwarp();
+    // the records in apply order: the sequential loop of k_tree_apply then reads them with coalesced loads instead of a
+    // key -> index -> record chain of three dependent round trips per 32 ops
+    for (u32 j = lane; j < n_tr; j += 32) {
+        uint4 rec;
+        rec.x = rec.y = rec.z = 0; rec.w = 0xFFFFFFFFu;
+        if (skey[j] != ~0ull) rec = t.tr_rec[tr_lo + sval[j]];
+        t.ts_rec[tr_lo + j] = rec;
+    }
 }
 
-__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_apply(const DocInfo* __restrict__ docs, u32 n_docs, TreeTables t) {
+__global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_apply(const DocInfo* __restrict__ docs, u32 n_docs, TreeTables t, u32 s_nodes) {
 #ifdef LB_SIMT_EMU
     LB_DYN_SMEM(u16, tree_smem);
 #else
@@ -229,22 +238,28 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_apply(const DocInfo* _
     const u64 base = di.tree0;
     ParentArr parent;
     parent.g = t.tn_parent + base;
-    parent.s = A <= TREE_S_NODES ? tree_smem + (threadIdx.x >> 5) * TREE_S_NODES : nullptr;
+    parent.s = A <= s_nodes ? tree_smem + (threadIdx.x >> 5) * s_nodes : nullptr;
     u32* move = t.tn_move + base;
     for (u32 i = lane; i < A; i += 32) parent.set(i, TREE_UNEXIST);
     const u64 tr_lo = t.blocks[di.b0].tr0, tr_hi = t.blocks[di.b1].tr0;
     const u32 n_tr = (u32)(tr_hi - tr_lo);
-    const u64* skey = t.ts_key + tr_lo;
     const u32* sval = t.ts_val + tr_lo;
     __syncwarp();
-    // ---- sequential apply, 32 records per round trip
+    // ---- sequential apply, 32 records per round trip, the next 32 in flight meanwhile
+    const uint4* srec = t.ts_rec + tr_lo;
     bool stop = false;
+    uint4 nrec;
+    u32 nti = 0;
+    nrec.x = nrec.y = nrec.z = 0; nrec.w = 0xFFFFFFFFu;
+    if ((u32)lane < n_tr) { nrec = srec[lane]; nti = sval[lane]; }
     for (u32 j0 = 0; j0 < n_tr && !stop; j0 += 32) {
-        u32 j = j0 + (u32)lane;
-        uint4 rec;
-        rec.x = rec.y = rec.z = 0; rec.w = 0xFFFFFFFFu;
-        u32 ti_l = 0;
-        if (j < n_tr && skey[j] != ~0ull) { ti_l = sval[j]; rec = t.tr_rec[tr_lo + ti_l]; }
+        uint4 rec = nrec;
+        u32 ti_l = nti;
+        {
+            u32 jn = j0 + 32 + (u32)lane;
+            nrec.w = 0xFFFFFFFFu;
+            if (jn < n_tr) { nrec = srec[jn]; nti = sval[jn]; }
+        }
         u32 cnt = n_tr - j0 < 32 ? n_tr - j0 : 32;
         for (u32 s = 0; s < cnt; s++) {
             u32 row = __shfl_sync(LB_FULL, rec.w, (int)s);
@@ -255,12 +270,23 @@ __global__ void __launch_bounds__(32 * TREE_WARPS) k_tree_apply(const DocInfo* _
             bool effected = true;
             if (np < TREE_UNEXIST && parent.get(target) != TREE_UNEXIST) {
                 // is the target an ancestor of (or equal to) the new parent?  (tree.rs:477-508, tree_state.rs:727-747)
-                u32 cur = np;
-                for (u32 guard = 0; guard <= A; guard++) {
-                    if (cur == target) { effected = false; break; }
-                    u32 pp = parent.get(cur);
-                    if (pp >= TREE_UNEXIST) break;
-                    cur = pp;
+                // This walk is the kernel: one dependent look-up per level, so the shared-memory form is kept minimal
+                if (parent.s) {
+                    const u16* ps = parent.s;
+                    u32 cur = np;
+                    for (u32 guard = 0; guard <= A; guard++) {
+                        if (cur == target) { effected = false; break; }
+                        cur = ps[cur];
+                        if (cur >= 0xFFFDu) break;   // root / deleted root / no parent yet
+                    }
+                } else {
+                    u32 cur = np;
+                    for (u32 guard = 0; guard <= A; guard++) {
+                        if (cur == target) { effected = false; break; }
+                        u32 pp = parent.g[cur];
+                        if (pp >= TREE_UNEXIST) break;
+                        cur = pp;
+                    }
                 }
             }
             __syncwarp();
