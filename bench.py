@@ -458,7 +458,8 @@ def main():
                    "name": args.config,
                    "docs_per_gpu": n_docs, "distinct_docs_per_gpu": distinct, "atom_ops_per_step_per_gpu": atoms_per_step,
                    "op_rows_per_gpu": rows, "blob_bytes_per_gpu": int(lens.sum()), "l2": "inputs_larger_than_L2" if lens.sum() > 126e6 else "inputs fit L2",
-                   "generator_seconds": round(gen_s, 1), "host_cores": host_cores(), "numa_bound": bool(numa_bound)},
+                   "generator_seconds": round(gen_s, 1), "host_cores": host_cores(), "numa_bound": bool(numa_bound),
+                   "device_table_bytes_per_step": int(tm["device_bytes"])},
         "phases_ms": {k: v / n_steps for k, v in phase.items()}, "wall_ms_per_step": wall_ms / n_steps,
         "roofline": roof, "decode_roofline": dec_roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,

@@ -149,7 +149,7 @@ lb_status lb_batch_counters(const lb_batch* b, lb_counters* out);
 lb_status lb_batch_timings(const lb_batch* b, lb_timings* out);
 const char* lb_last_error(void); /* thread-local, human readable */
 /* Device blocks that lived until lb_batch_free are kept (per device, by size class, at most LB_DEV_CACHE_GB gigabytes,
- * default 120) for the next batch of similar shape; this gives them back to the driver. */
+ * default 85 % of the device's memory) for the next batch of similar shape; this gives them back to the driver. */
 lb_status lb_device_trim(int device);
 
 /* One process per GPU: pin the calling thread -- and the staging / download threads the engine creates from it -- to

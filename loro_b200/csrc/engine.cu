@@ -116,10 +116,13 @@ BlockCache& block_cache(int device) {
     static BlockCache caches[64];
     return caches[(unsigned)device % 64];
 }
-size_t cache_cap_bytes() {
+size_t cache_cap_bytes() {   // LB_DEV_CACHE_GB, default 85 % of the device's memory
     static const size_t cap = [] {
         const char* e = getenv("LB_DEV_CACHE_GB");
-        return (size_t)((e ? atof(e) : 120.0) * 1e9);
+        if (e) return (size_t)(atof(e) * 1e9);
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) tot = (size_t)64e9;
+        return (size_t)((double)tot * 0.85);
     }();
     return cap;
 }
@@ -142,10 +145,44 @@ void cache_flush(int device, cudaStream_t st) {
     bc.bytes = 0;
 }
 
+// Batch streams are recycled per device: memory a batch frees early goes back to the stream-ordered pool, and the pool
+// serves a later request fastest when it comes from the stream the memory was freed on.
+struct StreamCache {
+    std::mutex mu;
+    std::vector<cudaStream_t> idle;
+};
+StreamCache& stream_cache(int device) {
+    static StreamCache caches[64];
+    return caches[(unsigned)device % 64];
+}
+cudaStream_t stream_take(int device) {
+    StreamCache& sc = stream_cache(device);
+    {
+        std::lock_guard<std::mutex> g(sc.mu);
+        if (!sc.idle.empty()) { cudaStream_t s = sc.idle.back(); sc.idle.pop_back(); return s; }
+    }
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreate(&s) != cudaSuccess) return nullptr;
+    return s;
+}
+void stream_give(int device, cudaStream_t s) {
+    StreamCache& sc = stream_cache(device);
+    std::lock_guard<std::mutex> g(sc.mu);
+    if (sc.idle.size() < 4 && !getenv("LB_NO_STREAM_REUSE")) sc.idle.push_back(s);
+    else cudaStreamDestroy(s);
+}
+
 struct Dev {  // owns every device allocation of a batch
     cudaStream_t stream = nullptr;
     int device = 0;
-    std::vector<std::pair<void*, size_t>> ptrs;
+    std::vector<std::pair<void*, size_t>> ptrs;   // whole blocks in use
+    // Blocks the batch is done with before it ends (the tracker pools after phase 5) stay with the batch: later tables
+    // are carved out of them (same stream, so the order of use is the order of enqueueing) and at the end they go to
+    // the block cache whole.  Handing them to the stream-ordered pool and asking it for the export tables made the
+    // multi-GB requests block the host at random (0.3 ms on one step, 120 ms -- once 1.2 s -- on the next).
+    struct Carve { size_t off, need; bool live; };
+    struct Region { char* base; size_t size, used; std::vector<Carve> stack; };
+    std::vector<Region> released;
     size_t bytes = 0;
     double alloc_ms = 0;   // host time inside the allocator (it blocks when the pool has to map memory)
     template <class T>
@@ -154,8 +191,14 @@ struct Dev {  // owns every device allocation of a batch
         const size_t want = (n ? n : 1) * sizeof(T);
         const size_t sz = size_class(want);
         auto t0 = std::chrono::steady_clock::now();
+        bool carved = false;
 #ifndef LB_SIMT_EMU
         {
+            const size_t need = (want + 255) & ~(size_t)255;
+            for (auto& r : released)
+                if (r.size - r.used >= need) { p = r.base + r.used; r.stack.push_back(Carve{r.used, need, true}); r.used += need; carved = true; break; }
+        }
+        if (!p) {
             BlockCache& bc = block_cache(device);
             std::lock_guard<std::mutex> g(bc.mu);
             auto it = bc.free_.find(sz);
@@ -178,27 +221,40 @@ struct Dev {  // owns every device allocation of a batch
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         alloc_ms += ms;
         if (ms > 1.0 && getenv("LB_PHASE_TRACE")) fprintf(stderr, "[trace] slow alloc: %zu bytes took %.3f ms\n", sz, ms);
-        ptrs.push_back({p, sz});
-        bytes += sz;
+        if (!carved) { ptrs.push_back({p, sz}); bytes += sz; }
         if (zero) CK(cudaMemsetAsync(p, 0, want, stream));
         return (T*)p;
     }
-    // give a table back to the stream-ordered pool as soon as its last consumer has been enqueued
+    // the batch has enqueued the last consumer of a table: its block becomes room for later tables (see `released`)
     template <class T>
     void release(T*& p) {
         if (!p) return;
         for (size_t i = 0; i < ptrs.size(); i++)
             if (ptrs[i].first == (void*)p) {
+#ifndef LB_SIMT_EMU
+                released.push_back(Region{(char*)p, ptrs[i].second, 0, {}});
+#else
                 cudaFreeAsync((void*)p, stream);
+#endif
                 ptrs[i] = ptrs.back();
                 ptrs.pop_back();
                 break;
             }
+        // a table carved out of a released block: its room is reusable once everything carved after it is gone too
+        for (auto& r : released) {
+            if ((char*)p < r.base || (char*)p >= r.base + r.size) continue;
+            const size_t off = (size_t)((char*)p - r.base);
+            for (auto& c : r.stack) if (c.off == off) c.live = false;
+            while (!r.stack.empty() && !r.stack.back().live) { r.used = r.stack.back().off; r.stack.pop_back(); }
+            break;
+        }
         p = nullptr;
     }
     // the batch is gone and its stream has been synchronised: the blocks are free for any stream
     void free_all() {
 #ifndef LB_SIMT_EMU
+        for (auto& r : released) ptrs.push_back({(void*)r.base, r.size});
+        released.clear();
         BlockCache& bc = block_cache(device);
         std::lock_guard<std::mutex> g(bc.mu);
         for (auto& pr : ptrs) {
@@ -829,7 +885,8 @@ lb_status check_device(const lb_options* opt) {
 
 void init_batch(lb_batch* b) {
     b->dev.device = b->device;
-    CK(cudaStreamCreate(&b->dev.stream));
+    b->dev.stream = stream_take(b->device);
+    if (!b->dev.stream) { g_last_error = "cudaStreamCreate failed"; throw lb_status(LB_ERR_CUDA); }
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&b->ev[i]));
     b->ev_created = true;
 }
@@ -1181,7 +1238,7 @@ void lb_batch_free(lb_batch* b) {
     if (b->ev_created) {   // the stream exists whenever the events do (init_batch)
         cudaStreamSynchronize(b->dev.stream);
         for (int i = 0; i < 16; i++) cudaEventDestroy(b->ev[i]);
-        cudaStreamDestroy(b->dev.stream);
+        stream_give(b->device, b->dev.stream);
     }
     lbstage::host_cache().give(b->json);
     lbstage::host_cache().give(b->exported);
