@@ -283,11 +283,12 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaPeekAtLastError() { return 0; }
-inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { static int dummy; *s = &dummy; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+inline cudaError_t cudaMemGetInfo(size_t* fr, size_t* tot) { *fr = *tot = (size_t)8 << 30; return 0; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e ? "emu error" : "no error"; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }
