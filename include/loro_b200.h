@@ -158,6 +158,32 @@ lb_status lb_device_trim(int device);
 lb_status lb_numa_bind(int device);
 void lb_batch_free(lb_batch* b);
 
+/* ---- persistent documents: imports against an EXISTING document state ------------------------------------------------
+ * LoroDoc::import / import_batch on a document that already holds history (crates/loro/src/lib.rs:639, :425;
+ * crates/loro-internal/src/loro.rs:562-643, 1183-1290; oplog.rs:130-196: changes the document knows are skipped or
+ * trimmed, pending changes wait in the oplog until a later import brings their dependencies).
+ * A docset keeps, per doc_id, the document's change store in wire form IN DEVICE MEMORY: the FastUpdates blob the
+ * document re-exports (what the reference's ChangeStore keeps: encoded blocks, change_store.rs:60-110), or -- while the
+ * document still has pending changes, which no export contains -- the blobs it was built from.  lb_docset_import lays
+ * the stored blobs of every touched document in front of the new ones (device-to-device) and replays the document;
+ * the batch it returns answers exactly like the reference's import on the existing document:
+ *   lb_doc_status    ImportStatus of THIS import: success = what the new blobs added (a change the document already
+ *                    held is not reported, a stored pending change released by this import is), pending = what the
+ *                    new blobs parked;
+ *   lb_doc_json / lb_doc_vv / lb_doc_frontiers / lb_doc_export_updates    the document after the import.
+ * Several blobs with one doc_id in one call = import_batch on that document (sorted by mode, then number of changes
+ * descending, among the new blobs).  A document whose import fails (checksum, decode error, ...) keeps its earlier
+ * state, like the reference (loro.rs:584: checked before any state change).  The engine merges by replaying the
+ * document's whole history, not from the common ancestor of the two versions (dag.rs:488-667): same results, the
+ * cost of an import grows with the history.
+ * One docset serves one device; calls on the same docset are serialised.  LB_FLAG_EXPORT is implied. */
+typedef struct lb_docset lb_docset;
+lb_status lb_docset_new(const lb_options* opt, lb_docset** out);
+lb_status lb_docset_import(lb_docset* set, const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out);
+size_t lb_docset_doc_count(const lb_docset* set);
+uint64_t lb_docset_stored_bytes(const lb_docset* set);   /* device bytes of the stored documents */
+void lb_docset_free(lb_docset* set);
+
 /* test hooks (need LB_FLAG_KEEP_DEVICE): copy one decoded SoA table to the host.
  * name in {"op_cid","op_prop","op_vtype","op_len","op_counter","ch_counter","ch_len","ch_lamport",
  *          "ch_ts","dep_peer","dep_counter","blk_doc","blk_nchanges"}; returns element count. */

@@ -94,6 +94,13 @@ def load_library(path=None):
     L.lb_batch_free.argtypes = [vp]
     L.lb_debug_table.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
                                  ctypes.POINTER(ctypes.c_size_t)]
+    L.lb_docset_new.argtypes = [ctypes.POINTER(_Options), ctypes.POINTER(vp)]
+    L.lb_docset_import.argtypes = [vp, ctypes.POINTER(_Blob), ctypes.c_size_t, ctypes.POINTER(_Options), ctypes.POINTER(vp)]
+    L.lb_docset_doc_count.restype = ctypes.c_size_t
+    L.lb_docset_doc_count.argtypes = [vp]
+    L.lb_docset_stored_bytes.restype = ctypes.c_uint64
+    L.lb_docset_stored_bytes.argtypes = [vp]
+    L.lb_docset_free.argtypes = [vp]
     _libs[path] = L
     return L
 
@@ -219,6 +226,15 @@ def import_batch(blobs, device=0, flags=0, lib_path=None, doc_ids=None):
     blobs with the same id form one document; documents are numbered in order of first appearance."""
     L = load_library(lib_path)
     n = len(blobs)
+    arr, keep = _blob_array(blobs, doc_ids)
+    opt = _Options(device=device, flags=flags)
+    h = ctypes.c_void_p()
+    _check(L, L.lb_import_batch(arr, n, ctypes.byref(opt), ctypes.byref(h)), "lb_import_batch")
+    return Batch(L, h.value)
+
+
+def _blob_array(blobs, doc_ids):
+    n = len(blobs)
     arr = (_Blob * max(n, 1))()
     keep = []
     for i, b in enumerate(blobs):
@@ -227,10 +243,55 @@ def import_batch(blobs, device=0, flags=0, lib_path=None, doc_ids=None):
         arr[i].ptr = b
         arr[i].len = len(b)
         arr[i].doc_id = i if doc_ids is None else int(doc_ids[i])
-    opt = _Options(device=device, flags=flags)
-    h = ctypes.c_void_p()
-    _check(L, L.lb_import_batch(arr, n, ctypes.byref(opt), ctypes.byref(h)), "lb_import_batch")
-    return Batch(L, h.value)
+    return arr, keep
+
+
+class DocSet:
+    """Persistent documents: LoroDoc::import / import_batch against documents that already hold history.  The documents
+    live in device memory between calls (their change stores in wire form, include/loro_b200.h lb_docset_*); every
+    import_() returns a Batch that answers for the documents it touched -- status of THIS import, state after it."""
+
+    def __init__(self, device=0, lib_path=None):
+        self._L = load_library(lib_path)
+        self._device = device
+        opt = _Options(device=device, flags=0)
+        h = ctypes.c_void_p()
+        _check(self._L, self._L.lb_docset_new(ctypes.byref(opt), ctypes.byref(h)), "lb_docset_new")
+        self._h = h.value
+
+    def import_(self, blobs, doc_ids, flags=0):
+        """blobs[i] is imported into document doc_ids[i]; several blobs for one id = import_batch on that document.
+        Documents of the returned Batch are numbered in order of first appearance of their id."""
+        arr, keep = _blob_array(blobs, doc_ids)
+        opt = _Options(device=self._device, flags=flags)
+        h = ctypes.c_void_p()
+        _check(self._L, self._L.lb_docset_import(self._h, arr, len(blobs), ctypes.byref(opt), ctypes.byref(h)), "lb_docset_import")
+        return Batch(self._L, h.value)
+
+    @property
+    def n_docs(self):
+        return self._L.lb_docset_doc_count(self._h)
+
+    @property
+    def stored_bytes(self):
+        return self._L.lb_docset_stored_bytes(self._h)
+
+    def close(self):
+        if self._h:
+            self._L.lb_docset_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def import_batch_device(d_bytes_ptr, offsets, lens, device=0, flags=0, lib_path=None, keep=None):

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -98,6 +99,21 @@ __global__ void k_excl_scan_multi(ScanJobs jobs) {
         __syncthreads();
     }
     if (threadIdx.x == 0) *(u64*)(out + n * out_stride) = carry_s;
+}
+
+// warp per segment: copy blobs between device buffers (lb_docset: the stored state of a document enters the next batch,
+// the re-exported blobs leave the batch).  Sources and destinations are 16-byte aligned.
+struct CopySeg { const u8* src; u8* dst; u64 len; };
+__global__ void k_copy_segments(const CopySeg* __restrict__ segs, u32 n) {
+    u32 w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    CopySeg sg = segs[w];
+    u64 n16 = sg.len >> 4;
+    const uint4* s4 = (const uint4*)sg.src;
+    uint4* d4 = (uint4*)sg.dst;
+    for (u64 i = lane; i < n16; i += 32) d4[i] = s4[i];
+    for (u64 i = (n16 << 4) + lane; i < sg.len; i += 32) sg.dst[i] = sg.src[i];
 }
 
 namespace {
@@ -281,6 +297,7 @@ struct lb_batch {
     u32* d_lens = nullptr;
     size_t n_blobs = 0;                       // blobs in the byte buffer (>= n_docs: import_batch groups)
     std::vector<u32> blob_doc, doc_blob0;     // blob -> document ; document -> first blob (n_docs + 1)
+    std::vector<u32> doc_nprior;              // lb_docset_import: leading blobs of each document that restate its earlier state
     DocInfo* d_docs = nullptr;
     BlockInfo* d_blocks = nullptr;
     DocPeer* d_dpeer = nullptr;
@@ -314,6 +331,24 @@ struct lb_batch {
     cudaEvent_t ev[16];
     int n_ev = 0;
     bool ev_created = false;
+};
+
+// Persistent documents (lb_docset_*): what a document keeps between imports is its change store in wire form -- the
+// FastUpdates blob it would export (ExportMode::all_updates), resident in device memory -- exactly what the reference's
+// ChangeStore keeps (encoded blocks in a kv store, change_store.rs:60-110).  A document that still has pending changes
+// keeps the blobs it was built from instead (pending changes are not part of an export).
+struct DocsetBuf {     // one device buffer per import generation, shared by the documents stored in it
+    u8* d = nullptr;
+    size_t bytes = 0;
+    ~DocsetBuf() { if (d) cudaFree(d); }
+};
+struct DocsetBlob { std::shared_ptr<DocsetBuf> buf; u64 off; u32 len; };
+struct DocsetDoc { std::vector<DocsetBlob> blobs; };
+struct lb_docset {
+    int device = 0;
+    std::mutex mu;
+    std::unordered_map<u64, DocsetDoc> docs;
+    u64 stored_bytes = 0;
 };
 
 namespace {
@@ -381,12 +416,17 @@ void pipeline(lb_batch* b) {
     CK(cudaMemcpyAsync(d_doc_blob0, b->doc_blob0.data(), sizeof(u32) * (D + 1), cudaMemcpyHostToDevice, st));
     LB_LAUNCH(k_frame_count, nblk((u64)Q * 32, 128), 128, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_code, d_blob_nblocks);
     run_scans(b, {ScanJob{(const u8*)d_blob_nblocks, (u8*)d_blob_block0, 4, 8, Q}});
-    LB_LAUNCH(k_frame_docs, nblk(D), TPB, 0, st, D, d_doc_blob0, d_blob_code, d_blob_block0, b->d_docs);
+    u32* d_doc_nprior = nullptr;
+    if (!b->doc_nprior.empty()) {
+        d_doc_nprior = dv.alloc<u32>(D + 1);
+        CK(cudaMemcpyAsync(d_doc_nprior, b->doc_nprior.data(), sizeof(u32) * D, cudaMemcpyHostToDevice, st));
+    }
+    LB_LAUNCH(k_frame_docs, nblk(D), TPB, 0, st, D, d_doc_blob0, d_blob_code, d_blob_block0, d_doc_nprior, b->d_docs);
     tm.kernel_launches += 2;
     u64 B = d2h_one(b, d_blob_block0 + Q);
     b->n_blocks = B;
     b->d_blocks = dv.alloc<BlockInfo>(B + 1, true);
-    LB_LAUNCH(k_frame_fill, nblk(Q), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_doc, d_blob_code, d_blob_block0, b->d_blocks);
+    LB_LAUNCH(k_frame_fill, nblk(Q), TPB, 0, st, b->d_bytes, b->d_offs, b->d_lens, Q, d_blob_doc, d_blob_code, d_blob_block0, d_doc_blob0, b->d_blocks);
     tm.kernel_launches += 1;
     mark(b);  // [1] frame done
     // ------------------------------------------------------------ phase 2: decode
@@ -474,6 +514,14 @@ void pipeline(lb_batch* b) {
     rt.ch_walk = dv.alloc<u32>(NCH);
     rt.ch_pos = dv.alloc<u32>(NCH, true);
     rt.ch_trim = dv.alloc<u32>(NCH, true);
+    // status of multi-blob documents (import_batch groups, lb_docset_import): per-copy epochs, per-blob pending hulls
+    i32* d_pend_scratch = nullptr;
+    if (Q > D) {
+        rt.ch_epoch = dv.alloc<u32>(NCH);
+        rt.ch_maxend = dv.alloc<i32>(NCH);
+        rt.head_lamport = dv.alloc<u32>(NP);
+        d_pend_scratch = dv.alloc<i32>(2 * (u64)Q + 2);
+    }
     LB_LAUNCH(k_doc_tables, nblk(D, 64), 64, 0, st, b->d_bytes, b->d_docs, D, blk, rt);
     u32* d_tmp_a = dv.alloc<u32>(D + 1, true);
     u32* d_tmp_b = dv.alloc<u32>(D + 1, true);
@@ -484,7 +532,7 @@ void pipeline(lb_batch* b) {
     u64 VV = d2h_one(b, &b->d_docs[D].vv0);
     rt.ch_vv = dv.alloc<i32>(VV);
     u32* d_cursor = dv.alloc<u32>(NP);
-    LB_LAUNCH(k_doc_causal, nblk(D, 64), 64, 0, st, b->d_docs, D, blk, rt, d_cursor);
+    LB_LAUNCH(k_doc_causal, nblk(D, 64), 64, 0, st, b->d_docs, D, blk, rt, d_cursor, d_doc_blob0, d_pend_scratch);
     LB_LAUNCH(k_doc_frontiers, nblk(D, 64), 64, 0, st, b->d_docs, D, rt);
     LB_LAUNCH(k_doc_sizes, nblk(D), TPB, 0, st, b->d_docs, D, d_tmp_a, d_tmp_b, d_tmp_c, 1);
     tm.kernel_launches += 3;
@@ -788,10 +836,8 @@ void build_status(lb_batch* b) {
         if (di.code != DOC_OK && di.code != DOC_ERR_UNSUPPORTED) continue;
         for (u32 p = 0; p < di.P; p++) {
             const DocPeer& dp = b->dpeer[di.peer0 + p];
-            if (dp.end_counter > 0) {
-                b->success[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
-                b->vv[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
-            }
+            if (dp.has_succ) b->success[d].push_back(lb_id_span{dp.id, dp.succ_lo, dp.end_counter});
+            if (dp.end_counter > 0) b->vv[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
             if (dp.pend_hi > dp.pend_lo) b->pending[d].push_back(lb_id_span{dp.id, dp.pend_lo, dp.pend_hi});
             if (dp.is_head && dp.end_counter > 0) b->frontiers[d].push_back(lb_id_span{dp.id, dp.end_counter - 1, dp.end_counter});
         }
@@ -953,27 +999,86 @@ lb_status export_from(lb_batch* b, size_t doc, const lb_id_span* from, size_t n_
 
 }  // namespace
 
+// After an import into a docset: every document of the batch whose import succeeded gets its new stored form -- the
+// blob it re-exports (ExportMode::all_updates) when nothing is pending and the export phase covers it, otherwise the
+// blobs it was built from (earlier state first), copied out of the batch's byte buffer.  A document whose import failed
+// (checksum, decode, ...) keeps its earlier state: the reference rejects such an import before any state change.
+void docset_store(lb_docset* set, lb_batch* b, const std::vector<u64>& offs, const std::vector<u32>& lens) {
+    const size_t nd = b->n_docs;
+    struct Pick { size_t doc; bool exported; };
+    std::vector<Pick> picks;
+    u64 total = 0;
+    for (size_t d = 0; d < nd; d++) {
+        const DocInfo& di = b->docs[d];
+        if (di.code != DOC_OK && di.code != DOC_ERR_UNSUPPORTED) continue;
+        bool exported = di.code == DOC_OK && di.n_pending == 0 && d < b->xdocs.size() && !(b->xdocs[d].flags & 1) && b->xdocs[d].exp_len > 0;
+        picks.push_back(Pick{d, exported});
+        if (exported) total += ((u64)b->xdocs[d].exp_len + 15) & ~(u64)15;
+        else for (u32 q = b->doc_blob0[d]; q < b->doc_blob0[d + 1]; q++) total += ((u64)lens[q] + 15) & ~(u64)15;
+    }
+    if (picks.empty()) return;
+    auto buf = std::make_shared<DocsetBuf>();
+    buf->bytes = total + 64;
+    if (cudaMalloc((void**)&buf->d, buf->bytes) != cudaSuccess) {
+        cudaGetLastError();
+        g_last_error = "docset: out of device memory for the stored documents";
+        throw lb_status(LB_ERR_OOM);
+    }
+    std::vector<CopySeg> segs;
+    std::vector<std::pair<u64, DocsetDoc>> fresh;
+    u64 w = 0;
+    for (const Pick& pk : picks) {
+        DocsetDoc nd_;
+        auto push = [&](const u8* src, u32 len) {
+            segs.push_back(CopySeg{src, buf->d + w, len});
+            nd_.blobs.push_back(DocsetBlob{buf, w, len});
+            w += ((u64)len + 15) & ~(u64)15;
+        };
+        if (pk.exported) push(b->d_export + b->xdocs[pk.doc].exp_off, b->xdocs[pk.doc].exp_len);
+        else for (u32 q = b->doc_blob0[pk.doc]; q < b->doc_blob0[pk.doc + 1]; q++) push(b->d_bytes + offs[q], lens[q]);
+        fresh.push_back({b->doc_ids[pk.doc], std::move(nd_)});
+    }
+    CopySeg* d_segs = b->dev.alloc<CopySeg>(segs.size());
+    CK(cudaMemcpyAsync(d_segs, segs.data(), sizeof(CopySeg) * segs.size(), cudaMemcpyHostToDevice, b->dev.stream));
+    LB_LAUNCH(k_copy_segments, nblk((u64)segs.size() * 32, 128), 128, 0, b->dev.stream, d_segs, (u32)segs.size());
+    CK(cudaStreamSynchronize(b->dev.stream));
+    for (auto& kv : fresh) {
+        DocsetDoc& slot = set->docs[kv.first];
+        for (const DocsetBlob& ob : slot.blobs) set->stored_bytes -= ob.len;
+        slot = std::move(kv.second);
+        for (const DocsetBlob& nb : slot.blobs) set->stored_bytes += nb.len;
+    }
+}
+
 extern "C" {
 
-lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out) {
+// Host-buffer import, shared by lb_import_batch (fresh documents) and lb_docset_import (documents with an earlier state:
+// their stored blobs come first, already in device memory, and count as `n_prior` for the import status).
+static lb_status import_host(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_docset* set, lb_batch** out) {
     if (!out || (!blobs && n_blobs)) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
     *out = nullptr;
-    lb_status s = check_device(opt);
+    lb_options o2;
+    memset(&o2, 0, sizeof(o2));
+    if (opt) o2 = *opt;
+    if (set) { o2.device = set->device; o2.flags |= LB_FLAG_EXPORT; }   // the re-export is what a stored document keeps
+    lb_status s = check_device(&o2);
     if (s != LB_OK) return s;
     if (n_blobs >= 0x7FFFFFFFull) { g_last_error = "too many blobs"; return LB_ERR_INVALID_ARG; }
     lb_batch* b = new lb_batch();
     b->n_docs = n_blobs;
-    b->flags = opt ? opt->flags : 0;
-    b->device = opt ? opt->device : 0;
+    b->flags = o2.flags;
+    b->device = o2.device;
     b->eager_json = true;   // host buffers in, host results expected
     try {
         init_batch(b);
         // blobs with the same doc_id form one document (LoroDoc::import_batch); documents are numbered in order of
         // first appearance and their blobs laid out consecutively, in the order given
         std::vector<u32> order(n_blobs);
+        std::vector<u32> host_count;
         {
             std::unordered_map<u64, u32> doc_of;
-            std::vector<u32> doc_idx(n_blobs), count;
+            std::vector<u32> doc_idx(n_blobs);
+            std::vector<u32>& count = host_count;
             for (size_t i = 0; i < n_blobs; i++) {
                 auto it = doc_of.find(blobs[i].doc_id);
                 if (it == doc_of.end()) {
@@ -985,21 +1090,15 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
                 count[it->second]++;
             }
             size_t nd = count.size();
-            b->n_docs = nd;
-            b->doc_blob0.assign(nd + 1, 0);
-            for (size_t d = 0; d < nd; d++) b->doc_blob0[d + 1] = b->doc_blob0[d] + count[d];
-            std::vector<u32> cursor(b->doc_blob0.begin(), b->doc_blob0.end() - 1);
-            b->blob_doc.resize(n_blobs);
-            for (size_t i = 0; i < n_blobs; i++) {
-                u32 q = cursor[doc_idx[i]]++;
-                order[q] = (u32)i;
-                b->blob_doc[q] = doc_idx[i];
-            }
+            std::vector<u32> first(nd + 1, 0);
+            for (size_t d = 0; d < nd; d++) first[d + 1] = first[d] + count[d];
+            std::vector<u32> cursor(first.begin(), first.end() - 1);
+            for (size_t i = 0; i < n_blobs; i++) order[cursor[doc_idx[i]]++] = (u32)i;
             // import_batch imports its blobs sorted by (mode, number of changes descending), stably
             // (loro.rs:1194-1202): the order decides where payloads land in the document's arenas, which the
             // re-export merge rules look at
             for (size_t d = 0; d < nd; d++) {
-                u32 q0 = b->doc_blob0[d], q1 = b->doc_blob0[d + 1];
+                u32 q0 = first[d], q1 = first[d + 1];
                 if (q1 - q0 < 2) continue;
                 std::vector<std::pair<std::pair<u32, i64>, u32>> keyed;
                 for (u32 q = q0; q < q1; q++) {
@@ -1009,48 +1108,130 @@ lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options
                 std::stable_sort(keyed.begin(), keyed.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
                 for (u32 q = q0; q < q1; q++) order[q] = keyed[q - q0].second;
             }
+            b->n_docs = nd;
         }
-        b->n_blobs = n_blobs;
-        std::vector<u64> offs(n_blobs + 1);
-        std::vector<u32> lens(n_blobs + 1, 0);
-        u64 total = 0;
-        for (size_t q = 0; q < n_blobs; q++) {
-            const lb_blob& bl = blobs[order[q]];
-            if (bl.len > 0xFFFFFFF0ull || (!bl.ptr && bl.len)) {
-                g_last_error = "blob too large or null";
-                throw lb_status(LB_ERR_INVALID_ARG);
+        const size_t nd = b->n_docs;
+        // the blob list of the batch: per document, its stored blobs (device) then the new ones (host)
+        std::vector<DocsetDoc*> prior(nd, nullptr);
+        size_t n_prior_total = 0;
+        if (set) {
+            b->doc_nprior.assign(nd, 0);
+            for (size_t d = 0; d < nd; d++) {
+                auto it = set->docs.find(b->doc_ids[d]);
+                if (it == set->docs.end()) continue;
+                prior[d] = &it->second;
+                b->doc_nprior[d] = (u32)it->second.blobs.size();
+                n_prior_total += it->second.blobs.size();
             }
-            offs[q] = total;
-            lens[q] = (u32)bl.len;
-            total += (bl.len + 15) & ~(u64)15;
-            b->counters.blob_bytes += bl.len;
         }
-        offs[n_blobs] = total;
+        const size_t Q = n_blobs + n_prior_total;
+        if (Q >= 0x7FFFFFFFull) { g_last_error = "too many blobs"; throw lb_status(LB_ERR_INVALID_ARG); }
+        b->n_blobs = Q;
+        b->doc_blob0.assign(nd + 1, 0);
+        b->blob_doc.resize(Q);
+        std::vector<u64> offs(Q + 1);
+        std::vector<u32> lens(Q + 1, 0);
+        std::vector<lbstage::BlobView> views;      // host blobs, with their offsets in the batch buffer
+        std::vector<u64> view_offs;
+        std::vector<CopySeg> segs;                 // stored blobs: device-to-device (dst filled in below)
+        std::vector<u64> seg_offs;
+        views.reserve(n_blobs);
+        view_offs.reserve(n_blobs + 1);
+        // the host blobs fill [0, H) of the batch buffer in one contiguous upload, the stored blobs follow
+        u64 total = 0, ptotal = 0;
+        for (size_t i = 0; i < n_blobs; i++) ptotal += (blobs[i].len + 15) & ~(u64)15;
+        size_t q = 0, hq = 0;
+        for (size_t d = 0; d < nd; d++) {
+            b->doc_blob0[d] = (u32)q;
+            if (prior[d])
+                for (const DocsetBlob& sb : prior[d]->blobs) {
+                    offs[q] = ptotal;
+                    lens[q] = sb.len;
+                    b->blob_doc[q] = (u32)d;
+                    segs.push_back(CopySeg{sb.buf->d + sb.off, nullptr, sb.len});
+                    seg_offs.push_back(ptotal);
+                    ptotal += ((u64)sb.len + 15) & ~(u64)15;
+                    b->counters.blob_bytes += sb.len;
+                    q++;
+                }
+            for (u32 k = 0; k < host_count[d]; k++, hq++) {
+                const lb_blob& bl = blobs[order[hq]];
+                if (bl.len > 0xFFFFFFF0ull || (!bl.ptr && bl.len)) {
+                    g_last_error = "blob too large or null";
+                    throw lb_status(LB_ERR_INVALID_ARG);
+                }
+                offs[q] = total;
+                lens[q] = (u32)bl.len;
+                b->blob_doc[q] = (u32)d;
+                views.push_back(lbstage::BlobView{bl.ptr, bl.len});
+                view_offs.push_back(total);
+                total += (bl.len + 15) & ~(u64)15;
+                b->counters.blob_bytes += bl.len;
+                q++;
+            }
+        }
+        b->doc_blob0[nd] = (u32)q;
+        offs[Q] = ptotal;
+        view_offs.push_back(total);
+        total = ptotal;
         // stage through the pinned ring: host gather of slot k overlaps the DMA of slot k-1 (host_stage.hpp)
-        std::vector<lbstage::BlobView> views(n_blobs);
-        for (size_t q = 0; q < n_blobs; q++) views[q] = lbstage::BlobView{blobs[order[q]].ptr, blobs[order[q]].len};
         CK(cudaEventRecord(b->ev[b->n_ev++], b->dev.stream));  // [0]
         u8* d_bytes = b->dev.alloc<u8>(total + 64);
-        b->d_offs = b->dev.alloc<u64>(n_blobs + 1);
-        b->d_lens = b->dev.alloc<u32>(n_blobs + 1);
-        if (!lbstage::upload_blobs(views.data(), offs.data(), n_blobs, d_bytes, b->dev.stream)) {
+        b->d_offs = b->dev.alloc<u64>(Q + 1);
+        b->d_lens = b->dev.alloc<u32>(Q + 1);
+        if (!segs.empty()) {
+            for (size_t k = 0; k < segs.size(); k++) segs[k].dst = d_bytes + seg_offs[k];
+            CopySeg* d_segs = b->dev.alloc<CopySeg>(segs.size());
+            CK(cudaMemcpyAsync(d_segs, segs.data(), sizeof(CopySeg) * segs.size(), cudaMemcpyHostToDevice, b->dev.stream));
+            LB_LAUNCH(k_copy_segments, nblk((u64)segs.size() * 32, 128), 128, 0, b->dev.stream, d_segs, (u32)segs.size());
+            CK(cudaStreamSynchronize(b->dev.stream));   // `segs` is pageable host memory
+        }
+        if (!views.empty() && !lbstage::upload_blobs(views.data(), view_offs.data(), views.size(), d_bytes, b->dev.stream)) {
             g_last_error = "h2d staging failed";
             throw lb_status(LB_ERR_CUDA);
         }
-        CK(cudaMemcpyAsync(b->d_offs, offs.data(), sizeof(u64) * (n_blobs + 1), cudaMemcpyHostToDevice, b->dev.stream));
-        CK(cudaMemcpyAsync(b->d_lens, lens.data(), sizeof(u32) * (n_blobs + 1), cudaMemcpyHostToDevice, b->dev.stream));
+        CK(cudaMemcpyAsync(b->d_offs, offs.data(), sizeof(u64) * (Q + 1), cudaMemcpyHostToDevice, b->dev.stream));
+        CK(cudaMemcpyAsync(b->d_lens, lens.data(), sizeof(u32) * (Q + 1), cudaMemcpyHostToDevice, b->dev.stream));
         b->d_bytes = d_bytes;
         b->timings.decode_bytes_read = b->counters.blob_bytes;
         mark(b);  // [1] h2d done (index 0 = start)
         // event indices: 0 start,1 h2d,2 frame,3 decode,4 resolve,5 classify,6 integrate,7 materialise,8 d2h
         s = run_batch(b);
         CK(cudaStreamSynchronize(b->dev.stream));
+        if (s == LB_OK && set) docset_store(set, b, offs, lens);
     } catch (lb_status e) {
         s = e;
     }
     if (s != LB_OK) { lb_batch_free(b); return s; }
     *out = b;
     return LB_OK;
+}
+
+lb_status lb_import_batch(const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out) {
+    return import_host(blobs, n_blobs, opt, nullptr, out);
+}
+
+lb_status lb_docset_new(const lb_options* opt, lb_docset** out) {
+    if (!out) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    lb_status s = check_device(opt);
+    if (s != LB_OK) return s;
+    lb_docset* set = new lb_docset();
+    set->device = opt ? opt->device : 0;
+    *out = set;
+    return LB_OK;
+}
+
+void lb_docset_free(lb_docset* set) { delete set; }
+
+size_t lb_docset_doc_count(const lb_docset* set) { return set ? set->docs.size() : 0; }
+
+uint64_t lb_docset_stored_bytes(const lb_docset* set) { return set ? set->stored_bytes : 0; }
+
+lb_status lb_docset_import(lb_docset* set, const lb_blob* blobs, size_t n_blobs, const lb_options* opt, lb_batch** out) {
+    if (!set) { g_last_error = "null argument"; return LB_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> g(set->mu);
+    return import_host(blobs, n_blobs, opt, set, out);
 }
 
 lb_status lb_import_batch_device(const uint8_t* d_bytes, const uint64_t* offsets, const uint32_t* blob_lens,

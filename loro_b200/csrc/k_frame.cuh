@@ -141,7 +141,8 @@ __global__ void k_frame_count(const u8* __restrict__ bytes, const u64* __restric
 // first blob that fails decides the document's code (header, checksum and mode are checked before any state
 // change: loro.rs:584)
 __global__ void k_frame_docs(u32 n_docs, const u32* __restrict__ doc_blob0, const u32* __restrict__ blob_code,
-                             const u64* __restrict__ blob_block0, DocInfo* __restrict__ docs) {
+                             const u64* __restrict__ blob_block0, const u32* __restrict__ doc_nprior,
+                             DocInfo* __restrict__ docs) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     u32 q0 = doc_blob0[d], q1 = doc_blob0[d + 1];
@@ -151,13 +152,14 @@ __global__ void k_frame_docs(u32 n_docs, const u32* __restrict__ doc_blob0, cons
     docs[d].b0 = (u32)blob_block0[q0];
     docs[d].b1 = (u32)blob_block0[q1];
     docs[d].n_blobs = q1 - q0;
+    docs[d].n_prior = doc_nprior ? doc_nprior[d] : 0;   // blobs that restate the document's earlier state (lb_docset_import)
 }
 
 // thread per blob: emit block descriptors at the scanned positions.
 __global__ void k_frame_fill(const u8* __restrict__ bytes, const u64* __restrict__ offs,
                              const u32* __restrict__ lens, u32 n_blobs, const u32* __restrict__ blob_doc,
                              const u32* __restrict__ blob_code, const u64* __restrict__ blob_block0,
-                             BlockInfo* __restrict__ blocks) {
+                             const u32* __restrict__ doc_blob0, BlockInfo* __restrict__ blocks) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_blobs) return;
     if (blob_code[q] != DOC_OK) return;
@@ -170,6 +172,7 @@ __global__ void k_frame_fill(const u8* __restrict__ bytes, const u64* __restrict
         BlockInfo& bi = blocks[i++];
         bi.doc = blob_doc[q];
         bi.err = 0;
+        bi.blob_rank = q - doc_blob0[blob_doc[q]];
         bi.off = offs[q] + (u64)(c.p - b);
         bi.len = (u32)len;
         c.skip(len);

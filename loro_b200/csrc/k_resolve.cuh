@@ -35,7 +35,16 @@ struct ResolveTables {
     u32* ch_pos;         // per change: its position in the doc's ch_order (= row of ch_vv)
     u32* ch_trim;        // per change: leading atoms the document already had when the change arrived
                          // (OpLog::trim_the_known_part_of_change, oplog.rs:181-196: the rest is applied as a slice)
+    u32* ch_epoch;       // per change COPY of a multi-blob document: the rank of the blob during whose import the reference
+                         // can first apply it (its own blob, or the later one that brings its last missing dependency:
+                         // blobs of a document are imported one after the other, loro.rs:1183-1290, and parked changes wait
+                         // in the pending store, pending_changes.rs); bit 31: in that blob's FIRST pass
+                         // (import_changes_to_oplog) rather than by its try_apply_pending
+    i32* ch_maxend;      // per position of the per-peer change lists: highest counter end among the entries up to there
+    u32* head_lamport;   // per doc peer: lamport of the first atom of the copy at the status pass's cursor
 };
+#define EPOCH_FP 0x80000000u
+#define EPOCH_NEVER 0x7FFFFFFFu
 
 __device__ inline bool bytes_eq(const u8* a, const u8* b, u32 n) {
     for (u32 i = 0; i < n; i++)
@@ -81,7 +90,8 @@ __global__ void k_doc_tables(const u8* __restrict__ bytes, DocInfo* __restrict__
                 DocPeer np;
                 np.id = id;
                 np.rank = 0;
-                np.first_counter = 0;
+                np.succ_lo = 0;
+                np.has_succ = 0;
                 np.end_counter = 0;
                 np.max_counter = 0;
                 np.atom_base = 0;
@@ -223,22 +233,76 @@ __device__ inline bool lamport_of(const DocInfo& di, const ResolveTables& t, u32
         if (t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + mid]] <= c) lo = mid;
         else hi = mid;
     }
-    // duplicates (the same change delivered twice inside an import_batch) sort next to each other: the first one
-    // is the one that was applied
-    while (lo > 0 && t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + lo - 1]] == t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + lo]]) lo--;
-    // a re-delivered or sliced copy (export from a version vector cuts a change: A[3..10) next to A[0..10)) was
-    // dropped, not applied: the applied change that covers c sorts before it
-    while (lo > 0 && !t.ch_applied[t.ch_order[di.ch0 + dp.ch_first + lo]]) lo--;
+    // `lo` is the last entry that starts at or before c.  Copies the walk dropped (the same change delivered twice, a
+    // sliced copy A[3..10) next to A[0..10) from an export cut at a version vector) and the head of a change applied as a
+    // slice (its first ch_trim atoms were already there) do not count: applied ranges are disjoint and in counter
+    // order, so the first applied entry, going back, whose applied range starts at or before c is the only candidate
+    while (lo > 0) {
+        u32 x = t.ch_order[di.ch0 + dp.ch_first + lo];
+        if (t.ch_applied[x] && c >= t.ch_counter[x] + (i32)t.ch_trim[x]) break;
+        lo--;
+    }
     u32 ch = t.ch_order[di.ch0 + dp.ch_first + lo];
-    if (!t.ch_applied[ch] || c < t.ch_counter[ch] || c >= t.ch_counter[ch] + (i32)t.ch_len[ch]) return false;
+    if (!t.ch_applied[ch] || c < t.ch_counter[ch] + (i32)t.ch_trim[ch] || c >= t.ch_counter[ch] + (i32)t.ch_len[ch]) return false;
     *out = t.ch_lamport[ch] + (u32)(c - t.ch_counter[ch]);
     *ch_out = ch;
     return true;
 }
 
 // thread per doc: pending detection, lamport recomputation, replay order, per-change version vectors.
+// ---- import status of multi-blob documents.  T(copy) = max(rank of its blob, epoch of every atom it depends on);
+// epoch(atom) = min T over the copies that cover it (whichever copy the reference meets first applies the atom, later
+// ones are skipped or trimmed: oplog.rs:181-196); first-pass flag likewise.  Copies are visited in the order of the
+// lamport of their first atom (a merge of the per-peer lists), so every copy covering a dependency has its T by then.
+#define EPOCH_SCAN_CAP 512   // covering copies looked at per atom: a document with more copies stacked on one atom gets an
+                             // approximate status (never a wrong state)
+__device__ inline u32 atom_epoch(const DocInfo& di, const ResolveTables& t, u32 p, i32 c) {
+    const DocPeer& dp = t.dpeer[di.peer0 + p];
+    if (c < 0 || c >= dp.end_counter) return EPOCH_NEVER;
+    const u32* lst = t.ch_order + di.ch0 + dp.ch_first;
+    const i32* mx = t.ch_maxend + di.ch0 + dp.ch_first;
+    u32 lo = 0, hi = dp.ch_count;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (t.ch_counter[lst[mid]] <= c) lo = mid; else hi = mid;
+    }
+    u32 best = EPOCH_NEVER;
+    for (u32 n = 0; n < EPOCH_SCAN_CAP; n++) {
+        if (mx[lo] <= c) break;                      // nothing at or before `lo` reaches c
+        u32 x = lst[lo];
+        if (c < t.ch_counter[x] + (i32)t.ch_len[x]) {
+            u32 e = t.ch_epoch[x];
+            if ((e & ~EPOCH_FP) < (best & ~EPOCH_FP)) best = e;
+            else if ((e & ~EPOCH_FP) == (best & ~EPOCH_FP)) best |= e & EPOCH_FP;
+        }
+        if (lo == 0) break;
+        lo--;
+    }
+    return best;
+}
+__device__ inline u32 copy_epoch(const DocInfo& di, const ResolveTables& t, const BlockInfo* blocks, u32 ch, u32 p) {
+    const BlockInfo& bi = blocks[t.ch_block[ch]];
+    const u32 k = bi.blob_rank;
+    u32 E = k;
+    bool fp = true;
+    const u32 nd = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
+    for (u32 j = 0; j < nd; j++) {
+        u32 dpi;
+        i32 dc;
+        if (j == t.ch_ndeps[ch]) { dpi = p; dc = t.ch_counter[ch] - 1; }
+        else { dpi = t.peer_map[bi.peer0 + t.dep_peer_idx[t.ch_dep0[ch] + j]]; dc = t.dep_counter[t.ch_dep0[ch] + j]; }
+        u32 ed = atom_epoch(di, t, dpi, dc);
+        u32 e = ed & ~EPOCH_FP;
+        if (e >= EPOCH_NEVER) return EPOCH_NEVER;
+        if (e > E) E = e;
+        if (e > k || (e == k && !(ed & EPOCH_FP))) fp = false;
+    }
+    return E | (fp ? EPOCH_FP : 0u);
+}
+
 __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const BlockInfo* __restrict__ blocks,
-                             ResolveTables t, u32* __restrict__ peer_cursor) {
+                             ResolveTables t, u32* __restrict__ peer_cursor, const u32* __restrict__ doc_blob0,
+                             i32* __restrict__ pend_scratch) {
     u32 d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     DocInfo di = docs[d];
@@ -336,20 +400,103 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
         cur = pick;
     }
     di.n_applied = walk_n;
-    // ---- pending bookkeeping + atom bases
+    // ---- import status + atom bases.  ImportStatus of LoroDoc::import_batch (loro.rs:1183-1290) folds the statuses of
+    // the blobs imported one after the other: success[peer] = (start of the first blob that applied something of the
+    // peer, highest end) -- atoms of a peer apply in counter order, so that is [first counter a new blob applied, end);
+    // pending[peer] = (min start, MIN end) over the blobs of the hull of the changes each blob parked in its first pass
+    // (encoding.rs:252-257), whether or not a later step released them.  Blobs below n_prior restate the earlier state
+    // of the document (lb_docset_import) and report nothing.
+    const bool multi = di.n_blobs > 1 && t.ch_maxend && pend_scratch;
+    if (multi) {
+        // T of every copy, in the order of the lamport of its first atom
+        for (u32 p = 0; p < P; p++) {
+            const DocPeer& dp = t.dpeer[di.peer0 + p];
+            i32 m = -1;
+            for (u32 k = 0; k < dp.ch_count; k++) {
+                u32 ch = t.ch_order[di.ch0 + dp.ch_first + k];
+                i32 e = t.ch_counter[ch] + (i32)t.ch_len[ch];
+                if (e > m) m = e;
+                t.ch_maxend[di.ch0 + dp.ch_first + k] = m;
+                t.ch_epoch[ch] = EPOCH_NEVER;
+            }
+            cursor[p] = 0;
+            t.head_lamport[di.peer0 + p] = 0xFFFFFFFFu;
+            if (dp.ch_count) {
+                u32 l, c2;
+                if (lamport_of(di, t, p, t.ch_counter[t.ch_order[di.ch0 + dp.ch_first]], &l, &c2)) t.head_lamport[di.peer0 + p] = l;
+            }
+        }
+        while (true) {
+            u32 bp = 0xFFFFFFFFu, bl = 0xFFFFFFFFu;
+            for (u32 p = 0; p < P; p++) {
+                u32 l = t.head_lamport[di.peer0 + p];
+                if (l < bl) { bl = l; bp = p; }
+            }
+            if (bp == 0xFFFFFFFFu) break;      // what is left starts beyond the document's version: never applied
+            const DocPeer& dp = t.dpeer[di.peer0 + bp];
+            u32 ch = t.ch_order[di.ch0 + dp.ch_first + cursor[bp]];
+            t.ch_epoch[ch] = copy_epoch(di, t, blocks, ch, bp);
+            cursor[bp]++;
+            u32 nl = 0xFFFFFFFFu;
+            if (cursor[bp] < dp.ch_count) {
+                u32 l, c2;
+                if (lamport_of(di, t, bp, t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + cursor[bp]]], &l, &c2)) nl = l;
+            }
+            t.head_lamport[di.peer0 + bp] = nl;
+        }
+    }
     u32 base = 0;
+    const u32 nb_new = di.n_blobs - di.n_prior;
+    i32* hull = (multi && nb_new > 1) ? pend_scratch + 2 * (u64)(doc_blob0[d] + di.n_prior) : nullptr;
     for (u32 p = 0; p < P; p++) {
         DocPeer& dp = t.dpeer[di.peer0 + p];
         dp.atom_base = base;
         base += (u32)dp.end_counter;
         dp.pend_lo = dp.pend_hi = 0;
-        for (u32 k = cursor[p]; k < dp.ch_count; k++) {
+        dp.has_succ = 0;
+        dp.succ_lo = 0;
+        if (hull) for (u32 k = 0; k < nb_new; k++) { hull[2 * k] = 0x7FFFFFFF; hull[2 * k + 1] = -1; }
+        i32 prior_end = -1;     // the atoms below it were in the document before this import
+        for (u32 k = 0; k < dp.ch_count; k++) {
             u32 ch = t.ch_order[di.ch0 + dp.ch_first + k];
             i32 c0 = t.ch_counter[ch], c1 = c0 + (i32)t.ch_len[ch];
-            if (c1 <= dp.end_counter) continue;
-            if (dp.pend_lo == dp.pend_hi) { dp.pend_lo = c0 < dp.end_counter ? dp.end_counter : c0; dp.pend_hi = c1; }
+            const u32 rank = blocks[t.ch_block[ch]].blob_rank;
+            bool parked;
+            if (!multi) {
+                // one blob: what it cannot apply stays parked, everything else applies in its first pass
+                if (t.ch_applied[ch]) { if (prior_end < 0) prior_end = c0 + (i32)t.ch_trim[ch]; continue; }
+                if (c1 <= dp.end_counter) continue;
+                parked = true;
+                di.n_pending++;
+            } else {
+                u32 e = t.ch_epoch[ch];
+                if ((e & ~EPOCH_FP) < di.n_prior) { if (c1 > prior_end) prior_end = c1; }
+                else if (prior_end < 0 && t.ch_applied[ch] && di.n_prior == 0) prior_end = c0 + (i32)t.ch_trim[ch];
+                if (!t.ch_applied[ch] && c1 > dp.end_counter) di.n_pending++;
+                if ((e & ~EPOCH_FP) >= EPOCH_NEVER) parked = true;
+                else {
+                    // known when its own blob arrived (all of it applied by an earlier blob)?  then it was skipped
+                    if ((atom_epoch(di, t, p, c1 - 1) & ~EPOCH_FP) < rank) continue;
+                    parked = !(e & EPOCH_FP);
+                }
+            }
+            if (!parked || rank < di.n_prior) continue;
+            if (hull) {
+                i32* h = hull + 2 * (rank - di.n_prior);
+                if (c0 < h[0]) h[0] = c0;
+                if (c1 > h[1]) h[1] = c1;
+            } else if (dp.pend_lo == dp.pend_hi) { dp.pend_lo = c0; dp.pend_hi = c1; }
             else { if (c0 < dp.pend_lo) dp.pend_lo = c0; if (c1 > dp.pend_hi) dp.pend_hi = c1; }
-            di.n_pending++;
+        }
+        if (prior_end < 0) prior_end = 0;
+        if (dp.end_counter > prior_end) { dp.has_succ = 1; dp.succ_lo = prior_end; }
+        if (hull) {
+            bool any = false;
+            for (u32 k = 0; k < nb_new; k++) {
+                if (hull[2 * k + 1] < 0) continue;
+                if (!any) { dp.pend_lo = hull[2 * k]; dp.pend_hi = hull[2 * k + 1]; any = true; }
+                else { if (hull[2 * k] < dp.pend_lo) dp.pend_lo = hull[2 * k]; if (hull[2 * k + 1] < dp.pend_hi) dp.pend_hi = hull[2 * k + 1]; }
+            }
         }
     }
     di.atom_total = base;

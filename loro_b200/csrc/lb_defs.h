@@ -9,6 +9,8 @@
 struct BlockInfo {
     u32 doc;
     u32 err;            // DOC_* code raised while parsing this block
+    u32 blob_rank;      // index of the block's blob among the blobs of its document (import order)
+    u32 pad_rank;
     u64 off;            // byte offset of the block inside the batch byte buffer
     u32 len;
     u32 counter_start, counter_len, lamport_start, lamport_len, n_changes;
@@ -49,7 +51,8 @@ struct DocInfo {
     u32 n_blobs;        // blobs imported into this document (import_batch)
     u32 has_unsupported;
     u32 has_tree;       // any applied movable-tree op (k_tree.cuh)
-    u32 pad2;
+    u32 n_prior;        // the first n_prior blobs are the document's EARLIER state (lb_docset_import): the import
+                        // status reports what the remaining blobs added to it
     u64 tree0;          // base into the per-document tree node tables (atom_total + C slots)
     u64 json_off;
     u32 json_len;
@@ -60,7 +63,7 @@ struct DocInfo {
 struct DocPeer {
     u64 id;
     u32 rank;          // rank of id among the doc's peers (ascending)
-    i32 first_counter; // first imported counter (0 for a fresh doc when nothing is missing)
+    i32 succ_lo;       // ImportStatus.success = [succ_lo, end_counter) when has_succ (first counter the import added)
     i32 end_counter;   // vv after import (exclusive)
     i32 max_counter;   // highest counter end seen in the blob (incl. pending)
     u32 atom_base;     // offset of this peer's atoms inside the doc's atom arrays
@@ -68,7 +71,7 @@ struct DocPeer {
     u32 ch_count;
     i32 pend_lo, pend_hi;  // pending counter range (lo<hi when any)
     u32 is_head;           // the peer's last imported id is a frontier of the document (version/frontiers.rs:233-246)
-    u32 pad_;
+    u32 has_succ;          // some change of this peer was applied by the (new) blobs of this import
 };
 
 // doc-level container entry (reference: ContainerID, loro-common/src/lib.rs:114-180)

@@ -108,6 +108,39 @@ class ImportError_(Exception):
         self.code = code
 
 
+def _uleb(b, i):
+    v, sh = 0, 0
+    while True:
+        c = b[i]
+        i += 1
+        v |= (c & 0x7f) << sh
+        sh += 7
+        if not c & 0x80:
+            return v, i
+
+
+def blob_mode(blob):
+    """encode mode of a blob (u16 big endian at [20..22), encoding.rs:299-330); 0xFFFF when too short"""
+    return (blob[20] << 8) | blob[21] if len(blob) >= 22 else 0xFFFF
+
+
+def blob_change_num(blob):
+    """ImportBlobMetadata.change_num of a FastUpdates blob: the sum of the blocks' n_changes (the fifth varint of
+    every EncodedBlock envelope, block_encode.rs:95-119)"""
+    total, i, n = 0, 22, len(blob)
+    try:
+        while i < n:
+            ln, i = _uleb(blob, i)
+            end, j, x = i + ln, i, 0
+            for _ in range(5):
+                x, j = _uleb(blob, j)
+            total += x
+            i = end
+    except IndexError:
+        pass
+    return total
+
+
 class OracleDoc:
     """Mirrors the slice of LoroDoc the hot path needs (crates/loro/src/lib.rs:425-866,1235)."""
 
@@ -276,6 +309,30 @@ class OracleDoc:
             "success": {int(k): tuple(v) for k, v in status["success"].items()},
             "pending": {int(k): tuple(v) for k, v in status["pending"].items()} or None,
         }
+
+    def import_batch(self, blobs):
+        """LoroDoc::import_batch (loro.rs:1183-1290): the blobs are imported one after the other, sorted by
+        (mode, number of changes descending) (stable), and the statuses folded -- success keeps the start of the first
+        blob that reported the peer and the highest end, pending keeps the lowest start and the LOWEST end."""
+        if not blobs:
+            return {"success": {}, "pending": None}
+        if len(blobs) == 1:
+            return self.import_(blobs[0])
+        order = sorted(range(len(blobs)), key=lambda i: (blob_mode(blobs[i]), -blob_change_num(blobs[i])))
+        success, pending, err = {}, {}, None
+        for i in order:
+            try:
+                st = self.import_(blobs[i])
+            except ImportError_ as e:
+                err = e
+                continue
+            for peer, (a, b) in st["success"].items():
+                success[peer] = (success[peer][0], max(success[peer][1], b)) if peer in success else (a, b)
+            for peer, (a, b) in (st["pending"] or {}).items():
+                pending[peer] = (min(pending[peer][0], a), min(pending[peer][1], b)) if peer in pending else (a, b)
+        if err:
+            raise err
+        return {"success": success, "pending": pending or None}
 
     def json_text(self):
         ln = ctypes.c_size_t()

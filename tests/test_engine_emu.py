@@ -190,20 +190,26 @@ def test_import_batch_groups_blobs_by_doc_id():
     for i in order:
         if ids[i] not in first_seen:
             first_seen.append(ids[i])
+    saw_pending = 0
     for k, did in enumerate(first_seen):
         js, tot = want[did - 1000]
+        ost = OracleDoc(77).import_batch([blobs[i] for i in order if ids[i] == did])   # same arrival order as the engine's
         st = b.status(k)
-        assert st.code == 0 and st.pending is None
+        # the status folds the per-blob statuses the way LoroDoc::import_batch does: a change parked by one blob and
+        # released by a later one still shows up in `pending` (encoding.rs:252-257, loro.rs:1228-1258)
+        assert st.code == 0 and st.success == ost["success"] and st.pending == ost["pending"], (did, st, ost)
+        saw_pending += ost["pending"] is not None
         assert b.json_bytes(k) == js
         assert b.oplog_vv(k) == tot
+    assert saw_pending > 0
     # a missing part leaves the dependants pending, exactly as a lone import would
     whole, js, tot, parts = _per_peer_blobs(3200, n_sites=3, n_ops=200)
     b2 = loro_b200.import_batch(parts[:2], doc_ids=[7, 7], lib_path=EMU)
     ref = OracleDoc(5)
-    for p in parts[:2]:
-        ref.import_(p)
+    ost = ref.import_batch(parts[:2])
     assert b2.n_docs == 1 and b2.json_bytes(0) == ref.json_text()
     assert b2.oplog_vv(0) == ref.oplog_vv()
+    assert b2.status(0).success == ost["success"] and b2.status(0).pending == ost["pending"], (b2.status(0), ost)
 
 
 def test_import_batch_full_blob_plus_overlapping_sliced_blob():
@@ -224,12 +230,12 @@ def test_import_batch_full_blob_plus_overlapping_sliced_blob():
     a.commit()
     full = a.export_updates()
     sliced = a.export_updates({1: 3})
-    ref = OracleDoc(9)
-    ref.import_(full)
-    ref.import_(sliced)
     for blobs in ([full, sliced], [sliced, full]):
+        ref = OracleDoc(9)
+        ost = ref.import_batch(blobs)
         r = loro_b200.import_batch(blobs, doc_ids=[5, 5], lib_path=EMU)
         assert r.n_docs == 1 and r.status(0).code == 0
+        assert r.status(0).success == ost["success"] and r.status(0).pending == ost["pending"], (r.status(0), ost)
         assert r.json_bytes(0) == ref.json_text()
         assert r.oplog_vv(0) == ref.oplog_vv()
 
@@ -357,3 +363,32 @@ def test_snapshot_blobs_and_unknown_modes():
     snap_ok, snap_bad, future = with_mode(good, 3), with_mode(good, 3, reseal=False), with_mode(good, 9)
     b = loro_b200.import_batch([snap_ok, snap_bad, future, good], lib_path=EMU)
     assert [b.status(i).code for i in range(4)] == [5, 2, 3, 0]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_import_batch_status_of_overlapping_updates(seed):
+    """ImportStatus of import_batch over blobs that overlap, repeat, arrive out of causal order or miss a part: the
+    engine's per-document status must equal the reference's fold of per-blob statuses (loro.rs:1228-1258) -- success
+    starts, pending hulls of changes parked by a blob's first pass even when a later blob releases them."""
+    import random
+    import loro_b200
+    rng = random.Random(9000 + seed)
+    blob, js, tot, sites = workloads.make_doc_history(4200 + seed, n_sites=2 + seed % 3, n_ops=160 + 30 * seed)
+    full = sites[0]
+    blobs = []
+    for _ in range(3 + seed % 3):
+        lo = {p: rng.randrange(0, c + 1) for p, c in tot.items() if rng.random() < 0.8}
+        blobs.append(full.export_updates(lo))
+    for p in list(tot)[:2]:
+        blobs.append(full.export_updates({q: c for q, c in tot.items() if q != p}))   # one peer's changes only
+    rng.shuffle(blobs)
+    if seed % 2:
+        blobs.append(blobs[0])
+    ref = OracleDoc(31)
+    ost = ref.import_batch(blobs)
+    r = loro_b200.import_batch(blobs, doc_ids=[3] * len(blobs), lib_path=EMU)
+    st = r.status(0)
+    assert r.n_docs == 1 and st.code == 0
+    assert r.json_bytes(0) == ref.json_text()
+    assert r.oplog_vv(0) == ref.oplog_vv()
+    assert st.success == ost["success"] and st.pending == ost["pending"], (st, ost)
