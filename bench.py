@@ -355,7 +355,7 @@ def main():
         c, tm = step()
         launches += tm["kernel_launches"]
         for k in ("frame", "decode", "resolve", "classify", "integrate", "tree", "materialise", "reexport", "total_device",
-                  "alloc_host_ms"):
+                  "alloc_host_ms", "host_call_ms", "host_tail_ms"):
             phase[k] = phase.get(k, 0.0) + tm[k]
     ev1.record()
     torch.cuda.synchronize()

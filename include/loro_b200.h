@@ -115,6 +115,9 @@ typedef struct lb_timings { /* device time per phase in milliseconds (CUDA event
     float alloc_host_ms;
     uint32_t reserved1;
     uint64_t device_bytes;
+    /* host wall time of the whole import call, and of its tail: from the moment the last kernel was enqueued (results
+     * download, status tables) -- what a step costs beyond `total_device` */
+    float host_call_ms, host_tail_ms;
 } lb_timings;
 
 typedef struct lb_batch lb_batch;

@@ -57,7 +57,8 @@ class _Timings(ctypes.Structure):
                 ("tree", ctypes.c_float), ("reserved0", ctypes.c_uint32), ("tree_ops", ctypes.c_uint64),
                 ("decode_fast_blocks", ctypes.c_uint64), ("decode_lane_blocks", ctypes.c_uint64),
                 ("decode_unstaged_blocks", ctypes.c_uint64),
-                ("alloc_host_ms", ctypes.c_float), ("reserved1", ctypes.c_uint32), ("device_bytes", ctypes.c_uint64)]
+                ("alloc_host_ms", ctypes.c_float), ("reserved1", ctypes.c_uint32), ("device_bytes", ctypes.c_uint64),
+                ("host_call_ms", ctypes.c_float), ("host_tail_ms", ctypes.c_float)]
 
 
 _libs = {}

@@ -22,6 +22,7 @@
 #include "k_frame.cuh"
 #include "k_decode.cuh"
 #include "k_decode_warp.cuh"
+#include "k_decode_group.cuh"
 #include "k_resolve.cuh"
 #include "k_classify.cuh"
 #include "k_seq.cuh"
@@ -115,6 +116,10 @@ __global__ void k_copy_segments(const CopySeg* __restrict__ segs, u32 n) {
     for (u64 i = lane; i < n16; i += 32) d4[i] = s4[i];
     for (u64 i = (n16 << 4) + lane; i < sg.len; i += 32) sg.dst[i] = sg.src[i];
 }
+
+#ifndef LB_DECODE_DEFAULT
+#define LB_DECODE_DEFAULT 1   // 0 rows, 1 cols, 2 warp, 3 group (k_decode*.cuh)
+#endif
 
 namespace {
 
@@ -324,10 +329,12 @@ struct lb_batch {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t json_ev = nullptr;
     std::thread json_thread;
-    std::vector<std::vector<lb_id_span>> success, pending, vv, frontiers;
+    std::vector<lb_id_span> spans[4];          // success, pending, vv, frontiers of all documents, flat
+    std::vector<size_t> span_off[4];           // document d owns [span_off[k][d], span_off[k][d + 1])
     std::vector<uint64_t> doc_ids;
     lb_counters counters{};
     lb_timings timings{};
+    std::chrono::steady_clock::time_point t_call = std::chrono::steady_clock::now(), t_tail = t_call;
     cudaEvent_t ev[16];
     int n_ev = 0;
     bool ev_created = false;
@@ -474,13 +481,22 @@ void pipeline(lb_batch* b) {
     t.tr_parent_peer = dv.alloc<u32>(NTR); t.tr_parent_ctr = dv.alloc<i32>(NTR); t.tr_pos = dv.alloc<u32>(NTR);
     t.dw_stats = dv.alloc<unsigned long long>(4, true);
     if (B) {
-        // decoder variants (A/B switch LB_DECODE = rows | cols | warp): thread per block with all cursors at once,
-        // thread per block one column at a time (default), warp per block on TMA-staged shared memory
+        // decoder variants (A/B switch LB_DECODE = rows | cols | warp | group): thread per block with all cursors at once,
+        // thread per block one column at a time, warp per block on TMA-staged shared memory (lane-parallel run
+        // expansion), warp per four TMA-staged blocks with a lane per column stream
         static const char* mode_env = getenv("LB_DECODE");
-        static const int mode = !mode_env ? 1 : (!strcmp(mode_env, "rows") ? 0 : (!strcmp(mode_env, "warp") ? 2 : 1));
+        static const int mode = !mode_env ? LB_DECODE_DEFAULT
+                                : (!strcmp(mode_env, "rows") ? 0 : (!strcmp(mode_env, "warp") ? 2 : (!strcmp(mode_env, "group") ? 3 : 1)));
         if (mode == 0) LB_LAUNCH(k_block_decode, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
         else if (mode == 1) LB_LAUNCH(k_block_decode_cols, nblk(B, 64), 64, 0, st, b->d_bytes, blk, B, t);
-        else {
+        else if (mode == 3) {
+            const size_t smem = sizeof(DgWarp) * DG_WARPS;
+#ifndef LB_SIMT_EMU
+            static bool attr_set_g = false;
+            if (!attr_set_g) { CK(cudaFuncSetAttribute(k_block_decode_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set_g = true; }
+#endif
+            LB_LAUNCH(k_block_decode_group, nblk(B, DG_G * DG_WARPS), 32 * DG_WARPS, smem, st, b->d_bytes, blk, B, t);
+        } else {
             const size_t smem = sizeof(DwWarp) * DW_WARPS;
 #ifndef LB_SIMT_EMU
             static bool attr_set = false;
@@ -795,6 +811,7 @@ void pipeline(lb_batch* b) {
     }
     mark(b);  // [7] export done
     // ------------------------------------------------------------ results to host
+    b->t_tail = std::chrono::steady_clock::now();
     b->docs.resize(D + 1);
     CK(cudaMemcpyAsync(b->docs.data(), b->d_docs, sizeof(DocInfo) * (D + 1), cudaMemcpyDeviceToHost, st));
     b->dpeer.resize(NP);
@@ -824,23 +841,27 @@ void pipeline(lb_batch* b) {
     (void)NDEL;
 }
 
+// ImportStatus / vv / frontiers spans of every document, flat: [off[d], off[d + 1]) of one array per kind (a vector per
+// document and kind cost ~0.1 s of host time per 10^5-document batch in allocations alone)
 void build_status(lb_batch* b) {
     size_t D = b->n_docs;
-    b->success.assign(D, {});
-    b->pending.assign(D, {});
-    b->vv.assign(D, {});
-    b->frontiers.assign(D, {});
+    for (int k = 0; k < 4; k++) { b->span_off[k].assign(D + 1, 0); b->spans[k].clear(); }
+    size_t total_peers = 0;
+    for (size_t d = 0; d < D; d++) total_peers += b->docs[d].P;
+    for (int k = 0; k < 4; k++) b->spans[k].reserve(k == 1 ? 16 : total_peers);
     for (size_t d = 0; d < D; d++) {
         DocInfo& di = b->docs[d];
         if (di.code == DOC_OK && di.has_unsupported) di.code = DOC_ERR_UNSUPPORTED;
-        if (di.code != DOC_OK && di.code != DOC_ERR_UNSUPPORTED) continue;
-        for (u32 p = 0; p < di.P; p++) {
-            const DocPeer& dp = b->dpeer[di.peer0 + p];
-            if (dp.has_succ) b->success[d].push_back(lb_id_span{dp.id, dp.succ_lo, dp.end_counter});
-            if (dp.end_counter > 0) b->vv[d].push_back(lb_id_span{dp.id, 0, dp.end_counter});
-            if (dp.pend_hi > dp.pend_lo) b->pending[d].push_back(lb_id_span{dp.id, dp.pend_lo, dp.pend_hi});
-            if (dp.is_head && dp.end_counter > 0) b->frontiers[d].push_back(lb_id_span{dp.id, dp.end_counter - 1, dp.end_counter});
+        if (di.code == DOC_OK || di.code == DOC_ERR_UNSUPPORTED) {
+            for (u32 p = 0; p < di.P; p++) {
+                const DocPeer& dp = b->dpeer[di.peer0 + p];
+                if (dp.has_succ) b->spans[0].push_back(lb_id_span{dp.id, dp.succ_lo, dp.end_counter});
+                if (dp.pend_hi > dp.pend_lo) b->spans[1].push_back(lb_id_span{dp.id, dp.pend_lo, dp.pend_hi});
+                if (dp.end_counter > 0) b->spans[2].push_back(lb_id_span{dp.id, 0, dp.end_counter});
+                if (dp.is_head && dp.end_counter > 0) b->spans[3].push_back(lb_id_span{dp.id, dp.end_counter - 1, dp.end_counter});
+            }
         }
+        for (int k = 0; k < 4; k++) b->span_off[k][d + 1] = b->spans[k].size();
     }
 }
 
@@ -869,6 +890,9 @@ lb_status run_batch(lb_batch* b) {
         pipeline(b);
         build_status(b);
         timings_from_events(b);
+        auto now = std::chrono::steady_clock::now();
+        b->timings.host_call_ms = std::chrono::duration<float, std::milli>(now - b->t_call).count();
+        b->timings.host_tail_ms = std::chrono::duration<float, std::milli>(now - b->t_tail).count();
     } catch (lb_status s) {
         return s;
     }
@@ -1282,24 +1306,24 @@ size_t lb_doc_count(const lb_batch* b) { return b ? b->n_docs : 0; }
 lb_status lb_doc_status(const lb_batch* b, size_t doc, lb_import_status* out) {
     if (!b || !out || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
     out->code = (lb_doc_code)b->docs[doc].code;
-    out->n_success = b->success[doc].size();
-    out->success = b->success[doc].data();
-    out->n_pending = b->pending[doc].size();
-    out->pending = b->pending[doc].data();
+    out->n_success = b->span_off[0][doc + 1] - b->span_off[0][doc];
+    out->success = b->spans[0].data() + b->span_off[0][doc];
+    out->n_pending = b->span_off[1][doc + 1] - b->span_off[1][doc];
+    out->pending = b->spans[1].data() + b->span_off[1][doc];
     return LB_OK;
 }
 
 lb_status lb_doc_vv(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n) {
     if (!b || !spans || !n || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
-    *spans = b->vv[doc].data();
-    *n = b->vv[doc].size();
+    *spans = b->spans[2].data() + b->span_off[2][doc];
+    *n = b->span_off[2][doc + 1] - b->span_off[2][doc];
     return LB_OK;
 }
 
 lb_status lb_doc_frontiers(const lb_batch* b, size_t doc, const lb_id_span** spans, size_t* n) {
     if (!b || !spans || !n || doc >= b->n_docs) { g_last_error = "bad argument"; return LB_ERR_INVALID_ARG; }
-    *spans = b->frontiers[doc].data();
-    *n = b->frontiers[doc].size();
+    *spans = b->spans[3].data() + b->span_off[3][doc];
+    *n = b->span_off[3][doc + 1] - b->span_off[3][doc];
     return LB_OK;
 }
 

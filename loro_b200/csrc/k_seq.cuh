@@ -778,6 +778,53 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
     seq_fail(c, LB_ERR(DOC_ERR_CAPACITY));
 }
 
+// ---- leaf prefetch.  The kernel is bound by the latency of the leaf round trip of every op (one dependent 512-byte
+// HBM read per op, profiles/r1_ncu_seq.md).  When 32 op records arrive, every lane predicts the leaf ITS record will
+// touch -- deletes from the atom -> leaf lookup they do anyway, inserts by walking the shared-memory nodes on its own
+// (lane-serial, the warp runs 32 descents at once) -- and asks L2 for it.  The prediction ignores the ops in between
+// and the version switches (a position is only right at the op's own version), so it is a hint: the op's real descent
+// runs as before and usually finds its leaf in L2 instead of HBM.
+#ifndef LB_SEQ_PF
+#define LB_SEQ_PF 2           // 0: off, 1: delete targets only, 2: inserts too
+#endif
+__device__ __forceinline__ void prefetch_leaf(const SeqPools& p, const Cx& c, u32 leaf) {
+#ifndef LB_SIMT_EMU
+    const char* a = (const char*)(p.leaf + (c.leaf0 + leaf) * 32);
+#ifdef LB_SEQ_PF_L1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 128));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 256));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 384));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 256));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 384));
+#endif
+#else
+    (void)p; (void)c; (void)leaf;
+#endif
+}
+__device__ __forceinline__ u32 predict_leaf(const Cx& c, i32 pos) {
+    const SeqSmem* sm = c.sm;
+    if (pos <= 0) return sm->first_leaf;
+    u32 nd = sm->root;
+    i32 rem = pos;
+    for (u32 lvl = sm->height; lvl >= 1; lvl--) {
+        if (nd >= LB_SEQ_NS) return LEAF_NONE;       // this node lives in HBM: no prediction
+        int i = 0;
+        for (; i < 32; i++) {
+            if (sm->child[nd][i] == NODE_NONE) return LEAF_NONE;
+            i32 v = sm->vis[nd][i];
+            if (v >= rem) break;
+            rem -= v;
+        }
+        if (i == 32) return LEAF_NONE;
+        nd = sm->child[nd][i];
+    }
+    return nd;
+}
+
 // ---- container switching: internal nodes < NS and the tracker version live in shared memory while a
 // container is active
 __device__ __noinline__ void store_container(const SeqPools& p, const SeqTables& t, Cx c, u64 cid0, u32 cidx) {
@@ -963,6 +1010,16 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
                 u32 kind_l = REC_KIND(rec.x);
                 // deletes: (possibly stale) home leaf of the first target atom
                 u32 hint_l = kind_l == OPK_SEQ_DEL ? pools.atom_leaf[atom_index(c, aux, (i32)rec.w)] : LEAF_NONE;
+#if LB_SEQ_PF
+                if (REC_CIDX(rec.x) == cidx && cidx != 0xFFFFFFFFu) {
+                    u32 pl = LEAF_NONE;
+                    if (kind_l == OPK_SEQ_DEL) pl = hint_l;
+#if LB_SEQ_PF > 1
+                    else if (kind_l == OPK_SEQ_INS) pl = predict_leaf(c, (i32)rec.w);
+#endif
+                    if (pl != LEAF_NONE && pl < sm->n_leaves) prefetch_leaf(pools, c, pl);
+                }
+#endif
                 unsigned m = __ballot_sync(LB_FULL, kind_l == OPK_SEQ_INS || kind_l == OPK_SEQ_DEL);
                 while (m && !sm->err) {
                     int s = __ffs(m) - 1;

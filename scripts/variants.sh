@@ -1,10 +1,14 @@
-# bench every library under build_variants/ (kernel tuning experiments) at a mid-size batch
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for lib in build_variants/*.so; do
-  v=$(basename $lib .so)
-  LORO_B200_LIB=$PWD/$lib python bench.py --docs ${DOCS:-8192} --steps 2 --warmup 2 --no-e2e --cpu-sample-docs 16 > gpurun_out/var_$v.json 2> gpurun_out/var_$v.err
-  python -c "
-import json,sys
-d=json.loads(open('gpurun_out/var_$v.json').read().strip().splitlines()[-1])
-print('$v', round(d['value']/1e6,1), 'Mops/s', {k: round(x,1) for k,x in d['phases_ms'].items()})"
+#!/bin/bash
+# Kernel tuning experiments: build one library per set of -D flags into build_variants/ (ignored by git, shipped to the
+# GPU box by gpurun), to be compared with LORO_B200_LIB=... python bench.py on the box.
+# usage: scripts/variants.sh name "flags" [name "flags" ...]
+set -e
+cd "$(dirname "$0")/.."
+mkdir -p build_variants
+while [ $# -ge 2 ]; do
+  name=$1; flags=$2; shift 2
+  (cd loro_b200/csrc && /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+      -Xcompiler -fPIC -shared -diag-suppress 550 $flags -o ../../build_variants/$name.so engine.cu) &
 done
+wait
+ls -la build_variants
