@@ -73,6 +73,7 @@ typedef struct lb_options {
 #define LB_FLAG_NO_JSON 1u      /* skip deep-value JSON materialisation */
 #define LB_FLAG_KEEP_DEVICE 2u  /* keep intermediate device tables for lb_debug_* (tests) */
 #define LB_FLAG_EXPORT 4u       /* also re-export every document (phase 7) for lb_doc_export_updates */
+#define LB_FLAG_COMPACT 8u      /* lb_docset_import: afterwards keep each touched document as its own export (see below) */
 
 typedef struct lb_id_span {
     uint64_t peer;
@@ -165,18 +166,23 @@ void lb_batch_free(lb_batch* b);
  * LoroDoc::import / import_batch on a document that already holds history (crates/loro/src/lib.rs:639, :425;
  * crates/loro-internal/src/loro.rs:562-643, 1183-1290; oplog.rs:130-196: changes the document knows are skipped or
  * trimmed, pending changes wait in the oplog until a later import brings their dependencies).
- * A docset keeps, per doc_id, the document's change store in wire form IN DEVICE MEMORY: the FastUpdates blob the
- * document re-exports (what the reference's ChangeStore keeps: encoded blocks, change_store.rs:60-110), or -- while the
- * document still has pending changes, which no export contains -- the blobs it was built from.  lb_docset_import lays
- * the stored blobs of every touched document in front of the new ones (device-to-device) and replays the document;
- * the batch it returns answers exactly like the reference's import on the existing document:
+ * A docset keeps, per doc_id, the document's change store in wire form IN DEVICE MEMORY: the update blobs it has
+ * imported, in order (what the reference's ChangeStore keeps are encoded blocks too, change_store.rs:60-110).
+ * lb_docset_import lays the stored blobs of every touched document in front of the new ones (device-to-device) and
+ * replays the document; the batch it returns answers exactly like the reference's import on the existing document:
  *   lb_doc_status    ImportStatus of THIS import: success = what the new blobs added (a change the document already
  *                    held is not reported, a stored pending change released by this import is), pending = what the
  *                    new blobs parked;
  *   lb_doc_json / lb_doc_vv / lb_doc_frontiers / lb_doc_export_updates    the document after the import.
  * Several blobs with one doc_id in one call = import_batch on that document (sorted by mode, then number of changes
  * descending, among the new blobs).  A document whose import fails (checksum, decode error, ...) keeps its earlier
- * state, like the reference (loro.rs:584: checked before any state change).  The engine merges by replaying the
+ * state, like the reference (loro.rs:584: checked before any state change).
+ * LB_FLAG_COMPACT in `opt->flags`: after this import every touched document without pending changes is replaced by a
+ * fresh document that imported its own export -- `fresh.import(doc.export(all_updates))`, the way a host drops
+ * redundant history; the stored form shrinks to one blob.  State, vv and frontiers are unaffected; later exports equal
+ * those of a reference document that was re-created the same way (the op segmentation of an export depends on which
+ * blob brought which piece of a change, so they may differ by a few bytes from an uncompacted document's).
+ * The engine merges by replaying the
  * document's whole history, not from the common ancestor of the two versions (dag.rs:488-667): same results, the
  * cost of an import grows with the history.
  * One docset serves one device; calls on the same docset are serialised.  LB_FLAG_EXPORT is implied. */

@@ -10,6 +10,7 @@ _DEFAULT_LIB = os.path.join(_HERE, "libloro_b200.so")
 LB_FLAG_NO_JSON = 1
 LB_FLAG_KEEP_DEVICE = 2
 LB_FLAG_EXPORT = 4
+LB_FLAG_COMPACT = 8
 
 DOC_CODES = {0: "Ok", 1: "DecodeError", 2: "DecodeChecksumMismatchError", 3: "IncompatibleFutureEncodingError",
              4: "DecodeDataCorruptionError", 5: "Unsupported", 6: "CapacityExceeded"}

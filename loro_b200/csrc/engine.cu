@@ -60,6 +60,13 @@ __global__ void k_doc_sizes(const DocInfo* __restrict__ docs, u32 n_docs, u32* _
         mapslots[d] = ok ? di.C * di.K : 0;
     }
 }
+__global__ void k_pack_peers(const DocInfo* __restrict__ docs, u32 n_docs, const DocPeer* __restrict__ dpeer,
+                             const u64* __restrict__ base, DocPeer* __restrict__ out) {
+    u32 d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const DocInfo& di = docs[d];
+    for (u32 p = 0; p < di.P; p++) out[base[d] + p] = dpeer[di.peer0 + p];
+}
 // multi-field scan: CTA f scans field f (offsets in bytes inside the strided records)
 struct ScanJob { const u8* in; u8* out; size_t in_stride, out_stride; u64 n; };
 struct ScanJobs { ScanJob j[8]; };
@@ -320,7 +327,8 @@ struct lb_batch {
     Tables tb{};
     // host results
     std::vector<DocInfo> docs;
-    std::vector<DocPeer> dpeer;
+    std::vector<DocPeer> dpeer;          // packed: document d owns [peer_base[d], peer_base[d] + P)
+    std::vector<u64> peer_base;
     char* json = nullptr;   // from lbstage::host_cache (never zero-filled): filled by lbstage::download
     bool json_fetched = false;
     // host-buffer entry point: the JSON goes home on a second stream while the export phase still computes
@@ -524,6 +532,7 @@ void pipeline(lb_batch* b) {
     rt.dkey_off = dv.alloc<u64>(NK); rt.dkey_len = dv.alloc<u32>(NK); rt.key_map = dv.alloc<u32>(NK);
     rt.blk_order = dv.alloc<u32>(B);
     rt.ch_order = dv.alloc<u32>(NCH);
+    rt.ch_aorder = dv.alloc<u32>(NCH);
     rt.ch_peer = dv.alloc<u16>(NCH);
     rt.ch_applied = dv.alloc<u8>(NCH, true);
     rt.ch_lamport = dv.alloc<u32>(NCH, true);
@@ -616,7 +625,7 @@ void pipeline(lb_batch* b) {
     memset(&sq, 0, sizeof(sq));
     sq.dpeer = b->d_dpeer; sq.dcont = dcont;
     sq.ch_walk = rt.ch_walk; sq.ch_op0 = t.ch_op0; sq.ch_nops = t.ch_nops; sq.ch_peer = rt.ch_peer; sq.ch_vv = rt.ch_vv;
-    sq.ch_order = rt.ch_order; sq.ch_counter = t.ch_counter; sq.ch_ndeps = t.ch_ndeps; sq.ch_dep_self = t.ch_dep_self;
+    sq.ch_order = rt.ch_aorder; sq.ch_counter = t.ch_counter; sq.ch_ndeps = t.ch_ndeps; sq.ch_dep_self = t.ch_dep_self;
     sq.ch_pos = rt.ch_pos;
     sq.op_rec = ct.op_rec; sq.op_aux = ct.op_aux; sq.op_change = t.op_change; sq.op_counter = t.op_counter;
     sq.atom_row = ct.atom_row;
@@ -714,7 +723,7 @@ void pipeline(lb_batch* b) {
         memset(&xt, 0, sizeof(xt));
         xt.bytes = b->d_bytes; xt.blocks = blk; xt.dpeer = b->d_dpeer; xt.dcont = dcont;
         xt.dkey_off = rt.dkey_off; xt.dkey_len = rt.dkey_len; xt.key_map = rt.key_map; xt.peer_map = rt.peer_map;
-        xt.ch_order = rt.ch_order; xt.ch_applied = rt.ch_applied; xt.ch_block = t.ch_block; xt.ch_counter = t.ch_counter;
+        xt.ch_order = rt.ch_aorder; xt.ch_applied = rt.ch_applied; xt.ch_block = t.ch_block; xt.ch_counter = t.ch_counter;
         xt.ch_len = t.ch_len; xt.ch_lamport = rt.ch_lamport; xt.ch_ts = t.ch_ts; xt.ch_op0 = t.ch_op0; xt.ch_nops = t.ch_nops;
         xt.ch_dep0 = t.ch_dep0; xt.ch_ndeps = t.ch_ndeps; xt.ch_dep_self = t.ch_dep_self;
         xt.dep_peer_idx = t.dep_peer_idx; xt.dep_counter = t.dep_counter;
@@ -814,8 +823,6 @@ void pipeline(lb_batch* b) {
     b->t_tail = std::chrono::steady_clock::now();
     b->docs.resize(D + 1);
     CK(cudaMemcpyAsync(b->docs.data(), b->d_docs, sizeof(DocInfo) * (D + 1), cudaMemcpyDeviceToHost, st));
-    b->dpeer.resize(NP);
-    if (NP) CK(cudaMemcpyAsync(b->dpeer.data(), b->d_dpeer, sizeof(DocPeer) * NP, cudaMemcpyDeviceToHost, st));
     unsigned long long acc[4];
     CK(cudaMemcpyAsync(acc, d_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
     unsigned long long dws[4] = {0, 0, 0, 0};
@@ -823,6 +830,23 @@ void pipeline(lb_batch* b) {
     if (b->d_xdoc) {
         b->xdocs.resize(D);
         CK(cudaMemcpyAsync(b->xdocs.data(), b->d_xdoc, sizeof(XDoc) * D, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    // the peer table is sized by the blocks' peer registers (a few entries per BLOCK: hundreds of MB for 10^6 blocks) but a
+    // document uses only its first P entries: those are packed on the device and only they travel
+    {
+        b->peer_base.assign(D + 1, 0);
+        for (u32 d = 0; d < D; d++) b->peer_base[d + 1] = b->peer_base[d] + b->docs[d].P;
+        const u64 total = b->peer_base[D];
+        b->dpeer.resize(total);
+        if (total) {
+            u64* d_pbase = dv.alloc<u64>(D + 1);
+            DocPeer* d_packed = dv.alloc<DocPeer>(total);
+            CK(cudaMemcpyAsync(d_pbase, b->peer_base.data(), sizeof(u64) * (D + 1), cudaMemcpyHostToDevice, st));
+            LB_LAUNCH(k_pack_peers, nblk(D), TPB, 0, st, b->d_docs, D, b->d_dpeer, d_pbase, d_packed);
+            tm.kernel_launches += 1;
+            CK(cudaMemcpyAsync(b->dpeer.data(), d_packed, sizeof(DocPeer) * total, cudaMemcpyDeviceToHost, st));
+        }
     }
     mark(b);  // [8] d2h queued
     CK(cudaStreamSynchronize(st));
@@ -854,7 +878,7 @@ void build_status(lb_batch* b) {
         if (di.code == DOC_OK && di.has_unsupported) di.code = DOC_ERR_UNSUPPORTED;
         if (di.code == DOC_OK || di.code == DOC_ERR_UNSUPPORTED) {
             for (u32 p = 0; p < di.P; p++) {
-                const DocPeer& dp = b->dpeer[di.peer0 + p];
+                const DocPeer& dp = b->dpeer[b->peer_base[d] + p];
                 if (dp.has_succ) b->spans[0].push_back(lb_id_span{dp.id, dp.succ_lo, dp.end_counter});
                 if (dp.pend_hi > dp.pend_lo) b->spans[1].push_back(lb_id_span{dp.id, dp.pend_lo, dp.pend_hi});
                 if (dp.end_counter > 0) b->spans[2].push_back(lb_id_span{dp.id, 0, dp.end_counter});
@@ -973,12 +997,14 @@ lb_status export_from(lb_batch* b, size_t doc, const lb_id_span* from, size_t n_
         const u64 NCH = b->n_changes;
         const DocInfo& di = b->docs[doc];
         ExportTables xt = b->xt;
-        std::vector<i32> h_from(b->n_peers_tot + 1, 0);
+        // only the document's own peer slots are read (every kernel is restricted to `only_doc`)
+        std::vector<i32> h_from(di.P + 1, 0);
         for (size_t k = 0; k < n_from; k++)
             for (u32 p = 0; p < di.P; p++)
-                if (b->dpeer[di.peer0 + p].id == from[k].peer) h_from[di.peer0 + p] = from[k].end;
+                if (b->dpeer[b->peer_base[doc] + p].id == from[k].peer) h_from[p] = from[k].end;
         i32* d_from = dv.alloc<i32>(b->n_peers_tot + 1);
-        CK(cudaMemcpyAsync(d_from, h_from.data(), sizeof(i32) * (b->n_peers_tot + 1), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_from + di.peer0, h_from.data(), sizeof(i32) * di.P, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // h_from is pageable host memory
         xt.from_ctr = d_from;
         xt.only_doc = (u32)doc;
         XDoc* xdoc = dv.alloc<XDoc>(D + 1, true);
@@ -1024,9 +1050,10 @@ lb_status export_from(lb_batch* b, size_t doc, const lb_id_span* from, size_t n_
 }  // namespace
 
 // After an import into a docset: every document of the batch whose import succeeded gets its new stored form -- the
-// blob it re-exports (ExportMode::all_updates) when nothing is pending and the export phase covers it, otherwise the
-// blobs it was built from (earlier state first), copied out of the batch's byte buffer.  A document whose import failed
-// (checksum, decode, ...) keeps its earlier state: the reference rejects such an import before any state change.
+// blobs it was built from (earlier ones first), copied out of the batch's byte buffer, or, with LB_FLAG_COMPACT, the
+// blob it re-exports (ExportMode::all_updates) when nothing is pending and the export phase covers it.  A document
+// whose import failed (checksum, decode, ...) keeps its earlier state: the reference rejects such an import before any
+// state change.
 void docset_store(lb_docset* set, lb_batch* b, const std::vector<u64>& offs, const std::vector<u32>& lens) {
     const size_t nd = b->n_docs;
     struct Pick { size_t doc; bool exported; };
@@ -1035,7 +1062,12 @@ void docset_store(lb_docset* set, lb_batch* b, const std::vector<u64>& offs, con
     for (size_t d = 0; d < nd; d++) {
         const DocInfo& di = b->docs[d];
         if (di.code != DOC_OK && di.code != DOC_ERR_UNSUPPORTED) continue;
-        bool exported = di.code == DOC_OK && di.n_pending == 0 && d < b->xdocs.size() && !(b->xdocs[d].flags & 1) && b->xdocs[d].exp_len > 0;
+        // LB_FLAG_COMPACT: the document is replaced by a fresh one that imported its own export (what a host does to drop
+        // redundant history: `fresh.import(doc.export(all_updates))`); otherwise it keeps every blob it ever imported, in
+        // order, so that a later export is byte-identical to the reference's after the same sequence of imports (the
+        // op segmentation of an export depends on which blob brought which piece of a change)
+        bool exported = (b->flags & LB_FLAG_COMPACT) && di.code == DOC_OK && di.n_pending == 0 && d < b->xdocs.size() &&
+                        !(b->xdocs[d].flags & 1) && b->xdocs[d].exp_len > 0;
         picks.push_back(Pick{d, exported});
         if (exported) total += ((u64)b->xdocs[d].exp_len + 15) & ~(u64)15;
         else for (u32 q = b->doc_blob0[d]; q < b->doc_blob0[d + 1]; q++) total += ((u64)lens[q] + 15) & ~(u64)15;

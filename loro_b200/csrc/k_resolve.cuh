@@ -26,7 +26,10 @@ struct ResolveTables {
     DocContainer* dcont; u32* cid_map;
     u64* dkey_off; u32* dkey_len; u32* key_map;
     u32* blk_order;      // per doc: its blocks sorted by (peer, counter_start)
-    u32* ch_order;       // per doc: changes grouped by peer, counter order (batch-wide change ids)
+    u32* ch_order;       // per doc: changes grouped by peer, counter order (batch-wide change ids): every COPY
+    u32* ch_aorder;      // same grouping: the peer's APPLIED copies in the order they were applied (their applied ranges
+                         // [counter + trim, counter + len) are disjoint and ascending), then the copies that were not;
+                         // this is the order every later phase walks (tracker version switches, change store)
     u16* ch_peer;        // doc peer idx of each change
     u8* ch_applied;
     u32* ch_lamport;     // recomputed lamport
@@ -93,7 +96,7 @@ __global__ void k_doc_tables(const u8* __restrict__ bytes, DocInfo* __restrict__
                 np.succ_lo = 0;
                 np.has_succ = 0;
                 np.end_counter = 0;
-                np.max_counter = 0;
+                np.n_app = 0;
                 np.atom_base = 0;
                 np.ch_first = 0;
                 np.ch_count = 0;
@@ -221,35 +224,26 @@ __global__ void k_doc_tables(const u8* __restrict__ bytes, DocInfo* __restrict__
     docs[d] = di;
 }
 
-// lamport of atom (peer p, counter c) if applied; returns false when unknown
+// lamport of atom (peer p, counter c) if applied; returns false when unknown.  The applied copies of a peer are kept in
+// application order (ch_aorder): their applied ranges ascend, so the one holding c is found by bisection on the start.
 __device__ inline bool lamport_of(const DocInfo& di, const ResolveTables& t, u32 p, i32 c, u32* out,
                                   u32* ch_out) {
     const DocPeer& dp = t.dpeer[di.peer0 + p];
-    if (c < 0 || c >= dp.end_counter) return false;
-    // binary search in the peer's ordered change list
-    u32 lo = 0, hi = dp.ch_count;
+    if (c < 0 || c >= dp.end_counter || dp.n_app == 0) return false;
+    const u32* lst = t.ch_aorder + di.ch0 + dp.ch_first;
+    u32 lo = 0, hi = dp.n_app;
     while (hi - lo > 1) {
         u32 mid = (lo + hi) >> 1;
-        if (t.ch_counter[t.ch_order[di.ch0 + dp.ch_first + mid]] <= c) lo = mid;
+        if (t.ch_counter[lst[mid]] + (i32)t.ch_trim[lst[mid]] <= c) lo = mid;
         else hi = mid;
     }
-    // `lo` is the last entry that starts at or before c.  Copies the walk dropped (the same change delivered twice, a
-    // sliced copy A[3..10) next to A[0..10) from an export cut at a version vector) and the head of a change applied as a
-    // slice (its first ch_trim atoms were already there) do not count: applied ranges are disjoint and in counter
-    // order, so the first applied entry, going back, whose applied range starts at or before c is the only candidate
-    while (lo > 0) {
-        u32 x = t.ch_order[di.ch0 + dp.ch_first + lo];
-        if (t.ch_applied[x] && c >= t.ch_counter[x] + (i32)t.ch_trim[x]) break;
-        lo--;
-    }
-    u32 ch = t.ch_order[di.ch0 + dp.ch_first + lo];
-    if (!t.ch_applied[ch] || c < t.ch_counter[ch] + (i32)t.ch_trim[ch] || c >= t.ch_counter[ch] + (i32)t.ch_len[ch]) return false;
+    u32 ch = lst[lo];
+    if (c < t.ch_counter[ch] + (i32)t.ch_trim[ch] || c >= t.ch_counter[ch] + (i32)t.ch_len[ch]) return false;
     *out = t.ch_lamport[ch] + (u32)(c - t.ch_counter[ch]);
     *ch_out = ch;
     return true;
 }
 
-// thread per doc: pending detection, lamport recomputation, replay order, per-change version vectors.
 // ---- import status of multi-blob documents.  T(copy) = max(rank of its blob, epoch of every atom it depends on);
 // epoch(atom) = min T over the copies that cover it (whichever copy the reference meets first applies the atom, later
 // ones are skipped or trimmed: oplog.rs:181-196); first-pass flag likewise.  Copies are visited in the order of the
@@ -300,6 +294,56 @@ __device__ inline u32 copy_epoch(const DocInfo& di, const ResolveTables& t, cons
     return E | (fp ? EPOCH_FP : 0u);
 }
 
+// ---- multi-blob documents: WHICH copy of a change supplies an atom.  The reference imports a document's blobs one after
+// the other, so an atom comes from the copy that can be applied first -- the lowest T = max(rank of its blob, epoch of
+// its dependencies), a blob's first pass before its release of parked changes -- and later copies are skipped or trimmed
+// (oplog.rs:181-196).  State does not care, exported bytes do: where a payload sits in the document's arenas, hence
+// which neighbouring ops re-merge, depends on the blob that brought it.  Among the copies of peer p that can extend its
+// frontier (consecutive in the counter-ordered list) the one with the lowest (T, parked, rank) is returned; *soft is set
+// when some candidate's dependencies are not applied YET, i.e. a better copy may still turn up.  During the walk
+// ch_epoch holds the epoch of every APPLIED copy (exact, because the copy applied for an atom is the reference's).
+__device__ inline u32 pick_copy_multi(const DocInfo& di, const ResolveTables& t, const BlockInfo* blocks, u32 p, u32 from,
+                                      u32* lam_out, u32* epoch_out, bool* soft) {
+    const DocPeer& dp = t.dpeer[di.peer0 + p];
+    u32 best = 0xFFFFFFFFu, best_lam = 0, best_e = 0;
+    u64 best_key = ~0ull;
+    *soft = false;
+    for (u32 j = from; j < dp.ch_count; j++) {
+        u32 ch = t.ch_order[di.ch0 + dp.ch_first + j];
+        i32 ctr = t.ch_counter[ch];
+        if (ctr > dp.end_counter) break;                                   // sorted by counter: nothing further reaches the frontier
+        if (t.ch_applied[ch] || ctr + (i32)t.ch_len[ch] <= dp.end_counter) continue;   // consumed / already known
+        const BlockInfo& bi = blocks[t.ch_block[ch]];
+        const u32 k = bi.blob_rank;
+        u32 E = k, lam = 0;
+        bool fp = true, ready = true;
+        const u32 nd = t.ch_ndeps[ch] + (t.ch_dep_self[ch] ? 1u : 0u);
+        for (u32 q = 0; q < nd; q++) {
+            u32 dpi;
+            i32 dc;
+            if (q == t.ch_ndeps[ch]) { dpi = p; dc = ctr - 1; }
+            else { dpi = t.peer_map[bi.peer0 + t.dep_peer_idx[t.ch_dep0[ch] + q]]; dc = t.dep_counter[t.ch_dep0[ch] + q]; }
+            u32 l, dch;
+            if (!lamport_of(di, t, dpi, dc, &l, &dch)) { ready = false; break; }
+            if (l + 1 > lam) lam = l + 1;
+            u32 ed = t.ch_epoch[dch], e = ed & ~EPOCH_FP;
+            if (e > E) E = e;
+            if (e > k || (e == k && !(ed & EPOCH_FP))) fp = false;
+        }
+        if (!ready) { *soft = true; continue; }
+        if (ctr < dp.end_counter) {          // applied as a slice: it follows its own predecessor (change.rs:248-252)
+            u32 l, dch;
+            if (!lamport_of(di, t, p, dp.end_counter - 1, &l, &dch)) { *soft = true; continue; }
+            lam = l + 1;
+        }
+        u64 key = ((u64)E << 33) | ((u64)(fp ? 0u : 1u) << 32) | k;
+        if (key < best_key) { best_key = key; best = j; best_lam = lam; best_e = E | (fp ? EPOCH_FP : 0u); }
+    }
+    *lam_out = best_lam;
+    *epoch_out = best_e;
+    return best;
+}
+
 __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const BlockInfo* __restrict__ blocks,
                              ResolveTables t, u32* __restrict__ peer_cursor, const u32* __restrict__ doc_blob0,
                              i32* __restrict__ pend_scratch) {
@@ -316,15 +360,40 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
     for (u32 p = 0; p < P; p++) cursor[p] = 0;
     u32 cur = 0xFFFFFFFFu;
     u32 walk_n = 0;
+    const bool multi_blob = di.n_blobs > 1 && t.ch_epoch != nullptr;
     while (true) {
         // ---- pick a ready change: stay on the current peer if possible, else min (lamport, peer)
-        u32 pick = 0xFFFFFFFFu, pick_lam = 0, pick_ch = 0;
+        u32 pick = 0xFFFFFFFFu, pick_lam = 0, pick_ch = 0, pick_e = EPOCH_FP;
+        u32 soft_pick = 0xFFFFFFFFu, soft_lam = 0, soft_ch = 0, soft_e = 0;
         for (u32 step = 0; step < P + 1; step++) {
             u32 p;
             if (step == 0) { if (cur == 0xFFFFFFFFu) continue; p = cur; }
             else { p = step - 1; if (p == cur) continue; }
             DocPeer& dp = t.dpeer[di.peer0 + p];
             if (cursor[p] >= dp.ch_count) continue;
+            if (multi_blob) {
+                // consumed and known copies at the front are done with
+                while (cursor[p] < dp.ch_count) {
+                    u32 c0 = t.ch_order[di.ch0 + dp.ch_first + cursor[p]];
+                    if (t.ch_applied[c0] || t.ch_counter[c0] + (i32)t.ch_len[c0] <= dp.end_counter) cursor[p]++; else break;
+                }
+                if (cursor[p] >= dp.ch_count) continue;
+                u32 lam_m, e_m;
+                bool soft;
+                u32 j = pick_copy_multi(di, t, blocks, p, cursor[p], &lam_m, &e_m, &soft);
+                if (j == 0xFFFFFFFFu) continue;
+                u32 chm = t.ch_order[di.ch0 + dp.ch_first + j];
+                if (soft) {      // a better copy may still become ready: only taken when nothing else can move
+                    if (soft_pick == 0xFFFFFFFFu) { soft_pick = p; soft_lam = lam_m; soft_ch = chm; soft_e = e_m; }
+                    continue;
+                }
+                if (step == 0) { pick = p; pick_lam = lam_m; pick_ch = chm; pick_e = e_m; break; }
+                if (pick == 0xFFFFFFFFu || lam_m < pick_lam ||
+                    (lam_m == pick_lam && t.dpeer[di.peer0 + p].rank < t.dpeer[di.peer0 + pick].rank)) {
+                    pick = p; pick_lam = lam_m; pick_ch = chm; pick_e = e_m;
+                }
+                continue;
+            }
             u32 ch = t.ch_order[di.ch0 + dp.ch_first + cursor[p]];
             i32 ctr = t.ch_counter[ch];
             if (ctr != dp.end_counter) {
@@ -366,13 +435,14 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
                 pick = p; pick_lam = lam; pick_ch = ch;
             }
         }
+        if (pick == 0xFFFFFFFFu && soft_pick != 0xFFFFFFFFu) { pick = soft_pick; pick_lam = soft_lam; pick_ch = soft_ch; pick_e = soft_e; }
         if (pick == 0xFFFFFFFFu || di.code != DOC_OK) break;
         // ---- apply
         u32 ch = pick_ch;
         DocPeer& dp = t.dpeer[di.peer0 + pick];
         i32 ctr = t.ch_counter[ch];
         const u32 trim = ctr < dp.end_counter ? (u32)(dp.end_counter - ctr) : 0u;
-        u32 local = dp.ch_first + cursor[pick];  // row of this change in the doc's ch_vv
+        u32 local = dp.ch_first + dp.n_app;  // its place in the peer's applied order = row of this change in the doc's ch_vv
         i32* v = t.ch_vv + di.vv0 + (u64)local * P;
         for (u32 q = 0; q < P; q++) v[q] = 0;
         const BlockInfo& bi = blocks[t.ch_block[ch]];
@@ -391,15 +461,27 @@ __global__ void k_doc_causal(DocInfo* __restrict__ docs, u32 n_docs, const Block
         }
         t.ch_lamport[ch] = pick_lam - trim;   // lamport of the change's (trimmed) first atom: counters and lamports run in step
         t.ch_trim[ch] = trim;
+        if (multi_blob) t.ch_epoch[ch] = pick_e;
         t.ch_applied[ch] = 1;
         t.ch_pos[ch] = local;
+        t.ch_aorder[di.ch0 + local] = ch;
+        dp.n_app++;
         t.ch_walk[di.ch0 + walk_n++] = ch;
         dp.end_counter = ctr + (i32)t.ch_len[ch];
         di.atom_ops += t.ch_len[ch] - trim;
-        cursor[pick]++;
+        if (!multi_blob) cursor[pick]++;     // (multi-blob: the cursor skips consumed copies when the peer is looked at again)
         cur = pick;
     }
     di.n_applied = walk_n;
+    // the copies that were not applied (dropped duplicates, pending changes) follow the applied ones
+    for (u32 p = 0; p < P; p++) {
+        const DocPeer& dp = t.dpeer[di.peer0 + p];
+        u32 w = dp.n_app;
+        for (u32 k = 0; k < dp.ch_count; k++) {
+            u32 ch = t.ch_order[di.ch0 + dp.ch_first + k];
+            if (!t.ch_applied[ch]) t.ch_aorder[di.ch0 + dp.ch_first + w++] = ch;
+        }
+    }
     // ---- import status + atom bases.  ImportStatus of LoroDoc::import_batch (loro.rs:1183-1290) folds the statuses of
     // the blobs imported one after the other: success[peer] = (start of the first blob that applied something of the
     // peer, highest end) -- atoms of a peer apply in counter order, so that is [first counter a new blob applied, end);
@@ -517,12 +599,8 @@ __global__ void k_doc_frontiers(const DocInfo* __restrict__ docs, u32 n_docs, Re
     for (u32 q = 0; q < P; q++) {
         const DocPeer& dq = t.dpeer[di.peer0 + q];
         // last applied change of q
-        u32 last = 0xFFFFFFFFu;
-        for (u32 k = dq.ch_count; k-- > 0;) {
-            u32 ch = t.ch_order[di.ch0 + dq.ch_first + k];
-            if (t.ch_applied[ch]) { last = ch; break; }
-        }
-        if (last == 0xFFFFFFFFu) continue;
+        if (dq.n_app == 0) continue;
+        u32 last = t.ch_aorder[di.ch0 + dq.ch_first + dq.n_app - 1];
         const i32* v = t.ch_vv + di.vv0 + (u64)t.ch_pos[last] * P;
         for (u32 p = 0; p < P; p++)
             if (p != q && v[p] >= t.dpeer[di.peer0 + p].end_counter && t.dpeer[di.peer0 + p].end_counter > 0) t.dpeer[di.peer0 + p].is_head = 0;

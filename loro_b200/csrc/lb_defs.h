@@ -65,7 +65,7 @@ struct DocPeer {
     u32 rank;          // rank of id among the doc's peers (ascending)
     i32 succ_lo;       // ImportStatus.success = [succ_lo, end_counter) when has_succ (first counter the import added)
     i32 end_counter;   // vv after import (exclusive)
-    i32 max_counter;   // highest counter end seen in the blob (incl. pending)
+    u32 n_app;         // applied copies of this peer's changes (the first n_app entries of its ch_aorder list)
     u32 atom_base;     // offset of this peer's atoms inside the doc's atom arrays
     u32 ch_first;      // index into doc_change_order of this peer's first change
     u32 ch_count;

@@ -20,7 +20,8 @@ def test_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "loro_b200.h")).read()
     names = set(re.findall(r"\b(lb_[a-z_]+)\s*\(", hdr))
     assert {"lb_import_batch", "lb_import_batch_device", "lb_doc_status", "lb_doc_json", "lb_doc_vv",
-            "lb_batch_counters", "lb_batch_timings", "lb_batch_free", "lb_doc_count", "lb_last_error"} <= names
+            "lb_batch_counters", "lb_batch_timings", "lb_batch_free", "lb_doc_count", "lb_last_error",
+            "lb_doc_frontiers", "lb_doc_export_updates", "lb_docset_new", "lb_docset_import", "lb_docset_free"} <= names
     for n in names:
         assert hasattr(lib, n), n
 
@@ -32,6 +33,8 @@ def test_no_cpu_fallback_without_a_device():
     import loro_b200
     with pytest.raises(loro_b200.EngineUnavailable):
         loro_b200.import_batch([b"loro" + bytes(30)])
+    with pytest.raises(loro_b200.EngineUnavailable):
+        loro_b200.DocSet()
 
 
 def test_sass_is_sm100a(lib):

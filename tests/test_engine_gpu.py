@@ -415,3 +415,15 @@ def test_docset_imports_against_existing_documents(seed):
     from tests.docset_checks import check_docset_against_oracle
     steps = check_docset_against_oracle(n_docs=12, seed=seed, rounds=8, edits=16)
     assert steps > 5
+
+
+def test_docset_compaction_equals_recreating_the_document_from_its_export():
+    """LB_FLAG_COMPACT: a document without pending changes is kept as its own export; everything it answers afterwards
+    equals a reference document re-created with fresh.import(doc.export(all_updates)) at the same points."""
+    from tests.docset_checks import check_docset_against_oracle
+    assert check_docset_against_oracle(n_docs=8, seed=21, rounds=8, edits=16, compact=True) > 5
+
+
+def test_docset_updates_that_start_inside_known_changes():
+    from tests.docset_checks import check_docset_against_oracle
+    assert check_docset_against_oracle(n_docs=8, seed=2, rounds=8, edits=16, stale_inside=True) > 5
