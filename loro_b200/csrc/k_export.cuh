@@ -901,13 +901,31 @@ __global__ void k_exp_sizes(const DocInfo* __restrict__ docs, u32 n_docs, Export
 // All work on an index range with a value functor, so that a literal segment's length is known before its values
 // are written (serde_columnar AnyRle state machine: maximal runs of >= 2 equal values become runs, the values
 // between them literal segments; a lone value is a literal of one).
+// The values come out of per-block scratch columns in global memory and every scan below is a chain of dependent
+// loads (28 % of the encoder's stall samples sat on them, profiles/r2_ncu_expenc.md): with LB_XENC_LOOKAHEAD the scans
+// fetch four values at a time -- the loads are independent of each other and of the comparisons -- and consume them in
+// order.  Same segments, same bytes.
+#ifndef LB_XENC_LOOKAHEAD
+#define LB_XENC_LOOKAHEAD 1
+#endif
 template <class F, class W>
 __device__ inline void enc_anyrle(XSink& s, u32 n, F val, W wr) {
     u32 i = 0;
     while (i < n) {
         i64 v = val(i);
         u32 j = i;
+#if LB_XENC_LOOKAHEAD
+        while (j + 1 < n) {
+            const u32 base = j + 1, m = n - base < 4 ? n - base : 4;
+            i64 w0 = val(base), w1 = m > 1 ? val(base + 1) : 0, w2 = m > 2 ? val(base + 2) : 0, w3 = m > 3 ? val(base + 3) : 0;
+            u32 q = 0;
+            if (w0 == v) { q = 1; if (m > 1 && w1 == v) { q = 2; if (m > 2 && w2 == v) { q = 3; if (m > 3 && w3 == v) q = 4; } } }
+            j += q;
+            if (q < m) break;
+        }
+#else
         while (j + 1 < n && val(j + 1) == v) j++;
+#endif
         if (j > i) {
             s.zigzag((i64)(j - i + 1));
             wr(s, v);
@@ -916,6 +934,33 @@ __device__ inline void enc_anyrle(XSink& s, u32 n, F val, W wr) {
         }
         u32 k = i;
         i64 cur = v;
+#if LB_XENC_LOOKAHEAD
+        while (k < n) {
+            const u32 base = k + 1;
+            if (base >= n) { k++; break; }
+            const u32 m = n - base < 4 ? n - base : 4;
+            i64 w[4];
+            w[0] = val(base); w[1] = m > 1 ? val(base + 1) : 0; w[2] = m > 2 ? val(base + 2) : 0; w[3] = m > 3 ? val(base + 3) : 0;
+            bool stop = false;
+#pragma unroll
+            for (u32 q = 0; q < 4; q++) {
+                if (q >= m || stop) break;
+                if (w[q] == cur) { stop = true; break; }
+                cur = w[q];
+                k++;
+            }
+            if (stop) break;
+        }
+        s.zigzag(-(i64)(k - i));
+        {
+            u32 q = i;
+            for (; q + 4 <= k; q += 4) {
+                i64 a = val(q), b = val(q + 1), c = val(q + 2), d = val(q + 3);
+                wr(s, a); wr(s, b); wr(s, c); wr(s, d);
+            }
+            for (; q < k; q++) wr(s, val(q));
+        }
+#else
         while (k < n) {
             if (k + 1 < n) {
                 i64 nx = val(k + 1);
@@ -926,6 +971,7 @@ __device__ inline void enc_anyrle(XSink& s, u32 n, F val, W wr) {
         }
         s.zigzag(-(i64)(k - i));
         for (u32 q = i; q < k; q++) wr(s, val(q));
+#endif
         i = k;
     }
 }

@@ -778,14 +778,15 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
     seq_fail(c, LB_ERR(DOC_ERR_CAPACITY));
 }
 
-// ---- leaf prefetch.  The kernel is bound by the latency of the leaf round trip of every op (one dependent 512-byte
-// HBM read per op, profiles/r1_ncu_seq.md).  When 32 op records arrive, every lane predicts the leaf ITS record will
-// touch -- deletes from the atom -> leaf lookup they do anyway, inserts by walking the shared-memory nodes on its own
-// (lane-serial, the warp runs 32 descents at once) -- and asks L2 for it.  The prediction ignores the ops in between
-// and the version switches (a position is only right at the op's own version), so it is a hint: the op's real descent
-// runs as before and usually finds its leaf in L2 instead of HBM.
+// ---- leaf prefetch (measured, NOT enabled).  The kernel is bound by the latency of the leaf round trip of every op (one
+// dependent 512-byte HBM read per op, profiles/r2_ncu_seq.md).  With LB_SEQ_PF, when 32 op records arrive, every lane
+// predicts the leaf ITS record will touch -- deletes from the atom -> leaf lookup they do anyway, inserts by walking the
+// shared-memory nodes on its own (lane-serial, the warp runs 32 descents at once) -- and asks L2 (or L1) for it.
+// On B200 at 8192 documents of C3 (profiles/r2_variants_8192docs.txt): off 87.6 ms, deletes only 87.6 ms, deletes +
+// inserts 94.4 ms (L2) / 94.6 ms (L1): the 32 resident warps per SM already overlap each other's leaf reads, the
+// predicted descents cost more issue slots than the prefetches save.  C2 and C4 (one warp on the whole GPU): no change.
 #ifndef LB_SEQ_PF
-#define LB_SEQ_PF 2           // 0: off, 1: delete targets only, 2: inserts too
+#define LB_SEQ_PF 0           // 0: off, 1: delete targets only, 2: inserts too
 #endif
 __device__ __forceinline__ void prefetch_leaf(const SeqPools& p, const Cx& c, u32 leaf) {
 #ifndef LB_SIMT_EMU

@@ -1,0 +1,50 @@
+#!/bin/bash
+# Round-2 final pass (run under gpurun): GPU parity tests, an A/B of the encoder lookahead, then the bench line of every
+# BASELINE config at stated size, the docset measurement, the reference arm and the launch list of the final build.
+O=gpurun_out
+mkdir -p $O
+T=${TAG:-r2f}
+exec < /dev/null
+TO="timeout -k 10"
+date > $O/${T}_times.txt
+$TO 600 python -m pytest tests -m gpu -x -q > $O/${T}_gputests.log 2>&1; tail -3 $O/${T}_gputests.log
+date >> $O/${T}_times.txt
+# ---- A/B at 8192 documents: default build (encoder lookahead on) against the variant without it
+$TO 240 python bench.py --docs 8192 --steps 3 --warmup 3 --no-e2e --cpu-sample-docs 4 > $O/${T}_ab_default.json 2> $O/ab_default.err
+USE=""
+if [ -f build_variants/xla0.so ]; then
+  LORO_B200_LIB=$PWD/build_variants/xla0.so $TO 240 python bench.py --docs 8192 --steps 3 --warmup 3 --no-e2e --cpu-sample-docs 4 > $O/${T}_ab_xla0.json 2> $O/ab_xla0.err
+  USE=$(python - <<'EOF'
+import json
+try:
+    a = json.loads(open("gpurun_out/r2f_ab_default.json").read().strip().splitlines()[-1])
+    b = json.loads(open("gpurun_out/r2f_ab_xla0.json").read().strip().splitlines()[-1])
+    print("xla0" if b["phases_ms"]["reexport"] < 0.98 * a["phases_ms"]["reexport"] else "")
+except Exception:
+    print("")
+EOF
+)
+fi
+echo "final lines use: ${USE:-default build}" | tee $O/${T}_choice.txt
+[ -n "$USE" ] && export LORO_B200_LIB=$PWD/build_variants/$USE.so
+python scripts/show_bench.py $O/${T}_ab_*.json
+date >> $O/${T}_times.txt
+# ---- the lines
+$TO 600 python bench.py --steps 5 --warmup 3 > $O/${T}_bench_C3.json 2> $O/bench_C3.err
+date >> $O/${T}_times.txt
+$TO 300 python bench.py --config C5 --steps 5 --warmup 3 > $O/${T}_bench_C5.json 2> $O/bench_C5.err
+$TO 300 python bench.py --config C2 --steps 5 --warmup 3 > $O/${T}_bench_C2.json 2> $O/bench_C2.err
+date >> $O/${T}_times.txt
+$TO 420 python bench.py --config C4 --steps 3 --warmup 3 > $O/${T}_bench_C4.json 2> $O/bench_C4.err
+date >> $O/${T}_times.txt
+$TO 300 python scripts/bench_docset.py --docs 8192 --steps 3 > $O/${T}_bench_docset.json 2> $O/bench_docset.err
+$TO 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference_arm.json 2> $O/bench_ref.err
+python scripts/show_bench.py $O/${T}_bench_C*.json
+cat $O/${T}_bench_docset.json
+date >> $O/${T}_times.txt
+# ---- launch list of the final build (shares of the step)
+$TO 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${T}_launches_C3.csv python bench.py --docs 8192 --steps 1 --warmup 1 --no-e2e --cpu-sample-docs 4 > /dev/null 2>&1
+$TO 60 python scripts/launch_summary.py $O/${T}_launches_C3.csv > $O/${T}_launches_summary.md 2>&1
+cat $O/${T}_launches_summary.md | head -12
+date >> $O/${T}_times.txt
+ls -la $O | tail -30
