@@ -12,19 +12,12 @@ date >> $O/${T}_times.txt
 # ---- A/B at 8192 documents: default build (encoder lookahead on) against the variant without it
 $TO 240 python bench.py --docs 8192 --steps 3 --warmup 3 --no-e2e --cpu-sample-docs 4 > $O/${T}_ab_default.json 2> $O/ab_default.err
 USE=""
-if [ -f build_variants/xla0.so ]; then
-  LORO_B200_LIB=$PWD/build_variants/xla0.so $TO 240 python bench.py --docs 8192 --steps 3 --warmup 3 --no-e2e --cpu-sample-docs 4 > $O/${T}_ab_xla0.json 2> $O/ab_xla0.err
-  USE=$(python - <<'EOF'
-import json
-try:
-    a = json.loads(open("gpurun_out/r2f_ab_default.json").read().strip().splitlines()[-1])
-    b = json.loads(open("gpurun_out/r2f_ab_xla0.json").read().strip().splitlines()[-1])
-    print("xla0" if b["phases_ms"]["reexport"] < 0.98 * a["phases_ms"]["reexport"] else "")
-except Exception:
-    print("")
-EOF
-)
-fi
+for v in build_variants/*.so; do
+  n=$(basename $v .so)
+  LORO_B200_LIB=$PWD/$v $TO 240 python bench.py --docs 8192 --steps 3 --warmup 3 --no-e2e --cpu-sample-docs 4 > $O/${T}_ab_$n.json 2> $O/ab_$n.err
+done
+# the fastest re-export among the encoder variants decides the build of the final lines (>= 2 % better than the default)
+USE=$(python scripts/pick_variant.py $T)
 echo "final lines use: ${USE:-default build}" | tee $O/${T}_choice.txt
 [ -n "$USE" ] && export LORO_B200_LIB=$PWD/build_variants/$USE.so
 python scripts/show_bench.py $O/${T}_ab_*.json
