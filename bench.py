@@ -380,7 +380,7 @@ def main():
         h2d = int(lens.sum())
         for _ in range(1):
             b = loro_b200.import_batch(blobs, device=local, flags=xflags)
-            b.json_bytes(0)
+            b.fetch_json()
             b.close()
         if world > 1:
             dist.barrier()
@@ -388,12 +388,12 @@ def main():
         t0 = time.time()
         d2h = 0
         for _ in range(args.steps):
-            b = loro_b200.import_batch(blobs, device=local, flags=xflags)
-            b.json_bytes(0)  # pulls the whole JSON buffer of the batch to the host
+            b = loro_b200.import_batch(blobs, device=local, flags=xflags)   # large batches: overlapping sub-batches (api.MultiBatch)
+            b.fetch_json()   # pulls the JSON of every document of the batch to the host
             cc = b.counters()
             d2h = cc["json_bytes"] + n_docs * 256
             if xflags:
-                b.export_updates(0)  # pulls every document's re-exported blob to the host
+                b.fetch_exports()  # pulls every document's re-exported blob to the host
                 d2h += b.timings()["export_bytes"]
             b.close()
         torch.cuda.synchronize()
@@ -402,7 +402,8 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": total_atoms * args.steps / (float(te.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+               "host_sub_batches": loro_b200.api.auto_split(blobs)}
 
     if rank != 0:
         if world > 1:

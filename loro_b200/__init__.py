@@ -10,8 +10,8 @@ Host-side mirror of the reference's public API for that path (crates/loro/src/li
 All compute runs in the CUDA library built from loro_b200/csrc (C ABI: include/loro_b200.h).  There is no
 CPU fallback: importing a batch without the built library or without a CUDA device raises.
 """
-from .api import (Batch, DocError, DocSet, EngineUnavailable, ImportStatus, import_batch, import_batch_device,
+from .api import (Batch, MultiBatch, DocError, DocSet, EngineUnavailable, ImportStatus, import_batch, import_batch_device,
                   library_path, load_library, numa_bind, device_trim, pack_blobs)
 
-__all__ = ["Batch", "DocError", "DocSet", "EngineUnavailable", "ImportStatus", "import_batch", "import_batch_device",
+__all__ = ["Batch", "MultiBatch", "DocError", "DocSet", "EngineUnavailable", "ImportStatus", "import_batch", "import_batch_device",
            "library_path", "load_library", "numa_bind", "device_trim", "pack_blobs"]

@@ -180,6 +180,16 @@ class Batch:
         _check(self._L, self._L.lb_doc_json(self._h, i, ctypes.byref(p), ctypes.byref(n)), "lb_doc_json")
         return ctypes.string_at(p, n.value)
 
+    def fetch_json(self):
+        """make sure the JSON of every document of the batch is in host memory (one download of the whole buffer)"""
+        if self.n_docs:
+            self.json_bytes(0)
+
+    def fetch_exports(self):
+        """same for the re-exported blobs (needs LB_FLAG_EXPORT)"""
+        if self.n_docs:
+            self.export_updates(0)
+
     def get_deep_value(self, i):
         st = self.status(i)
         if st.code != 0:
@@ -222,11 +232,138 @@ class Batch:
         return arr
 
 
-def import_batch(blobs, device=0, flags=0, lib_path=None, doc_ids=None):
+class MultiBatch:
+    """A large host batch imported as consecutive sub-batches, two C-ABI calls in flight: while one sub-batch computes,
+    the next one's blobs go through the pinned staging ring and the previous one's JSON / exported blobs come home
+    (documents are independent, so the split changes no result).  Same accessors as Batch; document i lives in the
+    sub-batch that holds it."""
+
+    def __init__(self, parts):
+        self._parts = parts
+        self._bounds = [0]
+        for p in parts:
+            self._bounds.append(self._bounds[-1] + p.n_docs)
+        self.n_docs = self._bounds[-1]
+
+    def _loc(self, i):
+        import bisect
+        if not 0 <= i < self.n_docs:
+            raise IndexError(i)
+        k = bisect.bisect_right(self._bounds, i) - 1
+        return self._parts[k], i - self._bounds[k]
+
+    def status(self, i): p, j = self._loc(i); return p.status(j)
+    def json_bytes(self, i): p, j = self._loc(i); return p.json_bytes(j)
+    def get_deep_value(self, i): p, j = self._loc(i); return p.get_deep_value(j)
+    def oplog_vv(self, i): p, j = self._loc(i); return p.oplog_vv(j)
+    def oplog_frontiers(self, i): p, j = self._loc(i); return p.oplog_frontiers(j)
+    def export_updates(self, i, from_vv=None): p, j = self._loc(i); return p.export_updates(j, from_vv)
+
+    def fetch_json(self):
+        for p in self._parts:
+            p.fetch_json()
+
+    def fetch_exports(self):
+        for p in self._parts:
+            p.fetch_exports()
+
+    def counters(self):
+        out = {}
+        for p in self._parts:
+            for k, v in p.counters().items():
+                out[k] = (out.get(k, 0) ^ v) if k == "state_hash" else out.get(k, 0) + v
+        return out
+
+    def timings(self):
+        """per-phase device times summed over the sub-batches (they overlap on the device: the sum is not a wall time)"""
+        out = {}
+        for p in self._parts:
+            for k, v in p.timings().items():
+                out[k] = out.get(k, 0) + v
+        return out
+
+    def close(self):
+        for p in self._parts:
+            p.close()
+        self._parts = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+SPLIT_MIN_BYTES = 256 << 20   # host batches at least this large are imported as overlapping sub-batches ...
+SPLIT_MIN_PART_DOCS = 2048    # ... of at least this many documents each (one warp per document: fewer would idle the SMs)
+SPLIT_PARTS = 4
+
+
+def auto_split(blobs):
+    """number of sub-batches import_batch uses for `blobs` when the caller does not say"""
+    n = len(blobs)
+    if n < 2 * SPLIT_MIN_PART_DOCS:
+        return 1
+    total = 0
+    for b in blobs:
+        total += len(b)
+        if total >= SPLIT_MIN_BYTES:
+            return max(1, min(SPLIT_PARTS, n // SPLIT_MIN_PART_DOCS))
+    return 1
+
+
+def _import_one(L, blobs, device, flags, doc_ids):
+    arr, keep = _blob_array(blobs, doc_ids)
+    opt = _Options(device=device, flags=flags)
+    h = ctypes.c_void_p()
+    _check(L, L.lb_import_batch(arr, len(blobs), ctypes.byref(opt), ctypes.byref(h)), "lb_import_batch")
+    return Batch(L, h.value)
+
+
+def import_batch(blobs, device=0, flags=0, lib_path=None, doc_ids=None, split=None):
     """LoroDoc::import for a batch: one fresh document per blob (bytes-like), host buffers in.
     `doc_ids` (one int per blob) groups blobs into documents the way LoroDoc::import_batch takes several updates:
-    blobs with the same id form one document; documents are numbered in order of first appearance."""
+    blobs with the same id form one document; documents are numbered in order of first appearance.
+    `split`: number of sub-batches (None = auto_split(blobs) for batches without doc_ids: up to SPLIT_PARTS once the
+    batch holds SPLIT_MIN_BYTES, never fewer than SPLIT_MIN_PART_DOCS documents each): sub-batches are imported two
+    at a time so that the host<->device transfers of one overlap the kernels of the other; the result is a MultiBatch."""
     L = load_library(lib_path)
+    n = len(blobs)
+    if split is None:
+        split = auto_split(blobs) if doc_ids is None else 1
+    if split > 1 and doc_ids is None and n >= 2 * split:
+        import threading
+        step = (n + split - 1) // split
+        ranges = [(a, min(n, a + step)) for a in range(0, n, step)]
+        parts = [None] * len(ranges)
+        errs = []
+        nxt = [0]
+        lock = threading.Lock()
+
+        def work():
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= len(ranges) or errs:
+                    return
+                a, b = ranges[k]
+                try:
+                    parts[k] = _import_one(L, blobs[a:b], device, flags, None)
+                except Exception as e:   # noqa: BLE001 -- re-raised below
+                    errs.append(e)
+
+        ts = [threading.Thread(target=work) for _ in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            for p in parts:
+                if p is not None:
+                    p.close()
+            raise errs[0]
+        return MultiBatch(parts)
     n = len(blobs)
     arr, keep = _blob_array(blobs, doc_ids)
     opt = _Options(device=device, flags=flags)

@@ -392,3 +392,24 @@ def test_import_batch_status_of_overlapping_updates(seed):
     assert r.json_bytes(0) == ref.json_text()
     assert r.oplog_vv(0) == ref.oplog_vv()
     assert st.success == ost["success"] and st.pending == ost["pending"], (st, ost)
+
+
+def test_host_batch_split_into_overlapping_sub_batches():
+    """import_batch(split=k): consecutive sub-batches, two C-ABI calls in flight; every accessor answers as the
+    unsplit batch does (documents are independent)."""
+    import loro_b200
+    from loro_b200 import api
+    blobs = [workloads.make_doc_history(6100 + i, n_sites=2 + i % 2, n_ops=50 + 7 * i)[0] for i in range(11)]
+    one = loro_b200.import_batch(blobs, flags=api.LB_FLAG_EXPORT, lib_path=EMU, split=1)
+    many = loro_b200.import_batch(blobs, flags=api.LB_FLAG_EXPORT, lib_path=EMU, split=3)
+    assert isinstance(many, api.MultiBatch) and many.n_docs == one.n_docs == 11
+    many.fetch_json()
+    many.fetch_exports()
+    for i in range(11):
+        assert many.status(i) == one.status(i)
+        assert many.json_bytes(i) == one.json_bytes(i)
+        assert many.oplog_vv(i) == one.oplog_vv(i) and many.oplog_frontiers(i) == one.oplog_frontiers(i)
+        assert many.export_updates(i) == one.export_updates(i)
+    a, b = many.counters(), one.counters()
+    assert a["atom_ops"] == b["atom_ops"] and a["state_hash"] == b["state_hash"] and a["docs_ok"] == 11
+    assert api.auto_split(blobs) == 1

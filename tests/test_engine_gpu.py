@@ -427,3 +427,14 @@ def test_docset_compaction_equals_recreating_the_document_from_its_export():
 def test_docset_updates_that_start_inside_known_changes():
     from tests.docset_checks import check_docset_against_oracle
     assert check_docset_against_oracle(n_docs=8, seed=2, rounds=8, edits=16, stale_inside=True) > 5
+
+
+def test_host_batch_split_into_overlapping_sub_batches():
+    from tests.test_engine_emu import test_host_batch_split_into_overlapping_sub_batches as body
+    import tests.test_engine_emu as emu
+    saved = emu.EMU
+    emu.EMU = None
+    try:
+        body()
+    finally:
+        emu.EMU = saved
