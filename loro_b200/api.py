@@ -302,6 +302,9 @@ SPLIT_PARTS = 4
 def auto_split(blobs):
     """number of sub-batches import_batch uses for `blobs` when the caller does not say"""
     n = len(blobs)
+    forced = os.environ.get("LORO_B200_SPLIT")     # measurement hook: force the number of sub-batches
+    if forced:
+        return max(1, int(forced))
     if n < 2 * SPLIT_MIN_PART_DOCS:
         return 1
     total = 0
@@ -350,6 +353,8 @@ def import_batch(blobs, device=0, flags=0, lib_path=None, doc_ids=None, split=No
                 a, b = ranges[k]
                 try:
                     parts[k] = _import_one(L, blobs[a:b], device, flags, None)
+                    if flags & LB_FLAG_EXPORT:
+                        parts[k].fetch_exports()    # this sub-batch's blobs come home while the next one computes
                 except Exception as e:   # noqa: BLE001 -- re-raised below
                     errs.append(e)
 

@@ -1,7 +1,7 @@
 // Host <-> device staging for the host-buffer entry points (lb_import_batch, lb_doc_json).
 //
 // The caller's blobs are ~100k separate pageable allocations; the JSON result is one large pageable buffer.
-// Both directions go through a small process-wide ring of pinned slots: worker threads gather/scatter one slot
+// Each direction goes through a small process-wide ring of pinned slots: worker threads gather/scatter one slot
 // while the copy engine moves the other, so the PCIe transfer overlaps the host memcpy and no batch-sized pinned
 // allocation (seconds for several GB) is ever made.
 #pragma once
@@ -34,9 +34,12 @@ struct Ring {
     }
 };
 
-inline Ring& ring() {
-    static Ring r;
-    return r;
+// One ring per direction: PCIe is full duplex, and with two imports in flight (api.MultiBatch, or any host that calls
+// the C ABI from two threads) the upload of one batch runs while the other's JSON / exported blobs come home.  A
+// download of JSON (second stream, its own thread) and one of exported blobs still take turns on the download ring.
+inline Ring& ring(int dir) {
+    static Ring r[2];
+    return r[dir & 1];
 }
 
 // LB_STAGE_SLOT (bytes, testing hook) shrinks the slot so that small inputs exercise the multi-slot, multi-thread paths.
@@ -140,7 +143,7 @@ inline void gather(const BlobView* blobs, const uint64_t* offs, size_t n_blobs, 
 
 // Host blobs -> one contiguous device buffer.  Returns false on a CUDA error.
 inline bool upload_blobs(const BlobView* blobs, const uint64_t* offs, size_t n_blobs, uint8_t* d_dst, cudaStream_t st) {
-    Ring& r = ring();
+    Ring& r = ring(0);
     std::lock_guard<std::mutex> g(r.mu);
     if (!r.init()) return false;
     size_t total = offs[n_blobs];
@@ -161,7 +164,7 @@ inline bool upload_blobs(const BlobView* blobs, const uint64_t* offs, size_t n_b
 
 // Device buffer -> pageable host buffer.
 inline bool download(const uint8_t* d_src, uint8_t* dst, size_t total, cudaStream_t st) {
-    Ring& r = ring();
+    Ring& r = ring(1);
     std::lock_guard<std::mutex> g(r.mu);
     if (!r.init()) return false;
     const size_t SB = slot_bytes();
