@@ -296,7 +296,7 @@ class MultiBatch:
 
 SPLIT_MIN_BYTES = 256 << 20   # host batches at least this large are imported as overlapping sub-batches ...
 SPLIT_MIN_PART_DOCS = 2048    # ... of at least this many documents each (one warp per document: fewer would idle the SMs)
-SPLIT_PARTS = 4
+SPLIT_PARTS = 2
 
 
 def auto_split(blobs):

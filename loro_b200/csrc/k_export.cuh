@@ -1172,12 +1172,14 @@ __global__ void k_exp_posrank(const DocInfo* __restrict__ docs, u32 n_docs, Expo
 }
 
 // thread per output block.  pass 0: gather ops into scratch columns, registers, section sizes ; pass 1: bytes.
-#ifdef LB_XENC_MINB
-__global__ void __launch_bounds__(64, LB_XENC_MINB) k_exp_encode(
-#else
-__global__ void k_exp_encode(
-#endif
-    const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
+// Two builds of the same code: <1> is compiled with __launch_bounds__(64, 5) (the compiler then schedules for 64-thread
+// CTAs: 132 registers against 124 without bounds, other load / store placement), <0> without bounds.
+// Measured on B200 (profiles/r2f_*, r2g_*): with ~10^5 output blocks in the batch the capped build is faster (C5 at
+// 10 k documents: 49.5 against 62.5 ms for the whole phase, C3 at 8192 documents 48.6 against 50.6), with ~10^6 <1> is
+// slower (C3 at 100 k documents 522 against 448 ms, C2 52.3 against 45.9): the host picks by the number of blocks.
+#define LB_XENC_CAP_BLOCKS 400000ull
+__device__ __forceinline__ void exp_encode_body(
+    const DocInfo* __restrict__ docs, u64 n_blocks, const ExportTables& t, XBlock* __restrict__ xb,
                              u32* __restrict__ scratch, u8* __restrict__ out, int pass) {
     u64 bi_ = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (bi_ >= n_blocks) return;
@@ -1519,6 +1521,18 @@ __global__ void k_exp_encode(
         for (int c = 0; c < 3; c++) { s.varint(B.col_len[4 + c]); w_delcol(s, c); }
     }
     s.varint(B.sec_len[7]); w_values(s);
+}
+
+template <int CAPPED> __global__ void k_exp_encode(const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
+                                                 u32* __restrict__ scratch, u8* __restrict__ out, int pass);
+template <> __global__ void k_exp_encode<0>(const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t, XBlock* __restrict__ xb,
+                                            u32* __restrict__ scratch, u8* __restrict__ out, int pass) {
+    exp_encode_body(docs, n_blocks, t, xb, scratch, out, pass);
+}
+template <> __global__ void __launch_bounds__(64, 5) k_exp_encode<1>(const DocInfo* __restrict__ docs, u64 n_blocks, ExportTables t,
+                                                                     XBlock* __restrict__ xb, u32* __restrict__ scratch,
+                                                                     u8* __restrict__ out, int pass) {
+    exp_encode_body(docs, n_blocks, t, xb, scratch, out, pass);
 }
 
 // thread per document: block offsets inside the blob, blob length (after encode pass 0)
