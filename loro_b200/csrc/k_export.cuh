@@ -1176,8 +1176,9 @@ __global__ void k_exp_posrank(const DocInfo* __restrict__ docs, u32 n_docs, Expo
 // CTAs: 132 registers against 124 without bounds, other load / store placement), <0> without bounds.
 // Measured on B200 (profiles/r2f_*, r2g_*): with ~10^5 output blocks in the batch the capped build is faster (C5 at
 // 10 k documents: 49.5 against 62.5 ms for the whole phase, C3 at 8192 documents 48.6 against 50.6), with ~10^6 <1> is
-// slower (C3 at 100 k documents 522 against 448 ms, C2 52.3 against 45.9): the host picks by the number of blocks.
-#define LB_XENC_CAP_BLOCKS 400000ull
+// slower (C3 at 100 k documents, 1.4 M blocks: 522 against 448 ms; C2, 258 k blocks: 52.3 against 45.9): the host picks by
+// the number of blocks.
+#define LB_XENC_CAP_BLOCKS 200000ull
 __device__ __forceinline__ void exp_encode_body(
     const DocInfo* __restrict__ docs, u64 n_blocks, const ExportTables& t, XBlock* __restrict__ xb,
                              u32* __restrict__ scratch, u8* __restrict__ out, int pass) {
