@@ -308,10 +308,13 @@ __device__ inline u32 pick_copy_multi(const DocInfo& di, const ResolveTables& t,
     u32 best = 0xFFFFFFFFu, best_lam = 0, best_e = 0;
     u64 best_key = ~0ull;
     *soft = false;
+    u32 looked = 0;
     for (u32 j = from; j < dp.ch_count; j++) {
         u32 ch = t.ch_order[di.ch0 + dp.ch_first + j];
         i32 ctr = t.ch_counter[ch];
         if (ctr > dp.end_counter) break;                                   // sorted by counter: nothing further reaches the frontier
+        if (++looked > EPOCH_SCAN_CAP) break;   // hundreds of copies stacked on one atom: the first ones decide (a bound on
+                                                // the work a hostile document can ask for; see EPOCH_SCAN_CAP)
         if (t.ch_applied[ch] || ctr + (i32)t.ch_len[ch] <= dp.end_counter) continue;   // consumed / already known
         const BlockInfo& bi = blocks[t.ch_block[ch]];
         const u32 k = bi.blob_rank;

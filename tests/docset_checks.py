@@ -62,7 +62,7 @@ def _session(seed, n_sites, rounds, edits, stale_inside=False):
 
 
 def check_docset_against_oracle(lib_path=None, n_docs=4, seed=0, rounds=6, edits=12, export_parity=True, compact=False,
-                                stale_inside=False):
+                                stale_inside=False, require_coverage=True):
     """compact=False: the documents keep every blob (exported bytes equal the reference's after the same sequence of
     imports).  compact=True: every import carries LB_FLAG_COMPACT, i.e. a document without pending changes is replaced
     by a fresh one that imported its own export -- the oracle documents do exactly that after every import.
@@ -126,6 +126,7 @@ def check_docset_against_oracle(lib_path=None, n_docs=4, seed=0, rounds=6, edits
         batch.close()
         steps += 1
     assert ds.n_docs == n_docs
-    assert saw_pending > 0 and (compact or saw_known > 0), (saw_pending, saw_known)
+    if require_coverage:   # the stream must have exercised pending changes and imports that added nothing
+        assert saw_pending > 0 and (compact or saw_known > 0), (saw_pending, saw_known)
     ds.close()
     return steps

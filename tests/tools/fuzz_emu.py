@@ -34,8 +34,45 @@ def main(lib, seed, n):
         big.text_insert(big.get_text("t"), 0, "w\u00e9 " * 2500)
         big.list_insert(big.get_list("l"), 0, *list(range(1500)))
         base.append(big.export_updates())
+    # several blobs per document (import_batch groups / docset imports): overlapping and repeated updates of one history,
+    # one of them mutated -- the copy selection, the applied-order lists and the status pass see inconsistent copies
+    multi = []
+    if os.environ.get("LB_FUZZ_MULTI"):
+        for i in range(3):
+            _, _, tot, sites = workloads.make_doc_history(500 + i, n_sites=3, n_ops=150)
+            full = sites[0]
+            parts = [full.export_updates({p: rnd.randrange(0, c + 1) for p, c in tot.items()}) for _ in range(3)]
+            parts += [full.export_updates({q: c for q, c in tot.items() if q != p}) for p in list(tot)[:2]]
+            multi.append(parts)
     ok = 0
-    for _ in range(n):
+    for it in range(n):
+        if multi:
+            parts = [bytes(x) for x in rnd.choice(multi)]
+            rnd.shuffle(parts)
+            k = rnd.randrange(len(parts))
+            b = bytearray(parts[k])
+            for _ in range(rnd.randint(1, 3)):
+                i = rnd.randrange(22, len(b))
+                b[i] = (b[i] & 0x80) | rnd.randrange(128) if rnd.random() < 0.7 else rnd.randrange(256)
+            parts[k] = reseal(b)
+            if it % 2:
+                r = loro_b200.import_batch(parts, doc_ids=[1] * len(parts), flags=api.LB_FLAG_EXPORT, lib_path=lib)
+                rs = [r]
+            else:       # the same through a docset, two calls
+                ds = loro_b200.DocSet(lib_path=lib)
+                rs = [ds.import_(parts[:2], [1, 1]), ds.import_(parts[2:], [1] * (len(parts) - 2))]
+            for r in rs:
+                if r.status(0).code == 0:
+                    ok += 1
+                    r.json_bytes(0)
+                    try:
+                        r.export_updates(0)
+                    except api.EngineError:
+                        pass
+                r.close()
+            if it % 2 == 0:
+                ds.close()
+            continue
         b = bytearray(rnd.choice(base))
         for _ in range(rnd.randint(1, 4)):
             i = rnd.randrange(22, len(b))
