@@ -1,8 +1,9 @@
 /* loro_b200 -- C ABI of the B200-native batched CRDT merge engine.
  *
- * Drop-in boundary for ONE hot path of loro-dev/loro: batched `LoroDoc::import` of FastUpdates blobs
- * into fresh documents -> (decode, causal scan, eg-walker merge) -> deep JSON state / import status
- * -> re-export of every document (`export(ExportMode::all_updates)`).
+ * Drop-in boundary for ONE hot path of loro-dev/loro: batched `LoroDoc::import` / `import_batch` of FastUpdates blobs
+ * into fresh documents (lb_import_batch*) or into documents that already hold history (lb_docset_*) -> (decode, causal
+ * scan, eg-walker merge of List / Text / Map / Tree) -> deep JSON state / import status / version vector / frontiers
+ * -> re-export of every document (`export(ExportMode::all_updates)`, `export(updates(from))` on demand).
  * The reference has no C FFI for this path; every entry point cites the Rust interface it
  * replaces (paths relative to /root/reference):
  *
@@ -14,8 +15,10 @@
  *   lb_doc_json              crates/loro/src/lib.rs:866  LoroDoc::get_deep_value() (serde_json text, keys sorted)
  *   lb_doc_vv                crates/loro/src/lib.rs:816  LoroDoc::oplog_vv()
  *   lb_doc_frontiers         crates/loro/src/lib.rs:881  LoroDoc::oplog_frontiers()
- *   lb_doc_export_updates    crates/loro/src/lib.rs:1235 LoroDoc::export(ExportMode::all_updates())
- *                            crates/loro-internal/src/encoding.rs:350-416, oplog/change_store.rs:494-576
+ *   lb_doc_export_updates    crates/loro/src/lib.rs:1235 LoroDoc::export(ExportMode::all_updates() / updates(from))
+ *                            crates/loro-internal/src/encoding.rs:79-83, 350-416, oplog/change_store.rs:494-576
+ *   lb_docset_import         crates/loro/src/lib.rs:639, :425 on a document that already holds history
+ *                            (crates/loro-internal/src/loro.rs:562-643, 1183-1290, oplog.rs:130-196)
  *   lb_batch_counters        crates/loro-internal/src/loro.rs:1458 len_ops / len_changes (summed over the batch)
  *
  * Conventions (mirroring the reference): input buffers are borrowed for the duration of the call only;

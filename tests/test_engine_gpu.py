@@ -438,3 +438,31 @@ def test_host_batch_split_into_overlapping_sub_batches():
         body()
     finally:
         emu.EMU = saved
+
+
+def test_config_c4_full_size_against_committed_oracle_digests(golden_dir):
+    """BASELINE config C4 AT STATED SIZE (1 M base chars + 64 peers x 50 k concurrent edits, one document): the oracle
+    replays it in minutes, so its answers are committed as digests (tests/golden/c4_full.json, made by
+    tests/golden/make_c4_golden.py); the engine's JSON, version vector and exported bytes must hash to the same."""
+    import json as _json
+    import loro_b200
+    from loro_b200 import api
+    from loro_b200.workload import C4Doc
+    path = os.path.join(golden_dir, "c4_full.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/c4_full.json not generated")
+    want = _json.load(open(path))
+    g = C4Doc(**want["config"])
+    blob = g.blob(0)
+    xxh = lambda b: oracle.i64s(oracle.codec("xxh32", bytes(b), 0))[0] & 0xFFFFFFFF   # noqa: E731
+    assert len(blob) == want["blob_len"] and xxh(blob) == want["blob_xxh32"]           # same generated input
+    b = loro_b200.import_batch([blob], flags=api.LB_FLAG_EXPORT)
+    st = b.status(0)
+    assert st.code == 0 and st.pending is None
+    assert b.counters()["atom_ops"] == want["atom_ops"]
+    assert b.counters()["state_hash"] == want["state_hash"]
+    js = b.json_bytes(0)
+    assert len(js) == want["json_len"] and xxh(js) == want["json_xxh32"]
+    assert {str(k): v for k, v in b.oplog_vv(0).items()} == want["vv"]
+    ex = b.export_updates(0)
+    assert len(ex) == want["export_len"] and xxh(ex) == want["export_xxh32"]
