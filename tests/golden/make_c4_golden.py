@@ -1,7 +1,7 @@
 """Golden answers for BASELINE config C4 AT STATED SIZE (one Text document: 1 M base chars + 64 peers x 50 k concurrent
 edits): the oracle imports the generated blob once (minutes on one core) and the digests of what it answers are committed
 as tests/golden/c4_full.json, so that the GPU test can check the engine's state and exported bytes for the full
-document without running the oracle on the GPU box.  Usage: python tests/golden/make_c4_golden.py"""
+document without running the oracle on the GPU box.  Usage: python tests/golden/make_c4_golden.py [quarter]"""
 import json
 import os
 import sys
@@ -19,7 +19,9 @@ def xxh32(b, seed=0):
 
 
 def main():
-    cfg = dict(base_chars=1000000, n_peers=64, edits=50000, seed=0)
+    # `quarter` = 500 k base chars + 64 peers x 12.5 k edits (the oracle needs ~5 minutes); default = the stated size (~1 h)
+    quarter = len(sys.argv) > 1 and sys.argv[1] == "quarter"
+    cfg = dict(base_chars=500000, n_peers=64, edits=12500, seed=0) if quarter else dict(base_chars=1000000, n_peers=64, edits=50000, seed=0)
     g = C4Doc(**cfg)
     blob = g.blob(0)
     t0 = time.time()
@@ -32,7 +34,7 @@ def main():
            "export_len": len(ex), "export_xxh32": xxh32(ex), "vv": {str(k): v for k, v in d.oplog_vv().items()},
            "pending": st["pending"], "oracle_seconds": round(time.time() - t0, 1),
            "inconsistent_delete": d.inconsistent_delete()}
-    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c4_full.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "c4_quarter.json" if quarter else "c4_full.json"), "w"), indent=1)
     print(out)
 
 

@@ -440,17 +440,19 @@ def test_host_batch_split_into_overlapping_sub_batches():
         emu.EMU = saved
 
 
-def test_config_c4_full_size_against_committed_oracle_digests(golden_dir):
+@pytest.mark.parametrize("which", ["c4_quarter.json", "c4_full.json"])
+def test_config_c4_full_size_against_committed_oracle_digests(golden_dir, which):
     """BASELINE config C4 AT STATED SIZE (1 M base chars + 64 peers x 50 k concurrent edits, one document): the oracle
     replays it in minutes, so its answers are committed as digests (tests/golden/c4_full.json, made by
-    tests/golden/make_c4_golden.py); the engine's JSON, version vector and exported bytes must hash to the same."""
+    tests/golden/make_c4_golden.py); the engine's JSON, version vector and exported bytes must hash to the same.
+    `c4_quarter.json` is the same generator at 500 k base chars + 64 x 12.5 k edits (4.1 M atom ops)."""
     import json as _json
     import loro_b200
     from loro_b200 import api
     from loro_b200.workload import C4Doc
-    path = os.path.join(golden_dir, "c4_full.json")
+    path = os.path.join(golden_dir, which)
     if not os.path.exists(path):
-        pytest.skip("tests/golden/c4_full.json not generated")
+        pytest.skip(f"tests/golden/{which} not generated")
     want = _json.load(open(path))
     g = C4Doc(**want["config"])
     blob = g.blob(0)
