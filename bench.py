@@ -38,6 +38,8 @@ def parse_args():
                     help="BASELINE.json config: C3 = 100k docs x 10k mixed List/Map ops, 3 peers (the config the metric is quoted on); "
                          "C2 = automerge-paper text trace x 4096 docs; C4 = ONE rich-text doc, 1M chars + 64 peers x 50k concurrent edits "
                          "(does not shard: every GPU runs a replica); C5 = 10k docs x 5k-node movable trees with 3 x 1k concurrent moves")
+    ap.add_argument("--c2-distinct-peers", action="store_true",
+                    help="C2: document i is typed by peer i + 1 (own peer id and checksum in every copy) instead of byte-identical copies")
     ap.add_argument("--c4-base", type=int, default=1000000)
     ap.add_argument("--c4-peers", type=int, default=64)
     ap.add_argument("--c4-edits", type=int, default=50000)
@@ -149,10 +151,66 @@ class TraceBatch:
         return self._blob
 
 
+def peer_id_offsets(blob):
+    """byte offsets of every 8-byte peer id in the `peers` tables of a FastUpdates blob's blocks (block_meta_encode.rs:
+    the header section starts with ULEB n_peers, then n_peers x u64 LE)"""
+    def uleb(i):
+        v, sh = 0, 0
+        while True:
+            c = blob[i]
+            i += 1
+            v |= (c & 0x7f) << sh
+            sh += 7
+            if not c & 0x80:
+                return v, i
+    out, i, n = [], 22, len(blob)
+    while i < n:
+        ln, i = uleb(i)
+        end, j = i + ln, i
+        for _ in range(5):
+            _, j = uleb(j)
+        _, j = uleb(j)            # length prefix of the header section
+        npeers, j = uleb(j)
+        out += [j + 8 * k for k in range(npeers)]
+        i = end
+    return out
+
+
+class TraceBatchDistinctPeers(TraceBatch):
+    """Config C2, SURVEY 8d's variant: document i is the same trace typed by peer (i + 1) -- every copy of the blob gets
+    its own peer id in every block's peers table and its own checksum, so no two documents share their bytes."""
+
+    def __init__(self, n_docs):
+        import struct
+        import numpy as np
+        import oracle
+        super().__init__()
+        base = bytearray(self._blob)
+        offs = peer_id_offsets(base)
+        assert offs and all(base[o:o + 8] == base[offs[0]:offs[0] + 8] for o in offs)   # the trace has one author
+        span = (len(base) + 15) & ~15
+        self.n_docs = n_docs
+        self.bytes = np.zeros(span * n_docs + 64, dtype=np.uint8)
+        self.offsets = (np.arange(n_docs, dtype=np.uint64) * np.uint64(span))
+        self.lens = np.full(n_docs, len(base), dtype=np.uint32)
+        self._blobs = []
+        for d in range(n_docs):
+            pid = struct.pack("<Q", d + 1)
+            for o in offs:
+                base[o:o + 8] = pid
+            h = oracle.i64s(oracle.codec("xxh32", bytes(base[20:]), 0x4F524F4C))[0] & 0xFFFFFFFF
+            base[16:20] = struct.pack("<I", h)
+            self.bytes[d * span:d * span + len(base)] = np.frombuffer(bytes(base), dtype=np.uint8)
+            self._blobs.append(bytes(base))
+
+    def blob(self, i):
+        return self._blobs[i]
+
+
 def workload_text(args, n_docs, extra=""):
     if args.config == "C2":
         return (f"C2: automerge-paper text trace (259,778 patches -> one FastUpdates blob of 1 peer) replicated x {n_docs} docs/GPU, "
-                f"each copy with its own bytes in HBM (SURVEY.md 8d){extra}")
+                f"each copy with its own bytes in HBM{' and its own peer id (document i typed by peer i + 1)' if args.c2_distinct_peers else ''} (SURVEY.md 8d){extra}")
     if args.config == "C4":
         return (f"C4: {n_docs} rich-text document(s)/GPU (replicas: a single document does not shard), {args.c4_base} ASCII chars by peer 0 + "
                 f"{args.c4_peers} peers x {args.c4_edits} concurrent edits (70 % insert 1-8 chars, 30 % delete 1-8), never synced (SURVEY.md 8d){extra}")
@@ -167,6 +225,8 @@ def affordable_distinct(args, world, n_docs):
     """How many DISTINCT documents this rank's share of the host cores can generate in about 90 s
     (~1.2 M generated atom ops/s/core); the batch is filled by cycling through them (every copy has its own bytes
     in HBM; `distinct_docs_per_gpu` in the config says how many there are)."""
+    if args.config == "C2" and args.c2_distinct_peers:
+        return n_docs
     if args.config in ("C2", "C4"):
         return 1
     if args.distinct:
@@ -183,7 +243,7 @@ def make_workload(args, rank, world, n_docs):
     threads = max(1, (host_cores() or 1) // max(1, world))
     t0 = time.time()
     if args.config == "C2":
-        gen = TraceBatch()
+        gen = TraceBatchDistinctPeers(n_docs) if args.c2_distinct_peers else TraceBatch()
     elif args.config == "C4":
         gen = C4Doc(args.c4_base, args.c4_peers, args.c4_edits, seed=rank)
     elif args.config == "C5":
