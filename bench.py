@@ -1,13 +1,16 @@
 #!/usr/bin/env python3
 """bench.py -- merged CRDT ops/sec of the batched import hot path (BASELINE.json metric).
 
-One "step" = one pass of the hot path (decode -> causal scan -> eg-walker merge -> deep JSON) over one batch
-of synthetic documents of config C3 (N docs x 10k mixed List/Map atom ops, 3 concurrent
-peers).  `value` is measured with the update blobs already resident in HBM (lb_import_batch_device); `e2e`
-is the same metric through the host-buffer C-ABI call (lb_import_batch: pinned staging + H2D inside the
-timed region, result JSON + status read back to the host).
+One "step" = one pass of the hot path (decode -> causal scan -> eg-walker / tree merge -> deep JSON -> re-export) over one
+batch of synthetic documents.  --config picks the BASELINE.json configuration: C3 (default, the one the
+metric is quoted on: N docs x 10k mixed List/Map atom ops, 3 concurrent peers), C2 (automerge-paper trace x 4096 docs;
+--c2-distinct-peers gives every copy its own peer id), C4 (ONE text document, 1M chars + 64 peers x 50k concurrent
+edits: replicas only), C5 (10k docs x 5k-node movable trees with concurrent moves).
+`value` is measured with the update blobs already resident in HBM (lb_import_batch_device); `e2e` is the same metric
+through the host-buffer path a user calls (loro_b200.import_batch -> lb_import_batch: pinned staging + H2D inside the
+timed region, JSON + status + re-exported blobs read back to the host; large batches go as two overlapping sub-batches).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--docs D] [--ops-per-doc 10000] [--distinct G]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C4|C5] [--docs D] [--ops-per-doc 10000]
   python bench.py --impl reference ...     # the CPU arm: the oracle port of the reference path on host cores
 
 Under torchrun (N>1) every rank imports its own shard of documents (weak scaling: per-GPU work fixed) and
