@@ -265,10 +265,10 @@ def cpu_baseline(args, gen, threads=None):
     if args.config == "C2":
         n = args.cpu_sample_docs or max(1, min(threads, 16))    # one trace import is ~0.26 M ops: a few copies suffice
     if args.config == "C4":
-        # the full document takes the restated CPU path far longer than the bench may run: a reduced instance of the
-        # same generator (100 k base chars, 16 peers x 3000 edits) on one core -- a single document has one task
+        # the full document takes the restated CPU path ~80 s (one core: a single document has one task), more than the
+        # bench may spend: a quarter-size instance of the same generator (500 k base chars, 64 peers x 12.5 k edits, ~35 s)
         from loro_b200.workload import C4Doc
-        gen = C4Doc(min(args.c4_base, 100000), min(args.c4_peers, 16), min(args.c4_edits, 3000), seed=0)
+        gen = C4Doc(min(args.c4_base, 500000), min(args.c4_peers, 64), min(args.c4_edits, 12500), seed=0)
         n, threads = 1, 1
         reduced = f" -- REDUCED instance ({gen.config['base_chars']} base chars, {gen.config['n_peers']} peers x {gen.config['edits']} edits)"
     else:

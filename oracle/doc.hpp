@@ -178,10 +178,22 @@ struct TSpan {
     struct TBlock* blk = nullptr;
     bool active() const { return !future && del == 0; }
 };
+struct TSuper;
 struct TBlock {
     std::vector<TSpan*> spans;
     int64_t vis = 0;
     std::list<TBlock>::iterator self;
+    TSuper* sup = nullptr;
+};
+// second level of the rope (the reference's is a B-tree, crdt_rope.rs): a run of consecutive blocks with its totals, so
+// that position queries and order keys skip 128 blocks at a time instead of walking the whole list (a single
+// document with millions of spans -- BASELINE config C4 -- took hours otherwise)
+struct TSuper {
+    int64_t vis = 0;       // visible atoms of its blocks
+    int64_t nspans = 0;    // spans of its blocks
+    int nblocks = 0;
+    std::list<TBlock>::iterator first;
+    std::list<TSuper>::iterator self;
 };
 struct DelRec {  // Cursor::Delete(id_span) (tracker/id_to_cursor.rs); op atoms [ctr, ctr+len)
     int len;
@@ -192,7 +204,9 @@ struct DelRec {  // Cursor::Delete(id_span) (tracker/id_to_cursor.rs); op atoms 
 
 struct Tracker {
     static const int BLK = 96;
+    static const int SUP = 256;     // blocks per superblock before it is cut in two
     std::list<TBlock> blocks;
+    std::list<TSuper> supers;
     std::vector<std::map<Counter, TSpan*>> idmap;  // per peer: span start counter -> span
     std::vector<std::map<Counter, DelRec>> delmap;  // per peer: delete-op start counter -> record
     std::vector<Counter> cur_vv;                    // current_vv (tracker.rs:26)
@@ -203,10 +217,36 @@ struct Tracker {
     explicit Tracker(int npeers) : idmap(npeers), delmap(npeers), cur_vv(npeers, 0) {
         blocks.emplace_back();
         blocks.back().self = std::prev(blocks.end());
+        supers.emplace_back();
+        supers.back().self = std::prev(supers.end());
+        supers.back().first = blocks.begin();
+        supers.back().nblocks = 1;
+        blocks.back().sup = &supers.back();
         unknown = new_span(-1, 0, (int)(UINT32_MAX / 4));
         unknown->blk = &blocks.back();
         blocks.back().spans.push_back(unknown);
         blocks.back().vis = unknown->len;
+        supers.back().vis = unknown->len;
+        supers.back().nspans = 1;
+    }
+    void add_vis(TBlock* b, int64_t d) { b->vis += d; b->sup->vis += d; }
+    // a superblock that grew past SUP blocks hands its second half to a new one
+    void split_super(TSuper* su) {
+        if (su->nblocks <= SUP) return;
+        auto ns = supers.emplace(std::next(su->self));
+        ns->self = ns;
+        int half = su->nblocks / 2;
+        auto b = su->first;
+        int64_t vis = 0, nsp = 0;
+        for (int k = 0; k < half; k++, ++b) { vis += b->vis; nsp += (int64_t)b->spans.size(); }
+        ns->first = b;
+        ns->nblocks = su->nblocks - half;
+        ns->vis = su->vis - vis;
+        ns->nspans = su->nspans - nsp;
+        su->nblocks = half;
+        su->vis = vis;
+        su->nspans = nsp;
+        for (int k = 0; k < ns->nblocks; k++, ++b) b->sup = &*ns;
     }
     ~Tracker() {
         for (auto s : pool) delete s;
@@ -239,20 +279,21 @@ struct Tracker {
     // global order key for cmp_pos (crdt_rope.rs:433-446)
     int64_t order_key(TSpan* s) {
         int64_t k = 0;
-        for (auto it = blocks.begin(); it != blocks.end(); ++it) {
-            if (&*it == s->blk) return k + index_in_block(s);
-            k += (int64_t)it->spans.size();
-        }
-        assert(false);
-        return -1;
+        TSuper* su = s->blk->sup;
+        for (auto it = supers.begin(); &*it != su; ++it) k += it->nspans;
+        for (auto it = su->first; &*it != s->blk; ++it) k += (int64_t)it->spans.size();
+        return k + index_in_block(s);
     }
     void insert_span_at(BIt b, int i, TSpan* s) {
         b->spans.insert(b->spans.begin() + i, s);
         s->blk = &*b;
-        b->vis += vlen(s);
+        add_vis(&*b, vlen(s));
+        b->sup->nspans++;
         if ((int)b->spans.size() > BLK) {
             auto nb = blocks.emplace(std::next(b));
             nb->self = nb;
+            nb->sup = b->sup;
+            b->sup->nblocks++;
             int half = (int)b->spans.size() / 2;
             nb->spans.assign(b->spans.begin() + half, b->spans.end());
             b->spans.resize(half);
@@ -261,7 +302,8 @@ struct Tracker {
                 x->blk = &*nb;
                 nb->vis += vlen(x);
             }
-            b->vis -= nb->vis;
+            b->vis -= nb->vis;          // (both blocks stay in the same superblock: its totals are unchanged)
+            split_super(b->sup);
         }
     }
     // split span s at offset k (0<k<len); returns the right part (FugueSpan::_slice, fugue_span.rs:257-279)
@@ -279,7 +321,7 @@ struct Tracker {
         s->len = k;
         BIt b = block_of(s);
         int i = index_in_block(s);
-        b->vis -= vlen(r);  // insert_span_at adds it back
+        add_vis(&*b, -vlen(r));  // insert_span_at adds it back
         insert_span_at(b, i + 1, r);
         if (s->peer >= 0) idmap[s->peer][r->ctr] = r;
         return r;
@@ -315,7 +357,7 @@ struct Tracker {
         int64_t before = vlen(s);
         if (set_future >= 0) s->future = set_future != 0;
         s->del += del_diff;
-        s->blk->vis += vlen(s) - before;
+        add_vis(s->blk, vlen(s) - before);
     }
     // retreat (dir=-1) / forward (dir=+1) the ops of `peer` with counters in [a,b)
     // (tracker.rs:334-441 _checkout, :448-526 forward)
@@ -351,7 +393,10 @@ struct Tracker {
     Cur query_left(int64_t pos) {
         if (pos == 0) return Cur{blocks.begin(), 0, 0};
         int64_t left = pos;
-        for (auto b = blocks.begin(); b != blocks.end(); ++b) {
+        auto su = supers.begin();
+        while (su != supers.end() && left > su->vis) { left -= su->vis; ++su; }   // the first block with left <= vis is in here
+        if (su == supers.end()) throw std::runtime_error("tracker: insert pos out of range");
+        for (auto b = su->first; b != blocks.end(); ++b) {
             if (left <= b->vis) {
                 for (int i = 0; i < (int)b->spans.size(); i++) {
                     int64_t v = vlen(b->spans[i]);
@@ -367,7 +412,10 @@ struct Tracker {
     // ActiveLenQueryPreferRight (crdt_rope.rs:600-652): first visible atom with index == pos
     Cur query_right(int64_t pos) {
         int64_t left = pos;
-        for (auto b = blocks.begin(); b != blocks.end(); ++b) {
+        auto su = supers.begin();
+        while (su != supers.end() && left >= su->vis) { left -= su->vis; ++su; }  // the first block with left < vis is in here
+        if (su == supers.end()) throw std::runtime_error("tracker: delete pos out of range");
+        for (auto b = su->first; b != blocks.end(); ++b) {
             if (left < b->vis) {
                 for (int i = 0; i < (int)b->spans.size(); i++) {
                     int64_t v = vlen(b->spans[i]);
