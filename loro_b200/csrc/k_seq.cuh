@@ -82,8 +82,6 @@ struct Cx {
     u64 leaf0, node0, atom0, cvv0;
     u32 P;
     int lane;
-    bool solo;              // the document has ONE peer: nothing is ever concurrent, so Fugue origins are never looked at
-                            // (sibling scans only run between future spans) and are not recorded either
 };
 
 __device__ __forceinline__ uint4 mk4(u32 x, u32 y, u32 z, u32 w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
@@ -304,10 +302,8 @@ __device__ __noinline__ void split_before(const SeqPools& p, Cx c, u32 peer, i32
         else if (lane > slot + 1) { L.x = ux; L.y = uy; L.z = uz; }
         leaf_store(p, c, leaf, L, slot);
         // origins of the new span start: left origin is its predecessor, right origin is inherited
-        if (!c.solo) {
-            uint4 og = p.a_org[atom_index(c, peer, s_ctr)];
-            if (lane == 0) p.a_org[atom_index(c, peer, ctr)] = mk4(peer | (og.x & 0xFFFF0000u), (u32)(ctr - 1), og.z, 0);
-        }
+        uint4 og = p.a_org[atom_index(c, peer, s_ctr)];
+        if (lane == 0) p.a_org[atom_index(c, peer, ctr)] = mk4(peer | (og.x & 0xFFFF0000u), (u32)(ctr - 1), og.z, 0);
         __syncwarp();
         return;
     }
@@ -563,7 +559,6 @@ __device__ __noinline__ SibOut sibling_scan(const SeqPools& p, Cx c, SibIn in) {
     out.after_valid = false;
     out.after_peer = 0;
     out.after_ctr = 0;
-    if (c.solo) return out;   // one peer: no origins were recorded (and nothing can be concurrent)
     u32 ol_peer = in.ol_peer, or_peer = in.or_peer;
     i32 ol_ctr = in.ol_ctr, or_ctr = in.or_ctr;
     // right parent of the new span: origin_right counts only if its origin_left equals ours
@@ -756,7 +751,7 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
             continue;   // positions moved: locate the cursor again
         }
         uint4 og = mk4(0, 0, 0, 0);
-        if (mid && !c.solo) og = p.a_org[atom_index(c, cur_peer, cur_ctr)];   // right origin inherited by the cut-off tail
+        if (mid) og = p.a_org[atom_index(c, cur_peer, cur_ctr)];   // right origin inherited by the cut-off tail
         u32 link = __shfl_sync(LB_FULL, L.w, 0);
         u32 ux = __shfl_up_sync(LB_FULL, L.x, need);
         u32 uy = __shfl_up_sync(LB_FULL, L.y, need);
@@ -769,11 +764,9 @@ __device__ __forceinline__ void seq_insert(const SeqPools& p, const Cx& c, u32 p
         }
         leaf_store(p, c, tgt_leaf, L, at > 0 ? at - 1 : 0);
         u64 a0 = atom_index(c, peer, ctr);
-        if (!c.solo) {
-            if (lane == 0) p.a_org[a0] = mk4(ol_peer | (or_peer << 16), (u32)ol_ctr, (u32)or_ctr, 0);
-            if (mid && lane == 1)
-                p.a_org[atom_index(c, cur_peer, cur_ctr + off)] = mk4(cur_peer | (og.x & 0xFFFF0000u), (u32)(cur_ctr + off - 1), og.z, 0);
-        }
+        if (lane == 0) p.a_org[a0] = mk4(ol_peer | (or_peer << 16), (u32)ol_ctr, (u32)or_ctr, 0);
+        if (mid && lane == 1)
+            p.a_org[atom_index(c, cur_peer, cur_ctr + off)] = mk4(cur_peer | (og.x & 0xFFFF0000u), (u32)(cur_ctr + off - 1), og.z, 0);
         if (lane < len) p.atom_leaf[a0 + lane] = tgt_leaf;
         for (i32 i = 32 + lane; i < len; i += 32) p.atom_leaf[a0 + i] = tgt_leaf;
         if (have_path && tgt_leaf == leaf) {   // every level of the recorded path at once
@@ -949,6 +942,9 @@ __device__ __noinline__ void emit_output(const SeqPools& p, const SeqTables& t, 
     __syncwarp();
 }
 
+// (measured and dropped: single-peer documents skipping the origin records -- nothing is ever concurrent in them, the
+//  records are never read -- made C2's integration 4 % SLOWER, 74.3 against 71.3 ms (profiles/r2z_bench_C2*.json against
+//  r2j_bench_C2.json): the flag costs a register in every helper of a kernel that sits at its 64-register budget)
 // one warp per document, LB_SEQ_WARPS documents per CTA
 #ifndef LB_SEQ_MINB
 #define LB_SEQ_MINB 8         // 8 CTAs x 4 warps = 32 resident documents per SM (64 registers/thread)
@@ -976,7 +972,6 @@ k_seq_integrate(DocInfo* __restrict__ docs, u32 n_docs, const __grid_constant__ 
     c.atom0 = di.atom0;
     c.P = P;
     c.lane = lane;
-    c.solo = P == 1;
     SeqSmem* sm = c.sm;
     sm->abase[lane] = (u32)lane < P ? c.dpeer[lane].atom_base : 0;
     if (lane == 0) sm->err = 0;
