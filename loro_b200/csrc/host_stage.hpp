@@ -6,6 +6,9 @@
 // allocation (seconds for several GB) is ever made.
 #pragma once
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -103,19 +106,69 @@ inline HostCache& host_cache() {
     return c;
 }
 
+// The gather / scatter workers are persistent: a 32 MB slot is handed to them every few milliseconds (540 slots per step of
+// config C3), and starting 16 threads per slot put ~0.4 ms of thread creation on the critical path of every slot.
+// The pool is process-wide and lives as long as the process (detached workers; callers from several threads -- one ring
+// per direction, two imports in flight -- share it through one queue).  Workers are created by the first caller, after
+// lb_numa_bind if the host called it, so they inherit its CPU affinity.
+struct WorkerPool {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    unsigned n = 0;
+    void ensure(unsigned want) {
+        std::lock_guard<std::mutex> g(mu);
+        for (; n < want; n++)
+            std::thread([this] {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this] { return !q.empty(); });
+                        job = std::move(q.front());
+                        q.pop_front();
+                    }
+                    job();
+                }
+            }).detach();
+    }
+    void submit(std::function<void()> job) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            q.push_back(std::move(job));
+        }
+        cv.notify_one();
+    }
+};
+inline WorkerPool& pool() {
+    static WorkerPool* p = new WorkerPool();   // never destroyed: its detached workers may outlive static destructors
+    return *p;
+}
+
 template <class F>
 inline void parallel_ranges(size_t lo, size_t hi, F&& f) {
     unsigned T = n_workers();
     size_t n = hi - lo;
     if (n < std::min<size_t>(1u << 20, slot_bytes() / 2) || T == 1) { f(lo, hi); return; }
-    std::vector<std::thread> th;
+    WorkerPool& wp = pool();
+    wp.ensure(T);
     size_t per = (n + T - 1) / T;
-    for (unsigned t = 0; t < T; t++) {
+    struct Done { std::mutex mu; std::condition_variable cv; unsigned left; } done;
+    unsigned parts = 0;
+    for (unsigned t = 0; t < T; t++)
+        if (lo + t * per < hi) parts++;
+    done.left = parts;
+    for (unsigned t = 1; t < parts; t++) {
         size_t a = lo + t * per, b = std::min(hi, a + per);
-        if (a >= b) break;
-        th.emplace_back([&f, a, b] { f(a, b); });
+        wp.submit([&f, &done, a, b] {
+            f(a, b);
+            std::lock_guard<std::mutex> g(done.mu);
+            if (--done.left == 0) done.cv.notify_one();
+        });
     }
-    for (auto& x : th) x.join();
+    f(lo, std::min(hi, lo + per));            // the caller takes the first part itself
+    std::unique_lock<std::mutex> lk(done.mu);
+    if (--done.left != 0) done.cv.wait(lk, [&done] { return done.left == 0; });
 }
 
 // Copy bytes [lo,hi) of the virtual stream "blob i at offs[i], zero padded up to offs[i+1]" into dst (dst[0] = lo).
