@@ -42,3 +42,20 @@ def test_sass_is_sm100a(lib):
     import loro_b200
     out = subprocess.run(["cuobjdump", "-lelf", loro_b200.library_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
+
+
+def test_plain_c_caller_compiles_links_and_fails_loudly_without_a_device(lib, tmp_path):
+    """include/loro_b200.h is plain C (no torch / C++ types in the signatures): examples/c/import_and_docset.c builds
+    with -std=c99 -Wall -Wextra -Werror, links against the library and, without a CUDA device, gets LB_ERR_NO_DEVICE."""
+    import subprocess
+    import loro_b200
+    exe = str(tmp_path / "demo")
+    libdir = os.path.dirname(loro_b200.library_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c", "import_and_docset.c"), "-L" + libdir, "-lloro_b200", "-o", exe])
+    import torch
+    if torch.cuda.is_available():
+        return
+    out = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "gv1_update.bin")], capture_output=True, text=True,
+                         env=dict(os.environ, LD_LIBRARY_PATH=libdir))
+    assert out.returncode == 1 and "no CUDA device" in out.stderr, (out.returncode, out.stderr)
