@@ -468,3 +468,30 @@ def test_config_c4_full_size_against_committed_oracle_digests(golden_dir, which)
     assert {str(k): v for k, v in b.oplog_vv(0).items()} == want["vv"]
     ex = b.export_updates(0)
     assert len(ex) == want["export_len"] and xxh(ex) == want["export_xxh32"]
+
+
+def test_plain_c_caller_runs_against_the_library(tmp_path, golden_dir):
+    """examples/c/import_and_docset.c (plain C99 against include/loro_b200.h): import_batch of two updates of one document,
+    then the same updates one call at a time into a docset document"""
+    import subprocess
+    import loro_b200
+    exe = str(tmp_path / "demo")
+    root = os.path.dirname(HERE)
+    libdir = os.path.dirname(loro_b200.library_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "c", "import_and_docset.c"), "-L" + libdir, "-lloro_b200", "-o", exe])
+    a, b = OracleDoc(1), OracleDoc(2)
+    a.text_insert(a.get_text("text"), 0, "hello")
+    a.commit()
+    u1 = a.export_updates()
+    workloads.merge(b, a)
+    b.text_insert(b.get_text("text"), 5, " world")
+    b.commit()
+    u2 = b.export_updates(a.oplog_vv())
+    p1, p2 = str(tmp_path / "u1.bin"), str(tmp_path / "u2.bin")
+    open(p1, "wb").write(u1)
+    open(p2, "wb").write(u2)
+    out = subprocess.run([exe, p1, p2], capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=libdir), timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.count('"text":"hello world"') == 2, out.stdout      # the batch import and the second docset import
+    assert '"text":"hello"' in out.stdout and "docset: 1 document(s)" in out.stdout
