@@ -3,6 +3,7 @@ with the oracle in the GPU-less container.  The same checks run on the real CUDA
 The emulated library is test infrastructure only -- loro_b200 never loads it by default."""
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -413,3 +414,27 @@ def test_host_batch_split_into_overlapping_sub_batches():
     a, b = many.counters(), one.counters()
     assert a["atom_ops"] == b["atom_ops"] and a["state_hash"] == b["state_hash"] and a["docs_ok"] == 11
     assert api.auto_split(blobs) == 1
+
+
+@pytest.mark.parametrize("mode", ["rows", "warp", "group"])
+def test_alternative_decoders_stay_parity_green(mode):
+    """The decoders that are not the default (LB_DECODE=rows: all cursors at once; warp / group: TMA-staged, warp-
+    cooperative, measured slower -- DESIGN.md section 4) are kept buildable and correct: same JSON, status and exported
+    bytes as the oracle on mixed, tree and large-insert documents."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from tests import workloads\n"
+        "from tests.engine_checks import check_batch_against_oracle\n"
+        "from tests.export_checks import check_export_against_oracle\n"
+        "import loro_b200\n"
+        "blobs = [workloads.make_doc_history(8100 + i, n_sites=3, n_ops=180)[0] for i in range(5)]\n"
+        "blobs.append(workloads.make_tree_history(11, n_sites=3, n_base=25, n_ops=70)[0])\n"
+        "b = check_batch_against_oracle(blobs, lib_path=%r)\n"
+        "t = b.timings()\n"
+        "check_export_against_oracle(blobs[:3], lib_path=%r)\n"
+        "print('ok', t['decode_fast_blocks'], t['decode_lane_blocks'], t['decode_unstaged_blocks'])\n"
+    ) % (os.path.dirname(HERE), EMU, EMU)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LB_DECODE=mode), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    fast = int(out.stdout.split()[1])
+    assert mode == "rows" or fast > 0, out.stdout     # the staged decoders really took their fast path
