@@ -117,6 +117,14 @@ inline bool rle_push(std::vector<Op>& ops, const Op& op) {
     ops.push_back(op);
     return false;
 }
+inline bool rle_push(std::vector<Op>& ops, Op&& op) {
+    if (!ops.empty() && op_mergable(ops.back(), op)) {
+        op_merge(ops.back(), op);
+        return true;
+    }
+    ops.push_back(std::move(op));
+    return false;
+}
 inline size_t utf8_byte_index(const std::string& s, size_t chars) {
     size_t i = 0, c = 0;
     while (i < s.size() && c < chars) {
@@ -995,9 +1003,11 @@ struct Doc : ArenaCtx {
                 if (raw.empty()) continue;
                 Counter start = vv_get(raw[0].id.peer);  // change_store.rs:244-267
                 for (auto& c0 : raw) {
-                    Change c = c0;  // re-push ops through the RleVec merge (block_encode.rs:651)
-                    c.ops.clear();
-                    for (auto& op : c0.ops) rle_push(c.ops, op);
+                    Change c = std::move(c0);  // re-push ops through the RleVec merge (block_encode.rs:651)
+                    std::vector<Op> src;
+                    src.swap(c.ops);
+                    c.ops.reserve(src.size());
+                    for (auto& op : src) rle_push(c.ops, std::move(op));
                     if (c.id.counter >= start)
                         changes.push_back(std::move(c));
                     else if (c.ctr_end() > start)
@@ -1016,14 +1026,14 @@ struct Doc : ArenaCtx {
             if (change.ctr_end() <= vv_get(change.id.peer)) continue;
             Lamport l;
             if (!lamport_from_deps(change.deps, &l)) {
-                pend.push_back(change);
+                pend.push_back(std::move(change));
                 continue;
             }
             change.lamport = l;
-            apply_remote(change, &st);
+            apply_remote(std::move(change), &st);
         }
         for (auto& c : pend) range_extend(st.pending, c.id.peer, c.id.counter, c.ctr_end());
-        for (auto& c : pend) pending.push_back(c);
+        for (auto& c : pend) pending.push_back(std::move(c));
         try_apply_pending(&st);
         if (status) *status = st;
         return 0;
@@ -1055,10 +1065,10 @@ struct Doc : ArenaCtx {
                 bool self_gap = c.id.counter > vv_get(c.id.peer);
                 if (!self_gap && lamport_from_deps(c.deps, &l)) {
                     c.lamport = l;
-                    apply_remote(c, st);
+                    apply_remote(std::move(c), st);
                     progress = true;
                 } else
-                    rest.push_back(c);
+                    rest.push_back(std::move(c));
             }
             pending.swap(rest);
         }
